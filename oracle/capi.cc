@@ -1,0 +1,514 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see mj.h).
+// C ABI over the oracle for ctypes (tests/, smoke(), bench.py cpu_baseline / --impl reference).
+#include "board.h"
+#include "sp.h"
+
+#include <atomic>
+#include <chrono>
+#include <thread>
+
+using namespace orc;
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::exception& e) { g_err = e.what(); return -1; }
+}  // namespace
+
+extern "C" {
+
+// flat mirror of orc::Event for ctypes
+struct orc_event {
+    uint8_t type, actor, target, pai, tsumogiri;
+    uint8_t consumed[4];
+    uint8_t bakaze, kyoku, honba, kyotaku, oya;
+    int32_t scores[4];
+    uint8_t tehais[4][13];
+    uint8_t has_deltas;
+    int32_t deltas[4];
+    uint8_t ura_markers[5];
+    uint8_t n_ura;
+};
+
+static Event from_c(const orc_event& c) {
+    Event e;
+    e.type = c.type; e.actor = c.actor; e.target = c.target; e.pai = c.pai; e.tsumogiri = c.tsumogiri != 0;
+    memcpy(e.consumed, c.consumed, 4);
+    e.bakaze = c.bakaze; e.kyoku = c.kyoku; e.honba = c.honba; e.kyotaku = c.kyotaku; e.oya = c.oya;
+    memcpy(e.scores, c.scores, sizeof e.scores);
+    memcpy(e.tehais, c.tehais, sizeof e.tehais);
+    e.has_deltas = c.has_deltas != 0;
+    memcpy(e.deltas, c.deltas, sizeof e.deltas);
+    memcpy(e.ura_markers, c.ura_markers, 5);
+    e.n_ura = c.n_ura;
+    return e;
+}
+static orc_event to_c(const Event& e) {
+    orc_event c;
+    memset(&c, 0, sizeof c);
+    c.type = e.type; c.actor = e.actor; c.target = e.target; c.pai = e.pai; c.tsumogiri = e.tsumogiri;
+    memcpy(c.consumed, e.consumed, 4);
+    c.bakaze = e.bakaze; c.kyoku = e.kyoku; c.honba = e.honba; c.kyotaku = e.kyotaku; c.oya = e.oya;
+    memcpy(c.scores, e.scores, sizeof c.scores);
+    memcpy(c.tehais, e.tehais, sizeof c.tehais);
+    c.has_deltas = e.has_deltas;
+    memcpy(c.deltas, e.deltas, sizeof c.deltas);
+    memcpy(c.ura_markers, e.ura_markers, 5);
+    c.n_ura = (uint8_t)e.n_ura;
+    return c;
+}
+
+const char* orc_last_error() { return g_err.c_str(); }
+
+int orc_init(const char* data_dir) {
+    try { tables_init(data_dir); return 0; } catch (const std::exception& e) { return fail(e); }
+}
+
+// ---------------- algo ----------------
+int orc_shanten(const uint8_t* tiles, const uint8_t* len_div3, int8_t* out, int n, int kind) {
+    try {
+        for (int i = 0; i < n; i++) {
+            const u8* t = tiles + (size_t)i * 34;
+            out[i] = kind == 0 ? shanten_all(t, len_div3[i]) : kind == 1 ? shanten_normal(t, len_div3[i])
+                     : kind == 2 ? shanten_chitoi(t) : shanten_kokushi(t);
+        }
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// one agari query; layout shared with include/mjx.h mjx_agari_in / mjx_agari_out
+struct orc_agari_in {
+    uint8_t tehai[34];
+    uint8_t chis[4], pons[4], minkans[4], ankans[4];
+    uint8_t n_chis, n_pons, n_minkans, n_ankans;
+    uint8_t bakaze, jikaze, winning_tile, is_ron;
+    uint8_t additional_hans, doras;  // for agari(); ignored by search_yakus
+    uint8_t is_oya, pad;
+};
+struct orc_agari_out {
+    uint8_t kind;  // 0 none, 1 normal, 2 yakuman
+    uint8_t fu, han, yakuman;
+    int32_t ron, tsumo_ko, tsumo_oya;  // Point for is_oya (0 if none / panic combo -> -1)
+};
+
+// mode 0: search_yakus, 1: agari(additional_hans, doras), 2: has_yaku (kind=1 if true)
+int orc_agari(const orc_agari_in* in, orc_agari_out* out, int n, int mode) {
+    try {
+        for (int i = 0; i < n; i++) {
+            const orc_agari_in& q = in[i];
+            AgariCalc c;
+            c.tehai = q.tehai;
+            c.chis = q.chis; c.n_chis = q.n_chis;
+            c.pons = q.pons; c.n_pons = q.n_pons;
+            c.minkans = q.minkans; c.n_minkans = q.n_minkans;
+            c.ankans = q.ankans; c.n_ankans = q.n_ankans;
+            c.is_menzen = q.n_chis == 0 && q.n_pons == 0 && q.n_minkans == 0;
+            c.bakaze = q.bakaze; c.jikaze = q.jikaze; c.winning_tile = q.winning_tile; c.is_ron = q.is_ron;
+            orc_agari_out& o = out[i];
+            memset(&o, 0, sizeof o);
+            if (mode == 2) { o.kind = c.has_yaku() ? 1 : 0; continue; }
+            Agari a = mode == 0 ? c.search_yakus() : c.agari(q.additional_hans, q.doras);
+            if (!a.valid) continue;
+            o.kind = a.is_yakuman ? 2 : 1;
+            o.fu = a.fu; o.han = a.han; o.yakuman = a.yakuman;
+            try {
+                Point p = a.point(q.is_oya);
+                o.ron = p.ron; o.tsumo_ko = p.tsumo_ko; o.tsumo_oya = p.tsumo_oya;
+            } catch (const OrcError&) {
+                o.ron = o.tsumo_ko = o.tsumo_oya = -1;
+            }
+        }
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+int orc_point(int is_oya, int fu, int han, int32_t* out3) {
+    try {
+        Point p = point_calc(is_oya, (u8)fu, (u8)han);
+        out3[0] = p.ron; out3[1] = p.tsumo_ko; out3[2] = p.tsumo_oya;
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+int orc_check_ankan_after_riichi(const uint8_t* tehai, int len_div3, int tile, int strict) {
+    try { return check_ankan_after_riichi(tehai, (u8)len_div3, (u8)tile, strict) ? 1 : 0; }
+    catch (const std::exception& e) { return fail(e); }
+}
+
+void orc_rankings(const int32_t* scores, uint8_t* player_by_rank, uint8_t* rank_by_player) {
+    rankings(scores, player_by_rank, rank_by_player);
+}
+
+uint32_t orc_agari_key(const uint8_t* tiles, uint8_t* tile14) { return get_tile14_and_key(tiles, tile14); }
+int orc_agari_lookup(uint32_t key, uint32_t* divs4) { return agari_table_lookup(key, divs4); }
+
+// ---------------- wall ----------------
+void orc_make_wall(uint64_t nonce, uint64_t key, int kyoku, int honba, int shuffle_kind, uint8_t* seq136) {
+    make_wall(nonce, key, (u8)kyoku, (u8)honba, shuffle_kind, seq136);
+}
+void orc_sha3_256(const uint8_t* data, int len, uint8_t* out32) { sha3_256(data, (size_t)len, out32); }
+void orc_chacha12(const uint8_t* seed32, uint32_t* out, int n) {
+    ChaCha12 r(seed32);
+    for (int i = 0; i < n; i++) out[i] = r.next_u32();
+}
+
+// ---------------- PlayerState ----------------
+void* orc_ps_new(int player_id) { return new PlayerState((u8)player_id); }
+void orc_ps_free(void* p) { delete static_cast<PlayerState*>(p); }
+void* orc_ps_clone(void* p) { return new PlayerState(*static_cast<PlayerState*>(p)); }
+
+static uint32_t pack_cans(const ActionCandidate& c) {
+    uint32_t v = 0;
+    v |= (uint32_t)c.can_discard << 0; v |= (uint32_t)c.can_chi_low << 1; v |= (uint32_t)c.can_chi_mid << 2;
+    v |= (uint32_t)c.can_chi_high << 3; v |= (uint32_t)c.can_pon << 4; v |= (uint32_t)c.can_daiminkan << 5;
+    v |= (uint32_t)c.can_kakan << 6; v |= (uint32_t)c.can_ankan << 7; v |= (uint32_t)c.can_riichi << 8;
+    v |= (uint32_t)c.can_tsumo_agari << 9; v |= (uint32_t)c.can_ron_agari << 10; v |= (uint32_t)c.can_ryukyoku << 11;
+    v |= (uint32_t)c.target_actor << 16;
+    return v;
+}
+
+// returns packed cans (>=0) or -1
+int64_t orc_ps_update(void* p, const orc_event* ev) {
+    try { return pack_cans(static_cast<PlayerState*>(p)->update(from_c(*ev))); }
+    catch (const std::exception& e) { return fail(e); }
+}
+int orc_ps_validate_reaction(void* p, const orc_event* ev) {
+    try { static_cast<PlayerState*>(p)->validate_reaction(from_c(*ev)); return 0; }
+    catch (const std::exception& e) { return fail(e); }
+}
+
+// field snapshot used by tests and by GPU-vs-oracle state diffs
+struct orc_ps_view {
+    uint8_t tehai[34], waits[34], dora_factor[34], tiles_seen[34], keep_shanten_discards[34],
+        next_shanten_discards[34], forbidden_tiles[34], discarded_tiles[34];
+    uint8_t akas_seen[3], akas_in_hand[3];
+    uint8_t bakaze, jikaze, kyoku, honba, kyotaku, rank, oya, is_all_last;
+    int32_t scores[4];
+    uint8_t n_dora_indicators, dora_indicators[5];
+    uint8_t riichi_declared[4], riichi_accepted[4];
+    uint8_t at_turn, tiles_left;
+    int8_t shanten, real_time_shanten;
+    uint8_t has_last_self_tsumo, last_self_tsumo, has_last_kawa_tile, last_kawa_tile;
+    uint32_t cans;
+    uint8_t n_ankan_candidates, ankan_candidates[3], n_kakan_candidates, kakan_candidates[3];
+    uint8_t chankan_chance, can_w_riichi, is_w_riichi, at_rinshan, at_ippatsu, at_furiten,
+        to_mark_same_cycle_furiten, kans_on_board, is_menzen;
+    uint8_t n_chis, chis[4], n_pons, pons[4], n_minkans, minkans[4], n_ankans, ankans[4];
+    uint8_t doras_owned[4], doras_seen, tehai_len_div3, has_next_shanten_discard;
+    uint8_t kawa_len[4];
+};
+
+void orc_ps_view_get(void* p, orc_ps_view* v) {
+    const PlayerState& s = *static_cast<PlayerState*>(p);
+    memset(v, 0, sizeof *v);
+    for (int i = 0; i < 34; i++) {
+        v->tehai[i] = s.tehai[i]; v->waits[i] = s.waits[i]; v->dora_factor[i] = s.dora_factor[i];
+        v->tiles_seen[i] = s.tiles_seen[i]; v->keep_shanten_discards[i] = s.keep_shanten_discards[i];
+        v->next_shanten_discards[i] = s.next_shanten_discards[i]; v->forbidden_tiles[i] = s.forbidden_tiles[i];
+        v->discarded_tiles[i] = s.discarded_tiles[i];
+    }
+    for (int i = 0; i < 3; i++) { v->akas_seen[i] = s.akas_seen[i]; v->akas_in_hand[i] = s.akas_in_hand[i]; }
+    v->bakaze = s.bakaze; v->jikaze = s.jikaze; v->kyoku = s.kyoku; v->honba = s.honba; v->kyotaku = s.kyotaku;
+    v->rank = s.rank; v->oya = s.oya; v->is_all_last = s.is_all_last;
+    for (int i = 0; i < 4; i++) v->scores[i] = s.scores[i];
+    v->n_dora_indicators = (u8)s.dora_indicators.size();
+    for (size_t i = 0; i < s.dora_indicators.size() && i < 5; i++) v->dora_indicators[i] = s.dora_indicators[i];
+    for (int i = 0; i < 4; i++) { v->riichi_declared[i] = s.riichi_declared[i]; v->riichi_accepted[i] = s.riichi_accepted[i]; }
+    v->at_turn = s.at_turn; v->tiles_left = s.tiles_left; v->shanten = s.shanten;
+    v->real_time_shanten = s.real_time_shanten();
+    v->has_last_self_tsumo = s.has_last_self_tsumo; v->last_self_tsumo = s.last_self_tsumo;
+    v->has_last_kawa_tile = s.has_last_kawa_tile; v->last_kawa_tile = s.last_kawa_tile;
+    v->cans = pack_cans(s.last_cans);
+    v->n_ankan_candidates = (u8)s.ankan_candidates.size();
+    for (size_t i = 0; i < s.ankan_candidates.size() && i < 3; i++) v->ankan_candidates[i] = s.ankan_candidates[i];
+    v->n_kakan_candidates = (u8)s.kakan_candidates.size();
+    for (size_t i = 0; i < s.kakan_candidates.size() && i < 3; i++) v->kakan_candidates[i] = s.kakan_candidates[i];
+    v->chankan_chance = s.chankan_chance; v->can_w_riichi = s.can_w_riichi; v->is_w_riichi = s.is_w_riichi;
+    v->at_rinshan = s.at_rinshan; v->at_ippatsu = s.at_ippatsu; v->at_furiten = s.at_furiten;
+    v->to_mark_same_cycle_furiten = s.to_mark_same_cycle_furiten; v->kans_on_board = s.kans_on_board;
+    v->is_menzen = s.is_menzen;
+    auto cp = [](const std::vector<u8>& src, uint8_t* n, uint8_t* dst) {
+        *n = (u8)src.size();
+        for (size_t i = 0; i < src.size() && i < 4; i++) dst[i] = src[i];
+    };
+    cp(s.chis, &v->n_chis, v->chis); cp(s.pons, &v->n_pons, v->pons);
+    cp(s.minkans, &v->n_minkans, v->minkans); cp(s.ankans, &v->n_ankans, v->ankans);
+    for (int i = 0; i < 4; i++) { v->doras_owned[i] = s.doras_owned[i]; v->kawa_len[i] = (u8)s.kawa[i].size(); }
+    v->doras_seen = s.doras_seen; v->tehai_len_div3 = s.tehai_len_div3;
+    v->has_next_shanten_discard = s.has_next_shanten_discard;
+}
+
+// direct field pokes for the unit tests that construct states by hand (state/test.rs:70-220)
+void orc_ps_set_tehai(void* p, const uint8_t* tehai34, int len_div3) {
+    PlayerState& s = *static_cast<PlayerState*>(p);
+    memcpy(s.tehai, tehai34, 34);
+    s.tehai_len_div3 = (u8)len_div3;
+}
+int orc_ps_update_waits_and_furiten(void* p) {
+    try {
+        PlayerState& s = *static_cast<PlayerState*>(p);
+        s.update_shanten();
+        s.update_waits_and_furiten();
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+uint32_t orc_ps_set_can_chi_from_tile(void* p, int tile) {
+    PlayerState& s = *static_cast<PlayerState*>(p);
+    s.set_can_chi_from_tile((u8)tile);
+    return pack_cans(s.last_cans);
+}
+int orc_ps_get_rank(int player_id, const int32_t* scores_rel) {
+    PlayerState s((u8)player_id);
+    return s.get_rank(scores_rel);
+}
+
+int orc_ps_agari_points(void* p, int is_ron, const uint8_t* ura, int n_ura, int32_t* out3) {
+    try {
+        Point pt = static_cast<PlayerState*>(p)->agari_points(is_ron != 0, ura, n_ura);
+        out3[0] = pt.ron; out3[1] = pt.tsumo_ko; out3[2] = pt.tsumo_oya;
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+int orc_ps_rule_based_agari(void* p) {
+    try { return static_cast<PlayerState*>(p)->rule_based_agari() ? 1 : 0; }
+    catch (const std::exception& e) { return fail(e); }
+}
+int orc_ps_rule_based_agari_slow(void* p, int is_ron, int target_rel) {
+    try { return static_cast<PlayerState*>(p)->rule_based_agari_slow(is_ron != 0, target_rel) ? 1 : 0; }
+    catch (const std::exception& e) { return fail(e); }
+}
+int orc_ps_discard_candidates(void* p, int kind, uint8_t* out37) {
+    try {
+        bool b[37];
+        PlayerState& s = *static_cast<PlayerState*>(p);
+        if (kind == 0) s.discard_candidates_aka(b);
+        else s.discard_candidates_with_unconditional_tenpai_aka(b);
+        for (int i = 0; i < 37; i++) out37[i] = b[i];
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+int orc_obs_rows(int version) { try { return obs_rows(version); } catch (const std::exception& e) { return fail(e); } }
+int orc_ps_encode_obs(void* p, int version, int at_kan_select, float* obs, uint8_t* mask46, int sp_mode) {
+    try { static_cast<PlayerState*>(p)->encode_obs(version, at_kan_select != 0, obs, mask46, sp_mode); return 0; }
+    catch (const std::exception& e) { return fail(e); }
+}
+int orc_ps_legal_mask(void* p, int at_kan_select, uint8_t* mask46) {
+    try { legal_mask(*static_cast<PlayerState*>(p), at_kan_select != 0, mask46); return 0; }
+    catch (const std::exception& e) { return fail(e); }
+}
+
+// ---------------- SP (algo/sp) ----------------
+struct orc_sp_in {
+    uint8_t tehai[34], akas_in_hand[3], tiles_seen[34], akas_seen[3];
+    uint8_t tehai_len_div3, is_menzen, bakaze, jikaze, num_doras_in_fuuro;
+    uint8_t n_dora_indicators, dora_indicators[5];
+    uint8_t calc_double_riichi, calc_haitei, prefer_riichi, sort_result, maximize_win_prob, calc_tegawari,
+        calc_shanten_down;
+    uint8_t chis[4], pons[4], minkans[4], ankans[4], n_chis, n_pons, n_minkans, n_ankans;
+    uint8_t can_discard, tsumos_left;
+    int8_t cur_shanten;
+};
+struct orc_sp_cand {
+    uint8_t tile, shanten_down, num_required_tiles, n_required, n_turns;
+    uint8_t required_tile[34], required_count[34];
+    float tenpai_probs[17], win_probs[17], exp_values[17];
+};
+int orc_sp_calc(const orc_sp_in* q, orc_sp_cand* out, int max_out) {
+    try {
+        SpCalculator sp;
+        sp.tehai_len_div3 = q->tehai_len_div3; sp.is_menzen = q->is_menzen; sp.bakaze = q->bakaze; sp.jikaze = q->jikaze;
+        sp.num_doras_in_fuuro = q->num_doras_in_fuuro;
+        sp.dora_indicators = q->dora_indicators; sp.n_dora_indicators = q->n_dora_indicators;
+        sp.calc_double_riichi = q->calc_double_riichi; sp.calc_haitei = q->calc_haitei; sp.prefer_riichi = q->prefer_riichi;
+        sp.sort_result = q->sort_result; sp.maximize_win_prob = q->maximize_win_prob; sp.calc_tegawari = q->calc_tegawari;
+        sp.calc_shanten_down = q->calc_shanten_down;
+        sp.chis = q->chis; sp.n_chis = q->n_chis; sp.pons = q->pons; sp.n_pons = q->n_pons;
+        sp.minkans = q->minkans; sp.n_minkans = q->n_minkans; sp.ankans = q->ankans; sp.n_ankans = q->n_ankans;
+        SpInitState init;
+        memcpy(init.tehai, q->tehai, 34);
+        memcpy(init.tiles_seen, q->tiles_seen, 34);
+        for (int i = 0; i < 3; i++) { init.akas_in_hand[i] = q->akas_in_hand[i]; init.akas_seen[i] = q->akas_seen[i]; }
+        auto cands = sp.calc(init, q->can_discard, q->tsumos_left, q->cur_shanten);
+        int n = 0;
+        for (auto& c : cands) {
+            if (n >= max_out) break;
+            orc_sp_cand& o = out[n++];
+            memset(&o, 0, sizeof o);
+            o.tile = c.tile; o.shanten_down = c.shanten_down; o.num_required_tiles = c.num_required_tiles;
+            o.n_required = (u8)c.required_tiles.size();
+            for (size_t i = 0; i < c.required_tiles.size(); i++) {
+                o.required_tile[i] = c.required_tiles[i].tile; o.required_count[i] = c.required_tiles[i].count;
+            }
+            o.n_turns = (u8)c.tenpai_probs.size();
+            for (size_t i = 0; i < c.tenpai_probs.size(); i++) {
+                o.tenpai_probs[i] = c.tenpai_probs[i]; o.win_probs[i] = c.win_probs[i]; o.exp_values[i] = c.exp_values[i];
+            }
+        }
+        return n;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// ---------------- manual game driving (golden-log replay) ----------------
+struct OrcGame {
+    Game g;
+    std::vector<u8> walls;  // optional injected walls, keyed sequentially
+};
+
+void* orc_game_new(uint64_t nonce, uint64_t key, int shuffle_kind, int table) {
+    OrcGame* og = new OrcGame();
+    og->g.seed_nonce = nonce; og->g.seed_key = key; og->g.shuffle_kind = shuffle_kind; og->g.table = table;
+    return og;
+}
+void orc_game_free(void* p) { delete static_cast<OrcGame*>(p); }
+// returns 1 if ended, 0 in game, -1 error
+int orc_game_poll(void* p) {
+    try { Game& g = static_cast<OrcGame*>(p)->g; g.poll(); return g.ended ? 1 : 0; }
+    catch (const std::exception& e) { return fail(e); }
+}
+void* orc_game_state(void* p, int seat) {
+    Game& g = static_cast<OrcGame*>(p)->g;
+    return g.board ? &g.board->player_states[seat] : nullptr;
+}
+void orc_game_set_reaction(void* p, int seat, const orc_event* ev) {
+    static_cast<OrcGame*>(p)->g.last_reactions[seat] = from_c(*ev);
+}
+// decode an action id for `seat` the way MortalBatchAgent does and stage it as the reaction
+int orc_game_set_action(void* p, int seat, int action, int kan_action) {
+    try {
+        Game& g = static_cast<OrcGame*>(p)->g;
+        g.last_reactions[seat] = decode_action(g.board->player_states[seat], (u8)seat, action, kan_action);
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+void orc_game_advance_step(void* p) { static_cast<OrcGame*>(p)->g.step_idx++; }
+// finalises scores once the game has ended (game.rs:180-184)
+int orc_game_finish(void* p, int32_t* scores4) {
+    try {
+        Game& g = static_cast<OrcGame*>(p)->g;
+        AgentConfig cfg[4]; PolicyFn pol[4];
+        if (!g.ended) throw OrcError("game not ended");
+        g.commit(cfg, pol, nullptr);
+        for (int i = 0; i < 4; i++) scores4[i] = g.scores[i];
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+void orc_game_info(void* p, int32_t* out /* kyoku, honba, kyotaku, scores[4], ended, n_kyoku_logs */) {
+    Game& g = static_cast<OrcGame*>(p)->g;
+    out[0] = g.kyoku; out[1] = g.honba; out[2] = g.kyotaku;
+    for (int i = 0; i < 4; i++) out[3 + i] = g.scores[i];
+    out[7] = g.ended; out[8] = (int32_t)g.game_log.size();
+}
+// copies the event log: finished kyokus followed by the running kyoku's log
+int orc_game_log(void* p, orc_event* out, int max_out) {
+    Game& g = static_cast<OrcGame*>(p)->g;
+    int n = 0;
+    for (auto& k : g.game_log)
+        for (auto& e : k) { if (n < max_out) out[n] = to_c(e); n++; }
+    if (g.board && g.kyoku_started)
+        for (auto& e : g.board->log) { if (n < max_out) out[n] = to_c(e); n++; }
+    return n;
+}
+
+// ---------------- batch self-play with built-in policies ----------------
+// Per-decision trace record: [table, step_idx, seat, action, kan_action, mask_lo, mask_hi]
+struct orc_run_cfg {
+    int32_t n_tables;
+    int32_t shuffle_kind;
+    int32_t policy_kind;        // test_policy kind for all seats
+    int32_t enable_quick_eval;
+    int32_t enable_agari_guard;
+    int32_t encode_obs;         // 0 none; else obs version to encode for every policy row (timed work)
+    int32_t sp_mode;
+    int32_t n_threads;
+    int64_t max_steps_per_table;  // stop early after this many table-steps (0 = run to the end)
+};
+struct orc_run_out {
+    int64_t table_steps;   // sum over tables of decision cycles (game.rs:304 `actions`)
+    int64_t obs_rows;      // rows handed to the policy (incl. kan-select rows)
+    double seconds;
+};
+
+static void run_range(const orc_run_cfg& cfg, const uint64_t* nonces, const uint64_t* keys, const int32_t* table_ids,
+                      int lo, int hi, int32_t* scores, uint8_t* ranks, int32_t* steps, int64_t* trace, int64_t trace_cap,
+                      std::atomic<int64_t>* trace_len, std::atomic<int64_t>* total_steps, std::atomic<int64_t>* total_rows,
+                      std::string* err) {
+    try {
+        std::vector<float> obs;
+        if (cfg.encode_obs) obs.resize((size_t)obs_rows(cfg.encode_obs) * 34);
+        for (int t = lo; t < hi; t++) {
+            Game g;
+            g.seed_nonce = nonces[t]; g.seed_key = keys[t]; g.shuffle_kind = cfg.shuffle_kind;
+            g.table = table_ids ? table_ids[t] : t;
+            AgentConfig ac;
+            ac.enable_quick_eval = cfg.enable_quick_eval != 0;
+            ac.enable_rule_based_agari_guard = cfg.enable_agari_guard != 0;
+            AgentConfig cfgs[4] = {ac, ac, ac, ac};
+            int64_t rows = 0;
+            PolicyFn pol = [&](const Scene& sc, const u8* mask, float*) {
+                rows++;
+                if (cfg.encode_obs) {
+                    u8 m2[46];
+                    sc.state->encode_obs(cfg.encode_obs, sc.is_kan_select, obs.data(), m2, cfg.sp_mode);
+                }
+                int a = test_policy(cfg.policy_kind, sc, g.seed_nonce, g.seed_key, mask);
+                if (trace) {
+                    int64_t at = trace_len->fetch_add(1);
+                    if (at < trace_cap) {
+                        u64 bits = 0;
+                        for (int i = 0; i < 46; i++) if (mask[i]) bits |= 1ull << i;
+                        int64_t* r = trace + at * 6;
+                        r[0] = sc.table; r[1] = (int64_t)sc.step_idx; r[2] = sc.seat; r[3] = a;
+                        r[4] = sc.is_kan_select; r[5] = (int64_t)bits;
+                    }
+                }
+                return a;
+            };
+            PolicyFn pols[4] = {pol, pol, pol, pol};
+            int64_t n_steps = 0;
+            for (;;) {
+                g.poll();
+                if (g.commit(cfgs, pols, nullptr)) break;
+                n_steps++;
+                if (cfg.max_steps_per_table > 0 && n_steps >= cfg.max_steps_per_table) break;
+            }
+            for (int i = 0; i < 4; i++) scores[t * 4 + i] = g.scores[i];
+            rankings(g.scores, nullptr, ranks + t * 4);
+            steps[t] = (int32_t)n_steps;
+            total_steps->fetch_add(n_steps);
+            total_rows->fetch_add(rows);
+        }
+    } catch (const std::exception& e) { *err = e.what(); }
+}
+
+int orc_run_batch(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t* keys, const int32_t* table_ids,
+                  int32_t* scores, uint8_t* ranks, int32_t* steps, int64_t* trace, int64_t trace_cap,
+                  int64_t* trace_len_out, orc_run_out* out) {
+    try {
+        int n = cfg->n_tables;
+        int nt = std::max(1, cfg->n_threads);
+        std::atomic<int64_t> tlen(0), tsteps(0), trows(0);
+        std::vector<std::string> errs(nt);
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; k++) {
+            int lo = (int)((int64_t)n * k / nt), hi = (int)((int64_t)n * (k + 1) / nt);
+            th.emplace_back(run_range, std::cref(*cfg), nonces, keys, table_ids, lo, hi, scores, ranks, steps, trace,
+                            trace_cap, &tlen, &tsteps, &trows, &errs[k]);
+        }
+        for (auto& t : th) t.join();
+        auto t1 = std::chrono::steady_clock::now();
+        for (auto& e : errs) if (!e.empty()) throw OrcError(e);
+        if (trace_len_out) *trace_len_out = tlen.load();
+        if (out) {
+            out->table_steps = tsteps.load();
+            out->obs_rows = trows.load();
+            out->seconds = std::chrono::duration<double>(t1 - t0).count();
+        }
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+uint64_t orc_policy_hash(uint64_t nonce, uint64_t key, uint64_t table, uint64_t step_idx, uint32_t seat, uint32_t kan) {
+    return policy_hash(nonce, key, table, step_idx, seat, kan);
+}
+
+}  // extern "C"
