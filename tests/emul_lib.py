@@ -1,0 +1,59 @@
+"""ctypes binding of tests/host_emul/libmjx_emul.so — TEST INFRASTRUCTURE (single-lane host build of the
+product's step sources; see tests/host_emul/emul.cc). Never used by mortal_b200/."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host_emul", "emul.cc")
+SO = os.path.join(ROOT, "tests", "host_emul", "libmjx_emul.so")
+CSRC = os.path.join(ROOT, "mortal_b200", "csrc")
+DATA_DIR = os.path.join(ROOT, "mortal_b200", "data")
+_lib = None
+
+
+def build():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-DMJX_HOST_EMUL", "-I" + CSRC,
+                               "-Wno-unknown-pragmas", "-o", SO, SRC])
+    return SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.emul_last_error.restype = C.c_char_p
+        L.emul_init.argtypes = [C.c_char_p]
+        L.emul_shanten.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.emul_make_wall.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.emul_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int64]
+        if L.emul_init(DATA_DIR.encode()) != 0:
+            raise RuntimeError(L.emul_last_error().decode())
+        _lib = L
+    return _lib
+
+
+def run(nonces, keys, *, shuffle_kind=0, quick_eval=True, policy_kind=1, trace_cap=0, max_cycles=0):
+    n = len(nonces)
+    nonces = np.ascontiguousarray(nonces, dtype=np.uint64)
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    scores = np.zeros((n, 4), dtype=np.int32)
+    ranks = np.zeros((n, 4), dtype=np.uint8)
+    steps = np.zeros(n, dtype=np.int32)
+    errs = np.zeros(n, dtype=np.int32)
+    trace = np.zeros((max(trace_cap, 1), 6), dtype=np.int64)
+    tl = C.c_int64(0)
+    rc = lib().emul_run(n, nonces.ctypes.data, keys.ctypes.data, shuffle_kind, int(quick_eval), policy_kind,
+                        scores.ctypes.data, ranks.ctypes.data, steps.ctypes.data, errs.ctypes.data,
+                        trace.ctypes.data if trace_cap else None, trace_cap, C.byref(tl), max_cycles)
+    assert rc == 0
+    out = dict(scores=scores, ranks=ranks, steps=steps, errs=errs, n_rows=tl.value)
+    if trace_cap:
+        assert tl.value <= trace_cap
+        out["trace"] = trace[: tl.value]
+    return out
