@@ -1,0 +1,107 @@
+/* mjx — C ABI of the B200-native batched riichi self-play environment (libmjx.so).
+ *
+ * This is the drop-in boundary for libriichi's self-play hot path. libriichi has no C ABI of its
+ * own (it is Rust re-exported through PyO3); each entry point below names the reference interface
+ * it stands in for (paths relative to /root/reference/libriichi/src). Plain pointers and sizes only;
+ * "dev" pointers are CUDA device pointers (e.g. torch.Tensor.data_ptr()), "host" pointers are
+ * ordinary host memory; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * Every function returns 0 on success or a negative mjx_status; mjx_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device every call fails with MJX_ERR_CUDA.
+ */
+#ifndef MJX_H
+#define MJX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum mjx_status { MJX_OK = 0, MJX_ERR_CUDA = -1, MJX_ERR_ARG = -2, MJX_ERR_TABLES = -3, MJX_ERR_STATE = -4 };
+
+#define MJX_ACTION_SPACE 46      /* consts.rs:7-15 */
+#define MJX_OBS_COLS 34
+#define MJX_MAX_ROWS_PER_TABLE 3 /* <=3 seats can act on one event; a kan-select pass adds a row to 1 */
+
+typedef struct mjx_env mjx_env;
+
+const char* mjx_last_error(void);
+
+/* lib.rs:139-140 (shanten::ensure_init / agari::ensure_init): load the three lookup tables from
+ * `data_dir` (shanten_suhai.bin, shanten_jihai.bin, agari.bin) into device memory of `device`. */
+int mjx_init(const char* data_dir, int device);
+
+/* consts.rs:20-28 obs_shape(version).0 ; returns <0 for an unsupported version. */
+int mjx_obs_rows(int version);
+
+/* ---- environment: arena/game.rs:230-316 BatchGame::run over n_tables Game objects -------------
+ * seeds: host arrays (nonce, key) per table = GameResult.seed (arena/one_vs_three.rs:140-142).
+ * shuffle_kind: 0 = rand 0.9.1 (Cargo.lock:1042), 1 = rand 0.8 (the shipped seeded log).
+ * enable_quick_eval: agent/mortal.rs:210-242. obs_version: consts.rs MAX_VERSION (4 supported). */
+int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces_host, const uint64_t* keys_host,
+                   int obs_version, int shuffle_kind, int enable_quick_eval);
+void mjx_env_destroy(mjx_env* env);
+
+/* One BatchGame::run loop iteration for every live table (game.rs:286-304): commit the actions
+ * chosen for the rows of the previous step (agent/mortal.rs:292-573 decode + board.rs:524-533
+ * validation), then poll every table to its next decision point (game.rs:59-178) and emit the
+ * decision rows + legal masks (agent/mortal.rs:200-290). `actions_dev` = int64 [row_cap], indexed
+ * by the previous step's row numbers (ignored on the first step; may be NULL then). */
+int mjx_env_step(mjx_env* env, const int64_t* actions_dev, void* stream);
+
+/* state/obs_repr.rs:776-790 encode_obs for every row of the current step:
+ * obs_dev = float32 [row_cap, rows(version), 34] (only the first n_rows rows are written). */
+int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream);
+
+/* Blocking read-backs (synchronise `stream` first). */
+int mjx_env_num_rows(mjx_env* env, void* stream, int* n_rows);          /* rows emitted by the last step */
+int mjx_env_num_live(mjx_env* env, void* stream, int* n_live);          /* tables still playing */
+int mjx_env_total_steps(mjx_env* env, void* stream, int64_t* steps);    /* game.rs:304 `actions` counter */
+
+/* Device views, valid for the lifetime of env (contents valid until the next mjx_env_step). */
+int mjx_env_row_cap(mjx_env* env);
+uint8_t* mjx_env_masks(mjx_env* env);      /* uint8/bool [row_cap, 46]  (obs_repr.rs mask) */
+int32_t* mjx_env_row_table(mjx_env* env);  /* int32 [row_cap] table index of each row */
+uint8_t* mjx_env_row_seat(mjx_env* env);   /* uint8 [row_cap] seat | (kan_select << 2) */
+int32_t* mjx_env_num_rows_dev(mjx_env* env); /* int32 [1] */
+
+/* arena/result.rs GameResult.scores + rankings.rs rank_by_player, plus per-table step counts and
+ * error codes (0 = clean; the reference would have raised/panicked otherwise). Host outputs. */
+int mjx_env_results(mjx_env* env, void* stream, int32_t* scores_host /*[n,4]*/, uint8_t* ranks_host /*[n,4]*/,
+                    int32_t* steps_host /*[n]*/, int32_t* err_host /*[n]*/, int32_t* done_host /*[n]*/);
+
+/* Counter-based TEST policy (not in the reference; shared definition with the oracle) writing
+ * int64 actions for the current rows. kind 0 uniform, 1 agari-first/shanten-greedy.
+ * trace_dev (optional): int64 [row_cap, 6] = table, step, seat, action, kan_select, mask_bits. */
+int mjx_env_policy_test(mjx_env* env, int kind, int64_t* actions_dev, int64_t* trace_dev, void* stream);
+
+/* ---- standalone kernels (BASELINE configs 3/4) ------------------------------------------------ */
+/* algo/shanten.rs:138-150 calc_all: tiles_dev uint8 [n,34], len_div3_dev uint8 [n] -> int8 [n]. */
+int mjx_shanten(const uint8_t* tiles_dev, const uint8_t* len_div3_dev, int8_t* out_dev, int n, void* stream);
+
+typedef struct mjx_agari_in {  /* algo/agari.rs:77-101 AgariCalculator */
+    uint8_t tehai[34];
+    uint8_t chis[4], pons[4], minkans[4], ankans[4];
+    uint8_t n_chis, n_pons, n_minkans, n_ankans;
+    uint8_t bakaze, jikaze, winning_tile, is_ron;
+    uint8_t additional_hans, doras; /* for mode 1 = agari(additional_hans, doras) */
+    uint8_t is_oya, pad;
+} mjx_agari_in;
+typedef struct mjx_agari_out { /* algo/agari.rs:66-74 Agari + algo/point.rs Point */
+    uint8_t kind; /* 0 none, 1 normal, 2 yakuman */
+    uint8_t fu, han, yakuman;
+    int32_t ron, tsumo_ko, tsumo_oya; /* -1 where point.rs would panic */
+} mjx_agari_out;
+/* mode 0 = search_yakus (agari.rs:212), 1 = agari (agari.rs:225), 2 = has_yaku (agari.rs:206) */
+int mjx_agari(const mjx_agari_in* in_dev, mjx_agari_out* out_dev, int n, int mode, void* stream);
+
+/* Host-buffer conveniences (H2D + kernel + D2H), the shape a foreign-language binding would call. */
+int mjx_shanten_host(const uint8_t* tiles, const uint8_t* len_div3, int8_t* out, int n);
+int mjx_agari_host(const mjx_agari_in* in, mjx_agari_out* out, int n, int mode);
+
+/* arena/board.rs:99-123 wall for one (seed, kyoku, honba): uint8 [136] (host out; runs on device). */
+int mjx_make_wall_host(uint64_t nonce, uint64_t key, int kyoku, int honba, int shuffle_kind, uint8_t* wall136);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MJX_H */

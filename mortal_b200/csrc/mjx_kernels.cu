@@ -1,0 +1,471 @@
+// mortal_b200 — CUDA kernels (sm_100a) and the C ABI of include/mjx.h.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mjx.h"
+#include "mjx_obs.cuh"
+#include "mjx_policy.cuh"
+#include "mjx_tables_host.h"
+
+using namespace mjx;
+
+// ================================================================ kernels
+constexpr int STEP_WARPS = 4;  // tables per CTA
+
+// One warp = one table: record HBM -> smem (uint4, coalesced), step, smem -> HBM.
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_step(EnvView V, Tables T) {
+    __shared__ __align__(16) unsigned char s_tab[STEP_WARPS][sizeof(TableState)];
+    __shared__ WarpScratch s_scratch[STEP_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int table = blockIdx.x * STEP_WARPS + warp;
+    if (table >= V.n_tables) return;
+    TableState* g = V.tables + table;
+    // cheap liveness probe before moving 2 KB
+    if (!(g->gflags & GF_ALIVE)) return;
+    constexpr int NV = sizeof(TableState) / 16;
+    uint4* dst = reinterpret_cast<uint4*>(s_tab[warp]);
+    const uint4* src = reinterpret_cast<const uint4*>(g);
+    for (int i = lane; i < NV; i += 32) dst[i] = src[i];
+    __syncwarp();
+    Ctx c;
+    c.S = reinterpret_cast<TableState*>(s_tab[warp]);
+    c.W = &s_scratch[warp];
+    c.T = T;
+    c.lane = lane;
+    const bool live = step_table(c, V, table);
+    __syncwarp();
+    uint4* gdst = reinterpret_cast<uint4*>(g);
+    for (int i = lane; i < NV; i += 32) gdst[i] = dst[i];
+    if (lane == 0 && live) {
+        atomicAdd(&V.counters[0], 1ull);
+        atomicAdd(&V.counters[1], 1ull);
+    }
+}
+
+__global__ void k_begin_step(EnvView V) {
+    *V.n_rows = 0;
+    V.counters[0] = 0;
+}
+
+__global__ void k_init_tables(TableState* tabs, int n, const u64* nonces, const u64* keys, int shuffle_kind, i32* done,
+                              i32* steps, i32* err) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    TableState* S = tabs + t;
+    unsigned char* p = reinterpret_cast<unsigned char*>(S);
+    for (size_t i = 0; i < sizeof(TableState); i++) p[i] = 0;
+    S->nonce = nonces[t];
+    S->key = keys[t];
+    for (int i = 0; i < 4; i++) {
+        S->scores[i] = 25000;  // game.rs:225
+        S->row_of_seat[i] = -1;
+        S->kan_row_of_seat[i] = -1;
+        S->auto_action[i] = -1;
+    }
+    S->shuffle_kind = (u8)shuffle_kind;
+    S->gflags = GF_ALIVE;
+    done[t] = 0;
+    steps[t] = 0;
+    err[t] = 0;
+}
+
+// Observation tile: built in shared memory, leaves as one bulk async copy (TMA).
+constexpr int ENC_THREADS = 256;
+constexpr size_t ENC_TILE_BYTES = (size_t)OBS_ROWS_V4 * OBS_COLS * sizeof(float);  // 137,632
+constexpr size_t ENC_SMEM_BYTES = ENC_TILE_BYTES + 64;
+
+__global__ void __launch_bounds__(ENC_THREADS, 1) k_encode_obs_v4(EnvView V, Tables T, float* __restrict__ obs) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float* tile = reinterpret_cast<float*>(s_raw);
+    u8* df = s_raw + ENC_TILE_BYTES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_rows = *V.n_rows;
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        uint4* t4 = reinterpret_cast<uint4*>(tile);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < (int)(ENC_TILE_BYTES / 16); i += ENC_THREADS) t4[i] = z;
+        const TableState* S = V.tables + V.row_table[row];
+        const int seat = V.row_seat[row] & 3;
+        const bool kan = (V.row_seat[row] >> 2) & 1;
+        if (tid < 34) {
+            int f = 0;
+            for (int k = 0; k < S->n_dora; k++) f += tile_next(S->wall[60 - k]) == tid;
+            df[tid] = (u8)f;
+        }
+        __syncthreads();
+        EncCtx e;
+        e.S = S; e.T = T; e.tile = tile; e.seat = seat; e.kan_select = kan;
+        e.lane = lane; e.warp = warp; e.nwarps = ENC_THREADS / 32; e.dora_factor = df;
+        Ctx c;
+        c.S = const_cast<TableState*>(S); c.W = nullptr; c.T = T; c.lane = lane;
+        encode_obs_v4(e, c, nullptr);
+        // make the generic-proxy smem writes visible to the async proxy, then one thread issues the bulk store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            float* dst = obs + (size_t)row * OBS_ROWS_V4 * OBS_COLS;
+            unsigned smem_addr = (unsigned)__cvta_generic_to_shared(tile);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst), "r"(smem_addr), "r"((unsigned)ENC_TILE_BYTES) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_policy_test(EnvView V, int kind, i64* actions, i64* trace) {
+    const int n_rows = *V.n_rows;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
+        const int t = V.row_table[r], seat = V.row_seat[r] & 3, kan = (V.row_seat[r] >> 2) & 1;
+        u64 m = 0;
+        for (int i = 0; i < ACTION_SPACE; i++) if (V.masks[(size_t)r * ACTION_SPACE + i]) m |= 1ull << i;
+        const TableState* S = V.tables + t;
+        const SeatPrivate& P = S->priv[seat];
+        u64 h = policy_hash(S->nonce, S->key, (u64)t, V.row_step[r], (u32)seat, (u32)kan);
+        int a = test_policy(kind, h, kan != 0, m, P.keep_shanten, P.next_shanten);
+        actions[r] = a;
+        if (trace) {
+            i64* o = trace + (size_t)r * 6;
+            o[0] = t; o[1] = V.row_step[r]; o[2] = seat; o[3] = a; o[4] = kan; o[5] = (i64)m;
+        }
+    }
+}
+
+// ---- standalone: shanten (hands staged through smem so the 34-byte records load coalesced)
+constexpr int SH_THREADS = 256;
+__global__ void __launch_bounds__(SH_THREADS) k_shanten(Tables T, const u8* __restrict__ tiles, const u8* __restrict__ len_div3,
+                                                         i8* __restrict__ out, int n) {
+    __shared__ __align__(16) u8 s_tiles[SH_THREADS * 34];
+    const int base = blockIdx.x * SH_THREADS;
+    const int cnt = min(SH_THREADS, n - base);
+    if (cnt <= 0) return;
+    const size_t byte0 = (size_t)base * 34;
+    const int nbytes = cnt * 34;
+    // 34-byte records: block start is 34*256-byte aligned -> 16-byte aligned when base is a multiple of 8
+    for (int i = threadIdx.x; i < nbytes; i += SH_THREADS) s_tiles[i] = tiles[byte0 + i];
+    __syncthreads();
+    if (threadIdx.x < cnt) {
+        const u8* h = s_tiles + threadIdx.x * 34;
+        u8 loc[34];
+#pragma unroll
+        for (int i = 0; i < 34; i++) loc[i] = h[i];
+        out[base + threadIdx.x] = (i8)shanten_all(T, loc, len_div3[base + threadIdx.x]);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_agari(Tables T, const mjx_agari_in* __restrict__ in, mjx_agari_out* __restrict__ out,
+                                                int n, int mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mjx_agari_in q = in[i];
+    AgariQuery a;
+    a.tehai = q.tehai;
+    a.chis = q.chis; a.pons = q.pons; a.minkans = q.minkans; a.ankans = q.ankans;
+    a.n_chis = q.n_chis; a.n_pons = q.n_pons; a.n_minkans = q.n_minkans; a.n_ankans = q.n_ankans;
+    a.bakaze = q.bakaze; a.jikaze = q.jikaze; a.winning_tile = q.winning_tile;
+    a.is_ron = q.is_ron != 0;
+    a.is_menzen = q.n_chis == 0 && q.n_pons == 0 && q.n_minkans == 0;
+    mjx_agari_out o;
+    o.kind = 0; o.fu = o.han = o.yakuman = 0; o.ron = o.tsumo_ko = o.tsumo_oya = 0;
+    if (mode == 2) {
+        o.kind = has_yaku(T, a) ? 1 : 0;
+    } else {
+        Agari r = mode == 0 ? search_yakus(T, a, false) : agari_with(T, a, q.additional_hans, q.doras);
+        if (r.kind != 0) {
+            o.kind = r.kind; o.fu = r.fu; o.han = r.han; o.yakuman = r.yakuman;
+            bool ok;
+            Point p = agari_point(r, q.is_oya != 0, &ok);
+            if (ok) { o.ron = p.ron; o.tsumo_ko = p.tsumo_ko; o.tsumo_oya = p.tsumo_oya; }
+            else { o.ron = o.tsumo_ko = o.tsumo_oya = -1; }
+        }
+    }
+    out[i] = o;
+}
+
+__global__ void k_make_wall(u64 nonce, u64 key, int kyoku, int honba, int kind, u8* out) {
+    __shared__ u8 w[136];
+    if (threadIdx.x == 0) make_wall(nonce, key, kyoku, honba, kind, w);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 136; i += blockDim.x) out[i] = w[i];
+}
+
+// ================================================================ host side
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+bool g_ready = false;
+int g_device = -1;
+int g_sm_count = 148;
+Tables g_T;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(MJX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename Tp>
+int upload(const std::vector<Tp>& v, const Tp** out) {
+    Tp* d = nullptr;
+    CU(cudaMalloc(&d, v.size() * sizeof(Tp)));
+    CU(cudaMemcpy(d, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+    *out = d;
+    return 0;
+}
+
+}  // namespace
+
+struct mjx_env {
+    int n_tables = 0, row_cap = 0, obs_version = 4, shuffle_kind = 0, quick_eval = 1;
+    bool first = true;
+    EnvView V;
+    u64 *d_nonces = nullptr, *d_keys = nullptr;
+    i64* d_dummy_actions = nullptr;
+};
+
+extern "C" {
+
+const char* mjx_last_error(void) { return g_err.c_str(); }
+
+int mjx_init(const char* data_dir, int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ready) {
+        if (device != g_device) return fail(MJX_ERR_ARG, "mjx_init: already initialised on another device");
+        return MJX_OK;
+    }
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(MJX_ERR_CUDA, "mjx_init: no CUDA device (this library has no CPU path)");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    g_sm_count = prop.multiProcessorCount;
+    HostTables H;
+    if (!load_host_tables(data_dir, H)) return fail(MJX_ERR_TABLES, "mjx_init: " + H.error);
+    int rc;
+    if ((rc = upload(H.suhai, &g_T.suhai))) return rc;
+    if ((rc = upload(H.jihai, &g_T.jihai))) return rc;
+    if ((rc = upload(H.agari_keys, &g_T.agari_keys))) return rc;
+    if ((rc = upload(H.agari_divs, &g_T.agari_divs))) return rc;
+    if ((rc = upload(H.agari_ndivs, &g_T.agari_ndivs))) return rc;
+    CU(cudaFuncSetAttribute(k_encode_obs_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_BYTES));
+    g_device = device;
+    g_ready = true;
+    return MJX_OK;
+}
+
+int mjx_obs_rows(int version) {
+    switch (version) {
+        case 1: return 938;
+        case 2: return 942;
+        case 3: return 934;
+        case 4: return 1012;
+        default: return MJX_ERR_ARG;
+    }
+}
+
+int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const uint64_t* keys, int obs_version,
+                   int shuffle_kind, int enable_quick_eval) {
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_env_create: call mjx_init first");
+    if (!out || n_tables <= 0 || !nonces || !keys) return fail(MJX_ERR_ARG, "mjx_env_create: bad arguments");
+    if (obs_version != 4) return fail(MJX_ERR_ARG, "mjx_env_create: only obs version 4 is implemented on device");
+    if (shuffle_kind != 0 && shuffle_kind != 1) return fail(MJX_ERR_ARG, "mjx_env_create: shuffle_kind must be 0 or 1");
+    mjx_env* env = new mjx_env();
+    env->n_tables = n_tables;
+    env->row_cap = n_tables * MJX_MAX_ROWS_PER_TABLE;
+    env->obs_version = obs_version;
+    env->shuffle_kind = shuffle_kind;
+    env->quick_eval = enable_quick_eval ? 1 : 0;
+    EnvView& V = env->V;
+    memset(&V, 0, sizeof V);
+    V.n_tables = n_tables;
+    V.row_cap = env->row_cap;
+    V.enable_quick_eval = env->quick_eval;
+    const size_t cap = (size_t)env->row_cap;
+    CU(cudaMalloc(&V.tables, sizeof(TableState) * (size_t)n_tables));
+    CU(cudaMalloc(&V.n_rows, sizeof(i32)));
+    CU(cudaMalloc(&V.row_table, sizeof(i32) * cap));
+    CU(cudaMalloc(&V.row_seat, cap));
+    CU(cudaMalloc(&V.row_step, sizeof(u32) * cap));
+    CU(cudaMalloc(&V.masks, cap * ACTION_SPACE));
+    CU(cudaMalloc(&V.scores, sizeof(i32) * 4 * (size_t)n_tables));
+    CU(cudaMalloc(&V.ranks, 4 * (size_t)n_tables));
+    CU(cudaMalloc(&V.done, sizeof(i32) * (size_t)n_tables));
+    CU(cudaMalloc(&V.steps, sizeof(i32) * (size_t)n_tables));
+    CU(cudaMalloc(&V.err, sizeof(i32) * (size_t)n_tables));
+    CU(cudaMalloc(&V.counters, sizeof(unsigned long long) * 2));
+    CU(cudaMalloc(&env->d_nonces, sizeof(u64) * (size_t)n_tables));
+    CU(cudaMalloc(&env->d_keys, sizeof(u64) * (size_t)n_tables));
+    CU(cudaMalloc(&env->d_dummy_actions, sizeof(i64) * cap));
+    CU(cudaMemset(env->d_dummy_actions, 0, sizeof(i64) * cap));
+    CU(cudaMemset(V.masks, 0, cap * ACTION_SPACE));
+    CU(cudaMemset(V.scores, 0, sizeof(i32) * 4 * (size_t)n_tables));
+    CU(cudaMemset(V.ranks, 0, 4 * (size_t)n_tables));
+    CU(cudaMemset(V.n_rows, 0, sizeof(i32)));
+    CU(cudaMemset(V.counters, 0, sizeof(unsigned long long) * 2));
+    CU(cudaMemcpy(env->d_nonces, nonces, sizeof(u64) * (size_t)n_tables, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(env->d_keys, keys, sizeof(u64) * (size_t)n_tables, cudaMemcpyHostToDevice));
+    k_init_tables<<<(n_tables + 127) / 128, 128>>>(V.tables, n_tables, env->d_nonces, env->d_keys, shuffle_kind, V.done,
+                                                   V.steps, V.err);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    *out = env;
+    return MJX_OK;
+}
+
+void mjx_env_destroy(mjx_env* env) {
+    if (!env) return;
+    EnvView& V = env->V;
+    cudaFree(V.tables); cudaFree(V.n_rows); cudaFree(V.row_table); cudaFree(V.row_seat); cudaFree(V.row_step);
+    cudaFree(V.masks); cudaFree(V.scores); cudaFree(V.ranks); cudaFree(V.done); cudaFree(V.steps); cudaFree(V.err);
+    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions);
+    delete env;
+}
+
+int mjx_env_step(mjx_env* env, const int64_t* actions_dev, void* stream) {
+    if (!env) return fail(MJX_ERR_ARG, "mjx_env_step: null env");
+    if (!env->first && !actions_dev) return fail(MJX_ERR_ARG, "mjx_env_step: actions required after the first step");
+    cudaStream_t st = (cudaStream_t)stream;
+    EnvView V = env->V;
+    V.actions = actions_dev ? (const i64*)actions_dev : env->d_dummy_actions;
+    k_begin_step<<<1, 1, 0, st>>>(V);
+    k_step<<<(env->n_tables + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32, 0, st>>>(V, g_T);
+    CU(cudaGetLastError());
+    env->first = false;
+    return MJX_OK;
+}
+
+int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
+    if (!env || !obs_dev) return fail(MJX_ERR_ARG, "mjx_env_encode_obs: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_encode_obs_v4<<<g_sm_count, ENC_THREADS, ENC_SMEM_BYTES, st>>>(env->V, g_T, obs_dev);
+    CU(cudaGetLastError());
+    return MJX_OK;
+}
+
+int mjx_env_num_rows(mjx_env* env, void* stream, int* n_rows) {
+    if (!env || !n_rows) return fail(MJX_ERR_ARG, "mjx_env_num_rows: bad arguments");
+    CU(cudaMemcpyAsync(n_rows, env->V.n_rows, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return MJX_OK;
+}
+
+int mjx_env_num_live(mjx_env* env, void* stream, int* n_live) {
+    if (!env || !n_live) return fail(MJX_ERR_ARG, "mjx_env_num_live: bad arguments");
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, env->V.counters, sizeof v, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    *n_live = (int)v;
+    return MJX_OK;
+}
+
+int mjx_env_total_steps(mjx_env* env, void* stream, int64_t* steps) {
+    if (!env || !steps) return fail(MJX_ERR_ARG, "mjx_env_total_steps: bad arguments");
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, env->V.counters + 1, sizeof v, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    *steps = (int64_t)v;
+    return MJX_OK;
+}
+
+int mjx_env_row_cap(mjx_env* env) { return env ? env->row_cap : MJX_ERR_ARG; }
+uint8_t* mjx_env_masks(mjx_env* env) { return env ? env->V.masks : nullptr; }
+int32_t* mjx_env_row_table(mjx_env* env) { return env ? env->V.row_table : nullptr; }
+uint8_t* mjx_env_row_seat(mjx_env* env) { return env ? env->V.row_seat : nullptr; }
+int32_t* mjx_env_num_rows_dev(mjx_env* env) { return env ? env->V.n_rows : nullptr; }
+
+int mjx_env_results(mjx_env* env, void* stream, int32_t* scores, uint8_t* ranks, int32_t* steps, int32_t* err,
+                    int32_t* done) {
+    if (!env) return fail(MJX_ERR_ARG, "mjx_env_results: null env");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)env->n_tables;
+    CU(cudaStreamSynchronize(st));
+    if (scores) CU(cudaMemcpy(scores, env->V.scores, sizeof(i32) * 4 * n, cudaMemcpyDeviceToHost));
+    if (ranks) CU(cudaMemcpy(ranks, env->V.ranks, 4 * n, cudaMemcpyDeviceToHost));
+    if (steps) CU(cudaMemcpy(steps, env->V.steps, sizeof(i32) * n, cudaMemcpyDeviceToHost));
+    if (err) CU(cudaMemcpy(err, env->V.err, sizeof(i32) * n, cudaMemcpyDeviceToHost));
+    if (done) CU(cudaMemcpy(done, env->V.done, sizeof(i32) * n, cudaMemcpyDeviceToHost));
+    return MJX_OK;
+}
+
+int mjx_env_policy_test(mjx_env* env, int kind, int64_t* actions_dev, int64_t* trace_dev, void* stream) {
+    if (!env || !actions_dev) return fail(MJX_ERR_ARG, "mjx_env_policy_test: bad arguments");
+    k_policy_test<<<g_sm_count * 2, 128, 0, (cudaStream_t)stream>>>(env->V, kind, (i64*)actions_dev, (i64*)trace_dev);
+    CU(cudaGetLastError());
+    return MJX_OK;
+}
+
+int mjx_shanten(const uint8_t* tiles_dev, const uint8_t* len_dev, int8_t* out_dev, int n, void* stream) {
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_shanten: call mjx_init first");
+    if (n <= 0) return MJX_OK;
+    k_shanten<<<(n + SH_THREADS - 1) / SH_THREADS, SH_THREADS, 0, (cudaStream_t)stream>>>(g_T, tiles_dev, len_dev,
+                                                                                         (i8*)out_dev, n);
+    CU(cudaGetLastError());
+    return MJX_OK;
+}
+
+int mjx_agari(const mjx_agari_in* in_dev, mjx_agari_out* out_dev, int n, int mode, void* stream) {
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_agari: call mjx_init first");
+    if (mode < 0 || mode > 2) return fail(MJX_ERR_ARG, "mjx_agari: mode must be 0, 1 or 2");
+    if (n <= 0) return MJX_OK;
+    k_agari<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g_T, in_dev, out_dev, n, mode);
+    CU(cudaGetLastError());
+    return MJX_OK;
+}
+
+int mjx_shanten_host(const uint8_t* tiles, const uint8_t* len_div3, int8_t* out, int n) {
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_shanten_host: call mjx_init first");
+    if (n <= 0) return MJX_OK;
+    u8 *d_t = nullptr, *d_l = nullptr;
+    i8* d_o = nullptr;
+    CU(cudaMalloc(&d_t, (size_t)n * 34));
+    CU(cudaMalloc(&d_l, (size_t)n));
+    CU(cudaMalloc(&d_o, (size_t)n));
+    CU(cudaMemcpy(d_t, tiles, (size_t)n * 34, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_l, len_div3, (size_t)n, cudaMemcpyHostToDevice));
+    int rc = mjx_shanten(d_t, d_l, (int8_t*)d_o, n, nullptr);
+    if (rc == MJX_OK) {
+        cudaError_t e = cudaMemcpy(out, d_o, (size_t)n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(MJX_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d_t); cudaFree(d_l); cudaFree(d_o);
+    return rc;
+}
+
+int mjx_agari_host(const mjx_agari_in* in, mjx_agari_out* out, int n, int mode) {
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_agari_host: call mjx_init first");
+    if (n <= 0) return MJX_OK;
+    mjx_agari_in* d_i = nullptr;
+    mjx_agari_out* d_o = nullptr;
+    CU(cudaMalloc(&d_i, sizeof(mjx_agari_in) * (size_t)n));
+    CU(cudaMalloc(&d_o, sizeof(mjx_agari_out) * (size_t)n));
+    CU(cudaMemcpy(d_i, in, sizeof(mjx_agari_in) * (size_t)n, cudaMemcpyHostToDevice));
+    int rc = mjx_agari(d_i, d_o, n, mode, nullptr);
+    if (rc == MJX_OK) {
+        cudaError_t e = cudaMemcpy(out, d_o, sizeof(mjx_agari_out) * (size_t)n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(MJX_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d_i); cudaFree(d_o);
+    return rc;
+}
+
+int mjx_make_wall_host(uint64_t nonce, uint64_t key, int kyoku, int honba, int shuffle_kind, uint8_t* wall136) {
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_make_wall_host: call mjx_init first");
+    u8* d = nullptr;
+    CU(cudaMalloc(&d, 136));
+    k_make_wall<<<1, 32>>>(nonce, key, kyoku, honba, shuffle_kind, d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(wall136, d, 136, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return MJX_OK;
+}
+
+}  // extern "C"

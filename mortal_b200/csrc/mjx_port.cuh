@@ -10,10 +10,12 @@
 
 #ifdef MJX_HOST_EMUL
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #define MJX_HD static inline
 #define MJX_D static inline
 #define MJX_DN static inline
+#define MJX_DM inline
 #define MJX_CONST static const
 #define MJX_LDG(p) (*(p))
 #define MJX_SYNCWARP() ((void)0)
@@ -32,6 +34,7 @@ using std::min;
 #define MJX_HD __host__ __device__ __forceinline__
 #define MJX_D __device__ __forceinline__
 #define MJX_DN __device__ inline
+#define MJX_DM __device__ __forceinline__
 #define MJX_CONST __constant__
 #define MJX_LDG(p) __ldg(p)
 #define MJX_SYNCWARP() __syncwarp()

@@ -1,0 +1,149 @@
+"""Device-resident batch environment: Python handle over mjx_env (include/mjx.h).
+
+Mirrors the loop of libriichi's BatchGame::run (arena/game.rs:230-316): `step()` = one iteration
+for every live table (commit the previous decisions, poll to the next decision point), the rows it
+emits are what MortalBatchAgent would hand to `engine.react_batch` (agent/mortal.rs:114-159).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class _CudaView:
+    """Zero-copy torch view of a device buffer owned by the C library (__cuda_array_interface__ v2)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class BatchEnv:
+    def __init__(self, nonces, keys, *, obs_version: int = 4, shuffle_kind: int = 0, enable_quick_eval: bool = True,
+                 device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise _lib.MjxError("mortal_b200.BatchEnv needs a CUDA device (there is no CPU fallback)")
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        _lib.init(device)
+        self.L = _lib.load()
+        nonces = np.ascontiguousarray(nonces, dtype=np.uint64)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        assert nonces.shape == keys.shape and nonces.ndim == 1
+        self.n_tables = int(nonces.shape[0])
+        self.obs_version = obs_version
+        self.obs_rows = self.L.mjx_obs_rows(obs_version)
+        h = C.c_void_p()
+        _lib.check(self.L.mjx_env_create(C.byref(h), self.n_tables, nonces.ctypes.data, keys.ctypes.data, obs_version,
+                                         shuffle_kind, int(enable_quick_eval)), "mjx_env_create")
+        self._h = h
+        self.row_cap = self.L.mjx_env_row_cap(h)
+        as_t = lambda ptr, shape, ts: torch.as_tensor(_CudaView(ptr, shape, ts), device=self.device)
+        self.masks = as_t(self.L.mjx_env_masks(h), (self.row_cap, 46), "|u1").view(torch.bool)
+        self.row_table = as_t(self.L.mjx_env_row_table(h), (self.row_cap,), "<i4")
+        self.row_seat = as_t(self.L.mjx_env_row_seat(h), (self.row_cap,), "|u1")
+        self.n_rows_dev = as_t(self.L.mjx_env_num_rows_dev(h), (1,), "<i4")
+        self._obs = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.mjx_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def step(self, actions=None) -> None:
+        """actions: int64 cuda tensor [row_cap] indexed by the previous step's rows (None on the first step)."""
+        ptr = None
+        if actions is not None:
+            assert actions.dtype == self.torch.int64 and actions.is_cuda and actions.is_contiguous()
+            assert actions.numel() >= self.row_cap
+            ptr = C.c_void_p(actions.data_ptr())
+        _lib.check(self.L.mjx_env_step(self._h, ptr, self._stream()), "mjx_env_step")
+
+    def obs_buffer(self):
+        if self._obs is None:
+            self._obs = self.torch.empty((self.row_cap, self.obs_rows, 34), dtype=self.torch.float32, device=self.device)
+        return self._obs
+
+    def encode_obs(self, out=None):
+        """Encode the current rows; returns the [row_cap, C, 34] buffer (first num_rows() rows valid)."""
+        out = self.obs_buffer() if out is None else out
+        assert out.dtype == self.torch.float32 and out.is_contiguous() and out.shape[1:] == (self.obs_rows, 34)
+        assert out.shape[0] >= self.row_cap
+        _lib.check(self.L.mjx_env_encode_obs(self._h, C.c_void_p(out.data_ptr()), self._stream()), "mjx_env_encode_obs")
+        return out
+
+    def num_rows(self) -> int:
+        n = C.c_int(0)
+        _lib.check(self.L.mjx_env_num_rows(self._h, self._stream(), C.byref(n)), "mjx_env_num_rows")
+        return n.value
+
+    def num_live(self) -> int:
+        n = C.c_int(0)
+        _lib.check(self.L.mjx_env_num_live(self._h, self._stream(), C.byref(n)), "mjx_env_num_live")
+        return n.value
+
+    def total_steps(self) -> int:
+        n = C.c_int64(0)
+        _lib.check(self.L.mjx_env_total_steps(self._h, self._stream(), C.byref(n)), "mjx_env_total_steps")
+        return n.value
+
+    def policy_test(self, kind: int, actions, trace=None) -> None:
+        tp = C.c_void_p(trace.data_ptr()) if trace is not None else None
+        _lib.check(self.L.mjx_env_policy_test(self._h, kind, C.c_void_p(actions.data_ptr()), tp, self._stream()),
+                   "mjx_env_policy_test")
+
+    def results(self):
+        n = self.n_tables
+        scores = np.zeros((n, 4), dtype=np.int32)
+        ranks = np.zeros((n, 4), dtype=np.uint8)
+        steps = np.zeros(n, dtype=np.int32)
+        err = np.zeros(n, dtype=np.int32)
+        done = np.zeros(n, dtype=np.int32)
+        _lib.check(self.L.mjx_env_results(self._h, self._stream(), scores.ctypes.data, ranks.ctypes.data,
+                                          steps.ctypes.data, err.ctypes.data, done.ctypes.data), "mjx_env_results")
+        return dict(scores=scores, ranks=ranks, steps=steps, err=err, done=done)
+
+    def run_test_policy(self, kind: int = 1, *, encode_obs: bool = False, max_cycles: int = 0, trace: bool = False):
+        """Play every table to the end with the built-in counter-based test policy (env-only loop)."""
+        torch = self.torch
+        actions = torch.zeros(self.row_cap, dtype=torch.int64, device=self.device)
+        tbuf = torch.zeros((self.row_cap, 6), dtype=torch.int64, device=self.device) if trace else None
+        traces = []
+        cycles = 0
+        first = True
+        while True:
+            self.step(None if first else actions)
+            first = False
+            if encode_obs:
+                self.encode_obs()
+            self.policy_test(kind, actions, tbuf)
+            cycles += 1
+            if trace:
+                n = self.num_rows()
+                traces.append(tbuf[:n].cpu().numpy().copy())
+                if self.num_live() == 0:
+                    break
+            elif cycles % 16 == 0 and self.num_live() == 0:
+                break
+            if max_cycles and cycles >= max_cycles:
+                break
+        res = self.results()
+        res["cycles"] = cycles
+        if trace:
+            res["trace"] = np.concatenate(traces) if traces else np.zeros((0, 6), dtype=np.int64)
+        return res

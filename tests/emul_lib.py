@@ -32,6 +32,15 @@ def lib():
         L.emul_make_wall.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.emul_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int64]
+        L.emul_env_create.restype = C.c_void_p
+        L.emul_env_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.emul_env_destroy.argtypes = [C.c_void_p]
+        L.emul_env_step.argtypes = [C.c_void_p, C.c_void_p]
+        L.emul_env_num_rows.argtypes = [C.c_void_p]
+        L.emul_env_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emul_env_policy_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.emul_env_encode_obs.argtypes = [C.c_void_p, C.c_void_p]
+        L.emul_env_results.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         if L.emul_init(DATA_DIR.encode()) != 0:
             raise RuntimeError(L.emul_last_error().decode())
         _lib = L
@@ -57,3 +66,48 @@ def run(nonces, keys, *, shuffle_kind=0, quick_eval=True, policy_kind=1, trace_c
         assert tl.value <= trace_cap
         out["trace"] = trace[: tl.value]
     return out
+
+
+class EmulEnv:
+    """Host-emulated stand-in with the stepping surface of mortal_b200.BatchEnv (numpy instead of torch)."""
+
+    def __init__(self, nonces, keys, *, shuffle_kind=0, enable_quick_eval=True):
+        self.L = lib()
+        nonces = np.ascontiguousarray(nonces, dtype=np.uint64)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        self.n_tables = len(nonces)
+        self.row_cap = self.n_tables * 3
+        self._h = self.L.emul_env_create(self.n_tables, nonces.ctypes.data, keys.ctypes.data, shuffle_kind,
+                                         int(enable_quick_eval))
+        self.live = self.n_tables
+
+    def close(self):
+        if self._h:
+            self.L.emul_env_destroy(self._h)
+            self._h = None
+
+    def step(self, actions=None):
+        a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int64)
+        self.live = self.L.emul_env_step(self._h, None if a is None else a.ctypes.data)
+
+    def num_rows(self):
+        return self.L.emul_env_num_rows(self._h)
+
+    def num_live(self):
+        return self.live
+
+    def rows(self):
+        n = self.num_rows()
+        rt = np.zeros(n, dtype=np.int32); rs = np.zeros(n, dtype=np.uint8); m = np.zeros((n, 46), dtype=np.uint8)
+        self.L.emul_env_rows(self._h, rt.ctypes.data, rs.ctypes.data, m.ctypes.data)
+        return rt, rs, m.astype(bool)
+
+    def policy_test(self, kind):
+        a = np.full(self.row_cap, 45, dtype=np.int64)
+        self.L.emul_env_policy_test(self._h, kind, a.ctypes.data)
+        return a
+
+    def encode_obs(self):
+        obs = np.zeros((self.num_rows(), 1012, 34), dtype=np.float32)
+        self.L.emul_env_encode_obs(self._h, obs.ctypes.data)
+        return obs

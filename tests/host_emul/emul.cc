@@ -6,7 +6,7 @@
 #include <string>
 #include <vector>
 
-#include "mjx_step.cuh"
+#include "mjx_obs.cuh"
 #include "mjx_policy.cuh"
 #include "mjx_tables_host.h"
 
@@ -99,6 +99,103 @@ int emul_run(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_ki
     if (trace_len) *trace_len = tl;
     for (int t = 0; t < n; t++) if (!done[t]) { errs[t] = errs[t] ? errs[t] : -1; }
     return 0;
+}
+
+// ---------------- stateful env (mirrors the C ABI's mjx_env_* so tests can drive it in lock step) ----------------
+struct EmulEnv {
+    int n = 0, cap = 0;
+    std::vector<TableState> tabs;
+    std::vector<i32> row_table, done, steps, errs, scores, n_rows;
+    std::vector<u8> row_seat, masks, ranks;
+    std::vector<u32> row_step;
+    std::vector<i64> actions;
+    unsigned long long counters[2] = {0, 0};
+    EnvView V;
+    bool first = true;
+};
+
+void* emul_env_create(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int quick_eval) {
+    EmulEnv* E = new EmulEnv();
+    E->n = n; E->cap = n * MAX_ROWS_PER_TABLE;
+    E->tabs.resize(n);
+    for (int t = 0; t < n; t++) {
+        TableState& S = E->tabs[t];
+        memset(&S, 0, sizeof S);
+        S.nonce = nonces[t]; S.key = keys[t];
+        for (int i = 0; i < 4; i++) { S.scores[i] = 25000; S.row_of_seat[i] = -1; S.kan_row_of_seat[i] = -1; S.auto_action[i] = -1; }
+        S.shuffle_kind = (u8)shuffle_kind;
+        S.gflags = GF_ALIVE;
+    }
+    E->row_table.assign(E->cap, 0); E->row_seat.assign(E->cap, 0); E->row_step.assign(E->cap, 0);
+    E->masks.assign((size_t)E->cap * ACTION_SPACE, 0); E->actions.assign(E->cap, 45);
+    E->done.assign(n, 0); E->steps.assign(n, 0); E->errs.assign(n, 0); E->scores.assign(n * 4, 0); E->ranks.assign(n * 4, 0);
+    E->n_rows.assign(1, 0);
+    EnvView& V = E->V;
+    V.tables = E->tabs.data(); V.n_tables = n; V.row_cap = E->cap; V.n_rows = E->n_rows.data();
+    V.row_table = E->row_table.data(); V.row_seat = E->row_seat.data(); V.row_step = E->row_step.data();
+    V.masks = E->masks.data(); V.actions = E->actions.data(); V.scores = E->scores.data(); V.ranks = E->ranks.data();
+    V.done = E->done.data(); V.steps = E->steps.data(); V.err = E->errs.data(); V.counters = E->counters;
+    V.enable_quick_eval = quick_eval;
+    return E;
+}
+void emul_env_destroy(void* p) { delete static_cast<EmulEnv*>(p); }
+
+// returns number of live tables after the step
+int emul_env_step(void* p, const int64_t* actions) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    if (actions) for (int i = 0; i < E->cap; i++) E->actions[i] = actions[i];
+    E->n_rows[0] = 0;
+    int live = 0;
+    WarpScratch W;
+    for (int t = 0; t < E->n; t++) {
+        Ctx c; c.S = &E->tabs[t]; c.W = &W; c.T = g_T; c.lane = 0;
+        if (step_table(c, E->V, t)) live++;
+    }
+    return live;
+}
+int emul_env_num_rows(void* p) { return static_cast<EmulEnv*>(p)->n_rows[0]; }
+void emul_env_rows(void* p, int32_t* row_table, uint8_t* row_seat, uint8_t* masks) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    int n = E->n_rows[0];
+    for (int r = 0; r < n; r++) { row_table[r] = E->row_table[r]; row_seat[r] = E->row_seat[r]; }
+    memcpy(masks, E->masks.data(), (size_t)n * ACTION_SPACE);
+}
+void emul_env_policy_test(void* p, int kind, int64_t* actions) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    for (int r = 0; r < E->n_rows[0]; r++) {
+        int t = E->row_table[r], seat = E->row_seat[r] & 3, kan = (E->row_seat[r] >> 2) & 1;
+        u64 m = 0;
+        for (int i = 0; i < ACTION_SPACE; i++) if (E->masks[(size_t)r * ACTION_SPACE + i]) m |= 1ull << i;
+        const SeatPrivate& P = E->tabs[t].priv[seat];
+        u64 h = policy_hash(E->tabs[t].nonce, E->tabs[t].key, (u64)t, E->row_step[r], (u32)seat, (u32)kan);
+        actions[r] = test_policy(kind, h, kan != 0, m, P.keep_shanten, P.next_shanten);
+    }
+}
+// obs: [n_rows, 1012, 34] f32
+void emul_env_encode_obs(void* p, float* obs) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    for (int r = 0; r < E->n_rows[0]; r++) {
+        float* tile = obs + (size_t)r * OBS_ROWS_V4 * OBS_COLS;
+        memset(tile, 0, sizeof(float) * OBS_ROWS_V4 * OBS_COLS);
+        const TableState* S = &E->tabs[E->row_table[r]];
+        u8 df[34];
+        for (int t = 0; t < 34; t++) {
+            int f = 0;
+            for (int k = 0; k < S->n_dora; k++) f += tile_next(S->wall[60 - k]) == t;
+            df[t] = (u8)f;
+        }
+        EncCtx e;
+        e.S = S; e.T = g_T; e.tile = tile; e.seat = E->row_seat[r] & 3; e.kan_select = (E->row_seat[r] >> 2) & 1;
+        e.lane = 0; e.warp = 0; e.nwarps = 1; e.dora_factor = df;
+        Ctx c; c.S = const_cast<TableState*>(S); c.W = nullptr; c.T = g_T; c.lane = 0;
+        encode_obs_v4(e, c, nullptr);
+    }
+}
+void emul_env_results(void* p, int32_t* scores, uint8_t* ranks, int32_t* steps, int32_t* errs, int32_t* done) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    memcpy(scores, E->scores.data(), sizeof(i32) * 4 * E->n); memcpy(ranks, E->ranks.data(), 4 * E->n);
+    memcpy(steps, E->steps.data(), sizeof(i32) * E->n); memcpy(errs, E->errs.data(), sizeof(i32) * E->n);
+    memcpy(done, E->done.data(), sizeof(i32) * E->n);
 }
 
 }  // extern "C"

@@ -72,3 +72,20 @@ def test_emul_wall_matches_oracle():
             E.lib().emul_make_wall(12345678901234567, 0xDEADBEEFCAFE, kyoku, honba, kind, a.ctypes.data)
             O.lib().orc_make_wall(12345678901234567, 0xDEADBEEFCAFE, kyoku, honba, kind, b.ctypes.data)
             assert (a == b).all()
+
+
+def test_obs_encode_parity_emulated():
+    """v4 observation rows 0..888 + legal masks of the product encoder (host-emulated) vs the oracle."""
+    from obs_check import check_obs_parity
+
+    def make_env(nonces, keys):
+        return E.EmulEnv(nonces, keys, enable_quick_eval=False)
+
+    def fetch(env, first, prev):
+        env.step(None if first else prev)
+        rt, rs, m = env.rows()
+        obs = env.encode_obs()
+        acts = env.policy_test(1)
+        return rt, rs, m, obs, acts
+
+    check_obs_parity(make_env, fetch, n=6, min_rows=1500)

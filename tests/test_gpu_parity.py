@@ -1,0 +1,207 @@
+"""GPU parity tests: the CUDA path through the C ABI (mortal_b200/libmjx.so) against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from test_emul_vs_oracle import first_diff, sort_trace
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mjx():
+    import torch
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import mortal_b200
+    from mortal_b200 import _lib
+
+    _lib.init(0)
+    return mortal_b200
+
+
+def random_hands(n, seed=0):
+    rng = np.random.default_rng(seed)
+    tiles = np.zeros((n, 34), dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.uint8)
+    deck = np.repeat(np.arange(34, dtype=np.uint8), 4)
+    for i in range(n):
+        k = int(rng.integers(0, 4)) if i % 4 == 0 else 0
+        cnt = 13 + (i & 1) - 3 * k
+        pick = rng.permutation(deck)[:cnt]
+        np.add.at(tiles[i], pick, 1)
+        lens[i] = 4 - k
+    return tiles, lens
+
+
+def test_shanten_kernel_bit_exact(mjx):
+    from mortal_b200 import _lib
+
+    L = _lib.load()
+    tiles, lens = random_hands(100_003)
+    out = np.zeros(len(lens), dtype=np.int8)
+    _lib.check(L.mjx_shanten_host(tiles.ctypes.data, lens.ctypes.data, out.ctypes.data, len(lens)), "mjx_shanten_host")
+    ref = O.shanten(tiles, lens)
+    assert (out == ref).all()
+    # empty and tiny inputs
+    _lib.check(L.mjx_shanten_host(tiles.ctypes.data, lens.ctypes.data, out.ctypes.data, 0), "empty")
+    _lib.check(L.mjx_shanten_host(tiles.ctypes.data, lens.ctypes.data, out.ctypes.data, 1), "one")
+    assert out[0] == ref[0]
+
+
+def winning_hands(n, seed=1):
+    """Constructed winning hands (4 mentsu + pair / chiitoi / kokushi) with random melds, winds, ron/tsumo."""
+    rng = np.random.default_rng(seed)
+    q = np.zeros(n, dtype=O.AGARI_IN_DTYPE)
+    for i in range(n):
+        while True:
+            counts = np.zeros(34, dtype=np.int64)
+            kind = rng.integers(0, 20)
+            chis, pons, minkans, ankans = [], [], [], []
+            if kind == 0:  # chiitoi
+                for t in rng.choice(34, 7, replace=False):
+                    counts[t] += 2
+            elif kind == 1:  # kokushi
+                yao = [0, 8, 9, 17, 18, 26, 27, 28, 29, 30, 31, 32, 33]
+                for t in yao:
+                    counts[t] += 1
+                counts[rng.choice(yao)] += 1
+            else:
+                closed = counts.copy()
+                total = counts.copy()
+                ok = True
+                for _ in range(4):
+                    melded = rng.random() < 0.3
+                    if rng.random() < 0.55:
+                        s = int(rng.integers(0, 3)) * 9 + int(rng.integers(0, 7))
+                        total[s:s + 3] += 1
+                        if melded:
+                            chis.append(s)
+                        else:
+                            closed[s:s + 3] += 1
+                    else:
+                        t = int(rng.integers(0, 34))
+                        r = rng.random()
+                        if melded and r < 0.15:
+                            total[t] += 4; minkans.append(t)
+                        elif melded and r < 0.3:
+                            total[t] += 4; ankans.append(t)
+                        elif melded:
+                            total[t] += 3; pons.append(t)
+                        else:
+                            total[t] += 3; closed[t] += 3
+                p = int(rng.integers(0, 34))
+                total[p] += 2
+                closed[p] += 2
+                if (total > 4).any():
+                    continue
+                counts = closed
+            if (counts > 4).any():
+                continue
+            break
+        q["tehai"][i] = counts
+        for name, v in (("chis", chis), ("pons", pons), ("minkans", minkans), ("ankans", ankans)):
+            q[name][i][: len(v)] = v
+            q["n_" + name][i] = len(v)
+        present = np.nonzero(counts)[0]
+        q["winning_tile"][i] = rng.choice(present)
+        q["bakaze"][i] = 27 + rng.integers(0, 3)
+        q["jikaze"][i] = 27 + rng.integers(0, 4)
+        q["is_ron"][i] = rng.integers(0, 2)
+        q["additional_hans"][i] = rng.integers(0, 4)
+        q["doras"][i] = rng.integers(0, 5)
+        q["is_oya"][i] = q["jikaze"][i] == 27
+    return q
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_agari_kernel_bit_exact(mjx, mode):
+    from mortal_b200 import _lib
+
+    L = _lib.load()
+    q = winning_hands(30_000)
+    out = np.zeros(len(q), dtype=O.AGARI_OUT_DTYPE)
+    _lib.check(L.mjx_agari_host(q.ctypes.data, out.ctypes.data, len(q), mode), "mjx_agari_host")
+    ref = O.agari(q, mode)
+    for f in ("kind", "fu", "han", "yakuman", "ron", "tsumo_ko", "tsumo_oya"):
+        bad = np.nonzero(out[f] != ref[f])[0]
+        assert len(bad) == 0, (f, bad[:5], out[bad[:5]], ref[bad[:5]])
+    assert (ref["kind"] != 0).mean() > 0.5
+
+
+def test_wall_kernel_matches_oracle(mjx):
+    from mortal_b200 import _lib
+
+    L = _lib.load()
+    for kind in (0, 1):
+        for kyoku, honba in ((0, 0), (5, 3), (11, 9)):
+            a = np.zeros(136, dtype=np.uint8)
+            b = np.zeros(136, dtype=np.uint8)
+            _lib.check(L.mjx_make_wall_host(10637, 12210010324280706444, kyoku, honba, kind, a.ctypes.data), "wall")
+            O.lib().orc_make_wall(10637, 12210010324280706444, kyoku, honba, kind, b.ctypes.data)
+            assert (a == b).all()
+
+
+@pytest.mark.parametrize("policy_kind,quick_eval,shuffle_kind", [(1, True, 0), (0, False, 1), (1, False, 0), (0, True, 1)])
+def test_selfplay_trace_parity(mjx, policy_kind, quick_eval, shuffle_kind):
+    """BASELINE config 1 shape: OneVsThree seed layout, counter-based agents; every decision row and the
+    end-of-hanchan scores / rankings bit-equal to the oracle."""
+    n = 64
+    nonces = np.repeat(np.arange(10000, 10000 + n // 4, dtype=np.uint64), 4)
+    keys = np.full(n, 0x2000, dtype=np.uint64)
+    env = mjx.BatchEnv(nonces, keys, shuffle_kind=shuffle_kind, enable_quick_eval=quick_eval)
+    got = env.run_test_policy(kind=policy_kind, trace=True)
+    ref = O.run_batch(nonces, keys, shuffle_kind=shuffle_kind, policy_kind=policy_kind, quick_eval=quick_eval,
+                      trace_cap=1 << 18)
+    assert (got["err"] == 0).all(), got["err"]
+    assert (got["done"] == 1).all()
+    to, tg = sort_trace(ref["trace"]), sort_trace(got["trace"])
+    i, a, b = first_diff(to, tg)
+    assert a is None, f"first divergence at sorted row {i}: oracle {a} gpu {b}"
+    assert len(to) == len(tg)
+    assert (got["steps"] == ref["steps"]).all()
+    assert (got["scores"] == ref["scores"]).all()
+    assert (got["ranks"] == ref["ranks"]).all()
+    env.close()
+
+
+def test_selfplay_4096_tables_scores(mjx):
+    """BASELINE config 2 size (4096 tables): scores/ranks/steps equal to the oracle; sum of scores conserved."""
+    n = 4096
+    nonces = np.repeat(np.arange(10000, 10000 + n // 4, dtype=np.uint64), 4)
+    keys = np.full(n, 0x2000, dtype=np.uint64)
+    env = mjx.BatchEnv(nonces, keys)
+    got = env.run_test_policy(kind=1)
+    assert (got["err"] == 0).all() and (got["done"] == 1).all()
+    assert (got["scores"].sum(axis=1) == 100000).all()
+    ref = O.run_batch(nonces, keys, policy_kind=1, n_threads=8)
+    assert (got["scores"] == ref["scores"]).all()
+    assert (got["ranks"] == ref["ranks"]).all()
+    assert (got["steps"] == ref["steps"]).all()
+    assert env.total_steps() == int(ref["steps"].sum())
+    env.close()
+
+
+def test_obs_encode_matches_oracle(mjx):
+    """Rows 0..888 of the v4 observation (everything except the single-player block) and the legal mask,
+    compared at every decision of a few seeded games. 0/1 and small-rational planes exactly, exp() planes 1e-6."""
+    import torch
+
+    from obs_check import check_obs_parity
+
+    def make_env(nonces, keys):
+        env = mjx.BatchEnv(nonces, keys, enable_quick_eval=False)
+        env._actions = torch.zeros(env.row_cap, dtype=torch.int64, device=env.device)
+        return env
+
+    def fetch(env, first, prev):
+        env.step(None if first else env._actions)
+        obs = env.encode_obs()
+        env.policy_test(1, env._actions)
+        nr = env.num_rows()
+        return (env.row_table[:nr].cpu().numpy(), env.row_seat[:nr].cpu().numpy(), env.masks[:nr].cpu().numpy(),
+                obs[:nr].cpu().numpy(), env._actions[:nr].cpu().numpy())
+
+    check_obs_parity(make_env, fetch)
