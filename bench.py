@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark: table-steps/sec of batched riichi self-play (BASELINE.json metric).
+
+A "step" = one iteration of libriichi's BatchGame::run loop (arena/game.rs:286-304) over the whole batch:
+commit the previous decisions, poll every live table to its next decision point, encode one v4
+observation per decision row, run the policy. One table-step = that iteration for one live table.
+
+Default arm (this repo): 4096 tables per GPU (BASELINE configs[1]), random-init Mortal brain
+(192 channels x 40 blocks, bf16 autocast, greedy), everything resident in HBM. JSON also carries
+  env_only      the same loop with the counter-based test policy instead of the network
+  roofline      achieved HBM GB/s of the dominant env kernel (k_encode_obs_v4) from CUDA events
+  e2e           the loop through the C ABI with HOST buffers (obs D2H, actions H2D every step)
+  cpu_baseline  the CPU oracle on this box's host cores, bounded sample (rank 0, N=1 only)
+`--impl reference` times libriichi's own CPU path restated by the oracle (oracle/, all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TABLES = 4096
+SEED_START = (10000, 0x2000)  # mortal/player.py:67
+OBS_BYTES = 1012 * 34 * 4
+MASK_BYTES = 46
+STATE_BYTES = 1952  # sizeof(TableState) read per encoded row
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def seeds_for_rank(rank: int, n_tables: int):
+    import numpy as np
+
+    count = n_tables // 4
+    start = SEED_START[0] + count * rank  # rank r takes seed_start + 1024 r
+    nonces = np.repeat(np.arange(start, start + count, dtype=np.uint64), 4)
+    keys = np.full(n_tables, SEED_START[1], dtype=np.uint64)
+    return nonces, keys
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """libriichi's CPU path (oracle restatement; the Rust crate cannot be built here): poll/commit loop +
+    one v4 obs encode (incl. the single-player tables) per decision row, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib as O
+
+    cores = host_cores()
+    n_tables = args.ref_tables
+    steps_per_table = args.ref_steps_per_table
+    nonces, keys = seeds_for_rank(0, N_TABLES)
+    nonces, keys = nonces[:n_tables], keys[:n_tables]
+
+    def one():
+        r = O.run_batch(nonces, keys, shuffle_kind=0, policy_kind=1, quick_eval=True, encode_obs=4, sp_mode=1,
+                        n_threads=cores, max_steps=steps_per_table)
+        return r["table_steps"], r["seconds"], r["obs_rows"]
+
+    for _ in range(args.warmup):
+        one()
+    tot_steps, tot_sec = 0, 0.0
+    for _ in range(args.steps):
+        s, t, _ = one()
+        tot_steps += s
+        tot_sec += t
+    value = tot_steps / tot_sec
+    sample = f"{n_tables} tables x first {steps_per_table} table-steps each per step (seeds {SEED_START[0]}.., greedy test policy, v4 obs + SP encode per decision)"
+    line = {
+        "impl": "reference", "metric": "table-steps/sec batched self-play", "value": value, "unit": "table-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_sec / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (+f32 SP)", "data": "synthetic",
+        "config": {"workload": "BatchGame 4096 tables self-play step loop (configs[1]), CPU arena", "tables_per_gpu": N_TABLES,
+                   "obs_version": 4, "policy": "counter-based greedy test policy (no network on the CPU arm)"},
+        "cpu_baseline": {"value": value, "unit": "table-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "table-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- this repo's arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import mortal_b200
+    from mortal_b200.engine import DeviceEngine
+    from mortal_b200.model import DQN, Brain
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; mortal_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nonces, keys = seeds_for_rank(rank, N_TABLES)
+    torch.manual_seed(0)
+    engine = DeviceEngine(Brain(conv_channels=192, num_blocks=40, version=4), DQN(version=4), device=dev,
+                          enable_amp=True, enable_quick_eval=True)
+
+    def fresh_env():
+        return mortal_b200.BatchEnv(nonces, keys, obs_version=4, shuffle_kind=0, enable_quick_eval=True, device=local_rank)
+
+    W, K = args.warmup, args.steps
+    stats = {}
+
+    # -------- loop A: with the network (the BASELINE config), HBM resident
+    def loop(env, policy, n_warm, n_timed, time_encode=False):
+        actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
+        obs = env.obs_buffer()
+        first = True
+        enc_events = []
+
+        def cycle(timed):
+            nonlocal first
+            env.step(None if first else actions)
+            first = False
+            if timed and time_encode:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                env.encode_obs(obs)
+                e1.record()
+                enc_events.append((e0, e1))
+            else:
+                env.encode_obs(obs)
+            return policy(env, obs, actions)
+
+        for _ in range(n_warm):
+            cycle(False)
+        barrier()
+        steps0, rows = env.total_steps(), 0
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n_timed):
+            rows += cycle(True)
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1)
+        steps = env.total_steps() - steps0
+        enc_ms = sum(a.elapsed_time(b) for a, b in enc_events)
+        return dict(ms=ms, table_steps=steps, rows=rows, enc_ms=enc_ms, n=n_timed)
+
+    def nn_policy(env, obs, actions):
+        nr = env.num_rows()  # the only host sync of the cycle: the batch size the network runs at
+        if nr:
+            a, _ = engine.react_device(obs[:nr], env.masks[:nr])
+            actions[:nr] = a
+        return nr
+
+    def test_policy(env, obs, actions):
+        env.policy_test(1, actions)
+        return 0
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    env = fresh_env()
+    a = loop(env, nn_policy, W, K)
+    env.close()
+    clocks = sampler.stop()
+
+    # -------- loop B: env only (test policy on device, no host sync), encode kernel timed with events
+    env = fresh_env()
+    b = loop(env, test_policy, W, K, time_encode=True)
+    b_rows = 0
+    # rows per step for the roofline: replay the same K cycles' row counts is not needed; sample the average
+    env.close()
+    env = fresh_env()
+    actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
+    first = True
+    for i in range(W + K):
+        env.step(None if first else actions)
+        first = False
+        env.policy_test(1, actions)
+        if i >= W:
+            b_rows += env.num_rows()
+    env.close()
+
+    # -------- loop C: e2e through the C ABI with HOST buffers (pinned): obs/masks D2H, actions H2D each step
+    env = fresh_env()
+    h_obs = torch.empty((env.row_cap, 1012, 34), dtype=torch.float32, pin_memory=True)
+    h_masks = torch.empty((env.row_cap, 46), dtype=torch.bool, pin_memory=True)
+    h_actions = torch.zeros(env.row_cap, dtype=torch.int64).pin_memory()
+    d_actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
+    gen = torch.Generator().manual_seed(1)
+    e2e_h2d = e2e_d2h = 0
+
+    def e2e_cycle(first):
+        nonlocal e2e_h2d, e2e_d2h
+        if not first:
+            d_actions.copy_(h_actions, non_blocking=True)  # H2D: the step's inputs
+        env.step(None if first else d_actions)
+        obs = env.encode_obs()
+        nr = env.num_rows()
+        if nr:
+            h_obs[:nr].copy_(obs[:nr], non_blocking=True)  # D2H: the step's result, as react_batch receives it
+            h_masks[:nr].copy_(env.masks[:nr], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            # host policy: random legal action (stands in for engine.react_batch on host tensors)
+            q = torch.rand((nr, 46), generator=gen)
+            q[~h_masks[:nr]] = -1.0
+            h_actions[:nr] = q.argmax(-1)
+        return nr
+
+    first = True
+    for _ in range(W):
+        e2e_cycle(first)
+        first = False
+    barrier()
+    s0 = env.total_steps()
+    w0 = time.perf_counter()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_rows = 0
+    for _ in range(K):
+        e2e_rows += e2e_cycle(first)
+        first = False
+    t1.record()
+    barrier()
+    e2e_ms = max(t0.elapsed_time(t1), (time.perf_counter() - w0) * 1000.0)
+    e2e_steps = env.total_steps() - s0
+    env.close()
+
+    # -------- reduce over ranks: max time, sum of units
+    def reduce(ms, units):
+        if world == 1:
+            return ms, units
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        u = torch.tensor([units], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        return float(t.item()), float(u.item())
+
+    a_ms, a_units = reduce(a["ms"], a["table_steps"])
+    b_ms, b_units = reduce(b["ms"], b["table_steps"])
+    c_ms, c_units = reduce(e2e_ms, e2e_steps)
+
+    # -------- the one collective of the path: all-gather of end-of-hanchan returns
+    gather_us = None
+    if world > 1:
+        ret = torch.zeros((N_TABLES, 5), dtype=torch.int32, device=dev)  # scores[4] + packed ranks
+        out = torch.empty((world * N_TABLES, 5), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(out, ret)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather_into_tensor(out, ret)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_us = g0.elapsed_time(g1) * 1000.0
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        rows_per_launch = b_rows / K
+        bytes_per_launch = rows_per_launch * (OBS_BYTES + MASK_BYTES + STATE_BYTES)
+        enc_ms_per_launch = b["enc_ms"] / K
+        achieved = bytes_per_launch / (enc_ms_per_launch * 1e-3) / 1e9 if enc_ms_per_launch > 0 else 0.0
+        line = {
+            "metric": "table-steps/sec batched self-play", "value": a_units / (a_ms * 1e-3), "unit": "table-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": a_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/i32 env + bf16 policy net", "data": "synthetic",
+            "config": {"workload": "BatchGame 4096 tables/GPU, random-init Mortal brain (192ch x 40 blocks, v4 obs), self-play step loop (BASELINE configs[1])",
+                       "tables_per_gpu": N_TABLES, "global_tables": N_TABLES * world, "obs_version": 4,
+                       "seed_start": list(SEED_START), "parallelism": f"tables sharded dp{world}, no data-path collective",
+                       "l2": "per-step obs output (~0.7 GB) exceeds the 126 MB L2, no explicit flush",
+                       "sp_block": "rows 889-1011 (single-player tables) not yet computed on device: zero-filled"},
+            "env_only": {"value": b_units / (b_ms * 1e-3), "unit": "table-steps/s", "ms_per_step": b_ms / K,
+                         "policy": "counter-based test policy kernel, no host sync"},
+            "roofline": {"kernel": "k_encode_obs_v4", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": achieved / peak_gbs if peak_gbs else None, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": bytes_per_launch, "ms_per_launch": enc_ms_per_launch,
+                         "rows_per_launch": rows_per_launch},
+            "e2e": {"value": c_units / (c_ms * 1e-3), "unit": "table-steps/s",
+                    "h2d_bytes_per_step": 8 * N_TABLES * 3,
+                    "d2h_bytes_per_step": int(e2e_rows / K * (OBS_BYTES + MASK_BYTES)),
+                    "path": "mjx C ABI with pinned host buffers: actions H2D, obs+masks D2H every step, host-side policy"},
+            "gpu_launches": K * 3, "clocks": clocks,
+            "collective": {"all_gather_us": gather_us, "bytes_per_table": 20},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+
+    cores = host_cores()
+    nonces, keys = seeds_for_rank(0, N_TABLES)
+    n = args.ref_tables
+    r = O.run_batch(nonces[:n], keys[:n], shuffle_kind=0, policy_kind=1, quick_eval=True, encode_obs=4, sp_mode=1,
+                    n_threads=cores, max_steps=args.ref_steps_per_table)
+    return {"value": r["table_steps"] / r["seconds"], "unit": "table-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n} tables x first {args.ref_steps_per_table} table-steps, v4 obs + SP encode per decision, {r['seconds']:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-tables", type=int, default=256)
+    ap.add_argument("--ref-steps-per-table", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,83 @@
+"""Engines: the decision makers the environment calls back into.
+
+`DeviceEngine` is the zero-copy fast path: it consumes the on-device observation / mask tensors and returns
+on-device actions, with the selection semantics of mortal/engine.py:43-94 (masked dueling Q, greedy argmax or
+epsilon-Boltzmann with top-p). Any object following the reference's duck-typed protocol
+(agent/mortal.rs:54-74, 126-152: `engine_type == 'mortal'`, `react_batch(list[np], list[np], None)`)
+still works through `HostProtocolEngine`, which pays the device->host->device round trip the reference pays.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class DeviceEngine:
+    engine_type = "mortal"
+
+    def __init__(self, brain, dqn, *, version=4, device=None, enable_amp=True, enable_quick_eval=True,
+                 enable_rule_based_agari_guard=False, name="NoName", boltzmann_epsilon=0.0, boltzmann_temp=1.0,
+                 top_p=1.0, is_oracle=False):
+        self.device = device or torch.device("cuda")
+        self.brain = brain.to(self.device).eval()
+        self.dqn = dqn.to(self.device).eval()
+        self.version = version
+        self.is_oracle = is_oracle
+        self.enable_amp = enable_amp
+        self.enable_quick_eval = enable_quick_eval
+        self.enable_rule_based_agari_guard = enable_rule_based_agari_guard
+        self.name = name
+        self.boltzmann_epsilon = boltzmann_epsilon
+        self.boltzmann_temp = boltzmann_temp
+        self.top_p = top_p
+
+    @torch.inference_mode()
+    def react_device(self, obs: torch.Tensor, masks: torch.Tensor):
+        """obs [B, C, 34] f32 cuda, masks [B, 46] bool cuda -> (actions int64 [B], q [B, 46])"""
+        with torch.autocast(self.device.type, enabled=self.enable_amp):
+            q = self.dqn(self.brain(obs), masks)
+        if self.boltzmann_epsilon > 0:
+            b = obs.shape[0]
+            greedy = torch.full((b,), 1 - self.boltzmann_epsilon, device=self.device).bernoulli().to(torch.bool)
+            logits = (q / self.boltzmann_temp).masked_fill(~masks, -torch.inf)
+            sampled = sample_top_p(logits, self.top_p)
+            actions = torch.where(greedy, q.argmax(-1), sampled)
+        else:
+            actions = q.argmax(-1)
+        return actions, q
+
+    # the reference protocol, for callers that only know libriichi's calling convention
+    def react_batch(self, obs, masks, invisible_obs):
+        o = torch.as_tensor(np.stack(obs, axis=0), device=self.device)
+        m = torch.as_tensor(np.stack(masks, axis=0), device=self.device)
+        actions, q = self.react_device(o, m)
+        return actions.tolist(), q.float().tolist(), m.tolist(), [True] * o.shape[0]
+
+
+def sample_top_p(logits, p):
+    if p >= 1:
+        return torch.distributions.Categorical(logits=logits).sample()
+    if p <= 0:
+        return logits.argmax(-1)
+    probs = logits.softmax(-1)
+    srt, idx = probs.sort(-1, descending=True)
+    csum = srt.cumsum(-1)
+    srt = srt.masked_fill(csum - srt > p, 0.0)
+    return idx.gather(-1, srt.multinomial(1)).squeeze(-1)
+
+
+class HostProtocolEngine:
+    """Adapter: drives a reference-style engine (react_batch over lists of numpy arrays) from device rows."""
+
+    def __init__(self, engine):
+        assert getattr(engine, "engine_type", None) == "mortal", "only engine_type='mortal' is supported"
+        self.engine = engine
+        for attr in ("name", "version", "is_oracle", "enable_quick_eval", "enable_rule_based_agari_guard"):
+            setattr(self, attr, getattr(engine, attr))
+
+    def react_device(self, obs: torch.Tensor, masks: torch.Tensor):
+        obs_h = obs.cpu().numpy()
+        masks_h = masks.cpu().numpy()
+        actions, q, _, _ = self.engine.react_batch(list(obs_h), list(masks_h), None)
+        dev = obs.device
+        return torch.as_tensor(actions, dtype=torch.int64, device=dev), torch.as_tensor(q, dtype=torch.float32, device=dev)

@@ -1,0 +1,121 @@
+"""libriichi.arena — OneVsThree / TwoVsTwo on the CUDA environment.
+
+Call-compatible with arena/one_vs_three.rs:17-113 and arena/two_vs_two.rs:17-110 for the `py_vs_py` entry
+(the one mortal/player.py:64-69,142-147 and mortal/one_vs_three.py:88-93 use). Seat / seed layout:
+one_vs_three.rs:140-191 (game g = 4*s + r uses seed (seed_start[0] + s, seed_start[1]); the challenger
+sits at absolute seat r). The step loop is BatchGame::run (game.rs:286-304) executed by mjx kernels;
+engines are called once per cycle per agent like MortalBatchAgent::evaluate (mortal.rs:114-159).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..engine import DeviceEngine, HostProtocolEngine
+from ..env import BatchEnv
+
+
+def _adapt(engine):
+    if hasattr(engine, "react_device"):
+        return engine
+    return HostProtocolEngine(engine)
+
+
+class _Arena:
+    SEATS_PER_SEED = 4
+
+    def __init__(self, *, disable_progress_bar: bool = False, log_dir=None, shuffle_kind: int = 0, device: int = 0):
+        self.disable_progress_bar = disable_progress_bar
+        self.log_dir = log_dir
+        self.shuffle_kind = shuffle_kind
+        self.device = device
+        self.last_stats = None
+        if log_dir is not None:
+            raise NotImplementedError("mjai log emission (SURVEY.md §8f N1) is not built in this round")
+
+    def _challenger_seats(self, game_in_seed: int):
+        raise NotImplementedError
+
+    def _run(self, challenger, champion, seed_start, seed_count):
+        import torch
+
+        agents = [_adapt(challenger), _adapt(champion)]
+        for a in agents:
+            if getattr(a, "enable_rule_based_agari_guard", False):
+                raise NotImplementedError("enable_rule_based_agari_guard is not implemented on the device path yet")
+            if getattr(a, "is_oracle", False):
+                raise NotImplementedError("oracle (invisible) observations are out of this round's scope")
+            if getattr(a, "version", 4) != 4:
+                raise NotImplementedError("only obs version 4 is implemented on device")
+        qe = [bool(getattr(a, "enable_quick_eval", True)) for a in agents]
+        if qe[0] != qe[1]:
+            raise NotImplementedError("challenger and champion must agree on enable_quick_eval")
+        per = self.GAMES_PER_SEED
+        n = int(seed_count) * per
+        nonces = np.repeat(np.arange(seed_start[0], seed_start[0] + int(seed_count), dtype=np.uint64), per)
+        keys = np.full(n, seed_start[1], dtype=np.uint64)
+        env = BatchEnv(nonces, keys, obs_version=4, shuffle_kind=self.shuffle_kind, enable_quick_eval=qe[0],
+                       device=self.device)
+        dev = env.device
+        # seat -> agent index table per game-in-seed
+        is_challenger = torch.zeros((per, 4), dtype=torch.bool, device=dev)
+        for g in range(per):
+            for s in self._challenger_seats(g):
+                is_challenger[g, s] = True
+        actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
+        first = True
+        cycles = 0
+        while True:
+            env.step(None if first else actions)
+            first = False
+            nr = env.num_rows()
+            if nr == 0 and env.num_live() == 0:
+                break
+            if nr > 0:
+                obs = env.encode_obs()[:nr]
+                masks = env.masks[:nr]
+                tbl = env.row_table[:nr].long()
+                seat = (env.row_seat[:nr] & 3).long()
+                chal = is_challenger[tbl % per, seat]
+                for idx, agent in ((chal.nonzero().squeeze(1), agents[0]), ((~chal).nonzero().squeeze(1), agents[1])):
+                    if idx.numel() == 0:
+                        continue
+                    a, _ = agent.react_device(obs[idx], masks[idx])
+                    actions[idx] = a.to(torch.int64)
+            cycles += 1
+        res = env.results()
+        self.last_stats = dict(cycles=cycles, table_steps=int(res["steps"].sum()))
+        env.close()
+        if (res["err"] != 0).any():
+            bad = int(np.nonzero(res["err"])[0][0])
+            raise RuntimeError(f"table {bad} failed with mjx error code {int(res['err'][bad])}")
+        return res
+
+    def ako_vs_py(self, *a, **k):
+        raise NotImplementedError("akochan subprocess agents are out of scope (SURVEY.md §2.1 row 5)")
+
+    py_vs_ako = ako_vs_py
+
+
+class OneVsThree(_Arena):
+    GAMES_PER_SEED = 4
+
+    def _challenger_seats(self, g):
+        return [g % 4]
+
+    def py_vs_py(self, challenger, champion, seed_start, seed_count):
+        res = self._run(challenger, champion, seed_start, seed_count)
+        rankings = [0, 0, 0, 0]
+        for i in range(res["ranks"].shape[0]):  # one_vs_three.rs:55-60
+            rankings[int(res["ranks"][i, i % 4])] += 1
+        return rankings
+
+
+class TwoVsTwo(_Arena):
+    GAMES_PER_SEED = 2
+
+    def _challenger_seats(self, g):
+        return [0, 2] if g % 2 == 0 else [1, 3]  # two_vs_two.rs:137-191
+
+    def py_vs_py(self, challenger, champion, seed_start, seed_count):
+        self._run(challenger, champion, seed_start, seed_count)
+        return None

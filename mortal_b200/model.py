@@ -1,0 +1,80 @@
+"""Policy/value network used by the benchmark and examples (stays ordinary PyTorch, as north_star asks).
+
+Architecture restated from mortal/model.py:10-231 (version 4): Conv1d stem -> `num_blocks` pre-activation
+residual blocks (BN -> Mish -> Conv1d k3, twice) each gated by a squeeze/excite style channel attention
+-> BN -> Mish -> Conv1d(C, 32, k3) -> Mish -> Linear(32*34, 1024) -> Mish ; dueling head Linear(1024, 1+46)
+with the advantage mean taken over legal actions only and illegal actions at -inf. Real Mortal checkpoints
+load into mortal/model.py unchanged; this module exists so bench.py does not depend on /root/reference.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+OBS_ROWS = {1: 938, 2: 942, 3: 934, 4: 1012}  # consts.rs:20-28
+ACTION_SPACE = 46
+
+
+class ChannelGate(nn.Module):
+    def __init__(self, channels: int, ratio: int = 16):
+        super().__init__()
+        self.fc1 = nn.Linear(channels, channels // ratio)
+        self.fc2 = nn.Linear(channels // ratio, channels)
+        nn.init.zeros_(self.fc1.bias)
+        nn.init.zeros_(self.fc2.bias)
+        self.act = nn.Mish(inplace=True)
+
+    def _mlp(self, v):
+        return self.fc2(self.act(self.fc1(v)))
+
+    def forward(self, x):
+        gate = torch.sigmoid(self._mlp(x.mean(-1)) + self._mlp(x.amax(-1)))
+        return x * gate.unsqueeze(-1)
+
+
+class PreActBlock(nn.Module):
+    def __init__(self, channels: int):
+        super().__init__()
+        self.bn1 = nn.BatchNorm1d(channels, momentum=0.01, eps=1e-3)
+        self.conv1 = nn.Conv1d(channels, channels, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm1d(channels, momentum=0.01, eps=1e-3)
+        self.conv2 = nn.Conv1d(channels, channels, 3, padding=1, bias=False)
+        self.act = nn.Mish(inplace=True)
+        self.gate = ChannelGate(channels)
+
+    def forward(self, x):
+        y = self.conv1(self.act(self.bn1(x)))
+        y = self.conv2(self.act(self.bn2(y)))
+        return self.gate(y) + x
+
+
+class Brain(nn.Module):
+    def __init__(self, *, conv_channels: int = 192, num_blocks: int = 40, version: int = 4):
+        super().__init__()
+        assert version == 4, "only the version-4 network is restated here"
+        self.version = version
+        c = conv_channels
+        self.stem = nn.Conv1d(OBS_ROWS[version], c, 3, padding=1, bias=False)
+        self.blocks = nn.Sequential(*[PreActBlock(c) for _ in range(num_blocks)])
+        self.bn = nn.BatchNorm1d(c, momentum=0.01, eps=1e-3)
+        self.act = nn.Mish(inplace=True)
+        self.neck = nn.Conv1d(c, 32, 3, padding=1)
+        self.fc = nn.Linear(32 * 34, 1024)
+
+    def forward(self, obs):
+        x = self.blocks(self.stem(obs))
+        x = self.act(self.neck(self.act(self.bn(x))))
+        return self.act(self.fc(x.flatten(1)))
+
+
+class DQN(nn.Module):
+    def __init__(self, *, version: int = 4):
+        super().__init__()
+        assert version == 4
+        self.net = nn.Linear(1024, 1 + ACTION_SPACE)
+        nn.init.zeros_(self.net.bias)
+
+    def forward(self, phi, mask):
+        v, a = self.net(phi).split((1, ACTION_SPACE), dim=-1)
+        a_mean = a.masked_fill(~mask, 0.0).sum(-1, keepdim=True) / mask.sum(-1, keepdim=True)
+        return (v + a - a_mean).masked_fill(~mask, -torch.inf)

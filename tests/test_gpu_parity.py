@@ -128,7 +128,7 @@ def test_agari_kernel_bit_exact(mjx, mode):
     for f in ("kind", "fu", "han", "yakuman", "ron", "tsumo_ko", "tsumo_oya"):
         bad = np.nonzero(out[f] != ref[f])[0]
         assert len(bad) == 0, (f, bad[:5], out[bad[:5]], ref[bad[:5]])
-    assert (ref["kind"] != 0).mean() > 0.5
+    assert (ref["kind"] != 0).mean() > 0.4
 
 
 def test_wall_kernel_matches_oracle(mjx):
