@@ -72,22 +72,37 @@ __global__ void k_init_tables(TableState* tabs, int n, const u64* nonces, const 
     err[t] = 0;
 }
 
-// Observation tile: built in shared memory, leaves as one bulk async copy (TMA).
+// Observation half-tile: built in shared memory, leaves as one bulk async copy (TMA).
 constexpr int ENC_THREADS = 256;
-constexpr size_t ENC_TILE_BYTES = (size_t)OBS_ROWS_V4 * OBS_COLS * sizeof(float);  // 137,632
-constexpr size_t ENC_SMEM_BYTES = ENC_TILE_BYTES + 64;
+constexpr int ENC_HALF_ROWS_MAX = OBS_SPLIT_ROW;  // 522 rows (first half) >= 490 rows (second half)
+constexpr size_t ENC_TILE_BYTES = (size_t)ENC_HALF_ROWS_MAX * OBS_COLS * sizeof(float);  // 70,992
+constexpr size_t ENC_STATE_OFF = ENC_TILE_BYTES;
+constexpr size_t ENC_SMEM_BYTES = ENC_TILE_BYTES + sizeof(TableState) + 64;  // ~73 KB -> 3 CTAs / SM
+static_assert((OBS_SPLIT_ROW * OBS_COLS * sizeof(float)) % 16 == 0, "half boundary must be 16-byte aligned");
+static_assert(((OBS_ROWS_V4 - OBS_SPLIT_ROW) * OBS_COLS * sizeof(float)) % 16 == 0, "second half must be 16-byte sized");
 
-__global__ void __launch_bounds__(ENC_THREADS, 1) k_encode_obs_v4(EnvView V, Tables T, float* __restrict__ obs) {
+__global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_obs_v4(EnvView V, Tables T, float* __restrict__ obs) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     float* tile = reinterpret_cast<float*>(s_raw);
-    u8* df = s_raw + ENC_TILE_BYTES;
+    TableState* s_state = reinterpret_cast<TableState*>(s_raw + ENC_STATE_OFF);
+    u8* df = s_raw + ENC_STATE_OFF + sizeof(TableState);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_rows = *V.n_rows;
-    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
-        uint4* t4 = reinterpret_cast<uint4*>(tile);
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < (int)(ENC_TILE_BYTES / 16); i += ENC_THREADS) t4[i] = z;
-        const TableState* S = V.tables + V.row_table[row];
+    const int n_items = *V.n_rows * 2;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int row = item >> 1, half = item & 1;
+        const int row_lo = half ? OBS_SPLIT_ROW : 0, row_hi = half ? OBS_ROWS_V4 : OBS_SPLIT_ROW;
+        const int tile_bytes = (row_hi - row_lo) * OBS_COLS * (int)sizeof(float);
+        // stage the table record (coalesced 16-byte loads) and clear the half-tile
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(V.tables + V.row_table[row]);
+            uint4* dst = reinterpret_cast<uint4*>(s_state);
+            for (int i = tid; i < (int)(sizeof(TableState) / 16); i += ENC_THREADS) dst[i] = __ldg(src + i);
+            uint4* t4 = reinterpret_cast<uint4*>(tile);
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (int i = tid; i < tile_bytes / 16; i += ENC_THREADS) t4[i] = z;
+        }
+        __syncthreads();
+        const TableState* S = s_state;
         const int seat = V.row_seat[row] & 3;
         const bool kan = (V.row_seat[row] >> 2) & 1;
         if (tid < 34) {
@@ -99,17 +114,18 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_encode_obs_v4(EnvView V, Tab
         EncCtx e;
         e.S = S; e.T = T; e.tile = tile; e.seat = seat; e.kan_select = kan;
         e.lane = lane; e.warp = warp; e.nwarps = ENC_THREADS / 32; e.dora_factor = df;
+        e.row_lo = row_lo; e.row_hi = row_hi;
         Ctx c;
-        c.S = const_cast<TableState*>(S); c.W = nullptr; c.T = T; c.lane = lane;
+        c.S = s_state; c.W = nullptr; c.T = T; c.lane = lane;
         encode_obs_v4(e, c, nullptr);
         // make the generic-proxy smem writes visible to the async proxy, then one thread issues the bulk store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
-            float* dst = obs + (size_t)row * OBS_ROWS_V4 * OBS_COLS;
+            float* dst = obs + ((size_t)row * OBS_ROWS_V4 + row_lo) * OBS_COLS;
             unsigned smem_addr = (unsigned)__cvta_generic_to_shared(tile);
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                         :: "l"(dst), "r"(smem_addr), "r"((unsigned)ENC_TILE_BYTES) : "memory");
+                         :: "l"(dst), "r"(smem_addr), "r"((unsigned)tile_bytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
@@ -346,7 +362,7 @@ int mjx_env_step(mjx_env* env, const int64_t* actions_dev, void* stream) {
 int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
     if (!env || !obs_dev) return fail(MJX_ERR_ARG, "mjx_env_encode_obs: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    k_encode_obs_v4<<<g_sm_count, ENC_THREADS, ENC_SMEM_BYTES, st>>>(env->V, g_T, obs_dev);
+    k_encode_obs_v4<<<g_sm_count * 3, ENC_THREADS, ENC_SMEM_BYTES, st>>>(env->V, g_T, obs_dev);
     CU(cudaGetLastError());
     return MJX_OK;
 }

@@ -23,17 +23,26 @@ struct EncCtx {
     bool kan_select;
     int lane, warp, nwarps;
     const u8* dora_factor;  // [34]
+    int row_lo, row_hi;     // this CTA builds obs rows [row_lo, row_hi); tile points at row_lo
 };
 
+// An observation is built as two half-tiles (rows [0,522) and [522,1012)) by different CTAs so that three
+// CTAs fit one SM and tile assembly overlaps the bulk stores of the others. The split falls on a section
+// boundary: sections 0-5 (+2a) live in the first half, 6-10 (+2b) in the second.
+constexpr int OBS_SPLIT_ROW = 522;
+
+// rows are addressed absolutely; ENC_AT maps them into the CTA's window
+#define ENC_AT(e, row, col) (e).tile[((row) - (e).row_lo) * 34 + (col)]
+#define ENC_HALF(e, first_half) ((first_half) ? (e).row_lo < OBS_SPLIT_ROW : (e).row_hi > OBS_SPLIT_ROW)
 #ifdef MJX_HOST_EMUL
-#define ENC_SECTION(e, k) (true)
-#define ENC_FILL(e, row, v) do { for (int c_ = 0; c_ < 34; c_++) (e).tile[(row) * 34 + c_] = (v); } while (0)
-#define ENC_ASSIGN(e, row, col, v) do { (e).tile[(row) * 34 + (col)] = (v); } while (0)
+#define ENC_SECTION(e, k, first_half) ENC_HALF(e, first_half)
+#define ENC_FILL(e, row, v) do { for (int c_ = 0; c_ < 34; c_++) ENC_AT(e, row, c_) = (v); } while (0)
+#define ENC_ASSIGN(e, row, col, v) do { ENC_AT(e, row, col) = (v); } while (0)
 #define ENC_SYNCWARP() ((void)0)
 #else
-#define ENC_SECTION(e, k) (((k) % (e).nwarps) == (e).warp)
-#define ENC_FILL(e, row, v) do { (e).tile[(row) * 34 + (e).lane] = (v); if ((e).lane < 2) (e).tile[(row) * 34 + 32 + (e).lane] = (v); } while (0)
-#define ENC_ASSIGN(e, row, col, v) do { if ((e).lane == 0) (e).tile[(row) * 34 + (col)] = (v); } while (0)
+#define ENC_SECTION(e, k, first_half) (ENC_HALF(e, first_half) && (((k) % (e).nwarps) == (e).warp))
+#define ENC_FILL(e, row, v) do { ENC_AT(e, row, (e).lane) = (v); if ((e).lane < 2) ENC_AT(e, row, 32 + (e).lane) = (v); } while (0)
+#define ENC_ASSIGN(e, row, col, v) do { if ((e).lane == 0) ENC_AT(e, row, col) = (v); } while (0)
 #define ENC_SYNCWARP() __syncwarp()
 #endif
 
@@ -72,7 +81,7 @@ MJX_D void enc_tile_set(EncCtx& e, int row, int n, F get) {
         for (int i = 0; i < n; i++) {
             int tile = get(i);
             int tid = deaka(tile);
-            e.tile[(row + counts[tid]) * 34 + tid] = 1.f;
+            ENC_AT(e, row + counts[tid], tid) = 1.f;
             counts[tid]++;
         }
     }
@@ -143,14 +152,14 @@ MJX_DN void encode_obs_v4(EncCtx& e, const Ctx& c, u64* mask_out) {
     const u8* df = e.dora_factor;
 
     // ---- section 0: hand (rows 0-6)
-    if (ENC_SECTION(e, 0)) {
+    if (ENC_SECTION(e, 0, true)) {
         MJX_FOR_TILES(e, t) {
-            for (int n = 0; n < P.tehai[t]; n++) e.tile[n * 34 + t] = 1.f;
+            for (int n = 0; n < P.tehai[t]; n++) ENC_AT(e, n, t) = 1.f;
         }
         for (int k = 0; k < 3; k++) if ((P.akas_in_hand >> k) & 1) ENC_FILL(e, 4 + k, 1.f);
     }
     // ---- section 1: scalars (rows 7-27)
-    if (ENC_SECTION(e, 1)) {
+    if (ENC_SECTION(e, 1, true)) {
         int rank = 0;
         for (int i = 0; i < 4; i++) {
             i32 sc = S->scores[rel_to_abs(p, i)];
@@ -169,9 +178,10 @@ MJX_DN void encode_obs_v4(EncCtx& e, const Ctx& c, u64* mask_out) {
         int gk = min(bakaze - T_E, 1) * 4 + kyoku_in_wind;
         ENC_FILL(e, 27, (float)min(gk, 7) / 7.f);
     }
-    // ---- section 2: dora indicators, counters (rows 28-34, 717-722)
-    if (ENC_SECTION(e, 2)) {
-        enc_tile_set(e, 28, S->n_dora, [&](int i) { return dora_indicator(S, i); });
+    // ---- section 2a: dora indicators (rows 28-34)
+    if (ENC_SECTION(e, 2, true)) enc_tile_set(e, 28, S->n_dora, [&](int i) { return dora_indicator(S, i); });
+    // ---- section 2b: counters (rows 717-722)
+    if (ENC_SECTION(e, 5, false)) {
         ENC_FILL(e, 717, (float)S->tiles_left / 69.f);
         int seen_doras = mjx_popc((u32)(S->akas_public | P.akas_in_hand));
         for (int t = 0; t < 34; t++) seen_doras += (S->public_seen[t] + P.tehai[t]) * df[t];
@@ -202,7 +212,7 @@ MJX_DN void encode_obs_v4(EncCtx& e, const Ctx& c, u64* mask_out) {
     for (int s = 0; s < 4; s++) max_kawa_len = max(max_kawa_len, kawa_view(S, p, s).len());
 
     // ---- section 3: own pond (rows 35-131)
-    if (ENC_SECTION(e, 3)) {
+    if (ENC_SECTION(e, 3, true)) {
         const KawaView kv = kawa_view(S, p, p);
         const int len = kv.len();
         for (int pass = 0; pass < 2; pass++) {
@@ -224,7 +234,7 @@ MJX_DN void encode_obs_v4(EncCtx& e, const Ctx& c, u64* mask_out) {
     }
     // ---- sections 4-6: the three opponents' ponds (rows 132-716)
     for (int rel = 1; rel < 4; rel++) {
-        if (!ENC_SECTION(e, 3 + rel)) continue;
+        if (!ENC_SECTION(e, rel == 3 ? 0 : 3 + rel, rel != 3)) continue;
         const KawaView kv = kawa_view(S, p, rel_to_abs(p, rel));
         const int len = kv.len();
         const int sec = 132 + 195 * (rel - 1);
@@ -257,7 +267,7 @@ MJX_DN void encode_obs_v4(EncCtx& e, const Ctx& c, u64* mask_out) {
         }
     }
     // ---- section 7: kawa overview (rows 723-750)
-    if (ENC_SECTION(e, 7)) {
+    if (ENC_SECTION(e, 1, false)) {
         for (int i = 0; i < 4; i++) {
             const SeatPublic& U = S->pub[rel_to_abs(p, i)];
             // real discards only, in order (update.rs:336)
@@ -267,7 +277,7 @@ MJX_DN void encode_obs_v4(EncCtx& e, const Ctx& c, u64* mask_out) {
         }
     }
     // ---- section 8: melds (rows 751-834)
-    if (ENC_SECTION(e, 8)) {
+    if (ENC_SECTION(e, 2, false)) {
         for (int i = 0; i < 4; i++) {
             const SeatPublic& U = S->pub[rel_to_abs(p, i)];
             for (int f = 0; f < U.n_fuuro; f++) {
@@ -285,10 +295,10 @@ MJX_DN void encode_obs_v4(EncCtx& e, const Ctx& c, u64* mask_out) {
         }
     }
     // ---- section 9: seen tiles, key discards, riichi / wait status (rows 835-873)
-    if (ENC_SECTION(e, 9)) {
+    if (ENC_SECTION(e, 3, false)) {
         MJX_FOR_TILES(e, t) {
-            e.tile[835 * 34 + t] = (float)(S->public_seen[t] + P.tehai[t]) / 4.f;
-            if ((P.waits >> t) & 1) e.tile[860 * 34 + t] = 1.f;
+            ENC_AT(e, 835, t) = (float)(S->public_seen[t] + P.tehai[t]) / 4.f;
+            if ((P.waits >> t) & 1) ENC_AT(e, 860, t) = 1.f;
         }
         for (int rel = 1; rel < 4; rel++) {
             const SeatPublic& U = S->pub[rel_to_abs(p, rel)];
@@ -319,19 +329,20 @@ MJX_DN void encode_obs_v4(EncCtx& e, const Ctx& c, u64* mask_out) {
         }
     }
     // ---- section 10: the action block (rows 874-888) + legal mask
-    const u64 discards = (cans & CAN_DISCARD) ? discard_candidates(c, p) : 0;  // collective: every warp runs it
-    if (mask_out) *mask_out = legal_mask(c, p, e.kan_select, discards);
-    if (ENC_SECTION(e, 10)) {
+    const bool second = ENC_HALF(e, false);
+    const u64 discards = (second && (cans & CAN_DISCARD)) ? discard_candidates(c, p) : 0;  // collective, every warp
+    if (mask_out && second) *mask_out = legal_mask(c, p, e.kan_select, discards);
+    if (ENC_SECTION(e, 4, false)) {
         if (cans & CAN_DISCARD) {
             u64 d34 = (discards & ((1ull << 34) - 1)) | (((discards >> 34) & 1) << 4) | (((discards >> 35) & 1) << 13) |
                       (((discards >> 36) & 1) << 22);
             u64 ut = 0;
             if (P.shanten <= 1) ut = unconditional_tenpai_discards(e, c);
             MJX_FOR_TILES(e, t) {
-                if ((d34 >> t) & 1) e.tile[874 * 34 + t] = 1.f;
-                if ((P.keep_shanten >> t) & 1) e.tile[875 * 34 + t] = 1.f;
-                if ((P.next_shanten >> t) & 1) e.tile[876 * 34 + t] = 1.f;
-                if ((ut >> t) & 1) e.tile[877 * 34 + t] = 1.f;
+                if ((d34 >> t) & 1) ENC_AT(e, 874, t) = 1.f;
+                if ((P.keep_shanten >> t) & 1) ENC_AT(e, 875, t) = 1.f;
+                if ((P.next_shanten >> t) & 1) ENC_AT(e, 876, t) = 1.f;
+                if ((ut >> t) & 1) ENC_AT(e, 877, t) = 1.f;
             }
             if ((S->riichi_declared >> p) & 1) ENC_FILL(e, 878, 1.f);
         }
@@ -342,8 +353,8 @@ MJX_DN void encode_obs_v4(EncCtx& e, const Ctx& c, u64* mask_out) {
         if (cans & CAN_PON) ENC_FILL(e, 883, 1.f);
         if (cans & CAN_DAIMINKAN) ENC_FILL(e, 884, 1.f);
         MJX_FOR_TILES(e, t) {
-            if ((cans & CAN_ANKAN) && ((P.ankan_cand >> t) & 1)) e.tile[885 * 34 + t] = 1.f;
-            if ((cans & CAN_KAKAN) && ((P.kakan_cand >> t) & 1)) e.tile[886 * 34 + t] = 1.f;
+            if ((cans & CAN_ANKAN) && ((P.ankan_cand >> t) & 1)) ENC_AT(e, 885, t) = 1.f;
+            if ((cans & CAN_KAKAN) && ((P.kakan_cand >> t) & 1)) ENC_AT(e, 886, t) = 1.f;
         }
         if (cans & CAN_AGARI) ENC_FILL(e, 887, 1.f);
         if (cans & CAN_RYUKYOKU) ENC_FILL(e, 888, 1.f);

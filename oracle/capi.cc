@@ -7,6 +7,7 @@
 #include <chrono>
 #include <thread>
 
+namespace orc { extern long g_sp_stats[8]; }
 using namespace orc;
 
 namespace {
@@ -506,6 +507,8 @@ int orc_run_batch(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t
         return 0;
     } catch (const std::exception& e) { return fail(e); }
 }
+
+void orc_sp_stats(long* out) { for (int i = 0; i < 8; i++) { out[i] = orc::g_sp_stats[i]; orc::g_sp_stats[i] = 0; } }
 
 uint64_t orc_policy_hash(uint64_t nonce, uint64_t key, uint64_t table, uint64_t step_idx, uint32_t seat, uint32_t kan) {
     return policy_hash(nonce, key, table, step_idx, seat, kan);

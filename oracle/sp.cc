@@ -11,6 +11,8 @@
 
 namespace orc {
 
+long g_sp_stats[8] = {0,0,0,0,0,0,0,0};  // calls, sum states, max states, calls>1k, >10k, >100k
+
 namespace {
 
 const int SHANTEN_THRES = 3;                   // calc.rs:13
@@ -551,7 +553,14 @@ std::vector<SpCandidate> SpCalculator::calc(const SpInitState& init, bool can_di
     st.n_extra_tsumo = 0;
     int n_left = sum_left_tiles(st);
     CalcState cs(*this, st, tsumos_left, n_left);
-    return cs.calc(can_discard, cur_shanten);
+    auto ret = cs.calc(can_discard, cur_shanten);
+    long n = 0;
+    for (int i = 0; i <= SHANTEN_THRES; i++) n += (long)cs.discard_cache[i].size() + (long)cs.draw_cache[i].size();
+    g_sp_stats[0]++; g_sp_stats[1] += n; if (n > g_sp_stats[2]) g_sp_stats[2] = n;
+    if (n > 1000) g_sp_stats[3]++;
+    if (n > 10000) g_sp_stats[4]++;
+    if (n > 100000) g_sp_stats[5]++;
+    return ret;
 }
 
 // agent_helper.rs:509-593

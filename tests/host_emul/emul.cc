@@ -188,6 +188,10 @@ void emul_env_encode_obs(void* p, float* obs) {
         e.S = S; e.T = g_T; e.tile = tile; e.seat = E->row_seat[r] & 3; e.kan_select = (E->row_seat[r] >> 2) & 1;
         e.lane = 0; e.warp = 0; e.nwarps = 1; e.dora_factor = df;
         Ctx c; c.S = const_cast<TableState*>(S); c.W = nullptr; c.T = g_T; c.lane = 0;
+        // built as the two half-tiles the CUDA kernel builds
+        e.row_lo = 0; e.row_hi = OBS_SPLIT_ROW; e.tile = tile;
+        encode_obs_v4(e, c, nullptr);
+        e.row_lo = OBS_SPLIT_ROW; e.row_hi = OBS_ROWS_V4; e.tile = tile + (size_t)OBS_SPLIT_ROW * OBS_COLS;
         encode_obs_v4(e, c, nullptr);
     }
 }

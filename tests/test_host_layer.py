@@ -1,0 +1,105 @@
+"""CPU-only checks of the host layer: the C ABI library loads and exports every declared symbol, fails loudly
+without a GPU (no CPU fallback), the libriichi mirror has the reference's surface, and the N>1 plumbing
+(seed sharding + the all-gather of returns) works over gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    import mortal_b200
+    from mortal_b200 import _lib
+
+    L = mortal_b200.load()
+    header = open(os.path.join(ROOT, "include", "mjx.h")).read()
+    declared = set(re.findall(r"\b(mjx_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mjx_status"}
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(L, name), f"libmjx.so does not export {name}"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert C.sizeof(_lib.AgariIn) == 62 and C.sizeof(_lib.AgariOut) == 16
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import mortal_b200
+    from mortal_b200 import _lib
+
+    L = mortal_b200.load()
+    rc = L.mjx_init(_lib.DATA_DIR.encode(), 0)
+    assert rc != 0 and b"no CUDA device" in L.mjx_last_error()
+    with pytest.raises(mortal_b200.MjxError):
+        mortal_b200.BatchEnv(np.array([1], dtype=np.uint64), np.array([2], dtype=np.uint64))
+    out = np.zeros(1, dtype=np.int8)
+    assert L.mjx_shanten_host(np.zeros(34, dtype=np.uint8).ctypes.data, np.zeros(1, dtype=np.uint8).ctypes.data,
+                              out.ctypes.data, 1) != 0
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ and tests/host_emul are test infrastructure: nothing under mortal_b200/ may reference them."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mortal_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in src and "oracle_lib" not in src and "libmjx_emul" not in src, f
+                if f.endswith(".py"):
+                    assert "emul_lib" not in src, f
+
+
+def test_libriichi_mirror_surface():
+    import mortal_b200.libriichi as lr
+
+    lr.install()
+    from libriichi.arena import OneVsThree, TwoVsTwo
+    from libriichi.consts import ACTION_SPACE, GRP_SIZE, MAX_VERSION, obs_shape, oracle_obs_shape
+
+    assert (ACTION_SPACE, GRP_SIZE, MAX_VERSION) == (46, 7, 4)
+    assert [obs_shape(v) for v in (1, 2, 3, 4)] == [(938, 34), (942, 34), (934, 34), (1012, 34)]
+    assert oracle_obs_shape(1) == (211, 34) and oracle_obs_shape(4) == (217, 34)
+    env = OneVsThree(disable_progress_bar=True, log_dir=None)
+    assert hasattr(env, "py_vs_py") and hasattr(TwoVsTwo(), "py_vs_py")
+    assert env._challenger_seats(6) == [2] and TwoVsTwo()._challenger_seats(1) == [1, 3]
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from mortal_b200.dist import shard_seeds, gather_returns
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+nonces, keys = shard_seeds((10000, 0x2000), 8, rank)
+assert nonces[0] == 10000 + 8 * rank and len(nonces) == 32 and (keys == 0x2000).all()
+scores = (np.arange(32 * 4, dtype=np.int32).reshape(32, 4) + 1000 * rank) - 500
+ranks = np.tile(np.array([[(0 + rank) % 4, 1, 2, 3]], dtype=np.uint8), (32, 1))
+s_all, r_all = gather_returns(scores, ranks)
+assert s_all.shape == (32 * world, 4) and r_all.shape == (32 * world, 4)
+for r in range(world):
+    assert (s_all[32 * r: 32 * r + 32] == np.arange(128, dtype=np.int32).reshape(32, 4) + 1000 * r - 500).all()
+    assert (r_all[32 * r: 32 * r + 32, 0] == r % 4).all()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_world_size_2_gloo_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
