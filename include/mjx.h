@@ -52,6 +52,13 @@ int mjx_env_step(mjx_env* env, const int64_t* actions_dev, void* stream);
  * obs_dev = float32 [row_cap, rows(version), 34] (only the first n_rows rows are written). */
 int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream);
 
+/* state/agent_helper.rs:509-593 single_player_tables (obs v4 rows 889-1011): on by default; `enable = 0`
+ * leaves the block zero (the reference has no such switch; it exists for profiling the rest of the encoder).
+ * mjx_env_sp_overflows: number of rows so far whose block was dropped because the per-CTA state arena
+ * (32768 states) overflowed — the reference has no such limit; 0 in every test and benchmark here. */
+int mjx_env_set_sp(mjx_env* env, int enable);
+int mjx_env_sp_overflows(mjx_env* env, void* stream, int* n);
+
 /* Blocking read-backs (synchronise `stream` first). */
 int mjx_env_num_rows(mjx_env* env, void* stream, int* n_rows);          /* rows emitted by the last step */
 int mjx_env_num_live(mjx_env* env, void* stream, int* n_live);          /* tables still playing */

@@ -6,7 +6,7 @@
 #include <vector>
 
 #include "../../include/mjx.h"
-#include "mjx_obs.cuh"
+#include "mjx_sp.cuh"
 #include "mjx_policy.cuh"
 #include "mjx_tables_host.h"
 
@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(EnvView V, Tables T) {
     c.W = &s_scratch[warp];
     c.T = T;
     c.lane = lane;
+    c.df = s_scratch[warp].dora_factor;
     const bool live = step_table(c, V, table);
     __syncwarp();
     uint4* gdst = reinterpret_cast<uint4*>(g);
@@ -81,7 +82,14 @@ constexpr size_t ENC_SMEM_BYTES = ENC_TILE_BYTES + sizeof(TableState) + 64;  // 
 static_assert((OBS_SPLIT_ROW * OBS_COLS * sizeof(float)) % 16 == 0, "half boundary must be 16-byte aligned");
 static_assert(((OBS_ROWS_V4 - OBS_SPLIT_ROW) * OBS_COLS * sizeof(float)) % 16 == 0, "second half must be 16-byte sized");
 
-__global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_obs_v4(EnvView V, Tables T, float* __restrict__ obs) {
+// per-CTA single-player workspace, carved out of flat device arrays (index = blockIdx.x)
+struct SpArena {
+    SpKey* keys; float* vals; u32* edges; u8* n_edges; u32* hash; i32* counters; SpShared* shared;
+    i32* overflow_count;  // [1] rows whose SP block was dropped because the state arena overflowed
+    int enabled;
+};
+
+__global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_obs_v4(EnvView V, Tables T, float* __restrict__ obs, SpArena A) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     float* tile = reinterpret_cast<float*>(s_raw);
     TableState* s_state = reinterpret_cast<TableState*>(s_raw + ENC_STATE_OFF);
@@ -116,8 +124,22 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_obs_v4(EnvView V, Tab
         e.lane = lane; e.warp = warp; e.nwarps = ENC_THREADS / 32; e.dora_factor = df;
         e.row_lo = row_lo; e.row_hi = row_hi;
         Ctx c;
-        c.S = s_state; c.W = nullptr; c.T = T; c.lane = lane;
+        c.S = s_state; c.W = nullptr; c.T = T; c.lane = lane; c.df = df;
         encode_obs_v4(e, c, nullptr);
+        if (half == 1 && A.enabled) {
+            SpCtx sp;
+            const size_t b = blockIdx.x;
+            sp.W.keys = A.keys + b * SP_NODE_CAP;
+            sp.W.vals = A.vals + b * (size_t)SP_NODE_CAP * 3 * SP_T_MAX;
+            sp.W.edges = A.edges + b * (size_t)SP_NODE_CAP * SP_EDGE_MAX;
+            sp.W.n_edges = A.n_edges + b * SP_NODE_CAP;
+            sp.W.hash = A.hash + b * SP_HASH_CAP;
+            sp.W.counters = A.counters + b * 4;
+            sp.sh = A.shared + b;
+            sp.T = T; sp.lane = lane; sp.warp = warp; sp.nwarps = ENC_THREADS / 32;
+            encode_sp_block(e, c, sp);
+            if (tid == 0 && sp.W.counters[1]) atomicAdd(A.overflow_count, 1);
+        }
         // make the generic-proxy smem writes visible to the async proxy, then one thread issues the bulk store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -244,6 +266,8 @@ struct mjx_env {
     EnvView V;
     u64 *d_nonces = nullptr, *d_keys = nullptr;
     i64* d_dummy_actions = nullptr;
+    SpArena sp;
+    int enc_grid = 0;
 };
 
 extern "C" {
@@ -321,6 +345,23 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
     CU(cudaMalloc(&env->d_nonces, sizeof(u64) * (size_t)n_tables));
     CU(cudaMalloc(&env->d_keys, sizeof(u64) * (size_t)n_tables));
     CU(cudaMalloc(&env->d_dummy_actions, sizeof(i64) * cap));
+    memset(&env->sp, 0, sizeof env->sp);
+    env->enc_grid = g_sm_count * 3;
+    {
+        const size_t g = (size_t)env->enc_grid;
+        SpArena& A = env->sp;
+        A.enabled = 1;
+        CU(cudaMalloc(&A.keys, g * SP_NODE_CAP * sizeof(SpKey)));
+        CU(cudaMalloc(&A.vals, g * SP_NODE_CAP * 3 * SP_T_MAX * sizeof(float)));
+        CU(cudaMalloc(&A.edges, g * SP_NODE_CAP * SP_EDGE_MAX * sizeof(u32)));
+        CU(cudaMalloc(&A.n_edges, g * SP_NODE_CAP));
+        CU(cudaMalloc(&A.hash, g * SP_HASH_CAP * sizeof(u32)));
+        CU(cudaMalloc(&A.counters, g * 4 * sizeof(i32)));
+        CU(cudaMalloc(&A.shared, g * sizeof(SpShared)));
+        CU(cudaMalloc(&A.overflow_count, sizeof(i32)));
+        CU(cudaMemset(A.overflow_count, 0, sizeof(i32)));
+        CU(cudaMemset(A.counters, 0, g * 4 * sizeof(i32)));
+    }
     CU(cudaMemset(env->d_dummy_actions, 0, sizeof(i64) * cap));
     CU(cudaMemset(V.masks, 0, cap * ACTION_SPACE));
     CU(cudaMemset(V.scores, 0, sizeof(i32) * 4 * (size_t)n_tables));
@@ -343,6 +384,9 @@ void mjx_env_destroy(mjx_env* env) {
     cudaFree(V.tables); cudaFree(V.n_rows); cudaFree(V.row_table); cudaFree(V.row_seat); cudaFree(V.row_step);
     cudaFree(V.masks); cudaFree(V.scores); cudaFree(V.ranks); cudaFree(V.done); cudaFree(V.steps); cudaFree(V.err);
     cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions);
+    SpArena& A = env->sp;
+    cudaFree(A.keys); cudaFree(A.vals); cudaFree(A.edges); cudaFree(A.n_edges); cudaFree(A.hash); cudaFree(A.counters);
+    cudaFree(A.shared); cudaFree(A.overflow_count);
     delete env;
 }
 
@@ -362,8 +406,21 @@ int mjx_env_step(mjx_env* env, const int64_t* actions_dev, void* stream) {
 int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
     if (!env || !obs_dev) return fail(MJX_ERR_ARG, "mjx_env_encode_obs: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    k_encode_obs_v4<<<g_sm_count * 3, ENC_THREADS, ENC_SMEM_BYTES, st>>>(env->V, g_T, obs_dev);
+    k_encode_obs_v4<<<env->enc_grid, ENC_THREADS, ENC_SMEM_BYTES, st>>>(env->V, g_T, obs_dev, env->sp);
     CU(cudaGetLastError());
+    return MJX_OK;
+}
+
+int mjx_env_set_sp(mjx_env* env, int enable) {
+    if (!env) return fail(MJX_ERR_ARG, "mjx_env_set_sp: null env");
+    env->sp.enabled = enable ? 1 : 0;
+    return MJX_OK;
+}
+
+int mjx_env_sp_overflows(mjx_env* env, void* stream, int* n) {
+    if (!env || !n) return fail(MJX_ERR_ARG, "mjx_env_sp_overflows: bad arguments");
+    CU(cudaMemcpyAsync(n, env->sp.overflow_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
     return MJX_OK;
 }
 

@@ -42,6 +42,7 @@ struct Ctx {
     WarpScratch* W;
     Tables T;
     int lane;
+    const u8* df;  // dora_factor[34] of the current record (k_step: W->dora_factor; encoder: its own copy)
 };
 
 MJX_D void set_err(Ctx& c, i32 e) {
@@ -361,7 +362,7 @@ MJX_DN void ev_dahai(Ctx& c, int actor, int pai, bool tsumogiri) {
         public_witness(S, pai);
         KawaItem it;
         it.tile = (u8)pai;
-        it.flags = (u8)((c.W->dora_factor[pid] > 0 ? SF_DORA : 0) | (!tsumogiri ? SF_TEDASHI : 0) | (is_riichi ? SF_RIICHI : 0) |
+        it.flags = (u8)((c.df[pid] > 0 ? SF_DORA : 0) | (!tsumogiri ? SF_TEDASHI : 0) | (is_riichi ? SF_RIICHI : 0) |
                         ((S->bflags & BF_HAS_CHIPON_PENDING) ? SF_HAS_CHIPON : 0));
         it.consumed[0] = S->chipon_consumed[0];
         it.consumed[1] = S->chipon_consumed[1];
@@ -623,23 +624,23 @@ MJX_D int doras_owned_self(const Ctx& c, int seat) {
     const SeatPrivate& P = S->priv[seat];
     const SeatPublic& U = S->pub[seat];
     int n = mjx_popc(P.akas_in_hand);
-    for (int t = 0; t < 34; t++) n += P.tehai[t] * c.W->dora_factor[t];
+    for (int t = 0; t < 34; t++) n += P.tehai[t] * c.df[t];
     for (int f = 0; f < U.n_fuuro; f++)
         for (int i = 0; i < 4; i++) {
             int t = U.fuuro[f][i];
             if (t == T_NONE) continue;
-            n += c.W->dora_factor[deaka(t)] + (is_aka(t) ? 1 : 0);
+            n += c.df[deaka(t)] + (is_aka(t) ? 1 : 0);
         }
     for (int i = 0; i < U.n_ankan; i++) {
         int t = U.ankan[i];
-        n += 4 * c.W->dora_factor[t] + ((t == T_5M || t == T_5P || t == T_5S) ? 1 : 0);
+        n += 4 * c.df[t] + ((t == T_5M || t == T_5P || t == T_5S) ? 1 : 0);
     }
     return n;
 }
 
 // agent_helper.rs:377-462; executed redundantly by every lane (uniform), n_ura = revealed ura count
-MJX_DN Point agari_points(Ctx& c, int seat, bool is_ron, int n_ura, bool* ok) {
-    TableState* S = c.S;
+MJX_DN Point agari_points(const Ctx& c, int seat, bool is_ron, int n_ura, bool* ok) {
+    const TableState* S = c.S;
     const SeatPrivate& P = S->priv[seat];
     const bool is_oya = seat == S->oya;
     *ok = true;
@@ -660,7 +661,7 @@ MJX_DN Point agari_points(Ctx& c, int seat, bool is_ron, int n_ura, bool* ok) {
     const int wid = deaka(winning_tile);
     if (is_ron) {
         th[wid] += 1;
-        doras += c.W->dora_factor[wid] + (is_aka(winning_tile) ? 1 : 0);
+        doras += c.df[wid] + (is_aka(winning_tile) ? 1 : 0);
     }
     if (racc) {
         const SeatPublic& U = S->pub[seat];

@@ -87,6 +87,14 @@ class BatchEnv:
         _lib.check(self.L.mjx_env_encode_obs(self._h, C.c_void_p(out.data_ptr()), self._stream()), "mjx_env_encode_obs")
         return out
 
+    def set_sp(self, enable: bool) -> None:
+        _lib.check(self.L.mjx_env_set_sp(self._h, int(enable)), "mjx_env_set_sp")
+
+    def sp_overflows(self) -> int:
+        n = C.c_int(0)
+        _lib.check(self.L.mjx_env_sp_overflows(self._h, self._stream(), C.byref(n)), "mjx_env_sp_overflows")
+        return n.value
+
     def num_rows(self) -> int:
         n = C.c_int(0)
         _lib.check(self.L.mjx_env_num_rows(self._h, self._stream(), C.byref(n)), "mjx_env_num_rows")

@@ -17,7 +17,7 @@ _lib = None
 def build():
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-DMJX_HOST_EMUL", "-I" + CSRC,
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-DMJX_HOST_EMUL", "-ffp-contract=off", "-I" + CSRC,
                                "-Wno-unknown-pragmas", "-o", SO, SRC])
     return SO
 
@@ -39,7 +39,8 @@ def lib():
         L.emul_env_num_rows.argtypes = [C.c_void_p]
         L.emul_env_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_env_policy_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        L.emul_env_encode_obs.argtypes = [C.c_void_p, C.c_void_p]
+        L.emul_env_encode_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.emul_sp_overflows.restype = C.c_long
         L.emul_env_results.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         if L.emul_init(DATA_DIR.encode()) != 0:
             raise RuntimeError(L.emul_last_error().decode())
@@ -107,7 +108,7 @@ class EmulEnv:
         self.L.emul_env_policy_test(self._h, kind, a.ctypes.data)
         return a
 
-    def encode_obs(self):
+    def encode_obs(self, sp=False):
         obs = np.zeros((self.num_rows(), 1012, 34), dtype=np.float32)
-        self.L.emul_env_encode_obs(self._h, obs.ctypes.data)
+        self.L.emul_env_encode_obs(self._h, obs.ctypes.data, int(sp))
         return obs

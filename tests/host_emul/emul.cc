@@ -6,7 +6,7 @@
 #include <string>
 #include <vector>
 
-#include "mjx_obs.cuh"
+#include "mjx_sp.cuh"
 #include "mjx_policy.cuh"
 #include "mjx_tables_host.h"
 
@@ -76,7 +76,7 @@ int emul_run(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_ki
         int live = 0;
         for (int t = 0; t < n; t++) {
             Ctx c;
-            c.S = &tabs[t]; c.W = &W; c.T = g_T; c.lane = 0;
+            c.S = &tabs[t]; c.W = &W; c.T = g_T; c.lane = 0; c.df = W.dora_factor;
             if (step_table(c, V, t)) live++;
         }
         if (live == 0) break;
@@ -148,7 +148,7 @@ int emul_env_step(void* p, const int64_t* actions) {
     int live = 0;
     WarpScratch W;
     for (int t = 0; t < E->n; t++) {
-        Ctx c; c.S = &E->tabs[t]; c.W = &W; c.T = g_T; c.lane = 0;
+        Ctx c; c.S = &E->tabs[t]; c.W = &W; c.T = g_T; c.lane = 0; c.df = W.dora_factor;
         if (step_table(c, E->V, t)) live++;
     }
     return live;
@@ -171,9 +171,18 @@ void emul_env_policy_test(void* p, int kind, int64_t* actions) {
         actions[r] = test_policy(kind, h, kan != 0, m, P.keep_shanten, P.next_shanten);
     }
 }
-// obs: [n_rows, 1012, 34] f32
-void emul_env_encode_obs(void* p, float* obs) {
+static long g_emul_sp_overflows = 0;
+long emul_sp_overflows() { return g_emul_sp_overflows; }
+
+// obs: [n_rows, 1012, 34] f32; sp: compute the single-player block
+void emul_env_encode_obs(void* p, float* obs, int sp) {
     EmulEnv* E = static_cast<EmulEnv*>(p);
+    static std::vector<SpKey> keys(SP_NODE_CAP);
+    static std::vector<float> vals((size_t)SP_NODE_CAP * 3 * SP_T_MAX);
+    static std::vector<u32> edges((size_t)SP_NODE_CAP * SP_EDGE_MAX), hash(SP_HASH_CAP);
+    static std::vector<u8> n_edges(SP_NODE_CAP);
+    static i32 counters[4];
+    static SpShared shared;
     for (int r = 0; r < E->n_rows[0]; r++) {
         float* tile = obs + (size_t)r * OBS_ROWS_V4 * OBS_COLS;
         memset(tile, 0, sizeof(float) * OBS_ROWS_V4 * OBS_COLS);
@@ -187,12 +196,20 @@ void emul_env_encode_obs(void* p, float* obs) {
         EncCtx e;
         e.S = S; e.T = g_T; e.tile = tile; e.seat = E->row_seat[r] & 3; e.kan_select = (E->row_seat[r] >> 2) & 1;
         e.lane = 0; e.warp = 0; e.nwarps = 1; e.dora_factor = df;
-        Ctx c; c.S = const_cast<TableState*>(S); c.W = nullptr; c.T = g_T; c.lane = 0;
+        Ctx c; c.S = const_cast<TableState*>(S); c.W = nullptr; c.T = g_T; c.lane = 0; c.df = df;
         // built as the two half-tiles the CUDA kernel builds
         e.row_lo = 0; e.row_hi = OBS_SPLIT_ROW; e.tile = tile;
         encode_obs_v4(e, c, nullptr);
         e.row_lo = OBS_SPLIT_ROW; e.row_hi = OBS_ROWS_V4; e.tile = tile + (size_t)OBS_SPLIT_ROW * OBS_COLS;
         encode_obs_v4(e, c, nullptr);
+        if (sp) {
+            SpCtx s;
+            s.W.keys = keys.data(); s.W.vals = vals.data(); s.W.edges = edges.data(); s.W.n_edges = n_edges.data();
+            s.W.hash = hash.data(); s.W.counters = counters; s.sh = &shared; s.T = g_T; s.lane = 0; s.warp = 0; s.nwarps = 1;
+            counters[1] = 0;
+            encode_sp_block(e, c, s);
+            if (counters[1]) g_emul_sp_overflows++;
+        }
     }
 }
 void emul_env_results(void* p, int32_t* scores, uint8_t* ranks, int32_t* steps, int32_t* errs, int32_t* done) {

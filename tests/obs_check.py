@@ -7,7 +7,7 @@ import oracle_lib as O
 EXP_ROWS = [131] + [132 + 195 * k + 192 + j for k in range(3) for j in range(3)]  # exp(-0.2 * age) planes
 
 
-def check_obs_parity(make_env, fetch, n=8, max_cycles=400, seed0=777, min_rows=2000):
+def check_obs_parity(make_env, fetch, n=8, max_cycles=400, seed0=777, min_rows=2000, sp=False, sp_tol=0.0):
     """make_env(nonces, keys) -> env ; fetch(env, first, prev_actions) -> (row_table, row_seat, masks, obs, actions)"""
     nonces = np.arange(seed0, seed0 + n, dtype=np.uint64)
     keys = np.full(n, 99, dtype=np.uint64)
@@ -27,14 +27,21 @@ def check_obs_parity(make_env, fetch, n=8, max_cycles=400, seed0=777, min_rows=2
             for r in range(len(rows_t)):
                 t, seat, kan = int(rows_t[r]), int(rows_s[r] & 3), bool(rows_s[r] & 4)
                 ps = O.PlayerState(0, _ptr=L.orc_game_state(games[t], seat), _own=False)
-                ref_obs, ref_mask = ps.encode_obs(4, kan, sp_mode=0)
+                ref_obs, ref_mask = ps.encode_obs(4, kan, sp_mode=1 if sp else 0)
                 assert (ref_mask == masks[r]).all(), (cycle, t, seat, kan)
                 d = np.abs(obs[r][:889] - ref_obs[:889])
                 bad = np.argwhere(d[exact] != 0)
                 assert len(bad) == 0, (cycle, t, seat, kan, np.nonzero(exact)[0][bad[:8, 0]], bad[:8, 1],
                                        obs[r][:889][exact][tuple(bad[0])], ref_obs[:889][exact][tuple(bad[0])])
                 assert d[~exact].max() <= 1e-6
-                assert (obs[r][889:] == 0).all()
+                if sp:
+                    dsp = np.abs(obs[r][889:] - ref_obs[889:])
+                    if dsp.max() > sp_tol:
+                        rr, cc = np.unravel_index(np.argmax(dsp), dsp.shape)
+                        raise AssertionError(("sp block", cycle, t, seat, kan, 889 + int(rr), int(cc),
+                                              float(obs[r][889 + rr, cc]), float(ref_obs[889 + rr, cc]), float(dsp.max())))
+                else:
+                    assert (obs[r][889:] == 0).all()
                 checked += 1
                 chosen[(t, seat, kan)] = int(actions[r])
             for (t, seat, kan), a in chosen.items():

@@ -89,3 +89,22 @@ def test_obs_encode_parity_emulated():
         return rt, rs, m, obs, acts
 
     check_obs_parity(make_env, fetch, n=6, min_rows=1500)
+
+
+def test_sp_block_parity_emulated():
+    """obs v4 rows 889..1011 (single-player tables): product DP (host-emulated) vs the oracle's memoised recursion.
+    Same f32 operation order on both sides, so the comparison is exact."""
+    from obs_check import check_obs_parity
+
+    def make_env(nonces, keys):
+        return E.EmulEnv(nonces, keys, enable_quick_eval=False)
+
+    def fetch(env, first, prev):
+        env.step(None if first else prev)
+        rt, rs, m = env.rows()
+        obs = env.encode_obs(sp=True)
+        acts = env.policy_test(1)
+        return rt, rs, m, obs, acts
+
+    check_obs_parity(make_env, fetch, n=4, max_cycles=150, min_rows=400, sp=True, sp_tol=0.0)
+    assert E.lib().emul_sp_overflows() == 0

@@ -185,8 +185,8 @@ def test_selfplay_4096_tables_scores(mjx):
 
 
 def test_obs_encode_matches_oracle(mjx):
-    """Rows 0..888 of the v4 observation (everything except the single-player block) and the legal mask,
-    compared at every decision of a few seeded games. 0/1 and small-rational planes exactly, exp() planes 1e-6."""
+    """All 1012 rows of the v4 observation (incl. the single-player block 889-1011) and the legal mask, compared
+    at every decision of a few seeded games. Everything exactly, except the exp() planes (<= 1e-6)."""
     import torch
 
     from obs_check import check_obs_parity
@@ -194,6 +194,14 @@ def test_obs_encode_matches_oracle(mjx):
     def make_env(nonces, keys):
         env = mjx.BatchEnv(nonces, keys, enable_quick_eval=False)
         env._actions = torch.zeros(env.row_cap, dtype=torch.int64, device=env.device)
+        orig_close = env.close
+
+        def close_and_record():
+            if env._h:
+                make_env.overflows = env.sp_overflows()
+            orig_close()
+
+        env.close = close_and_record
         return env
 
     def fetch(env, first, prev):
@@ -204,4 +212,5 @@ def test_obs_encode_matches_oracle(mjx):
         return (env.row_table[:nr].cpu().numpy(), env.row_seat[:nr].cpu().numpy(), env.masks[:nr].cpu().numpy(),
                 obs[:nr].cpu().numpy(), env._actions[:nr].cpu().numpy())
 
-    check_obs_parity(make_env, fetch)
+    check_obs_parity(make_env, fetch, sp=True, sp_tol=0.0)
+    assert make_env.overflows == 0
