@@ -45,8 +45,14 @@ void mjx_env_destroy(mjx_env* env);
  * chosen for the rows of the previous step (agent/mortal.rs:292-573 decode + board.rs:524-533
  * validation), then poll every table to its next decision point (game.rs:59-178) and emit the
  * decision rows + legal masks (agent/mortal.rs:200-290). `actions_dev` = int64 [row_cap], indexed
- * by the previous step's row numbers (ignored on the first step; may be NULL then). */
-int mjx_env_step(mjx_env* env, const int64_t* actions_dev, void* stream);
+ * by the previous step's row numbers (ignored on the first step; may be NULL then).
+ * `q_values_dev` = float32 [row_cap, 46] Q-values of those rows, or NULL; only read for seats whose engine
+ * set enable_rule_based_agari_guard (agent/mortal.rs:319-336: "wants agari but the guard objects -> best other Q"). */
+int mjx_env_step(mjx_env* env, const int64_t* actions_dev, const float* q_values_dev, void* stream);
+
+/* agent/mortal.rs:61-66 enable_rule_based_agari_guard per table and seat: host uint8 [n_tables, 4] (NULL = off).
+ * The guard itself is state/agent_helper.rs:262-368 rule_based_agari, evaluated on device. */
+int mjx_env_set_agari_guard(mjx_env* env, const uint8_t* flags_host);
 
 /* state/obs_repr.rs:776-790 encode_obs for every row of the current step:
  * obs_dev = float32 [row_cap, rows(version), 34] (only the first n_rows rows are written). */
@@ -78,8 +84,10 @@ int mjx_env_results(mjx_env* env, void* stream, int32_t* scores_host /*[n,4]*/, 
 
 /* Counter-based TEST policy (not in the reference; shared definition with the oracle) writing
  * int64 actions for the current rows. kind 0 uniform, 1 agari-first/shanten-greedy.
- * trace_dev (optional): int64 [row_cap, 6] = table, step, seat, action, kan_select, mask_bits. */
-int mjx_env_policy_test(mjx_env* env, int kind, int64_t* actions_dev, int64_t* trace_dev, void* stream);
+ * trace_dev (optional): int64 [row_cap, 6] = table, step, seat, action, kan_select, mask_bits.
+ * q_values_dev (optional): float32 [row_cap, 46] filled with 0 on legal and -inf on illegal actions. */
+int mjx_env_policy_test(mjx_env* env, int kind, int64_t* actions_dev, int64_t* trace_dev, float* q_values_dev,
+                        void* stream);
 
 /* ---- standalone kernels (BASELINE configs 3/4) ------------------------------------------------ */
 /* algo/shanten.rs:138-150 calc_all: tiles_dev uint8 [n,34], len_div3_dev uint8 [n] -> int8 [n]. */

@@ -40,7 +40,8 @@ SYMBOLS = {
     "mjx_obs_rows": (C.c_int, [C.c_int]),
     "mjx_env_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "mjx_env_destroy": (None, [C.c_void_p]),
-    "mjx_env_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mjx_env_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mjx_env_set_agari_guard": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mjx_env_encode_obs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mjx_env_set_sp": (C.c_int, [C.c_void_p, C.c_int]),
     "mjx_env_sp_overflows": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
@@ -53,7 +54,7 @@ SYMBOLS = {
     "mjx_env_row_seat": (C.c_void_p, [C.c_void_p]),
     "mjx_env_num_rows_dev": (C.c_void_p, [C.c_void_p]),
     "mjx_env_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "mjx_env_policy_test": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mjx_env_policy_test": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mjx_shanten": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "mjx_agari": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mjx_shanten_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

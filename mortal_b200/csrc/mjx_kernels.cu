@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_obs_v4(EnvView V, Tab
     }
 }
 
-__global__ void k_policy_test(EnvView V, int kind, i64* actions, i64* trace) {
+__global__ void k_policy_test(EnvView V, int kind, i64* actions, i64* trace, float* q_out) {
     const int n_rows = *V.n_rows;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
         const int t = V.row_table[r], seat = V.row_seat[r] & 3, kan = (V.row_seat[r] >> 2) & 1;
@@ -166,6 +166,8 @@ __global__ void k_policy_test(EnvView V, int kind, i64* actions, i64* trace) {
         u64 h = policy_hash(S->nonce, S->key, (u64)t, V.row_step[r], (u32)seat, (u32)kan);
         int a = test_policy(kind, h, kan != 0, m, P.keep_shanten, P.next_shanten);
         actions[r] = a;
+        if (q_out)  // what a masked dueling head would give a uniform policy: 0 on legal actions, -inf elsewhere
+            for (int i = 0; i < ACTION_SPACE; i++) q_out[(size_t)r * ACTION_SPACE + i] = ((m >> i) & 1) ? 0.f : -INFINITY;
         if (trace) {
             i64* o = trace + (size_t)r * 6;
             o[0] = t; o[1] = V.row_step[r]; o[2] = seat; o[3] = a; o[4] = kan; o[5] = (i64)m;
@@ -266,6 +268,7 @@ struct mjx_env {
     EnvView V;
     u64 *d_nonces = nullptr, *d_keys = nullptr;
     i64* d_dummy_actions = nullptr;
+    u8* d_guard = nullptr;
     SpArena sp;
     int enc_grid = 0;
 };
@@ -383,19 +386,29 @@ void mjx_env_destroy(mjx_env* env) {
     EnvView& V = env->V;
     cudaFree(V.tables); cudaFree(V.n_rows); cudaFree(V.row_table); cudaFree(V.row_seat); cudaFree(V.row_step);
     cudaFree(V.masks); cudaFree(V.scores); cudaFree(V.ranks); cudaFree(V.done); cudaFree(V.steps); cudaFree(V.err);
-    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions);
+    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard);
     SpArena& A = env->sp;
     cudaFree(A.keys); cudaFree(A.vals); cudaFree(A.edges); cudaFree(A.n_edges); cudaFree(A.hash); cudaFree(A.counters);
     cudaFree(A.shared); cudaFree(A.overflow_count);
     delete env;
 }
 
-int mjx_env_step(mjx_env* env, const int64_t* actions_dev, void* stream) {
+int mjx_env_set_agari_guard(mjx_env* env, const uint8_t* flags_host) {
+    if (!env) return fail(MJX_ERR_ARG, "mjx_env_set_agari_guard: null env");
+    if (!flags_host) { cudaFree(env->d_guard); env->d_guard = nullptr; return MJX_OK; }
+    if (!env->d_guard) CU(cudaMalloc(&env->d_guard, (size_t)env->n_tables * 4));
+    CU(cudaMemcpy(env->d_guard, flags_host, (size_t)env->n_tables * 4, cudaMemcpyHostToDevice));
+    return MJX_OK;
+}
+
+int mjx_env_step(mjx_env* env, const int64_t* actions_dev, const float* q_values_dev, void* stream) {
     if (!env) return fail(MJX_ERR_ARG, "mjx_env_step: null env");
     if (!env->first && !actions_dev) return fail(MJX_ERR_ARG, "mjx_env_step: actions required after the first step");
     cudaStream_t st = (cudaStream_t)stream;
     EnvView V = env->V;
     V.actions = actions_dev ? (const i64*)actions_dev : env->d_dummy_actions;
+    V.q_values = q_values_dev;
+    V.agari_guard = env->d_guard;
     k_begin_step<<<1, 1, 0, st>>>(V);
     k_step<<<(env->n_tables + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32, 0, st>>>(V, g_T);
     CU(cudaGetLastError());
@@ -469,9 +482,9 @@ int mjx_env_results(mjx_env* env, void* stream, int32_t* scores, uint8_t* ranks,
     return MJX_OK;
 }
 
-int mjx_env_policy_test(mjx_env* env, int kind, int64_t* actions_dev, int64_t* trace_dev, void* stream) {
+int mjx_env_policy_test(mjx_env* env, int kind, int64_t* actions_dev, int64_t* trace_dev, float* q_values_dev, void* stream) {
     if (!env || !actions_dev) return fail(MJX_ERR_ARG, "mjx_env_policy_test: bad arguments");
-    k_policy_test<<<g_sm_count * 2, 128, 0, (cudaStream_t)stream>>>(env->V, kind, (i64*)actions_dev, (i64*)trace_dev);
+    k_policy_test<<<g_sm_count * 2, 128, 0, (cudaStream_t)stream>>>(env->V, kind, (i64*)actions_dev, (i64*)trace_dev, q_values_dev);
     CU(cudaGetLastError());
     return MJX_OK;
 }

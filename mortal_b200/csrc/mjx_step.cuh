@@ -27,7 +27,7 @@ struct Reaction {
 enum : i32 {
     ERR_NONE = 0, ERR_ILLEGAL_ACTION = 1, ERR_KAWA_OVERFLOW = 2, ERR_WALL_EXHAUSTED = 3, ERR_FIFTH_KAN = 4,
     ERR_INTERNAL = 5, ERR_FOUR_WIND_STATE = 6, ERR_NO_KAWA_TILE = 7, ERR_ROW_OVERFLOW = 8, ERR_BAD_POINT = 9,
-    ERR_KAN_CHOICE = 10,
+    ERR_KAN_CHOICE = 10, ERR_GUARD_NEEDS_Q = 11,
 };
 
 struct WarpScratch {
@@ -639,7 +639,7 @@ MJX_D int doras_owned_self(const Ctx& c, int seat) {
 }
 
 // agent_helper.rs:377-462; executed redundantly by every lane (uniform), n_ura = revealed ura count
-MJX_DN Point agari_points(const Ctx& c, int seat, bool is_ron, int n_ura, bool* ok) {
+MJX_DN Point agari_points_ura(const Ctx& c, int seat, bool is_ron, const u8* ura, int n_ura, bool* ok) {
     const TableState* S = c.S;
     const SeatPrivate& P = S->priv[seat];
     const bool is_oya = seat == S->oya;
@@ -666,7 +666,7 @@ MJX_DN Point agari_points(const Ctx& c, int seat, bool is_ron, int n_ura, bool* 
     if (racc) {
         const SeatPublic& U = S->pub[seat];
         for (int k = 0; k < n_ura; k++) {
-            int next = tile_next(ura_indicator(S, k));
+            int next = tile_next(ura[k]);
             int cnt = th[next];
             for (int i = 0; i < U.n_ankan; i++) if (U.ankan[i] == next) cnt += 4;
             doras += cnt;
@@ -678,6 +678,82 @@ MJX_DN Point agari_points(const Ctx& c, int seat, bool is_ron, int n_ura, bool* 
     Point p = agari_point(a, is_oya, &pok);
     if (!pok) *ok = false;
     return p;
+}
+
+// the board's own ura indicators: wall[61 + k] (board.rs:381-382)
+MJX_D Point agari_points(const Ctx& c, int seat, bool is_ron, int n_ura, bool* ok) {
+    return agari_points_ura(c, seat, is_ron, c.S->wall + 61, n_ura, ok);
+}
+
+// agent_helper.rs:262-368 — the all-last "do not win into 4th place" guard. Executed by one lane.
+MJX_DN bool rule_based_agari(const Ctx& c, int p) {
+    const TableState* S = c.S;
+    const SeatPrivate& P = S->priv[p];
+    if (!(P.cans & CAN_AGARI)) return false;
+    const bool is_ron = (P.cans & CAN_RON_AGARI) != 0;
+    const int target_rel = (P.target_actor - p) & 3;
+    const int bakaze = T_E + S->kyoku / 4, kyoku_in_wind = S->kyoku & 3;
+    const bool is_all_last = bakaze == T_E ? false : (bakaze == T_S ? kyoku_in_wind == 3 : true);
+    const int oya_rel = (S->oya - p) & 3;
+    i32 sc[4];
+    for (int i = 0; i < 4; i++) sc[i] = S->scores[(p + i) & 3];
+    auto rank_of = [&](const i32* rel) {  // update.rs:966-972 get_rank on relative scores
+        int r = 0;
+        for (int i = 1; i < 4; i++) {
+            const int s = (p + i) & 3;
+            if (rel[i] > rel[0] || (rel[i] == rel[0] && s < p)) r++;
+        }
+        return r;
+    };
+    if (!is_all_last || oya_rel == 0 || rank_of(sc) < 3) return true;
+    if (bakaze == T_W) {
+        if (kyoku_in_wind < 3) return true;
+    } else if (sc[0] < 30000 && sc[1] < 30000 && sc[2] < 30000 && sc[3] < 30000) {
+        return true;
+    }
+    const bool racc = (S->riichi_accepted >> p) & 1;
+    bool ok;
+    Point pt;
+    if (racc) {
+        // most valuable possible ura indicators first (agent_helper.rs:294-326)
+        u8 full[34], seen[34];
+        const SeatPublic& U = S->pub[p];
+        for (int t = 0; t < 34; t++) { full[t] = P.tehai[t]; seen[t] = (u8)(S->public_seen[t] + P.tehai[t]); }
+        for (int j = 0; j < U.n_ankan; j++) full[U.ankan[j]] += 4;
+        u8 ura[5]; int n_ura = 0;
+        u64 used = 0;
+        bool done = false;
+        for (int round = 0; round < 34 && !done; round++) {
+            // next tile by descending count, ascending id among equals (stable order of the reference's small sort)
+            int best = -1;
+            for (int t = 0; t < 34; t++)
+                if (full[t] > 0 && !((used >> t) & 1) && (best < 0 || full[t] > full[best])) best = t;
+            if (best < 0) break;
+            used |= 1ull << best;
+            const int ind = tile_prev(best);
+            for (;;) {
+                if (n_ura >= S->n_dora) { done = true; break; }
+                if (seen[ind] >= 4) break;
+                ura[n_ura++] = (u8)ind;
+                seen[ind] += 1;
+            }
+        }
+        pt = agari_points_ura(c, p, is_ron, ura, n_ura, &ok);
+    } else {
+        pt = agari_points_ura(c, p, is_ron, nullptr, 0, &ok);
+    }
+    if (!ok) return true;  // the reference unwraps; cannot happen when can_agari holds
+    i32 ex[4] = {sc[0], sc[1], sc[2], sc[3]};
+    const i32 kyotaku = S->kyotaku, honba = S->honba;
+    if (is_ron) {
+        ex[0] += pt.ron + kyotaku * 1000 + honba * 300;
+        ex[target_rel] -= pt.ron + honba * 300;
+    } else {
+        ex[0] += tsumo_total(pt, false) + kyotaku * 1000 + honba * 300;
+        for (int i = 1; i < 4; i++) ex[i] -= (i == oya_rel ? pt.tsumo_oya : pt.tsumo_ko) + honba * 100;
+    }
+    if (ex[0] < 30000 && ex[1] < 30000 && ex[2] < 30000 && ex[3] < 30000) return true;
+    return rank_of(ex) < 3;
 }
 
 // board.rs:366-471
@@ -1125,6 +1201,8 @@ struct EnvView {
     u32* row_step;      // [row_cap] table-step index (policy hashing / tracing)
     u8* masks;          // [row_cap, 46] legal-action mask, 1 byte per action (torch.bool compatible)
     const i64* actions; // [row_cap] chosen action per row of the PREVIOUS step
+    const float* q_values;   // [row_cap, 46] or null: needed only by the rule-based agari guard (mortal.rs:319-336)
+    const u8* agari_guard;   // [n_tables, 4] or null: 1 where the seat's engine has enable_rule_based_agari_guard
     i32* scores;        // [n_tables, 4] final scores (valid once done)
     u8* ranks;          // [n_tables, 4] rank_by_player (rankings.rs:8-22)
     i32* done;          // [n_tables]
@@ -1156,7 +1234,7 @@ MJX_D void write_mask_row(Ctx& c, EnvView& V, int row, u64 m) {
 
 // Game::commit (game.rs:200-217) through MortalBatchAgent::get_reaction (mortal.rs:292-573):
 // turn last step's chosen actions into the four reactions.
-MJX_DN void gather_reactions(Ctx& c, EnvView& V) {
+MJX_DN void gather_reactions(Ctx& c, EnvView& V, int table) {
     TableState* S = c.S;
     clear_reactions(c);
     // The mask rows written last step may already be overwritten by other tables of this launch, so
@@ -1176,6 +1254,21 @@ MJX_DN void gather_reactions(Ctx& c, EnvView& V) {
             i64 a = V.actions[S->row_of_seat[s]];
             if (a < 0 || a >= ACTION_SPACE || !((c.W->legal[s] >> a) & 1)) e = ERR_ILLEGAL_ACTION;
             else action = (int)a;
+            // mortal.rs:319-336: the engine wants agari but the rule-based guard objects -> best other Q
+            if (e == 0 && action == 43 && V.agari_guard && V.agari_guard[table * 4 + s] && !rule_based_agari(c, s)) {
+                if (!V.q_values) e = ERR_GUARD_NEEDS_Q;
+                else {
+                    const float* q = V.q_values + (size_t)S->row_of_seat[s] * ACTION_SPACE;
+                    int best = -1;
+                    float bq = 0.f;
+                    for (int i = 0; i < ACTION_SPACE; i++) {
+                        const float v = i == 43 ? -3.40282347e+38f : q[i];
+                        if (best < 0 || !(v < bq)) { best = i; bq = v; }  // max_by(total_cmp): last maximum
+                    }
+                    if (!((c.W->legal[s] >> best) & 1)) e = ERR_ILLEGAL_ACTION;
+                    else action = best;
+                }
+            }
             if (S->kan_row_of_seat[s] >= 0) {
                 i64 k = V.actions[S->kan_row_of_seat[s]];
                 if (k < 0 || k >= ACTION_SPACE || !((c.W->legal_kan[s] >> k) & 1)) e = ERR_ILLEGAL_ACTION;
@@ -1233,7 +1326,7 @@ MJX_DN bool step_table(Ctx& c, EnvView& V, int table) {
     if (!(S->gflags & GF_ALIVE)) return false;
     recompute_dora_factor(c);
     if (S->gflags & GF_KYOKU_STARTED) {
-        gather_reactions(c, V);
+        gather_reactions(c, V, table);
         MJX_L0(S->step_idx += 1);
     } else {
         clear_reactions(c);

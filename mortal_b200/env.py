@@ -65,14 +65,28 @@ class BatchEnv:
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
-    def step(self, actions=None) -> None:
-        """actions: int64 cuda tensor [row_cap] indexed by the previous step's rows (None on the first step)."""
-        ptr = None
+    def step(self, actions=None, q_values=None) -> None:
+        """actions: int64 cuda tensor [row_cap] indexed by the previous step's rows (None on the first step);
+        q_values: float32 cuda tensor [row_cap, 46], only needed when an agari guard is set."""
+        ptr = qptr = None
         if actions is not None:
             assert actions.dtype == self.torch.int64 and actions.is_cuda and actions.is_contiguous()
             assert actions.numel() >= self.row_cap
             ptr = C.c_void_p(actions.data_ptr())
-        _lib.check(self.L.mjx_env_step(self._h, ptr, self._stream()), "mjx_env_step")
+        if q_values is not None:
+            assert q_values.dtype == self.torch.float32 and q_values.is_cuda and q_values.is_contiguous()
+            assert q_values.shape == (self.row_cap, 46)
+            qptr = C.c_void_p(q_values.data_ptr())
+        _lib.check(self.L.mjx_env_step(self._h, ptr, qptr, self._stream()), "mjx_env_step")
+
+    def set_agari_guard(self, flags) -> None:
+        """flags: None or uint8 array [n_tables, 4] (1 = that seat's engine has enable_rule_based_agari_guard)."""
+        if flags is None:
+            _lib.check(self.L.mjx_env_set_agari_guard(self._h, None), "mjx_env_set_agari_guard")
+            return
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        assert f.shape == (self.n_tables, 4)
+        _lib.check(self.L.mjx_env_set_agari_guard(self._h, f.ctypes.data), "mjx_env_set_agari_guard")
 
     def obs_buffer(self):
         if self._obs is None:
@@ -110,9 +124,10 @@ class BatchEnv:
         _lib.check(self.L.mjx_env_total_steps(self._h, self._stream(), C.byref(n)), "mjx_env_total_steps")
         return n.value
 
-    def policy_test(self, kind: int, actions, trace=None) -> None:
+    def policy_test(self, kind: int, actions, trace=None, q_values=None) -> None:
         tp = C.c_void_p(trace.data_ptr()) if trace is not None else None
-        _lib.check(self.L.mjx_env_policy_test(self._h, kind, C.c_void_p(actions.data_ptr()), tp, self._stream()),
+        qp = C.c_void_p(q_values.data_ptr()) if q_values is not None else None
+        _lib.check(self.L.mjx_env_policy_test(self._h, kind, C.c_void_p(actions.data_ptr()), tp, qp, self._stream()),
                    "mjx_env_policy_test")
 
     def results(self):
@@ -126,20 +141,25 @@ class BatchEnv:
                                           steps.ctypes.data, err.ctypes.data, done.ctypes.data), "mjx_env_results")
         return dict(scores=scores, ranks=ranks, steps=steps, err=err, done=done)
 
-    def run_test_policy(self, kind: int = 1, *, encode_obs: bool = False, max_cycles: int = 0, trace: bool = False):
+    def run_test_policy(self, kind: int = 1, *, encode_obs: bool = False, max_cycles: int = 0, trace: bool = False,
+                        agari_guard: bool = False):
         """Play every table to the end with the built-in counter-based test policy (env-only loop)."""
         torch = self.torch
         actions = torch.zeros(self.row_cap, dtype=torch.int64, device=self.device)
+        q = None
+        if agari_guard:
+            self.set_agari_guard(np.ones((self.n_tables, 4), dtype=np.uint8))
+            q = torch.zeros((self.row_cap, 46), dtype=torch.float32, device=self.device)
         tbuf = torch.zeros((self.row_cap, 6), dtype=torch.int64, device=self.device) if trace else None
         traces = []
         cycles = 0
         first = True
         while True:
-            self.step(None if first else actions)
+            self.step(None if first else actions, None if first else q)
             first = False
             if encode_obs:
                 self.encode_obs()
-            self.policy_test(kind, actions, tbuf)
+            self.policy_test(kind, actions, tbuf, q)
             cycles += 1
             if trace:
                 n = self.num_rows()

@@ -40,8 +40,6 @@ class _Arena:
 
         agents = [_adapt(challenger), _adapt(champion)]
         for a in agents:
-            if getattr(a, "enable_rule_based_agari_guard", False):
-                raise NotImplementedError("enable_rule_based_agari_guard is not implemented on the device path yet")
             if getattr(a, "is_oracle", False):
                 raise NotImplementedError("oracle (invisible) observations are out of this round's scope")
             if getattr(a, "version", 4) != 4:
@@ -62,10 +60,20 @@ class _Arena:
             for s in self._challenger_seats(g):
                 is_challenger[g, s] = True
         actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
+        guards = [bool(getattr(a, "enable_rule_based_agari_guard", False)) for a in agents]
+        q_all = None
+        if any(guards):  # mortal.rs:319-336 needs the Q-values of the previous decision
+            flags = np.zeros((n, 4), dtype=np.uint8)
+            ic = is_challenger.cpu().numpy()
+            for g in range(n):
+                for seat in range(4):
+                    flags[g, seat] = guards[0] if ic[g % per, seat] else guards[1]
+            env.set_agari_guard(flags)
+            q_all = torch.zeros((env.row_cap, 46), dtype=torch.float32, device=dev)
         first = True
         cycles = 0
         while True:
-            env.step(None if first else actions)
+            env.step(None if first else actions, None if first else q_all)
             first = False
             nr = env.num_rows()
             if nr == 0 and env.num_live() == 0:
@@ -79,8 +87,10 @@ class _Arena:
                 for idx, agent in ((chal.nonzero().squeeze(1), agents[0]), ((~chal).nonzero().squeeze(1), agents[1])):
                     if idx.numel() == 0:
                         continue
-                    a, _ = agent.react_device(obs[idx], masks[idx])
+                    a, q = agent.react_device(obs[idx], masks[idx])
                     actions[idx] = a.to(torch.int64)
+                    if q_all is not None:
+                        q_all[idx] = q.float()
             cycles += 1
         res = env.results()
         self.last_stats = dict(cycles=cycles, table_steps=int(res["steps"].sum()))

@@ -31,7 +31,7 @@ def lib():
         L.emul_shanten.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.emul_make_wall.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.emul_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int64]
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int64, C.c_int]
         L.emul_env_create.restype = C.c_void_p
         L.emul_env_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.emul_env_destroy.argtypes = [C.c_void_p]
@@ -48,7 +48,7 @@ def lib():
     return _lib
 
 
-def run(nonces, keys, *, shuffle_kind=0, quick_eval=True, policy_kind=1, trace_cap=0, max_cycles=0):
+def run(nonces, keys, *, shuffle_kind=0, quick_eval=True, policy_kind=1, trace_cap=0, max_cycles=0, agari_guard=False):
     n = len(nonces)
     nonces = np.ascontiguousarray(nonces, dtype=np.uint64)
     keys = np.ascontiguousarray(keys, dtype=np.uint64)
@@ -60,7 +60,7 @@ def run(nonces, keys, *, shuffle_kind=0, quick_eval=True, policy_kind=1, trace_c
     tl = C.c_int64(0)
     rc = lib().emul_run(n, nonces.ctypes.data, keys.ctypes.data, shuffle_kind, int(quick_eval), policy_kind,
                         scores.ctypes.data, ranks.ctypes.data, steps.ctypes.data, errs.ctypes.data,
-                        trace.ctypes.data if trace_cap else None, trace_cap, C.byref(tl), max_cycles)
+                        trace.ctypes.data if trace_cap else None, trace_cap, C.byref(tl), max_cycles, int(agari_guard))
     assert rc == 0
     out = dict(scores=scores, ranks=ranks, steps=steps, errs=errs, n_rows=tl.value)
     if trace_cap:

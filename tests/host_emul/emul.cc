@@ -47,7 +47,7 @@ void emul_make_wall(uint64_t nonce, uint64_t key, int kyoku, int honba, int kind
 // trace rows: [table, step_idx, seat, action, kan_select, mask_bits]
 int emul_run(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int quick_eval, int policy_kind,
              int32_t* scores, uint8_t* ranks, int32_t* steps, int32_t* errs, int64_t* trace, int64_t trace_cap,
-             int64_t* trace_len, int64_t max_cycles) {
+             int64_t* trace_len, int64_t max_cycles, int agari_guard) {
     std::vector<TableState> tabs(n);
     for (int t = 0; t < n; t++) {
         TableState& S = tabs[t];
@@ -68,6 +68,10 @@ int emul_run(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_ki
     V.row_table = row_table.data(); V.row_seat = row_seat.data(); V.row_step = row_step.data();
     V.masks = masks.data(); V.actions = actions.data(); V.scores = scores; V.ranks = ranks; V.done = done.data();
     V.steps = steps; V.err = errs; V.counters = counters; V.enable_quick_eval = quick_eval;
+    std::vector<float> qv((size_t)cap * ACTION_SPACE, 0.f);
+    std::vector<u8> guard((size_t)n * 4, 1);
+    V.q_values = agari_guard ? qv.data() : nullptr;
+    V.agari_guard = agari_guard ? guard.data() : nullptr;
     for (int t = 0; t < n; t++) { steps[t] = 0; errs[t] = 0; }
     int64_t tl = 0;
     WarpScratch W;
@@ -89,6 +93,7 @@ int emul_run(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_ki
             u64 h = policy_hash(tabs[t].nonce, tabs[t].key, (u64)t, row_step[r], (u32)seat, (u32)kan);
             int a = test_policy(policy_kind, h, kan != 0, m, P.keep_shanten, P.next_shanten);
             actions[r] = a;
+            if (agari_guard) for (int i = 0; i < ACTION_SPACE; i++) qv[(size_t)r * ACTION_SPACE + i] = ((m >> i) & 1) ? 0.f : -INFINITY;
             if (trace && tl < trace_cap) {
                 int64_t* o = trace + tl * 6;
                 o[0] = t; o[1] = row_step[r]; o[2] = seat; o[3] = a; o[4] = kan; o[5] = (int64_t)m;
@@ -135,6 +140,7 @@ void* emul_env_create(int n, const uint64_t* nonces, const uint64_t* keys, int s
     V.row_table = E->row_table.data(); V.row_seat = E->row_seat.data(); V.row_step = E->row_step.data();
     V.masks = E->masks.data(); V.actions = E->actions.data(); V.scores = E->scores.data(); V.ranks = E->ranks.data();
     V.done = E->done.data(); V.steps = E->steps.data(); V.err = E->errs.data(); V.counters = E->counters;
+    V.q_values = nullptr; V.agari_guard = nullptr;
     V.enable_quick_eval = quick_eval;
     return E;
 }

@@ -47,6 +47,23 @@ def test_selfplay_trace_parity(policy_kind, quick_eval, shuffle_kind):
     assert (ro["ranks"] == re["ranks"]).all()
 
 
+def test_agari_guard_parity():
+    """mortal.rs:319-336 + agent_helper.rs:262-368: with the rule-based agari guard on for every seat the decisions
+    (incl. refused wins at all-last) and final scores still match the oracle."""
+    n = 96
+    nonces = np.arange(4000, 4000 + n, dtype=np.uint64)
+    keys = np.full(n, 5, dtype=np.uint64)
+    ro = O.run_batch(nonces, keys, policy_kind=1, quick_eval=True, agari_guard=True, trace_cap=1 << 18)
+    re = E.run(nonces, keys, policy_kind=1, quick_eval=True, agari_guard=True, trace_cap=1 << 18)
+    assert (re["errs"] == 0).all(), re["errs"]
+    rn = O.run_batch(nonces, keys, policy_kind=1, quick_eval=True, agari_guard=False)
+    assert (rn["scores"] != ro["scores"]).any(), "guard never fired: the test does not cover it"
+    to, te = sort_trace(ro["trace"]), sort_trace(re["trace"])
+    i, a, b = first_diff(to, te)
+    assert a is None, f"first divergence at sorted row {i}: oracle {a} emul {b}"
+    assert (ro["scores"] == re["scores"]).all() and (ro["ranks"] == re["ranks"]).all()
+
+
 def test_emul_shanten_matches_oracle_random_hands():
     rng = np.random.default_rng(0)
     n = 20000
