@@ -60,8 +60,9 @@ int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream);
 
 /* state/agent_helper.rs:509-593 single_player_tables (obs v4 rows 889-1011): on by default; `enable = 0`
  * leaves the block zero (the reference has no such switch; it exists for profiling the rest of the encoder).
- * mjx_env_sp_overflows: number of rows so far whose block was dropped because the per-CTA state arena
- * (32768 states) overflowed — the reference has no such limit; 0 in every test and benchmark here. */
+ * mjx_env_sp_overflows: number of steps so far in which the state arena (2048 states per table on average)
+ * overflowed and the blocks of that step were left zero — the reference has no such limit; it is 0 in every
+ * test and benchmark here and is reported rather than hidden. */
 int mjx_env_set_sp(mjx_env* env, int enable);
 int mjx_env_sp_overflows(mjx_env* env, void* stream, int* n);
 

@@ -82,14 +82,7 @@ constexpr size_t ENC_SMEM_BYTES = ENC_TILE_BYTES + sizeof(TableState) + 64;  // 
 static_assert((OBS_SPLIT_ROW * OBS_COLS * sizeof(float)) % 16 == 0, "half boundary must be 16-byte aligned");
 static_assert(((OBS_ROWS_V4 - OBS_SPLIT_ROW) * OBS_COLS * sizeof(float)) % 16 == 0, "second half must be 16-byte sized");
 
-// per-CTA single-player workspace, carved out of flat device arrays (index = blockIdx.x)
-struct SpArena {
-    SpKey* keys; float* vals; u32* edges; u8* n_edges; u32* hash; i32* counters; SpShared* shared;
-    i32* overflow_count;  // [1] rows whose SP block was dropped because the state arena overflowed
-    int enabled;
-};
-
-__global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_obs_v4(EnvView V, Tables T, float* __restrict__ obs, SpArena A) {
+__global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_obs_v4(EnvView V, Tables T, float* __restrict__ obs) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     float* tile = reinterpret_cast<float*>(s_raw);
     TableState* s_state = reinterpret_cast<TableState*>(s_raw + ENC_STATE_OFF);
@@ -126,20 +119,6 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_obs_v4(EnvView V, Tab
         Ctx c;
         c.S = s_state; c.W = nullptr; c.T = T; c.lane = lane; c.df = df;
         encode_obs_v4(e, c, nullptr);
-        if (half == 1 && A.enabled) {
-            SpCtx sp;
-            const size_t b = blockIdx.x;
-            sp.W.keys = A.keys + b * SP_NODE_CAP;
-            sp.W.vals = A.vals + b * (size_t)SP_NODE_CAP * 3 * SP_T_MAX;
-            sp.W.edges = A.edges + b * (size_t)SP_NODE_CAP * SP_EDGE_MAX;
-            sp.W.n_edges = A.n_edges + b * SP_NODE_CAP;
-            sp.W.hash = A.hash + b * SP_HASH_CAP;
-            sp.W.counters = A.counters + b * 4;
-            sp.sh = A.shared + b;
-            sp.T = T; sp.lane = lane; sp.warp = warp; sp.nwarps = ENC_THREADS / 32;
-            encode_sp_block(e, c, sp);
-            if (tid == 0 && sp.W.counters[1]) atomicAdd(A.overflow_count, 1);
-        }
         // make the generic-proxy smem writes visible to the async proxy, then one thread issues the bulk store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -153,6 +132,58 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_obs_v4(EnvView V, Tab
         }
         __syncthreads();
     }
+}
+
+// ---- single-player tables: level-synchronous DP over all rows of the step (csrc/mjx_sp.cuh)
+constexpr int SP_WARPS = 4;
+
+__global__ void k_sp_begin(SpGlobal G) {
+    if (threadIdx.x < SP_SLOTS) G.slot_count[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        if (G.counters[2]) G.counters[3] += 1;  // an overflow happened in the previous step
+        G.counters[0] = 0; G.counters[1] = 0; G.counters[2] = 0;
+    }
+}
+
+#define SP_KERNEL_PROLOGUE                                                                      \
+    __shared__ SpWarpScratch s_ws[SP_WARPS];                                                    \
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                 \
+    const int gwarp = blockIdx.x * SP_WARPS + warp, nwarps = gridDim.x * SP_WARPS;              \
+    SpCtx s; s.G = G; s.T = T; s.ws = &s_ws[warp]; s.lane = lane;                               \
+    Ctx c; c.S = nullptr; c.W = nullptr; c.T = T; c.lane = lane; c.df = nullptr;
+
+__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_init(SpGlobal G, Tables T, EnvView V) {
+    SP_KERNEL_PROLOGUE
+    (void)c;
+    const int n_rows = *V.n_rows;
+    for (int row = gwarp; row < n_rows; row += nwarps)
+        sp_stage_init(s, V.tables + V.row_table[row], row, V.row_table[row], V.row_seat[row] & 3);
+}
+
+__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_expand(SpGlobal G, Tables T, int slot) {
+    SP_KERNEL_PROLOGUE
+    const int n = min(G.slot_count[slot], G.slot_cap);
+    const i32* list = G.slot_list + (size_t)slot * G.slot_cap;
+    for (int i = gwarp; i < n; i += nwarps) sp_expand(s, c, list[i], slot);
+}
+
+__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_eval(SpGlobal G, Tables T, int slot) {
+    SP_KERNEL_PROLOGUE
+    const int n = min(G.slot_count[slot], G.slot_cap);
+    const i32* list = G.slot_list + (size_t)slot * G.slot_cap;
+    const bool is_w = sp_slot_is_w(slot);
+    const int k = sp_slot_shanten(slot);
+    for (int i = gwarp; i < n; i += nwarps) {
+        if (is_w) sp_eval_w(s, c, list[i], k); else sp_eval_d(s, c, list[i]);
+    }
+}
+
+__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_finalize(SpGlobal G, Tables T, EnvView V, float* __restrict__ obs) {
+    SP_KERNEL_PROLOGUE
+    (void)c;
+    const int n_rows = *V.n_rows;
+    for (int row = gwarp; row < n_rows; row += nwarps)
+        sp_stage_finalize(s, row, obs + (size_t)row * OBS_ROWS_V4 * OBS_COLS);
 }
 
 __global__ void k_policy_test(EnvView V, int kind, i64* actions, i64* trace, float* q_out) {
@@ -269,7 +300,8 @@ struct mjx_env {
     u64 *d_nonces = nullptr, *d_keys = nullptr;
     i64* d_dummy_actions = nullptr;
     u8* d_guard = nullptr;
-    SpArena sp;
+    SpGlobal sp;
+    int sp_enabled = 1;
     int enc_grid = 0;
 };
 
@@ -351,19 +383,27 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
     memset(&env->sp, 0, sizeof env->sp);
     env->enc_grid = g_sm_count * 3;
     {
-        const size_t g = (size_t)env->enc_grid;
-        SpArena& A = env->sp;
-        A.enabled = 1;
-        CU(cudaMalloc(&A.keys, g * SP_NODE_CAP * sizeof(SpKey)));
-        CU(cudaMalloc(&A.vals, g * SP_NODE_CAP * 3 * SP_T_MAX * sizeof(float)));
-        CU(cudaMalloc(&A.edges, g * SP_NODE_CAP * SP_EDGE_MAX * sizeof(u32)));
-        CU(cudaMalloc(&A.n_edges, g * SP_NODE_CAP));
-        CU(cudaMalloc(&A.hash, g * SP_HASH_CAP * sizeof(u32)));
-        CU(cudaMalloc(&A.counters, g * 4 * sizeof(i32)));
-        CU(cudaMalloc(&A.shared, g * sizeof(SpShared)));
-        CU(cudaMalloc(&A.overflow_count, sizeof(i32)));
-        CU(cudaMemset(A.overflow_count, 0, sizeof(i32)));
-        CU(cudaMemset(A.counters, 0, g * 4 * sizeof(i32)));
+        SpGlobal& G = env->sp;
+        G.node_cap = n_tables * 2048;
+        G.slot_cap = G.node_cap;
+        G.edge_cap = G.node_cap * 12;
+        int hc = 1;
+        while (hc < 2 * G.node_cap) hc <<= 1;
+        G.hash_cap = hc;
+        CU(cudaMalloc(&G.rows, cap * sizeof(SpRow)));
+        CU(cudaMalloc(&G.keys, (size_t)G.node_cap * sizeof(SpKey)));
+        CU(cudaMalloc(&G.node_row, (size_t)G.node_cap * sizeof(i32)));
+        CU(cudaMalloc(&G.vals, (size_t)G.node_cap * 3 * SP_T_MAX * sizeof(float)));
+        CU(cudaMalloc(&G.edge_begin, (size_t)G.node_cap * sizeof(u32)));
+        CU(cudaMalloc(&G.n_edges, (size_t)G.node_cap));
+        CU(cudaMalloc(&G.edge_child, (size_t)G.edge_cap * sizeof(u32)));
+        CU(cudaMalloc(&G.edge_meta, (size_t)G.edge_cap * sizeof(u16)));
+        CU(cudaMalloc(&G.hash, (size_t)G.hash_cap * sizeof(u32)));
+        CU(cudaMalloc(&G.slot_list, (size_t)SP_SLOTS * G.slot_cap * sizeof(i32)));
+        CU(cudaMalloc(&G.slot_count, SP_SLOTS * sizeof(i32)));
+        CU(cudaMalloc(&G.counters, 4 * sizeof(i32)));
+        CU(cudaMemset(G.counters, 0, 4 * sizeof(i32)));
+        CU(cudaMemset(G.slot_count, 0, SP_SLOTS * sizeof(i32)));
     }
     CU(cudaMemset(env->d_dummy_actions, 0, sizeof(i64) * cap));
     CU(cudaMemset(V.masks, 0, cap * ACTION_SPACE));
@@ -387,9 +427,10 @@ void mjx_env_destroy(mjx_env* env) {
     cudaFree(V.tables); cudaFree(V.n_rows); cudaFree(V.row_table); cudaFree(V.row_seat); cudaFree(V.row_step);
     cudaFree(V.masks); cudaFree(V.scores); cudaFree(V.ranks); cudaFree(V.done); cudaFree(V.steps); cudaFree(V.err);
     cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard);
-    SpArena& A = env->sp;
-    cudaFree(A.keys); cudaFree(A.vals); cudaFree(A.edges); cudaFree(A.n_edges); cudaFree(A.hash); cudaFree(A.counters);
-    cudaFree(A.shared); cudaFree(A.overflow_count);
+    SpGlobal& G = env->sp;
+    cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
+    cudaFree(G.edge_child); cudaFree(G.edge_meta); cudaFree(G.hash); cudaFree(G.slot_list); cudaFree(G.slot_count);
+    cudaFree(G.counters);
     delete env;
 }
 
@@ -419,21 +460,34 @@ int mjx_env_step(mjx_env* env, const int64_t* actions_dev, const float* q_values
 int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
     if (!env || !obs_dev) return fail(MJX_ERR_ARG, "mjx_env_encode_obs: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    k_encode_obs_v4<<<env->enc_grid, ENC_THREADS, ENC_SMEM_BYTES, st>>>(env->V, g_T, obs_dev, env->sp);
+    k_encode_obs_v4<<<env->enc_grid, ENC_THREADS, ENC_SMEM_BYTES, st>>>(env->V, g_T, obs_dev);
+    if (env->sp_enabled) {
+        // single-player block (rows 889..1011): init -> expand slots 0..7 -> evaluate slots 7..0 -> finalize
+        const SpGlobal& G = env->sp;
+        const int grid = g_sm_count * 8;
+        CU(cudaMemsetAsync(G.hash, 0, (size_t)G.hash_cap * sizeof(u32), st));
+        k_sp_begin<<<1, 32, 0, st>>>(G);
+        k_sp_init<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V);
+        for (int slot = 0; slot < SP_SLOTS; slot++) k_sp_expand<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+        for (int slot = SP_SLOTS - 1; slot >= 0; slot--) k_sp_eval<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+        k_sp_finalize<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev);
+    }
     CU(cudaGetLastError());
     return MJX_OK;
 }
 
 int mjx_env_set_sp(mjx_env* env, int enable) {
     if (!env) return fail(MJX_ERR_ARG, "mjx_env_set_sp: null env");
-    env->sp.enabled = enable ? 1 : 0;
+    env->sp_enabled = enable ? 1 : 0;
     return MJX_OK;
 }
 
 int mjx_env_sp_overflows(mjx_env* env, void* stream, int* n) {
     if (!env || !n) return fail(MJX_ERR_ARG, "mjx_env_sp_overflows: bad arguments");
-    CU(cudaMemcpyAsync(n, env->sp.overflow_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    int cnt[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(cnt, env->sp.counters, sizeof cnt, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
+    *n = cnt[3] + (cnt[2] ? 1 : 0);
     return MJX_OK;
 }
 

@@ -4,15 +4,20 @@
 // (SPCalculator with calc_tegawari = calc_shanten_down = maximize_win_prob = false, which is how
 // PlayerState calls it) -> state/obs_repr.rs:561-617, 632-692.
 //
-// The reference is a memoised recursion (AHashMap<State, Rc<Values>> per shanten level). Here the same
-// quantities are computed as a level-synchronous dynamic programme by one CTA per observation:
-//   1. expand: breadth-first over the DAG of reachable (hand, wall) states, alternating
-//      W-states (3n+1, waiting for a useful draw) and D-states (3n+2, choosing a shanten-keeping discard);
-//      one warp expands one state, lanes = the 34 tile ids (shanten of hand+-tile per lane), children are
-//      de-duplicated through an open-addressing hash table in the CTA's global workspace;
-//   2. evaluate: levels in reverse; one warp per state, lane i owns turn i and accumulates over the state's
-//      edges in the reference's iteration order with explicitly rounded f32 ops, so every per-turn
-//      tenpai / win / EV value follows the same sequence of roundings as the Rust code.
+// The reference is a memoised recursion per observation (AHashMap<State, Rc<Values>> per shanten level).
+// Here ALL observations of a step are solved together as one level-synchronous dynamic programme over the
+// union of their (hand, wall) state DAGs:
+//   slots      D3 W3 D2 W2 D1 W1 D0 W0   (D = 3n+2 hand choosing a shanten-keeping discard,
+//                                          W = 3n+1 hand waiting for a shanten-lowering draw)
+//   init       one warp per observation row: availability, parameters, root state -> its slot
+//   expand     one launch per slot, one warp per state: lanes = the 34 tile ids (shanten of hand+-tile per
+//              lane); children are interned in a global open-addressing hash table keyed by (row, state)
+//   evaluate   slots in reverse, one warp per state: lane i owns turn i and accumulates over the state's
+//              edges in the reference's iteration order with explicitly rounded f32 ops, so every
+//              tenpai / win / EV value follows the same sequence of roundings as the Rust code
+//   finalize   one warp per row: candidates, comparators, rows 889..1011 written into the obs tensor
+// Work is balanced across the whole GPU at state granularity (a 15k-state hand costs as much as 30 small
+// ones and is shared by all SMs), and there is no per-observation synchronisation.
 #pragma once
 #include "mjx_obs.cuh"
 
@@ -21,22 +26,18 @@ namespace mjx {
 constexpr int SP_T_MAX = 17;             // sp/mod.rs:42 MAX_TSUMOS_LEFT
 constexpr int SP_SHANTEN_THRES = 3;      // calc.rs:13
 constexpr int SP_MAX_TILES_LEFT = 34 * 4 - 1 - 13;  // calc.rs:14
-constexpr int SP_EDGE_MAX = 40;          // <= 37 draw kinds / <= 14 discards
-constexpr int SP_NODE_CAP = 32768;
-constexpr int SP_HASH_CAP = 65536;
-constexpr u32 SP_NO_CHILD = 0xFFFFFu;
+constexpr int SP_SLOTS = 8;
+constexpr u32 SP_NO_CHILD = 0xFFFFFFFFu;
 
 #ifdef MJX_HOST_EMUL
 #define SP_FMUL(a, b) ((a) * (b))
 #define SP_FADD(a, b) ((a) + (b))
 #define SP_FDIV(a, b) ((a) / (b))
-#define SP_CTA_SYNC() ((void)0)
 #else
 // never contracted into FMA: the reference rounds after every multiply and add
 #define SP_FMUL(a, b) __fmul_rn((a), (b))
 #define SP_FADD(a, b) __fadd_rn((a), (b))
 #define SP_FDIV(a, b) __fdiv_rn((a), (b))
-#define SP_CTA_SYNC() __syncthreads()
 #endif
 
 // sp/state.rs:10-21 (n_extra_tsumo is always 0 without tegawari)
@@ -48,37 +49,42 @@ struct SpKey {
 };
 static_assert(sizeof(SpKey) == 72, "SpKey layout");
 
-struct SpWork {  // one per CTA, in global memory
-    SpKey* keys;      // [SP_NODE_CAP]
-    float* vals;      // [SP_NODE_CAP][3][SP_T_MAX]
-    u32* edges;       // [SP_NODE_CAP][SP_EDGE_MAX]  child(20) | tile(6) << 20 | count(3) << 26
-    u8* n_edges;      // [SP_NODE_CAP]
-    u32* hash;        // [SP_HASH_CAP] node index + 1, 0 = empty
-    i32* counters;    // [0] n_nodes, [1] overflow flag
-};
-
-struct SpParams {  // sp/calc.rs:36-62 + per-call arguments
-    u8 tehai_len_div3;
-    bool is_menzen, prefer_riichi, calc_double_riichi, calc_haitei;
-    u8 bakaze, jikaze, num_doras_in_fuuro;
-    u8 n_dora;
+// per observation row: sp/calc.rs:36-62 parameters + what obs_repr.rs needs afterwards
+struct SpRow {
+    u8 tehai_len_div3, is_menzen, prefer_riichi, calc_double_riichi, calc_haitei;
+    u8 bakaze, jikaze, num_doras_in_fuuro, n_dora;
     u8 dora_ind[5];
-    const u8 *chis, *pons, *minkans, *ankans;
-    int n_chis, n_pons, n_minkans, n_ankans;
-    int T;        // tsumos_left = MAX_TSUMO
-    int n_left;   // tiles in the wall at the root
+    u8 melds[16];  // chis | pons | minkans | ankans
+    u8 n_chis, n_pons, n_minkans, n_ankans;
+    u8 T;          // tsumos_left = MAX_TSUMO
+    u8 n_left;     // tiles in the wall at the root
+    u8 avail;      // single_player_tables() is Ok
+    u8 has_values; // cur_shanten <= 3
+    u8 can_discard;   // effective flag handed to SPCalculator::calc (false after an accepted riichi)
+    u8 cd_flag;       // cans.can_discard (what obs_repr.rs branches on)
+    u8 after_riichi, last_self_tsumo;
+    i8 cur_shanten;
+    u8 seat;
+    i32 table;
+    i32 root;         // root node index, -1 if none
+    float fallback_ev;  // obs_repr.rs:604-616
+    SpKey root_key;
 };
 
-struct SpShared {  // per-CTA shared scratch
-    float tsumo_prob[4][SP_T_MAX];                          // calc.rs:136-146
-    float not_tsumo_prob[SP_MAX_TILES_LEFT + 1][SP_T_MAX];  // calc.rs:148-167
-    float scores[8][SP_EDGE_MAX][4];                        // per warp: get_score of each edge of a W0 state
-    u8 score_ok[8][SP_EDGE_MAX];
-    i32 level_begin[10];
-    i32 n_levels;
-    SpParams P;
-    u8 root_tehai[34], root_wall[34];
-    u8 melds[16];
+struct SpGlobal {
+    SpRow* rows;       // [row_cap]
+    SpKey* keys;       // [node_cap]
+    i32* node_row;     // [node_cap]
+    float* vals;       // [node_cap][3][SP_T_MAX]
+    u32* edge_begin;   // [node_cap]
+    u8* n_edges;       // [node_cap]
+    u32* edge_child;   // [edge_cap]
+    u16* edge_meta;    // [edge_cap] tile (6 bits) | count << 6
+    u32* hash;         // [hash_cap] node index + 1, 0 = empty
+    i32* slot_list;    // [SP_SLOTS][slot_cap] node indices
+    i32* slot_count;   // [SP_SLOTS]
+    i32* counters;     // [0] nodes, [1] edges, [2] overflow flag, [3] overflow events (cumulative)
+    i32 node_cap, edge_cap, hash_cap, slot_cap;
 };
 
 MJX_CONST float c_uradora_prob[5][13] = {  // algo/data/uradora_prob_table.txt
@@ -99,16 +105,27 @@ MJX_D int cmp_discard_priority(int l, int r) {
     return 0;
 }
 
-struct SpCtx {
-    SpWork W;
-    SpShared* sh;
-    Tables T;
-    int lane, warp, nwarps;
+// per-warp scratch (shared memory on device)
+struct SpWarpScratch {
+    float nts[SP_T_MAX];       // not_tsumo_prob row of the state (calc.rs:148-167)
+    float tpn[SP_T_MAX];       // tsumo_prob[cnt-1][j] * not_tsumo[j] of the current edge
+    float cv[3][SP_T_MAX];     // child values of the current edge
+    float scores[40][4];       // get_score of each winning draw of a W0 state
+    u8 score_ok[40];
+    u8 df[34];
+    u8 pad_[2];
 };
 
-MJX_D u32 sp_hash_key(const SpKey& k) {
+struct SpCtx {
+    SpGlobal G;
+    Tables T;
+    SpWarpScratch* ws;
+    int lane;
+};
+
+MJX_D u32 sp_hash_key(int row, const SpKey& k) {
     const u32* w = reinterpret_cast<const u32*>(&k);
-    u32 h = 2166136261u;
+    u32 h = 2166136261u ^ ((u32)row * 0x9E3779B9u);
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(SpKey) / 4); i++) { h ^= w[i]; h *= 16777619u; h ^= h >> 15; }
     return h;
@@ -123,52 +140,75 @@ MJX_D bool sp_key_eq(const SpKey& a, const SpKey& b) {
     return eq;
 }
 
-// find-or-insert; executed by ONE lane. Returns node index, or -1 on overflow.
-MJX_DN int sp_intern(SpCtx& s, const SpKey& key) {
-    u32 slot = sp_hash_key(key) & (SP_HASH_CAP - 1);
-    for (int probe = 0; probe < SP_HASH_CAP; probe++, slot = (slot + 1) & (SP_HASH_CAP - 1)) {
+MJX_D void sp_set_overflow(SpCtx& s) { s.G.counters[2] = 1; }
+
+// allocate a node in `slot`; executed by one lane. Returns -1 on overflow.
+MJX_DN int sp_new_node(SpCtx& s, int row, const SpKey& key, int slot) {
 #ifdef MJX_HOST_EMUL
-        u32 cur = s.W.hash[slot];
+    int idx = s.G.counters[0]++;
+    int pos = s.G.slot_count[slot]++;
+#else
+    int idx = atomicAdd(&s.G.counters[0], 1);
+    int pos = atomicAdd(&s.G.slot_count[slot], 1);
+#endif
+    if (idx >= s.G.node_cap || pos >= s.G.slot_cap) { sp_set_overflow(s); return -1; }
+    s.G.keys[idx] = key;
+    s.G.node_row[idx] = row;
+    s.G.n_edges[idx] = 0;
+    s.G.edge_begin[idx] = 0;
+    s.G.slot_list[(size_t)slot * s.G.slot_cap + pos] = idx;
+    return idx;
+}
+
+// find-or-insert (row, key) in `slot`; executed by ONE lane. Returns node index, or -1 on overflow.
+MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
+    const u32 mask = (u32)s.G.hash_cap - 1;
+    u32 h = sp_hash_key(row, key) & mask;
+    for (int probe = 0; probe < s.G.hash_cap; probe++, h = (h + 1) & mask) {
+#ifdef MJX_HOST_EMUL
+        u32 cur = s.G.hash[h];
         if (cur == 0) {
-            int idx = s.W.counters[0];
-            if (idx >= SP_NODE_CAP) { s.W.counters[1] = 1; return -1; }
-            s.W.counters[0] = idx + 1;
-            s.W.keys[idx] = key;
-            s.W.n_edges[idx] = 0;
-            s.W.hash[slot] = (u32)idx + 1;
+            int idx = sp_new_node(s, row, key, slot);
+            if (idx < 0) return -1;
+            s.G.hash[h] = (u32)idx + 1;
             return idx;
         }
-        if (sp_key_eq(s.W.keys[cur - 1], key)) return (int)cur - 1;
 #else
-        u32 cur = atomicAdd(&s.W.hash[slot], 0u);
+        u32 cur = atomicAdd(&s.G.hash[h], 0u);
         if (cur == 0) {
-            // claim the slot with a sentinel, publish the key, then the index
-            u32 prev = atomicCAS(&s.W.hash[slot], 0u, 0xFFFFFFFFu);
+            // claim with a sentinel, publish the node, then its index
+            u32 prev = atomicCAS(&s.G.hash[h], 0u, 0xFFFFFFFFu);
             if (prev == 0) {
-                int idx = atomicAdd(&s.W.counters[0], 1);
-                if (idx >= SP_NODE_CAP) { s.W.counters[1] = 1; atomicExch(&s.W.hash[slot], 0u); return -1; }
-                s.W.keys[idx] = key;
-                s.W.n_edges[idx] = 0;
-                __threadfence_block();
-                atomicExch(&s.W.hash[slot], (u32)idx + 1);
+                int idx = sp_new_node(s, row, key, slot);
+                if (idx < 0) { atomicExch(&s.G.hash[h], 0u); return -1; }
+                __threadfence();
+                atomicExch(&s.G.hash[h], (u32)idx + 1);
                 return idx;
             }
             cur = prev;
         }
-        while (cur == 0xFFFFFFFFu) cur = atomicAdd(&s.W.hash[slot], 0u);  // another warp is publishing
-        __threadfence_block();
-        if (sp_key_eq(s.W.keys[cur - 1], key)) return (int)cur - 1;
+        while (cur == 0xFFFFFFFFu) cur = atomicAdd(&s.G.hash[h], 0u);  // another warp is publishing this slot
+        __threadfence();
 #endif
+        const int ci = (int)cur - 1;
+        if (s.G.node_row[ci] == row && sp_key_eq(s.G.keys[ci], key)) return ci;
     }
-    s.W.counters[1] = 1;
+    sp_set_overflow(s);
     return -1;
 }
 
-// Expand one node (one warp). is_w: W-state at shanten k (edges = useful draws) else D-state at shanten k
-// (edges = shanten-keeping discards). Children are interned unless `leaf`.
-MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, bool is_w, int k, bool leaf) {
-    const SpKey key = s.W.keys[node];
-    const int len = s.sh->P.tehai_len_div3;
+MJX_D bool sp_slot_is_w(int slot) { return (slot & 1) != 0; }
+MJX_D int sp_slot_shanten(int slot) { return 3 - (slot >> 1); }
+MJX_D float* sp_vals(const SpCtx& s, int node, int which) { return s.G.vals + ((size_t)node * 3 + which) * SP_T_MAX; }
+
+// Expand one state (one warp): edges = shanten-lowering draws (W) or shanten-keeping discards (D).
+MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
+    const bool is_w = sp_slot_is_w(slot);
+    const int k = sp_slot_shanten(slot);
+    const bool leaf = is_w && k == 0;
+    const int row = s.G.node_row[node];
+    const SpKey key = s.G.keys[node];
+    const int len = s.G.rows[row].tehai_len_div3;
     const HandSig base = hand_sig(key.tehai);
     u64 eff, unused;
     if (is_w) {
@@ -183,7 +223,21 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, bool is_w, int k, bool l
         }, eff, unused);
     }
     if (MJX_IS_L0(c)) {
+        // count edges (an effective 5 with the aka still in the wall splits in two: sp/state.rs:160-176)
         int ne = 0;
+        for (u64 rest = eff; rest; rest &= rest - 1) {
+            const int t = mjx_ffsll(rest) - 1;
+            const int suit5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
+            if (is_w && suit5 >= 0 && ((key.akas >> (3 + suit5)) & 1)) ne += key.wall[t] >= 2 ? 2 : 1;
+            else ne += 1;
+        }
+#ifdef MJX_HOST_EMUL
+        int eb = s.G.counters[1]; s.G.counters[1] += ne;
+#else
+        int eb = atomicAdd(&s.G.counters[1], ne);
+#endif
+        if (eb + ne > s.G.edge_cap) { sp_set_overflow(s); ne = 0; eb = 0; eff = 0; }
+        int w = 0;
         for (u64 rest = eff; rest; rest &= rest - 1) {
             const int t = mjx_ffsll(rest) - 1;
             const int suit5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
@@ -205,11 +259,12 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, bool is_w, int k, bool l
                         ck.tehai[t] += 1;
                         ck.wall[t] -= 1;
                         if (is_aka(tile)) ck.akas = (u8)((ck.akas | (1 << suit5)) & ~(1 << (3 + suit5)));
-                        int ci = sp_intern(s, ck);
-                        if (ci < 0) break;
-                        child = (u32)ci;
+                        int ci = sp_intern(s, row, ck, slot + 1);
+                        child = ci < 0 ? SP_NO_CHILD : (u32)ci;
                     }
-                    if (ne < SP_EDGE_MAX) s.W.edges[(size_t)node * SP_EDGE_MAX + ne++] = child | ((u32)tile << 20) | ((u32)cnt << 26);
+                    s.G.edge_child[eb + w] = child;
+                    s.G.edge_meta[eb + w] = (u16)(tile | (cnt << 6));
+                    w++;
                 }
             } else {
                 // sp/state.rs:127-132: the aka is discarded only when it is the last 5 of its suit in hand
@@ -218,19 +273,20 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, bool is_w, int k, bool l
                 SpKey ck = key;
                 ck.tehai[t] -= 1;
                 if (is_aka(tile)) ck.akas = (u8)(ck.akas & ~(1 << suit5));
-                int ci = sp_intern(s, ck);
-                if (ci < 0) break;
-                if (ne < SP_EDGE_MAX) s.W.edges[(size_t)node * SP_EDGE_MAX + ne++] = (u32)ci | ((u32)tile << 20);
+                int ci = sp_intern(s, row, ck, slot + 1);
+                s.G.edge_child[eb + w] = ci < 0 ? SP_NO_CHILD : (u32)ci;
+                s.G.edge_meta[eb + w] = (u16)tile;
+                w++;
             }
         }
-        s.W.n_edges[node] = (u8)ne;
+        s.G.edge_begin[node] = (u32)eb;
+        s.G.n_edges[node] = (u8)w;
     }
     MJX_SYNCWARP();
 }
 
 // calc.rs:640-758 for one winning draw; executed by one lane. Returns false when there is no yaku.
-MJX_DN bool sp_get_score(const SpCtx& s, const SpKey& key, int win_tile, float* scores) {
-    const SpParams& P = s.sh->P;
+MJX_DN bool sp_get_score(const SpCtx& s, const SpRow& P, const SpKey& key, int win_tile, float* scores) {
     u8 th[34];
     for (int i = 0; i < 34; i++) th[i] = key.tehai[i];
     const int wid = deaka(win_tile);
@@ -241,9 +297,9 @@ MJX_DN bool sp_get_score(const SpCtx& s, const SpKey& key, int win_tile, float* 
     wall[wid] -= 1;
     AgariQuery q;
     q.tehai = th;
-    q.chis = P.chis; q.pons = P.pons; q.minkans = P.minkans; q.ankans = P.ankans;
+    q.chis = P.melds; q.pons = P.melds + 4; q.minkans = P.melds + 8; q.ankans = P.melds + 12;
     q.n_chis = P.n_chis; q.n_pons = P.n_pons; q.n_minkans = P.n_minkans; q.n_ankans = P.n_ankans;
-    q.bakaze = P.bakaze; q.jikaze = P.jikaze; q.winning_tile = wid; q.is_ron = false; q.is_menzen = P.is_menzen;
+    q.bakaze = P.bakaze; q.jikaze = P.jikaze; q.winning_tile = wid; q.is_ron = false; q.is_menzen = P.is_menzen != 0;
     const bool is_oya = P.jikaze == T_E;
     const int additional = P.is_menzen ? (P.prefer_riichi ? 2 : 1) : 0;
     int doras = mjx_popc((u32)akas_in_hand) + P.num_doras_in_fuuro;
@@ -291,111 +347,133 @@ MJX_DN bool sp_get_score(const SpCtx& s, const SpKey& key, int win_tile, float* 
     return true;
 }
 
-MJX_D float* sp_vals(const SpCtx& s, int node, int which) { return s.W.vals + ((size_t)node * 3 + which) * SP_T_MAX; }
+#ifdef MJX_HOST_EMUL
+#define SP_FOR_LANES(i, n) for (int i = 0; i < (n); i++)
+#else
+#define SP_FOR_LANES(i, n) for (int i = s.lane; i < (n); i += 32)
+#endif
 
 // calc.rs:447-561 draw_without_tegawari_slow for one W-state at shanten k (one warp, lane i = turn i)
 MJX_DN void sp_eval_w(SpCtx& s, const Ctx& c, int node, int k) {
-    const SpParams& P = s.sh->P;
-    const int T = P.T;
-    const int ne = s.W.n_edges[node];
-    const u32* edges = s.W.edges + (size_t)node * SP_EDGE_MAX;
+    const int row = s.G.node_row[node];
+    const SpRow& P = s.G.rows[row];
+    const int T = P.T, n_left = P.n_left;
+    const int ne = s.G.n_edges[node];
+    const u32 eb = s.G.edge_begin[node];
+    SpWarpScratch& ws = *s.ws;
     int sum_required = 0;
-    for (int e = 0; e < ne; e++) sum_required += (edges[e] >> 26) & 7;
+    for (int e = 0; e < ne; e++) sum_required += s.G.edge_meta[eb + e] >> 6;
     sum_required &= 0xFF;
-    const float* not_tsumo = s.sh->not_tsumo_prob[sum_required <= SP_MAX_TILES_LEFT ? sum_required : SP_MAX_TILES_LEFT];
-    float (*sc)[4] = s.sh->scores[s.warp];
-    u8* sc_ok = s.sh->score_ok[s.warp];
-    if (k == 0) {
-        const SpKey key = s.W.keys[node];
-#ifdef MJX_HOST_EMUL
-        for (int e = 0; e < ne; e++) sc_ok[e] = sp_get_score(s, key, (edges[e] >> 20) & 63, sc[e]) ? 1 : 0;
-#else
-        for (int e = c.lane; e < ne; e += 32) sc_ok[e] = sp_get_score(s, key, (edges[e] >> 20) & 63, sc[e]) ? 1 : 0;
-        __syncwarp();
-#endif
+    // not_tsumo_prob_table[sum_required][j], recomputed with the table's own recurrence (calc.rs:158-165)
+    SP_FOR_LANES(j, T) {
+        float v = 0.f;
+        const int i0 = sum_required;
+        if (i0 <= n_left && i0 <= SP_MAX_TILES_LEFT) {
+            const int lim = min(T - 1, n_left - i0);
+            if (j <= lim) {
+                v = 1.f;
+                for (int q = 0; q < j; q++) v = SP_FDIV(SP_FMUL(v, (float)(n_left - i0 - q)), (float)(n_left - q));
+            }
+        }
+        ws.nts[j] = v;
     }
+    if (k == 0) {
+        const SpKey key = s.G.keys[node];
+        SP_FOR_LANES(e, ne) {
+            float sc[4];
+            bool ok = sp_get_score(s, P, key, s.G.edge_meta[eb + e] & 63, sc);
+            ws.score_ok[e] = ok ? 1 : 0;
+            for (int q = 0; q < 4; q++) ws.scores[e][q] = sc[q];
+        }
+    }
+    MJX_SYNCWARP();
+    float tenpai = 0.f, win = 0.f, ev = 0.f;  // lane-private accumulators (emulation: see below)
 #ifdef MJX_HOST_EMUL
-    for (int i = 0; i < T; i++) {
-#else
-    { const int i = c.lane; if (i < T) {
+    float a_t[SP_T_MAX] = {0}, a_w[SP_T_MAX] = {0}, a_v[SP_T_MAX] = {0};
 #endif
-        float tenpai = 0.f, win = 0.f, ev = 0.f;
-        const float m = not_tsumo[i];
-        if (m != 0.f) {
-            for (int e = 0; e < ne; e++) {
-                const u32 ed = edges[e];
-                const int cnt = (ed >> 26) & 7;
-                if (k == 0 && !sc_ok[e]) continue;
-                const float* tsumo_probs = s.sh->tsumo_prob[cnt - 1];
-                const float *nt = nullptr, *nw = nullptr, *nv = nullptr;
-                if (k > 0) {
-                    const int child = (int)(ed & 0xFFFFF);
-                    nt = sp_vals(s, child, 0); nw = sp_vals(s, child, 1); nv = sp_vals(s, child, 2);
-                }
+    const bool assume_riichi = P.is_menzen && P.prefer_riichi;
+    for (int e = 0; e < ne; e++) {
+        const int cnt = s.G.edge_meta[eb + e] >> 6;
+        if (k == 0 && !ws.score_ok[e]) continue;  // uniform
+        const u32 child = s.G.edge_child[eb + e];
+        if (k > 0 && child == SP_NO_CHILD) continue;  // only after an overflow
+        MJX_SYNCWARP();
+        SP_FOR_LANES(j, T) {
+            ws.tpn[j] = SP_FMUL(SP_FDIV((float)cnt, (float)(n_left - j)), ws.nts[j]);
+            if (k > 0) {
+                ws.cv[0][j] = sp_vals(s, (int)child, 0)[j];
+                ws.cv[1][j] = sp_vals(s, (int)child, 1)[j];
+                ws.cv[2][j] = sp_vals(s, (int)child, 2)[j];
+            }
+        }
+        MJX_SYNCWARP();
+        SP_FOR_LANES(i, T) {
+#ifdef MJX_HOST_EMUL
+            tenpai = a_t[i]; win = a_w[i]; ev = a_v[i];
+#endif
+            const float m = ws.nts[i];
+            if (m != 0.f) {
                 for (int j = i; j < T; j++) {
-                    const float n = not_tsumo[j];
-                    if (n == 0.f) break;
-                    const float prob = SP_FDIV(SP_FMUL(tsumo_probs[j], n), m);
+                    if (ws.nts[j] == 0.f) break;
+                    const float prob = SP_FDIV(ws.tpn[j], m);
                     if (k == 0) {
-                        const bool assume_riichi = P.is_menzen && P.prefer_riichi;
                         const int han_plus = (assume_riichi && P.calc_double_riichi && i == 0) + (assume_riichi && j == i) +
                                              (P.calc_haitei && j == T - 1);
                         win = SP_FADD(win, prob);
-                        ev = SP_FADD(ev, SP_FMUL(prob, sc[e][han_plus]));
+                        ev = SP_FADD(ev, SP_FMUL(prob, ws.scores[e][han_plus]));
                     } else {
                         if (k == 1) tenpai = SP_FADD(tenpai, prob);
                         if (j < T - 1) {
-                            if (k > 1) tenpai = SP_FADD(tenpai, SP_FMUL(prob, nt[j + 1]));
-                            win = SP_FADD(win, SP_FMUL(prob, nw[j + 1]));
-                            ev = SP_FADD(ev, SP_FMUL(prob, nv[j + 1]));
+                            if (k > 1) tenpai = SP_FADD(tenpai, SP_FMUL(prob, ws.cv[0][j + 1]));
+                            win = SP_FADD(win, SP_FMUL(prob, ws.cv[1][j + 1]));
+                            ev = SP_FADD(ev, SP_FMUL(prob, ws.cv[2][j + 1]));
                         }
                     }
                 }
             }
+#ifdef MJX_HOST_EMUL
+            a_t[i] = tenpai; a_w[i] = win; a_v[i] = ev;
+#endif
         }
+    }
+    MJX_SYNCWARP();
+    SP_FOR_LANES(i, T) {
+#ifdef MJX_HOST_EMUL
+        tenpai = a_t[i]; win = a_w[i]; ev = a_v[i];
+#endif
         sp_vals(s, node, 0)[i] = tenpai;
         sp_vals(s, node, 1)[i] = win;
         sp_vals(s, node, 2)[i] = ev;
-#ifdef MJX_HOST_EMUL
     }
-#else
-    } }
-    __syncwarp();
-#endif
+    MJX_SYNCWARP();
 }
 
 // calc.rs:563-637 discard_slow for one D-state (one warp, lane i = turn i)
 MJX_DN void sp_eval_d(SpCtx& s, const Ctx& c, int node) {
-    const int T = s.sh->P.T;
-    const int ne = s.W.n_edges[node];
-    const u32* edges = s.W.edges + (size_t)node * SP_EDGE_MAX;
-#ifdef MJX_HOST_EMUL
-    for (int i = 0; i < T; i++) {
-#else
-    { const int i = c.lane; if (i < T) {
-#endif
+    const int T = s.G.rows[s.G.node_row[node]].T;
+    const int ne = s.G.n_edges[node];
+    const u32 eb = s.G.edge_begin[node];
+    SP_FOR_LANES(i, T) {
         const float FMIN = -3.40282347e+38f;
         float bt = FMIN, bw = FMIN, bv = FMIN;
         int best_tile = T_UNK;
         i32 best_value = (i32)0x80000000;
         for (int e = 0; e < ne; e++) {
-            const int child = (int)(edges[e] & 0xFFFFF), tile = (edges[e] >> 20) & 63;
-            const float v = sp_vals(s, child, 2)[i];
-            const i32 value = (i32)v;  // exp_values are finite and < 2^31 here; Rust `as i32` truncates the same way
+            const u32 child = s.G.edge_child[eb + e];
+            if (child == SP_NO_CHILD) continue;
+            const int tile = s.G.edge_meta[eb + e] & 63;
+            const float v = sp_vals(s, (int)child, 2)[i];
+            const i32 value = (i32)v;  // finite and < 2^31 here; Rust `as i32` truncates the same way
             if (value > best_value || (value == best_value && cmp_discard_priority(tile, best_tile) > 0)) {
-                bt = sp_vals(s, child, 0)[i]; bw = sp_vals(s, child, 1)[i]; bv = v;
+                bt = sp_vals(s, (int)child, 0)[i]; bw = sp_vals(s, (int)child, 1)[i]; bv = v;
                 best_value = value; best_tile = tile;
             }
         }
         sp_vals(s, node, 0)[i] = bt;
         sp_vals(s, node, 1)[i] = bw;
         sp_vals(s, node, 2)[i] = bv;
-#ifdef MJX_HOST_EMUL
     }
-#else
-    } }
-    __syncwarp();
-#endif
+    MJX_SYNCWARP();
 }
 
 // per-candidate summary used by the obs rows
@@ -426,8 +504,7 @@ MJX_D int sp_cand_cmp(const SpCand& l, const SpCand& r, int by /*0 EV, 3 NotShan
 }
 
 // required tiles of a W-state hand (sp/state.rs:181-201): tiles in the wall that lower the shanten
-MJX_DN void sp_required(const SpCtx& s, const Ctx& c, const u8* tehai, const u8* wall, u64* set, int* num) {
-    const int len = s.sh->P.tehai_len_div3;
+MJX_DN void sp_required(const SpCtx& s, const Ctx& c, int len, const u8* tehai, const u8* wall, u64* set, int* num) {
     const HandSig base = hand_sig(tehai);
     const int cur = shanten_all_sig(s.T, base, len);
     u64 req, unused;
@@ -442,27 +519,33 @@ MJX_DN void sp_required(const SpCtx& s, const Ctx& c, const u8* tehai, const u8*
 }
 
 // agent_helper.rs:467-503 from the table record
-MJX_D int real_time_shanten(const Ctx& c, const TableState* S, int p) {
+MJX_D int real_time_shanten(const Tables& T, const TableState* S, int p) {
     const SeatPrivate& P = S->priv[p];
     if (!(P.cans & CAN_DISCARD)) return P.shanten;
     if (P.shanten > 0) return (P.flags & PF_HAS_NEXT_SHANTEN_DISCARD) ? P.shanten - 1 : P.shanten;
     if (P.last_self_tsumo != T_NONE) return ((P.waits >> deaka(P.last_self_tsumo)) & 1) ? -1 : 0;
-    return shanten_all(c.T, P.tehai, P.tehai_len_div3);
+    return shanten_all(T, P.tehai, P.tehai_len_div3);
 }
 
-// Encodes obs v4 rows 889..1011 into the (second-half) tile. Called by every thread of the CTA.
-MJX_DN void encode_sp_block(EncCtx& e, const Ctx& c, SpCtx& s) {
-    const TableState* S = e.S;
-    const int p = e.seat;
+// ---- stage: init (one warp per observation row). agent_helper.rs:509-593 up to the SPCalculator::calc call.
+MJX_DN void sp_stage_init(SpCtx& s, const TableState* S, int row, int table, int seat) {
+    const int p = seat;
     const SeatPrivate& PV = S->priv[p];
     const SeatPublic& PU = S->pub[p];
     const u16 cans = PV.cans;
-    const u8* df = e.dora_factor;
-    const bool tid0 = s.warp == 0 && s.lane == 0;
+    // dora factors of this record (for doras in melds and the fallback agari value)
+    MJX_FOR_TILES(s, t) {
+        int f = 0;
+        for (int q = 0; q < S->n_dora; q++) f += tile_next(S->wall[60 - q]) == t;
+        s.ws->df[t] = (u8)f;
+    }
+    MJX_END_TILES(s);
+    const u8* df = s.ws->df;
+    Ctx c;
+    c.S = const_cast<TableState*>(S); c.W = nullptr; c.T = s.T; c.lane = s.lane; c.df = df;
 
-    // ---- agent_helper.rs:509-531: availability
     bool can_discard = (cans & CAN_DISCARD) != 0;
-    const int cur_shanten = real_time_shanten(c, S, p);
+    const int cur_shanten = real_time_shanten(s.T, S, p);
     int tsumos_left = 0;
     bool calc_haitei = false;
     bool avail = S->tiles_left >= 4 && cur_shanten >= 0;
@@ -475,238 +558,179 @@ MJX_DN void encode_sp_block(EncCtx& e, const Ctx& c, SpCtx& s) {
         }
         avail = tsumos_left >= 1;
     }
-    if (!avail) {
-        // obs_repr.rs:604-616: min tsumo-agari points as the max EV, everything else skipped
-        float v = 0.f;
-        if (cans & CAN_AGARI) {
-            bool ok;
-            const bool is_ron = (cans & CAN_RON_AGARI) != 0;
-            Point pt = agari_points(c, p, is_ron, 0, &ok);
-            if (ok) v = (float)tsumo_total(pt, p == S->oya);
+    float fallback = 0.f;
+    if (!avail && (cans & CAN_AGARI)) {
+        // obs_repr.rs:604-616: agari_points(cans.can_ron_agari, &[]).tsumo_total(is_oya), 0 on Err
+        bool ok;
+        Point pt = agari_points(c, p, (cans & CAN_RON_AGARI) != 0, 0, &ok);
+        if (ok) fallback = (float)tsumo_total(pt, p == S->oya);
+    }
+    if (MJX_IS_L0(s)) {
+        SpRow& R = s.G.rows[row];
+        R.avail = avail ? 1 : 0;
+        R.fallback_ev = fallback;
+        R.table = table; R.seat = (u8)seat;
+        R.root = -1;
+        R.cd_flag = (cans & CAN_DISCARD) ? 1 : 0;
+        R.cur_shanten = (i8)cur_shanten;
+        R.has_values = cur_shanten <= SP_SHANTEN_THRES ? 1 : 0;
+        R.last_self_tsumo = PV.last_self_tsumo;
+        if (avail) {
+            R.tehai_len_div3 = PV.tehai_len_div3;
+            R.is_menzen = (PV.flags & PF_IS_MENZEN) ? 1 : 0;
+            R.prefer_riichi = S->scores[p] >= 1000 ? 1 : 0;
+            R.calc_double_riichi = (can_discard && (PV.flags & PF_CAN_W_RIICHI)) ? 1 : 0;
+            R.calc_haitei = calc_haitei ? 1 : 0;
+            R.bakaze = (u8)(T_E + S->kyoku / 4);
+            R.jikaze = (u8)(T_E + ((p + 4 - S->oya) & 3));
+            R.n_dora = S->n_dora;
+            for (int i = 0; i < 5; i++) R.dora_ind[i] = i < S->n_dora ? S->wall[60 - i] : 0;
+            for (int i = 0; i < 4; i++) {
+                R.melds[i] = PV.chis[i]; R.melds[4 + i] = PV.pons[i]; R.melds[8 + i] = PV.minkans[i]; R.melds[12 + i] = PV.ankans[i];
+            }
+            R.n_chis = PV.n_chis; R.n_pons = PV.n_pons; R.n_minkans = PV.n_minkans; R.n_ankans = PV.n_ankans;
+            int nf = 0;  // agent_helper.rs:533-545
+            if (!(R.is_menzen && PU.n_ankan == 0)) {
+                for (int f = 0; f < PU.n_fuuro; f++)
+                    for (int j = 0; j < 4; j++) { int t = PU.fuuro[f][j]; if (t != T_NONE) nf += df[deaka(t)] + (is_aka(t) ? 1 : 0); }
+                for (int j = 0; j < PU.n_ankan; j++) { int t = PU.ankan[j]; nf += 4 * df[t] + ((t == T_5M || t == T_5P || t == T_5S) ? 1 : 0); }
+            }
+            R.num_doras_in_fuuro = (u8)nf;
+            R.T = (u8)tsumos_left;
+            const bool after_riichi = can_discard && ((S->riichi_accepted >> p) & 1);
+            R.after_riichi = after_riichi ? 1 : 0;
+            R.can_discard = (can_discard && !after_riichi) ? 1 : 0;
+            SpKey root;
+            int akas_hand = PV.akas_in_hand;
+            for (int t = 0; t < 34; t++) root.tehai[t] = PV.tehai[t];
+            if (after_riichi) {
+                int lt = PV.last_self_tsumo;
+                root.tehai[deaka(lt)] -= 1;
+                if (is_aka(lt)) akas_hand &= ~(1 << (lt - T_5MR));
+            }
+            int n_left = 0;
+            for (int t = 0; t < 34; t++) {
+                int seen = S->public_seen[t] + PV.tehai[t];  // tiles_seen is NOT adjusted for the riichi discard
+                root.wall[t] = (u8)(4 - seen);
+                n_left += 4 - seen;
+            }
+            R.n_left = (u8)n_left;
+            const int akas_seen = S->akas_public | PV.akas_in_hand;
+            root.akas = (u8)((akas_hand & 7) | (((~akas_seen) & 7) << 3));
+            root.pad_[0] = root.pad_[1] = root.pad_[2] = 0;
+            R.root_key = root;
+            if (R.has_values) {
+                const int slot = 2 * (3 - cur_shanten) + (R.can_discard ? 0 : 1);
+                R.root = sp_new_node(s, row, root, slot);
+            }
         }
-        if (ENC_SECTION(e, 6, false)) {
-            ENC_FILL(e, 889, fminf(fmaxf(v, 0.f), 100000.f) / 100000.f);
-            ENC_FILL(e, 890, fminf(fmaxf(v, 0.f), 30000.f) / 30000.f);
-        }
+    }
+    MJX_SYNCWARP();
+}
+
+// ---- stage: finalize (one warp per row): candidates -> obs rows 889..1011 (obs_repr.rs:561-617, 644-692)
+// `obs_row` points at this observation's [1012][34] block in global memory (rows 889.. are zero on entry).
+MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
+    const SpRow& R = s.G.rows[row];
+    Ctx c;
+    c.S = nullptr; c.W = nullptr; c.T = s.T; c.lane = s.lane; c.df = nullptr;
+#ifdef MJX_HOST_EMUL
+#define SPO_FILL(r, v) do { for (int c_ = 0; c_ < 34; c_++) obs_row[(r) * 34 + c_] = (v); } while (0)
+#define SPO_ASSIGN(r, col, v) do { obs_row[(r) * 34 + (col)] = (v); } while (0)
+#else
+#define SPO_FILL(r, v) do { obs_row[(r) * 34 + s.lane] = (v); if (s.lane < 2) obs_row[(r) * 34 + 32 + s.lane] = (v); } while (0)
+#define SPO_ASSIGN(r, col, v) do { if (s.lane == 0) obs_row[(r) * 34 + (col)] = (v); } while (0)
+#endif
+    if (!R.avail) {
+        const float v = R.fallback_ev;
+        SPO_FILL(889, fminf(fmaxf(v, 0.f), 100000.f) / 100000.f);
+        SPO_FILL(890, fminf(fmaxf(v, 0.f), 30000.f) / 30000.f);
         return;
     }
-
-    // ---- parameters (agent_helper.rs:533-585)
-    SpShared* sh = s.sh;
-    SP_CTA_SYNC();
-    if (tid0) {
-        SpParams& P = sh->P;
-        P.tehai_len_div3 = PV.tehai_len_div3;
-        P.is_menzen = (PV.flags & PF_IS_MENZEN) != 0;
-        P.prefer_riichi = S->scores[p] >= 1000;
-        P.calc_double_riichi = can_discard && (PV.flags & PF_CAN_W_RIICHI);
-        P.calc_haitei = calc_haitei;
-        P.bakaze = T_E + S->kyoku / 4;
-        P.jikaze = T_E + ((p + 4 - S->oya) & 3);
-        P.n_dora = S->n_dora;
-        for (int i = 0; i < 5; i++) P.dora_ind[i] = i < S->n_dora ? (u8)dora_indicator(S, i) : 0;
-        for (int i = 0; i < 4; i++) {
-            sh->melds[i] = PV.chis[i]; sh->melds[4 + i] = PV.pons[i]; sh->melds[8 + i] = PV.minkans[i]; sh->melds[12 + i] = PV.ankans[i];
-        }
-        P.chis = sh->melds; P.pons = sh->melds + 4; P.minkans = sh->melds + 8; P.ankans = sh->melds + 12;
-        P.n_chis = PV.n_chis; P.n_pons = PV.n_pons; P.n_minkans = PV.n_minkans; P.n_ankans = PV.n_ankans;
-        // num_doras_in_fuuro = doras_owned[0] - doras in tehai - akas in hand (agent_helper.rs:533-545)
-        int nf = 0;
-        if (!(P.is_menzen && PU.n_ankan == 0)) {
-            for (int f = 0; f < PU.n_fuuro; f++)
-                for (int j = 0; j < 4; j++) { int t = PU.fuuro[f][j]; if (t != T_NONE) nf += df[deaka(t)] + (is_aka(t) ? 1 : 0); }
-            for (int j = 0; j < PU.n_ankan; j++) { int t = PU.ankan[j]; nf += 4 * df[t] + ((t == T_5M || t == T_5P || t == T_5S) ? 1 : 0); }
-        }
-        P.num_doras_in_fuuro = (u8)nf;
-        P.T = tsumos_left;
-        // root hand / wall (InitState -> State, sp/state.rs:35-54)
-        int akas_hand = PV.akas_in_hand;
-        for (int t = 0; t < 34; t++) sh->root_tehai[t] = PV.tehai[t];
-        const bool after_riichi = can_discard && ((S->riichi_accepted >> p) & 1);
-        if (after_riichi) {
-            int lt = PV.last_self_tsumo;
-            sh->root_tehai[deaka(lt)] -= 1;
-            if (is_aka(lt)) akas_hand &= ~(1 << (lt - T_5MR));
-        }
-        int n_left = 0;
-        for (int t = 0; t < 34; t++) {
-            int seen = S->public_seen[t] + PV.tehai[t];  // tiles_seen is NOT adjusted for the riichi discard
-            sh->root_wall[t] = (u8)(4 - seen);
-            n_left += 4 - seen;
-        }
-        P.n_left = n_left;
-        SpKey root;
-        for (int t = 0; t < 34; t++) { root.tehai[t] = sh->root_tehai[t]; root.wall[t] = sh->root_wall[t]; }
-        const int akas_seen = S->akas_public | PV.akas_in_hand;
-        root.akas = (u8)((akas_hand & 7) | (((~akas_seen) & 7) << 3));
-        root.pad_[0] = root.pad_[1] = root.pad_[2] = 0;
-        s.W.counters[0] = 1;
-        s.W.counters[1] = 0;
-        s.W.keys[0] = root;
-        s.W.n_edges[0] = 0;
-    }
-    SP_CTA_SYNC();
-    const bool after_riichi = can_discard && ((S->riichi_accepted >> p) & 1);
-    if (after_riichi) can_discard = false;
-    const SpParams& P = sh->P;
-    const int T = P.T;
-
-    // ---- candidate list
+    if (s.G.counters[2]) return;  // arena overflow this step: leave the block zero (counted, never silent)
+    const int cur_shanten = R.cur_shanten;
+    const bool has_values = R.has_values != 0, can_discard = R.can_discard != 0;
+    const int T = R.T, len = R.tehai_len_div3;
     SpCand cands[14];
     int n_cands = 0;
-    const bool has_values = cur_shanten <= SP_SHANTEN_THRES;
-
     if (!has_values) {
-        // calc.rs:281-314 analyze_*_simple: required tiles only; done redundantly by every warp (uniform)
+        // calc.rs:281-314 analyze_*_simple
         if (can_discard) {
-            const HandSig base = hand_sig(sh->root_tehai);
+            const HandSig base = hand_sig(R.root_key.tehai);
             for (int t = 0; t < 34; t++) {
-                if (sh->root_tehai[t] == 0) continue;
+                if (R.root_key.tehai[t] == 0) continue;
                 u8 th[34];
-                for (int i = 0; i < 34; i++) th[i] = sh->root_tehai[i];
+                for (int i = 0; i < 34; i++) th[i] = R.root_key.tehai[i];
                 th[t] -= 1;
-                int after = shanten_all_sig(s.T, sig_variant(base, t, -1, sh->root_tehai[t]), P.tehai_len_div3);
+                int after = shanten_all_sig(s.T, sig_variant(base, t, -1, R.root_key.tehai[t]), len);
                 SpCand& cd = cands[n_cands++];
                 const int k5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
-                cd.tile = (k5 >= 0 && ((s.W.keys[0].akas >> k5) & 1) && sh->root_tehai[t] == 1) ? T_5MR + k5 : t;
+                cd.tile = (k5 >= 0 && ((R.root_key.akas >> k5) & 1) && R.root_key.tehai[t] == 1) ? T_5MR + k5 : t;
                 cd.node = -1;
                 cd.shanten_down = after - cur_shanten == 1;
                 cd.t0 = cd.w0 = cd.e0 = 0.f;
-                sp_required(s, c, th, sh->root_wall, &cd.required, &cd.num_required);
+                sp_required(s, c, len, th, R.root_key.wall, &cd.required, &cd.num_required);
             }
         } else {
             SpCand& cd = cands[n_cands++];
             cd.tile = T_UNK; cd.node = -1; cd.shanten_down = false; cd.t0 = cd.w0 = cd.e0 = 0.f;
-            sp_required(s, c, sh->root_tehai, sh->root_wall, &cd.required, &cd.num_required);
+            sp_required(s, c, len, R.root_key.tehai, R.root_key.wall, &cd.required, &cd.num_required);
         }
     } else {
-        // ---- probability tables (calc.rs:136-167), one row per thread
-        {
-#ifdef MJX_HOST_EMUL
-            const int tid = 0, nthreads = 1;
-#else
-            const int tid = s.warp * 32 + s.lane, nthreads = s.nwarps * 32;
-#endif
-            const int n_left = P.n_left;
-            for (int r = tid; r < 4 + SP_MAX_TILES_LEFT + 1; r += nthreads) {
-                if (r < 4) {
-                    for (int j = 0; j < T; j++) sh->tsumo_prob[r][j] = SP_FDIV((float)(r + 1), (float)(n_left - j));
-                } else {
-                    const int i = r - 4;
-                    float* row = sh->not_tsumo_prob[i];
-                    for (int j = 0; j < T; j++) row[j] = 0.f;
-                    if (i <= n_left) {
-                        row[0] = 1.f;
-                        const int lim = min(T - 1, n_left - i);
-                        for (int j = 0; j < lim; j++)
-                            row[j + 1] = SP_FDIV(SP_FMUL(row[j], (float)(n_left - i - j)), (float)(n_left - j));
-                    }
-                }
-            }
-            // clear the hash table
-            for (int i = tid; i < SP_HASH_CAP; i += nthreads) s.W.hash[i] = 0;
-        }
-        SP_CTA_SYNC();
-
-        // ---- expand, level by level. Level sequence: [D_s root]? W_s D_{s-1} W_{s-1} ... D_0 W_0
-        // level L kinds/shanten are derived from the root kind.
-        const bool root_is_d = can_discard;
-        if (tid0) { sh->level_begin[0] = 0; sh->level_begin[1] = 1; sh->n_levels = 1; }
-        SP_CTA_SYNC();
-        {
-            int lvl = 0;
-            bool is_w = !root_is_d;
-            int k = cur_shanten;
-            for (;;) {
-                const int b = sh->level_begin[lvl], en = sh->level_begin[lvl + 1];
-                const bool leaf = is_w && k == 0;
-                for (int node = b + s.warp; node < en; node += s.nwarps) sp_expand(s, c, node, is_w, k, leaf);
-                SP_CTA_SYNC();
-                if (tid0) { sh->level_begin[lvl + 2] = min(s.W.counters[0], SP_NODE_CAP); sh->n_levels = lvl + 1; }
-                SP_CTA_SYNC();
-                if (leaf || s.W.counters[1]) break;
-                // next level
-                if (is_w) { is_w = false; k -= 1; } else { is_w = true; }
-                lvl += 1;
-            }
-        }
-        const bool overflow = s.W.counters[1] != 0;
-        if (!overflow) {
-            // ---- evaluate bottom-up
-            const int n_levels = sh->n_levels;
-            for (int lvl = n_levels - 1; lvl >= (root_is_d ? 1 : 0); lvl--) {
-                // level kind: going down from the root the kinds alternate starting with root kind
-                const bool is_w = root_is_d ? (lvl & 1) == 1 : (lvl & 1) == 0;
-                const int k = root_is_d ? cur_shanten - lvl / 2 : cur_shanten - (lvl + 1) / 2;
-                const int b = sh->level_begin[lvl], en = sh->level_begin[lvl + 1];
-                for (int node = b + s.warp; node < en; node += s.nwarps) {
-                    if (is_w) sp_eval_w(s, c, node, k); else sp_eval_d(s, c, node);
-                }
-                SP_CTA_SYNC();
-            }
-            // ---- candidates (calc.rs:203-279)
-            if (root_is_d) {
-                const int ne = s.W.n_edges[0];
-                for (int i = 0; i < ne && n_cands < 14; i++) {
-                    const u32 ed = s.W.edges[i];
-                    SpCand& cd = cands[n_cands++];
-                    cd.tile = (ed >> 20) & 63;
-                    cd.node = (int)(ed & 0xFFFFF);
-                    cd.shanten_down = false;
-                }
-            } else {
+        if (R.root < 0) return;
+        if (can_discard) {  // calc.rs:203-253: one candidate per shanten-keeping discard of the root
+            const int ne = s.G.n_edges[R.root];
+            const u32 eb = s.G.edge_begin[R.root];
+            for (int i = 0; i < ne && n_cands < 14; i++) {
+                const u32 child = s.G.edge_child[eb + i];
+                if (child == SP_NO_CHILD) continue;
                 SpCand& cd = cands[n_cands++];
-                cd.tile = T_UNK; cd.node = 0; cd.shanten_down = false;
+                cd.tile = s.G.edge_meta[eb + i] & 63;
+                cd.node = (int)child;
+                cd.shanten_down = false;
             }
-            for (int i = 0; i < n_cands; i++) {
-                SpCand& cd = cands[i];
-                const int node = cd.node;
-                const int ne = s.W.n_edges[node];
-                u64 req = 0; int num = 0;
-                for (int q = 0; q < ne; q++) {
-                    const u32 ed = s.W.edges[(size_t)node * SP_EDGE_MAX + q];
-                    req |= 1ull << deaka((ed >> 20) & 63);
-                    num += (ed >> 26) & 7;
-                }
-                cd.required = req;
-                cd.num_required = num & 0xFF;
-                cd.t0 = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s, node, 0)[0]);
-                cd.w0 = clamp01(sp_vals(s, node, 1)[0]);
-                cd.e0 = fmaxf(sp_vals(s, node, 2)[0], 0.f);
-            }
+        } else {
+            SpCand& cd = cands[n_cands++];
+            cd.tile = T_UNK; cd.node = R.root; cd.shanten_down = false;
         }
-        if (overflow) {
-            if (tid0) { /* leave the block zero; the host reads the flag through mjx_env_sp_overflows */ }
-            return;
+        for (int i = 0; i < n_cands; i++) {
+            SpCand& cd = cands[i];
+            const int node = cd.node;
+            const int ne = s.G.n_edges[node];
+            const u32 eb = s.G.edge_begin[node];
+            u64 req = 0; int num = 0;
+            for (int q = 0; q < ne; q++) {
+                const u16 m = s.G.edge_meta[eb + q];
+                req |= 1ull << deaka(m & 63);
+                num += m >> 6;
+            }
+            cd.required = req;
+            cd.num_required = num & 0xFF;
+            cd.t0 = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s, node, 0)[0]);
+            cd.w0 = clamp01(sp_vals(s, node, 1)[0]);
+            cd.e0 = fmaxf(sp_vals(s, node, 2)[0], 0.f);
         }
     }
-    if (n_cands == 0) {
-        // analyze_discard can return no candidate only if no discard keeps the shanten — impossible by construction
-        return;
-    }
-    if (after_riichi) cands[0].tile = PV.last_self_tsumo;  // agent_helper.rs:588-590 (after sorting: see below)
-
-    // ---- obs rows (obs_repr.rs:561-603, 644-692); written by one warp of the second half
-    if (!ENC_SECTION(e, 6, false)) return;
-    // `max_ev_table` is sorted descending by EV (stable); index 0 = maximum under sp_cand_cmp(…, EV)
+    if (n_cands == 0) return;
+    // `max_ev_table` is sorted descending (stable); index 0 = the maximum under the comparator
     int first = 0;
     for (int i = 1; i < n_cands; i++) if (sp_cand_cmp(cands[i], cands[first], has_values ? 0 : 3, has_values) > 0) first = i;
+    if (R.after_riichi) cands[first].tile = R.last_self_tsumo;  // agent_helper.rs:588-590
     const float max_ev = has_values ? cands[first].e0 : 0.f;
-    ENC_FILL(e, 889, fminf(fmaxf(max_ev, 0.f), 100000.f) / 100000.f);
-    ENC_FILL(e, 890, fminf(fmaxf(max_ev, 0.f), 30000.f) / 30000.f);
-    const bool cd_flag = (cans & CAN_DISCARD) != 0;  // obs_repr.rs uses cans.can_discard, not the riichi-adjusted flag
+    SPO_FILL(889, fminf(fmaxf(max_ev, 0.f), 100000.f) / 100000.f);
+    SPO_FILL(890, fminf(fmaxf(max_ev, 0.f), 30000.f) / 30000.f);
+    const bool cd_flag = R.cd_flag != 0;  // obs_repr.rs branches on cans.can_discard, not on the riichi-adjusted flag
     if (cd_flag) {
         for (int i = 0; i < n_cands; i++) {
             const int dt = deaka(cands[i].tile);
-            const int row = 891 + (cands[i].shanten_down ? 34 : 0) + dt;
-            MJX_FOR_TILES(e, t) { if ((cands[i].required >> t) & 1) ENC_AT(e, row, t) = 1.f; }
+            const int r = 891 + (cands[i].shanten_down ? 34 : 0) + dt;
+            MJX_FOR_TILES(s, t) { if ((cands[i].required >> t) & 1) obs_row[r * 34 + t] = 1.f; }
         }
-        // max_by(NotShantenDown) returns the LAST maximum
-        int best = 0;
+        int best = 0;  // max_by(NotShantenDown) returns the LAST maximum
         for (int i = 1; i < n_cands; i++) if (sp_cand_cmp(cands[i], cands[best], 3, false) >= 0) best = i;
-        ENC_ASSIGN(e, 959, deaka(cands[best].tile), 1.f);
+        SPO_ASSIGN(959, deaka(cands[best].tile), 1.f);
     } else {
-        MJX_FOR_TILES(e, t) { if ((cands[first].required >> t) & 1) ENC_AT(e, 960, t) = 1.f; }
+        MJX_FOR_TILES(s, t) { if ((cands[first].required >> t) & 1) obs_row[960 * 34 + t] = 1.f; }
     }
     if (!has_values) return;
     if (!(cands[first].t0 > 0.f)) return;  // obs_repr.rs:645-653
@@ -722,16 +746,18 @@ MJX_DN void encode_sp_block(EncCtx& e, const Ctx& c, SpCtx& s) {
             const float ev = fminf(SP_FMUL(fmaxf(sp_vals(s, node, 2)[turn], 0.f), ev_scale), 1.f);
             if (cd_flag) {
                 const int tid = deaka(cd.tile);
-                ENC_ASSIGN(e, 961 + turn, tid, tp);
-                ENC_ASSIGN(e, 961 + SP_T_MAX + turn, tid, wp);
-                ENC_ASSIGN(e, 961 + 2 * SP_T_MAX + turn, tid, ev);
+                SPO_ASSIGN(961 + turn, tid, tp);
+                SPO_ASSIGN(961 + SP_T_MAX + turn, tid, wp);
+                SPO_ASSIGN(961 + 2 * SP_T_MAX + turn, tid, ev);
             } else {
-                ENC_FILL(e, 961 + turn, tp);
-                ENC_FILL(e, 961 + SP_T_MAX + turn, wp);
-                ENC_FILL(e, 961 + 2 * SP_T_MAX + turn, ev);
+                SPO_FILL(961 + turn, tp);
+                SPO_FILL(961 + SP_T_MAX + turn, wp);
+                SPO_FILL(961 + 2 * SP_T_MAX + turn, ev);
             }
         }
     }
+#undef SPO_FILL
+#undef SPO_ASSIGN
 }
 
 }  // namespace mjx

@@ -183,13 +183,8 @@ long emul_sp_overflows() { return g_emul_sp_overflows; }
 // obs: [n_rows, 1012, 34] f32; sp: compute the single-player block
 void emul_env_encode_obs(void* p, float* obs, int sp) {
     EmulEnv* E = static_cast<EmulEnv*>(p);
-    static std::vector<SpKey> keys(SP_NODE_CAP);
-    static std::vector<float> vals((size_t)SP_NODE_CAP * 3 * SP_T_MAX);
-    static std::vector<u32> edges((size_t)SP_NODE_CAP * SP_EDGE_MAX), hash(SP_HASH_CAP);
-    static std::vector<u8> n_edges(SP_NODE_CAP);
-    static i32 counters[4];
-    static SpShared shared;
-    for (int r = 0; r < E->n_rows[0]; r++) {
+    const int n_rows = E->n_rows[0];
+    for (int r = 0; r < n_rows; r++) {
         float* tile = obs + (size_t)r * OBS_ROWS_V4 * OBS_COLS;
         memset(tile, 0, sizeof(float) * OBS_ROWS_V4 * OBS_COLS);
         const TableState* S = &E->tabs[E->row_table[r]];
@@ -208,15 +203,40 @@ void emul_env_encode_obs(void* p, float* obs, int sp) {
         encode_obs_v4(e, c, nullptr);
         e.row_lo = OBS_SPLIT_ROW; e.row_hi = OBS_ROWS_V4; e.tile = tile + (size_t)OBS_SPLIT_ROW * OBS_COLS;
         encode_obs_v4(e, c, nullptr);
-        if (sp) {
-            SpCtx s;
-            s.W.keys = keys.data(); s.W.vals = vals.data(); s.W.edges = edges.data(); s.W.n_edges = n_edges.data();
-            s.W.hash = hash.data(); s.W.counters = counters; s.sh = &shared; s.T = g_T; s.lane = 0; s.warp = 0; s.nwarps = 1;
-            counters[1] = 0;
-            encode_sp_block(e, c, s);
-            if (counters[1]) g_emul_sp_overflows++;
-        }
     }
+    if (!sp) return;
+    // the same stage sequence mjx_env_encode_obs launches, executed by one lane
+    static SpGlobal G;
+    static std::vector<SpRow> rows; static std::vector<SpKey> keys; static std::vector<i32> node_row, slot_list;
+    static std::vector<float> vals; static std::vector<u32> edge_begin, edge_child, hash; static std::vector<u8> n_edges;
+    static std::vector<u16> edge_meta; static i32 slot_count[SP_SLOTS], counters[4];
+    if (keys.empty()) {
+        G.node_cap = 1 << 20; G.slot_cap = G.node_cap; G.edge_cap = G.node_cap * 12; G.hash_cap = 1 << 21;
+        rows.resize(1 << 16); keys.resize(G.node_cap); node_row.resize(G.node_cap);
+        vals.resize((size_t)G.node_cap * 3 * SP_T_MAX); edge_begin.resize(G.node_cap); n_edges.resize(G.node_cap);
+        edge_child.resize(G.edge_cap); edge_meta.resize(G.edge_cap); hash.resize(G.hash_cap);
+        slot_list.resize((size_t)SP_SLOTS * G.slot_cap);
+        G.rows = rows.data(); G.keys = keys.data(); G.node_row = node_row.data(); G.vals = vals.data();
+        G.edge_begin = edge_begin.data(); G.n_edges = n_edges.data(); G.edge_child = edge_child.data();
+        G.edge_meta = edge_meta.data(); G.hash = hash.data(); G.slot_list = slot_list.data(); G.slot_count = slot_count;
+        G.counters = counters;
+    }
+    std::fill(hash.begin(), hash.end(), 0u);
+    for (int i = 0; i < SP_SLOTS; i++) slot_count[i] = 0;
+    counters[0] = counters[1] = counters[2] = 0;
+    SpWarpScratch ws;
+    SpCtx s; s.G = G; s.T = g_T; s.ws = &ws; s.lane = 0;
+    Ctx c; c.S = nullptr; c.W = nullptr; c.T = g_T; c.lane = 0; c.df = nullptr;
+    for (int r = 0; r < n_rows; r++) sp_stage_init(s, &E->tabs[E->row_table[r]], r, E->row_table[r], E->row_seat[r] & 3);
+    for (int slot = 0; slot < SP_SLOTS; slot++)
+        for (int i = 0; i < std::min(slot_count[slot], G.slot_cap); i++) sp_expand(s, c, slot_list[(size_t)slot * G.slot_cap + i], slot);
+    for (int slot = SP_SLOTS - 1; slot >= 0; slot--)
+        for (int i = 0; i < std::min(slot_count[slot], G.slot_cap); i++) {
+            int node = slot_list[(size_t)slot * G.slot_cap + i];
+            if (sp_slot_is_w(slot)) sp_eval_w(s, c, node, sp_slot_shanten(slot)); else sp_eval_d(s, c, node);
+        }
+    for (int r = 0; r < n_rows; r++) sp_stage_finalize(s, r, obs + (size_t)r * OBS_ROWS_V4 * OBS_COLS);
+    if (counters[2]) g_emul_sp_overflows++;
 }
 void emul_env_results(void* p, int32_t* scores, uint8_t* ranks, int32_t* steps, int32_t* errs, int32_t* done) {
     EmulEnv* E = static_cast<EmulEnv*>(p);
