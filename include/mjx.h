@@ -76,6 +76,7 @@ int mjx_env_row_cap(mjx_env* env);
 uint8_t* mjx_env_masks(mjx_env* env);      /* uint8/bool [row_cap, 46]  (obs_repr.rs mask) */
 int32_t* mjx_env_row_table(mjx_env* env);  /* int32 [row_cap] table index of each row */
 uint8_t* mjx_env_row_seat(mjx_env* env);   /* uint8 [row_cap] seat | (kan_select << 2) */
+uint32_t* mjx_env_row_step(mjx_env* env); /* uint32 [row_cap] table-step index of the table when the row was emitted */
 int32_t* mjx_env_num_rows_dev(mjx_env* env); /* int32 [1] */
 
 /* arena/result.rs GameResult.scores + rankings.rs rank_by_player, plus per-table step counts and

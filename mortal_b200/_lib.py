@@ -52,6 +52,7 @@ SYMBOLS = {
     "mjx_env_masks": (C.c_void_p, [C.c_void_p]),
     "mjx_env_row_table": (C.c_void_p, [C.c_void_p]),
     "mjx_env_row_seat": (C.c_void_p, [C.c_void_p]),
+    "mjx_env_row_step": (C.c_void_p, [C.c_void_p]),
     "mjx_env_num_rows_dev": (C.c_void_p, [C.c_void_p]),
     "mjx_env_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mjx_env_policy_test": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

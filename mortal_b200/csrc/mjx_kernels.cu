@@ -520,6 +520,7 @@ int mjx_env_row_cap(mjx_env* env) { return env ? env->row_cap : MJX_ERR_ARG; }
 uint8_t* mjx_env_masks(mjx_env* env) { return env ? env->V.masks : nullptr; }
 int32_t* mjx_env_row_table(mjx_env* env) { return env ? env->V.row_table : nullptr; }
 uint8_t* mjx_env_row_seat(mjx_env* env) { return env ? env->V.row_seat : nullptr; }
+uint32_t* mjx_env_row_step(mjx_env* env) { return env ? env->V.row_step : nullptr; }
 int32_t* mjx_env_num_rows_dev(mjx_env* env) { return env ? env->V.n_rows : nullptr; }
 
 int mjx_env_results(mjx_env* env, void* stream, int32_t* scores, uint8_t* ranks, int32_t* steps, int32_t* err,

@@ -131,13 +131,28 @@ MJX_D u32 sp_hash_key(int row, const SpKey& k) {
     return h;
 }
 
+// `a` lives in the global arena and may have been written by another SM during this launch: read it through
+// L2 (ld.global.cg) — an L1 line shared with a neighbouring, older node could otherwise serve stale bytes.
 MJX_D bool sp_key_eq(const SpKey& a, const SpKey& b) {
     const u32* x = reinterpret_cast<const u32*>(&a);
     const u32* y = reinterpret_cast<const u32*>(&b);
     bool eq = true;
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(SpKey) / 4); i++) eq &= x[i] == y[i];
+    for (int i = 0; i < (int)(sizeof(SpKey) / 4); i++) {
+#ifdef MJX_HOST_EMUL
+        eq &= x[i] == y[i];
+#else
+        eq &= __ldcg(x + i) == y[i];
+#endif
+    }
     return eq;
+}
+MJX_D int sp_ld_row(const i32* p) {
+#ifdef MJX_HOST_EMUL
+    return *p;
+#else
+    return __ldcg(p);
+#endif
 }
 
 MJX_D void sp_set_overflow(SpCtx& s) { s.G.counters[2] = 1; }
@@ -191,7 +206,7 @@ MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
         __threadfence();
 #endif
         const int ci = (int)cur - 1;
-        if (s.G.node_row[ci] == row && sp_key_eq(s.G.keys[ci], key)) return ci;
+        if (sp_ld_row(s.G.node_row + ci) == row && sp_key_eq(s.G.keys[ci], key)) return ci;
     }
     sp_set_overflow(s);
     return -1;

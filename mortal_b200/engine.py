@@ -17,10 +17,14 @@ class DeviceEngine:
 
     def __init__(self, brain, dqn, *, version=4, device=None, enable_amp=True, enable_quick_eval=True,
                  enable_rule_based_agari_guard=False, name="NoName", boltzmann_epsilon=0.0, boltzmann_temp=1.0,
-                 top_p=1.0, is_oracle=False):
+                 top_p=1.0, is_oracle=False, fast_inference=True):
         self.device = device or torch.device("cuda")
         self.brain = brain.to(self.device).eval()
         self.dqn = dqn.to(self.device).eval()
+        # BN-folded bf16 inference path when the brain offers one (mortal_b200.model.Brain); plain autocast otherwise
+        self.fast = bool(fast_inference and enable_amp and hasattr(self.brain, "prepare_fast") and self.device.type == "cuda")
+        if self.fast:
+            self.brain.prepare_fast(torch.bfloat16)
         self.version = version
         self.is_oracle = is_oracle
         self.enable_amp = enable_amp
@@ -34,8 +38,11 @@ class DeviceEngine:
     @torch.inference_mode()
     def react_device(self, obs: torch.Tensor, masks: torch.Tensor):
         """obs [B, C, 34] f32 cuda, masks [B, 46] bool cuda -> (actions int64 [B], q [B, 46])"""
-        with torch.autocast(self.device.type, enabled=self.enable_amp):
-            q = self.dqn(self.brain(obs), masks)
+        if self.fast:
+            q = self.dqn(self.brain.forward_fast(obs).float(), masks)
+        else:
+            with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.enable_amp):
+                q = self.dqn(self.brain(obs), masks)
         if self.boltzmann_epsilon > 0:
             b = obs.shape[0]
             greedy = torch.full((b,), 1 - self.boltzmann_epsilon, device=self.device).bernoulli().to(torch.bool)

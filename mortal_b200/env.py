@@ -48,6 +48,7 @@ class BatchEnv:
         self.masks = as_t(self.L.mjx_env_masks(h), (self.row_cap, 46), "|u1").view(torch.bool)
         self.row_table = as_t(self.L.mjx_env_row_table(h), (self.row_cap,), "<i4")
         self.row_seat = as_t(self.L.mjx_env_row_seat(h), (self.row_cap,), "|u1")
+        self.row_step = as_t(self.L.mjx_env_row_step(h), (self.row_cap,), "<u4")
         self.n_rows_dev = as_t(self.L.mjx_env_num_rows_dev(h), (1,), "<i4")
         self._obs = None
 

@@ -29,6 +29,8 @@ class _Arena:
         self.shuffle_kind = shuffle_kind
         self.device = device
         self.last_stats = None
+        self.record_decisions = False  # test hook: keep (table, step, seat, kan_select, action) of every row
+        self.last_decisions = None
         if log_dir is not None:
             raise NotImplementedError("mjai log emission (SURVEY.md §8f N1) is not built in this round")
 
@@ -72,6 +74,7 @@ class _Arena:
             q_all = torch.zeros((env.row_cap, 46), dtype=torch.float32, device=dev)
         first = True
         cycles = 0
+        recorded = []
         while True:
             env.step(None if first else actions, None if first else q_all)
             first = False
@@ -91,9 +94,15 @@ class _Arena:
                     actions[idx] = a.to(torch.int64)
                     if q_all is not None:
                         q_all[idx] = q.float()
+                if self.record_decisions:
+                    recorded.append(torch.stack([tbl, env.row_step[:nr].long(), seat, (env.row_seat[:nr] >> 2).long() & 1,
+                                                 actions[:nr]], dim=1).cpu())
             cycles += 1
         res = env.results()
         self.last_stats = dict(cycles=cycles, table_steps=int(res["steps"].sum()))
+        self.last_results = res
+        if self.record_decisions:
+            self.last_decisions = torch.cat(recorded).numpy() if recorded else np.zeros((0, 5), dtype=np.int64)
         env.close()
         if (res["err"] != 0).any():
             bad = int(np.nonzero(res["err"])[0][0])

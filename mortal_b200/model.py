@@ -31,6 +31,13 @@ class ChannelGate(nn.Module):
         gate = torch.sigmoid(self._mlp(x.mean(-1)) + self._mlp(x.amax(-1)))
         return x * gate.unsqueeze(-1)
 
+    def forward_fast(self, x):
+        # same maths; the two length-34 reductions go through pooling kernels instead of generic reduce kernels
+        avg = torch.nn.functional.avg_pool1d(x, x.shape[-1]).squeeze(-1)
+        mx = torch.nn.functional.max_pool1d(x, x.shape[-1]).squeeze(-1)
+        gate = torch.sigmoid(self._mlp(avg) + self._mlp(mx))
+        return x * gate.unsqueeze(-1)
+
 
 class PreActBlock(nn.Module):
     def __init__(self, channels: int):
@@ -46,6 +53,19 @@ class PreActBlock(nn.Module):
         y = self.conv1(self.act(self.bn1(x)))
         y = self.conv2(self.act(self.bn2(y)))
         return self.gate(y) + x
+
+    @staticmethod
+    def _affine(bn):
+        # eval-mode BatchNorm is a per-channel affine map: y = x * scale + shift
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        shift = bn.bias - bn.running_mean * scale
+        return scale.view(1, -1, 1), shift.view(1, -1, 1)
+
+    def forward_fast(self, x, aff):
+        (s1, b1), (s2, b2) = aff
+        y = self.conv1(torch.nn.functional.mish(torch.addcmul(b1, x, s1)))
+        y = self.conv2(torch.nn.functional.mish(torch.addcmul(b2, y, s2)))
+        return self.gate.forward_fast(y) + x
 
 
 class Brain(nn.Module):
@@ -65,6 +85,29 @@ class Brain(nn.Module):
         x = self.blocks(self.stem(obs))
         x = self.act(self.neck(self.act(self.bn(x))))
         return self.act(self.fc(x.flatten(1)))
+
+    @torch.no_grad()
+    def prepare_fast(self, dtype=None):
+        """Inference-only fast path: eval-mode BatchNorms pre-folded into per-channel affines (two elementwise
+        kernels instead of cuDNN's NCHW batch-norm kernel) and optional reduced-precision weights so that no
+        autocast casts are needed. Mathematically the same network; call after loading weights / .eval()."""
+        assert not self.training, "prepare_fast() is for eval mode"
+        if dtype is not None:
+            self.to(dtype)
+        self._aff = [(PreActBlock._affine(b.bn1), PreActBlock._affine(b.bn2)) for b in self.blocks]
+        self._aff_out = PreActBlock._affine(self.bn)
+        self._fast_dtype = dtype
+        return self
+
+    def forward_fast(self, obs):
+        if self._fast_dtype is not None:
+            obs = obs.to(self._fast_dtype)
+        x = self.stem(obs)
+        for blk, aff in zip(self.blocks, self._aff):
+            x = blk.forward_fast(x, aff)
+        s, b = self._aff_out
+        x = torch.nn.functional.mish(self.neck(torch.nn.functional.mish(torch.addcmul(b, x, s))))
+        return torch.nn.functional.mish(self.fc(x.flatten(1)))
 
 
 class DQN(nn.Module):

@@ -510,6 +510,54 @@ int orc_run_batch(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t
 
 void orc_sp_stats(long* out) { for (int i = 0; i < 8; i++) { out[i] = orc::g_sp_stats[i]; orc::g_sp_stats[i] = 0; } }
 
+// Action-replay parity (SURVEY.md §8d protocol ii): drive the oracle with decisions recorded elsewhere.
+// replay rows: [table, step_idx, seat, kan_select, action], sorted lexicographically by the first four.
+// Every replayed action must be legal in the oracle's own mask, otherwise the call fails.
+int orc_run_replay(int n_tables, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int enable_quick_eval,
+                   const int64_t* replay, int64_t n_replay, int32_t* scores, uint8_t* ranks, int32_t* steps) {
+    try {
+        int64_t used = 0;
+        for (int t = 0; t < n_tables; t++) {
+            Game g;
+            g.seed_nonce = nonces[t]; g.seed_key = keys[t]; g.shuffle_kind = shuffle_kind; g.table = t;
+            AgentConfig ac;
+            ac.enable_quick_eval = enable_quick_eval != 0;
+            AgentConfig cfgs[4] = {ac, ac, ac, ac};
+            PolicyFn pol = [&](const Scene& sc, const u8* mask, float*) {
+                int64_t key[4] = {sc.table, (int64_t)sc.step_idx, sc.seat, sc.is_kan_select ? 1 : 0};
+                int64_t lo = 0, hi = n_replay;
+                while (lo < hi) {
+                    int64_t mid = (lo + hi) / 2;
+                    const int64_t* r = replay + mid * 5;
+                    bool less = false;
+                    for (int q = 0; q < 4; q++) { if (r[q] != key[q]) { less = r[q] < key[q]; break; } }
+                    if (less) lo = mid + 1; else hi = mid;
+                }
+                const int64_t* r = replay + lo * 5;
+                if (lo >= n_replay || r[0] != key[0] || r[1] != key[1] || r[2] != key[2] || r[3] != key[3])
+                    throw OrcError("replay: no recorded decision for table " + std::to_string(sc.table) + " step " +
+                                   std::to_string(sc.step_idx) + " seat " + std::to_string(sc.seat));
+                int a = (int)r[4];
+                if (a < 0 || a >= 46 || !mask[a]) throw OrcError("replay: recorded action is illegal in the oracle");
+                used++;
+                return a;
+            };
+            PolicyFn pols[4] = {pol, pol, pol, pol};
+            int64_t n_steps = 0;
+            for (;;) {
+                g.poll();
+                if (g.commit(cfgs, pols, nullptr)) break;
+                n_steps++;
+            }
+            for (int i = 0; i < 4; i++) scores[t * 4 + i] = g.scores[i];
+            rankings(g.scores, nullptr, ranks + t * 4);
+            steps[t] = (int32_t)n_steps;
+        }
+        if (used != n_replay) throw OrcError("replay: " + std::to_string(n_replay - used) + " recorded decisions were never requested");
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
 uint64_t orc_policy_hash(uint64_t nonce, uint64_t key, uint64_t table, uint64_t step_idx, uint32_t seat, uint32_t kan) {
     return policy_hash(nonce, key, table, step_idx, seat, kan);
 }

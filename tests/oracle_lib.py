@@ -194,6 +194,8 @@ def lib():
     L.orc_game_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.orc_run_batch.argtypes = [C.POINTER(RunCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(RunOut)]
+    L.orc_run_replay.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]
     L.orc_policy_hash.restype = C.c_uint64
     L.orc_policy_hash.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
     if L.orc_init(DATA_DIR.encode()) != 0:
@@ -460,3 +462,21 @@ def run_batch(nonces, keys, *, shuffle_kind=0, policy_kind=1, quick_eval=True, a
         assert tlen.value <= trace_cap, "trace overflow"
         res["trace"] = trace[: tlen.value]
     return res
+
+
+def run_replay(nonces, keys, replay, *, shuffle_kind=0, quick_eval=True):
+    """replay: int64 [m, 5] rows (table, step, seat, kan_select, action) recorded from another implementation."""
+    n = len(nonces)
+    nonces = np.ascontiguousarray(nonces, dtype=np.uint64)
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    rp = np.ascontiguousarray(replay, dtype=np.int64).reshape(-1, 5)
+    order = np.lexsort((rp[:, 3], rp[:, 2], rp[:, 1], rp[:, 0]))
+    rp = np.ascontiguousarray(rp[order])
+    scores = np.zeros((n, 4), dtype=np.int32)
+    ranks = np.zeros((n, 4), dtype=np.uint8)
+    steps = np.zeros(n, dtype=np.int32)
+    rc = lib().orc_run_replay(n, nonces.ctypes.data, keys.ctypes.data, shuffle_kind, int(quick_eval), rp.ctypes.data,
+                              len(rp), scores.ctypes.data, ranks.ctypes.data, steps.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(err())
+    return dict(scores=scores, ranks=ranks, steps=steps)

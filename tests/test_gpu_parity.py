@@ -214,3 +214,40 @@ def test_obs_encode_matches_oracle(mjx):
 
     check_obs_parity(make_env, fetch, sp=True, sp_tol=0.0)
     assert make_env.overflows == 0
+
+
+def test_one_vs_three_network_policy_action_replay(mjx):
+    """BASELINE config 2 protocol (SURVEY.md §8d ii): a float policy (random-init Mortal brain, greedy) drives the CUDA
+    arena through the libriichi-compatible OneVsThree.py_vs_py; the recorded decisions are replayed in the oracle,
+    which must accept every action as legal and reproduce scores, rankings and the returned histogram bit for bit."""
+    import torch
+
+    import mortal_b200.libriichi as lr
+    from mortal_b200.engine import DeviceEngine
+    from mortal_b200.model import DQN, Brain
+
+    lr.install()
+    from libriichi.arena import OneVsThree
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    mk = lambda name: DeviceEngine(Brain(conv_channels=32, num_blocks=2, version=4), DQN(version=4), device=dev,
+                                   enable_amp=True, enable_quick_eval=True, name=name)
+    challenger, champion = mk("a"), mk("b")
+    arena = OneVsThree(disable_progress_bar=True, log_dir=None)
+    arena.record_decisions = True
+    seed_start, seed_count = (10000, 0x2000), 6
+    rankings = arena.py_vs_py(challenger=challenger, champion=champion, seed_start=seed_start, seed_count=seed_count)
+    assert sum(rankings) == 4 * seed_count
+    n = 4 * seed_count
+    nonces = np.repeat(np.arange(seed_start[0], seed_start[0] + seed_count, dtype=np.uint64), 4)
+    keys = np.full(n, seed_start[1], dtype=np.uint64)
+    ref = O.run_replay(nonces, keys, arena.last_decisions, quick_eval=True)
+    got = arena.last_results
+    assert (got["scores"] == ref["scores"]).all()
+    assert (got["ranks"] == ref["ranks"]).all()
+    assert (got["steps"] == ref["steps"]).all()
+    hist = [0, 0, 0, 0]
+    for i in range(n):
+        hist[int(ref["ranks"][i, i % 4])] += 1
+    assert hist == rankings
