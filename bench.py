@@ -239,9 +239,15 @@ def run_ours(args):
     env.close()
     clocks = sampler.stop()
 
-    # -------- loop B: env only (test policy on device, no host sync), encode kernel timed with events
+    # -------- loop B: env only (test policy on device, no host sync)
     env = fresh_env()
-    b = loop(env, test_policy, W, K, time_encode=True)
+    b = loop(env, test_policy, W, K)
+    sp_overflows = env.sp_overflows()
+    env.close()
+    # -------- loop B2: the HBM-bound encode kernel alone (single-player block off), timed with CUDA events
+    env = fresh_env()
+    env.set_sp(False)
+    b2 = loop(env, test_policy, W, K, time_encode=True)
     b_rows = 0
     # rows per step for the roofline: replay the same K cycles' row counts is not needed; sample the average
     env.close()
@@ -340,7 +346,7 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         rows_per_launch = b_rows / K
         bytes_per_launch = rows_per_launch * (OBS_BYTES + MASK_BYTES + STATE_BYTES)
-        enc_ms_per_launch = b["enc_ms"] / K
+        enc_ms_per_launch = b2["enc_ms"] / K
         achieved = bytes_per_launch / (enc_ms_per_launch * 1e-3) / 1e9 if enc_ms_per_launch > 0 else 0.0
         line = {
             "metric": "table-steps/sec batched self-play", "value": a_units / (a_ms * 1e-3), "unit": "table-steps/s",
@@ -350,9 +356,11 @@ def run_ours(args):
                        "tables_per_gpu": N_TABLES, "global_tables": N_TABLES * world, "obs_version": 4,
                        "seed_start": list(SEED_START), "parallelism": f"tables sharded dp{world}, no data-path collective",
                        "l2": "per-step obs output (~0.7 GB) exceeds the 126 MB L2, no explicit flush",
-                       "sp_block": "rows 889-1011 (single-player tables) not yet computed on device: zero-filled"},
+                       "sp_block": "rows 889-1011 (single-player tables) computed on device by the k_sp_* kernels",
+                       "sp_arena_overflows": sp_overflows},
             "env_only": {"value": b_units / (b_ms * 1e-3), "unit": "table-steps/s", "ms_per_step": b_ms / K,
-                         "policy": "counter-based test policy kernel, no host sync"},
+                         "policy": "counter-based test policy kernel, no host sync",
+                         "without_sp_block": {"value": b2["table_steps"] / (b2["ms"] * 1e-3), "ms_per_step": b2["ms"] / K}},
             "roofline": {"kernel": "k_encode_obs_v4", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs if peak_gbs else None, "traffic": None, "peak_source": peak_src,
                          "bytes_per_launch": bytes_per_launch, "ms_per_launch": enc_ms_per_launch,
@@ -361,7 +369,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": 8 * N_TABLES * 3,
                     "d2h_bytes_per_step": int(e2e_rows / K * (OBS_BYTES + MASK_BYTES)),
                     "path": "mjx C ABI with pinned host buffers: actions H2D, obs+masks D2H every step, host-side policy"},
-            "gpu_launches": K * 3, "clocks": clocks,
+            "gpu_launches": K * 23, "clocks": clocks,
             "collective": {"all_gather_us": gather_us, "bytes_per_table": 20},
         }
         if world == 1 and not args.no_cpu_baseline:

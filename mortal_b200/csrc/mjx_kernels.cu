@@ -384,7 +384,7 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
     env->enc_grid = g_sm_count * 3;
     {
         SpGlobal& G = env->sp;
-        G.node_cap = n_tables * 2048;
+        G.node_cap = n_tables * 2048 > (1 << 20) ? n_tables * 2048 : (1 << 20);  // ~0.4 KB per state
         G.slot_cap = G.node_cap;
         G.edge_cap = G.node_cap * 12;
         int hc = 1;

@@ -112,8 +112,10 @@ struct SpWarpScratch {
     float cv[3][SP_T_MAX];     // child values of the current edge
     float scores[40][4];       // get_score of each winning draw of a W0 state
     u8 score_ok[40];
+    u8 ed_tile[40], ed_cnt[40];  // edge descriptors of the state being expanded
     u8 df[34];
     u8 pad_[2];
+    i32 ed_n, ed_begin;
 };
 
 struct SpCtx {
@@ -122,6 +124,12 @@ struct SpCtx {
     SpWarpScratch* ws;
     int lane;
 };
+
+#ifdef MJX_HOST_EMUL
+#define SP_FOR_LANES(i, n) for (int i = 0; i < (n); i++)
+#else
+#define SP_FOR_LANES(i, n) for (int i = s.lane; i < (n); i += 32)
+#endif
 
 MJX_D u32 sp_hash_key(int row, const SpKey& k) {
     const u32* w = reinterpret_cast<const u32*>(&k);
@@ -175,10 +183,13 @@ MJX_DN int sp_new_node(SpCtx& s, int row, const SpKey& key, int slot) {
     return idx;
 }
 
-// find-or-insert (row, key) in `slot`; executed by ONE lane. Returns node index, or -1 on overflow.
+// find-or-insert (row, key) in `slot`. May be called by several lanes of a warp at once (different keys).
+// Lock-free without spinning: the node is allocated and written first, then published with one CAS; if another
+// thread published the same state in the meantime its node wins and ours is simply never referenced.
 MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
     const u32 mask = (u32)s.G.hash_cap - 1;
     u32 h = sp_hash_key(row, key) & mask;
+    int mine = -1;
     for (int probe = 0; probe < s.G.hash_cap; probe++, h = (h + 1) & mask) {
 #ifdef MJX_HOST_EMUL
         u32 cur = s.G.hash[h];
@@ -189,21 +200,17 @@ MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
             return idx;
         }
 #else
-        u32 cur = atomicAdd(&s.G.hash[h], 0u);
+        u32 cur = __ldcg(&s.G.hash[h]);
         if (cur == 0) {
-            // claim with a sentinel, publish the node, then its index
-            u32 prev = atomicCAS(&s.G.hash[h], 0u, 0xFFFFFFFFu);
-            if (prev == 0) {
-                int idx = sp_new_node(s, row, key, slot);
-                if (idx < 0) { atomicExch(&s.G.hash[h], 0u); return -1; }
+            if (mine < 0) {
+                mine = sp_new_node(s, row, key, slot);
+                if (mine < 0) return -1;
                 __threadfence();
-                atomicExch(&s.G.hash[h], (u32)idx + 1);
-                return idx;
             }
+            const u32 prev = atomicCAS(&s.G.hash[h], 0u, (u32)mine + 1);
+            if (prev == 0) return mine;
             cur = prev;
         }
-        while (cur == 0xFFFFFFFFu) cur = atomicAdd(&s.G.hash[h], 0u);  // another warp is publishing this slot
-        __threadfence();
 #endif
         const int ci = (int)cur - 1;
         if (sp_ld_row(s.G.node_row + ci) == row && sp_key_eq(s.G.keys[ci], key)) return ci;
@@ -237,65 +244,60 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
             return shanten_all_sig(s.T, sig_variant(base, t, -1, key.tehai[t]), len) == k ? 1 : 0;
         }, eff, unused);
     }
+    SpWarpScratch& ws = *s.ws;
     if (MJX_IS_L0(c)) {
-        // count edges (an effective 5 with the aka still in the wall splits in two: sp/state.rs:160-176)
+        // edge descriptors in tile order; an effective 5 whose aka is still in the wall splits in two
+        // (sp/state.rs:160-176); a discarded 5 is the aka only when it is the last 5 in hand (state.rs:127-132)
         int ne = 0;
         for (u64 rest = eff; rest; rest &= rest - 1) {
             const int t = mjx_ffsll(rest) - 1;
             const int suit5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
-            if (is_w && suit5 >= 0 && ((key.akas >> (3 + suit5)) & 1)) ne += key.wall[t] >= 2 ? 2 : 1;
-            else ne += 1;
+            if (is_w) {
+                const int count = key.wall[t];
+                if (suit5 >= 0 && ((key.akas >> (3 + suit5)) & 1)) {
+                    if (count >= 2) { ws.ed_tile[ne] = (u8)t; ws.ed_cnt[ne] = (u8)(count - 1); ne++; }
+                    ws.ed_tile[ne] = (u8)(T_5MR + suit5); ws.ed_cnt[ne] = 1; ne++;
+                } else {
+                    ws.ed_tile[ne] = (u8)t; ws.ed_cnt[ne] = (u8)count; ne++;
+                }
+            } else {
+                int tile = t;
+                if (suit5 >= 0 && ((key.akas >> suit5) & 1) && key.tehai[t] == 1) tile = T_5MR + suit5;
+                ws.ed_tile[ne] = (u8)tile; ws.ed_cnt[ne] = 0; ne++;
+            }
         }
 #ifdef MJX_HOST_EMUL
         int eb = s.G.counters[1]; s.G.counters[1] += ne;
 #else
         int eb = atomicAdd(&s.G.counters[1], ne);
 #endif
-        if (eb + ne > s.G.edge_cap) { sp_set_overflow(s); ne = 0; eb = 0; eff = 0; }
-        int w = 0;
-        for (u64 rest = eff; rest; rest &= rest - 1) {
-            const int t = mjx_ffsll(rest) - 1;
-            const int suit5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
-            if (is_w) {
-                const int count = key.wall[t];
-                const bool aka_in_wall = suit5 >= 0 && ((key.akas >> (3 + suit5)) & 1);
-                for (int variant = 0; variant < 2; variant++) {
-                    int tile, cnt;
-                    if (aka_in_wall) {
-                        if (variant == 0) { if (count < 2) continue; tile = t; cnt = count - 1; }
-                        else { tile = T_5MR + suit5; cnt = 1; }
-                    } else {
-                        if (variant == 1) break;
-                        tile = t; cnt = count;
-                    }
-                    u32 child = SP_NO_CHILD;
-                    if (!leaf) {
-                        SpKey ck = key;
-                        ck.tehai[t] += 1;
-                        ck.wall[t] -= 1;
-                        if (is_aka(tile)) ck.akas = (u8)((ck.akas | (1 << suit5)) & ~(1 << (3 + suit5)));
-                        int ci = sp_intern(s, row, ck, slot + 1);
-                        child = ci < 0 ? SP_NO_CHILD : (u32)ci;
-                    }
-                    s.G.edge_child[eb + w] = child;
-                    s.G.edge_meta[eb + w] = (u16)(tile | (cnt << 6));
-                    w++;
-                }
-            } else {
-                // sp/state.rs:127-132: the aka is discarded only when it is the last 5 of its suit in hand
-                int tile = t;
-                if (suit5 >= 0 && ((key.akas >> suit5) & 1) && key.tehai[t] == 1) tile = T_5MR + suit5;
-                SpKey ck = key;
-                ck.tehai[t] -= 1;
-                if (is_aka(tile)) ck.akas = (u8)(ck.akas & ~(1 << suit5));
-                int ci = sp_intern(s, row, ck, slot + 1);
-                s.G.edge_child[eb + w] = ci < 0 ? SP_NO_CHILD : (u32)ci;
-                s.G.edge_meta[eb + w] = (u16)tile;
-                w++;
-            }
-        }
+        if (eb + ne > s.G.edge_cap) { sp_set_overflow(s); ne = 0; eb = 0; }
+        ws.ed_n = ne; ws.ed_begin = eb;
         s.G.edge_begin[node] = (u32)eb;
-        s.G.n_edges[node] = (u8)w;
+        s.G.n_edges[node] = (u8)ne;
+    }
+    MJX_SYNCWARP();
+    // one edge per lane: build the child state and intern it
+    const int ne = ws.ed_n, eb = ws.ed_begin;
+    SP_FOR_LANES(e, ne) {
+        const int tile = ws.ed_tile[e], t = deaka(tile);
+        const int suit5 = is_aka(tile) ? tile - T_5MR : -1;
+        u32 child = SP_NO_CHILD;
+        if (!leaf) {
+            SpKey ck = key;
+            if (is_w) {
+                ck.tehai[t] += 1;
+                ck.wall[t] -= 1;
+                if (suit5 >= 0) ck.akas = (u8)((ck.akas | (1 << suit5)) & ~(1 << (3 + suit5)));
+            } else {
+                ck.tehai[t] -= 1;
+                if (suit5 >= 0) ck.akas = (u8)(ck.akas & ~(1 << suit5));
+            }
+            int ci = sp_intern(s, row, ck, slot + 1);
+            child = ci < 0 ? SP_NO_CHILD : (u32)ci;
+        }
+        s.G.edge_child[eb + e] = child;
+        s.G.edge_meta[eb + e] = (u16)(tile | (ws.ed_cnt[e] << 6));
     }
     MJX_SYNCWARP();
 }
@@ -361,12 +363,6 @@ MJX_DN bool sp_get_score(const SpCtx& s, const SpRow& P, const SpKey& key, int w
     }
     return true;
 }
-
-#ifdef MJX_HOST_EMUL
-#define SP_FOR_LANES(i, n) for (int i = 0; i < (n); i++)
-#else
-#define SP_FOR_LANES(i, n) for (int i = s.lane; i < (n); i += 32)
-#endif
 
 // calc.rs:447-561 draw_without_tegawari_slow for one W-state at shanten k (one warp, lane i = turn i)
 MJX_DN void sp_eval_w(SpCtx& s, const Ctx& c, int node, int k) {
