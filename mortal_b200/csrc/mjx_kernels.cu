@@ -160,22 +160,33 @@ __global__ void __launch_bounds__(SP_WARPS * 32) k_sp_init(SpGlobal G, Tables T,
         sp_stage_init(s, V.tables + V.row_table[row], row, V.row_table[row], V.row_seat[row] & 3);
 }
 
-__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_expand(SpGlobal G, Tables T, int slot) {
+__global__ void __launch_bounds__(SP_WARPS * 32, 4) k_sp_expand(SpGlobal G, Tables T, int slot) {
     SP_KERNEL_PROLOGUE
     const int n = min(G.slot_count[slot], G.slot_cap);
     const i32* list = G.slot_list + (size_t)slot * G.slot_cap;
     for (int i = gwarp; i < n; i += nwarps) sp_expand(s, c, list[i], slot);
 }
 
-__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_eval(SpGlobal G, Tables T, int slot) {
+// KIND 0: D-state (per-turn best discard), 1: W-state above tenpai, 2: tenpai W-state (scores the winning draws)
+template <int KIND>
+__global__ void __launch_bounds__(SP_WARPS * 32, KIND == 2 ? 3 : (KIND == 1 ? 4 : 8)) k_sp_eval(SpGlobal G, Tables T, int slot) {
     SP_KERNEL_PROLOGUE
     const int n = min(G.slot_count[slot], G.slot_cap);
     const i32* list = G.slot_list + (size_t)slot * G.slot_cap;
-    const bool is_w = sp_slot_is_w(slot);
     const int k = sp_slot_shanten(slot);
     for (int i = gwarp; i < n; i += nwarps) {
-        if (is_w) sp_eval_w(s, c, list[i], k); else sp_eval_d(s, c, list[i]);
+        if (KIND == 0) sp_eval_d(s, c, list[i]);
+        else if (KIND == 1) sp_eval_w<false>(s, c, list[i], k);
+        else sp_eval_w<true>(s, c, list[i], 0);
     }
+}
+
+__global__ void k_sp_mark(SpGlobal G, int which) { G.counters[4 + which] = min(G.counters[1], G.edge_cap); }
+
+__global__ void __launch_bounds__(128) k_sp_score(SpGlobal G, Tables T) {
+    SpCtx s; s.G = G; s.T = T; s.ws = nullptr; s.lane = threadIdx.x & 31;
+    const int b = G.counters[4], e_end = G.counters[5];
+    for (int e = b + blockIdx.x * blockDim.x + threadIdx.x; e < e_end; e += gridDim.x * blockDim.x) sp_score_edge(s, e);
 }
 
 __global__ void __launch_bounds__(SP_WARPS * 32) k_sp_finalize(SpGlobal G, Tables T, EnvView V, float* __restrict__ obs) {
@@ -386,7 +397,8 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
         SpGlobal& G = env->sp;
         G.node_cap = n_tables * 2048 > (1 << 20) ? n_tables * 2048 : (1 << 20);  // ~0.4 KB per state
         G.slot_cap = G.node_cap;
-        G.edge_cap = G.node_cap * 12;
+        G.edge_cap = G.node_cap * 6;
+        G.score_cap = G.edge_cap / 2;
         int hc = 1;
         while (hc < 2 * G.node_cap) hc <<= 1;
         G.hash_cap = hc;
@@ -398,11 +410,13 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
         CU(cudaMalloc(&G.n_edges, (size_t)G.node_cap));
         CU(cudaMalloc(&G.edge_child, (size_t)G.edge_cap * sizeof(u32)));
         CU(cudaMalloc(&G.edge_meta, (size_t)G.edge_cap * sizeof(u16)));
+        CU(cudaMalloc(&G.edge_owner, (size_t)G.edge_cap * sizeof(u32)));
+        CU(cudaMalloc(&G.leaf_scores, (size_t)G.score_cap * 4 * sizeof(float)));
         CU(cudaMalloc(&G.hash, (size_t)G.hash_cap * sizeof(u32)));
         CU(cudaMalloc(&G.slot_list, (size_t)SP_SLOTS * G.slot_cap * sizeof(i32)));
         CU(cudaMalloc(&G.slot_count, SP_SLOTS * sizeof(i32)));
-        CU(cudaMalloc(&G.counters, 4 * sizeof(i32)));
-        CU(cudaMemset(G.counters, 0, 4 * sizeof(i32)));
+        CU(cudaMalloc(&G.counters, 8 * sizeof(i32)));
+        CU(cudaMemset(G.counters, 0, 8 * sizeof(i32)));
         CU(cudaMemset(G.slot_count, 0, SP_SLOTS * sizeof(i32)));
     }
     CU(cudaMemset(env->d_dummy_actions, 0, sizeof(i64) * cap));
@@ -429,7 +443,7 @@ void mjx_env_destroy(mjx_env* env) {
     cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard);
     SpGlobal& G = env->sp;
     cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
-    cudaFree(G.edge_child); cudaFree(G.edge_meta); cudaFree(G.hash); cudaFree(G.slot_list); cudaFree(G.slot_count);
+    cudaFree(G.edge_child); cudaFree(G.edge_meta); cudaFree(G.edge_owner); cudaFree(G.leaf_scores); cudaFree(G.hash); cudaFree(G.slot_list); cudaFree(G.slot_count);
     cudaFree(G.counters);
     delete env;
 }
@@ -468,8 +482,17 @@ int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
         CU(cudaMemsetAsync(G.hash, 0, (size_t)G.hash_cap * sizeof(u32), st));
         k_sp_begin<<<1, 32, 0, st>>>(G);
         k_sp_init<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V);
-        for (int slot = 0; slot < SP_SLOTS; slot++) k_sp_expand<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
-        for (int slot = SP_SLOTS - 1; slot >= 0; slot--) k_sp_eval<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+        for (int slot = 0; slot < SP_SLOTS; slot++) {
+            if (slot == SP_SLOTS - 1) k_sp_mark<<<1, 1, 0, st>>>(G, 0);
+            k_sp_expand<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+        }
+        k_sp_mark<<<1, 1, 0, st>>>(G, 1);
+        k_sp_score<<<g_sm_count * 16, 128, 0, st>>>(G, g_T);
+        for (int slot = SP_SLOTS - 1; slot >= 0; slot--) {
+            if (!sp_slot_is_w(slot)) k_sp_eval<0><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+            else if (slot == SP_SLOTS - 1) k_sp_eval<2><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+            else k_sp_eval<1><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+        }
         k_sp_finalize<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev);
     }
     CU(cudaGetLastError());

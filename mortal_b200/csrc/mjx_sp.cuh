@@ -79,12 +79,15 @@ struct SpGlobal {
     u32* edge_begin;   // [node_cap]
     u8* n_edges;       // [node_cap]
     u32* edge_child;   // [edge_cap]
-    u16* edge_meta;    // [edge_cap] tile (6 bits) | count << 6
+    u16* edge_meta;    // [edge_cap] tile (6 bits) | count << 6 | (no-yaku flag << 15, tenpai states only)
+    u32* edge_owner;   // [edge_cap] node the edge belongs to
+    float* leaf_scores;  // [score_cap][4] get_score of every winning draw of the tenpai (W0) states
     u32* hash;         // [hash_cap] node index + 1, 0 = empty
     i32* slot_list;    // [SP_SLOTS][slot_cap] node indices
     i32* slot_count;   // [SP_SLOTS]
-    i32* counters;     // [0] nodes, [1] edges, [2] overflow flag, [3] overflow events (cumulative)
-    i32 node_cap, edge_cap, hash_cap, slot_cap;
+    i32* counters;     // [0] nodes, [1] edges, [2] overflow flag, [3] overflow events (cumulative),
+                       // [4],[5] edge range of the tenpai (W0) states
+    i32 node_cap, edge_cap, hash_cap, slot_cap, score_cap;
 };
 
 MJX_CONST float c_uradora_prob[5][13] = {  // algo/data/uradora_prob_table.txt
@@ -219,8 +222,8 @@ MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
     return -1;
 }
 
-MJX_D bool sp_slot_is_w(int slot) { return (slot & 1) != 0; }
-MJX_D int sp_slot_shanten(int slot) { return 3 - (slot >> 1); }
+MJX_HD bool sp_slot_is_w(int slot) { return (slot & 1) != 0; }
+MJX_HD int sp_slot_shanten(int slot) { return 3 - (slot >> 1); }
 MJX_D float* sp_vals(const SpCtx& s, int node, int which) { return s.G.vals + ((size_t)node * 3 + which) * SP_T_MAX; }
 
 // Expand one state (one warp): edges = shanten-lowering draws (W) or shanten-keeping discards (D).
@@ -234,12 +237,12 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
     const HandSig base = hand_sig(key.tehai);
     u64 eff, unused;
     if (is_w) {
-        tile_eval2(c, true, [&](int t) {
+        tile_eval2(c, (key.wall[32] | key.wall[33]) != 0, [&](int t) {
             if (key.wall[t] == 0) return 0;
             return shanten_all_sig(s.T, sig_variant(base, t, +1, key.tehai[t]), len) - k == -1 ? 1 : 0;
         }, eff, unused);
     } else {
-        tile_eval2(c, true, [&](int t) {
+        tile_eval2(c, (key.tehai[32] | key.tehai[33]) != 0, [&](int t) {
             if (key.tehai[t] == 0) return 0;
             return shanten_all_sig(s.T, sig_variant(base, t, -1, key.tehai[t]), len) == k ? 1 : 0;
         }, eff, unused);
@@ -298,6 +301,7 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
         }
         s.G.edge_child[eb + e] = child;
         s.G.edge_meta[eb + e] = (u16)(tile | (ws.ed_cnt[e] << 6));
+        s.G.edge_owner[eb + e] = (u32)node;
     }
     MJX_SYNCWARP();
 }
@@ -329,8 +333,11 @@ MJX_DN bool sp_get_score(const SpCtx& s, const SpRow& P, const SpKey& key, int w
         return true;
     }
     const int fu = a.fu, han = a.han;
-    auto pts = [&](int h) { bool ok; return (float)tsumo_total(point_calc(is_oya, fu, h, &ok), is_oya); };
     const bool assume_riichi = P.is_menzen && P.prefer_riichi;
+    // tsumo totals for han .. han+15 once (the reference recomputes Point::calc inside the double loops)
+    const int n_extra = !assume_riichi ? 4 : (P.n_dora == 1 ? 8 : 16);
+    float pts[16];
+    for (int h = 0; h < n_extra; h++) { bool ok; pts[h] = (float)tsumo_total(point_calc(is_oya, fu, han + h, &ok), is_oya); }
     for (int i = 0; i < 4; i++) scores[i] = 0.f;
     if (assume_riichi && P.n_dora == 1) {
         int n_ind[5] = {0, 0, 0, 0, 0};
@@ -349,23 +356,41 @@ MJX_DN bool sp_get_score(const SpCtx& s, const SpRow& P, const SpKey& key, int w
         for (int i = 0; i < 4; i++)
             for (int j = 0; j < 5; j++) {
                 if (up[j] == 0.f) continue;
-                scores[i] = SP_FADD(scores[i], SP_FMUL(pts(han + i + j), up[j]));
+                scores[i] = SP_FADD(scores[i], SP_FMUL(pts[i + j], up[j]));
             }
     } else if (assume_riichi && P.n_dora > 1) {
         for (int i = 0; i < 4; i++)
             for (int j = 0; j < 13; j++) {
                 float p = c_uradora_prob[P.n_dora - 1][j];
                 if (p == 0.f) continue;
-                scores[i] = SP_FADD(scores[i], SP_FMUL(pts(han + i + j), p));
+                scores[i] = SP_FADD(scores[i], SP_FMUL(pts[i + j], p));
             }
     } else {
-        for (int i = 0; i < 4; i++) scores[i] = pts(han + i);
+        for (int i = 0; i < 4; i++) scores[i] = pts[i];
     }
     return true;
 }
 
 // calc.rs:447-561 draw_without_tegawari_slow for one W-state at shanten k (one warp, lane i = turn i)
-MJX_DN void sp_eval_w(SpCtx& s, const Ctx& c, int node, int k) {
+// stage: score every winning draw of every tenpai state, ONE THREAD PER DRAW (calc.rs:478-479 get_score).
+// Full lane utilisation for the branchy agari evaluation; the per-turn accumulation happens in sp_eval_w<true>.
+MJX_DN void sp_score_edge(const SpCtx& s, int e) {
+    const int node = (int)s.G.edge_owner[e];
+    const SpRow& P = s.G.rows[s.G.node_row[node]];
+    float sc[4];
+    const u16 m = s.G.edge_meta[e];
+    const bool ok = sp_get_score(s, P, s.G.keys[node], m & 63, sc);
+    const int le = e - s.G.counters[4];
+    if (!ok) s.G.edge_meta[e] = (u16)(m | 0x8000);
+    else if (le >= 0 && le < s.G.score_cap) {
+        float* o = s.G.leaf_scores + (size_t)le * 4;
+        o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2]; o[3] = sc[3];
+    }
+}
+
+template <bool LEAF>
+MJX_DN void sp_eval_w(SpCtx& s, const Ctx& c, int node, int k_rt) {
+    const int k = LEAF ? 0 : k_rt;
     const int row = s.G.node_row[node];
     const SpRow& P = s.G.rows[row];
     const int T = P.T, n_left = P.n_left;
@@ -373,7 +398,7 @@ MJX_DN void sp_eval_w(SpCtx& s, const Ctx& c, int node, int k) {
     const u32 eb = s.G.edge_begin[node];
     SpWarpScratch& ws = *s.ws;
     int sum_required = 0;
-    for (int e = 0; e < ne; e++) sum_required += s.G.edge_meta[eb + e] >> 6;
+    for (int e = 0; e < ne; e++) sum_required += (s.G.edge_meta[eb + e] >> 6) & 7;
     sum_required &= 0xFF;
     // not_tsumo_prob_table[sum_required][j], recomputed with the table's own recurrence (calc.rs:158-165)
     SP_FOR_LANES(j, T) {
@@ -389,12 +414,12 @@ MJX_DN void sp_eval_w(SpCtx& s, const Ctx& c, int node, int k) {
         ws.nts[j] = v;
     }
     if (k == 0) {
-        const SpKey key = s.G.keys[node];
+        // scores were produced by sp_score_edge; stage them for the turn lanes
+        const int le0 = (int)eb - s.G.counters[4];
         SP_FOR_LANES(e, ne) {
-            float sc[4];
-            bool ok = sp_get_score(s, P, key, s.G.edge_meta[eb + e] & 63, sc);
+            const bool ok = !(s.G.edge_meta[eb + e] & 0x8000) && le0 + e >= 0 && le0 + e < s.G.score_cap;
             ws.score_ok[e] = ok ? 1 : 0;
-            for (int q = 0; q < 4; q++) ws.scores[e][q] = sc[q];
+            if (ok) for (int q = 0; q < 4; q++) ws.scores[e][q] = s.G.leaf_scores[(size_t)(le0 + e) * 4 + q];
         }
     }
     MJX_SYNCWARP();
@@ -404,7 +429,7 @@ MJX_DN void sp_eval_w(SpCtx& s, const Ctx& c, int node, int k) {
 #endif
     const bool assume_riichi = P.is_menzen && P.prefer_riichi;
     for (int e = 0; e < ne; e++) {
-        const int cnt = s.G.edge_meta[eb + e] >> 6;
+        const int cnt = (s.G.edge_meta[eb + e] >> 6) & 7;
         if (k == 0 && !ws.score_ok[e]) continue;  // uniform
         const u32 child = s.G.edge_child[eb + e];
         if (k > 0 && child == SP_NO_CHILD) continue;  // only after an overflow
@@ -713,7 +738,7 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
             for (int q = 0; q < ne; q++) {
                 const u16 m = s.G.edge_meta[eb + q];
                 req |= 1ull << deaka(m & 63);
-                num += m >> 6;
+                num += (m >> 6) & 7;
             }
             cd.required = req;
             cd.num_required = num & 0xFF;

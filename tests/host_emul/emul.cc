@@ -209,9 +209,11 @@ void emul_env_encode_obs(void* p, float* obs, int sp) {
     static SpGlobal G;
     static std::vector<SpRow> rows; static std::vector<SpKey> keys; static std::vector<i32> node_row, slot_list;
     static std::vector<float> vals; static std::vector<u32> edge_begin, edge_child, hash; static std::vector<u8> n_edges;
-    static std::vector<u16> edge_meta; static i32 slot_count[SP_SLOTS], counters[4];
+    static std::vector<u16> edge_meta; static i32 slot_count[SP_SLOTS], counters[8];
+    static std::vector<u32> edge_owner; static std::vector<float> leaf_scores;
     if (keys.empty()) {
-        G.node_cap = 1 << 20; G.slot_cap = G.node_cap; G.edge_cap = G.node_cap * 12; G.hash_cap = 1 << 21;
+        G.node_cap = 1 << 20; G.slot_cap = G.node_cap; G.edge_cap = G.node_cap * 6; G.hash_cap = 1 << 21; G.score_cap = G.edge_cap / 2;
+        edge_owner.resize(G.edge_cap); leaf_scores.resize((size_t)G.score_cap * 4); G.edge_owner = edge_owner.data(); G.leaf_scores = leaf_scores.data();
         rows.resize(1 << 16); keys.resize(G.node_cap); node_row.resize(G.node_cap);
         vals.resize((size_t)G.node_cap * 3 * SP_T_MAX); edge_begin.resize(G.node_cap); n_edges.resize(G.node_cap);
         edge_child.resize(G.edge_cap); edge_meta.resize(G.edge_cap); hash.resize(G.hash_cap);
@@ -228,12 +230,18 @@ void emul_env_encode_obs(void* p, float* obs, int sp) {
     SpCtx s; s.G = G; s.T = g_T; s.ws = &ws; s.lane = 0;
     Ctx c; c.S = nullptr; c.W = nullptr; c.T = g_T; c.lane = 0; c.df = nullptr;
     for (int r = 0; r < n_rows; r++) sp_stage_init(s, &E->tabs[E->row_table[r]], r, E->row_table[r], E->row_seat[r] & 3);
-    for (int slot = 0; slot < SP_SLOTS; slot++)
+    for (int slot = 0; slot < SP_SLOTS; slot++) {
+        if (slot == SP_SLOTS - 1) counters[4] = counters[1];
         for (int i = 0; i < std::min(slot_count[slot], G.slot_cap); i++) sp_expand(s, c, slot_list[(size_t)slot * G.slot_cap + i], slot);
+    }
+    counters[5] = counters[1];
+    for (int e = counters[4]; e < counters[5]; e++) sp_score_edge(s, e);
     for (int slot = SP_SLOTS - 1; slot >= 0; slot--)
         for (int i = 0; i < std::min(slot_count[slot], G.slot_cap); i++) {
             int node = slot_list[(size_t)slot * G.slot_cap + i];
-            if (sp_slot_is_w(slot)) sp_eval_w(s, c, node, sp_slot_shanten(slot)); else sp_eval_d(s, c, node);
+            if (!sp_slot_is_w(slot)) sp_eval_d(s, c, node);
+            else if (sp_slot_shanten(slot) == 0) sp_eval_w<true>(s, c, node, 0);
+            else sp_eval_w<false>(s, c, node, sp_slot_shanten(slot));
         }
     for (int r = 0; r < n_rows; r++) sp_stage_finalize(s, r, obs + (size_t)r * OBS_ROWS_V4 * OBS_COLS);
     if (counters[2]) g_emul_sp_overflows++;
