@@ -396,11 +396,14 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
     {
         SpGlobal& G = env->sp;
         G.node_cap = n_tables * 2048 > (1 << 20) ? n_tables * 2048 : (1 << 20);  // ~0.4 KB per state
+        if (G.node_cap > (1 << 24) - 2) G.node_cap = (1 << 24) - 2;  // 24-bit index field of the hash entries
         G.slot_cap = G.node_cap;
         G.edge_cap = G.node_cap * 6;
         G.score_cap = G.edge_cap / 2;
+        // ~1.3x the arena capacity: a typical step fills a third of the arena, so the table stays under ~25%
+        // load and (32 MB at 4096 tables) inside the 126 MB L2; the 24-bit index field bounds node_cap at 16M
         int hc = 1;
-        while (hc < 2 * G.node_cap) hc <<= 1;
+        while (hc < G.node_cap + G.node_cap / 4) hc <<= 1;
         G.hash_cap = hc;
         CU(cudaMalloc(&G.rows, cap * sizeof(SpRow)));
         CU(cudaMalloc(&G.keys, (size_t)G.node_cap * sizeof(SpKey)));

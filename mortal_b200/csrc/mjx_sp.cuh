@@ -41,13 +41,21 @@ constexpr u32 SP_NO_CHILD = 0xFFFFFFFFu;
 #endif
 
 // sp/state.rs:10-21 (n_extra_tsumo is always 0 without tegawari)
-struct SpKey {
+struct alignas(8) SpKey {
     u8 tehai[34];
     u8 wall[34];
     u8 akas;      // bits 0-2 akas_in_hand, bits 3-5 akas_in_wall
     u8 pad_[3];
 };
 static_assert(sizeof(SpKey) == 72, "SpKey layout");
+
+// 9 x 8-byte moves instead of 72 byte moves (the u8 arrays alone would only guarantee 1-byte alignment)
+MJX_D void sp_key_copy(SpKey* dst, const SpKey* src) {
+    const u64* a = reinterpret_cast<const u64*>(src);
+    u64* b = reinterpret_cast<u64*>(dst);
+#pragma unroll
+    for (int i = 0; i < 9; i++) b[i] = a[i];
+}
 
 // per observation row: sp/calc.rs:36-62 parameters + what obs_repr.rs needs afterwards
 struct SpRow {
@@ -115,6 +123,7 @@ struct SpWarpScratch {
     float cv[3][SP_T_MAX];     // child values of the current edge
     float scores[40][4];       // get_score of each winning draw of a W0 state
     u8 score_ok[40];
+    SpKey key;                   // the state being expanded, staged once per warp
     u8 ed_tile[40], ed_cnt[40];  // edge descriptors of the state being expanded
     u8 df[34];
     u8 pad_[2];
@@ -178,7 +187,7 @@ MJX_DN int sp_new_node(SpCtx& s, int row, const SpKey& key, int slot) {
     int pos = atomicAdd(&s.G.slot_count[slot], 1);
 #endif
     if (idx >= s.G.node_cap || pos >= s.G.slot_cap) { sp_set_overflow(s); return -1; }
-    s.G.keys[idx] = key;
+    sp_key_copy(&s.G.keys[idx], &key);
     s.G.node_row[idx] = row;
     s.G.n_edges[idx] = 0;
     s.G.edge_begin[idx] = 0;
@@ -191,7 +200,9 @@ MJX_DN int sp_new_node(SpCtx& s, int row, const SpKey& key, int slot) {
 // thread published the same state in the meantime its node wins and ours is simply never referenced.
 MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
     const u32 mask = (u32)s.G.hash_cap - 1;
-    u32 h = sp_hash_key(row, key) & mask;
+    const u32 hv = sp_hash_key(row, key);
+    const u32 tag = (hv >> 24) << 24;  // 8-bit tag kept beside the 24-bit index: mismatches never touch the key array
+    u32 h = hv & mask;
     int mine = -1;
     for (int probe = 0; probe < s.G.hash_cap; probe++, h = (h + 1) & mask) {
 #ifdef MJX_HOST_EMUL
@@ -199,7 +210,7 @@ MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
         if (cur == 0) {
             int idx = sp_new_node(s, row, key, slot);
             if (idx < 0) return -1;
-            s.G.hash[h] = (u32)idx + 1;
+            s.G.hash[h] = ((u32)idx + 1) | tag;
             return idx;
         }
 #else
@@ -210,12 +221,13 @@ MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
                 if (mine < 0) return -1;
                 __threadfence();
             }
-            const u32 prev = atomicCAS(&s.G.hash[h], 0u, (u32)mine + 1);
+            const u32 prev = atomicCAS(&s.G.hash[h], 0u, ((u32)mine + 1) | tag);
             if (prev == 0) return mine;
             cur = prev;
         }
 #endif
-        const int ci = (int)cur - 1;
+        if ((cur & 0xFF000000u) != tag) continue;
+        const int ci = (int)(cur & 0x00FFFFFFu) - 1;
         if (sp_ld_row(s.G.node_row + ci) == row && sp_key_eq(s.G.keys[ci], key)) return ci;
     }
     sp_set_overflow(s);
@@ -232,7 +244,15 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
     const int k = sp_slot_shanten(slot);
     const bool leaf = is_w && k == 0;
     const int row = s.G.node_row[node];
-    const SpKey key = s.G.keys[node];
+    SpWarpScratch& ws = *s.ws;
+    MJX_SYNCWARP();
+#ifdef MJX_HOST_EMUL
+    sp_key_copy(&ws.key, &s.G.keys[node]);
+#else
+    if (s.lane < 9) reinterpret_cast<u64*>(&ws.key)[s.lane] = reinterpret_cast<const u64*>(&s.G.keys[node])[s.lane];
+#endif
+    MJX_SYNCWARP();
+    const SpKey& key = ws.key;
     const int len = s.G.rows[row].tehai_len_div3;
     const HandSig base = hand_sig(key.tehai);
     u64 eff, unused;
@@ -247,7 +267,6 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
             return shanten_all_sig(s.T, sig_variant(base, t, -1, key.tehai[t]), len) == k ? 1 : 0;
         }, eff, unused);
     }
-    SpWarpScratch& ws = *s.ws;
     if (MJX_IS_L0(c)) {
         // edge descriptors in tile order; an effective 5 whose aka is still in the wall splits in two
         // (sp/state.rs:160-176); a discarded 5 is the aka only when it is the last 5 in hand (state.rs:127-132)
@@ -287,7 +306,8 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
         const int suit5 = is_aka(tile) ? tile - T_5MR : -1;
         u32 child = SP_NO_CHILD;
         if (!leaf) {
-            SpKey ck = key;
+            SpKey ck;
+            sp_key_copy(&ck, &key);
             if (is_w) {
                 ck.tehai[t] += 1;
                 ck.wall[t] -= 1;
@@ -379,7 +399,9 @@ MJX_DN void sp_score_edge(const SpCtx& s, int e) {
     const SpRow& P = s.G.rows[s.G.node_row[node]];
     float sc[4];
     const u16 m = s.G.edge_meta[e];
-    const bool ok = sp_get_score(s, P, s.G.keys[node], m & 63, sc);
+    SpKey key;
+    sp_key_copy(&key, &s.G.keys[node]);
+    const bool ok = sp_get_score(s, P, key, m & 63, sc);
     const int le = e - s.G.counters[4];
     if (!ok) s.G.edge_meta[e] = (u16)(m | 0x8000);
     else if (le >= 0 && le < s.G.score_cap) {
@@ -654,7 +676,7 @@ MJX_DN void sp_stage_init(SpCtx& s, const TableState* S, int row, int table, int
             const int akas_seen = S->akas_public | PV.akas_in_hand;
             root.akas = (u8)((akas_hand & 7) | (((~akas_seen) & 7) << 3));
             root.pad_[0] = root.pad_[1] = root.pad_[2] = 0;
-            R.root_key = root;
+            sp_key_copy(&R.root_key, &root);
             if (R.has_values) {
                 const int slot = 2 * (3 - cur_shanten) + (R.can_discard ? 0 : 1);
                 R.root = sp_new_node(s, row, root, slot);
