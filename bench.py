@@ -124,7 +124,7 @@ def run_reference(args):
 
     def one():
         r = O.run_batch(nonces, keys, shuffle_kind=0, policy_kind=1, quick_eval=True, encode_obs=4, sp_mode=1,
-                        n_threads=cores, max_steps=steps_per_table)
+                        n_threads=cores, max_steps=args.skip + steps_per_table, encode_from_step=args.skip)
         return r["table_steps"], r["seconds"], r["obs_rows"]
 
     for _ in range(args.warmup):
@@ -135,7 +135,7 @@ def run_reference(args):
         tot_steps += s
         tot_sec += t
     value = tot_steps / tot_sec
-    sample = f"{n_tables} tables x first {steps_per_table} table-steps each per step (seeds {SEED_START[0]}.., greedy test policy, v4 obs + SP encode per decision)"
+    sample = f"{n_tables} tables x table-steps {args.skip}..{args.skip + steps_per_table} each per step (seeds {SEED_START[0]}.., greedy test policy, v4 obs + SP encode per decision)"
     line = {
         "impl": "reference", "metric": "table-steps/sec batched self-play", "value": value, "unit": "table-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_sec / args.steps,
@@ -180,22 +180,28 @@ def run_ours(args):
                           enable_amp=True, enable_quick_eval=True)
 
     def fresh_env():
-        return mortal_b200.BatchEnv(nonces, keys, obs_version=4, shuffle_kind=0, enable_quick_eval=True, device=local_rank)
+        """A new batch, fast-forwarded (untimed, greedy test policy, no encode) by --skip batch steps so that the timed
+        steps see the steady-state mix of early/late kyoku positions instead of 4096 freshly dealt hands."""
+        env = mortal_b200.BatchEnv(nonces, keys, obs_version=4, shuffle_kind=0, enable_quick_eval=True, device=local_rank)
+        actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
+        env.step(None)
+        env.policy_test(1, actions)
+        for _ in range(args.skip):
+            env.step(actions)
+            env.policy_test(1, actions)
+        return env, actions
 
     W, K = args.warmup, args.steps
     stats = {}
 
     # -------- loop A: with the network (the BASELINE config), HBM resident
-    def loop(env, policy, n_warm, n_timed, time_encode=False):
-        actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
+    def loop(env_actions, policy, n_warm, n_timed, time_encode=False):
+        env, actions = env_actions
         obs = env.obs_buffer()
-        first = True
         enc_events = []
 
         def cycle(timed):
-            nonlocal first
-            env.step(None if first else actions)
-            first = False
+            env.step(actions)
             if timed and time_encode:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -209,7 +215,7 @@ def run_ours(args):
         for _ in range(n_warm):
             cycle(False)
         barrier()
-        steps0, rows = env.total_steps(), 0
+        steps0, rows, l0 = env.total_steps(), 0, env.launch_count()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(n_timed):
@@ -219,7 +225,7 @@ def run_ours(args):
         ms = t0.elapsed_time(t1)
         steps = env.total_steps() - steps0
         enc_ms = sum(a.elapsed_time(b) for a, b in enc_events)
-        return dict(ms=ms, table_steps=steps, rows=rows, enc_ms=enc_ms, n=n_timed)
+        return dict(ms=ms, table_steps=steps, rows=rows, enc_ms=enc_ms, n=n_timed, launches=env.launch_count() - l0)
 
     def nn_policy(env, obs, actions):
         nr = env.num_rows()  # the only host sync of the cycle: the batch size the network runs at
@@ -234,48 +240,43 @@ def run_ours(args):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    env = fresh_env()
-    a = loop(env, nn_policy, W, K)
-    env.close()
+    ea = fresh_env()
+    a = loop(ea, nn_policy, W, K)
+    ea[0].close()
     clocks = sampler.stop()
 
     # -------- loop B: env only (test policy on device, no host sync)
-    env = fresh_env()
-    b = loop(env, test_policy, W, K)
-    sp_overflows = env.sp_overflows()
-    env.close()
+    ea = fresh_env()
+    b = loop(ea, test_policy, W, K)
+    sp_overflows = ea[0].sp_overflows()
+    ea[0].close()
     # -------- loop B2: the HBM-bound encode kernel alone (single-player block off), timed with CUDA events
-    env = fresh_env()
-    env.set_sp(False)
-    b2 = loop(env, test_policy, W, K, time_encode=True)
+    ea = fresh_env()
+    ea[0].set_sp(False)
+    b2 = loop(ea, test_policy, W, K, time_encode=True)
+    ea[0].close()
+    # rows per launch for the roofline: the same deterministic K cycles again, reading the row count each step
+    env, actions = fresh_env()
     b_rows = 0
-    # rows per step for the roofline: replay the same K cycles' row counts is not needed; sample the average
-    env.close()
-    env = fresh_env()
-    actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
-    first = True
     for i in range(W + K):
-        env.step(None if first else actions)
-        first = False
+        env.step(actions)
         env.policy_test(1, actions)
         if i >= W:
             b_rows += env.num_rows()
     env.close()
 
     # -------- loop C: e2e through the C ABI with HOST buffers (pinned): obs/masks D2H, actions H2D each step
-    env = fresh_env()
+    env, d_actions = fresh_env()
     h_obs = torch.empty((env.row_cap, 1012, 34), dtype=torch.float32, pin_memory=True)
     h_masks = torch.empty((env.row_cap, 46), dtype=torch.bool, pin_memory=True)
     h_actions = torch.zeros(env.row_cap, dtype=torch.int64).pin_memory()
-    d_actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
+    h_actions.copy_(d_actions)
     gen = torch.Generator().manual_seed(1)
     e2e_h2d = e2e_d2h = 0
 
-    def e2e_cycle(first):
-        nonlocal e2e_h2d, e2e_d2h
-        if not first:
-            d_actions.copy_(h_actions, non_blocking=True)  # H2D: the step's inputs
-        env.step(None if first else d_actions)
+    def e2e_cycle():
+        d_actions.copy_(h_actions, non_blocking=True)  # H2D: the step's inputs
+        env.step(d_actions)
         obs = env.encode_obs()
         nr = env.num_rows()
         if nr:
@@ -288,10 +289,8 @@ def run_ours(args):
             h_actions[:nr] = q.argmax(-1)
         return nr
 
-    first = True
     for _ in range(W):
-        e2e_cycle(first)
-        first = False
+        e2e_cycle()
     barrier()
     s0 = env.total_steps()
     w0 = time.perf_counter()
@@ -299,8 +298,7 @@ def run_ours(args):
     t0.record()
     e2e_rows = 0
     for _ in range(K):
-        e2e_rows += e2e_cycle(first)
-        first = False
+        e2e_rows += e2e_cycle()
     t1.record()
     barrier()
     e2e_ms = max(t0.elapsed_time(t1), (time.perf_counter() - w0) * 1000.0)
@@ -354,7 +352,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u8/i32 env + bf16 policy net", "data": "synthetic",
             "config": {"workload": "BatchGame 4096 tables/GPU, random-init Mortal brain (192ch x 40 blocks, v4 obs), self-play step loop (BASELINE configs[1])",
                        "tables_per_gpu": N_TABLES, "global_tables": N_TABLES * world, "obs_version": 4,
-                       "seed_start": list(SEED_START), "parallelism": f"tables sharded dp{world}, no data-path collective",
+                       "seed_start": list(SEED_START), "fast_forward_steps": args.skip, "parallelism": f"tables sharded dp{world}, no data-path collective",
                        "l2": "per-step obs output (~0.7 GB) exceeds the 126 MB L2, no explicit flush",
                        "sp_block": "rows 889-1011 (single-player tables) computed on device by the k_sp_* kernels",
                        "sp_arena_overflows": sp_overflows},
@@ -369,7 +367,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": 8 * N_TABLES * 3,
                     "d2h_bytes_per_step": int(e2e_rows / K * (OBS_BYTES + MASK_BYTES)),
                     "path": "mjx C ABI with pinned host buffers: actions H2D, obs+masks D2H every step, host-side policy"},
-            "gpu_launches": K * 23, "clocks": clocks,
+            "gpu_launches": a["launches"], "clocks": clocks,
             "collective": {"all_gather_us": gather_us, "bytes_per_table": 20},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -387,9 +385,10 @@ def cpu_baseline(args):
     nonces, keys = seeds_for_rank(0, N_TABLES)
     n = args.ref_tables
     r = O.run_batch(nonces[:n], keys[:n], shuffle_kind=0, policy_kind=1, quick_eval=True, encode_obs=4, sp_mode=1,
-                    n_threads=cores, max_steps=args.ref_steps_per_table)
+                    n_threads=cores, max_steps=args.skip + args.ref_steps_per_table, encode_from_step=args.skip)
     return {"value": r["table_steps"] / r["seconds"], "unit": "table-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n} tables x first {args.ref_steps_per_table} table-steps, v4 obs + SP encode per decision, {r['seconds']:.1f} s"}
+            "sample": f"{n} tables x table-steps {args.skip}..{args.skip + args.ref_steps_per_table} (same fast-forward as the GPU arm), "
+                      f"v4 obs + SP encode per decision, {r['seconds']:.1f} s"}
 
 
 def main():
@@ -397,6 +396,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--skip", type=int, default=300, help="untimed fast-forward batch steps before warm-up (both arms)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-tables", type=int, default=256)
     ap.add_argument("--ref-steps-per-table", type=int, default=40)

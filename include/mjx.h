@@ -71,6 +71,9 @@ int mjx_env_num_rows(mjx_env* env, void* stream, int* n_rows);          /* rows 
 int mjx_env_num_live(mjx_env* env, void* stream, int* n_live);          /* tables still playing */
 int mjx_env_total_steps(mjx_env* env, void* stream, int64_t* steps);    /* game.rs:304 `actions` counter */
 
+/* Number of kernels this library has launched for env so far (host-side counter; bench.py's gpu_launches). */
+long long mjx_env_launch_count(mjx_env* env);
+
 /* Device views, valid for the lifetime of env (contents valid until the next mjx_env_step). */
 int mjx_env_row_cap(mjx_env* env);
 uint8_t* mjx_env_masks(mjx_env* env);      /* uint8/bool [row_cap, 46]  (obs_repr.rs mask) */

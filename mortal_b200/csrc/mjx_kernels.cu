@@ -314,6 +314,7 @@ struct mjx_env {
     SpGlobal sp;
     int sp_enabled = 1;
     int enc_grid = 0;
+    long long launches = 0;  // kernels launched on behalf of this env (bench.py's gpu_launches)
 };
 
 extern "C" {
@@ -470,6 +471,7 @@ int mjx_env_step(mjx_env* env, const int64_t* actions_dev, const float* q_values
     k_begin_step<<<1, 1, 0, st>>>(V);
     k_step<<<(env->n_tables + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32, 0, st>>>(V, g_T);
     CU(cudaGetLastError());
+    env->launches += 2;
     env->first = false;
     return MJX_OK;
 }
@@ -497,10 +499,14 @@ int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
             else k_sp_eval<1><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
         }
         k_sp_finalize<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev);
+        env->launches += 5 + 2 * SP_SLOTS + 1;
     }
     CU(cudaGetLastError());
+    env->launches += 1;
     return MJX_OK;
 }
+
+long long mjx_env_launch_count(mjx_env* env) { return env ? env->launches : -1; }
 
 int mjx_env_set_sp(mjx_env* env, int enable) {
     if (!env) return fail(MJX_ERR_ARG, "mjx_env_set_sp: null env");
@@ -567,6 +573,7 @@ int mjx_env_policy_test(mjx_env* env, int kind, int64_t* actions_dev, int64_t* t
     if (!env || !actions_dev) return fail(MJX_ERR_ARG, "mjx_env_policy_test: bad arguments");
     k_policy_test<<<g_sm_count * 2, 128, 0, (cudaStream_t)stream>>>(env->V, kind, (i64*)actions_dev, (i64*)trace_dev, q_values_dev);
     CU(cudaGetLastError());
+    env->launches += 1;
     return MJX_OK;
 }
 

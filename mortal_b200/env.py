@@ -110,6 +110,10 @@ class BatchEnv:
         _lib.check(self.L.mjx_env_sp_overflows(self._h, self._stream(), C.byref(n)), "mjx_env_sp_overflows")
         return n.value
 
+    def launch_count(self) -> int:
+        """kernels launched for this env so far (host-side counter in libmjx)"""
+        return int(self.L.mjx_env_launch_count(self._h))
+
     def num_rows(self) -> int:
         n = C.c_int(0)
         _lib.check(self.L.mjx_env_num_rows(self._h, self._stream(), C.byref(n)), "mjx_env_num_rows")

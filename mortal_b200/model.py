@@ -32,11 +32,9 @@ class ChannelGate(nn.Module):
         return x * gate.unsqueeze(-1)
 
     def forward_fast(self, x):
-        # same maths; the two length-34 reductions go through pooling kernels instead of generic reduce kernels
-        avg = torch.nn.functional.avg_pool1d(x, x.shape[-1]).squeeze(-1)
-        mx = torch.nn.functional.max_pool1d(x, x.shape[-1]).squeeze(-1)
-        gate = torch.sigmoid(self._mlp(avg) + self._mlp(mx))
-        return x * gate.unsqueeze(-1)
+        # x: [B, C, 1, L] channels_last; same maths as forward()
+        gate = torch.sigmoid(self._mlp(x.mean((2, 3))) + self._mlp(x.amax((2, 3))))
+        return x * gate.view(gate.shape[0], gate.shape[1], 1, 1)
 
 
 class PreActBlock(nn.Module):
@@ -59,12 +57,13 @@ class PreActBlock(nn.Module):
         # eval-mode BatchNorm is a per-channel affine map: y = x * scale + shift
         scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
         shift = bn.bias - bn.running_mean * scale
-        return scale.view(1, -1, 1), shift.view(1, -1, 1)
+        return scale.view(1, -1, 1, 1).contiguous(), shift.view(1, -1, 1, 1).contiguous()
 
-    def forward_fast(self, x, aff):
+    def forward_fast(self, x, aff, w1, w2):
         (s1, b1), (s2, b2) = aff
-        y = self.conv1(torch.nn.functional.mish(torch.addcmul(b1, x, s1)))
-        y = self.conv2(torch.nn.functional.mish(torch.addcmul(b2, y, s2)))
+        F = torch.nn.functional
+        y = F.conv2d(F.mish(torch.addcmul(b1, x, s1)), w1, padding=(0, 1))
+        y = F.conv2d(F.mish(torch.addcmul(b2, y, s2)), w2, padding=(0, 1))
         return self.gate.forward_fast(y) + x
 
 
@@ -96,18 +95,24 @@ class Brain(nn.Module):
             self.to(dtype)
         self._aff = [(PreActBlock._affine(b.bn1), PreActBlock._affine(b.bn2)) for b in self.blocks]
         self._aff_out = PreActBlock._affine(self.bn)
+        # the Conv1d kernels as (1 x 3) Conv2d kernels in channels_last, so cuDNN runs NHWC without layout round trips
+        cl = lambda conv: conv.weight.unsqueeze(2).contiguous(memory_format=torch.channels_last)
+        self._w = [(cl(b.conv1), cl(b.conv2)) for b in self.blocks]
+        self._w_stem, self._w_neck = cl(self.stem), cl(self.neck)
         self._fast_dtype = dtype
         return self
 
     def forward_fast(self, obs):
+        F = torch.nn.functional
         if self._fast_dtype is not None:
             obs = obs.to(self._fast_dtype)
-        x = self.stem(obs)
-        for blk, aff in zip(self.blocks, self._aff):
-            x = blk.forward_fast(x, aff)
+        x = obs.unsqueeze(2).contiguous(memory_format=torch.channels_last)  # [B, C, 1, 34]
+        x = F.conv2d(x, self._w_stem, padding=(0, 1))
+        for blk, aff, (w1, w2) in zip(self.blocks, self._aff, self._w):
+            x = blk.forward_fast(x, aff, w1, w2)
         s, b = self._aff_out
-        x = torch.nn.functional.mish(self.neck(torch.nn.functional.mish(torch.addcmul(b, x, s))))
-        return torch.nn.functional.mish(self.fc(x.flatten(1)))
+        x = F.mish(F.conv2d(F.mish(torch.addcmul(b, x, s)), self._w_neck, self.neck.bias, padding=(0, 1)))
+        return F.mish(self.fc(x.flatten(1)))
 
 
 class DQN(nn.Module):

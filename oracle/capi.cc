@@ -421,6 +421,7 @@ struct orc_run_cfg {
     int32_t sp_mode;
     int32_t n_threads;
     int64_t max_steps_per_table;  // stop early after this many table-steps (0 = run to the end)
+    int64_t encode_from_step;     // bench fast-forward: steps before this one are played without encoding and not counted
 };
 struct orc_run_out {
     int64_t table_steps;   // sum over tables of decision cycles (game.rs:304 `actions`)
@@ -446,7 +447,7 @@ static void run_range(const orc_run_cfg& cfg, const uint64_t* nonces, const uint
             int64_t rows = 0;
             PolicyFn pol = [&](const Scene& sc, const u8* mask, float*) {
                 rows++;
-                if (cfg.encode_obs) {
+                if (cfg.encode_obs && (int64_t)sc.step_idx >= cfg.encode_from_step) {
                     u8 m2[46];
                     sc.state->encode_obs(cfg.encode_obs, sc.is_kan_select, obs.data(), m2, cfg.sp_mode);
                 }
@@ -474,7 +475,7 @@ static void run_range(const orc_run_cfg& cfg, const uint64_t* nonces, const uint
             for (int i = 0; i < 4; i++) scores[t * 4 + i] = g.scores[i];
             rankings(g.scores, nullptr, ranks + t * 4);
             steps[t] = (int32_t)n_steps;
-            total_steps->fetch_add(n_steps);
+            total_steps->fetch_add(std::max<int64_t>(0, n_steps - cfg.encode_from_step));
             total_rows->fetch_add(rows);
         }
     } catch (const std::exception& e) { *err = e.what(); }

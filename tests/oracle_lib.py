@@ -122,7 +122,8 @@ class SpCand(C.Structure):
 class RunCfg(C.Structure):
     _fields_ = [("n_tables", C.c_int32), ("shuffle_kind", C.c_int32), ("policy_kind", C.c_int32),
                 ("enable_quick_eval", C.c_int32), ("enable_agari_guard", C.c_int32), ("encode_obs", C.c_int32),
-                ("sp_mode", C.c_int32), ("n_threads", C.c_int32), ("max_steps_per_table", C.c_int64)]
+                ("sp_mode", C.c_int32), ("n_threads", C.c_int32), ("max_steps_per_table", C.c_int64),
+                ("encode_from_step", C.c_int64)]
 
 
 class RunOut(C.Structure):
@@ -438,7 +439,7 @@ class PlayerState:
 
 
 def run_batch(nonces, keys, *, shuffle_kind=0, policy_kind=1, quick_eval=True, agari_guard=False, encode_obs=0,
-              sp_mode=1, n_threads=1, max_steps=0, table_ids=None, trace_cap=0):
+              sp_mode=1, n_threads=1, max_steps=0, table_ids=None, trace_cap=0, encode_from_step=0):
     n = len(nonces)
     nonces = np.ascontiguousarray(nonces, dtype=np.uint64)
     keys = np.ascontiguousarray(keys, dtype=np.uint64)
@@ -448,7 +449,7 @@ def run_batch(nonces, keys, *, shuffle_kind=0, policy_kind=1, quick_eval=True, a
     steps = np.zeros(n, dtype=np.int32)
     trace = np.zeros((trace_cap, 6), dtype=np.int64) if trace_cap else None
     tlen = C.c_int64(0)
-    cfg = RunCfg(n, shuffle_kind, policy_kind, int(quick_eval), int(agari_guard), encode_obs, sp_mode, n_threads, max_steps)
+    cfg = RunCfg(n, shuffle_kind, policy_kind, int(quick_eval), int(agari_guard), encode_obs, sp_mode, n_threads, max_steps, encode_from_step)
     out = RunOut()
     rc = lib().orc_run_batch(C.byref(cfg), nonces.ctypes.data, keys.ctypes.data,
                              None if tids is None else tids.ctypes.data, scores.ctypes.data, ranks.ctypes.data,
