@@ -58,6 +58,12 @@ int mjx_env_set_agari_guard(mjx_env* env, const uint8_t* flags_host);
  * obs_dev = float32 [row_cap, rows(version), 34] (only the first n_rows rows are written). */
 int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream);
 
+/* The same for a caller that holds HOST buffers (what agent/mortal.rs:126-152 hands to react_batch): encodes into the
+ * device scratch `obs_dev` [row_cap, rows, 34] and copies rows [0, *n_rows) to `obs_host` (same layout) and `masks_host`
+ * (uint8 [row_cap, 46]); the copy of rows 0..888 overlaps the single-player kernels. Blocking; host buffers should be
+ * pinned (cudaHostAlloc / torch pin_memory) for the overlap to happen. */
+int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8_t* masks_host, int* n_rows, void* stream);
+
 /* state/agent_helper.rs:509-593 single_player_tables (obs v4 rows 889-1011): on by default; `enable = 0`
  * leaves the block zero (the reference has no such switch; it exists for profiling the rest of the encoder).
  * mjx_env_sp_overflows: number of steps so far in which the state arena (2048 states per table on average)

@@ -73,65 +73,125 @@ __global__ void k_init_tables(TableState* tabs, int n, const u64* nonces, const 
     err[t] = 0;
 }
 
-// Observation half-tile: built in shared memory, leaves as one bulk async copy (TMA).
-constexpr int ENC_THREADS = 256;
-constexpr int ENC_HALF_ROWS_MAX = OBS_SPLIT_ROW;  // 522 rows (first half) >= 490 rows (second half)
-constexpr size_t ENC_TILE_BYTES = (size_t)ENC_HALF_ROWS_MAX * OBS_COLS * sizeof(float);  // 70,992
-constexpr size_t ENC_STATE_OFF = ENC_TILE_BYTES;
-constexpr size_t ENC_SMEM_BYTES = ENC_TILE_BYTES + sizeof(TableState) + 64;  // ~73 KB -> 3 CTAs / SM
-static_assert((OBS_SPLIT_ROW * OBS_COLS * sizeof(float)) % 16 == 0, "half boundary must be 16-byte aligned");
-static_assert(((OBS_ROWS_V4 - OBS_SPLIT_ROW) * OBS_COLS * sizeof(float)) % 16 == 0, "second half must be 16-byte sized");
+// Observation encoder, stage 1: one warp = one feature group (ENC_N_PARTS row ranges) of one decision row. Stage the
+// table record, derive that part of the compact form (row masks + value rows, csrc/mjx_obs.cuh) in shared memory,
+// copy it out coalesced (10,944 B per row in total). Items are ordered part-major: neighbouring warps run the same code.
+constexpr int ENCF_WARPS = 16;
+constexpr int ENC_COMPACT_BYTES = OBS_BM_ROWS * 8 + OBS_N_SPECIAL * OBS_COLS * 4;                  // 7,136 + 3,808
+constexpr int ENCF_WARP_BYTES = ENC_COMPACT_BYTES + (int)sizeof(TableState) + 48;                  // + record + dora factors
+constexpr size_t ENCF_SMEM_BYTES = (size_t)ENCF_WARPS * ENCF_WARP_BYTES;
+static_assert(ENC_COMPACT_BYTES % 16 == 0 && ENCF_WARP_BYTES % 16 == 0, "16-byte vector copies");
+static_assert(ENCF_SMEM_BYTES <= 232448, "one CTA per SM");
 
-__global__ void __launch_bounds__(ENC_THREADS, 3) k_encode_obs_v4(EnvView V, Tables T, float* __restrict__ obs) {
+__global__ void __launch_bounds__(ENCF_WARPS * 32, 1) k_encode_features(EnvView V, Tables T, unsigned char* __restrict__ compact) {
     extern __shared__ __align__(128) unsigned char s_raw[];
-    float* tile = reinterpret_cast<float*>(s_raw);
-    TableState* s_state = reinterpret_cast<TableState*>(s_raw + ENC_STATE_OFF);
-    u8* df = s_raw + ENC_STATE_OFF + sizeof(TableState);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_items = *V.n_rows * 2;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int row = item >> 1, half = item & 1;
-        const int row_lo = half ? OBS_SPLIT_ROW : 0, row_hi = half ? OBS_ROWS_V4 : OBS_SPLIT_ROW;
-        const int tile_bytes = (row_hi - row_lo) * OBS_COLS * (int)sizeof(float);
-        // stage the table record (coalesced 16-byte loads) and clear the half-tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = s_raw + (size_t)warp * ENCF_WARP_BYTES;
+    u64* bm = reinterpret_cast<u64*>(base);
+    float* sv = reinterpret_cast<float*>(base + OBS_BM_ROWS * 8);
+    TableState* s_state = reinterpret_cast<TableState*>(base + ENC_COMPACT_BYTES);
+    u8* df = base + ENC_COMPACT_BYTES + sizeof(TableState);
+    const int n_rows = *V.n_rows;
+    const int n_items = n_rows * ENC_N_PARTS;
+    for (int item = blockIdx.x * ENCF_WARPS + warp; item < n_items; item += gridDim.x * ENCF_WARPS) {
+        const int part = item / n_rows, row = item - part * n_rows;
+        // this part's window of the compact form, in 8-byte words (mask rows, then the value rows as word pairs x 17)
+        const int bm_lo = enc_part_bm_begin(part), bm_hi = enc_part_bm_begin(part + 1);
+        const int sv_lo = OBS_BM_ROWS + enc_part_sv_begin(part) * 17, sv_hi = OBS_BM_ROWS + enc_part_sv_begin(part + 1) * 17;
         {
             const uint4* src = reinterpret_cast<const uint4*>(V.tables + V.row_table[row]);
             uint4* dst = reinterpret_cast<uint4*>(s_state);
-            for (int i = tid; i < (int)(sizeof(TableState) / 16); i += ENC_THREADS) dst[i] = __ldg(src + i);
-            uint4* t4 = reinterpret_cast<uint4*>(tile);
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            for (int i = tid; i < tile_bytes / 16; i += ENC_THREADS) t4[i] = z;
+            for (int i = lane; i < (int)(sizeof(TableState) / 16); i += 32) dst[i] = __ldg(src + i);
+            for (int i = bm_lo + lane; i < bm_hi; i += 32) bm[i] = 0;
+            for (int i = sv_lo + lane; i < sv_hi; i += 32) bm[i] = 0;
         }
-        __syncthreads();
+        __syncwarp();
         const TableState* S = s_state;
-        const int seat = V.row_seat[row] & 3;
-        const bool kan = (V.row_seat[row] >> 2) & 1;
-        if (tid < 34) {
-            int f = 0;
-            for (int k = 0; k < S->n_dora; k++) f += tile_next(S->wall[60 - k]) == tid;
-            df[tid] = (u8)f;
+        {   // dora factors: lane k resolves indicator k once, every lane counts its own tile kinds
+            const int nd = S->n_dora;
+            const int d = lane < nd ? tile_next(S->wall[60 - lane]) : -1;
+            int f0 = 0, f1 = 0;
+            for (int k = 0; k < nd; k++) {
+                const int dk = __shfl_sync(0xffffffffu, d, k);
+                f0 += dk == lane;
+                f1 += dk == lane + 32;
+            }
+            df[lane] = (u8)f0;
+            if (lane < 2) df[32 + lane] = (u8)f1;
         }
-        __syncthreads();
+        __syncwarp();
+        const u8 rs = V.row_seat[row];
         EncCtx e;
-        e.S = S; e.T = T; e.tile = tile; e.seat = seat; e.kan_select = kan;
-        e.lane = lane; e.warp = warp; e.nwarps = ENC_THREADS / 32; e.dora_factor = df;
-        e.row_lo = row_lo; e.row_hi = row_hi;
+        e.S = S; e.T = T; e.bm = bm; e.sv = sv; e.seat = rs & 3; e.kan_select = (rs >> 2) & 1;
+        e.lane = lane; e.dora_factor = df; e.parts = 1u << part;
         Ctx c;
         c.S = s_state; c.W = nullptr; c.T = T; c.lane = lane; c.df = df;
         encode_obs_v4(e, c, nullptr);
-        // make the generic-proxy smem writes visible to the async proxy, then one thread issues the bulk store
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            float* dst = obs + ((size_t)row * OBS_ROWS_V4 + row_lo) * OBS_COLS;
-            unsigned smem_addr = (unsigned)__cvta_generic_to_shared(tile);
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                         :: "l"(dst), "r"(smem_addr), "r"((unsigned)tile_bytes) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-        __syncthreads();
+        __syncwarp();
+        u64* out = reinterpret_cast<u64*>(compact + (size_t)row * ENC_COMPACT_BYTES);
+        for (int i = bm_lo + lane; i < bm_hi; i += 32) out[i] = bm[i];
+        for (int i = sv_lo + lane; i < sv_hi; i += 32) out[i] = bm[i];
+        __syncwarp();
     }
+}
+
+// Stage 2, the HBM-bound one: one warp = one slice of one observation at a time. Clear a shared-memory tile, light
+// the non-zero rows from the compact form, hand the tile to the copy engine as one bulk async store (TMA). Two tiles
+// per warp: the next slice is built while the copy engine still reads the previous one.
+constexpr int ENCS_WARPS = 16;
+constexpr int ENC_SLICE_BYTES = OBS_SLICE_ROWS * OBS_COLS * (int)sizeof(float);  // 6,256
+constexpr size_t ENCS_SMEM_BYTES = (size_t)ENCS_WARPS * 2 * ENC_SLICE_BYTES;     // 200,192
+static_assert(ENC_SLICE_BYTES % 16 == 0, "bulk copies need 16-byte alignment");
+static_assert(OBS_ROWS_V4 % OBS_SLICE_ROWS == 0, "slices tile the observation exactly");
+static_assert(ENCS_SMEM_BYTES <= 232448, "one CTA per SM");
+
+__global__ void __launch_bounds__(ENCS_WARPS * 32, 1) k_encode_store(EnvView V, const unsigned char* __restrict__ compact,
+                                                                     float* __restrict__ obs) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* base = s_raw + (size_t)warp * 2 * ENC_SLICE_BYTES;
+    const int n_items = *V.n_rows * OBS_N_SLICES;
+    const int stride = gridDim.x * ENCS_WARPS;
+    // the 0.5 GB of observations stream through L2 as evict-first so that they do not push out the compact form
+    // this kernel is reading (44 MB, written by k_encode_features just before)
+    unsigned long long evict_first;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
+    int item = blockIdx.x * ENCS_WARPS + warp;
+    u64 m0 = 0, m1 = 0;
+    if (item < n_items) {
+        const int row = item / OBS_N_SLICES;
+        enc_load_masks(reinterpret_cast<const u64*>(compact + (size_t)row * ENC_COMPACT_BYTES), (item - row * OBS_N_SLICES) * OBS_SLICE_ROWS, lane, m0, m1);
+    }
+    for (int buf = 0; item < n_items; item += stride, buf ^= 1) {
+        const int row = item / OBS_N_SLICES, slice = item - row * OBS_N_SLICES;
+        const int row_lo = slice * OBS_SLICE_ROWS, row_hi = row_lo + OBS_SLICE_ROWS;
+        // the next item's row masks are requested now and consumed one iteration later
+        u64 n0 = 0, n1 = 0;
+        if (item + stride < n_items) {
+            const int nrow = (item + stride) / OBS_N_SLICES;
+            enc_load_masks(reinterpret_cast<const u64*>(compact + (size_t)nrow * ENC_COMPACT_BYTES),
+                           (item + stride - nrow * OBS_N_SLICES) * OBS_SLICE_ROWS, lane, n0, n1);
+        }
+        float* tile = reinterpret_cast<float*>(base + buf * ENC_SLICE_BYTES);
+        // the store that last used this tile (two items ago) must have finished reading it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const unsigned char* cf = compact + (size_t)row * ENC_COMPACT_BYTES;
+        enc_materialize(reinterpret_cast<const float*>(cf + OBS_BM_ROWS * 8), lane, tile, row_lo, row_hi, m0, m1);
+        // make the generic-proxy smem writes visible to the async proxy, then one lane issues the bulk store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            float* dst = obs + ((size_t)row * OBS_ROWS_V4 + row_lo) * OBS_COLS;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                         :: "l"(dst), "r"((unsigned)__cvta_generic_to_shared(tile)), "r"((unsigned)ENC_SLICE_BYTES), "l"(evict_first)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        m0 = n0; m1 = n1;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
 }
 
 // ---- single-player tables: level-synchronous DP over all rows of the step (csrc/mjx_sp.cuh)
@@ -313,7 +373,9 @@ struct mjx_env {
     u8* d_guard = nullptr;
     SpGlobal sp;
     int sp_enabled = 1;
-    int enc_grid = 0;
+    unsigned char* d_compact = nullptr;
+    cudaStream_t copy_stream = nullptr;  // mjx_env_encode_obs_host: D2H overlapped with the SP kernels
+    cudaEvent_t ev_rows = nullptr, ev_sp = nullptr;
     long long launches = 0;  // kernels launched on behalf of this env (bench.py's gpu_launches)
 };
 
@@ -343,7 +405,8 @@ int mjx_init(const char* data_dir, int device) {
     if ((rc = upload(H.agari_keys, &g_T.agari_keys))) return rc;
     if ((rc = upload(H.agari_divs, &g_T.agari_divs))) return rc;
     if ((rc = upload(H.agari_ndivs, &g_T.agari_ndivs))) return rc;
-    CU(cudaFuncSetAttribute(k_encode_obs_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_encode_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENCF_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_encode_store, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENCS_SMEM_BYTES));
     g_device = device;
     g_ready = true;
     return MJX_OK;
@@ -393,7 +456,7 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
     CU(cudaMalloc(&env->d_keys, sizeof(u64) * (size_t)n_tables));
     CU(cudaMalloc(&env->d_dummy_actions, sizeof(i64) * cap));
     memset(&env->sp, 0, sizeof env->sp);
-    env->enc_grid = g_sm_count * 3;
+    CU(cudaMalloc(&env->d_compact, cap * (size_t)ENC_COMPACT_BYTES));  // compact observations (mjx_obs.cuh), 11 KB per row
     {
         SpGlobal& G = env->sp;
         G.node_cap = n_tables * 2048 > (1 << 20) ? n_tables * 2048 : (1 << 20);  // ~0.4 KB per state
@@ -444,11 +507,12 @@ void mjx_env_destroy(mjx_env* env) {
     EnvView& V = env->V;
     cudaFree(V.tables); cudaFree(V.n_rows); cudaFree(V.row_table); cudaFree(V.row_seat); cudaFree(V.row_step);
     cudaFree(V.masks); cudaFree(V.scores); cudaFree(V.ranks); cudaFree(V.done); cudaFree(V.steps); cudaFree(V.err);
-    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard);
+    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard); cudaFree(env->d_compact);
     SpGlobal& G = env->sp;
     cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
     cudaFree(G.edge_child); cudaFree(G.edge_meta); cudaFree(G.edge_owner); cudaFree(G.leaf_scores); cudaFree(G.hash); cudaFree(G.slot_list); cudaFree(G.slot_count);
     cudaFree(G.counters);
+    if (env->copy_stream) { cudaStreamDestroy(env->copy_stream); cudaEventDestroy(env->ev_rows); cudaEventDestroy(env->ev_sp); }
     delete env;
 }
 
@@ -476,33 +540,79 @@ int mjx_env_step(mjx_env* env, const int64_t* actions_dev, const float* q_values
     return MJX_OK;
 }
 
+static int launch_encode_rows(mjx_env* env, float* obs_dev, cudaStream_t st) {
+    k_encode_features<<<g_sm_count, ENCF_WARPS * 32, ENCF_SMEM_BYTES, st>>>(env->V, g_T, env->d_compact);
+    k_encode_store<<<g_sm_count, ENCS_WARPS * 32, ENCS_SMEM_BYTES, st>>>(env->V, env->d_compact, obs_dev);
+    CU(cudaGetLastError());
+    env->launches += 2;
+    return MJX_OK;
+}
+
+// single-player block (rows 889..1011): init -> expand slots 0..7 -> score -> evaluate slots 7..0 -> finalize
+static int launch_sp_block(mjx_env* env, float* obs_dev, cudaStream_t st) {
+    if (!env->sp_enabled) return MJX_OK;
+    const SpGlobal& G = env->sp;
+    const int grid = g_sm_count * 8;
+    CU(cudaMemsetAsync(G.hash, 0, (size_t)G.hash_cap * sizeof(u32), st));
+    k_sp_begin<<<1, 32, 0, st>>>(G);
+    k_sp_init<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V);
+    for (int slot = 0; slot < SP_SLOTS; slot++) {
+        if (slot == SP_SLOTS - 1) k_sp_mark<<<1, 1, 0, st>>>(G, 0);
+        k_sp_expand<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+    }
+    k_sp_mark<<<1, 1, 0, st>>>(G, 1);
+    k_sp_score<<<g_sm_count * 16, 128, 0, st>>>(G, g_T);
+    for (int slot = SP_SLOTS - 1; slot >= 0; slot--) {
+        if (!sp_slot_is_w(slot)) k_sp_eval<0><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+        else if (slot == SP_SLOTS - 1) k_sp_eval<2><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+        else k_sp_eval<1><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+    }
+    k_sp_finalize<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev);
+    CU(cudaGetLastError());
+    env->launches += 5 + 2 * SP_SLOTS + 1;
+    return MJX_OK;
+}
+
 int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
     if (!env || !obs_dev) return fail(MJX_ERR_ARG, "mjx_env_encode_obs: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    k_encode_obs_v4<<<env->enc_grid, ENC_THREADS, ENC_SMEM_BYTES, st>>>(env->V, g_T, obs_dev);
-    if (env->sp_enabled) {
-        // single-player block (rows 889..1011): init -> expand slots 0..7 -> evaluate slots 7..0 -> finalize
-        const SpGlobal& G = env->sp;
-        const int grid = g_sm_count * 8;
-        CU(cudaMemsetAsync(G.hash, 0, (size_t)G.hash_cap * sizeof(u32), st));
-        k_sp_begin<<<1, 32, 0, st>>>(G);
-        k_sp_init<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V);
-        for (int slot = 0; slot < SP_SLOTS; slot++) {
-            if (slot == SP_SLOTS - 1) k_sp_mark<<<1, 1, 0, st>>>(G, 0);
-            k_sp_expand<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
-        }
-        k_sp_mark<<<1, 1, 0, st>>>(G, 1);
-        k_sp_score<<<g_sm_count * 16, 128, 0, st>>>(G, g_T);
-        for (int slot = SP_SLOTS - 1; slot >= 0; slot--) {
-            if (!sp_slot_is_w(slot)) k_sp_eval<0><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
-            else if (slot == SP_SLOTS - 1) k_sp_eval<2><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
-            else k_sp_eval<1><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
-        }
-        k_sp_finalize<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev);
-        env->launches += 5 + 2 * SP_SLOTS + 1;
+    int rc = launch_encode_rows(env, obs_dev, st);
+    if (rc) return rc;
+    return launch_sp_block(env, obs_dev, st);
+}
+
+int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8_t* masks_host, int* n_rows_out, void* stream) {
+    if (!env || !obs_dev || !obs_host || !masks_host || !n_rows_out)
+        return fail(MJX_ERR_ARG, "mjx_env_encode_obs_host: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!env->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&env->ev_rows, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&env->ev_sp, cudaEventDisableTiming));
     }
-    CU(cudaGetLastError());
-    env->launches += 1;
+    int n = 0;
+    CU(cudaMemcpyAsync(&n, env->V.n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_rows_out = n;
+    if (n == 0) return MJX_OK;
+    const size_t pitch = (size_t)OBS_ROWS_V4 * 34 * sizeof(float);
+    const size_t head = env->sp_enabled ? (size_t)SP_ROW0 * 34 * sizeof(float) : pitch;  // rows below the SP block
+    int rc = launch_encode_rows(env, obs_dev, st);
+    if (rc) return rc;
+    CU(cudaEventRecord(env->ev_rows, st));
+    // the copy engine drains rows [0, 889) and the masks while the SMs compute the single-player block
+    CU(cudaStreamWaitEvent(env->copy_stream, env->ev_rows, 0));
+    CU(cudaMemcpy2DAsync(obs_host, pitch, obs_dev, pitch, head, (size_t)n, cudaMemcpyDeviceToHost, env->copy_stream));
+    CU(cudaMemcpyAsync(masks_host, env->V.masks, (size_t)n * MJX_ACTION_SPACE, cudaMemcpyDeviceToHost, env->copy_stream));
+    if (env->sp_enabled) {
+        rc = launch_sp_block(env, obs_dev, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(env->ev_sp, st));
+        CU(cudaStreamWaitEvent(env->copy_stream, env->ev_sp, 0));
+        CU(cudaMemcpy2DAsync((char*)obs_host + head, pitch, (const char*)obs_dev + head, pitch, pitch - head, (size_t)n,
+                             cudaMemcpyDeviceToHost, env->copy_stream));
+    }
+    CU(cudaStreamSynchronize(env->copy_stream));
     return MJX_OK;
 }
 

@@ -102,6 +102,19 @@ class BatchEnv:
         _lib.check(self.L.mjx_env_encode_obs(self._h, C.c_void_p(out.data_ptr()), self._stream()), "mjx_env_encode_obs")
         return out
 
+    def encode_obs_host(self, obs_host, masks_host) -> int:
+        """Encode the current rows into HOST tensors (pinned for speed): obs_host f32 [>=row_cap, C, 34], masks_host
+        bool/uint8 [>=row_cap, 46]. The D2H copy of rows 0..888 overlaps the single-player kernels. Returns num_rows."""
+        assert obs_host.dtype == self.torch.float32 and obs_host.is_contiguous() and not obs_host.is_cuda
+        assert obs_host.shape[0] >= self.row_cap and tuple(obs_host.shape[1:]) == (self.obs_rows, 34)
+        assert masks_host.element_size() == 1 and masks_host.is_contiguous() and not masks_host.is_cuda
+        assert masks_host.shape[0] >= self.row_cap and masks_host.shape[1] == 46
+        n = C.c_int(0)
+        _lib.check(self.L.mjx_env_encode_obs_host(self._h, C.c_void_p(self.obs_buffer().data_ptr()), C.c_void_p(obs_host.data_ptr()),
+                                                  C.c_void_p(masks_host.data_ptr()), C.byref(n), self._stream()),
+                   "mjx_env_encode_obs_host")
+        return n.value
+
     def set_sp(self, enable: bool) -> None:
         _lib.check(self.L.mjx_env_set_sp(self._h, int(enable)), "mjx_env_set_sp")
 

@@ -194,15 +194,19 @@ void emul_env_encode_obs(void* p, float* obs, int sp) {
             for (int k = 0; k < S->n_dora; k++) f += tile_next(S->wall[60 - k]) == t;
             df[t] = (u8)f;
         }
+        std::vector<u64> bm(OBS_BM_ROWS, 0);
+        std::vector<float> sv((size_t)OBS_N_SPECIAL * OBS_COLS, 0.f);
         EncCtx e;
-        e.S = S; e.T = g_T; e.tile = tile; e.seat = E->row_seat[r] & 3; e.kan_select = (E->row_seat[r] >> 2) & 1;
-        e.lane = 0; e.warp = 0; e.nwarps = 1; e.dora_factor = df;
+        e.S = S; e.T = g_T; e.bm = bm.data(); e.sv = sv.data(); e.seat = E->row_seat[r] & 3; e.kan_select = (E->row_seat[r] >> 2) & 1;
+        e.lane = 0; e.dora_factor = df;
         Ctx c; c.S = const_cast<TableState*>(S); c.W = nullptr; c.T = g_T; c.lane = 0; c.df = df;
-        // built as the two half-tiles the CUDA kernel builds
-        e.row_lo = 0; e.row_hi = OBS_SPLIT_ROW; e.tile = tile;
-        encode_obs_v4(e, c, nullptr);
-        e.row_lo = OBS_SPLIT_ROW; e.row_hi = OBS_ROWS_V4; e.tile = tile + (size_t)OBS_SPLIT_ROW * OBS_COLS;
-        encode_obs_v4(e, c, nullptr);
+        for (int part = 0; part < ENC_N_PARTS; part++) {  // part by part, as the CUDA kernel derives them
+            e.parts = 1u << part;
+            encode_obs_v4(e, c, nullptr);
+        }
+        // materialised slice by slice, as the CUDA kernel does
+        for (int sl = 0; sl < OBS_N_SLICES; sl++)
+            enc_materialize(e, tile + (size_t)sl * OBS_SLICE_ROWS * OBS_COLS, sl * OBS_SLICE_ROWS, (sl + 1) * OBS_SLICE_ROWS);
     }
     if (!sp) return;
     // the same stage sequence mjx_env_encode_obs launches, executed by one lane

@@ -216,6 +216,32 @@ def test_obs_encode_matches_oracle(mjx):
     assert make_env.overflows == 0
 
 
+def test_encode_obs_host_equals_device_encode(mjx):
+    """mjx_env_encode_obs_host (D2H overlapped with the SP kernels) delivers exactly the device encoding."""
+    import torch
+
+    n = 64
+    nonces = np.arange(500, 500 + n, dtype=np.uint64)
+    keys = np.full(n, 3, dtype=np.uint64)
+    env = mjx.BatchEnv(nonces, keys)
+    actions = torch.zeros(env.row_cap, dtype=torch.int64, device=env.device)
+    h_obs = torch.full((env.row_cap, 1012, 34), -1.0, dtype=torch.float32).pin_memory()
+    h_masks = torch.zeros((env.row_cap, 46), dtype=torch.bool).pin_memory()
+    env.step(None)
+    checked = 0
+    for cycle in range(60):
+        nr = env.encode_obs_host(h_obs, h_masks)
+        assert nr == env.num_rows()
+        dev = env.encode_obs()[:nr].cpu()
+        assert torch.equal(h_obs[:nr], dev)
+        assert torch.equal(h_masks[:nr], env.masks[:nr].cpu())
+        checked += nr
+        env.policy_test(1, actions)
+        env.step(actions)
+    assert checked > 60 * n * 0.9 and env.sp_overflows() == 0
+    env.close()
+
+
 def test_one_vs_three_network_policy_action_replay(mjx):
     """BASELINE config 2 protocol (SURVEY.md §8d ii): a float policy (random-init Mortal brain, greedy) drives the CUDA
     arena through the libriichi-compatible OneVsThree.py_vs_py; the recorded decisions are replayed in the oracle,
