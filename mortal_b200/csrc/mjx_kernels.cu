@@ -75,29 +75,39 @@ __global__ void k_init_tables(TableState* tabs, int n, const u64* nonces, const 
 
 // Observation encoder, stage 1: one warp = one feature group (ENC_N_PARTS row ranges) of one decision row. Stage the
 // table record, derive that part of the compact form (row masks + value rows, csrc/mjx_obs.cuh) in shared memory,
-// copy it out coalesced (10,944 B per row in total). Items are ordered part-major: neighbouring warps run the same code.
-constexpr int ENCF_WARPS = 16;
-constexpr int ENC_COMPACT_BYTES = OBS_BM_ROWS * 8 + OBS_N_SPECIAL * OBS_COLS * 4;                  // 7,136 + 3,808
-constexpr int ENCF_WARP_BYTES = ENC_COMPACT_BYTES + (int)sizeof(TableState) + 48;                  // + record + dora factors
-constexpr size_t ENCF_SMEM_BYTES = (size_t)ENCF_WARPS * ENCF_WARP_BYTES;
-static_assert(ENC_COMPACT_BYTES % 16 == 0 && ENCF_WARP_BYTES % 16 == 0, "16-byte vector copies");
-static_assert(ENCF_SMEM_BYTES <= 232448, "one CTA per SM");
+// copy it out coalesced (10,944 B per row for v4). Items are ordered part-major: neighbouring warps run the same code.
+template <int VER> struct EncF {
+    static constexpr int COMPACT = enc_compact_bytes(VER);
+    static constexpr int COMPACT_PAD = (COMPACT + 15) & ~15;                       // the staged record wants 16-byte alignment
+    static constexpr int WARP_BYTES = COMPACT_PAD + (int)sizeof(TableState) + 48;  // + record + dora factors
+    static constexpr int WARPS = 232448 / WARP_BYTES >= 16 ? 16 : 232448 / WARP_BYTES;  // one CTA per SM
+    static constexpr size_t SMEM = (size_t)WARPS * WARP_BYTES;
+    static_assert(COMPACT % 8 == 0 && WARP_BYTES % 16 == 0, "vector copies");
+};
 
-__global__ void __launch_bounds__(ENCF_WARPS * 32, 1) k_encode_features(EnvView V, Tables T, unsigned char* __restrict__ compact) {
+template <int VER>
+__global__ void __launch_bounds__(EncF<VER>::WARPS * 32, 1) k_encode_features(EnvView V, Tables T, unsigned char* __restrict__ compact) {
+    constexpr ObsLayout L = make_layout(VER);
+    constexpr int COMPACT = EncF<VER>::COMPACT, WARPS = EncF<VER>::WARPS;
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* base = s_raw + (size_t)warp * ENCF_WARP_BYTES;
+    unsigned char* base = s_raw + (size_t)warp * EncF<VER>::WARP_BYTES;
     u64* bm = reinterpret_cast<u64*>(base);
-    float* sv = reinterpret_cast<float*>(base + OBS_BM_ROWS * 8);
-    TableState* s_state = reinterpret_cast<TableState*>(base + ENC_COMPACT_BYTES);
-    u8* df = base + ENC_COMPACT_BYTES + sizeof(TableState);
+    float* sv = reinterpret_cast<float*>(base + L.bm_rows * 8);
+    TableState* s_state = reinterpret_cast<TableState*>(base + EncF<VER>::COMPACT_PAD);
+    u8* df = base + EncF<VER>::COMPACT_PAD + sizeof(TableState);
     const int n_rows = *V.n_rows;
     const int n_items = n_rows * ENC_N_PARTS;
-    for (int item = blockIdx.x * ENCF_WARPS + warp; item < n_items; item += gridDim.x * ENCF_WARPS) {
+    for (int item = blockIdx.x * WARPS + warp; item < n_items; item += gridDim.x * WARPS) {
         const int part = item / n_rows, row = item - part * n_rows;
-        // this part's window of the compact form, in 8-byte words (mask rows, then the value rows as word pairs x 17)
-        const int bm_lo = enc_part_bm_begin(part), bm_hi = enc_part_bm_begin(part + 1);
-        const int sv_lo = OBS_BM_ROWS + enc_part_sv_begin(part) * 17, sv_hi = OBS_BM_ROWS + enc_part_sv_begin(part + 1) * 17;
+        // this part's window of the compact form, in 8-byte words (mask rows, then the value rows as 17 words each)
+        int bm_lo = 0, bm_hi = 0, sv_lo = 0, sv_hi = 0;
+#pragma unroll
+        for (int q = 0; q < ENC_N_PARTS; q++)
+            if (q == part) {
+                bm_lo = L.part_row[q]; bm_hi = L.part_row[q + 1];
+                sv_lo = L.bm_rows + L.part_sv[q] * 17; sv_hi = L.bm_rows + L.part_sv[q + 1] * 17;
+            }
         {
             const uint4* src = reinterpret_cast<const uint4*>(V.tables + V.row_table[row]);
             uint4* dst = reinterpret_cast<uint4*>(s_state);
@@ -126,9 +136,9 @@ __global__ void __launch_bounds__(ENCF_WARPS * 32, 1) k_encode_features(EnvView 
         e.lane = lane; e.dora_factor = df; e.parts = 1u << part;
         Ctx c;
         c.S = s_state; c.W = nullptr; c.T = T; c.lane = lane; c.df = df;
-        encode_obs_v4(e, c, nullptr);
+        encode_obs<VER>(e, c, nullptr);
         __syncwarp();
-        u64* out = reinterpret_cast<u64*>(compact + (size_t)row * ENC_COMPACT_BYTES);
+        u64* out = reinterpret_cast<u64*>(compact + (size_t)row * COMPACT);
         for (int i = bm_lo + lane; i < bm_hi; i += 32) out[i] = bm[i];
         for (int i = sv_lo + lane; i < sv_hi; i += 32) out[i] = bm[i];
         __syncwarp();
@@ -142,16 +152,19 @@ constexpr int ENCS_WARPS = 16;
 constexpr int ENC_SLICE_BYTES = OBS_SLICE_ROWS * OBS_COLS * (int)sizeof(float);  // 6,256
 constexpr size_t ENCS_SMEM_BYTES = (size_t)ENCS_WARPS * 2 * ENC_SLICE_BYTES;     // 200,192
 static_assert(ENC_SLICE_BYTES % 16 == 0, "bulk copies need 16-byte alignment");
-static_assert(OBS_ROWS_V4 % OBS_SLICE_ROWS == 0, "slices tile the observation exactly");
 static_assert(ENCS_SMEM_BYTES <= 232448, "one CTA per SM");
 
-__global__ void __launch_bounds__(ENCS_WARPS * 32, 1) k_encode_store(EnvView V, const unsigned char* __restrict__ compact,
+struct EncStoreArgs { int rows, bm_rows, n_sv, compact_bytes, n_slices, ver; };
+__constant__ short c_sv_row[4][OBS_MAX_SV];  // ObsLayout::sv_row of versions 1..4
+
+__global__ void __launch_bounds__(ENCS_WARPS * 32, 1) k_encode_store(EnvView V, EncStoreArgs A, const unsigned char* __restrict__ compact,
                                                                      float* __restrict__ obs) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = s_raw + (size_t)warp * 2 * ENC_SLICE_BYTES;
-    const int n_items = *V.n_rows * OBS_N_SLICES;
+    const int n_items = *V.n_rows * A.n_slices;
     const int stride = gridDim.x * ENCS_WARPS;
+    const short* sv_row = c_sv_row[A.ver - 1];
     // the 0.5 GB of observations stream through L2 as evict-first so that they do not push out the compact form
     // this kernel is reading (44 MB, written by k_encode_features just before)
     unsigned long long evict_first;
@@ -159,32 +172,34 @@ __global__ void __launch_bounds__(ENCS_WARPS * 32, 1) k_encode_store(EnvView V, 
     int item = blockIdx.x * ENCS_WARPS + warp;
     u64 m0 = 0, m1 = 0;
     if (item < n_items) {
-        const int row = item / OBS_N_SLICES;
-        enc_load_masks(reinterpret_cast<const u64*>(compact + (size_t)row * ENC_COMPACT_BYTES), (item - row * OBS_N_SLICES) * OBS_SLICE_ROWS, lane, m0, m1);
+        const int row = item / A.n_slices;
+        enc_load_masks(reinterpret_cast<const u64*>(compact + (size_t)row * A.compact_bytes), A.bm_rows,
+                       (item - row * A.n_slices) * OBS_SLICE_ROWS, lane, m0, m1);
     }
     for (int buf = 0; item < n_items; item += stride, buf ^= 1) {
-        const int row = item / OBS_N_SLICES, slice = item - row * OBS_N_SLICES;
-        const int row_lo = slice * OBS_SLICE_ROWS, row_hi = row_lo + OBS_SLICE_ROWS;
+        const int row = item / A.n_slices, slice = item - row * A.n_slices;
+        const int row_lo = slice * OBS_SLICE_ROWS, row_hi = min(row_lo + OBS_SLICE_ROWS, A.rows);
         // the next item's row masks are requested now and consumed one iteration later
         u64 n0 = 0, n1 = 0;
         if (item + stride < n_items) {
-            const int nrow = (item + stride) / OBS_N_SLICES;
-            enc_load_masks(reinterpret_cast<const u64*>(compact + (size_t)nrow * ENC_COMPACT_BYTES),
-                           (item + stride - nrow * OBS_N_SLICES) * OBS_SLICE_ROWS, lane, n0, n1);
+            const int nrow = (item + stride) / A.n_slices;
+            enc_load_masks(reinterpret_cast<const u64*>(compact + (size_t)nrow * A.compact_bytes), A.bm_rows,
+                           (item + stride - nrow * A.n_slices) * OBS_SLICE_ROWS, lane, n0, n1);
         }
         float* tile = reinterpret_cast<float*>(base + buf * ENC_SLICE_BYTES);
         // the store that last used this tile (two items ago) must have finished reading it
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
-        const unsigned char* cf = compact + (size_t)row * ENC_COMPACT_BYTES;
-        enc_materialize(reinterpret_cast<const float*>(cf + OBS_BM_ROWS * 8), lane, tile, row_lo, row_hi, m0, m1);
+        const unsigned char* cf = compact + (size_t)row * A.compact_bytes;
+        enc_materialize(reinterpret_cast<const float*>(cf + A.bm_rows * 8), sv_row, A.n_sv, lane, tile, row_lo, row_hi, m0, m1);
         // make the generic-proxy smem writes visible to the async proxy, then one lane issues the bulk store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-            float* dst = obs + ((size_t)row * OBS_ROWS_V4 + row_lo) * OBS_COLS;
+            float* dst = obs + ((size_t)row * A.rows + row_lo) * OBS_COLS;
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                         :: "l"(dst), "r"((unsigned)__cvta_generic_to_shared(tile)), "r"((unsigned)ENC_SLICE_BYTES), "l"(evict_first)
+                         :: "l"(dst), "r"((unsigned)__cvta_generic_to_shared(tile)),
+                            "r"((unsigned)((row_hi - row_lo) * OBS_COLS * (int)sizeof(float))), "l"(evict_first)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -374,10 +389,16 @@ struct mjx_env {
     SpGlobal sp;
     int sp_enabled = 1;
     unsigned char* d_compact = nullptr;
+    EncStoreArgs enc_args{};
     cudaStream_t copy_stream = nullptr;  // mjx_env_encode_obs_host: D2H overlapped with the SP kernels
     cudaEvent_t ev_rows = nullptr, ev_sp = nullptr;
     long long launches = 0;  // kernels launched on behalf of this env (bench.py's gpu_launches)
 };
+
+template <int VER>
+static void launch_features(mjx_env* env, cudaStream_t st) {
+    k_encode_features<VER><<<g_sm_count, EncF<VER>::WARPS * 32, EncF<VER>::SMEM, st>>>(env->V, g_T, env->d_compact);
+}
 
 extern "C" {
 
@@ -405,7 +426,18 @@ int mjx_init(const char* data_dir, int device) {
     if ((rc = upload(H.agari_keys, &g_T.agari_keys))) return rc;
     if ((rc = upload(H.agari_divs, &g_T.agari_divs))) return rc;
     if ((rc = upload(H.agari_ndivs, &g_T.agari_ndivs))) return rc;
-    CU(cudaFuncSetAttribute(k_encode_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENCF_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_encode_features<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EncF<1>::SMEM));
+    CU(cudaFuncSetAttribute(k_encode_features<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EncF<2>::SMEM));
+    CU(cudaFuncSetAttribute(k_encode_features<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EncF<3>::SMEM));
+    CU(cudaFuncSetAttribute(k_encode_features<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EncF<4>::SMEM));
+    {
+        short tab[4][OBS_MAX_SV];
+        for (int v = 1; v <= 4; v++) {
+            const ObsLayout L = make_layout(v);
+            for (int i = 0; i < OBS_MAX_SV; i++) tab[v - 1][i] = i < L.n_sv ? L.sv_row[i] : (short)-1;
+        }
+        CU(cudaMemcpyToSymbol(c_sv_row, tab, sizeof tab));
+    }
     CU(cudaFuncSetAttribute(k_encode_store, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENCS_SMEM_BYTES));
     g_device = device;
     g_ready = true;
@@ -426,7 +458,7 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
                    int shuffle_kind, int enable_quick_eval) {
     if (!g_ready) return fail(MJX_ERR_STATE, "mjx_env_create: call mjx_init first");
     if (!out || n_tables <= 0 || !nonces || !keys) return fail(MJX_ERR_ARG, "mjx_env_create: bad arguments");
-    if (obs_version != 4) return fail(MJX_ERR_ARG, "mjx_env_create: only obs version 4 is implemented on device");
+    if (obs_version < 1 || obs_version > 4) return fail(MJX_ERR_ARG, "mjx_env_create: obs_version must be 1..4 (consts.rs:18)");
     if (shuffle_kind != 0 && shuffle_kind != 1) return fail(MJX_ERR_ARG, "mjx_env_create: shuffle_kind must be 0 or 1");
     mjx_env* env = new mjx_env();
     env->n_tables = n_tables;
@@ -456,7 +488,15 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
     CU(cudaMalloc(&env->d_keys, sizeof(u64) * (size_t)n_tables));
     CU(cudaMalloc(&env->d_dummy_actions, sizeof(i64) * cap));
     memset(&env->sp, 0, sizeof env->sp);
-    CU(cudaMalloc(&env->d_compact, cap * (size_t)ENC_COMPACT_BYTES));  // compact observations (mjx_obs.cuh), 11 KB per row
+    {
+        const ObsLayout L = make_layout(obs_version);
+        env->enc_args.rows = L.rows; env->enc_args.bm_rows = L.bm_rows; env->enc_args.n_sv = L.n_sv;
+        env->enc_args.compact_bytes = L.bm_rows * 8 + L.n_sv * OBS_COLS * 4;
+        env->enc_args.n_slices = (L.rows + OBS_SLICE_ROWS - 1) / OBS_SLICE_ROWS;
+        env->enc_args.ver = obs_version;
+        CU(cudaMalloc(&env->d_compact, cap * (size_t)env->enc_args.compact_bytes));  // compact observations (mjx_obs.cuh)
+        env->sp_enabled = obs_version == 4 ? 1 : 0;  // the single-player block exists in v4 only
+    }
     {
         SpGlobal& G = env->sp;
         G.node_cap = n_tables * 2048 > (1 << 20) ? n_tables * 2048 : (1 << 20);  // ~0.4 KB per state
@@ -541,8 +581,13 @@ int mjx_env_step(mjx_env* env, const int64_t* actions_dev, const float* q_values
 }
 
 static int launch_encode_rows(mjx_env* env, float* obs_dev, cudaStream_t st) {
-    k_encode_features<<<g_sm_count, ENCF_WARPS * 32, ENCF_SMEM_BYTES, st>>>(env->V, g_T, env->d_compact);
-    k_encode_store<<<g_sm_count, ENCS_WARPS * 32, ENCS_SMEM_BYTES, st>>>(env->V, env->d_compact, obs_dev);
+    switch (env->obs_version) {
+        case 1: launch_features<1>(env, st); break;
+        case 2: launch_features<2>(env, st); break;
+        case 3: launch_features<3>(env, st); break;
+        default: launch_features<4>(env, st); break;
+    }
+    k_encode_store<<<g_sm_count, ENCS_WARPS * 32, ENCS_SMEM_BYTES, st>>>(env->V, env->enc_args, env->d_compact, obs_dev);
     CU(cudaGetLastError());
     env->launches += 2;
     return MJX_OK;
@@ -595,7 +640,7 @@ int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8
     CU(cudaStreamSynchronize(st));
     *n_rows_out = n;
     if (n == 0) return MJX_OK;
-    const size_t pitch = (size_t)OBS_ROWS_V4 * 34 * sizeof(float);
+    const size_t pitch = (size_t)env->enc_args.rows * 34 * sizeof(float);
     const size_t head = env->sp_enabled ? (size_t)SP_ROW0 * 34 * sizeof(float) : pitch;  // rows below the SP block
     int rc = launch_encode_rows(env, obs_dev, st);
     if (rc) return rc;
@@ -620,7 +665,7 @@ long long mjx_env_launch_count(mjx_env* env) { return env ? env->launches : -1; 
 
 int mjx_env_set_sp(mjx_env* env, int enable) {
     if (!env) return fail(MJX_ERR_ARG, "mjx_env_set_sp: null env");
-    env->sp_enabled = enable ? 1 : 0;
+    env->sp_enabled = (enable && env->obs_version == 4) ? 1 : 0;
     return MJX_OK;
 }
 

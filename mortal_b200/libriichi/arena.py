@@ -44,8 +44,11 @@ class _Arena:
         for a in agents:
             if getattr(a, "is_oracle", False):
                 raise NotImplementedError("oracle (invisible) observations are out of this round's scope")
-            if getattr(a, "version", 4) != 4:
-                raise NotImplementedError("only obs version 4 is implemented on device")
+            if getattr(a, "version", 4) not in (1, 2, 3, 4):
+                raise ValueError(f"unsupported obs version {a.version} (consts.rs:18 MAX_VERSION = 4)")
+        versions = [int(getattr(a, "version", 4)) for a in agents]
+        if versions[0] != versions[1]:
+            raise NotImplementedError("challenger and champion must use the same obs version (one encoder pass per step)")
         qe = [bool(getattr(a, "enable_quick_eval", True)) for a in agents]
         if qe[0] != qe[1]:
             raise NotImplementedError("challenger and champion must agree on enable_quick_eval")
@@ -53,7 +56,7 @@ class _Arena:
         n = int(seed_count) * per
         nonces = np.repeat(np.arange(seed_start[0], seed_start[0] + int(seed_count), dtype=np.uint64), per)
         keys = np.full(n, seed_start[1], dtype=np.uint64)
-        env = BatchEnv(nonces, keys, obs_version=4, shuffle_kind=self.shuffle_kind, enable_quick_eval=qe[0],
+        env = BatchEnv(nonces, keys, obs_version=versions[0], shuffle_kind=self.shuffle_kind, enable_quick_eval=qe[0],
                        device=self.device)
         dev = env.device
         # seat -> agent index table per game-in-seed

@@ -40,6 +40,7 @@ def lib():
         L.emul_env_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_env_policy_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.emul_env_encode_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.emul_env_encode_obs_v.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.emul_sp_overflows.restype = C.c_long
         L.emul_env_results.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         if L.emul_init(DATA_DIR.encode()) != 0:
@@ -108,7 +109,8 @@ class EmulEnv:
         self.L.emul_env_policy_test(self._h, kind, a.ctypes.data)
         return a
 
-    def encode_obs(self, sp=False):
-        obs = np.zeros((self.num_rows(), 1012, 34), dtype=np.float32)
-        self.L.emul_env_encode_obs(self._h, obs.ctypes.data, int(sp))
+    def encode_obs(self, sp=False, version=4):
+        rows = {1: 938, 2: 942, 3: 934, 4: 1012}[version]
+        obs = np.zeros((self.num_rows(), rows, 34), dtype=np.float32)
+        self.L.emul_env_encode_obs_v(self._h, obs.ctypes.data, int(sp), version)
         return obs

@@ -177,16 +177,19 @@ void emul_env_policy_test(void* p, int kind, int64_t* actions) {
         actions[r] = test_policy(kind, h, kan != 0, m, P.keep_shanten, P.next_shanten);
     }
 }
+void emul_env_encode_obs_v(void* p, float* obs, int sp, int version);
+void emul_env_encode_obs(void* p, float* obs, int sp) { emul_env_encode_obs_v(p, obs, sp, 4); }
 static long g_emul_sp_overflows = 0;
 long emul_sp_overflows() { return g_emul_sp_overflows; }
 
-// obs: [n_rows, 1012, 34] f32; sp: compute the single-player block
-void emul_env_encode_obs(void* p, float* obs, int sp) {
+// obs: [n_rows, rows(version), 34] f32; sp: compute the single-player block (version 4 only)
+void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
     EmulEnv* E = static_cast<EmulEnv*>(p);
     const int n_rows = E->n_rows[0];
+    const ObsLayout L = make_layout(version);
     for (int r = 0; r < n_rows; r++) {
-        float* tile = obs + (size_t)r * OBS_ROWS_V4 * OBS_COLS;
-        memset(tile, 0, sizeof(float) * OBS_ROWS_V4 * OBS_COLS);
+        float* tile = obs + (size_t)r * L.rows * OBS_COLS;
+        memset(tile, 0, sizeof(float) * L.rows * OBS_COLS);
         const TableState* S = &E->tabs[E->row_table[r]];
         u8 df[34];
         for (int t = 0; t < 34; t++) {
@@ -194,21 +197,21 @@ void emul_env_encode_obs(void* p, float* obs, int sp) {
             for (int k = 0; k < S->n_dora; k++) f += tile_next(S->wall[60 - k]) == t;
             df[t] = (u8)f;
         }
-        std::vector<u64> bm(OBS_BM_ROWS, 0);
-        std::vector<float> sv((size_t)OBS_N_SPECIAL * OBS_COLS, 0.f);
+        std::vector<u64> bm(L.bm_rows, 0);
+        std::vector<float> sv((size_t)OBS_MAX_SV * OBS_COLS, 0.f);
         EncCtx e;
         e.S = S; e.T = g_T; e.bm = bm.data(); e.sv = sv.data(); e.seat = E->row_seat[r] & 3; e.kan_select = (E->row_seat[r] >> 2) & 1;
         e.lane = 0; e.dora_factor = df;
         Ctx c; c.S = const_cast<TableState*>(S); c.W = nullptr; c.T = g_T; c.lane = 0; c.df = df;
         for (int part = 0; part < ENC_N_PARTS; part++) {  // part by part, as the CUDA kernel derives them
             e.parts = 1u << part;
-            encode_obs_v4(e, c, nullptr);
+            encode_obs_any(version, e, c, nullptr);
         }
         // materialised slice by slice, as the CUDA kernel does
-        for (int sl = 0; sl < OBS_N_SLICES; sl++)
-            enc_materialize(e, tile + (size_t)sl * OBS_SLICE_ROWS * OBS_COLS, sl * OBS_SLICE_ROWS, (sl + 1) * OBS_SLICE_ROWS);
+        for (int lo = 0; lo < L.rows; lo += OBS_SLICE_ROWS)
+            enc_materialize(L, e, tile + (size_t)lo * OBS_COLS, lo, lo + OBS_SLICE_ROWS < L.rows ? lo + OBS_SLICE_ROWS : L.rows);
     }
-    if (!sp) return;
+    if (!sp || version != 4) return;
     // the same stage sequence mjx_env_encode_obs launches, executed by one lane
     static SpGlobal G;
     static std::vector<SpRow> rows; static std::vector<SpKey> keys; static std::vector<i32> node_row, slot_list;

@@ -7,7 +7,7 @@ import oracle_lib as O
 EXP_ROWS = [131] + [132 + 195 * k + 192 + j for k in range(3) for j in range(3)]  # exp(-0.2 * age) planes
 
 
-def check_obs_parity(make_env, fetch, n=8, max_cycles=400, seed0=777, min_rows=2000, sp=False, sp_tol=0.0):
+def check_obs_parity(make_env, fetch, n=8, max_cycles=400, seed0=777, min_rows=2000, sp=False, sp_tol=0.0, version=4):
     """make_env(nonces, keys) -> env ; fetch(env, first, prev_actions) -> (row_table, row_seat, masks, obs, actions)"""
     nonces = np.arange(seed0, seed0 + n, dtype=np.uint64)
     keys = np.full(n, 99, dtype=np.uint64)
@@ -27,8 +27,20 @@ def check_obs_parity(make_env, fetch, n=8, max_cycles=400, seed0=777, min_rows=2
             for r in range(len(rows_t)):
                 t, seat, kan = int(rows_t[r]), int(rows_s[r] & 3), bool(rows_s[r] & 4)
                 ps = O.PlayerState(0, _ptr=L.orc_game_state(games[t], seat), _own=False)
-                ref_obs, ref_mask = ps.encode_obs(4, kan, sp_mode=1 if sp else 0)
+                ref_obs, ref_mask = ps.encode_obs(version, kan, sp_mode=1 if sp else 0)
                 assert (ref_mask == masks[r]).all(), (cycle, t, seat, kan)
+                if version != 4:
+                    # legacy layouts: cells the reference sets to exactly 0 or 1 must match exactly, the exp()-derived
+                    # planes (RBF integer encodings, pond decay) to 1e-6
+                    assert obs[r].shape == ref_obs.shape, (obs[r].shape, ref_obs.shape)
+                    d = np.abs(obs[r] - ref_obs)
+                    binary = (ref_obs == 0) | (ref_obs == 1)
+                    bad = np.argwhere((d != 0) & binary)
+                    assert len(bad) == 0, (version, cycle, t, seat, kan, bad[:8], obs[r][tuple(bad[0])], ref_obs[tuple(bad[0])])
+                    assert d.max() <= 1e-6, (version, float(d.max()), np.unravel_index(np.argmax(d), d.shape))
+                    checked += 1
+                    chosen[(t, seat, kan)] = int(actions[r])
+                    continue
                 d = np.abs(obs[r][:889] - ref_obs[:889])
                 bad = np.argwhere(d[exact] != 0)
                 assert len(bad) == 0, (cycle, t, seat, kan, np.nonzero(exact)[0][bad[:8, 0]], bad[:8, 1],

@@ -108,6 +108,24 @@ def test_obs_encode_parity_emulated():
     check_obs_parity(make_env, fetch, n=6, min_rows=1500)
 
 
+@pytest.mark.parametrize("version", [1, 2, 3])
+def test_obs_encode_parity_emulated_legacy_versions(version):
+    """obs versions 1-3 (consts.rs:20-28; 938 / 942 / 934 rows) of the product encoder (host-emulated) vs the oracle."""
+    from obs_check import check_obs_parity
+
+    def make_env(nonces, keys):
+        return E.EmulEnv(nonces, keys, enable_quick_eval=False)
+
+    def fetch(env, first, prev):
+        env.step(None if first else prev)
+        rt, rs, m = env.rows()
+        obs = env.encode_obs(version=version)
+        acts = env.policy_test(1)
+        return rt, rs, m, obs, acts
+
+    check_obs_parity(make_env, fetch, n=4, min_rows=1000, version=version)
+
+
 def test_sp_block_parity_emulated():
     """obs v4 rows 889..1011 (single-player tables): product DP (host-emulated) vs the oracle's memoised recursion.
     Same f32 operation order on both sides, so the comparison is exact."""

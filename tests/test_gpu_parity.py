@@ -216,6 +216,29 @@ def test_obs_encode_matches_oracle(mjx):
     assert make_env.overflows == 0
 
 
+@pytest.mark.parametrize("version", [1, 2, 3])
+def test_obs_encode_legacy_versions_match_oracle(mjx, version):
+    """obs versions 1-3 on device vs the oracle (exact on 0/1 cells, 1e-6 on the exp()-derived planes)."""
+    import torch
+
+    from obs_check import check_obs_parity
+
+    def make_env(nonces, keys):
+        env = mjx.BatchEnv(nonces, keys, enable_quick_eval=False, obs_version=version)
+        env._actions = torch.zeros(env.row_cap, dtype=torch.int64, device=env.device)
+        return env
+
+    def fetch(env, first, prev):
+        env.step(None if first else env._actions)
+        obs = env.encode_obs()
+        env.policy_test(1, env._actions)
+        nr = env.num_rows()
+        return (env.row_table[:nr].cpu().numpy(), env.row_seat[:nr].cpu().numpy(), env.masks[:nr].cpu().numpy(),
+                obs[:nr].cpu().numpy(), env._actions[:nr].cpu().numpy())
+
+    check_obs_parity(make_env, fetch, n=6, min_rows=1500, version=version)
+
+
 def test_encode_obs_host_equals_device_encode(mjx):
     """mjx_env_encode_obs_host (D2H overlapped with the SP kernels) delivers exactly the device encoding."""
     import torch
