@@ -72,6 +72,10 @@ int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8
 int mjx_env_set_sp(mjx_env* env, int enable);
 int mjx_env_sp_overflows(mjx_env* env, void* stream, int* n);
 
+/* Size of the last step's single-player DP: out[0] = states, out[1] = edges, out[2..9] = states per level slot
+ * (D3 W3 D2 W2 D1 W1 D0 W0). Instrumentation for profiles/ and bench.py; blocking. */
+int mjx_env_sp_stats(mjx_env* env, void* stream, int* out10);
+
 /* Blocking read-backs (synchronise `stream` first). */
 int mjx_env_num_rows(mjx_env* env, void* stream, int* n_rows);          /* rows emitted by the last step */
 int mjx_env_num_live(mjx_env* env, void* stream, int* n_live);          /* tables still playing */

@@ -249,10 +249,17 @@ __global__ void __launch_bounds__(SP_WARPS * 32, KIND == 2 ? 3 : (KIND == 1 ? 4 
     const int n = min(G.slot_count[slot], G.slot_cap);
     const i32* list = G.slot_list + (size_t)slot * G.slot_cap;
     const int k = sp_slot_shanten(slot);
-    for (int i = gwarp; i < n; i += nwarps) {
-        if (KIND == 0) sp_eval_d(s, c, list[i]);
-        else if (KIND == 1) sp_eval_w<false>(s, c, list[i], k);
-        else sp_eval_w<true>(s, c, list[i], 0);
+    if (KIND == 0) {
+        for (int i = gwarp; i < n; i += nwarps) sp_eval_d(s, c, list[i]);
+    } else {
+        // two W-states per warp, one per half-warp (csrc/mjx_sp.cuh sp_eval_w2)
+        __shared__ SpEvalScratch s_es[SP_WARPS];
+        const int hw = lane >> 4;
+        for (int i = gwarp * 2; i < n; i += nwarps * 2) {
+            const int node = i + hw < n ? list[i + hw] : -1;
+            if (KIND == 1) sp_eval_w2<false>(s, s_es[warp], node, k);
+            else sp_eval_w2<true>(s, s_es[warp], node, 0);
+        }
     }
 }
 
@@ -511,6 +518,7 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
         G.hash_cap = hc;
         CU(cudaMalloc(&G.rows, cap * sizeof(SpRow)));
         CU(cudaMalloc(&G.keys, (size_t)G.node_cap * sizeof(SpKey)));
+        CU(cudaMalloc(&G.sigs, (size_t)G.node_cap * sizeof(SpSig)));
         CU(cudaMalloc(&G.node_row, (size_t)G.node_cap * sizeof(i32)));
         CU(cudaMalloc(&G.vals, (size_t)G.node_cap * 3 * SP_T_MAX * sizeof(float)));
         CU(cudaMalloc(&G.edge_begin, (size_t)G.node_cap * sizeof(u32)));
@@ -549,7 +557,7 @@ void mjx_env_destroy(mjx_env* env) {
     cudaFree(V.masks); cudaFree(V.scores); cudaFree(V.ranks); cudaFree(V.done); cudaFree(V.steps); cudaFree(V.err);
     cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard); cudaFree(env->d_compact);
     SpGlobal& G = env->sp;
-    cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
+    cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.sigs); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
     cudaFree(G.edge_child); cudaFree(G.edge_meta); cudaFree(G.edge_owner); cudaFree(G.leaf_scores); cudaFree(G.hash); cudaFree(G.slot_list); cudaFree(G.slot_count);
     cudaFree(G.counters);
     if (env->copy_stream) { cudaStreamDestroy(env->copy_stream); cudaEventDestroy(env->ev_rows); cudaEventDestroy(env->ev_sp); }
@@ -675,6 +683,16 @@ int mjx_env_sp_overflows(mjx_env* env, void* stream, int* n) {
     CU(cudaMemcpyAsync(cnt, env->sp.counters, sizeof cnt, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     *n = cnt[3] + (cnt[2] ? 1 : 0);
+    return MJX_OK;
+}
+
+int mjx_env_sp_stats(mjx_env* env, void* stream, int* out10) {
+    if (!env || !out10) return fail(MJX_ERR_ARG, "mjx_env_sp_stats: bad arguments");
+    int cnt[2] = {0, 0};
+    CU(cudaMemcpyAsync(cnt, env->sp.counters, sizeof cnt, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(out10 + 2, env->sp.slot_count, SP_SLOTS * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    out10[0] = cnt[0]; out10[1] = cnt[1];
     return MJX_OK;
 }
 

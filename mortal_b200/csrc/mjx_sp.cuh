@@ -57,6 +57,34 @@ MJX_D void sp_key_copy(SpKey* dst, const SpKey* src) {
     for (int i = 0; i < 9; i++) b[i] = a[i];
 }
 
+// What a state's expansion needs besides the key, carried from parent to child incrementally instead of being
+// recomputed from the 34 counts: the shanten signatures of the hand (mjx_algo.cuh HandSig) and a Zobrist hash of the key.
+struct alignas(8) SpSig {
+    u32 idx[4];
+    i8 kinds, pairs, kkinds, kpairs;
+    u32 hash;
+};
+static_assert(sizeof(SpSig) == 24, "SpSig layout");
+MJX_D HandSig sp_sig_hand(const SpSig& g) {
+    HandSig h;
+    for (int i = 0; i < 4; i++) h.idx[i] = g.idx[i];
+    h.kinds = g.kinds; h.pairs = g.pairs; h.kkinds = g.kkinds; h.kpairs = g.kpairs;
+    return h;
+}
+MJX_D SpSig sp_sig_make(const HandSig& h, u32 hash) {
+    SpSig g;
+    for (int i = 0; i < 4; i++) g.idx[i] = h.idx[i];
+    g.kinds = (i8)h.kinds; g.pairs = (i8)h.pairs; g.kkinds = (i8)h.kkinds; g.kpairs = (i8)h.kpairs;
+    g.hash = hash;
+    return g;
+}
+// Zobrist terms: kind 0 = tehai[t] == c, 1 = wall[t] == c, 2 = the akas byte; the key hash is their XOR
+MJX_D u32 sp_zob(int kind, int t, int c) {
+    u32 x = ((u32)kind << 9) | ((u32)t << 3) | (u32)c;
+    x = (x + 0x9E3779B9u) * 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+
 // per observation row: sp/calc.rs:36-62 parameters + what obs_repr.rs needs afterwards
 struct SpRow {
     u8 tehai_len_div3, is_menzen, prefer_riichi, calc_double_riichi, calc_haitei;
@@ -82,6 +110,7 @@ struct SpRow {
 struct SpGlobal {
     SpRow* rows;       // [row_cap]
     SpKey* keys;       // [node_cap]
+    SpSig* sigs;       // [node_cap]
     i32* node_row;     // [node_cap]
     float* vals;       // [node_cap][3][SP_T_MAX]
     u32* edge_begin;   // [node_cap]
@@ -125,6 +154,7 @@ struct SpWarpScratch {
     u8 score_ok[40];
     SpKey key;                   // the state being expanded, staged once per warp
     u8 ed_tile[40], ed_cnt[40];  // edge descriptors of the state being expanded
+    u8 cand[40];                 // candidate tiles of the state being expanded, compacted
     u8 df[34];
     u8 pad_[2];
     i32 ed_n, ed_begin;
@@ -143,12 +173,16 @@ struct SpCtx {
 #define SP_FOR_LANES(i, n) for (int i = s.lane; i < (n); i += 32)
 #endif
 
-MJX_D u32 sp_hash_key(int row, const SpKey& k) {
-    const u32* w = reinterpret_cast<const u32*>(&k);
-    u32 h = 2166136261u ^ ((u32)row * 0x9E3779B9u);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(SpKey) / 4); i++) { h ^= w[i]; h *= 16777619u; h ^= h >> 15; }
+MJX_D u32 sp_key_hash_full(const SpKey& k) {
+    u32 h = sp_zob(2, 0, k.akas);
+    for (int t = 0; t < 34; t++) h ^= sp_zob(0, t, k.tehai[t]) ^ sp_zob(1, t, k.wall[t]);
     return h;
+}
+// table slot hash of (row, key): the key's Zobrist hash mixed with the row
+MJX_D u32 sp_hash_key(int row, u32 key_hash) {
+    u32 x = key_hash ^ ((u32)row * 0x9E3779B9u);
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
 }
 
 // `a` lives in the global arena and may have been written by another SM during this launch: read it through
@@ -178,7 +212,7 @@ MJX_D int sp_ld_row(const i32* p) {
 MJX_D void sp_set_overflow(SpCtx& s) { s.G.counters[2] = 1; }
 
 // allocate a node in `slot`; executed by one lane. Returns -1 on overflow.
-MJX_DN int sp_new_node(SpCtx& s, int row, const SpKey& key, int slot) {
+MJX_DN int sp_new_node(SpCtx& s, int row, const SpKey& key, const SpSig& sig, int slot) {
 #ifdef MJX_HOST_EMUL
     int idx = s.G.counters[0]++;
     int pos = s.G.slot_count[slot]++;
@@ -188,6 +222,11 @@ MJX_DN int sp_new_node(SpCtx& s, int row, const SpKey& key, int slot) {
 #endif
     if (idx >= s.G.node_cap || pos >= s.G.slot_cap) { sp_set_overflow(s); return -1; }
     sp_key_copy(&s.G.keys[idx], &key);
+    {
+        const u64* a = reinterpret_cast<const u64*>(&sig);
+        u64* b = reinterpret_cast<u64*>(&s.G.sigs[idx]);
+        b[0] = a[0]; b[1] = a[1]; b[2] = a[2];
+    }
     s.G.node_row[idx] = row;
     s.G.n_edges[idx] = 0;
     s.G.edge_begin[idx] = 0;
@@ -198,9 +237,9 @@ MJX_DN int sp_new_node(SpCtx& s, int row, const SpKey& key, int slot) {
 // find-or-insert (row, key) in `slot`. May be called by several lanes of a warp at once (different keys).
 // Lock-free without spinning: the node is allocated and written first, then published with one CAS; if another
 // thread published the same state in the meantime its node wins and ours is simply never referenced.
-MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
+MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, const SpSig& sig, int slot) {
     const u32 mask = (u32)s.G.hash_cap - 1;
-    const u32 hv = sp_hash_key(row, key);
+    const u32 hv = sp_hash_key(row, sig.hash);
     const u32 tag = (hv >> 24) << 24;  // 8-bit tag kept beside the 24-bit index: mismatches never touch the key array
     u32 h = hv & mask;
     int mine = -1;
@@ -208,7 +247,7 @@ MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
 #ifdef MJX_HOST_EMUL
         u32 cur = s.G.hash[h];
         if (cur == 0) {
-            int idx = sp_new_node(s, row, key, slot);
+            int idx = sp_new_node(s, row, key, sig, slot);
             if (idx < 0) return -1;
             s.G.hash[h] = ((u32)idx + 1) | tag;
             return idx;
@@ -217,7 +256,7 @@ MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, int slot) {
         u32 cur = __ldcg(&s.G.hash[h]);
         if (cur == 0) {
             if (mine < 0) {
-                mine = sp_new_node(s, row, key, slot);
+                mine = sp_new_node(s, row, key, sig, slot);
                 if (mine < 0) return -1;
                 __threadfence();
             }
@@ -251,43 +290,68 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
 #else
     if (s.lane < 9) reinterpret_cast<u64*>(&ws.key)[s.lane] = reinterpret_cast<const u64*>(&s.G.keys[node])[s.lane];
 #endif
+    const SpSig sg = s.G.sigs[node];
     MJX_SYNCWARP();
     const SpKey& key = ws.key;
     const int len = s.G.rows[row].tehai_len_div3;
-    const HandSig base = hand_sig(key.tehai);
-    u64 eff, unused;
-    if (is_w) {
-        tile_eval2(c, (key.wall[32] | key.wall[33]) != 0, [&](int t) {
-            if (key.wall[t] == 0) return 0;
-            return shanten_all_sig(s.T, sig_variant(base, t, +1, key.tehai[t]), len) - k == -1 ? 1 : 0;
-        }, eff, unused);
-    } else {
-        tile_eval2(c, (key.tehai[32] | key.tehai[33]) != 0, [&](int t) {
-            if (key.tehai[t] == 0) return 0;
-            return shanten_all_sig(s.T, sig_variant(base, t, -1, key.tehai[t]), len) == k ? 1 : 0;
-        }, eff, unused);
+    const HandSig base = sp_sig_hand(sg);
+    // candidate tiles: still in the wall (W) / held (D); only those need a shanten evaluation
+    const u8* cnts = is_w ? key.wall : key.tehai;
+    const u64 cand = tile_mask(c, [&](int t) { return cnts[t] != 0; });
+    auto effective = [&](int t) {
+        if (is_w) return shanten_all_sig(s.T, sig_variant(base, t, +1, key.tehai[t]), len) - k == -1;
+        return shanten_all_sig(s.T, sig_variant(base, t, -1, key.tehai[t]), len) == k;
+    };
+    u64 eff = 0;
+#ifdef MJX_HOST_EMUL
+    for (int t = 0; t < 34; t++) if (((cand >> t) & 1) && effective(t)) eff |= 1ull << t;
+#else
+    {   // lane i evaluates the i-th candidate: one pass unless more than 32 kinds qualify
+        for (int t = s.lane; t < 34; t += 32)
+            if ((cand >> t) & 1) ws.cand[mjx_popcll(cand & ((1ull << t) - 1))] = (u8)t;
+        __syncwarp();
+        const int n_c = mjx_popcll(cand);
+        for (int i0 = 0; i0 < n_c; i0 += 32) {
+            const int i = i0 + s.lane;
+            const int t = i < n_c ? (int)ws.cand[i] : -1;
+            const bool ok = t >= 0 && effective(t);
+            const unsigned lo = (ok && t < 32) ? 1u << t : 0u, hi = (ok && t >= 32) ? 1u << (t - 32) : 0u;
+            eff |= (u64)__reduce_or_sync(0xffffffffu, lo) | ((u64)__reduce_or_sync(0xffffffffu, hi) << 32);
+        }
+    }
+#endif
+    // edge descriptors in tile order; an effective 5 whose aka is still in the wall splits in two
+    // (sp/state.rs:160-176); a discarded 5 is the aka only when it is the last 5 in hand (state.rs:127-132).
+    // Every effective tile writes its own descriptors at the offset its rank gives.
+    u64 split = 0;
+    if (is_w)
+        for (int s5 = 0; s5 < 3; s5++) {
+            const int t5 = 4 + 9 * s5;
+            if (((eff >> t5) & 1) && ((key.akas >> (3 + s5)) & 1) && key.wall[t5] >= 2) split |= 1ull << t5;
+        }
+    const int ne_all = mjx_popcll(eff) + mjx_popcll(split);
+    MJX_FOR_TILES(c, t) {
+        if (!((eff >> t) & 1)) continue;
+        const u64 below = (1ull << t) - 1;
+        const int off = mjx_popcll(eff & below) + mjx_popcll(split & below);
+        const int suit5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
+        if (is_w) {
+            const int count = key.wall[t];
+            if (suit5 >= 0 && ((key.akas >> (3 + suit5)) & 1)) {
+                int o = off;
+                if (count >= 2) { ws.ed_tile[o] = (u8)t; ws.ed_cnt[o] = (u8)(count - 1); o++; }
+                ws.ed_tile[o] = (u8)(T_5MR + suit5); ws.ed_cnt[o] = 1;
+            } else {
+                ws.ed_tile[off] = (u8)t; ws.ed_cnt[off] = (u8)count;
+            }
+        } else {
+            int tile = t;
+            if (suit5 >= 0 && ((key.akas >> suit5) & 1) && key.tehai[t] == 1) tile = T_5MR + suit5;
+            ws.ed_tile[off] = (u8)tile; ws.ed_cnt[off] = 0;
+        }
     }
     if (MJX_IS_L0(c)) {
-        // edge descriptors in tile order; an effective 5 whose aka is still in the wall splits in two
-        // (sp/state.rs:160-176); a discarded 5 is the aka only when it is the last 5 in hand (state.rs:127-132)
-        int ne = 0;
-        for (u64 rest = eff; rest; rest &= rest - 1) {
-            const int t = mjx_ffsll(rest) - 1;
-            const int suit5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
-            if (is_w) {
-                const int count = key.wall[t];
-                if (suit5 >= 0 && ((key.akas >> (3 + suit5)) & 1)) {
-                    if (count >= 2) { ws.ed_tile[ne] = (u8)t; ws.ed_cnt[ne] = (u8)(count - 1); ne++; }
-                    ws.ed_tile[ne] = (u8)(T_5MR + suit5); ws.ed_cnt[ne] = 1; ne++;
-                } else {
-                    ws.ed_tile[ne] = (u8)t; ws.ed_cnt[ne] = (u8)count; ne++;
-                }
-            } else {
-                int tile = t;
-                if (suit5 >= 0 && ((key.akas >> suit5) & 1) && key.tehai[t] == 1) tile = T_5MR + suit5;
-                ws.ed_tile[ne] = (u8)tile; ws.ed_cnt[ne] = 0; ne++;
-            }
-        }
+        int ne = ne_all;
 #ifdef MJX_HOST_EMUL
         int eb = s.G.counters[1]; s.G.counters[1] += ne;
 #else
@@ -299,7 +363,7 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
         s.G.n_edges[node] = (u8)ne;
     }
     MJX_SYNCWARP();
-    // one edge per lane: build the child state and intern it
+    // one edge per lane: build the child state (key, signatures, hash: all incremental) and intern it
     const int ne = ws.ed_n, eb = ws.ed_begin;
     SP_FOR_LANES(e, ne) {
         const int tile = ws.ed_tile[e], t = deaka(tile);
@@ -308,15 +372,21 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
         if (!leaf) {
             SpKey ck;
             sp_key_copy(&ck, &key);
+            const int c0 = key.tehai[t];
+            u32 h = sg.hash ^ sp_zob(0, t, c0);
             if (is_w) {
                 ck.tehai[t] += 1;
                 ck.wall[t] -= 1;
                 if (suit5 >= 0) ck.akas = (u8)((ck.akas | (1 << suit5)) & ~(1 << (3 + suit5)));
+                h ^= sp_zob(0, t, c0 + 1) ^ sp_zob(1, t, key.wall[t]) ^ sp_zob(1, t, key.wall[t] - 1);
             } else {
                 ck.tehai[t] -= 1;
                 if (suit5 >= 0) ck.akas = (u8)(ck.akas & ~(1 << suit5));
+                h ^= sp_zob(0, t, c0 - 1);
             }
-            int ci = sp_intern(s, row, ck, slot + 1);
+            if (ck.akas != key.akas) h ^= sp_zob(2, 0, key.akas) ^ sp_zob(2, 0, ck.akas);
+            const SpSig cs = sp_sig_make(sig_variant(base, t, is_w ? +1 : -1, c0), h);
+            int ci = sp_intern(s, row, ck, cs, slot + 1);
             child = ci < 0 ? SP_NO_CHILD : (u32)ci;
         }
         s.G.edge_child[eb + e] = child;
@@ -506,6 +576,113 @@ MJX_DN void sp_eval_w(SpCtx& s, const Ctx& c, int node, int k_rt) {
     MJX_SYNCWARP();
 }
 
+#ifndef MJX_HOST_EMUL
+// Device form of sp_eval_w: TWO states per warp, one per half-warp (turn i = sub-lane; a state has at most 17
+// turns, sub-lane 15 also carries turn 16). Every lane performs exactly the float operations sp_eval_w performs for
+// its turn, in the same order, so the values are bit-identical; the halves only share the instruction stream.
+struct SpEvalScratch {
+    float nts[2][SP_T_MAX], tpn[2][SP_T_MAX], cv[2][3][SP_T_MAX];
+    float scores[2][40][4];
+    u8 score_ok[2][40];
+};
+
+template <bool LEAF>
+MJX_DN void sp_eval_w2(SpCtx& s, SpEvalScratch& es, int node, int k_rt) {
+    const int k = LEAF ? 0 : k_rt;
+    const int hw = s.lane >> 4, l = s.lane & 15;
+    const bool live = node >= 0;
+    const SpRow* P = live ? &s.G.rows[s.G.node_row[node]] : nullptr;
+    const int T = live ? P->T : 0, n_left = live ? P->n_left : 0;
+    const int ne = live ? s.G.n_edges[node] : 0;
+    const u32 eb = live ? s.G.edge_begin[node] : 0;
+    float* nts = es.nts[hw];
+    float* tpn = es.tpn[hw];
+    int sum_required = 0;
+    for (int e = 0; e < ne; e++) sum_required += (s.G.edge_meta[eb + e] >> 6) & 7;
+    sum_required &= 0xFF;
+    for (int j = l; j < T; j += 16) {  // not_tsumo_prob_table[sum_required][j] (calc.rs:158-165)
+        float v = 0.f;
+        const int i0 = sum_required;
+        if (i0 <= n_left && i0 <= SP_MAX_TILES_LEFT) {
+            const int lim = min(T - 1, n_left - i0);
+            if (j <= lim) {
+                v = 1.f;
+                for (int q = 0; q < j; q++) v = SP_FDIV(SP_FMUL(v, (float)(n_left - i0 - q)), (float)(n_left - q));
+            }
+        }
+        nts[j] = v;
+    }
+    if (k == 0) {
+        const int le0 = (int)eb - s.G.counters[4];
+        for (int e = l; e < ne; e += 16) {
+            const bool ok = !(s.G.edge_meta[eb + e] & 0x8000) && le0 + e >= 0 && le0 + e < s.G.score_cap;
+            es.score_ok[hw][e] = ok ? 1 : 0;
+            if (ok) for (int q = 0; q < 4; q++) es.scores[hw][e][q] = s.G.leaf_scores[(size_t)(le0 + e) * 4 + q];
+        }
+    }
+    __syncwarp();
+    float a0[3] = {0.f, 0.f, 0.f}, a1[3] = {0.f, 0.f, 0.f};  // (tenpai, win, ev) of turn l and of turn 16
+    const bool assume_riichi = live && P->is_menzen && P->prefer_riichi;
+    const bool dbl = live && P->calc_double_riichi, haitei = live && P->calc_haitei;
+    const int ne_max = max(ne, __shfl_xor_sync(0xffffffffu, ne, 16));
+    for (int e = 0; e < ne_max; e++) {
+        bool skip = e >= ne;
+        int cnt = 0;
+        u32 child = SP_NO_CHILD;
+        if (!skip) {
+            cnt = (s.G.edge_meta[eb + e] >> 6) & 7;
+            if (k == 0 && !es.score_ok[hw][e]) skip = true;
+            child = s.G.edge_child[eb + e];
+            if (k > 0 && child == SP_NO_CHILD) skip = true;  // only after an overflow
+        }
+        __syncwarp();
+        if (!skip)
+            for (int j = l; j < T; j += 16) {
+                tpn[j] = SP_FMUL(SP_FDIV((float)cnt, (float)(n_left - j)), nts[j]);
+                if (k > 0) {
+                    es.cv[hw][0][j] = sp_vals(s, (int)child, 0)[j];
+                    es.cv[hw][1][j] = sp_vals(s, (int)child, 1)[j];
+                    es.cv[hw][2][j] = sp_vals(s, (int)child, 2)[j];
+                }
+            }
+        __syncwarp();
+        if (!skip) {
+            auto turn = [&](int i, float* a) {
+                float tenpai = a[0], win = a[1], ev = a[2];
+                const float m = nts[i];
+                if (m != 0.f) {
+                    for (int j = i; j < T; j++) {
+                        if (nts[j] == 0.f) break;
+                        const float prob = SP_FDIV(tpn[j], m);
+                        if (k == 0) {
+                            const int han_plus = (assume_riichi && dbl && i == 0) + (assume_riichi && j == i) + (haitei && j == T - 1);
+                            win = SP_FADD(win, prob);
+                            ev = SP_FADD(ev, SP_FMUL(prob, es.scores[hw][e][han_plus]));
+                        } else {
+                            if (k == 1) tenpai = SP_FADD(tenpai, prob);
+                            if (j < T - 1) {
+                                if (k > 1) tenpai = SP_FADD(tenpai, SP_FMUL(prob, es.cv[hw][0][j + 1]));
+                                win = SP_FADD(win, SP_FMUL(prob, es.cv[hw][1][j + 1]));
+                                ev = SP_FADD(ev, SP_FMUL(prob, es.cv[hw][2][j + 1]));
+                            }
+                        }
+                    }
+                }
+                a[0] = tenpai; a[1] = win; a[2] = ev;
+            };
+            if (l < T) turn(l, a0);
+            if (T > 16 && l == 15) turn(16, a1);
+        }
+    }
+    __syncwarp();
+    if (live) {
+        if (l < T) for (int q = 0; q < 3; q++) sp_vals(s, node, q)[l] = a0[q];
+        if (T > 16 && l == 15) for (int q = 0; q < 3; q++) sp_vals(s, node, q)[16] = a1[q];
+    }
+    __syncwarp();
+}
+#endif
+
 // calc.rs:563-637 discard_slow for one D-state (one warp, lane i = turn i)
 MJX_DN void sp_eval_d(SpCtx& s, const Ctx& c, int node) {
     const int T = s.G.rows[s.G.node_row[node]].T;
@@ -679,7 +856,7 @@ MJX_DN void sp_stage_init(SpCtx& s, const TableState* S, int row, int table, int
             sp_key_copy(&R.root_key, &root);
             if (R.has_values) {
                 const int slot = 2 * (3 - cur_shanten) + (R.can_discard ? 0 : 1);
-                R.root = sp_new_node(s, row, root, slot);
+                R.root = sp_new_node(s, row, root, sp_sig_make(hand_sig(root.tehai), sp_key_hash_full(root)), slot);
             }
         }
     }

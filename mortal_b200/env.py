@@ -123,6 +123,12 @@ class BatchEnv:
         _lib.check(self.L.mjx_env_sp_overflows(self._h, self._stream(), C.byref(n)), "mjx_env_sp_overflows")
         return n.value
 
+    def sp_stats(self):
+        """(states, edges, [states per level slot D3 W3 D2 W2 D1 W1 D0 W0]) of the last step's single-player DP"""
+        out = (C.c_int * 10)()
+        _lib.check(self.L.mjx_env_sp_stats(self._h, self._stream(), out), "mjx_env_sp_stats")
+        return out[0], out[1], list(out[2:10])
+
     def launch_count(self) -> int:
         """kernels launched for this env so far (host-side counter in libmjx)"""
         return int(self.L.mjx_env_launch_count(self._h))

@@ -217,7 +217,7 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
     static std::vector<SpRow> rows; static std::vector<SpKey> keys; static std::vector<i32> node_row, slot_list;
     static std::vector<float> vals; static std::vector<u32> edge_begin, edge_child, hash; static std::vector<u8> n_edges;
     static std::vector<u16> edge_meta; static i32 slot_count[SP_SLOTS], counters[8];
-    static std::vector<u32> edge_owner; static std::vector<float> leaf_scores;
+    static std::vector<u32> edge_owner; static std::vector<float> leaf_scores; static std::vector<SpSig> sigs;
     if (keys.empty()) {
         G.node_cap = 1 << 20; G.slot_cap = G.node_cap; G.edge_cap = G.node_cap * 6; G.hash_cap = 1 << 21; G.score_cap = G.edge_cap / 2;
         edge_owner.resize(G.edge_cap); leaf_scores.resize((size_t)G.score_cap * 4); G.edge_owner = edge_owner.data(); G.leaf_scores = leaf_scores.data();
@@ -225,6 +225,7 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
         vals.resize((size_t)G.node_cap * 3 * SP_T_MAX); edge_begin.resize(G.node_cap); n_edges.resize(G.node_cap);
         edge_child.resize(G.edge_cap); edge_meta.resize(G.edge_cap); hash.resize(G.hash_cap);
         slot_list.resize((size_t)SP_SLOTS * G.slot_cap);
+        sigs.resize(G.node_cap); G.sigs = sigs.data();
         G.rows = rows.data(); G.keys = keys.data(); G.node_row = node_row.data(); G.vals = vals.data();
         G.edge_begin = edge_begin.data(); G.n_edges = n_edges.data(); G.edge_child = edge_child.data();
         G.edge_meta = edge_meta.data(); G.hash = hash.data(); G.slot_list = slot_list.data(); G.slot_count = slot_count;

@@ -37,4 +37,4 @@ for i in range(args.cycles):
 t1.record()
 torch.cuda.synchronize()
 print(f"{args.cycles - 3} cycles, {t0.elapsed_time(t1) / max(args.cycles - 3, 1):.3f} ms/cycle, rows last {env.num_rows()}, "
-      f"sp_overflows {env.sp_overflows()}")
+      f"sp_overflows {env.sp_overflows()}, sp states/edges/slots {env.sp_stats() if not args.no_sp else None}")
