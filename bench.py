@@ -8,7 +8,7 @@ observation per decision row, run the policy. One table-step = that iteration fo
 Default arm (this repo): 4096 tables per GPU (BASELINE configs[1]), random-init Mortal brain
 (192 channels x 40 blocks, bf16 autocast, greedy), everything resident in HBM. JSON also carries
   env_only      the same loop with the counter-based test policy instead of the network
-  roofline      achieved HBM GB/s of the dominant env kernel (k_encode_obs_v4) from CUDA events
+  roofline      achieved HBM GB/s of the HBM-bound env kernels (k_encode_features + k_encode_store) from CUDA events
   e2e           the loop through the C ABI with HOST buffers (obs D2H, actions H2D every step)
   cpu_baseline  the CPU oracle on this box's host cores, bounded sample (rank 0, N=1 only)
 `--impl reference` times libriichi's own CPU path restated by the oracle (oracle/, all host threads).
@@ -249,6 +249,7 @@ def run_ours(args):
     ea = fresh_env()
     b = loop(ea, test_policy, W, K)
     sp_overflows = ea[0].sp_overflows()
+    sp_states, sp_edges, _ = ea[0].sp_stats()  # size of the last step's single-player DP
     ea[0].close()
     # -------- loop B2: the HBM-bound encode kernel alone (single-player block off), timed with CUDA events
     ea = fresh_env()
@@ -271,18 +272,30 @@ def run_ours(args):
     h_masks = torch.empty((env.row_cap, 46), dtype=torch.bool, pin_memory=True)
     h_actions = torch.zeros(env.row_cap, dtype=torch.int64).pin_memory()
     h_actions.copy_(d_actions)
-    gen = torch.Generator().manual_seed(1)
-    e2e_h2d = e2e_d2h = 0
+    # host policy standing in for engine.react_batch on HOST tensors: greedy on the observation it was handed
+    # (agari > riichi > shanten-lowering discard > shanten-keeping discard > pass > calls), so that the hands keep
+    # developing the way they do under a real policy and the single-player block stays as expensive as in self-play
+    prio = torch.zeros(46)
+    prio[43], prio[37], prio[44], prio[45] = 100.0, 50.0, 10.0, 0.5
+    prio[38:43] = 0.25
+    prio += torch.arange(46, dtype=torch.float32) * 1e-4
+    aka_base = torch.tensor([4, 13, 22])
+
+    def host_policy(nr):
+        m = h_masks[:nr]
+        score = prio.repeat(nr, 1)
+        disc = 2.0 * h_obs[:nr, 876, :] + h_obs[:nr, 875, :] + 1.0  # v4 rows 875/876: keep / next shanten discards
+        score[:, :34] += disc
+        score[:, 34:37] += disc[:, aka_base] - 0.5
+        score[~m] = -1.0
+        return score.argmax(-1)
 
     def e2e_cycle():
         d_actions.copy_(h_actions, non_blocking=True)  # H2D: the step's inputs
         env.step(d_actions)
         nr = env.encode_obs_host(h_obs, h_masks)  # D2H: the step's result, as react_batch receives it (blocking)
         if nr:
-            # host policy: random legal action (stands in for engine.react_batch on host tensors)
-            q = torch.rand((nr, 46), generator=gen)
-            q[~h_masks[:nr]] = -1.0
-            h_actions[:nr] = q.argmax(-1)
+            h_actions[:nr] = host_policy(nr)
         return nr
 
     for _ in range(W):
@@ -367,14 +380,22 @@ def run_ours(args):
                          "policy": "counter-based test policy kernel, no host sync",
                          "without_sp_block": {"value": b2["table_steps"] / (b2["ms"] * 1e-3), "ms_per_step": b2["ms"] / K}},
             "roofline": {"kernel": "k_encode_features + k_encode_store (the whole v4 encode without the SP block)", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs if peak_gbs else None, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak_gbs if peak_gbs else None,
+                         # dram__bytes_read + dram__bytes_write of the two kernels, one `ncu --set full` capture each at this
+                         # workload (profiles/r01_ncu_k_encode_{features,store}.md): 9.8 MB + 541.8 MB per launch pair
+                         "traffic": 551.6e6, "peak_source": peak_src,
                          "bytes_per_launch": bytes_per_launch, "ms_per_launch": enc_ms_per_launch,
                          "rows_per_launch": rows_per_launch},
+            # the single-player block is a latency-bound graph DP (hash interning + value propagation over an arena far larger
+            # than L2); it has no meaningful HBM roofline, so it is reported as states/s. ms = env_only minus the same loop
+            # with the block switched off.
+            "sp_block": {"ms_per_step": (b["ms"] - b2["ms"]) / K, "states_last_step": sp_states, "edges_last_step": sp_edges,
+                         "states_per_s": sp_states / max((b["ms"] - b2["ms"]) / K * 1e-3, 1e-9), "share_of_env_step": 1.0 - b2["ms"] / b["ms"]},
             "e2e": {"value": c_units / (c_ms * 1e-3), "unit": "table-steps/s",
                     "h2d_bytes_per_step": 8 * N_TABLES * 3,
                     "d2h_bytes_per_step": int(e2e_rows / K * (OBS_BYTES + MASK_BYTES)),
                     "path": "mjx_env_encode_obs_host with pinned host buffers: actions H2D, obs+masks D2H every step "
-                            "(rows 0-888 drain while the SP kernels run), host-side policy",
+                            "(rows 0-888 drain while the SP kernels run), greedy host-side policy reading the host obs",
                     "plain_d2h_copy_gbs": pcie_gbs},
             "gpu_launches": a["launches"], "clocks": clocks,
             "collective": {"all_gather_us": gather_us, "bytes_per_table": 20},
