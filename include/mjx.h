@@ -81,6 +81,13 @@ int mjx_env_num_rows(mjx_env* env, void* stream, int* n_rows);          /* rows 
 int mjx_env_num_live(mjx_env* env, void* stream, int* n_live);          /* tables still playing */
 int mjx_env_total_steps(mjx_env* env, void* stream, int64_t* steps);    /* game.rs:304 `actions` counter */
 
+/* arena/result.rs:19-51 GameResult.game_log: record every table's mjai events on device (compact 64-bit words, layout in
+ * csrc/mjx_step.cuh `log_word`; mortal_b200/mjai_log.py turns them into the reference's JSON lines). Call
+ * mjx_env_enable_log before the first step; `words_per_table` bounds one hanchan (a kyoku is ~170 words; 8192 is ample).
+ * mjx_env_read_log copies [n_tables, words_per_table] words and the per-table counts to host (count > capacity = overflow). */
+int mjx_env_enable_log(mjx_env* env, int words_per_table);
+int mjx_env_read_log(mjx_env* env, void* stream, uint64_t* words_host, int32_t* len_host);
+
 /* Number of kernels this library has launched for env so far (host-side counter; bench.py's gpu_launches). */
 long long mjx_env_launch_count(mjx_env* env);
 

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(EnvView V, Tables T) {
     c.T = T;
     c.lane = lane;
     c.df = s_scratch[warp].dora_factor;
+    if (V.log) { c.log = V.log + (size_t)table * V.log_cap; c.log_n = V.log_len + table; c.log_cap = V.log_cap; }
     const bool live = step_table(c, V, table);
     __syncwarp();
     uint4* gdst = reinterpret_cast<uint4*>(g);
@@ -555,7 +556,7 @@ void mjx_env_destroy(mjx_env* env) {
     EnvView& V = env->V;
     cudaFree(V.tables); cudaFree(V.n_rows); cudaFree(V.row_table); cudaFree(V.row_seat); cudaFree(V.row_step);
     cudaFree(V.masks); cudaFree(V.scores); cudaFree(V.ranks); cudaFree(V.done); cudaFree(V.steps); cudaFree(V.err);
-    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard); cudaFree(env->d_compact);
+    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard); cudaFree(env->d_compact); cudaFree(env->V.log); cudaFree(env->V.log_len);
     SpGlobal& G = env->sp;
     cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.sigs); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
     cudaFree(G.edge_child); cudaFree(G.edge_meta); cudaFree(G.edge_owner); cudaFree(G.leaf_scores); cudaFree(G.hash); cudaFree(G.slot_list); cudaFree(G.slot_count);
@@ -666,6 +667,27 @@ int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8
                              cudaMemcpyDeviceToHost, env->copy_stream));
     }
     CU(cudaStreamSynchronize(env->copy_stream));
+    return MJX_OK;
+}
+
+int mjx_env_enable_log(mjx_env* env, int words_per_table) {
+    if (!env || words_per_table <= 0) return fail(MJX_ERR_ARG, "mjx_env_enable_log: bad arguments");
+    if (!env->first) return fail(MJX_ERR_STATE, "mjx_env_enable_log: must be called before the first mjx_env_step");
+    if (env->V.log) return MJX_OK;
+    CU(cudaMalloc(&env->V.log, (size_t)env->n_tables * (size_t)words_per_table * sizeof(u64)));
+    CU(cudaMalloc(&env->V.log_len, (size_t)env->n_tables * sizeof(i32)));
+    CU(cudaMemset(env->V.log_len, 0, (size_t)env->n_tables * sizeof(i32)));
+    env->V.log_cap = words_per_table;
+    return MJX_OK;
+}
+
+int mjx_env_read_log(mjx_env* env, void* stream, uint64_t* words_host, int32_t* len_host) {
+    if (!env || !words_host || !len_host) return fail(MJX_ERR_ARG, "mjx_env_read_log: bad arguments");
+    if (!env->V.log) return fail(MJX_ERR_STATE, "mjx_env_read_log: mjx_env_enable_log was not called");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(len_host, env->V.log_len, (size_t)env->n_tables * sizeof(i32), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(words_host, env->V.log, (size_t)env->n_tables * (size_t)env->V.log_cap * sizeof(u64), cudaMemcpyDeviceToHost));
     return MJX_OK;
 }
 

@@ -43,7 +43,42 @@ struct Ctx {
     Tables T;
     int lane;
     const u8* df;  // dora_factor[34] of the current record (k_step: W->dora_factor; encoder: its own copy)
+    // optional mjai event log of this table (arena/result.rs GameResult.game_log); null = not recorded
+    u64* log = nullptr;
+    i32* log_n = nullptr;
+    int log_cap = 0;
 };
+
+// ---------------------------------------------------------------- event log (mjai/event.rs:20-120, compact form)
+// One 64-bit word per event: type | actor << 8 | target << 10 | pai << 12 | tsumogiri << 20 | aux << 21 |
+// consumed[0..3] << 24.. | extra << 56. start_kyoku is followed by 2 words of scores and 7 words of haipai
+// (4 x 13 tile bytes); hora / ryukyoku by 2 words of deltas. Decoded by mortal_b200/mjai_log.py.
+enum : u8 { LOG_START_KYOKU = 1, LOG_TSUMO, LOG_DAHAI, LOG_CHI, LOG_PON, LOG_DAIMINKAN, LOG_KAKAN, LOG_ANKAN, LOG_DORA,
+            LOG_REACH, LOG_REACH_ACCEPTED, LOG_HORA, LOG_RYUKYOKU, LOG_END_KYOKU };
+
+MJX_D u64 log_word(int type, int actor, int target, int pai, int tsumogiri, int aux, int c0, int c1, int c2, int c3, int extra) {
+    return (u64)(u8)type | ((u64)(actor & 3) << 8) | ((u64)(target & 3) << 10) | ((u64)(u8)pai << 12) | ((u64)(tsumogiri & 1) << 20) |
+           ((u64)(aux & 7) << 21) | ((u64)(u8)c0 << 24) | ((u64)(u8)c1 << 32) | ((u64)(u8)c2 << 40) | ((u64)(u8)c3 << 48) |
+           ((u64)(u8)extra << 56);
+}
+// executed by ONE lane; a full log keeps counting so that the host can see the overflow
+MJX_D void log_push(const Ctx& c, u64 w) {
+    if (!c.log) return;
+    const int n = *c.log_n;
+    if (n < c.log_cap) c.log[n] = w;
+    *c.log_n = n + 1;
+}
+MJX_D void log_push_i32x4(const Ctx& c, const i32* v) {
+    log_push(c, (u64)(u32)v[0] | ((u64)(u32)v[1] << 32));
+    log_push(c, (u64)(u32)v[2] | ((u64)(u32)v[3] << 32));
+}
+MJX_D void log_reaction(const Ctx& c, int type, const Reaction& r) {
+    log_push(c, log_word(type, r.actor, r.target, r.pai, r.tsumogiri, 0, r.consumed[0], r.consumed[1], r.consumed[2], r.consumed[3], 0));
+}
+// board.rs:502-509
+#define MJX_ABORTIVE_RYUKYOKU(c) MJX_L0((c).S->bflags |= BF_HAS_ABORTIVE; { const i32 z_[4] = {0, 0, 0, 0}; \
+    log_push(c, log_word(LOG_RYUKYOKU, 0, 0, T_UNK, 0, 0, 0, 0, 0, 0, 0)); log_push_i32x4(c, z_); })
+
 
 MJX_D void set_err(Ctx& c, i32 e) {
     if (MJX_IS_L0(c) && c.S->err == 0) c.S->err = e;
@@ -239,7 +274,8 @@ MJX_D void ev_dora(Ctx& c) {
     if (S->n_dora >= 5) { set_err(c, ERR_FIFTH_KAN); return; }
     // ReachAccepted / Dora / Hora are "in-game announces" but the arena always resets cans (update.rs:25)
     ev_prologue(c, -1);
-    MJX_L0(public_witness(S, S->wall[60 - S->n_dora]); S->n_dora += 1);
+    MJX_L0(log_push(c, log_word(LOG_DORA, 0, 0, S->wall[60 - S->n_dora], 0, 0, 0, 0, 0, 0, 0));
+           public_witness(S, S->wall[60 - S->n_dora]); S->n_dora += 1);
     recompute_dora_factor(c);
 }
 
@@ -284,6 +320,15 @@ MJX_DN void ev_start_kyoku(Ctx& c) {
     }
     MJX_SYNCWARP();
     MJX_L0(public_witness(S, S->wall[60]); S->n_dora = 1);
+    if (MJX_IS_L0(c) && c.log) {
+        log_push(c, log_word(LOG_START_KYOKU, 0, 0, S->wall[60], 0, 0, S->kyoku, S->honba, S->kyotaku, S->oya, 0));
+        log_push_i32x4(c, S->scores);
+        for (int w = 0; w < 7; w++) {
+            u64 v = 0;
+            for (int b = 0; b < 8; b++) { const int i = w * 8 + b; if (i < 52) v |= (u64)S->wall[i] << (8 * b); }
+            log_push(c, v);
+        }
+    }
     recompute_dora_factor(c);
     for (int s = 0; s < 4; s++) {
         update_shanten(c, s);
@@ -609,7 +654,8 @@ MJX_D void check_riichi_accepted(Ctx& c) {
     if (S->riichi_to_be_accepted < 0) return;
     const int actor = S->riichi_to_be_accepted;
     ev_prologue(c, actor);
-    MJX_L0(S->riichi_to_be_accepted = -1;
+    MJX_L0(log_push(c, log_word(LOG_REACH_ACCEPTED, actor, 0, T_UNK, 0, 0, 0, 0, 0, 0, 0));
+           S->riichi_to_be_accepted = -1;
            S->riichi_accepted |= (u8)(1 << actor);
            S->priv[actor].flags |= PF_AT_IPPATSU;
            S->scores[actor] -= 1000;
@@ -756,6 +802,17 @@ MJX_DN bool rule_based_agari(const Ctx& c, int p) {
     return rank_of(ex) < 3;
 }
 
+// Hora event of one winner (board.rs:421-431, 456-468): ura markers only for an accepted riichi
+MJX_D void log_hora(const Ctx& c, int actor, int target, const i32* deltas, int n_ura) {
+    if (!MJX_IS_L0(c) || !c.log) return;
+    const TableState* S = c.S;
+    const int nu = ((S->riichi_accepted >> actor) & 1) ? n_ura : 0;
+    u8 u[5] = {T_UNK, T_UNK, T_UNK, T_UNK, T_UNK};
+    for (int j = 0; j < nu; j++) u[j] = S->wall[61 + j];
+    log_push(c, log_word(LOG_HORA, actor, target, T_UNK, 0, nu, u[0], u[1], u[2], u[3], u[4]));
+    log_push_i32x4(c, deltas);
+}
+
 // board.rs:366-471
 MJX_DN void handle_hora(Ctx& c, int single_actor, int single_target) {
     TableState* S = c.S;
@@ -785,6 +842,7 @@ MJX_DN void handle_hora(Ctx& c, int single_actor, int single_target) {
             kyotaku_point = 0;
             honba_left = 0;
             for (int j = 0; j < 4; j++) deltas_total[j] += d[j];
+            log_hora(c, actor, single_target, d, n_ura);
         }
     } else {
         renchan = single_actor == S->oya;
@@ -801,6 +859,7 @@ MJX_DN void handle_hora(Ctx& c, int single_actor, int single_target) {
         }
         d[single_actor] = tsumo_total(p, single_actor == S->oya) + kyotaku_point + honba_left * 300;
         for (int j = 0; j < 4; j++) deltas_total[j] += d[j];
+        log_hora(c, single_actor, single_target, d, n_ura);
     }
     // NOTE board.rs:387: can_renchan is OR-ed for every Hora reaction, including ron reactions
     if (is_ron)
@@ -835,7 +894,8 @@ MJX_DN void exhaustive_ryukyoku(Ctx& c) {
             for (int j = 0; j < 4; j++) deltas[j] += S->priv[j].shanten == 0 ? plus : minus;
     }
     MJX_L0(if (renchan) S->bflags |= BF_CAN_RENCHAN; else S->bflags &= ~BF_CAN_RENCHAN;
-           for (int j = 0; j < 4; j++) S->kyoku_deltas[j] += deltas[j]);
+           for (int j = 0; j < 4; j++) S->kyoku_deltas[j] += deltas[j];
+           log_push(c, log_word(LOG_RYUKYOKU, 0, 0, T_UNK, 0, 0, 0, 0, 0, 0, 0)); log_push_i32x4(c, deltas));
 }
 
 // ---------------------------------------------------------------- board step (board.rs:511-678)
@@ -846,10 +906,11 @@ MJX_DN bool board_step(Ctx& c) {
         // haipai: StartKyoku + oya's first draw (board.rs:206-239)
         ev_start_kyoku(c);
         int tile = S->wall[135];
+        MJX_L0(log_push(c, log_word(LOG_TSUMO, S->oya, 0, tile, 0, 0, 0, 0, 0, 0, 0)));
         ev_tsumo(c, S->oya, tile);
         return false;
     }
-    if (S->accepted_riichis == 4) { MJX_L0(S->bflags |= BF_HAS_ABORTIVE); return true; }
+    if (S->accepted_riichis == 4) { MJX_ABORTIVE_RYUKYOKU(c); return true; }
 
     // pick the winning reaction: Hora 0 < Daiminkan/Pon 1 < other 2 < None 3, lowest seat on ties
     int best = 0, best_p = 4;
@@ -861,7 +922,7 @@ MJX_DN bool board_step(Ctx& c) {
     const Reaction ev = c.W->react[best];
     MJX_SYNCWARP();
 
-    if ((S->bflags & BF_CHECK_FOUR_KAN) && ev.type != R_HORA) { MJX_L0(S->bflags |= BF_HAS_ABORTIVE); return true; }
+    if ((S->bflags & BF_CHECK_FOUR_KAN) && ev.type != R_HORA) { MJX_ABORTIVE_RYUKYOKU(c); return true; }
 
     // board.rs:296-312
     if (MJX_IS_L0(c)) {
@@ -892,11 +953,13 @@ MJX_DN bool board_step(Ctx& c) {
                 MJX_L0(S->bflags &= ~BF_NEW_DORA_AT_TSUMO);
                 ev_dora(c);
             }
+            MJX_L0(log_push(c, log_word(LOG_TSUMO, S->tsumo_actor, 0, tile, 0, 0, 0, 0, 0, 0, 0)));
             ev_tsumo(c, S->tsumo_actor, tile);
             break;
         }
         case R_DAHAI: {
             if (S->bflags & BF_NEW_DORA_AT_DISCARD) { MJX_L0(S->bflags &= ~BF_NEW_DORA_AT_DISCARD); ev_dora(c); }
+            MJX_L0(log_reaction(c, LOG_DAHAI, ev));
             ev_dahai(c, ev.actor, ev.pai, ev.tsumogiri != 0);
             MJX_L0(S->tsumo_actor = (u8)((ev.actor + 1) & 3));
             // four-wind (board.rs:314-340, 597-600)
@@ -911,7 +974,7 @@ MJX_DN bool board_step(Ctx& c) {
                     if (S->four_wind_tile == pai) abort_now = true;
                     else { MJX_L0(S->bflags &= ~BF_CAN_FOUR_WIND); }
                 } else { set_err(c, ERR_FOUR_WIND_STATE); return true; }
-                if (abort_now) { MJX_L0(S->bflags |= BF_HAS_ABORTIVE); return true; }
+                if (abort_now) { MJX_ABORTIVE_RYUKYOKU(c); return true; }
             }
             if (S->kans == 4) {
                 bool all_lt4 = true;
@@ -922,14 +985,17 @@ MJX_DN bool board_step(Ctx& c) {
         }
         case R_CHI:
             check_riichi_accepted(c);
+            MJX_L0(log_reaction(c, LOG_CHI, ev));
             ev_chi(c, ev);
             break;
         case R_PON:
             check_riichi_accepted(c);
+            MJX_L0(log_reaction(c, LOG_PON, ev));
             ev_pon(c, ev);
             break;
         case R_ANKAN:
             if (S->bflags & BF_NEW_DORA_AT_DISCARD) { MJX_L0(S->bflags &= ~BF_NEW_DORA_AT_DISCARD); ev_dora(c); }
+            MJX_L0(log_reaction(c, LOG_ANKAN, ev));
             ev_ankan(c, ev);
             ev_dora(c);
             MJX_L0(S->tsumo_actor = ev.actor; S->bflags |= BF_DEAL_FROM_RINSHAN; S->kans += 1);
@@ -938,10 +1004,12 @@ MJX_DN bool board_step(Ctx& c) {
         case R_KAKAN:
             if (S->bflags & BF_NEW_DORA_AT_DISCARD) { MJX_L0(S->bflags |= BF_NEW_DORA_AT_TSUMO); }
             check_riichi_accepted(c);
+            MJX_L0(log_reaction(c, ev.type == R_DAIMINKAN ? LOG_DAIMINKAN : LOG_KAKAN, ev));
             if (ev.type == R_DAIMINKAN) ev_daiminkan(c, ev); else ev_kakan(c, ev);
             MJX_L0(S->bflags |= BF_NEW_DORA_AT_DISCARD | BF_DEAL_FROM_RINSHAN; S->tsumo_actor = ev.actor; S->kans += 1);
             break;
         case R_REACH:
+            MJX_L0(log_push(c, log_word(LOG_REACH, ev.actor, 0, T_UNK, 0, 0, 0, 0, 0, 0, 0)));
             ev_reach(c, ev.actor);
             MJX_L0(S->riichi_to_be_accepted = (i8)ev.actor);
             break;
@@ -949,7 +1017,7 @@ MJX_DN bool board_step(Ctx& c) {
             handle_hora(c, ev.actor, ev.target);
             return true;
         case R_RYUKYOKU:
-            MJX_L0(S->bflags |= BF_HAS_ABORTIVE);
+            MJX_ABORTIVE_RYUKYOKU(c);
             return true;
         default:
             set_err(c, ERR_INTERNAL);
@@ -1030,6 +1098,7 @@ MJX_DN void game_poll(Ctx& c) {
         }
         clear_reactions(c);
         if (S->err != 0) { MJX_L0(S->gflags |= GF_ENDED); return; }
+        MJX_L0(log_push(c, log_word(LOG_END_KYOKU, 0, 0, T_UNK, 0, 0, 0, 0, 0, 0, 0)));  // board.rs:150-152
         // kyoku end bookkeeping (board.rs:150-157, game.rs:114-174)
         const bool abortive = (S->bflags & BF_HAS_ABORTIVE) != 0;
         const bool can_renchan = abortive || (S->bflags & BF_CAN_RENCHAN);
@@ -1210,6 +1279,9 @@ struct EnvView {
     i32* err;           // [n_tables]
     unsigned long long* counters;  // [0] live tables after this step, [1] total table-steps so far
     i32 enable_quick_eval;
+    u64* log;           // [n_tables, log_cap] mjai event words (see log_word) or null
+    i32* log_len;       // [n_tables] words written (may exceed log_cap: overflow)
+    i32 log_cap;
 };
 
 MJX_D int alloc_rows(Ctx& c, EnvView& V, int n) {

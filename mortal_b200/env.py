@@ -129,6 +129,20 @@ class BatchEnv:
         _lib.check(self.L.mjx_env_sp_stats(self._h, self._stream(), out), "mjx_env_sp_stats")
         return out[0], out[1], list(out[2:10])
 
+    def enable_log(self, words_per_table: int = 8192) -> None:
+        """Record every table's mjai events on device (arena/result.rs GameResult.game_log); call before the first step."""
+        _lib.check(self.L.mjx_env_enable_log(self._h, int(words_per_table)), "mjx_env_enable_log")
+        self._log_cap = int(words_per_table)
+
+    def read_log(self):
+        """-> (words uint64 [n_tables, cap], lengths int32 [n_tables]); decode with mortal_b200.mjai_log"""
+        words = np.zeros((self.n_tables, self._log_cap), dtype=np.uint64)
+        lens = np.zeros(self.n_tables, dtype=np.int32)
+        _lib.check(self.L.mjx_env_read_log(self._h, self._stream(), words.ctypes.data, lens.ctypes.data), "mjx_env_read_log")
+        if (lens > self._log_cap).any():
+            raise RuntimeError(f"event log overflow: {int(lens.max())} words > capacity {self._log_cap}")
+        return words, lens
+
     def launch_count(self) -> int:
         """kernels launched for this env so far (host-side counter in libmjx)"""
         return int(self.L.mjx_env_launch_count(self._h))

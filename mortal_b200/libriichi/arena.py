@@ -31,8 +31,7 @@ class _Arena:
         self.last_stats = None
         self.record_decisions = False  # test hook: keep (table, step, seat, kan_select, action) of every row
         self.last_decisions = None
-        if log_dir is not None:
-            raise NotImplementedError("mjai log emission (SURVEY.md §8f N1) is not built in this round")
+        self.log_dir = log_dir  # arena/one_vs_three.rs:26-34: gz mjai logs are written here when set
 
     def _challenger_seats(self, game_in_seed: int):
         raise NotImplementedError
@@ -64,6 +63,8 @@ class _Arena:
         for g in range(per):
             for s in self._challenger_seats(g):
                 is_challenger[g, s] = True
+        if self.log_dir is not None:
+            env.enable_log()
         actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
         guards = [bool(getattr(a, "enable_rule_based_agari_guard", False)) for a in agents]
         q_all = None
@@ -102,6 +103,15 @@ class _Arena:
                                                  actions[:nr]], dim=1).cpu())
             cycles += 1
         res = env.results()
+        if self.log_dir is not None:  # one_vs_three.rs:195-225: one {seed}_{key}_{split}.json.gz per game
+            from .. import mjai_log
+
+            words, lens = env.read_log()
+            ic = is_challenger.cpu().numpy()
+            agent_names = [str(getattr(a, "name", "NoName")) for a in agents]
+            names = [[agent_names[0] if ic[g % per, seat] else agent_names[1] for seat in range(4)] for g in range(n)]
+            seeds = [(int(nonces[g]), int(keys[g])) for g in range(n)]
+            self.last_log_paths = mjai_log.write_logs(self.log_dir, words, lens, seeds, names, "abcd"[:per])
         self.last_stats = dict(cycles=cycles, table_steps=int(res["steps"].sum()))
         self.last_results = res
         if self.record_decisions:

@@ -42,6 +42,8 @@ def lib():
         L.emul_env_encode_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.emul_env_encode_obs_v.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.emul_sp_overflows.restype = C.c_long
+        L.emul_env_enable_log.argtypes = [C.c_void_p, C.c_int]
+        L.emul_env_read_log.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_env_results.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         if L.emul_init(DATA_DIR.encode()) != 0:
             raise RuntimeError(L.emul_last_error().decode())
@@ -108,6 +110,17 @@ class EmulEnv:
         a = np.full(self.row_cap, 45, dtype=np.int64)
         self.L.emul_env_policy_test(self._h, kind, a.ctypes.data)
         return a
+
+    def enable_log(self, cap=8192):
+        self._log_cap = cap
+        self.L.emul_env_enable_log(self._h, cap)
+
+    def read_log(self):
+        words = np.zeros((self.n_tables, self._log_cap), dtype=np.uint64)
+        lens = np.zeros(self.n_tables, dtype=np.int32)
+        self.L.emul_env_read_log(self._h, words.ctypes.data, lens.ctypes.data)
+        assert (lens <= self._log_cap).all()
+        return words, lens
 
     def encode_obs(self, sp=False, version=4):
         rows = {1: 938, 2: 942, 3: 934, 4: 1012}[version]

@@ -70,6 +70,7 @@ int emul_run(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_ki
     V.steps = steps; V.err = errs; V.counters = counters; V.enable_quick_eval = quick_eval;
     std::vector<float> qv((size_t)cap * ACTION_SPACE, 0.f);
     std::vector<u8> guard((size_t)n * 4, 1);
+    V.log = nullptr; V.log_len = nullptr; V.log_cap = 0;
     V.q_values = agari_guard ? qv.data() : nullptr;
     V.agari_guard = agari_guard ? guard.data() : nullptr;
     for (int t = 0; t < n; t++) { steps[t] = 0; errs[t] = 0; }
@@ -117,6 +118,7 @@ struct EmulEnv {
     unsigned long long counters[2] = {0, 0};
     EnvView V;
     bool first = true;
+    std::vector<u64> log; std::vector<i32> log_len; int log_cap = 0;
 };
 
 void* emul_env_create(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int quick_eval) {
@@ -142,6 +144,7 @@ void* emul_env_create(int n, const uint64_t* nonces, const uint64_t* keys, int s
     V.done = E->done.data(); V.steps = E->steps.data(); V.err = E->errs.data(); V.counters = E->counters;
     V.q_values = nullptr; V.agari_guard = nullptr;
     V.enable_quick_eval = quick_eval;
+    V.log = nullptr; V.log_len = nullptr; V.log_cap = 0;
     return E;
 }
 void emul_env_destroy(void* p) { delete static_cast<EmulEnv*>(p); }
@@ -155,9 +158,19 @@ int emul_env_step(void* p, const int64_t* actions) {
     WarpScratch W;
     for (int t = 0; t < E->n; t++) {
         Ctx c; c.S = &E->tabs[t]; c.W = &W; c.T = g_T; c.lane = 0; c.df = W.dora_factor;
+        if (E->log_cap) { c.log = E->log.data() + (size_t)t * E->log_cap; c.log_n = &E->log_len[t]; c.log_cap = E->log_cap; }
         if (step_table(c, E->V, t)) live++;
     }
     return live;
+}
+void emul_env_enable_log(void* p, int cap) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    E->log_cap = cap; E->log.assign((size_t)E->n * cap, 0); E->log_len.assign(E->n, 0);
+}
+void emul_env_read_log(void* p, uint64_t* words, int32_t* lens) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    memcpy(words, E->log.data(), E->log.size() * sizeof(u64));
+    memcpy(lens, E->log_len.data(), E->log_len.size() * sizeof(i32));
 }
 int emul_env_num_rows(void* p) { return static_cast<EmulEnv*>(p)->n_rows[0]; }
 void emul_env_rows(void* p, int32_t* row_table, uint8_t* row_seat, uint8_t* masks) {

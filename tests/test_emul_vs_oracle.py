@@ -143,3 +143,75 @@ def test_sp_block_parity_emulated():
 
     check_obs_parity(make_env, fetch, n=4, max_cycles=150, min_rows=400, sp=True, sp_tol=0.0)
     assert E.lib().emul_sp_overflows() == 0
+
+
+def _log_parity(env_cls, n, policy_kind, shuffle_kind, seed0, **env_kw):
+    """Drive an env and the oracle in lock step with the same decisions; compare the complete mjai event logs."""
+    import json
+
+    from mortal_b200 import mjai_log
+
+    nonces = np.arange(seed0, seed0 + n, dtype=np.uint64)
+    keys = np.full(n, 4242, dtype=np.uint64)
+    env = env_cls(nonces, keys, shuffle_kind=shuffle_kind, **env_kw)
+    env.enable_log()
+    L = O.lib()
+    games = [L.orc_game_new(int(nonces[t]), int(keys[t]), shuffle_kind, t) for t in range(n)]
+    try:
+        actions = None
+        for cycle in range(4000):
+            rt, rs, acts = env.step_and_policy(actions, policy_kind)
+            for t in range(n):
+                assert L.orc_game_poll(games[t]) >= 0, O.err()
+            chosen = {(int(rt[r]), int(rs[r] & 3), bool(rs[r] & 4)): int(acts[r]) for r in range(len(rt))}
+            for (t, seat, kan), a in chosen.items():
+                if kan:
+                    continue
+                ka = chosen.get((t, seat, True), -1)
+                assert L.orc_game_set_action(games[t], seat, a, ka if a == 42 else -1) == 0, O.err()
+            for t in range(n):
+                L.orc_game_advance_step(games[t])
+            actions = acts
+            if env.num_live() == 0:
+                break
+        else:
+            raise AssertionError("games did not finish")
+        words, lens = env.read_log()
+        n_events = 0
+        for t in range(n):
+            ours = mjai_log.decode_events(words[t, : int(lens[t])])
+            buf = (O.OrcEvent * 8192)()
+            m = L.orc_game_log(games[t], buf, 8192)
+            assert m <= 8192
+            ref = [O.event_to_dict(buf[i]) for i in range(m)]
+            assert len(ours) == len(ref), (t, len(ours), len(ref))
+            for i, (a, b) in enumerate(zip(ours, ref)):
+                assert a == b, (t, i, a, b)
+            # and the serialised form is what serde writes: compact separators, `type` first
+            text = mjai_log.dump_json_log(ours, ["a", "b", "c", "d"], (int(nonces[t]), int(keys[t])))
+            lines = text.strip().split("\n")
+            assert json.loads(lines[0]) == {"type": "start_game", "names": ["a", "b", "c", "d"], "seed": [int(nonces[t]), 4242]}
+            assert lines[0].startswith('{"type":"start_game","names":["a","b","c","d"],"seed":[')
+            assert lines[-1] == '{"type":"end_game"}' and len(lines) == len(ours) + 2
+            n_events += len(ours)
+        return n_events
+    finally:
+        for g in games:
+            L.orc_game_free(g)
+        env.close()
+
+
+class _EmulLogEnv(E.EmulEnv):
+    def step_and_policy(self, actions, kind):
+        self.step(actions)
+        rt, rs, _ = self.rows()
+        return rt, rs, self.policy_test(kind)
+
+
+@pytest.mark.parametrize("policy_kind,shuffle_kind", [(1, 0), (0, 1)])
+def test_mjai_event_log_parity_emulated(policy_kind, shuffle_kind):
+    """the product's device-side event log, decoded by mortal_b200.mjai_log, equals the oracle's
+    game log event for event (start_kyoku with haipai, draws, calls, dora, riichi, hora with deltas and ura markers,
+    ryukyoku, end_kyoku) over whole hanchans."""
+    n_events = _log_parity(_EmulLogEnv, 12, policy_kind, shuffle_kind, 31337, enable_quick_eval=False)  # the oracle stepping API has no quick-eval
+    assert n_events > 12 * 500

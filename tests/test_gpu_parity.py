@@ -300,3 +300,73 @@ def test_one_vs_three_network_policy_action_replay(mjx):
     for i in range(n):
         hist[int(ref["ranks"][i, i % 4])] += 1
     assert hist == rankings
+
+
+def test_mjai_event_log_matches_oracle(mjx):
+    """SURVEY.md §8f N1 on device: the event log recorded by k_step, decoded by mortal_b200.mjai_log, equals the oracle's
+    game log event for event over whole hanchans (same decisions on both sides)."""
+    import torch
+
+    from test_emul_vs_oracle import _log_parity
+
+    class GpuLogEnv(mjx.BatchEnv):
+        def __init__(self, nonces, keys, **kw):
+            super().__init__(nonces, keys, **kw)
+            self._a = torch.zeros(self.row_cap, dtype=torch.int64, device=self.device)
+
+        def step_and_policy(self, actions, kind):
+            self.step(None if actions is None else self._a)
+            self.policy_test(kind, self._a)
+            nr = self.num_rows()
+            return self.row_table[:nr].cpu().numpy(), self.row_seat[:nr].cpu().numpy(), self._a.cpu().numpy()
+
+    n_events = _log_parity(GpuLogEnv, 48, 1, 0, 777, enable_quick_eval=False)
+    assert n_events > 48 * 500
+
+
+def test_arena_writes_mjai_logs(mjx, tmp_path):
+    """OneVsThree(log_dir=...) writes one {seed}_{key}_{a|b|c|d}.json.gz per game (one_vs_three.rs:195-225) whose final
+    scores are consistent with the returned results."""
+    import gzip
+    import json
+
+    import torch
+
+    from mortal_b200.libriichi.arena import OneVsThree
+
+    class Greedy:
+        engine_type = "mortal"
+        version = 4
+        is_oracle = False
+        enable_quick_eval = True
+        enable_rule_based_agari_guard = False
+
+        def __init__(self, name):
+            self.name = name
+
+        def react_device(self, obs, masks):
+            q = torch.rand(masks.shape, device=masks.device) + 10.0 * obs[:, 876, :].new_zeros(masks.shape)
+            q = q.masked_fill(~masks, -1.0)
+            return q.argmax(-1), q
+
+    arena = OneVsThree(disable_progress_bar=True, log_dir=str(tmp_path))
+    torch.manual_seed(0)
+    rankings = arena.py_vs_py(Greedy("chal"), Greedy("champ"), (4000, 77), 3)
+    assert sum(rankings) == 12
+    names = sorted(p.name for p in tmp_path.iterdir())
+    assert names == sorted(f"{4000 + s}_77_{c}.json.gz" for s in range(3) for c in "abcd")
+    res = arena.last_results
+    for g, path in enumerate(arena.last_log_paths):
+        lines = [json.loads(ln) for ln in gzip.open(path, "rt")]
+        assert lines[0]["type"] == "start_game" and lines[0]["seed"] == [4000 + g // 4, 77]
+        assert lines[0]["names"] == ["chal" if s == g % 4 else "champ" for s in range(4)]
+        assert lines[-1] == {"type": "end_game"}
+        scores = None
+        for ev in lines:
+            if ev["type"] == "start_kyoku":
+                scores = list(ev["scores"])
+            elif ev["type"] in ("hora", "ryukyoku"):
+                scores = [a + b for a, b in zip(scores, ev["deltas"])]
+            elif ev["type"] == "reach_accepted":
+                scores[ev["actor"]] -= 1000
+        assert scores == [int(x) for x in res["scores"][g]], (g, scores, res["scores"][g])
