@@ -370,3 +370,60 @@ def test_arena_writes_mjai_logs(mjx, tmp_path):
             elif ev["type"] == "reach_accepted":
                 scores[ev["actor"]] -= 1000
         assert scores == [int(x) for x in res["scores"][g]], (g, scores, res["scores"][g])
+
+
+def test_agari_guard_on_device_matches_oracle(mjx):
+    """mortal.rs:319-336 + agent_helper.rs:262-368 on device: with the rule-based agari guard on for every seat the
+    decisions (incl. refused wins at all-last) and final scores match the oracle, and differ from the unguarded run."""
+    n = 256
+    nonces = np.arange(4000, 4000 + n, dtype=np.uint64)
+    keys = np.full(n, 5, dtype=np.uint64)
+    ro = O.run_batch(nonces, keys, policy_kind=1, quick_eval=True, agari_guard=True, trace_cap=1 << 19, n_threads=8)
+    rn = O.run_batch(nonces, keys, policy_kind=1, quick_eval=True, agari_guard=False, n_threads=8)
+    assert (rn["scores"] != ro["scores"]).any(), "guard never fired: the test does not cover it"
+    env = mjx.BatchEnv(nonces, keys, enable_quick_eval=True)
+    rg = env.run_test_policy(1, trace=True, agari_guard=True)
+    env.close()
+    assert (rg["err"] == 0).all()
+    to, tg = sort_trace(ro["trace"]), sort_trace(rg["trace"])
+    i, a, b = first_diff(to, tg)
+    assert a is None, f"first divergence at sorted row {i}: oracle {a} gpu {b}"
+    assert (ro["scores"] == rg["scores"]).all() and (ro["ranks"] == rg["ranks"]).all()
+
+
+def test_two_vs_two_arena_runs_and_logs(mjx, tmp_path):
+    """TwoVsTwo.py_vs_py (two_vs_two.rs:35-55) returns None; its product is the log files: 2 games per seed named
+    {seed}_{key}_{a|b}.json.gz, challenger pair on seats {0,2} in game a and {1,3} in game b."""
+    import gzip
+    import json
+
+    import torch
+
+    from mortal_b200.libriichi.arena import TwoVsTwo
+
+    class Rand:
+        engine_type = "mortal"
+        version = 4
+        is_oracle = False
+        enable_quick_eval = True
+        enable_rule_based_agari_guard = False
+
+        def __init__(self, name):
+            self.name = name
+
+        def react_device(self, obs, masks):
+            q = torch.rand(masks.shape, device=masks.device).masked_fill(~masks, -1.0)
+            return q.argmax(-1), q
+
+    torch.manual_seed(1)
+    arena = TwoVsTwo(disable_progress_bar=True, log_dir=str(tmp_path))
+    assert arena.py_vs_py(Rand("x"), Rand("y"), (9000, 3), 8) is None
+    res = arena.last_results
+    assert res["ranks"].shape[0] == 16
+    assert (np.sort(res["ranks"], axis=1) == np.arange(4)).all() and (res["scores"].sum(1) % 100 == 0).all()
+    names = sorted(p.name for p in tmp_path.iterdir())
+    assert names == sorted(f"{9000 + s}_3_{c}.json.gz" for s in range(8) for c in "ab")
+    for g, path in enumerate(arena.last_log_paths):
+        first = json.loads(gzip.open(path, "rt").readline())
+        chal = [0, 2] if g % 2 == 0 else [1, 3]
+        assert first["names"] == ["x" if s in chal else "y" for s in range(4)]
