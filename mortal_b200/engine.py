@@ -82,6 +82,12 @@ class HostProtocolEngine:
         for attr in ("name", "version", "is_oracle", "enable_quick_eval", "enable_rule_based_agari_guard"):
             setattr(self, attr, getattr(engine, attr))
 
+    def react_host(self, obs_np: np.ndarray, masks_np: np.ndarray, idx: np.ndarray):
+        """rows `idx` of host arrays (views over pinned buffers filled by mjx_env_encode_obs_host) -> (actions, q) numpy,
+        through the reference protocol: lists of per-row arrays in, lists out (agent/mortal.rs:126-152)."""
+        actions, q, _, _ = self.engine.react_batch([obs_np[i] for i in idx], [masks_np[i] for i in idx], None)
+        return np.asarray(actions, dtype=np.int64), np.asarray(q, dtype=np.float32)
+
     def react_device(self, obs: torch.Tensor, masks: torch.Tensor):
         obs_h = obs.cpu().numpy()
         masks_h = masks.cpu().numpy()

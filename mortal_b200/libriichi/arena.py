@@ -76,12 +76,46 @@ class _Arena:
                     flags[g, seat] = guards[0] if ic[g % per, seat] else guards[1]
             env.set_agari_guard(flags)
             q_all = torch.zeros((env.row_cap, 46), dtype=torch.float32, device=dev)
+        # engines that only speak the reference protocol (react_batch over host arrays) get the observations through
+        # mjx_env_encode_obs_host: pinned host buffers, D2H overlapped with the single-player kernels
+        host_mode = all(isinstance(a, HostProtocolEngine) for a in agents)
+        if host_mode:
+            h_obs = torch.empty((env.row_cap, env.obs_rows, 34), dtype=torch.float32).pin_memory()
+            h_masks = torch.empty((env.row_cap, 46), dtype=torch.bool).pin_memory()
+            h_actions = torch.zeros(env.row_cap, dtype=torch.int64).pin_memory()
+            h_q = torch.zeros((env.row_cap, 46), dtype=torch.float32).pin_memory() if q_all is not None else None
+            obs_np, masks_np = h_obs.numpy(), h_masks.numpy()
+            ic_host = is_challenger.cpu().numpy()
         first = True
         cycles = 0
         recorded = []
         while True:
             env.step(None if first else actions, None if first else q_all)
             first = False
+            if host_mode:
+                nr = env.encode_obs_host(h_obs, h_masks)
+                if nr == 0 and env.num_live() == 0:
+                    break
+                if nr > 0:
+                    tbl_h = env.row_table[:nr].cpu().numpy()
+                    rs_h = env.row_seat[:nr].cpu().numpy()
+                    chal_h = ic_host[tbl_h % per, rs_h & 3]
+                    for idx, agent in ((np.nonzero(chal_h)[0], agents[0]), (np.nonzero(~chal_h)[0], agents[1])):
+                        if idx.size == 0:
+                            continue
+                        a, q = agent.react_host(obs_np, masks_np, idx)
+                        h_actions[torch.from_numpy(idx)] = torch.from_numpy(a)
+                        if h_q is not None:
+                            h_q[torch.from_numpy(idx)] = torch.from_numpy(q).reshape(-1, 46)
+                    actions[:nr].copy_(h_actions[:nr], non_blocking=True)
+                    if h_q is not None:
+                        q_all[:nr].copy_(h_q[:nr], non_blocking=True)
+                    if self.record_decisions:
+                        recorded.append(torch.stack([torch.from_numpy(tbl_h).long(), env.row_step[:nr].cpu().long(),
+                                                     torch.from_numpy(rs_h & 3).long(), torch.from_numpy((rs_h >> 2) & 1).long(),
+                                                     h_actions[:nr].clone()], dim=1))
+                cycles += 1
+                continue
             nr = env.num_rows()
             if nr == 0 and env.num_live() == 0:
                 break

@@ -427,3 +427,46 @@ def test_two_vs_two_arena_runs_and_logs(mjx, tmp_path):
         first = json.loads(gzip.open(path, "rt").readline())
         chal = [0, 2] if g % 2 == 0 else [1, 3]
         assert first["names"] == ["x" if s in chal else "y" for s in range(4)]
+
+
+def test_reference_protocol_engine_through_host_buffers(mjx):
+    """An engine that only implements the reference protocol (react_batch over lists of numpy arrays, mortal.rs:126-152)
+    runs through OneVsThree unchanged; the arena feeds it from pinned host buffers (mjx_env_encode_obs_host). The recorded
+    decisions replay in the oracle to the same scores, and every observation it saw had the right shape and range."""
+    from mortal_b200.libriichi.arena import OneVsThree
+
+    seen = dict(rows=0, batches=0)
+
+    class RefProtocolEngine:
+        engine_type = "mortal"
+        name = "ref"
+        version = 4
+        is_oracle = False
+        enable_quick_eval = True
+        enable_rule_based_agari_guard = False
+
+        def __init__(self, seed):
+            self.rng = np.random.default_rng(seed)
+
+        def react_batch(self, obs, masks, invisible_obs):
+            assert invisible_obs is None and len(obs) == len(masks) > 0
+            assert obs[0].shape == (1012, 34) and obs[0].dtype == np.float32 and masks[0].shape == (46,)
+            o = np.stack(obs)
+            assert o.min() >= 0.0 and o.max() <= 1.0
+            m = np.stack(masks).astype(bool)
+            q = self.rng.random(m.shape, dtype=np.float32)
+            q[~m] = -np.inf
+            seen["rows"] += len(obs)
+            seen["batches"] += 1
+            return q.argmax(-1).tolist(), q.tolist(), m.tolist(), [True] * len(obs)
+
+    arena = OneVsThree(disable_progress_bar=True)
+    arena.record_decisions = True
+    rankings = arena.py_vs_py(RefProtocolEngine(1), RefProtocolEngine(2), (6000, 9), 4)
+    assert sum(rankings) == 16 and seen["rows"] > 16 * 300
+    dec = arena.last_decisions
+    order = np.lexsort((dec[:, 3], dec[:, 2], dec[:, 1], dec[:, 0]))
+    nonces = np.repeat(np.arange(6000, 6004, dtype=np.uint64), 4)
+    keys = np.full(16, 9, dtype=np.uint64)
+    ref = O.run_replay(nonces, keys, dec[order], quick_eval=True)
+    assert (ref["scores"] == arena.last_results["scores"]).all() and (ref["ranks"] == arena.last_results["ranks"]).all()
