@@ -111,6 +111,15 @@ int mjx_env_results(mjx_env* env, void* stream, int32_t* scores_host /*[n,4]*/, 
 int mjx_env_policy_test(mjx_env* env, int kind, int64_t* actions_dev, int64_t* trace_dev, float* q_values_dev,
                         void* stream);
 
+/* ---- policy-net inference helpers (not part of libriichi's surface; mortal/model.py ResBlock + ChannelAttention) ------------
+ * Fused elementwise passes between the cuDNN convolutions: bf16 channels-last activations [batch, length, channels]
+ * (device pointers, 16-byte aligned, channels % 8 == 0), fp32 math. scale/bias = eval-mode BatchNorm folded to an affine. */
+int mjx_nn_affine_mish_bf16(const void* x, const float* scale, const float* bias, void* out, long long n_elems, int channels,
+                            void* stream);                                   /* out = mish(x * scale[c] + bias[c]) */
+int mjx_nn_pool_bf16(const void* x, void* avg, void* mx, int batch, int length, int channels, void* stream);  /* [batch, channels] each */
+int mjx_nn_gate_residual_bf16(const void* y, const void* gate, const void* x, void* out, int batch, int length, int channels,
+                              void* stream);                                 /* out = y * gate[b, c] + x */
+
 /* ---- standalone kernels (BASELINE configs 3/4) ------------------------------------------------ */
 /* algo/shanten.rs:138-150 calc_all: tiles_dev uint8 [n,34], len_div3_dev uint8 [n] -> int8 [n]. */
 int mjx_shanten(const uint8_t* tiles_dev, const uint8_t* len_div3_dev, int8_t* out_dev, int n, void* stream);

@@ -8,6 +8,7 @@
 #include "../../include/mjx.h"
 #include "mjx_sp.cuh"
 #include "mjx_policy.cuh"
+#include "mjx_nn.cuh"
 #include "mjx_tables_host.h"
 
 using namespace mjx;
@@ -769,6 +770,45 @@ int mjx_env_policy_test(mjx_env* env, int kind, int64_t* actions_dev, int64_t* t
     k_policy_test<<<g_sm_count * 2, 128, 0, (cudaStream_t)stream>>>(env->V, kind, (i64*)actions_dev, (i64*)trace_dev, q_values_dev);
     CU(cudaGetLastError());
     env->launches += 1;
+    return MJX_OK;
+}
+
+// ---- policy-net helpers (csrc/mjx_nn.cuh): bf16 NHWC activations [batch, length, channels], channels % 8 == 0
+static int nn_grid(size_t n_items) {
+    size_t g = (n_items + 255) / 256;
+    const size_t cap = (size_t)g_sm_count * 16;
+    return (int)(g < cap ? (g ? g : 1) : cap);
+}
+int mjx_nn_affine_mish_bf16(const void* x, const float* scale, const float* bias, void* out, long long n_elems, int channels,
+                            void* stream) {
+    if (!x || !scale || !bias || !out || channels <= 0 || channels % 8 || n_elems % channels)
+        return fail(MJX_ERR_ARG, "mjx_nn_affine_mish_bf16: bad arguments");
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_nn_*: call mjx_init first");
+    const size_t n_vec = (size_t)n_elems / 8;
+    mjx_nn::k_affine_mish<<<nn_grid(n_vec), 256, 0, (cudaStream_t)stream>>>((const mjx_nn::Vec8*)x, scale, bias, (mjx_nn::Vec8*)out,
+                                                                            n_vec, channels / 8);
+    CU(cudaGetLastError());
+    return MJX_OK;
+}
+int mjx_nn_pool_bf16(const void* x, void* avg, void* mx, int batch, int length, int channels, void* stream) {
+    if (!x || !avg || !mx || batch <= 0 || length <= 0 || channels <= 0 || channels % 8)
+        return fail(MJX_ERR_ARG, "mjx_nn_pool_bf16: bad arguments");
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_nn_*: call mjx_init first");
+    mjx_nn::k_pool<<<nn_grid((size_t)batch * (channels / 8)), 256, 0, (cudaStream_t)stream>>>(
+        (const mjx_nn::Vec8*)x, (mjx_nn::Vec8*)avg, (mjx_nn::Vec8*)mx, batch, length, channels / 8);
+    CU(cudaGetLastError());
+    return MJX_OK;
+}
+int mjx_nn_gate_residual_bf16(const void* y, const void* gate, const void* x, void* out, int batch, int length, int channels,
+                              void* stream) {
+    if (!y || !gate || !x || !out || batch <= 0 || length <= 0 || channels <= 0 || channels % 8)
+        return fail(MJX_ERR_ARG, "mjx_nn_gate_residual_bf16: bad arguments");
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_nn_*: call mjx_init first");
+    const size_t n_vec = (size_t)batch * length * (channels / 8);
+    mjx_nn::k_gate_residual<<<nn_grid(n_vec), 256, 0, (cudaStream_t)stream>>>((const mjx_nn::Vec8*)y, (const mjx_nn::Vec8*)gate,
+                                                                              (const mjx_nn::Vec8*)x, (mjx_nn::Vec8*)out, n_vec,
+                                                                              length, channels / 8);
+    CU(cudaGetLastError());
     return MJX_OK;
 }
 

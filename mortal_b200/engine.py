@@ -24,6 +24,9 @@ class DeviceEngine:
         # BN-folded bf16 inference path when the brain offers one (mortal_b200.model.Brain); plain autocast otherwise
         self.fast = bool(fast_inference and enable_amp and hasattr(self.brain, "prepare_fast") and self.device.type == "cuda")
         if self.fast:
+            from . import _lib
+
+            _lib.init(self.device.index or 0)  # the fused elementwise kernels live in libmjx
             self.brain.prepare_fast(torch.bfloat16)
         self.version = version
         self.is_oracle = is_oracle

@@ -59,9 +59,20 @@ class PreActBlock(nn.Module):
         shift = bn.bias - bn.running_mean * scale
         return scale.view(1, -1, 1, 1).contiguous(), shift.view(1, -1, 1, 1).contiguous()
 
-    def forward_fast(self, x, aff, w1, w2):
+    def forward_fast(self, x, aff, w1, w2, aff32=None):
         (s1, b1), (s2, b2) = aff
         F = torch.nn.functional
+        if aff32 is not None and x.is_cuda and x.dtype == torch.bfloat16:
+            # fused bandwidth-bound passes (libmjx, csrc/mjx_nn.cuh) around the two cuDNN convolutions
+            from . import nn_ops
+
+            (f1, g1), (f2, g2) = aff32
+            y = F.conv2d(nn_ops.affine_mish(x, f1, g1), w1, padding=(0, 1))
+            y = F.conv2d(nn_ops.affine_mish(y, f2, g2), w2, padding=(0, 1))
+            avg, mx = nn_ops.pool_mean_max(y)
+            h = self.gate._mlp(torch.cat((avg, mx), 0))  # both pooled vectors through the gate MLP in one call
+            gate = torch.sigmoid(h[: avg.shape[0]] + h[avg.shape[0]:])
+            return nn_ops.gate_residual(y, gate.contiguous(), x)
         y = F.conv2d(F.mish(torch.addcmul(b1, x, s1)), w1, padding=(0, 1))
         y = F.conv2d(F.mish(torch.addcmul(b2, y, s2)), w2, padding=(0, 1))
         return self.gate.forward_fast(y) + x
@@ -91,6 +102,10 @@ class Brain(nn.Module):
         kernels instead of cuDNN's NCHW batch-norm kernel) and optional reduced-precision weights so that no
         autocast casts are needed. Mathematically the same network; call after loading weights / .eval()."""
         assert not self.training, "prepare_fast() is for eval mode"
+        # fp32 copies of the folded affines for the fused kernels, taken before any down-cast of the parameters
+        flat = lambda a: (a[0].float().flatten().contiguous(), a[1].float().flatten().contiguous())
+        self._aff32 = [(flat(PreActBlock._affine(b.bn1)), flat(PreActBlock._affine(b.bn2))) for b in self.blocks]
+        self._aff32_out = flat(PreActBlock._affine(self.bn))
         if dtype is not None:
             self.to(dtype)
         self._aff = [(PreActBlock._affine(b.bn1), PreActBlock._affine(b.bn2)) for b in self.blocks]
@@ -108,10 +123,17 @@ class Brain(nn.Module):
             obs = obs.to(self._fast_dtype)
         x = obs.unsqueeze(2).contiguous(memory_format=torch.channels_last)  # [B, C, 1, 34]
         x = F.conv2d(x, self._w_stem, padding=(0, 1))
-        for blk, aff, (w1, w2) in zip(self.blocks, self._aff, self._w):
-            x = blk.forward_fast(x, aff, w1, w2)
+        fused = x.is_cuda and x.dtype == torch.bfloat16
+        for blk, aff, (w1, w2), a32 in zip(self.blocks, self._aff, self._w, self._aff32):
+            x = blk.forward_fast(x, aff, w1, w2, a32 if fused else None)
         s, b = self._aff_out
-        x = F.mish(F.conv2d(F.mish(torch.addcmul(b, x, s)), self._w_neck, self.neck.bias, padding=(0, 1)))
+        if fused:
+            from . import nn_ops
+
+            x = nn_ops.affine_mish(x, *self._aff32_out)
+        else:
+            x = F.mish(torch.addcmul(b, x, s))
+        x = F.mish(F.conv2d(x, self._w_neck, self.neck.bias, padding=(0, 1)))
         return F.mish(self.fc(x.flatten(1)))
 
 

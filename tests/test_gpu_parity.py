@@ -470,3 +470,43 @@ def test_reference_protocol_engine_through_host_buffers(mjx):
     keys = np.full(16, 9, dtype=np.uint64)
     ref = O.run_replay(nonces, keys, dec[order], quick_eval=True)
     assert (ref["scores"] == arena.last_results["scores"]).all() and (ref["ranks"] == arena.last_results["ranks"]).all()
+
+
+def test_fused_policy_net_kernels_match_torch(mjx):
+    """csrc/mjx_nn.cuh against plain PyTorch fp32 references of the same ops (bf16 in / out, fp32 math: <= 1 bf16 ulp),
+    and the fused bf16 fast path of the 192-channel brain against its fp32 forward."""
+    import torch
+
+    from mortal_b200 import nn_ops
+    from mortal_b200.model import Brain
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    B, Cc, L = 257, 192, 34
+    x = (torch.randn(B, Cc, 1, L, device=dev) * 2).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = (torch.randn(B, Cc, 1, L, device=dev) * 2).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    scale = torch.rand(Cc, device=dev) + 0.5
+    bias = torch.randn(Cc, device=dev)
+    ref = torch.nn.functional.mish(x.float() * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    got = nn_ops.affine_mish(x, scale, bias).float()
+    assert (got - ref).abs().max() <= 2 ** -7 * ref.abs().max()  # one bf16 rounding (8 significant bits)
+    assert ((got - ref).abs() <= ref.abs() * 2 ** -8 + 1e-6).all()
+    avg, mx = nn_ops.pool_mean_max(x)
+    assert ((avg.float() - x.float().mean((2, 3))).abs() <= x.float().mean((2, 3)).abs() * 2 ** -8 + 1e-3).all()
+    assert torch.equal(mx.float(), x.float().amax((2, 3)))
+    gate = torch.rand(B, Cc, device=dev).to(torch.bfloat16)
+    ref = y.float() * gate.float().view(B, Cc, 1, 1) + x.float()
+    got = nn_ops.gate_residual(y, gate, x).float()
+    assert ((got - ref).abs() <= ref.abs() * 2 ** -8 + 1e-6).all()
+
+    brain = Brain(conv_channels=192, num_blocks=6).to(dev).eval()
+    for m in brain.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5); m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.1)
+    obs = (torch.rand(64, 1012, 34, device=dev) < 0.05).float()
+    with torch.inference_mode():
+        ref = brain(obs)
+        brain.prepare_fast(torch.bfloat16)
+        fast = brain.forward_fast(obs).float()
+    err = (fast - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 0.05, err  # bf16 end to end over 6 residual blocks
