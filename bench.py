@@ -230,7 +230,7 @@ def run_ours(args):
     def nn_policy(env, obs, actions):
         nr = env.num_rows()  # the only host sync of the cycle: the batch size the network runs at
         if nr:
-            a, _ = engine.react_device(obs[:nr], env.masks[:nr])
+            a, _ = engine.react_static(obs, env.masks, nr)  # CUDA-graph replay over the env's persistent buffers
             actions[:nr] = a
         return nr
 

@@ -37,6 +37,7 @@ class DeviceEngine:
         self.boltzmann_epsilon = boltzmann_epsilon
         self.boltzmann_temp = boltzmann_temp
         self.top_p = top_p
+        self._graphs = {}
 
     @torch.inference_mode()
     def react_device(self, obs: torch.Tensor, masks: torch.Tensor):
@@ -55,6 +56,32 @@ class DeviceEngine:
         else:
             actions = q.argmax(-1)
         return actions, q
+
+    @torch.inference_mode()
+    def react_static(self, obs_buf: torch.Tensor, masks_buf: torch.Tensor, nr: int, bucket: int = 256):
+        """react_device(obs_buf[:nr], masks_buf[:nr]) for PERSISTENT buffers (BatchEnv.obs_buffer() / .masks): the forward
+        over the first ceil(nr / bucket) * bucket rows is captured once per bucket as a CUDA graph and replayed, which
+        removes the ~600 kernel-launch calls per step from the host. Greedy engines only; rows past nr are stale and ignored."""
+        if self.boltzmann_epsilon > 0 or not self.fast:
+            return self.react_device(obs_buf[:nr], masks_buf[:nr])
+        nb = min(((nr + bucket - 1) // bucket) * bucket, obs_buf.shape[0])
+        key = (obs_buf.data_ptr(), masks_buf.data_ptr(), nb)
+        entry = self._graphs.get(key)
+        if entry is None:
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up outside the capture (cuDNN algorithm selection, lazy init)
+                for _ in range(2):
+                    self.react_device(obs_buf[:nb], masks_buf[:nb])
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                a, q = self.react_device(obs_buf[:nb], masks_buf[:nb])
+            entry = (graph, a, q)
+            self._graphs[key] = entry
+        entry[0].replay()
+        return entry[1][:nr], entry[2][:nr]
 
     # the reference protocol, for callers that only know libriichi's calling convention
     def react_batch(self, obs, masks, invisible_obs):

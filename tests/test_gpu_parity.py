@@ -510,3 +510,28 @@ def test_fused_policy_net_kernels_match_torch(mjx):
         fast = brain.forward_fast(obs).float()
     err = (fast - ref).abs().max().item() / ref.abs().max().item()
     assert err < 0.05, err  # bf16 end to end over 6 residual blocks
+
+
+def test_device_engine_graph_replay_equals_eager(mjx):
+    """DeviceEngine.react_static (CUDA-graph replay over persistent buffers) returns what react_device returns."""
+    import torch
+
+    from mortal_b200.engine import DeviceEngine
+    from mortal_b200.model import DQN, Brain
+
+    torch.manual_seed(3)
+    dev = torch.device("cuda", 0)
+    eng = DeviceEngine(Brain(conv_channels=64, num_blocks=3), DQN(), device=dev)
+    obs = (torch.rand(700, 1012, 34, device=dev) < 0.05).float()
+    masks = torch.rand(700, 46, device=dev) > 0.5
+    masks[:, 45] = True
+    for nr in (300, 511, 512, 650, 300):
+        nb = min(-(-nr // 256) * 256, 700)  # the graph runs the padded batch; same shapes -> same kernels -> same bits
+        a0, q0 = eng.react_device(obs[:nb], masks[:nb])
+        a1, q1 = eng.react_static(obs, masks, nr)
+        assert torch.equal(a0[:nr], a1) and torch.equal(q0[:nr], q1), nr
+        # and against the un-padded eager call up to bf16 kernel-selection noise
+        a2, q2 = eng.react_device(obs[:nr], masks[:nr])
+        fin = torch.isfinite(q2)
+        assert (q2[fin] - q1[fin]).abs().max() <= 0.05 * q2[fin].abs().max() + 1e-3
+    assert len(eng._graphs) == 2  # buckets 512 and 700 (capped at the buffer size)
