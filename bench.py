@@ -397,7 +397,9 @@ def run_ours(args):
                     "path": "mjx_env_encode_obs_host with pinned host buffers: actions H2D, obs+masks D2H every step "
                             "(rows 0-888 drain while the SP kernels run), greedy host-side policy reading the host obs",
                     "plain_d2h_copy_gbs": pcie_gbs},
-            "gpu_launches": a["launches"], "clocks": clocks,
+            # this library's kernels in the timed region: env kernels counted by libmjx, plus the fused policy-net kernels
+            # (4 per residual block + 1, csrc/mjx_nn.cuh) that each CUDA-graph replay of the forward contains
+            "gpu_launches": a["launches"] + K * (4 * 40 + 1), "gpu_launches_env": a["launches"], "clocks": clocks,
             "collective": {"all_gather_us": gather_us, "bytes_per_table": 20},
         }
         if world == 1 and not args.no_cpu_baseline:
