@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""Derive the lookup tables used by both the oracle and the CUDA library.
+"""Build the lookup tables used by both the oracle and the CUDA library into mortal_b200/data/ (git-ignored, travels
+to the GPU box like a built .so).
 
-Round-1 provenance: the three tables are *data* (tomohxx shanten tables, 山岡 agari
-table) that libriichi ships gzipped under libriichi/src/algo/data/. This script only
-gunzips them into mortal_b200/data/ (git-ignored, travels to the GPU box like a built
-.so). It runs in the dev container where /root/reference exists; on the GPU box the
-prebuilt files are used. Formats: SURVEY.md Appendix A.
+* shanten_suhai.bin / shanten_jihai.bin are GENERATED from first principles by tools/gen_shanten_tables.cc (a DP over
+  the rank counts; no input files) and truncated to the row counts of libriichi's tables (1,940,777 / 78,032 rows:
+  indices past the end read as an all-zero row in the reference, algo/shanten.rs:52, and that quirk is part of the
+  contract). When the reference tree is present the result is checked byte for byte against its data files.
+* agari.bin (9,362 keys) is data libriichi ships gzipped under libriichi/src/algo/data/; it is only gunzipped here.
+  On a box without /root/reference the prebuilt file is used. Formats: SURVEY.md Appendix A.
 """
 import gzip
 import os
+import subprocess
 import sys
+import tempfile
 
 REF = os.environ.get("MORTAL_REF_DATA", "/root/reference/libriichi/src/algo/data")
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mortal_b200", "data")
@@ -20,8 +24,36 @@ FILES = {
 }
 
 
+def generate_shanten_tables() -> dict:
+    """name -> bytes, from tools/gen_shanten_tables.cc"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "gen_shanten_tables")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(here, "gen_shanten_tables.cc")], check=True)
+        a, b = os.path.join(tmp, "suhai.bin"), os.path.join(tmp, "jihai.bin")
+        subprocess.run([exe, a, b], check=True)
+        out = {}
+        for name, path in (("shanten_suhai.bin", a), ("shanten_jihai.bin", b)):
+            with open(path, "rb") as f:
+                out[name] = f.read()[: FILES[name][1]]
+            assert len(out[name]) == FILES[name][1]
+    return out
+
+
 def main() -> int:
     os.makedirs(OUT, exist_ok=True)
+    todo = [n for n in ("shanten_suhai.bin", "shanten_jihai.bin")
+            if not (os.path.exists(os.path.join(OUT, n)) and os.path.getsize(os.path.join(OUT, n)) == FILES[n][1])]
+    if todo:
+        gen = generate_shanten_tables()
+        for name in todo:
+            ref_path = os.path.join(REF, FILES[name][0])
+            if os.path.exists(ref_path):
+                with gzip.open(ref_path, "rb") as f:
+                    assert f.read() == gen[name], f"{name}: generated table differs from the reference's data file"
+            with open(os.path.join(OUT, name), "wb") as f:
+                f.write(gen[name])
+            print(f"build_tables: generated {name} ({len(gen[name])} bytes)")
     for out_name, (src, size) in FILES.items():
         dst = os.path.join(OUT, out_name)
         if os.path.exists(dst) and os.path.getsize(dst) == size:
