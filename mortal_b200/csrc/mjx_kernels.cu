@@ -88,7 +88,7 @@ template <int VER> struct EncF {
 };
 
 template <int VER>
-__global__ void __launch_bounds__(EncF<VER>::WARPS * 32, 1) k_encode_features(EnvView V, Tables T, unsigned char* __restrict__ compact) {
+__global__ void __launch_bounds__(EncF<VER>::WARPS * 32, 1) k_encode_features(EnvView V, Tables T, unsigned char* __restrict__ compact, int* __restrict__ work) {
     constexpr ObsLayout L = make_layout(VER);
     constexpr int COMPACT = EncF<VER>::COMPACT, WARPS = EncF<VER>::WARPS;
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -100,8 +100,16 @@ __global__ void __launch_bounds__(EncF<VER>::WARPS * 32, 1) k_encode_features(En
     u8* df = base + EncF<VER>::COMPACT_PAD + sizeof(TableState);
     const int n_rows = *V.n_rows;
     const int n_items = n_rows * ENC_N_PARTS;
-    for (int item = blockIdx.x * WARPS + warp; item < n_items; item += gridDim.x * WARPS) {
-        const int part = item / n_rows, row = item - part * n_rows;
+    // Items are handed out dynamically, longest first: the action block (part 3: discard candidates, unconditional-tenpai
+    // scan, L2 table gathers) of every row, then the ponds, the counters/overview group and the cheap hand/scalar group,
+    // so that the expensive rows do not form the tail. `work` is reset by k_encode_store, which always runs next.
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(work, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int ord = item / n_rows, row = item - ord * n_rows;
+        const int part = ord == 0 ? 3 : ord == 1 ? 1 : ord == 2 ? 2 : 0;
         // this part's window of the compact form, in 8-byte words (mask rows, then the value rows as 17 words each)
         int bm_lo = 0, bm_hi = 0, sv_lo = 0, sv_hi = 0;
 #pragma unroll
@@ -160,9 +168,10 @@ struct EncStoreArgs { int rows, bm_rows, n_sv, compact_bytes, n_slices, ver; };
 __constant__ short c_sv_row[4][OBS_MAX_SV];  // ObsLayout::sv_row of versions 1..4
 
 __global__ void __launch_bounds__(ENCS_WARPS * 32, 1) k_encode_store(EnvView V, EncStoreArgs A, const unsigned char* __restrict__ compact,
-                                                                     float* __restrict__ obs) {
+                                                                     float* __restrict__ obs, int* __restrict__ work) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *work = 0;  // re-arm k_encode_features' work counter for the next step
     unsigned char* base = s_raw + (size_t)warp * 2 * ENC_SLICE_BYTES;
     const int n_items = *V.n_rows * A.n_slices;
     const int stride = gridDim.x * ENCS_WARPS;
@@ -398,6 +407,7 @@ struct mjx_env {
     SpGlobal sp;
     int sp_enabled = 1;
     unsigned char* d_compact = nullptr;
+    int* d_enc_work = nullptr;  // k_encode_features' dynamic work counter
     EncStoreArgs enc_args{};
     cudaStream_t copy_stream = nullptr;  // mjx_env_encode_obs_host: D2H overlapped with the SP kernels
     cudaEvent_t ev_rows = nullptr, ev_sp = nullptr;
@@ -406,7 +416,7 @@ struct mjx_env {
 
 template <int VER>
 static void launch_features(mjx_env* env, cudaStream_t st) {
-    k_encode_features<VER><<<g_sm_count, EncF<VER>::WARPS * 32, EncF<VER>::SMEM, st>>>(env->V, g_T, env->d_compact);
+    k_encode_features<VER><<<g_sm_count, EncF<VER>::WARPS * 32, EncF<VER>::SMEM, st>>>(env->V, g_T, env->d_compact, env->d_enc_work);
 }
 
 extern "C" {
@@ -505,6 +515,8 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
         env->enc_args.ver = obs_version;
         CU(cudaMalloc(&env->d_compact, cap * (size_t)env->enc_args.compact_bytes));  // compact observations (mjx_obs.cuh)
         env->sp_enabled = obs_version == 4 ? 1 : 0;  // the single-player block exists in v4 only
+        CU(cudaMalloc(&env->d_enc_work, sizeof(int)));
+        CU(cudaMemset(env->d_enc_work, 0, sizeof(int)));
     }
     {
         SpGlobal& G = env->sp;
@@ -557,7 +569,7 @@ void mjx_env_destroy(mjx_env* env) {
     EnvView& V = env->V;
     cudaFree(V.tables); cudaFree(V.n_rows); cudaFree(V.row_table); cudaFree(V.row_seat); cudaFree(V.row_step);
     cudaFree(V.masks); cudaFree(V.scores); cudaFree(V.ranks); cudaFree(V.done); cudaFree(V.steps); cudaFree(V.err);
-    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard); cudaFree(env->d_compact); cudaFree(env->V.log); cudaFree(env->V.log_len);
+    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len);
     SpGlobal& G = env->sp;
     cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.sigs); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
     cudaFree(G.edge_child); cudaFree(G.edge_meta); cudaFree(G.edge_owner); cudaFree(G.leaf_scores); cudaFree(G.hash); cudaFree(G.slot_list); cudaFree(G.slot_count);
@@ -597,7 +609,7 @@ static int launch_encode_rows(mjx_env* env, float* obs_dev, cudaStream_t st) {
         case 3: launch_features<3>(env, st); break;
         default: launch_features<4>(env, st); break;
     }
-    k_encode_store<<<g_sm_count, ENCS_WARPS * 32, ENCS_SMEM_BYTES, st>>>(env->V, env->enc_args, env->d_compact, obs_dev);
+    k_encode_store<<<g_sm_count, ENCS_WARPS * 32, ENCS_SMEM_BYTES, st>>>(env->V, env->enc_args, env->d_compact, obs_dev, env->d_enc_work);
     CU(cudaGetLastError());
     env->launches += 2;
     return MJX_OK;
