@@ -78,11 +78,21 @@ __global__ void k_init_tables(TableState* tabs, int n, const u64* nonces, const 
 // Observation encoder, stage 1: one warp = one feature group (ENC_N_PARTS row ranges) of one decision row. Stage the
 // table record, derive that part of the compact form (row masks + value rows, csrc/mjx_obs.cuh) in shared memory,
 // copy it out coalesced (10,944 B per row for v4). Items are ordered part-major: neighbouring warps run the same code.
+// largest per-part window of the compact form (mask rows * 8 + value rows * 136 bytes): what one warp stages
+constexpr int enc_max_window_bytes(int ver) {
+    const ObsLayout L = make_layout(ver);
+    int best = 0;
+    for (int q = 0; q < ENC_N_PARTS; q++) {
+        const int b = (L.part_row[q + 1] - L.part_row[q]) * 8 + (L.part_sv[q + 1] - L.part_sv[q]) * OBS_COLS * 4;
+        if (b > best) best = b;
+    }
+    return best;
+}
 template <int VER> struct EncF {
     static constexpr int COMPACT = enc_compact_bytes(VER);
-    static constexpr int COMPACT_PAD = (COMPACT + 15) & ~15;                       // the staged record wants 16-byte alignment
-    static constexpr int WARP_BYTES = COMPACT_PAD + (int)sizeof(TableState) + 48;  // + record + dora factors
-    static constexpr int WARPS = 232448 / WARP_BYTES >= 16 ? 16 : 232448 / WARP_BYTES;  // one CTA per SM
+    static constexpr int WINDOW_PAD = (enc_max_window_bytes(VER) + 15) & ~15;          // the staged record wants 16-byte alignment
+    static constexpr int WARP_BYTES = WINDOW_PAD + (int)sizeof(TableState) + 48;        // + record + dora factors
+    static constexpr int WARPS = 232448 / WARP_BYTES >= 20 ? 20 : 232448 / WARP_BYTES;  // one CTA per SM, register-limited
     static constexpr size_t SMEM = (size_t)WARPS * WARP_BYTES;
     static_assert(COMPACT % 8 == 0 && WARP_BYTES % 16 == 0, "vector copies");
 };
@@ -94,10 +104,9 @@ __global__ void __launch_bounds__(EncF<VER>::WARPS * 32, 1) k_encode_features(En
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* base = s_raw + (size_t)warp * EncF<VER>::WARP_BYTES;
-    u64* bm = reinterpret_cast<u64*>(base);
-    float* sv = reinterpret_cast<float*>(base + L.bm_rows * 8);
-    TableState* s_state = reinterpret_cast<TableState*>(base + EncF<VER>::COMPACT_PAD);
-    u8* df = base + EncF<VER>::COMPACT_PAD + sizeof(TableState);
+    u64* win = reinterpret_cast<u64*>(base);  // this part's window: its mask rows, then its value rows
+    TableState* s_state = reinterpret_cast<TableState*>(base + EncF<VER>::WINDOW_PAD);
+    u8* df = base + EncF<VER>::WINDOW_PAD + sizeof(TableState);
     const int n_rows = *V.n_rows;
     const int n_items = n_rows * ENC_N_PARTS;
     // Items are handed out dynamically, longest first: the action block (part 3: discard candidates, unconditional-tenpai
@@ -111,19 +120,19 @@ __global__ void __launch_bounds__(EncF<VER>::WARPS * 32, 1) k_encode_features(En
         const int ord = item / n_rows, row = item - ord * n_rows;
         const int part = ord == 0 ? 3 : ord == 1 ? 1 : ord == 2 ? 2 : 0;
         // this part's window of the compact form, in 8-byte words (mask rows, then the value rows as 17 words each)
-        int bm_lo = 0, bm_hi = 0, sv_lo = 0, sv_hi = 0;
+        int bm_lo = 0, bm_hi = 0, slot_lo = 0, slot_hi = 0;
 #pragma unroll
         for (int q = 0; q < ENC_N_PARTS; q++)
-            if (q == part) {
-                bm_lo = L.part_row[q]; bm_hi = L.part_row[q + 1];
-                sv_lo = L.bm_rows + L.part_sv[q] * 17; sv_hi = L.bm_rows + L.part_sv[q + 1] * 17;
-            }
+            if (q == part) { bm_lo = L.part_row[q]; bm_hi = L.part_row[q + 1]; slot_lo = L.part_sv[q]; slot_hi = L.part_sv[q + 1]; }
+        const int n_bm = bm_hi - bm_lo, n_win = n_bm + (slot_hi - slot_lo) * 17;  // window size in 8-byte words
+        // biased pointers: bm[row] / sv[slot * 34 + col] address the window for the rows / slots of this part
+        u64* bm = win - bm_lo;
+        float* sv = reinterpret_cast<float*>(win + n_bm) - slot_lo * OBS_COLS;
         {
             const uint4* src = reinterpret_cast<const uint4*>(V.tables + V.row_table[row]);
             uint4* dst = reinterpret_cast<uint4*>(s_state);
             for (int i = lane; i < (int)(sizeof(TableState) / 16); i += 32) dst[i] = __ldg(src + i);
-            for (int i = bm_lo + lane; i < bm_hi; i += 32) bm[i] = 0;
-            for (int i = sv_lo + lane; i < sv_hi; i += 32) bm[i] = 0;
+            for (int i = lane; i < n_win; i += 32) win[i] = 0;
         }
         __syncwarp();
         const TableState* S = s_state;
@@ -149,8 +158,8 @@ __global__ void __launch_bounds__(EncF<VER>::WARPS * 32, 1) k_encode_features(En
         encode_obs<VER>(e, c, nullptr);
         __syncwarp();
         u64* out = reinterpret_cast<u64*>(compact + (size_t)row * COMPACT);
-        for (int i = bm_lo + lane; i < bm_hi; i += 32) out[i] = bm[i];
-        for (int i = sv_lo + lane; i < sv_hi; i += 32) out[i] = bm[i];
+        for (int i = lane; i < n_bm; i += 32) out[bm_lo + i] = win[i];
+        for (int i = n_bm + lane; i < n_win; i += 32) out[L.bm_rows + slot_lo * 17 + (i - n_bm)] = win[i];
         __syncwarp();
     }
 }
