@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ..engine import DeviceEngine, HostProtocolEngine
+from ..engine import HostProtocolEngine
 from ..env import BatchEnv
 
 
