@@ -195,12 +195,22 @@ def run_ours(args):
     stats = {}
 
     # -------- loop A: with the network (the BASELINE config), HBM resident
-    def loop(env_actions, policy, n_warm, n_timed, time_encode=False):
+    def loop(env_actions, policy, n_warm, n_timed, time_encode=False, split_events=None):
         env, actions = env_actions
         obs = env.obs_buffer()
         enc_events = []
 
         def cycle(timed):
+            if timed and split_events is not None:  # where the step goes: env kernels vs policy (events only, no sync)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
+                env.step(actions)
+                env.encode_obs(obs)
+                ev[1].record()
+                r = policy(env, obs, actions)
+                ev[2].record()
+                split_events.append(ev)
+                return r
             env.step(actions)
             if timed and time_encode:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -241,7 +251,10 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ea = fresh_env()
-    a = loop(ea, nn_policy, W, K)
+    a_split = []
+    a = loop(ea, nn_policy, W, K, split_events=a_split)
+    a_env_ms = sum(e[0].elapsed_time(e[1]) for e in a_split) / K
+    a_nn_ms = sum(e[1].elapsed_time(e[2]) for e in a_split) / K
     ea[0].close()
     clocks = sampler.stop()
 
@@ -376,6 +389,9 @@ def run_ours(args):
                        "l2": "per-step obs output (~0.7 GB) exceeds the 126 MB L2, no explicit flush",
                        "sp_block": "rows 889-1011 (single-player tables) computed on device by the k_sp_* kernels",
                        "sp_arena_overflows": sp_overflows},
+            # the timed step split with CUDA events (rank 0): env kernels (k_step + encode + single-player block, whose cost
+            # depends on the positions the policy steers the tables into) and the policy network incl. the row-count sync
+            "step_breakdown_ms": {"env": a_env_ms, "policy_net": a_nn_ms},
             "env_only": {"value": b_units / (b_ms * 1e-3), "unit": "table-steps/s", "ms_per_step": b_ms / K,
                          "policy": "counter-based test policy kernel, no host sync",
                          "without_sp_block": {"value": b2["table_steps"] / (b2["ms"] * 1e-3), "ms_per_step": b2["ms"] / K}},

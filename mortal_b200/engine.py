@@ -92,15 +92,18 @@ class DeviceEngine:
 
 
 def sample_top_p(logits, p):
+    """Nucleus sampling over the last axis: draw from the smallest set of highest-probability actions whose mass reaches
+    `p` (engine.py:83-94 semantics: p >= 1 is plain categorical sampling, p <= 0 the argmax)."""
     if p >= 1:
         return torch.distributions.Categorical(logits=logits).sample()
     if p <= 0:
         return logits.argmax(-1)
-    probs = logits.softmax(-1)
-    srt, idx = probs.sort(-1, descending=True)
-    csum = srt.cumsum(-1)
-    srt = srt.masked_fill(csum - srt > p, 0.0)
-    return idx.gather(-1, srt.multinomial(1)).squeeze(-1)
+    order = logits.argsort(-1, descending=True)
+    mass = logits.gather(-1, order).softmax(-1)
+    before = mass.cumsum(-1) - mass               # probability mass ranked strictly above each action
+    nucleus = torch.where(before <= p, mass, torch.zeros_like(mass))
+    pick = nucleus.multinomial(1)                 # multinomial renormalises the kept mass itself
+    return order.gather(-1, pick).squeeze(-1)
 
 
 class HostProtocolEngine:
