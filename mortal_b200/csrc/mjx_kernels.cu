@@ -236,7 +236,7 @@ __global__ void k_sp_begin(SpGlobal G) {
     if (threadIdx.x < SP_SLOTS) G.slot_count[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         if (G.counters[2]) G.counters[3] += 1;  // an overflow happened in the previous step
-        G.counters[0] = 0; G.counters[1] = 0; G.counters[2] = 0;
+        G.counters[0] = 0; G.counters[1] = 0; G.counters[2] = 0; G.counters[6] = 0; G.counters[7] = 0;
     }
 }
 
@@ -259,7 +259,21 @@ __global__ void __launch_bounds__(SP_WARPS * 32, 4) k_sp_expand(SpGlobal G, Tabl
     SP_KERNEL_PROLOGUE
     const int n = min(G.slot_count[slot], G.slot_cap);
     const i32* list = G.slot_list + (size_t)slot * G.slot_cap;
-    for (int i = gwarp; i < n; i += nwarps) sp_expand(s, c, list[i], slot);
+    if (lane == 0) {
+        SpWarpScratch& ws = s_ws[warp];
+        ws.a_node = ws.a_node_end = ws.a_pos = ws.a_pos_end = ws.a_edge = ws.a_edge_end = 0;
+        ws.created = ws.created_edges = 0;
+    }
+    __syncwarp();
+    for (int i = gwarp; i < n; i += nwarps) {
+        const int node = list[i];
+        if (node >= 0) sp_expand(s, c, node, slot);  // negative = hole (unused tail of a reserved chunk)
+    }
+    __syncwarp();
+    if (lane == 0) {  // statistics: states / edges actually created (the allocation counters include chunk tails)
+        if (s_ws[warp].created) atomicAdd(&G.counters[6], s_ws[warp].created);
+        if (s_ws[warp].created_edges) atomicAdd(&G.counters[7], s_ws[warp].created_edges);
+    }
 }
 
 // KIND 0: D-state (per-turn best discard), 1: W-state above tenpai, 2: tenpai W-state (scores the winning draws)
@@ -270,7 +284,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32, KIND == 2 ? 3 : (KIND == 1 ? 4 
     const i32* list = G.slot_list + (size_t)slot * G.slot_cap;
     const int k = sp_slot_shanten(slot);
     if (KIND == 0) {
-        for (int i = gwarp; i < n; i += nwarps) sp_eval_d(s, c, list[i]);
+        for (int i = gwarp; i < n; i += nwarps) if (list[i] >= 0) sp_eval_d(s, c, list[i]);
     } else {
         // two W-states per warp, one per half-warp (csrc/mjx_sp.cuh sp_eval_w2)
         __shared__ SpEvalScratch s_es[SP_WARPS];
@@ -732,11 +746,11 @@ int mjx_env_sp_overflows(mjx_env* env, void* stream, int* n) {
 
 int mjx_env_sp_stats(mjx_env* env, void* stream, int* out10) {
     if (!env || !out10) return fail(MJX_ERR_ARG, "mjx_env_sp_stats: bad arguments");
-    int cnt[2] = {0, 0};
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(cnt, env->sp.counters, sizeof cnt, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaMemcpyAsync(out10 + 2, env->sp.slot_count, SP_SLOTS * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    out10[0] = cnt[0]; out10[1] = cnt[1];
+    out10[0] = cnt[6]; out10[1] = cnt[7];  // states / edges actually created; out[2..9] are work-list lengths incl. holes
     return MJX_OK;
 }
 

@@ -23,6 +23,9 @@
 
 namespace mjx {
 
+constexpr int SP_NODE_CHUNK = 16;   // state indices / work-list positions reserved per global atomic
+constexpr int SP_EDGE_CHUNK = 128;  // edge slots reserved per global atomic
+constexpr u32 SP_NO_OWNER = 0xFFFFFFFFu;  // edge_owner of a reserved-but-unused edge slot
 constexpr int SP_T_MAX = 17;             // sp/mod.rs:42 MAX_TSUMOS_LEFT
 constexpr int SP_SHANTEN_THRES = 3;      // calc.rs:13
 constexpr int SP_MAX_TILES_LEFT = 34 * 4 - 1 - 13;  // calc.rs:14
@@ -158,6 +161,10 @@ struct SpWarpScratch {
     u8 df[34];
     u8 pad_[2];
     i32 ed_n, ed_begin;
+    // warp-private allocation chunks (device): indices are taken from the global counters SP_*_CHUNK at a time, so the
+    // three hot counters see ~1/16 .. 1/128 of the atomics (same-address L2 atomics serialise, B300 guide 'Atomics')
+    i32 a_node, a_node_end, a_pos, a_pos_end, a_edge, a_edge_end;
+    i32 fill_from, fill_n, efill_from, efill_n, created, created_edges, bc_node, bc_pos;
 };
 
 struct SpCtx {
@@ -219,6 +226,7 @@ MJX_DN int sp_new_node(SpCtx& s, int row, const SpKey& key, const SpSig& sig, in
 #else
     int idx = atomicAdd(&s.G.counters[0], 1);
     int pos = atomicAdd(&s.G.slot_count[slot], 1);
+    atomicAdd(&s.G.counters[6], 1);  // states actually created (counters[0] also counts abandoned chunk tails)
 #endif
     if (idx >= s.G.node_cap || pos >= s.G.slot_cap) { sp_set_overflow(s); return -1; }
     sp_key_copy(&s.G.keys[idx], &key);
@@ -272,6 +280,76 @@ MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, const SpSig& sig, int 
     sp_set_overflow(s);
     return -1;
 }
+
+#ifndef MJX_HOST_EMUL
+// Device interning in two phases so that new states are allocated per warp, not per lane.
+// Phase 1: read-only probe. Returns the state's index, or -1 with `h` left at the first empty hash slot seen.
+MJX_DN int sp_lookup(const SpCtx& s, int row, const SpKey& key, u32 hv, u32& h) {
+    const u32 mask = (u32)s.G.hash_cap - 1;
+    const u32 tag = (hv >> 24) << 24;
+    h = hv & mask;
+    for (int probe = 0; probe < s.G.hash_cap; probe++, h = (h + 1) & mask) {
+        const u32 cur = __ldcg(&s.G.hash[h]);
+        if (cur == 0) return -1;
+        if ((cur & 0xFF000000u) != tag) continue;
+        const int ci = (int)(cur & 0x00FFFFFFu) - 1;
+        if (sp_ld_row(s.G.node_row + ci) == row && sp_key_eq(s.G.keys[ci], key)) return ci;
+    }
+    return -1;
+}
+// Phase 2: publish the already written state `mine` starting at hash slot `h`. If another warp published the same
+// state in the meantime its index is returned and `lost` is set (ours becomes a hole in the work list).
+MJX_DN int sp_publish(SpCtx& s, int row, const SpKey& key, u32 hv, u32 h, int mine, bool& lost) {
+    const u32 mask = (u32)s.G.hash_cap - 1;
+    const u32 tag = (hv >> 24) << 24;
+    lost = false;
+    for (int probe = 0; probe < s.G.hash_cap; probe++, h = (h + 1) & mask) {
+        u32 cur = __ldcg(&s.G.hash[h]);
+        if (cur == 0) {
+            const u32 prev = atomicCAS(&s.G.hash[h], 0u, ((u32)mine + 1) | tag);
+            if (prev == 0) return mine;
+            cur = prev;
+        }
+        if ((cur & 0xFF000000u) != tag) continue;
+        const int ci = (int)(cur & 0x00FFFFFFu) - 1;
+        if (sp_ld_row(s.G.node_row + ci) == row && sp_key_eq(s.G.keys[ci], key)) { lost = true; return ci; }
+    }
+    sp_set_overflow(s);
+    lost = true;
+    return -1;
+}
+// Warp-collective: reserve `count` consecutive state indices and work-list positions of `slot` from the warp's chunks,
+// refilling a chunk from its global counter when it runs short (the abandoned remainder stays a run of holes: the
+// positions were pre-filled with -1 when the chunk was taken). Returns false on arena overflow.
+MJX_DN bool sp_reserve(SpCtx& s, int slot, int count, int& node_base, int& pos_base) {
+    SpWarpScratch& ws = *s.ws;
+    __syncwarp();
+    if (s.lane == 0) {
+        if (ws.a_node_end - ws.a_node < count) {
+            const int n = max(SP_NODE_CHUNK, count);
+            ws.a_node = atomicAdd(&s.G.counters[0], n);
+            ws.a_node_end = ws.a_node + n;
+        }
+        ws.fill_n = 0;
+        if (ws.a_pos_end - ws.a_pos < count) {
+            const int n = max(SP_NODE_CHUNK, count);
+            ws.a_pos = atomicAdd(&s.G.slot_count[slot], n);
+            ws.a_pos_end = ws.a_pos + n;
+            ws.fill_from = ws.a_pos; ws.fill_n = n;
+        }
+        ws.bc_node = ws.a_node; ws.bc_pos = ws.a_pos;
+        ws.a_node += count; ws.a_pos += count;
+    }
+    __syncwarp();
+    node_base = ws.bc_node; pos_base = ws.bc_pos;
+    const int ff = ws.fill_from, fn = ws.fill_n;
+    i32* list = s.G.slot_list + (size_t)slot * s.G.slot_cap;
+    for (int i = s.lane; i < fn; i += 32) if (ff + i < s.G.slot_cap) list[ff + i] = -1;
+    __syncwarp();
+    if (node_base + count > s.G.node_cap || pos_base + count > s.G.slot_cap) { sp_set_overflow(s); return false; }
+    return true;
+}
+#endif
 
 MJX_HD bool sp_slot_is_w(int slot) { return (slot & 1) != 0; }
 MJX_HD int sp_slot_shanten(int slot) { return 3 - (slot >> 1); }
@@ -355,7 +433,16 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
 #ifdef MJX_HOST_EMUL
         int eb = s.G.counters[1]; s.G.counters[1] += ne;
 #else
-        int eb = atomicAdd(&s.G.counters[1], ne);
+        ws.efill_n = 0;
+        if (ws.a_edge_end - ws.a_edge < ne) {  // take a new chunk of edge slots; the remainder of the old one stays unused
+            const int n = max(SP_EDGE_CHUNK, ne);
+            ws.a_edge = atomicAdd(&s.G.counters[1], n);
+            ws.a_edge_end = ws.a_edge + n;
+            ws.efill_from = ws.a_edge; ws.efill_n = n;
+        }
+        int eb = ws.a_edge;
+        ws.a_edge += ne;
+        ws.created_edges += ne;
 #endif
         if (eb + ne > s.G.edge_cap) { sp_set_overflow(s); ne = 0; eb = 0; }
         ws.ed_n = ne; ws.ed_begin = eb;
@@ -363,36 +450,97 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
         s.G.n_edges[node] = (u8)ne;
     }
     MJX_SYNCWARP();
+#ifndef MJX_HOST_EMUL
+    {   // unused edge slots of a fresh chunk must read as "no edge" for k_sp_score, which walks the edge range
+        const int ff = ws.efill_from, fn = ws.efill_n;
+        for (int i = s.lane; i < fn; i += 32) if (ff + i < s.G.edge_cap) s.G.edge_owner[ff + i] = SP_NO_OWNER;
+        __syncwarp();
+    }
+#endif
     // one edge per lane: build the child state (key, signatures, hash: all incremental) and intern it
     const int ne = ws.ed_n, eb = ws.ed_begin;
-    SP_FOR_LANES(e, ne) {
+    auto child_of = [&](int e, SpKey& ck, SpSig& cs) {
         const int tile = ws.ed_tile[e], t = deaka(tile);
         const int suit5 = is_aka(tile) ? tile - T_5MR : -1;
+        sp_key_copy(&ck, &key);
+        const int c0 = key.tehai[t];
+        u32 h = sg.hash ^ sp_zob(0, t, c0);
+        if (is_w) {
+            ck.tehai[t] += 1;
+            ck.wall[t] -= 1;
+            if (suit5 >= 0) ck.akas = (u8)((ck.akas | (1 << suit5)) & ~(1 << (3 + suit5)));
+            h ^= sp_zob(0, t, c0 + 1) ^ sp_zob(1, t, key.wall[t]) ^ sp_zob(1, t, key.wall[t] - 1);
+        } else {
+            ck.tehai[t] -= 1;
+            if (suit5 >= 0) ck.akas = (u8)(ck.akas & ~(1 << suit5));
+            h ^= sp_zob(0, t, c0 - 1);
+        }
+        if (ck.akas != key.akas) h ^= sp_zob(2, 0, key.akas) ^ sp_zob(2, 0, ck.akas);
+        cs = sp_sig_make(sig_variant(base, t, is_w ? +1 : -1, c0), h);
+    };
+#ifdef MJX_HOST_EMUL
+    for (int e = 0; e < ne; e++) {
         u32 child = SP_NO_CHILD;
         if (!leaf) {
-            SpKey ck;
-            sp_key_copy(&ck, &key);
-            const int c0 = key.tehai[t];
-            u32 h = sg.hash ^ sp_zob(0, t, c0);
-            if (is_w) {
-                ck.tehai[t] += 1;
-                ck.wall[t] -= 1;
-                if (suit5 >= 0) ck.akas = (u8)((ck.akas | (1 << suit5)) & ~(1 << (3 + suit5)));
-                h ^= sp_zob(0, t, c0 + 1) ^ sp_zob(1, t, key.wall[t]) ^ sp_zob(1, t, key.wall[t] - 1);
-            } else {
-                ck.tehai[t] -= 1;
-                if (suit5 >= 0) ck.akas = (u8)(ck.akas & ~(1 << suit5));
-                h ^= sp_zob(0, t, c0 - 1);
-            }
-            if (ck.akas != key.akas) h ^= sp_zob(2, 0, key.akas) ^ sp_zob(2, 0, ck.akas);
-            const SpSig cs = sp_sig_make(sig_variant(base, t, is_w ? +1 : -1, c0), h);
+            SpKey ck; SpSig cs;
+            child_of(e, ck, cs);
             int ci = sp_intern(s, row, ck, cs, slot + 1);
             child = ci < 0 ? SP_NO_CHILD : (u32)ci;
         }
         s.G.edge_child[eb + e] = child;
-        s.G.edge_meta[eb + e] = (u16)(tile | (ws.ed_cnt[e] << 6));
+        s.G.edge_meta[eb + e] = (u16)(ws.ed_tile[e] | (ws.ed_cnt[e] << 6));
         s.G.edge_owner[eb + e] = (u32)node;
     }
+#else
+    for (int e0 = 0; e0 < ne; e0 += 32) {
+        const int e = e0 + s.lane;
+        const bool active = e < ne;
+        const int my_tile = active ? ws.ed_tile[e] : 0, my_cnt = active ? ws.ed_cnt[e] : 0;
+        u32 child = SP_NO_CHILD;
+        if (!leaf) {
+            SpKey ck; SpSig cs;
+            u32 hv = 0, h = 0;
+            int found = -1;
+            if (active) {
+                child_of(e, ck, cs);
+                hv = sp_hash_key(row, cs.hash);
+                found = sp_lookup(s, row, ck, hv, h);
+            }
+            const bool need = active && found < 0;
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (m) {
+                int node_base = 0, pos_base = 0;
+                const bool ok = sp_reserve(s, slot + 1, __popc(m), node_base, pos_base);
+                if (need && ok) {
+                    const int rank = __popc(m & ((1u << s.lane) - 1));
+                    const int idx = node_base + rank, pos = pos_base + rank;
+                    sp_key_copy(&s.G.keys[idx], &ck);
+                    {
+                        const u64* a = reinterpret_cast<const u64*>(&cs);
+                        u64* b = reinterpret_cast<u64*>(&s.G.sigs[idx]);
+                        b[0] = a[0]; b[1] = a[1]; b[2] = a[2];
+                    }
+                    s.G.node_row[idx] = row;
+                    s.G.n_edges[idx] = 0;
+                    s.G.edge_begin[idx] = 0;
+                    i32* list = s.G.slot_list + (size_t)(slot + 1) * s.G.slot_cap;
+                    list[pos] = idx;
+                    __threadfence();
+                    bool lost;
+                    found = sp_publish(s, row, ck, hv, h, idx, lost);
+                    if (lost) list[pos] = -1;
+                }
+                if (s.lane == 0) ws.created += __popc(m);
+            }
+            child = found < 0 ? SP_NO_CHILD : (u32)found;
+        }
+        if (active) {
+            s.G.edge_child[eb + e] = child;
+            s.G.edge_meta[eb + e] = (u16)(my_tile | (my_cnt << 6));
+            s.G.edge_owner[eb + e] = (u32)node;
+        }
+    }
+#endif
     MJX_SYNCWARP();
 }
 
@@ -465,6 +613,7 @@ MJX_DN bool sp_get_score(const SpCtx& s, const SpRow& P, const SpKey& key, int w
 // stage: score every winning draw of every tenpai state, ONE THREAD PER DRAW (calc.rs:478-479 get_score).
 // Full lane utilisation for the branchy agari evaluation; the per-turn accumulation happens in sp_eval_w<true>.
 MJX_DN void sp_score_edge(const SpCtx& s, int e) {
+    if (s.G.edge_owner[e] == SP_NO_OWNER) return;  // reserved but unused edge slot
     const int node = (int)s.G.edge_owner[e];
     const SpRow& P = s.G.rows[s.G.node_row[node]];
     float sc[4];
@@ -473,6 +622,7 @@ MJX_DN void sp_score_edge(const SpCtx& s, int e) {
     sp_key_copy(&key, &s.G.keys[node]);
     const bool ok = sp_get_score(s, P, key, m & 63, sc);
     const int le = e - s.G.counters[4];
+    if (le >= s.G.score_cap) s.G.counters[2] = 1;  // score arena too small for this step: reported as an overflow
     if (!ok) s.G.edge_meta[e] = (u16)(m | 0x8000);
     else if (le >= 0 && le < s.G.score_cap) {
         float* o = s.G.leaf_scores + (size_t)le * 4;
