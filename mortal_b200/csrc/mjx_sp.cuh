@@ -435,7 +435,8 @@ MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
 #else
         ws.efill_n = 0;
         if (ws.a_edge_end - ws.a_edge < ne) {  // take a new chunk of edge slots; the remainder of the old one stays unused
-            const int n = max(SP_EDGE_CHUNK, ne);
+            // the tenpai level's edge range is walked edge by edge by k_sp_score: keep its unused tails short
+            const int n = max(leaf ? 32 : SP_EDGE_CHUNK, ne);
             ws.a_edge = atomicAdd(&s.G.counters[1], n);
             ws.a_edge_end = ws.a_edge + n;
             ws.efill_from = ws.a_edge; ws.efill_n = n;
