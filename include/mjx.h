@@ -88,6 +88,20 @@ int mjx_env_total_steps(mjx_env* env, void* stream, int64_t* steps);    /* game.
 int mjx_env_enable_log(mjx_env* env, int words_per_table);
 int mjx_env_read_log(mjx_env* env, void* stream, uint64_t* words_host, int32_t* len_host);
 
+/* ---- log replay: dataset/gameplay.rs:247-449 GameplayLoader ------------------------------------------
+ * A job = one (game log, player). `hdr`: the games' events as 64-bit words (csrc/mjx_step.cuh `log_word`; start_game = 15,
+ * end_game = 16), concatenated, job j owning ev_cnt[j] words from ev_off[j]; `kyoku`: 9 words per start_kyoku (scores, haipai),
+ * job j's first payload at index ky_off[j]; `players`: the job's point of view. All host arrays. Full-information logs only.
+ * mjx_env_replay_step advances every job to the next decision the log shows its player making and emits the row(s)
+ * (decision, then kan-select); observation / mask / row_table / row_seat are read exactly as after mjx_env_step, plus the
+ * label and (at_kyoku, at_turn, shanten, apply_gamma) of each row. A job is finished when mjx_env_num_live stops counting it. */
+int mjx_env_create_replay(mjx_env** out, int n_jobs, const uint64_t* hdr, const int32_t* ev_off, const int32_t* ev_cnt, long long n_hdr,
+                          const uint64_t* kyoku, const int32_t* ky_off, long long n_kyoku_words, const uint8_t* players,
+                          int obs_version, int always_include_kan_select);
+int mjx_env_replay_step(mjx_env* env, void* stream);
+int64_t* mjx_env_row_label(mjx_env* env); /* int64 [row_cap] device */
+uint8_t* mjx_env_row_meta(mjx_env* env);  /* uint8 [row_cap, 4] device: at_kyoku, at_turn, shanten (int8), apply_gamma */
+
 /* Number of kernels this library has launched for env so far (host-side counter; bench.py's gpu_launches). */
 long long mjx_env_launch_count(mjx_env* env);
 

@@ -7,6 +7,6 @@ host layer that mirrors libriichi's Python surface. There is no CPU implementati
 package: importing works anywhere, but every compute call requires the CUDA library and a GPU.
 """
 from ._lib import MjxError, lib_path, load  # noqa: F401
-from .env import BatchEnv  # noqa: F401
+from .env import BatchEnv, ReplayEnv  # noqa: F401
 
-__all__ = ["BatchEnv", "MjxError", "load", "lib_path"]
+__all__ = ["BatchEnv", "ReplayEnv", "MjxError", "load", "lib_path"]

@@ -52,6 +52,11 @@ SYMBOLS = {
     "mjx_nn_affine_mish_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "mjx_nn_pool_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mjx_nn_gate_residual_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mjx_env_create_replay": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
+                                        C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int]),
+    "mjx_env_replay_step": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mjx_env_row_label": (C.c_void_p, [C.c_void_p]),
+    "mjx_env_row_meta": (C.c_void_p, [C.c_void_p]),
     "mjx_env_launch_count": (C.c_longlong, [C.c_void_p]),
     "mjx_env_num_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "mjx_env_num_live": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),

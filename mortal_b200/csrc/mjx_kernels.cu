@@ -8,6 +8,7 @@
 #include "../../include/mjx.h"
 #include "mjx_sp.cuh"
 #include "mjx_policy.cuh"
+#include "mjx_replay.cuh"
 #include "mjx_nn.cuh"
 #include "mjx_tables_host.h"
 
@@ -46,6 +47,33 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(EnvView V, Tables T) {
         atomicAdd(&V.counters[0], 1ull);
         atomicAdd(&V.counters[1], 1ull);
     }
+}
+
+// Log replay (csrc/mjx_replay.cuh): one warp = one (game log, player) job, advanced to its next logged decision.
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_replay_step(EnvView V, ReplayView R, Tables T) {
+    __shared__ __align__(16) unsigned char s_tab[STEP_WARPS][sizeof(TableState)];
+    __shared__ WarpScratch s_scratch[STEP_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int job = blockIdx.x * STEP_WARPS + warp;
+    if (job >= V.n_tables) return;
+    TableState* g = V.tables + job;
+    if (!(g->gflags & GF_ALIVE)) return;
+    constexpr int NV = sizeof(TableState) / 16;
+    uint4* dst = reinterpret_cast<uint4*>(s_tab[warp]);
+    const uint4* src = reinterpret_cast<const uint4*>(g);
+    for (int i = lane; i < NV; i += 32) dst[i] = src[i];
+    __syncwarp();
+    Ctx c;
+    c.S = reinterpret_cast<TableState*>(s_tab[warp]);
+    c.W = &s_scratch[warp];
+    c.T = T;
+    c.lane = lane;
+    c.df = s_scratch[warp].dora_factor;
+    const bool live = replay_table(c, V, R, job);
+    __syncwarp();
+    uint4* gdst = reinterpret_cast<uint4*>(g);
+    for (int i = lane; i < NV; i += 32) gdst[i] = dst[i];
+    if (lane == 0 && live) atomicAdd(&V.counters[0], 1ull);
 }
 
 __global__ void k_begin_step(EnvView V) {
@@ -430,6 +458,8 @@ struct mjx_env {
     SpGlobal sp;
     int sp_enabled = 1;
     unsigned char* d_compact = nullptr;
+    ReplayView R{};  // replay mode (mjx_env_create_replay): device arrays of the jobs
+    bool replay = false;
     int* d_enc_work = nullptr;  // k_encode_features' dynamic work counter
     EncStoreArgs enc_args{};
     cudaStream_t copy_stream = nullptr;  // mjx_env_encode_obs_host: D2H overlapped with the SP kernels
@@ -592,7 +622,12 @@ void mjx_env_destroy(mjx_env* env) {
     EnvView& V = env->V;
     cudaFree(V.tables); cudaFree(V.n_rows); cudaFree(V.row_table); cudaFree(V.row_seat); cudaFree(V.row_step);
     cudaFree(V.masks); cudaFree(V.scores); cudaFree(V.ranks); cudaFree(V.done); cudaFree(V.steps); cudaFree(V.err);
-    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); cudaFree(env->d_guard); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len);
+    cudaFree(V.counters); cudaFree(env->d_nonces); cudaFree(env->d_keys); cudaFree(env->d_dummy_actions); if (env->replay) {
+        ReplayView& R = env->R;
+        cudaFree((void*)R.hdr); cudaFree((void*)R.kyoku); cudaFree((void*)R.ev_off); cudaFree((void*)R.ev_cnt); cudaFree((void*)R.ky_off);
+        cudaFree((void*)R.player); cudaFree(R.pos); cudaFree(R.ky_idx); cudaFree(R.ky_seen); cudaFree(R.row_label); cudaFree(R.row_meta);
+    }
+    cudaFree(env->d_guard); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len);
     SpGlobal& G = env->sp;
     cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.sigs); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
     cudaFree(G.edge_child); cudaFree(G.edge_meta); cudaFree(G.edge_owner); cudaFree(G.leaf_scores); cudaFree(G.hash); cudaFree(G.slot_list); cudaFree(G.slot_count);
@@ -726,6 +761,59 @@ int mjx_env_read_log(mjx_env* env, void* stream, uint64_t* words_host, int32_t* 
     CU(cudaMemcpy(words_host, env->V.log, (size_t)env->n_tables * (size_t)env->V.log_cap * sizeof(u64), cudaMemcpyDeviceToHost));
     return MJX_OK;
 }
+
+int mjx_env_create_replay(mjx_env** out, int n_jobs, const uint64_t* hdr, const int32_t* ev_off, const int32_t* ev_cnt, long long n_hdr,
+                          const uint64_t* kyoku, const int32_t* ky_off, long long n_kyoku_words, const uint8_t* players,
+                          int obs_version, int always_include_kan_select) {
+    if (!out || n_jobs <= 0 || !hdr || !ev_off || !ev_cnt || !ky_off || !players || n_hdr <= 0)
+        return fail(MJX_ERR_ARG, "mjx_env_create_replay: bad arguments");
+    std::vector<uint64_t> zeros((size_t)n_jobs, 0);
+    int rc = mjx_env_create(out, n_jobs, zeros.data(), zeros.data(), obs_version, 0, 0);
+    if (rc) return rc;
+    mjx_env* env = *out;
+    env->replay = true;
+    ReplayView& R = env->R;
+    const size_t cap = (size_t)env->row_cap;
+    u64 *d_hdr = nullptr, *d_ky = nullptr;
+    i32 *d_off = nullptr, *d_cnt = nullptr, *d_kyoff = nullptr;
+    u8* d_pl = nullptr;
+    CU(cudaMalloc(&d_hdr, sizeof(u64) * (size_t)n_hdr));
+    CU(cudaMalloc(&d_ky, sizeof(u64) * (size_t)(n_kyoku_words > 0 ? n_kyoku_words : 1)));
+    CU(cudaMalloc(&d_off, sizeof(i32) * (size_t)n_jobs));
+    CU(cudaMalloc(&d_cnt, sizeof(i32) * (size_t)n_jobs));
+    CU(cudaMalloc(&d_kyoff, sizeof(i32) * (size_t)n_jobs));
+    CU(cudaMalloc(&d_pl, (size_t)n_jobs));
+    CU(cudaMalloc(&R.pos, sizeof(i32) * (size_t)n_jobs));
+    CU(cudaMalloc(&R.ky_idx, sizeof(i32) * (size_t)n_jobs));
+    CU(cudaMalloc(&R.ky_seen, sizeof(i32) * (size_t)n_jobs));
+    CU(cudaMalloc(&R.row_label, sizeof(i64) * cap));
+    CU(cudaMalloc(&R.row_meta, cap * 4));
+    CU(cudaMemcpy(d_hdr, hdr, sizeof(u64) * (size_t)n_hdr, cudaMemcpyHostToDevice));
+    if (n_kyoku_words > 0) CU(cudaMemcpy(d_ky, kyoku, sizeof(u64) * (size_t)n_kyoku_words, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_off, ev_off, sizeof(i32) * (size_t)n_jobs, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_cnt, ev_cnt, sizeof(i32) * (size_t)n_jobs, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_kyoff, ky_off, sizeof(i32) * (size_t)n_jobs, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_pl, players, (size_t)n_jobs, cudaMemcpyHostToDevice));
+    CU(cudaMemset(R.pos, 0, sizeof(i32) * (size_t)n_jobs));
+    CU(cudaMemset(R.ky_idx, 0, sizeof(i32) * (size_t)n_jobs));
+    CU(cudaMemset(R.ky_seen, 0, sizeof(i32) * (size_t)n_jobs));
+    R.hdr = d_hdr; R.kyoku = d_ky; R.ev_off = d_off; R.ev_cnt = d_cnt; R.ky_off = d_kyoff; R.player = d_pl;
+    R.always_include_kan_select = always_include_kan_select ? 1 : 0;
+    return MJX_OK;
+}
+
+int mjx_env_replay_step(mjx_env* env, void* stream) {
+    if (!env || !env->replay) return fail(MJX_ERR_ARG, "mjx_env_replay_step: not a replay env");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_begin_step<<<1, 1, 0, st>>>(env->V);
+    k_replay_step<<<(env->n_tables + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32, 0, st>>>(env->V, env->R, g_T);
+    CU(cudaGetLastError());
+    env->launches += 2;
+    env->first = false;
+    return MJX_OK;
+}
+int64_t* mjx_env_row_label(mjx_env* env) { return env && env->replay ? (int64_t*)env->R.row_label : nullptr; }
+uint8_t* mjx_env_row_meta(mjx_env* env) { return env && env->replay ? env->R.row_meta : nullptr; }
 
 long long mjx_env_launch_count(mjx_env* env) { return env ? env->launches : -1; }
 

@@ -1,0 +1,148 @@
+"""libriichi.dataset.GameplayLoader on the CUDA environment.
+
+Mirror of dataset/gameplay.rs:24-45, 80-218: `GameplayLoader(version, *, oracle, player_names, excludes, trust_seed,
+always_include_kan_select, augmented)`, `.load_gz_log_files(filenames) -> list[list[Gameplay]]`, `.load_log(text)`;
+`Gameplay.take_obs / take_actions / take_masks / take_at_kyoku / take_dones / take_apply_gamma / take_at_turns /
+take_shantens / take_player_id`. The logs are replayed on device (csrc/mjx_replay.cuh) and the observations come from the
+same encoder kernels self-play uses. Differences, stated rather than hidden: `take_obs()` / `take_masks()` return ONE tensor
+per Gameplay ([n_moves, C, 34] float32 / [n_moves, 46] bool, CUDA by default, `host=True` for numpy) instead of a list of
+per-move arrays; the oracle (invisible) observation, `Grp` and tile augmentation are not built (`oracle=True` /
+`augmented=True` / `take_grp` raise NotImplementedError); logs must carry full information (no "?" tiles).
+"""
+from __future__ import annotations
+
+import gzip
+
+import numpy as np
+
+from . import dataset_codec
+from .env import ReplayEnv
+
+
+class Gameplay:
+    def __init__(self, player_id: int, player_name: str, obs, actions, masks, at_kyoku, apply_gamma, at_turns, shantens):
+        self.player_id, self.player_name = player_id, player_name
+        self._obs, self._masks = obs, masks
+        self._actions, self._at_kyoku, self._apply_gamma = actions, at_kyoku, apply_gamma
+        self._at_turns, self._shantens = at_turns, shantens
+        # gameplay.rs:285-286: done wherever the next move belongs to a later kyoku, and at the last move
+        self._dones = np.append(at_kyoku[1:] > at_kyoku[:-1], True) if len(at_kyoku) else np.zeros(0, dtype=bool)
+
+    def take_obs(self, host: bool = False):
+        return self._obs.cpu().numpy() if host else self._obs
+
+    def take_masks(self, host: bool = False):
+        return self._masks.cpu().numpy() if host else self._masks
+
+    def take_invisible_obs(self):
+        raise NotImplementedError("oracle (invisible) observations are not built (SURVEY.md §8f N4)")
+
+    def take_grp(self):
+        raise NotImplementedError("Grp is not built (SURVEY.md §8f N3/N4)")
+
+    def take_actions(self):
+        return self._actions.tolist()
+
+    def take_at_kyoku(self):
+        return self._at_kyoku.tolist()
+
+    def take_dones(self):
+        return self._dones.tolist()
+
+    def take_apply_gamma(self):
+        return self._apply_gamma.tolist()
+
+    def take_at_turns(self):
+        return self._at_turns.tolist()
+
+    def take_shantens(self):
+        return self._shantens.tolist()
+
+    def take_player_id(self):
+        return self.player_id
+
+
+class GameplayLoader:
+    def __init__(self, version: int, *, oracle: bool = False, player_names=None, excludes=None, trust_seed: bool = False,
+                 always_include_kan_select: bool = True, augmented: bool = False, device: int = 0):
+        if oracle:
+            raise NotImplementedError("oracle (invisible) observations are not built (SURVEY.md §8f N4); pass oracle=False")
+        if augmented:
+            raise NotImplementedError("tile augmentation is not built")
+        self.version, self.oracle, self.trust_seed = version, oracle, trust_seed
+        self.player_names, self.excludes = list(player_names or []), list(excludes or [])
+        self.always_include_kan_select, self.augmented = always_include_kan_select, augmented
+        self.device = device
+
+    def _players(self, names):  # gameplay.rs:166-176
+        if self.player_names:
+            return [i for i, nm in enumerate(names) if nm in set(self.player_names)]
+        if self.excludes:
+            return [i for i, nm in enumerate(names) if nm not in set(self.excludes)]
+        return [0, 1, 2, 3]
+
+    def load_log(self, raw_log: str):
+        return self.load_logs([raw_log])[0]
+
+    def load_gz_log_files(self, gzip_filenames):
+        texts = []
+        for fn in gzip_filenames:
+            with gzip.open(fn, "rt") as f:
+                texts.append(f.read())
+        return self.load_logs(texts)
+
+    def load_logs(self, texts):
+        """list of log texts -> list (per log) of list (per selected player) of Gameplay; all logs replayed as one batch"""
+        import torch
+
+        games = [dataset_codec.parse_log(t) for t in texts]
+        for ev in games:
+            if not ev or ev[0].get("type") != "start_game" or len(ev) < 4:
+                raise ValueError("empty or invalid game log")
+        players = [self._players(ev[0].get("names", ["", "", "", ""])) for ev in games]
+        jobs = dataset_codec.build_jobs(games, players)
+        n_jobs = len(jobs["players"])
+        out = [[] for _ in games]
+        if n_jobs == 0:
+            return out
+        env = ReplayEnv(jobs, obs_version=self.version, always_include_kan_select=self.always_include_kan_select, device=self.device)
+        chunks = []  # per step: (job ids, obs, masks, labels, meta)
+        try:
+            while True:
+                env.replay_step()
+                nr = env.num_rows()
+                if nr:
+                    obs = env.encode_obs()[:nr]
+                    chunks.append((env.row_table[:nr].long().clone(), obs.clone(), env.masks[:nr].clone(),
+                                   env.row_label[:nr].clone(), env.row_meta[:nr].clone()))
+                if env.num_live() == 0:
+                    break
+            res = env.results()
+        finally:
+            env.close()
+        if (res["err"] != 0).any():
+            bad = int(np.nonzero(res["err"])[0][0])
+            raise RuntimeError(f"replay job {bad} (log {int(jobs['job_game'][bad])}, player {int(jobs['players'][bad])}) failed "
+                               f"with mjx error code {int(res['err'][bad])}: the log is inconsistent or not full-information")
+        if chunks:
+            job = torch.cat([c[0] for c in chunks]); obs = torch.cat([c[1] for c in chunks]); masks = torch.cat([c[2] for c in chunks])
+            label = torch.cat([c[3] for c in chunks]); meta = torch.cat([c[4] for c in chunks])
+            order = torch.sort(job, stable=True).indices  # moves of a job stay in emission order
+            job, obs, masks, label, meta = job[order], obs[order], masks[order], label[order].cpu().numpy(), meta[order].cpu().numpy()
+            counts = torch.bincount(job, minlength=n_jobs).cpu().numpy()
+        else:
+            counts = np.zeros(n_jobs, dtype=np.int64)
+        start = 0
+        for j in range(n_jobs):
+            n = int(counts[j]); sl = slice(start, start + n); start += n
+            g, pid = int(jobs["job_game"][j]), int(jobs["players"][j])
+            name = games[g][0].get("names", ["", "", "", ""])[pid]
+            if n:
+                gp = Gameplay(pid, name, obs[sl], label[sl], masks[sl], meta[sl, 0].copy(), meta[sl, 3].astype(bool),
+                              meta[sl, 1].copy(), meta[sl, 2].astype(np.int8))
+            else:
+                z = np.zeros(0, dtype=np.uint8)
+                gp = Gameplay(pid, name, torch.zeros((0, env.obs_rows, 34), device=obs.device if chunks else "cpu"), np.zeros(0, dtype=np.int64),
+                              torch.zeros((0, 46), dtype=torch.bool), z, z.astype(bool), z, z.astype(np.int8))
+            out[g].append(gp)
+        return out

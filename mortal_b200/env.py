@@ -43,8 +43,13 @@ class BatchEnv:
         _lib.check(self.L.mjx_env_create(C.byref(h), self.n_tables, nonces.ctypes.data, keys.ctypes.data, obs_version,
                                          shuffle_kind, int(enable_quick_eval)), "mjx_env_create")
         self._h = h
+        self._bind_views()
+
+    def _bind_views(self):
+        torch, h = self.torch, self._h
         self.row_cap = self.L.mjx_env_row_cap(h)
         as_t = lambda ptr, shape, ts: torch.as_tensor(_CudaView(ptr, shape, ts), device=self.device)
+        self._as_t = as_t
         self.masks = as_t(self.L.mjx_env_masks(h), (self.row_cap, 46), "|u1").view(torch.bool)
         self.row_table = as_t(self.L.mjx_env_row_table(h), (self.row_cap,), "<i4")
         self.row_seat = as_t(self.L.mjx_env_row_seat(h), (self.row_cap,), "|u1")
@@ -213,3 +218,35 @@ class BatchEnv:
         if trace:
             res["trace"] = np.concatenate(traces) if traces else np.zeros((0, 6), dtype=np.int64)
         return res
+
+
+class ReplayEnv(BatchEnv):
+    """Replay mode (include/mjx.h mjx_env_create_replay): jobs = (game log, player) pairs advanced from logged decision to
+    logged decision; the encoder API of BatchEnv applies unchanged. `jobs` comes from mortal_b200.dataset_codec.build_jobs."""
+
+    def __init__(self, jobs, *, obs_version: int = 4, always_include_kan_select: bool = True, device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise _lib.MjxError("mortal_b200.ReplayEnv needs a CUDA device (there is no CPU fallback)")
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        _lib.init(device)
+        self.L = _lib.load()
+        j = {k: np.ascontiguousarray(v) for k, v in jobs.items()}
+        self.n_tables = int(len(j["players"]))
+        self.obs_version = obs_version
+        self.obs_rows = self.L.mjx_obs_rows(obs_version)
+        h = C.c_void_p()
+        _lib.check(self.L.mjx_env_create_replay(C.byref(h), self.n_tables, j["hdr"].ctypes.data, j["ev_off"].ctypes.data,
+                                                j["ev_cnt"].ctypes.data, len(j["hdr"]), j["kyoku"].ctypes.data,
+                                                j["ky_off"].ctypes.data, len(j["kyoku"]), j["players"].ctypes.data, obs_version,
+                                                int(always_include_kan_select)), "mjx_env_create_replay")
+        self._h = h
+        self._bind_views()
+        self.row_label = self._as_t(self.L.mjx_env_row_label(h), (self.row_cap,), "<i8")
+        self.row_meta = self._as_t(self.L.mjx_env_row_meta(h), (self.row_cap, 4), "|u1")
+
+    def replay_step(self) -> None:
+        _lib.check(self.L.mjx_env_replay_step(self._h, self._stream()), "mjx_env_replay_step")

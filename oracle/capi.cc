@@ -563,4 +563,89 @@ uint64_t orc_policy_hash(uint64_t nonce, uint64_t key, uint64_t table, uint64_t 
     return policy_hash(nonce, key, table, step_idx, seat, kan);
 }
 
+// ---------------- dataset::GameplayLoader (dataset/gameplay.rs:247-449), SURVEY.md §8f N3 ----------------
+// Replays one game's events from one player's point of view and records, at every decision the log shows the player
+// making, the observation, legal mask and the label derived from the following events. Not restated: the oracle
+// (invisible) observation, Grp and tile augmentation.
+// Outputs are caller-allocated for `max_moves` entries; returns the number of moves (negative on error).
+int orc_gameplay_load(const orc_event* evs, int n_events, int player_id, int version, int always_include_kan_select, int sp_mode,
+                      int max_moves, float* obs /*[max_moves, rows, 34] or null*/, uint8_t* masks /*[max_moves, 46]*/,
+                      int64_t* actions, uint8_t* at_kyoku, uint8_t* apply_gamma, uint8_t* at_turns, int8_t* shantens) {
+    try {
+        PlayerState state((u8)player_id);
+        const int rows = obs_rows(version);
+        int kyoku_idx = 0, n = 0;
+        std::vector<Event> ev(n_events);
+        for (int i = 0; i < n_events; i++) ev[i] = from_c(evs[i]);
+        auto add_entry = [&](bool at_kan_select, int label) {  // gameplay.rs:425-447
+            if (n >= max_moves) throw OrcError("orc_gameplay_load: max_moves too small");
+            std::vector<float> tmp;
+            float* o = obs ? obs + (size_t)n * rows * 34 : nullptr;
+            if (!o) { tmp.resize((size_t)rows * 34); o = tmp.data(); }
+            state.encode_obs(version, at_kan_select, o, masks + (size_t)n * 46, sp_mode);
+            actions[n] = label;
+            at_kyoku[n] = (uint8_t)kyoku_idx;
+            apply_gamma[n] = label <= 37;
+            at_turns[n] = state.at_turn;
+            shantens[n] = state.shanten;
+            n++;
+        };
+        // gameplay.rs:279-283: windows of 4 events
+        for (int w = 0; w + 4 <= n_events; w++) {
+            const Event& cur = ev[w];
+            const Event& next = (ev[w + 1].type == EV_REACH_ACCEPTED || ev[w + 1].type == EV_DORA) ? ev[w + 2] : ev[w + 1];
+            if (cur.type == EV_END_KYOKU) kyoku_idx += 1;
+            const ActionCandidate cans = state.update(cur);
+            if (!cans.can_act()) continue;
+            int label = -1, kan_select = -1;
+            switch (next.type) {
+                case EV_DAHAI: label = next.pai; break;
+                case EV_REACH: label = 37; break;
+                case EV_CHI:
+                    if (next.actor == player_id) {
+                        const u8 a = deaka(next.consumed[0]), b = deaka(next.consumed[1]), t = deaka(next.pai);
+                        label = t < std::min(a, b) ? 38 : (t < std::max(a, b) ? 39 : 40);  // chi_type.rs:10-25
+                    }
+                    break;
+                case EV_PON: if (next.actor == player_id) label = 41; break;
+                case EV_DAIMINKAN:
+                    if (next.actor == player_id) { if (always_include_kan_select) kan_select = deaka(next.pai); label = 42; }
+                    break;
+                case EV_KAKAN:
+                    if (always_include_kan_select || state.kakan_candidates.size() > 1) kan_select = deaka(next.pai);
+                    label = 42;
+                    break;
+                case EV_ANKAN:
+                    if (always_include_kan_select || state.ankan_candidates.size() > 1) kan_select = deaka(next.consumed[0]);
+                    label = 42;
+                    break;
+                case EV_RYUKYOKU: if (cans.can_ryukyoku) label = 44; break;
+                default: break;
+            }
+            // the reference's match arms with guards fall through to the catch-all when the guard fails (gameplay.rs:349-416)
+            const bool guarded_miss = label < 0 && next.type != EV_DAHAI && next.type != EV_REACH && next.type != EV_KAKAN &&
+                                      next.type != EV_ANKAN;
+            if (guarded_miss) {
+                const bool has_any_ron = ev[w + 1].type == EV_HORA;
+                if (has_any_ron) {
+                    for (int k = w + 1; k < w + 4; k++) {
+                        if (ev[k].type == EV_END_KYOKU) break;
+                        if (ev[k].type == EV_HORA && ev[k].actor == player_id) { label = 43; break; }
+                    }
+                }
+                if (label < 0) {
+                    if ((cans.can_chi() && next.type == EV_TSUMO) ||
+                        ((cans.can_pon || cans.can_daiminkan || cans.can_ron_agari) && !has_any_ron))
+                        label = 45;
+                }
+            }
+            if (label >= 0) {
+                add_entry(false, label);
+                if (kan_select >= 0) add_entry(true, kan_select);
+            }
+        }
+        return n;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
 }  // extern "C"

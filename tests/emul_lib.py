@@ -42,6 +42,11 @@ def lib():
         L.emul_env_encode_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.emul_env_encode_obs_v.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.emul_sp_overflows.restype = C.c_long
+        L.emul_replay_create.restype = C.c_void_p
+        L.emul_replay_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int]
+        L.emul_replay_step.argtypes = [C.c_void_p]
+        L.emul_replay_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emul_env_errs.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_env_enable_log.argtypes = [C.c_void_p, C.c_int]
         L.emul_env_read_log.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_env_results.argtypes = [C.c_void_p] + [C.c_void_p] * 5
@@ -127,3 +132,32 @@ class EmulEnv:
         obs = np.zeros((self.num_rows(), rows, 34), dtype=np.float32)
         self.L.emul_env_encode_obs_v(self._h, obs.ctypes.data, int(sp), version)
         return obs
+
+
+class EmulReplay(EmulEnv):
+    """Host-emulated stand-in for the replay mode of mortal_b200.BatchEnv (mjx_env_create_replay / mjx_env_replay_step)."""
+
+    def __init__(self, jobs, always_include_kan_select=True):
+        self.L = lib()
+        self.jobs = {k: np.ascontiguousarray(v) for k, v in jobs.items()}
+        j = self.jobs
+        self.n_tables = len(j["players"])
+        self.row_cap = self.n_tables * 3
+        self._h = self.L.emul_replay_create(self.n_tables, j["hdr"].ctypes.data, j["ev_off"].ctypes.data, j["ev_cnt"].ctypes.data,
+                                            len(j["hdr"]), j["kyoku"].ctypes.data, j["ky_off"].ctypes.data, len(j["kyoku"]),
+                                            j["players"].ctypes.data, int(always_include_kan_select))
+        self.live = self.n_tables
+
+    def replay_step(self):
+        self.live = self.L.emul_replay_step(self._h)
+
+    def row_labels(self):
+        n = self.num_rows()
+        lab = np.zeros(max(n, 1), dtype=np.int64); meta = np.zeros((max(n, 1), 4), dtype=np.uint8)
+        self.L.emul_replay_rows(self._h, lab.ctypes.data, meta.ctypes.data)
+        return lab[:n], meta[:n]
+
+    def errs(self):
+        e = np.zeros(self.n_tables, dtype=np.int32)
+        self.L.emul_env_errs(self._h, e.ctypes.data)
+        return e

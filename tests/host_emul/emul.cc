@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "mjx_sp.cuh"
+#include "mjx_replay.cuh"
 #include "mjx_policy.cuh"
 #include "mjx_tables_host.h"
 
@@ -119,6 +120,10 @@ struct EmulEnv {
     EnvView V;
     bool first = true;
     std::vector<u64> log; std::vector<i32> log_len; int log_cap = 0;
+    // log replay (mjx_replay.cuh)
+    std::vector<u64> r_hdr, r_kyoku; std::vector<i32> r_ev_off, r_ev_cnt, r_ky_off, r_pos, r_ky_idx, r_ky_seen;
+    std::vector<u8> r_player, r_meta; std::vector<i64> r_label;
+    ReplayView R;
 };
 
 void* emul_env_create(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int quick_eval) {
@@ -163,6 +168,48 @@ int emul_env_step(void* p, const int64_t* actions) {
     }
     return live;
 }
+// ---- log replay: the stepping surface of mjx_env_create_replay / mjx_env_replay_step
+void* emul_env_create(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int quick_eval);
+void* emul_replay_create(int n_jobs, const uint64_t* hdr, const int32_t* ev_off, const int32_t* ev_cnt, long long n_hdr,
+                         const uint64_t* kyoku, const int32_t* ky_off, long long n_kyoku_words, const uint8_t* players,
+                         int always_include_kan_select) {
+    std::vector<uint64_t> zeros(n_jobs, 0);
+    EmulEnv* E = static_cast<EmulEnv*>(emul_env_create(n_jobs, zeros.data(), zeros.data(), 0, 0));
+    E->r_hdr.assign(hdr, hdr + n_hdr); E->r_kyoku.assign(kyoku, kyoku + n_kyoku_words);
+    E->r_ev_off.assign(ev_off, ev_off + n_jobs); E->r_ev_cnt.assign(ev_cnt, ev_cnt + n_jobs); E->r_ky_off.assign(ky_off, ky_off + n_jobs);
+    E->r_pos.assign(n_jobs, 0); E->r_ky_idx.assign(n_jobs, 0); E->r_ky_seen.assign(n_jobs, 0);
+    E->r_player.assign(players, players + n_jobs);
+    E->r_label.assign(E->cap, 0); E->r_meta.assign((size_t)E->cap * 4, 0);
+    ReplayView& R = E->R;
+    R.hdr = E->r_hdr.data(); R.ev_off = E->r_ev_off.data(); R.ev_cnt = E->r_ev_cnt.data(); R.kyoku = E->r_kyoku.data();
+    R.ky_off = E->r_ky_off.data(); R.pos = E->r_pos.data(); R.ky_idx = E->r_ky_idx.data(); R.ky_seen = E->r_ky_seen.data();
+    R.player = E->r_player.data(); R.row_label = E->r_label.data(); R.row_meta = E->r_meta.data();
+    R.always_include_kan_select = always_include_kan_select;
+    return E;
+}
+int emul_replay_step(void* p) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    E->n_rows[0] = 0;
+    int live = 0;
+    WarpScratch W;
+    for (int t = 0; t < E->n; t++) {
+        Ctx c; c.S = &E->tabs[t]; c.W = &W; c.T = g_T; c.lane = 0; c.df = W.dora_factor;
+        if (replay_table(c, E->V, E->R, t)) live++;
+    }
+    return live;
+}
+void emul_replay_rows(void* p, int64_t* labels, uint8_t* meta) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    const int n = E->n_rows[0];
+    for (int r = 0; r < n; r++) { labels[r] = E->r_label[r]; for (int k = 0; k < 4; k++) meta[r * 4 + k] = E->r_meta[(size_t)r * 4 + k]; }
+}
+int emul_env_errs(void* p, int32_t* errs) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    int bad = 0;
+    for (int t = 0; t < E->n; t++) { errs[t] = E->errs[t]; bad += errs[t] != 0; }
+    return bad;
+}
+
 void emul_env_enable_log(void* p, int cap) {
     EmulEnv* E = static_cast<EmulEnv*>(p);
     E->log_cap = cap; E->log.assign((size_t)E->n * cap, 0); E->log_len.assign(E->n, 0);

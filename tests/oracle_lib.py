@@ -193,6 +193,7 @@ def lib():
     L.orc_game_finish.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_game_info.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_game_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_gameplay_load.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
     L.orc_run_batch.argtypes = [C.POINTER(RunCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(RunOut)]
     L.orc_run_replay.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
@@ -481,3 +482,20 @@ def run_replay(nonces, keys, replay, *, shuffle_kind=0, quick_eval=True):
     if rc != 0:
         raise RuntimeError(err())
     return dict(scores=scores, ranks=ranks, steps=steps)
+
+
+def gameplay_load(events, player_id, *, version=4, always_include_kan_select=True, sp_mode=1, max_moves=600, with_obs=True):
+    """dataset/gameplay.rs GameplayLoader for one (game, player): events = list of mjai dicts (start_game .. end_game)."""
+    evs = (OrcEvent * len(events))(*[event_from_json(e) for e in events])
+    rows = {1: 938, 2: 942, 3: 934, 4: 1012}[version]
+    obs = np.zeros((max_moves, rows, 34), dtype=np.float32) if with_obs else None
+    masks = np.zeros((max_moves, 46), dtype=np.uint8)
+    actions = np.zeros(max_moves, dtype=np.int64)
+    at_kyoku = np.zeros(max_moves, dtype=np.uint8); gamma = np.zeros(max_moves, dtype=np.uint8)
+    at_turns = np.zeros(max_moves, dtype=np.uint8); shantens = np.zeros(max_moves, dtype=np.int8)
+    n = lib().orc_gameplay_load(evs, len(events), player_id, version, int(always_include_kan_select), sp_mode, max_moves,
+                                obs.ctypes.data if with_obs else None, masks.ctypes.data, actions.ctypes.data,
+                                at_kyoku.ctypes.data, gamma.ctypes.data, at_turns.ctypes.data, shantens.ctypes.data)
+    assert n >= 0, err()
+    return dict(obs=obs[:n] if with_obs else None, masks=masks[:n].astype(bool), actions=actions[:n], at_kyoku=at_kyoku[:n],
+                apply_gamma=gamma[:n].astype(bool), at_turns=at_turns[:n], shantens=shantens[:n])

@@ -215,3 +215,86 @@ def test_mjai_event_log_parity_emulated(policy_kind, shuffle_kind):
     ryukyoku, end_kyoku) over whole hanchans."""
     n_events = _log_parity(_EmulLogEnv, 12, policy_kind, shuffle_kind, 31337, enable_quick_eval=False)  # the oracle stepping API has no quick-eval
     assert n_events > 12 * 500
+
+
+def _selfplay_logs(n, policy_kind, seed0):
+    """whole-hanchan mjai logs (lists of event dicts) produced by the emulated env under a test policy"""
+    from mortal_b200 import mjai_log
+
+    nonces = np.arange(seed0, seed0 + n, dtype=np.uint64)
+    keys = np.full(n, 11, dtype=np.uint64)
+    env = E.EmulEnv(nonces, keys, enable_quick_eval=True)
+    env.enable_log()
+    acts = None
+    for _ in range(4000):
+        env.step(acts)
+        acts = env.policy_test(policy_kind)
+        if env.num_live() == 0:
+            break
+    words, lens = env.read_log()
+    env.close()
+    return [[{"type": "start_game", "names": ["a", "b", "c", "d"], "seed": [int(nonces[t]), 11]}]
+            + mjai_log.decode_events(words[t, : int(lens[t])]) + [{"type": "end_game"}] for t in range(n)]
+
+
+@pytest.mark.parametrize("policy_kind", [1, 0])
+def test_log_replay_labels_match_gameplay_loader_emulated(policy_kind):
+    """the product's log replay (csrc/mjx_replay.cuh, host-emulated) against the oracle's restatement of
+    dataset/gameplay.rs: per (game, player) the same moves with the same labels, masks, at_kyoku, at_turn, shanten,
+    apply_gamma, including kan-select rows."""
+    from mortal_b200 import dataset_codec as DC
+
+    games = _selfplay_logs(6, policy_kind, 900)
+    jobs = DC.build_jobs(games, [[0, 1, 2, 3]] * len(games))
+    rep = E.EmulReplay(jobs)
+    per_job = [dict(actions=[], masks=[], meta=[], kan=0) for _ in range(rep.n_tables)]
+    for _ in range(3000):
+        rep.replay_step()
+        if rep.num_rows():
+            rt, rs, m = rep.rows()
+            lab, meta = rep.row_labels()
+            for r in range(len(rt)):
+                j = per_job[rt[r]]
+                j["actions"].append(int(lab[r])); j["masks"].append(m[r]); j["meta"].append(meta[r].copy()); j["kan"] += int(rs[r] >> 2) & 1
+        if rep.live == 0:
+            break
+    assert rep.live == 0 and (rep.errs() == 0).all()
+    moves = 0
+    for job in range(rep.n_tables):
+        ref = O.gameplay_load(games[jobs["job_game"][job]], int(jobs["players"][job]), with_obs=False, sp_mode=0)
+        got = per_job[job]
+        assert got["actions"] == ref["actions"].tolist(), job
+        meta = np.array(got["meta"])
+        assert (np.array(got["masks"]) == ref["masks"]).all(), job
+        assert (meta[:, 0] == ref["at_kyoku"]).all() and (meta[:, 1] == ref["at_turns"]).all(), job
+        assert (meta[:, 2].astype(np.int8) == ref["shantens"]).all() and (meta[:, 3].astype(bool) == ref["apply_gamma"]).all(), job
+        moves += len(got["actions"])
+    assert moves > 4000 and sum(j["kan"] for j in per_job) > 0
+    rep.close()
+
+
+def test_log_replay_observations_match_gameplay_loader_emulated():
+    """the observations emitted during replay equal the oracle loader's (v4 incl. the single-player block, v3, v1)"""
+    from mortal_b200 import dataset_codec as DC
+
+    games = _selfplay_logs(2, 1, 1900)
+    for version, sp in ((4, True), (3, False), (1, False)):
+        jobs = DC.build_jobs(games, [[0, 2], [1, 3]])
+        rep = E.EmulReplay(jobs)
+        obs_per = [[] for _ in range(rep.n_tables)]
+        for _ in range(3000):
+            rep.replay_step()
+            if rep.num_rows():
+                rt, _, _ = rep.rows()
+                obs = rep.encode_obs(sp=sp, version=version)
+                for r in range(len(rt)):
+                    obs_per[rt[r]].append(obs[r])
+            if rep.live == 0:
+                break
+        for job in range(rep.n_tables):
+            ref = O.gameplay_load(games[jobs["job_game"][job]], int(jobs["players"][job]), version=version, sp_mode=1 if sp else 0)
+            got = np.array(obs_per[job])
+            assert got.shape == ref["obs"].shape
+            d = np.abs(got - ref["obs"])
+            assert not ((d != 0) & ((ref["obs"] == 0) | (ref["obs"] == 1))).any() and d.max() <= 1e-6
+        rep.close()

@@ -535,3 +535,62 @@ def test_device_engine_graph_replay_equals_eager(mjx):
         fin = torch.isfinite(q2)
         assert (q2[fin] - q1[fin]).abs().max() <= 0.05 * q2[fin].abs().max() + 1e-3
     assert len(eng._graphs) == 2  # buckets 512 and 700 (capped at the buffer size)
+
+
+def test_gameplay_loader_on_device_matches_oracle(mjx, tmp_path):
+    """libriichi.dataset.GameplayLoader on device — mjai logs written by the arena, loaded back through the
+    device log replay, equal the oracle's restatement of dataset/gameplay.rs move for move (labels, masks, at_kyoku, dones,
+    apply_gamma, at_turns, shantens) and observation for observation (v4 incl. the single-player block: exact)."""
+    import gzip
+
+    import torch
+
+    from mortal_b200 import dataset_codec as DC
+    from mortal_b200.libriichi.arena import OneVsThree
+    from mortal_b200.libriichi.dataset import GameplayLoader
+
+    class Rand:
+        engine_type = "mortal"
+        version = 4
+        is_oracle = False
+        enable_quick_eval = True
+        enable_rule_based_agari_guard = False
+
+        def __init__(self, name):
+            self.name = name
+
+        def react_device(self, obs, masks):
+            # prefers shanten-lowering discards so that riichi / calls / kans all occur
+            q = torch.rand(masks.shape, device=masks.device)
+            q[:, :34] += 2.0 * obs[:, 876, :] + obs[:, 875, :]
+            q = q.masked_fill(~masks, -1.0)
+            return q.argmax(-1), q
+
+    torch.manual_seed(5)
+    arena = OneVsThree(disable_progress_bar=True, log_dir=str(tmp_path))
+    arena.py_vs_py(Rand("x"), Rand("y"), (7000, 21), 2)
+    files = sorted(str(p) for p in tmp_path.iterdir())
+    assert len(files) == 8
+    loader = GameplayLoader(4, oracle=False)
+    loaded = loader.load_gz_log_files(files)
+    assert len(loaded) == 8 and all(len(g) == 4 for g in loaded)
+    moves = 0
+    for fn, per_player in zip(files, loaded):
+        events = DC.parse_log(gzip.open(fn, "rt").read())
+        for gp in per_player:
+            ref = O.gameplay_load(events, gp.take_player_id(), version=4, sp_mode=1)
+            assert gp.take_actions() == ref["actions"].tolist()
+            assert gp.take_at_kyoku() == ref["at_kyoku"].tolist() and gp.take_at_turns() == ref["at_turns"].tolist()
+            assert gp.take_shantens() == ref["shantens"].tolist() and gp.take_apply_gamma() == ref["apply_gamma"].tolist()
+            dones = np.append(ref["at_kyoku"][1:] > ref["at_kyoku"][:-1], True)
+            assert gp.take_dones() == dones.tolist()
+            assert (gp.take_masks(host=True) == ref["masks"]).all()
+            obs = gp.take_obs(host=True)
+            d = np.abs(obs - ref["obs"])
+            assert obs.shape == ref["obs"].shape and not ((d != 0) & ((ref["obs"] == 0) | (ref["obs"] == 1))).any() and d.max() <= 1e-6
+            assert (d[:, 889:] == 0).all()  # single-player block: exact
+            assert gp.player_name == ("x" if gp.take_player_id() == files.index(fn) % 4 else "y")
+            moves += len(ref["actions"])
+    assert moves > 8 * 4 * 100
+    only_x = GameplayLoader(4, oracle=False, player_names=["x"]).load_gz_log_files(files[:2])
+    assert [len(g) for g in only_x] == [1, 1] and only_x[0][0].player_name == "x"
