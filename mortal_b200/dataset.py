@@ -6,8 +6,9 @@ always_include_kan_select, augmented)`, `.load_gz_log_files(filenames) -> list[l
 take_shantens / take_player_id`. The logs are replayed on device (csrc/mjx_replay.cuh) and the observations come from the
 same encoder kernels self-play uses. Differences, stated rather than hidden: `take_obs()` / `take_masks()` return ONE tensor
 per Gameplay ([n_moves, C, 34] float32 / [n_moves, 46] bool, CUDA by default, `host=True` for numpy) instead of a list of
-per-move arrays; the oracle (invisible) observation, `Grp` and tile augmentation are not built (`oracle=True` /
-`augmented=True` / `take_grp` raise NotImplementedError); logs must carry full information (no "?" tiles).
+per-move arrays; the oracle (invisible) observation and tile augmentation are not built (`oracle=True` / `augmented=True`
+raise NotImplementedError); logs must carry full information (no "?" tiles). `Grp` (dataset/grp.rs:19-164) is plain host-side
+log arithmetic and is provided in Python.
 """
 from __future__ import annotations
 
@@ -19,9 +20,71 @@ from . import dataset_codec
 from .env import ReplayEnv
 
 
+class Grp:
+    """dataset/grp.rs:19-164: per-kyoku features [grand_kyoku, honba, kyotaku, scores / 10000] (float64 [n_kyoku, 7]),
+    the final ranking and final scores of a game. Pure log arithmetic on the host."""
+
+    def __init__(self, feature, rank_by_player, final_scores):
+        self.feature, self.rank_by_player, self.final_scores = feature, rank_by_player, final_scores
+
+    @staticmethod
+    def load_events(events):
+        info, rank, final_deltas, final_scores = [], None, [0, 0, 0, 0], [0, 0, 0, 0]
+        for ev in reversed(events):  # grp.rs:96-152 walks the log backwards
+            ty = ev["type"]
+            if ty in ("hora", "ryukyoku"):
+                if rank is None:
+                    if ev.get("deltas") is None:
+                        raise ValueError("invalid log: field `deltas` is required for Hora and Ryukyoku of AL")
+                    final_deltas = [a + b for a, b in zip(final_deltas, ev["deltas"])]
+            elif ty == "reach_accepted":
+                if rank is None:
+                    final_deltas[ev["actor"]] -= 1000
+            elif ty == "start_kyoku":
+                if rank is None:
+                    final_scores = [a + b for a, b in zip(ev["scores"], final_deltas)]
+                    order = sorted(range(4), key=lambda i: -final_scores[i])  # rankings.rs:8-22: stable by seat
+                    total = sum(final_scores)
+                    if total < 100_000:  # leftover riichi sticks go to the top (grp.rs:127-131)
+                        final_scores[order[0]] += 100_000 - total
+                    rank = [0, 0, 0, 0]
+                    for r, pl in enumerate(order):
+                        rank[pl] = r
+                grand = {"E": ev["kyoku"] - 1, "S": 3 + ev["kyoku"]}.get(ev["bakaze"], 7 + ev["kyoku"])
+                info.insert(0, [float(grand), float(ev["honba"]), float(ev["kyotaku"])] + [sc / 10000.0 for sc in ev["scores"]])
+        if rank is None:
+            raise ValueError("invalid log: no Hora or Ryukyoku after a StartKyoku")
+        return Grp(np.array(info, dtype=np.float64).reshape(-1, 7), rank, final_scores)
+
+    @staticmethod
+    def load_log(raw_log: str):
+        return Grp.load_events(dataset_codec.parse_log(raw_log))
+
+    @staticmethod
+    def load_gz_log_files(gzip_filenames):
+        out = []
+        for fn in gzip_filenames:
+            with gzip.open(fn, "rt") as f:
+                out.append(Grp.load_log(f.read()))
+        return out
+
+    def take_feature(self):
+        return self.feature
+
+    def take_rank_by_player(self):
+        return list(self.rank_by_player)
+
+    def take_final_scores(self):
+        return list(self.final_scores)
+
+    def __len__(self):
+        return int(self.feature.shape[0])
+
+
 class Gameplay:
-    def __init__(self, player_id: int, player_name: str, obs, actions, masks, at_kyoku, apply_gamma, at_turns, shantens):
+    def __init__(self, player_id: int, player_name: str, obs, actions, masks, at_kyoku, apply_gamma, at_turns, shantens, grp=None):
         self.player_id, self.player_name = player_id, player_name
+        self.grp = grp
         self._obs, self._masks = obs, masks
         self._actions, self._at_kyoku, self._apply_gamma = actions, at_kyoku, apply_gamma
         self._at_turns, self._shantens = at_turns, shantens
@@ -38,7 +101,7 @@ class Gameplay:
         raise NotImplementedError("oracle (invisible) observations are not built (SURVEY.md §8f N4)")
 
     def take_grp(self):
-        raise NotImplementedError("Grp is not built (SURVEY.md §8f N3/N4)")
+        return self.grp
 
     def take_actions(self):
         return self._actions.tolist()
@@ -132,6 +195,7 @@ class GameplayLoader:
             counts = torch.bincount(job, minlength=n_jobs).cpu().numpy()
         else:
             counts = np.zeros(n_jobs, dtype=np.int64)
+        grps = [Grp.load_events(ev) for ev in games]
         start = 0
         for j in range(n_jobs):
             n = int(counts[j]); sl = slice(start, start + n); start += n
@@ -139,10 +203,10 @@ class GameplayLoader:
             name = games[g][0].get("names", ["", "", "", ""])[pid]
             if n:
                 gp = Gameplay(pid, name, obs[sl], label[sl], masks[sl], meta[sl, 0].copy(), meta[sl, 3].astype(bool),
-                              meta[sl, 1].copy(), meta[sl, 2].astype(np.int8))
+                              meta[sl, 1].copy(), meta[sl, 2].astype(np.int8), grp=grps[g])
             else:
                 z = np.zeros(0, dtype=np.uint8)
                 gp = Gameplay(pid, name, torch.zeros((0, env.obs_rows, 34), device=obs.device if chunks else "cpu"), np.zeros(0, dtype=np.int64),
-                              torch.zeros((0, 46), dtype=torch.bool), z, z.astype(bool), z, z.astype(np.int8))
+                              torch.zeros((0, 46), dtype=torch.bool), z, z.astype(bool), z, z.astype(np.int8), grp=grps[g])
             out[g].append(gp)
         return out

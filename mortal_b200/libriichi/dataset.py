@@ -1,2 +1,2 @@
-"""libriichi.dataset — the GameplayLoader part (dataset/gameplay.rs), backed by the device log replay."""
-from ..dataset import Gameplay, GameplayLoader  # noqa: F401
+"""libriichi.dataset — GameplayLoader (dataset/gameplay.rs) and Grp (dataset/grp.rs), backed by the device log replay."""
+from ..dataset import Gameplay, GameplayLoader, Grp  # noqa: F401

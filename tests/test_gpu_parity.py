@@ -361,14 +361,19 @@ def test_arena_writes_mjai_logs(mjx, tmp_path):
         assert lines[0]["type"] == "start_game" and lines[0]["seed"] == [4000 + g // 4, 77]
         assert lines[0]["names"] == ["chal" if s == g % 4 else "champ" for s in range(4)]
         assert lines[-1] == {"type": "end_game"}
-        scores = None
+        scores, sticks = None, 0
         for ev in lines:
             if ev["type"] == "start_kyoku":
-                scores = list(ev["scores"])
+                scores, sticks = list(ev["scores"]), ev["kyotaku"]
             elif ev["type"] in ("hora", "ryukyoku"):
                 scores = [a + b for a, b in zip(scores, ev["deltas"])]
+                if ev["type"] == "hora":
+                    sticks = 0  # the first winner's deltas already contain the sticks on the table (board.rs:401-403)
             elif ev["type"] == "reach_accepted":
                 scores[ev["actor"]] -= 1000
+                sticks += 1
+        if sticks:  # game.rs:181-198: sticks left at the very end go to the first top seat
+            scores[max(range(4), key=lambda i: (scores[i], -i))] += 1000 * sticks
         assert scores == [int(x) for x in res["scores"][g]], (g, scores, res["scores"][g])
 
 

@@ -103,3 +103,22 @@ def test_world_size_2_gloo_gather(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_grp_on_the_reference_golden_log():
+    """dataset/grp.rs:90-164 on the seeded example log (log-viewer/index.example.html): features per kyoku, final scores with
+    the busted player's sticks handling, stable ranking."""
+    import json
+
+    from mortal_b200.dataset import Grp
+
+    with open(os.path.join(ROOT, "tests", "golden", "golden_game.jsonl")) as f:
+        events = [json.loads(ln) for ln in f if ln.strip()]
+    g = Grp.load_events(events)
+    assert g.feature.shape == (3, 7) and len(g) == 3
+    assert g.feature[0].tolist() == [0.0, 0.0, 0.0, 2.5, 2.5, 2.5, 2.5]
+    assert g.feature[1].tolist() == [0.0, 1.0, 0.0, 3.27, 2.5, 1.73, 2.5]
+    assert g.feature[2].tolist() == [1.0, 0.0, 0.0, 3.27, 3.02, 1.31, 2.4]
+    # last kyoku: 32700/30200/13100/24000 + hora [0, 20000, -18000, 0] - one riichi stick of the winner, returned to the top
+    assert sum(g.take_final_scores()) == 100_000
+    assert g.take_rank_by_player() == [1, 0, 3, 2]
