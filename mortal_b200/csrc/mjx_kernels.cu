@@ -312,7 +312,9 @@ __global__ void __launch_bounds__(SP_WARPS * 32, KIND == 2 ? 3 : (KIND == 1 ? 4 
     const i32* list = G.slot_list + (size_t)slot * G.slot_cap;
     const int k = sp_slot_shanten(slot);
     if (KIND == 0) {
-        for (int i = gwarp; i < n; i += nwarps) if (list[i] >= 0) sp_eval_d(s, c, list[i]);
+        // two D-states per warp, one per half-warp (sp_eval_d2); no warp-level sync inside, the halves just diverge
+        const int hw = lane >> 4;
+        for (int i = gwarp * 2; i < n; i += nwarps * 2) sp_eval_d2(s, i + hw < n ? list[i + hw] : -1);
     } else {
         // two W-states per warp, one per half-warp (csrc/mjx_sp.cuh sp_eval_w2)
         __shared__ SpEvalScratch s_es[SP_WARPS];

@@ -862,6 +862,39 @@ MJX_DN void sp_eval_d(SpCtx& s, const Ctx& c, int node) {
     MJX_SYNCWARP();
 }
 
+#ifndef MJX_HOST_EMUL
+// Device form of sp_eval_d: two D-states per warp, one per half-warp (turn i = sub-lane, sub-lane 15 also carries turn 16).
+MJX_DN void sp_eval_d2(SpCtx& s, int node) {
+    if (node < 0) return;
+    const int l = s.lane & 15;
+    const int T = s.G.rows[s.G.node_row[node]].T;
+    const int ne = s.G.n_edges[node];
+    const u32 eb = s.G.edge_begin[node];
+    for (int pass = 0; pass < 2; pass++) {
+        const int i = pass == 0 ? l : 16;
+        if (pass == 0 ? i >= T : !(T > 16 && l == 15)) continue;
+        const float FMIN = -3.40282347e+38f;
+        float bt = FMIN, bw = FMIN, bv = FMIN;
+        int best_tile = T_UNK;
+        i32 best_value = (i32)0x80000000;
+        for (int e = 0; e < ne; e++) {
+            const u32 child = s.G.edge_child[eb + e];
+            if (child == SP_NO_CHILD) continue;
+            const int tile = s.G.edge_meta[eb + e] & 63;
+            const float v = sp_vals(s, (int)child, 2)[i];
+            const i32 value = (i32)v;  // finite and < 2^31 here; Rust `as i32` truncates the same way
+            if (value > best_value || (value == best_value && cmp_discard_priority(tile, best_tile) > 0)) {
+                bt = sp_vals(s, (int)child, 0)[i]; bw = sp_vals(s, (int)child, 1)[i]; bv = v;
+                best_value = value; best_tile = tile;
+            }
+        }
+        sp_vals(s, node, 0)[i] = bt;
+        sp_vals(s, node, 1)[i] = bw;
+        sp_vals(s, node, 2)[i] = bv;
+    }
+}
+#endif
+
 // per-candidate summary used by the obs rows
 struct SpCand {
     int tile;           // as sp/candidate.rs (may be an aka id)
