@@ -279,6 +279,39 @@ def run_ours(args):
             b_rows += env.num_rows()
     env.close()
 
+    # -------- BASELINE configs[3]: encode_obs throughput at 65536 decision rows per launch (rank 0, N=1 only: it is a
+    # kernel measurement, not part of the step). 65536 tables, one row per table-step on average, SP block off.
+    enc64k = None
+    if world == 1 and not args.no_encode_64k:
+        n64 = 65536
+        n_nonce = np.repeat(np.arange(SEED_START[0], SEED_START[0] + n64 // 4, dtype=np.uint64), 4)
+        env = mortal_b200.BatchEnv(n_nonce, np.full(n64, SEED_START[1], dtype=np.uint64), obs_version=4, device=local_rank)
+        env.set_sp(False)
+        acts = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
+        env.step(None)
+        env.policy_test(1, acts)
+        for _ in range(60):
+            env.step(acts)
+            env.policy_test(1, acts)
+        obs64 = env.obs_buffer()
+        rows64, ms64 = 0, 0.0
+        for i in range(3 + 5):
+            env.step(acts)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            env.encode_obs(obs64)
+            e1.record()
+            env.policy_test(1, acts)
+            nr64 = env.num_rows()
+            if i >= 3:
+                rows64 += nr64
+                ms64 += e0.elapsed_time(e1)
+        env.close()
+        del obs64
+        torch.cuda.empty_cache()
+        gbs64 = rows64 * (OBS_BYTES + MASK_BYTES + STATE_BYTES) / (ms64 * 1e-3) / 1e9
+        enc64k = {"rows_per_launch": rows64 / 5, "ms_per_launch": ms64 / 5, "achieved": gbs64, "unit": "GB/s"}
+
     # -------- loop C: e2e through the C ABI with HOST buffers (pinned): obs/masks D2H, actions H2D each step
     env, d_actions = fresh_env()
     h_obs = torch.empty((env.row_cap, 1012, 34), dtype=torch.float32, pin_memory=True)
@@ -407,6 +440,8 @@ def run_ours(args):
             # with the block switched off.
             "sp_block": {"ms_per_step": (b["ms"] - b2["ms"]) / K, "states_last_step": sp_states, "edges_last_step": sp_edges,
                          "states_per_s": sp_states / max((b["ms"] - b2["ms"]) / K * 1e-3, 1e-9), "share_of_env_step": 1.0 - b2["ms"] / b["ms"]},
+            # BASELINE configs[3] (encode_obs throughput, 65536 states -> obs tensor): the same two kernels at 16x the rows
+            "encode_65536": (dict(enc64k, frac=enc64k["achieved"] / peak_gbs) if enc64k else None),
             "e2e": {"value": c_units / (c_ms * 1e-3), "unit": "table-steps/s",
                     "h2d_bytes_per_step": 8 * N_TABLES * 3,
                     "d2h_bytes_per_step": int(e2e_rows / K * (OBS_BYTES + MASK_BYTES)),
@@ -449,6 +484,7 @@ def main():
     ap.add_argument("--ref-tables", type=int, default=256)
     ap.add_argument("--ref-steps-per-table", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encode-64k", action="store_true", help="skip the BASELINE configs[3] encode measurement (27 GB obs buffer)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
