@@ -8,7 +8,7 @@ observation per decision row, run the policy. One table-step = that iteration fo
 Default arm (this repo): 4096 tables per GPU (BASELINE configs[1]), random-init Mortal brain
 (192 channels x 40 blocks, bf16 autocast, greedy), everything resident in HBM. JSON also carries
   env_only      the same loop with the counter-based test policy instead of the network
-  roofline      achieved HBM GB/s of the HBM-bound env kernels (k_encode_features + k_encode_store) from CUDA events
+  roofline      achieved HBM GB/s of the HBM-bound env kernel (k_encode_store; .pair = with k_encode_features) from CUDA events
   e2e           the loop through the C ABI with HOST buffers (obs D2H, actions H2D every step)
   cpu_baseline  the CPU oracle on this box's host cores, bounded sample (rank 0, N=1 only)
 `--impl reference` times libriichi's own CPU path restated by the oracle (oracle/, all host threads).
@@ -270,13 +270,22 @@ def run_ours(args):
     b2 = loop(ea, test_policy, W, K, time_encode=True)
     ea[0].close()
     # rows per launch for the roofline: the same deterministic K cycles again, reading the row count each step
+    # and the two encoder kernels timed separately (events inside libmjx on the launch stream; a sync per step, so this
+    # pass is not the one `env_only` is quoted from)
     env, actions = fresh_env()
-    b_rows = 0
+    env.set_sp(False)
+    env.set_encode_timing(True)
+    obs_t = env.obs_buffer()
+    b_rows, feat_ms, store_ms = 0, 0.0, 0.0
     for i in range(W + K):
         env.step(actions)
+        env.encode_obs(obs_t)
         env.policy_test(1, actions)
         if i >= W:
             b_rows += env.num_rows()
+            f_ms, s_ms = env.last_encode_ms()
+            feat_ms += f_ms
+            store_ms += s_ms
     env.close()
 
     # -------- BASELINE configs[3]: encode_obs throughput at 65536 decision rows per launch (rank 0, N=1 only: it is a
@@ -428,13 +437,18 @@ def run_ours(args):
             "env_only": {"value": b_units / (b_ms * 1e-3), "unit": "table-steps/s", "ms_per_step": b_ms / K,
                          "policy": "counter-based test policy kernel, no host sync",
                          "without_sp_block": {"value": b2["table_steps"] / (b2["ms"] * 1e-3), "ms_per_step": b2["ms"] / K}},
-            "roofline": {"kernel": "k_encode_features + k_encode_store (the whole v4 encode without the SP block)", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs if peak_gbs else None,
-                         # dram__bytes_read + dram__bytes_write of the two kernels, one `ncu --set full` capture each at this
-                         # workload (profiles/r01_ncu_k_encode_{features,store}.md): 9.8 MB + 541.8 MB per launch pair
-                         "traffic": 551.6e6, "peak_source": peak_src,
-                         "bytes_per_launch": bytes_per_launch, "ms_per_launch": enc_ms_per_launch,
-                         "rows_per_launch": rows_per_launch},
+            # the HBM-bound kernel of the path: k_encode_store materialises and stores every observation of the step (the
+            # algorithmic bytes); k_encode_features, which derives the 11 KB/row compact form it reads, is latency-bound and
+            # is reported beside it (`pair` = both kernels together, the figure earlier rounds quoted)
+            "roofline": {"kernel": "k_encode_store", "bound": "hbm", "achieved": bytes_per_launch / (store_ms / K * 1e-3) / 1e9,
+                         "peak": peak_gbs, "unit": "GB/s", "frac": bytes_per_launch / (store_ms / K * 1e-3) / 1e9 / peak_gbs,
+                         # dram__bytes_read + dram__bytes_write of one `ncu --set full` capture at this workload
+                         # (profiles/r01_ncu_k_encode_store.md): 44.2 MB read + 497.6 MB written per launch
+                         "traffic": 541.8e6, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
+                         "ms_per_launch": store_ms / K, "rows_per_launch": rows_per_launch,
+                         "k_encode_features_ms": feat_ms / K,
+                         "pair": {"ms_per_launch": enc_ms_per_launch, "achieved": achieved, "frac": achieved / peak_gbs if peak_gbs else None,
+                                  "traffic": 551.6e6}},
             # the single-player block is a latency-bound graph DP (hash interning + value propagation over an arena far larger
             # than L2); it has no meaningful HBM roofline, so it is reported as states/s. ms = env_only minus the same loop
             # with the block switched off.

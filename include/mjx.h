@@ -102,6 +102,11 @@ int mjx_env_replay_step(mjx_env* env, void* stream);
 int64_t* mjx_env_row_label(mjx_env* env); /* int64 [row_cap] device */
 uint8_t* mjx_env_row_meta(mjx_env* env);  /* uint8 [row_cap, 4] device: at_kyoku, at_turn, shanten (int8), apply_gamma */
 
+/* Instrumentation for bench.py's roofline: when enabled, mjx_env_encode_obs brackets its two encoder kernels with CUDA events
+ * on the launch stream; mjx_env_last_encode_ms (blocking) returns the durations of k_encode_features and k_encode_store. */
+int mjx_env_set_encode_timing(mjx_env* env, int enable);
+int mjx_env_last_encode_ms(mjx_env* env, float* ms_features, float* ms_store);
+
 /* Number of kernels this library has launched for env so far (host-side counter; bench.py's gpu_launches). */
 long long mjx_env_launch_count(mjx_env* env);
 

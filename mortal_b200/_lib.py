@@ -57,6 +57,8 @@ SYMBOLS = {
     "mjx_env_replay_step": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mjx_env_row_label": (C.c_void_p, [C.c_void_p]),
     "mjx_env_row_meta": (C.c_void_p, [C.c_void_p]),
+    "mjx_env_set_encode_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "mjx_env_last_encode_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "mjx_env_launch_count": (C.c_longlong, [C.c_void_p]),
     "mjx_env_num_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "mjx_env_num_live": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),

@@ -460,6 +460,8 @@ struct mjx_env {
     SpGlobal sp;
     int sp_enabled = 1;
     unsigned char* d_compact = nullptr;
+    cudaEvent_t ev_enc[3] = {nullptr, nullptr, nullptr};  // optional per-kernel timing of the encoder pair (bench.py roofline)
+    bool time_encode = false;
     ReplayView R{};  // replay mode (mjx_env_create_replay): device arrays of the jobs
     bool replay = false;
     int* d_enc_work = nullptr;  // k_encode_features' dynamic work counter
@@ -629,6 +631,7 @@ void mjx_env_destroy(mjx_env* env) {
         cudaFree((void*)R.hdr); cudaFree((void*)R.kyoku); cudaFree((void*)R.ev_off); cudaFree((void*)R.ev_cnt); cudaFree((void*)R.ky_off);
         cudaFree((void*)R.player); cudaFree(R.pos); cudaFree(R.ky_idx); cudaFree(R.ky_seen); cudaFree(R.row_label); cudaFree(R.row_meta);
     }
+    for (int i = 0; i < 3; i++) if (env->ev_enc[i]) cudaEventDestroy(env->ev_enc[i]);
     cudaFree(env->d_guard); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len);
     SpGlobal& G = env->sp;
     cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.sigs); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
@@ -663,13 +666,16 @@ int mjx_env_step(mjx_env* env, const int64_t* actions_dev, const float* q_values
 }
 
 static int launch_encode_rows(mjx_env* env, float* obs_dev, cudaStream_t st) {
+    if (env->time_encode) CU(cudaEventRecord(env->ev_enc[0], st));
     switch (env->obs_version) {
         case 1: launch_features<1>(env, st); break;
         case 2: launch_features<2>(env, st); break;
         case 3: launch_features<3>(env, st); break;
         default: launch_features<4>(env, st); break;
     }
+    if (env->time_encode) CU(cudaEventRecord(env->ev_enc[1], st));
     k_encode_store<<<g_sm_count, ENCS_WARPS * 32, ENCS_SMEM_BYTES, st>>>(env->V, env->enc_args, env->d_compact, obs_dev, env->d_enc_work);
+    if (env->time_encode) CU(cudaEventRecord(env->ev_enc[2], st));
     CU(cudaGetLastError());
     env->launches += 2;
     return MJX_OK;
@@ -816,6 +822,20 @@ int mjx_env_replay_step(mjx_env* env, void* stream) {
 }
 int64_t* mjx_env_row_label(mjx_env* env) { return env && env->replay ? (int64_t*)env->R.row_label : nullptr; }
 uint8_t* mjx_env_row_meta(mjx_env* env) { return env && env->replay ? env->R.row_meta : nullptr; }
+
+int mjx_env_set_encode_timing(mjx_env* env, int enable) {
+    if (!env) return fail(MJX_ERR_ARG, "mjx_env_set_encode_timing: null env");
+    if (enable && !env->ev_enc[0]) for (int i = 0; i < 3; i++) CU(cudaEventCreate(&env->ev_enc[i]));
+    env->time_encode = enable != 0;
+    return MJX_OK;
+}
+int mjx_env_last_encode_ms(mjx_env* env, float* ms_features, float* ms_store) {
+    if (!env || !ms_features || !ms_store || !env->ev_enc[0]) return fail(MJX_ERR_ARG, "mjx_env_last_encode_ms: timing not enabled");
+    CU(cudaEventSynchronize(env->ev_enc[2]));
+    CU(cudaEventElapsedTime(ms_features, env->ev_enc[0], env->ev_enc[1]));
+    CU(cudaEventElapsedTime(ms_store, env->ev_enc[1], env->ev_enc[2]));
+    return MJX_OK;
+}
 
 long long mjx_env_launch_count(mjx_env* env) { return env ? env->launches : -1; }
 

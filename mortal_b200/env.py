@@ -148,6 +148,15 @@ class BatchEnv:
             raise RuntimeError(f"event log overflow: {int(lens.max())} words > capacity {self._log_cap}")
         return words, lens
 
+    def set_encode_timing(self, enable: bool) -> None:
+        _lib.check(self.L.mjx_env_set_encode_timing(self._h, int(enable)), "mjx_env_set_encode_timing")
+
+    def last_encode_ms(self):
+        """(k_encode_features ms, k_encode_store ms) of the last encode_obs call; needs set_encode_timing(True); blocking"""
+        a, b = C.c_float(0), C.c_float(0)
+        _lib.check(self.L.mjx_env_last_encode_ms(self._h, C.byref(a), C.byref(b)), "mjx_env_last_encode_ms")
+        return a.value, b.value
+
     def launch_count(self) -> int:
         """kernels launched for this env so far (host-side counter in libmjx)"""
         return int(self.L.mjx_env_launch_count(self._h))
