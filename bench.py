@@ -345,17 +345,24 @@ def run_ours(args):
         score[~m] = -1.0
         return score.argmax(-1)
 
+    e2e_stage = {"step_encode_d2h": 0.0, "host_policy": 0.0}
+
     def e2e_cycle():
+        ta = time.perf_counter()
         d_actions.copy_(h_actions, non_blocking=True)  # H2D: the step's inputs
         env.step(d_actions)
         nr = env.encode_obs_host(h_obs, h_masks)  # D2H: the step's result, as react_batch receives it (blocking)
+        tb = time.perf_counter()
         if nr:
             h_actions[:nr] = host_policy(nr)
+        e2e_stage["step_encode_d2h"] += tb - ta
+        e2e_stage["host_policy"] += time.perf_counter() - tb
         return nr
 
     for _ in range(W):
         e2e_cycle()
     barrier()
+    e2e_stage["step_encode_d2h"] = e2e_stage["host_policy"] = 0.0
     s0 = env.total_steps()
     w0 = time.perf_counter()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -460,8 +467,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": 8 * N_TABLES * 3,
                     "d2h_bytes_per_step": int(e2e_rows / K * (OBS_BYTES + MASK_BYTES)),
                     "path": "mjx_env_encode_obs_host with pinned host buffers: actions H2D, obs+masks D2H every step "
-                            "(rows 0-888 drain while the SP kernels run), greedy host-side policy reading the host obs",
-                    "plain_d2h_copy_gbs": pcie_gbs},
+                            "(the single-player block runs in 4 row groups; finished groups drain through the copy engine meanwhile), "
+                            "greedy host-side policy reading the host obs",
+                    "plain_d2h_copy_gbs": pcie_gbs,
+                    "stages_ms_per_step": {k: 1000.0 * v / K for k, v in e2e_stage.items()}},
             # this library's kernels in the timed region: env kernels counted by libmjx, plus the fused policy-net kernels
             # (4 per residual block + 1, csrc/mjx_nn.cuh) that each CUDA-graph replay of the forward contains
             "gpu_launches": a["launches"] + K * (4 * 40 + 1), "gpu_launches_env": a["launches"], "clocks": clocks,

@@ -60,8 +60,9 @@ int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream);
 
 /* The same for a caller that holds HOST buffers (what agent/mortal.rs:126-152 hands to react_batch): encodes into the
  * device scratch `obs_dev` [row_cap, rows, 34] and copies rows [0, *n_rows) to `obs_host` (same layout) and `masks_host`
- * (uint8 [row_cap, 46]); the copy of rows 0..888 overlaps the single-player kernels. Blocking; host buffers should be
- * pinned (cudaHostAlloc / torch pin_memory) for the overlap to happen. */
+ * (uint8 [row_cap, 46]). The single-player block is computed in four row groups and the finished observations of one group drain
+ * through the copy engine while the SMs work on the next. Blocking; host buffers should be pinned (cudaHostAlloc / torch
+ * pin_memory) for the overlap to happen. */
 int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8_t* masks_host, int* n_rows, void* stream);
 
 /* state/agent_helper.rs:509-593 single_player_tables (obs v4 rows 889-1011): on by default; `enable = 0`

@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(ENCS_WARPS * 32, 1) k_encode_store(EnvView V, 
 
 // ---- single-player tables: level-synchronous DP over all rows of the step (csrc/mjx_sp.cuh)
 constexpr int SP_WARPS = 4;
+constexpr int MJX_HOST_COPY_GROUPS = 4;  // mjx_env_encode_obs_host: row groups of the SP block / D2H pipeline
 
 __global__ void k_sp_begin(SpGlobal G) {
     if (threadIdx.x < SP_SLOTS) G.slot_count[threadIdx.x] = 0;
@@ -275,11 +276,11 @@ __global__ void k_sp_begin(SpGlobal G) {
     SpCtx s; s.G = G; s.T = T; s.ws = &s_ws[warp]; s.lane = lane;                               \
     Ctx c; c.S = nullptr; c.W = nullptr; c.T = T; c.lane = lane; c.df = nullptr;
 
-__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_init(SpGlobal G, Tables T, EnvView V) {
+__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_init(SpGlobal G, Tables T, EnvView V, int row_lo, int row_hi) {
     SP_KERNEL_PROLOGUE
     (void)c;
-    const int n_rows = *V.n_rows;
-    for (int row = gwarp; row < n_rows; row += nwarps)
+    const int n_rows = min(*V.n_rows, row_hi);
+    for (int row = row_lo + gwarp; row < n_rows; row += nwarps)
         sp_stage_init(s, V.tables + V.row_table[row], row, V.row_table[row], V.row_seat[row] & 3);
 }
 
@@ -335,11 +336,12 @@ __global__ void __launch_bounds__(128) k_sp_score(SpGlobal G, Tables T) {
     for (int e = b + blockIdx.x * blockDim.x + threadIdx.x; e < e_end; e += gridDim.x * blockDim.x) sp_score_edge(s, e);
 }
 
-__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_finalize(SpGlobal G, Tables T, EnvView V, float* __restrict__ obs) {
+__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_finalize(SpGlobal G, Tables T, EnvView V, float* __restrict__ obs, int row_lo,
+                                                               int row_hi) {
     SP_KERNEL_PROLOGUE
     (void)c;
-    const int n_rows = *V.n_rows;
-    for (int row = gwarp; row < n_rows; row += nwarps)
+    const int n_rows = min(*V.n_rows, row_hi);
+    for (int row = row_lo + gwarp; row < n_rows; row += nwarps)
         sp_stage_finalize(s, row, obs + (size_t)row * OBS_ROWS_V4 * OBS_COLS);
 }
 
@@ -467,7 +469,7 @@ struct mjx_env {
     int* d_enc_work = nullptr;  // k_encode_features' dynamic work counter
     EncStoreArgs enc_args{};
     cudaStream_t copy_stream = nullptr;  // mjx_env_encode_obs_host: D2H overlapped with the SP kernels
-    cudaEvent_t ev_rows = nullptr, ev_sp = nullptr;
+    cudaEvent_t ev_rows = nullptr, ev_sp = nullptr, ev_grp[MJX_HOST_COPY_GROUPS] = {};
     long long launches = 0;  // kernels launched on behalf of this env (bench.py's gpu_launches)
 };
 
@@ -637,7 +639,7 @@ void mjx_env_destroy(mjx_env* env) {
     cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.sigs); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
     cudaFree(G.edge_child); cudaFree(G.edge_meta); cudaFree(G.edge_owner); cudaFree(G.leaf_scores); cudaFree(G.hash); cudaFree(G.slot_list); cudaFree(G.slot_count);
     cudaFree(G.counters);
-    if (env->copy_stream) { cudaStreamDestroy(env->copy_stream); cudaEventDestroy(env->ev_rows); cudaEventDestroy(env->ev_sp); }
+    if (env->copy_stream) { cudaStreamDestroy(env->copy_stream); cudaEventDestroy(env->ev_rows); cudaEventDestroy(env->ev_sp); for (int g = 0; g < MJX_HOST_COPY_GROUPS; g++) cudaEventDestroy(env->ev_grp[g]); }
     delete env;
 }
 
@@ -682,13 +684,14 @@ static int launch_encode_rows(mjx_env* env, float* obs_dev, cudaStream_t st) {
 }
 
 // single-player block (rows 889..1011): init -> expand slots 0..7 -> score -> evaluate slots 7..0 -> finalize
-static int launch_sp_block(mjx_env* env, float* obs_dev, cudaStream_t st) {
+// rows [row_lo, row_hi) of the step form one DP (the whole step by default; mjx_env_encode_obs_host runs it in row groups)
+static int launch_sp_block(mjx_env* env, float* obs_dev, cudaStream_t st, int row_lo = 0, int row_hi = 0x7fffffff) {
     if (!env->sp_enabled) return MJX_OK;
     const SpGlobal& G = env->sp;
     const int grid = g_sm_count * 8;
     CU(cudaMemsetAsync(G.hash, 0, (size_t)G.hash_cap * sizeof(u32), st));
     k_sp_begin<<<1, 32, 0, st>>>(G);
-    k_sp_init<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V);
+    k_sp_init<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, row_lo, row_hi);
     for (int slot = 0; slot < SP_SLOTS; slot++) {
         if (slot == SP_SLOTS - 1) k_sp_mark<<<1, 1, 0, st>>>(G, 0);
         k_sp_expand<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
@@ -700,7 +703,7 @@ static int launch_sp_block(mjx_env* env, float* obs_dev, cudaStream_t st) {
         else if (slot == SP_SLOTS - 1) k_sp_eval<2><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
         else k_sp_eval<1><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
     }
-    k_sp_finalize<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev);
+    k_sp_finalize<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev, row_lo, row_hi);
     CU(cudaGetLastError());
     env->launches += 5 + 2 * SP_SLOTS + 1;
     return MJX_OK;
@@ -722,29 +725,36 @@ int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8
         CU(cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&env->ev_rows, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&env->ev_sp, cudaEventDisableTiming));
+        for (int g = 0; g < MJX_HOST_COPY_GROUPS; g++) CU(cudaEventCreateWithFlags(&env->ev_grp[g], cudaEventDisableTiming));
     }
     int n = 0;
     CU(cudaMemcpyAsync(&n, env->V.n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     *n_rows_out = n;
     if (n == 0) return MJX_OK;
-    const size_t pitch = (size_t)env->enc_args.rows * 34 * sizeof(float);
-    const size_t head = env->sp_enabled ? (size_t)SP_ROW0 * 34 * sizeof(float) : pitch;  // rows below the SP block
+    const size_t pitch = (size_t)env->enc_args.rows * 34 * sizeof(float);  // bytes of one observation
     int rc = launch_encode_rows(env, obs_dev, st);
     if (rc) return rc;
-    CU(cudaEventRecord(env->ev_rows, st));
-    // the copy engine drains rows [0, 889) and the masks while the SMs compute the single-player block
-    CU(cudaStreamWaitEvent(env->copy_stream, env->ev_rows, 0));
-    CU(cudaMemcpy2DAsync(obs_host, pitch, obs_dev, pitch, head, (size_t)n, cudaMemcpyDeviceToHost, env->copy_stream));
-    CU(cudaMemcpyAsync(masks_host, env->V.masks, (size_t)n * MJX_ACTION_SPACE, cudaMemcpyDeviceToHost, env->copy_stream));
-    if (env->sp_enabled) {
-        rc = launch_sp_block(env, obs_dev, st);
-        if (rc) return rc;
-        CU(cudaEventRecord(env->ev_sp, st));
-        CU(cudaStreamWaitEvent(env->copy_stream, env->ev_sp, 0));
-        CU(cudaMemcpy2DAsync((char*)obs_host + head, pitch, (const char*)obs_dev + head, pitch, pitch - head, (size_t)n,
-                             cudaMemcpyDeviceToHost, env->copy_stream));
+    if (!env->sp_enabled) {
+        CU(cudaEventRecord(env->ev_rows, st));
+        CU(cudaStreamWaitEvent(env->copy_stream, env->ev_rows, 0));
+        CU(cudaMemcpyAsync(obs_host, obs_dev, pitch * (size_t)n, cudaMemcpyDeviceToHost, env->copy_stream));
+    } else {
+        // The single-player block is computed in row groups, each its own DP, so that the finished observations of one
+        // group (one CONTIGUOUS chunk) drain through the copy engine while the SMs work on the next group.
+        constexpr int GROUPS = MJX_HOST_COPY_GROUPS;
+        for (int g = 0; g < GROUPS; g++) {
+            const int r0 = (int)((long long)n * g / GROUPS), r1 = (int)((long long)n * (g + 1) / GROUPS);
+            if (r1 <= r0) continue;
+            rc = launch_sp_block(env, obs_dev, st, r0, r1);
+            if (rc) return rc;
+            CU(cudaEventRecord(env->ev_grp[g], st));
+            CU(cudaStreamWaitEvent(env->copy_stream, env->ev_grp[g], 0));
+            CU(cudaMemcpyAsync((char*)obs_host + pitch * (size_t)r0, (const char*)obs_dev + pitch * (size_t)r0, pitch * (size_t)(r1 - r0),
+                               cudaMemcpyDeviceToHost, env->copy_stream));
+        }
     }
+    CU(cudaMemcpyAsync(masks_host, env->V.masks, (size_t)n * MJX_ACTION_SPACE, cudaMemcpyDeviceToHost, env->copy_stream));
     CU(cudaStreamSynchronize(env->copy_stream));
     return MJX_OK;
 }
