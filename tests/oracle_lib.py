@@ -484,7 +484,7 @@ def run_replay(nonces, keys, replay, *, shuffle_kind=0, quick_eval=True):
     return dict(scores=scores, ranks=ranks, steps=steps)
 
 
-def gameplay_load(events, player_id, *, version=4, always_include_kan_select=True, sp_mode=1, max_moves=600, with_obs=True):
+def gameplay_load(events, player_id, *, version=4, always_include_kan_select=True, sp_mode=1, max_moves=2048, with_obs=True):
     """dataset/gameplay.rs GameplayLoader for one (game, player): events = list of mjai dicts (start_game .. end_game)."""
     evs = (OrcEvent * len(events))(*[event_from_json(e) for e in events])
     rows = {1: 938, 2: 942, 3: 934, 4: 1012}[version]
