@@ -122,3 +122,50 @@ def test_grp_on_the_reference_golden_log():
     # last kyoku: 32700/30200/13100/24000 + hora [0, 20000, -18000, 0] - one riichi stick of the winner, returned to the top
     assert sum(g.take_final_scores()) == 100_000
     assert g.take_rank_by_player() == [1, 0, 3, 2]
+
+
+def test_stat_on_the_reference_golden_log_and_invariants():
+    """stat.rs:263-442 on the seeded example log (hand-checked) and field-wise invariants over emulated self-play logs."""
+    import json
+    import math
+
+    from mortal_b200.stat import Stat
+
+    with open(os.path.join(ROOT, "tests", "golden", "golden_game.jsonl")) as f:
+        events = [json.loads(ln) for ln in f if ln.strip()]
+    st = [Stat.from_game(events, p) for p in range(4)]
+    # 3 kyoku; hora by 0 (ron on 2, riichi), by 1 (ron on 2, no riichi stick of its own counted), by 1 (ron on 2): see the log
+    assert [s.round for s in st] == [3, 3, 3, 3] and [s.agari for s in st] == [1, 2, 0, 0] and [s.houjuu for s in st] == [0, 0, 3, 0]
+    assert st[2].tobi == 1 and [s.rank_1 + s.rank_2 + s.rank_3 + s.rank_4 for s in st] == [1, 1, 1, 1]
+    assert st[1].rank_1 == 1 and st[0].rank_2 == 1 and st[3].rank_3 == 1 and st[2].rank_4 == 1
+    assert sum(s.point for s in st) == 0
+    assert st[0].agari_point_oya == 8700 - 1000 and st[0].riichi_agari == 1  # own stick not counted (stat.rs:336)
+    assert math.isnan(st[3].avg_point_per_agari) and st[2].houjuu_rate == 1.0
+    total = sum(st[1:], st[0])
+    assert total.game == 4 and total.agari == 3 and abs(total.avg_rank - 2.5) < 1e-12
+    assert st[1].avg_pt([90, 45, 0, -135]) == 90.0
+
+
+def test_stat_from_dir_and_field_invariants(tmp_path):
+    import gzip
+    import json
+
+    from mortal_b200 import mjai_log
+    from mortal_b200.stat import COUNTERS, Stat
+    from test_emul_vs_oracle import _selfplay_logs
+
+    games = _selfplay_logs(8, 1, 4321)
+    for g, ev in enumerate(games):
+        ev[0]["names"] = ["hero" if s == g % 4 else "villain" for s in range(4)]
+        with gzip.open(tmp_path / f"{g}.json.gz", "wt") as f:
+            f.write("\n".join(json.dumps(e, separators=(",", ":")) for e in ev) + "\n")
+    hero = Stat.from_dir(str(tmp_path), "hero")
+    villain = Stat.from_dir(str(tmp_path), "villain")
+    assert hero.game == 8 and villain.game == 24
+    n_hora = sum(e["type"] == "hora" for ev in games for e in ev)
+    assert hero.agari + villain.agari == n_hora
+    assert hero.rank_1 + hero.rank_2 + hero.rank_3 + hero.rank_4 == 8
+    assert hero.point + villain.point == 0 and hero.round * 3 == villain.round
+    assert hero.dama_agari + hero.fuuro_agari + hero.riichi_agari == hero.agari
+    assert 1.0 <= hero.avg_rank <= 4.0 and all(getattr(hero, c) >= 0 for c in COUNTERS if "point" not in c)
+    assert str(hero).startswith("Games 8") and "agari_rate" in str(hero)
