@@ -169,3 +169,39 @@ def test_stat_from_dir_and_field_invariants(tmp_path):
     assert hero.dama_agari + hero.fuuro_agari + hero.riichi_agari == hero.agari
     assert 1.0 <= hero.avg_rank <= 4.0 and all(getattr(hero, c) >= 0 for c in COUNTERS if "point" not in c)
     assert str(hero).startswith("Games 8") and "agari_rate" in str(hero)
+
+
+def test_event_codec_round_trip_on_golden_and_selfplay_logs():
+    """mortal_b200.dataset_codec.encode_events is the inverse of mortal_b200.mjai_log.decode_events for everything the replay
+    needs: every event survives a round trip except the payloads the replay does not use (hora / ryukyoku deltas, ura markers)."""
+    import json
+
+    from mortal_b200 import dataset_codec as DC
+    from mortal_b200 import mjai_log
+    from test_emul_vs_oracle import _selfplay_logs
+
+    with open(os.path.join(ROOT, "tests", "golden", "golden_game.jsonl")) as f:
+        golden = [{k: v for k, v in json.loads(ln).items() if k != "meta"} for ln in f if ln.strip()]
+    for events in [golden] + _selfplay_logs(3, 0, 77):
+        hdr, pay = DC.encode_events(events)
+        assert len(hdr) == len(events) and pay.shape == (sum(e["type"] == "start_kyoku" for e in events), 9)
+        # re-expand into the multi-word stream decode_events reads (payload after each start_kyoku, zero deltas after hora/ryukyoku)
+        words, k = [], 0
+        for w in hdr:
+            ty = int(w) & 0xFF
+            if ty in (DC.START_GAME, DC.END_GAME):
+                continue
+            words.append(int(w))
+            if ty == mjai_log.START_KYOKU:
+                words += [int(x) for x in pay[k]]
+                k += 1
+            elif ty in (mjai_log.HORA, mjai_log.RYUKYOKU):
+                words += [0, 0]
+        back = mjai_log.decode_events(words)
+        inner = [e for e in events if e["type"] not in ("start_game", "end_game")]
+        assert len(back) == len(inner)
+        for a, b in zip(back, inner):
+            if b["type"] in ("hora", "ryukyoku"):
+                assert a["type"] == b["type"] and a.get("actor") == b.get("actor") and a.get("target") == b.get("target")
+            else:
+                assert a == b, (a, b)
