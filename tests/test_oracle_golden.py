@@ -155,3 +155,38 @@ def test_rand09_shuffle_is_a_permutation_and_differs():
     L.orc_make_wall(10000, 0x2000, 0, 0, 1, b.ctypes.data)
     assert sorted(a.tolist()) == sorted(b.tolist())
     assert a.tolist() != b.tolist()
+
+
+def test_gameplay_loader_restatement_on_golden_log():
+    """The oracle's restatement of dataset/gameplay.rs is pinned to the reference's own data: on the seeded example log
+    every non-pass move it extracts is, in order, exactly the agent event the log holds for that player (dahai / reach /
+    chi / pon), and where the log carries the agent's `meta.mask_bits` (written by the reference itself) the extracted
+    legal mask equals it."""
+    golden = load_golden()
+    events = [strip_meta(e) for e in golden]
+    tile_id = {name: i for i, name in enumerate(O.TILE_NAMES)}
+    checked_masks = 0
+    for p in range(4):
+        got = O.gameplay_load(events, p, with_obs=False, sp_mode=0)
+        # pass (45) has no event at all; agari (43) shows up as the board's `hora`, not as an agent event
+        moves = [(int(a), got["masks"][i]) for i, a in enumerate(got["actions"]) if a not in (43, 45)]
+        n_hora = sum(e["type"] == "hora" and e["actor"] == p for e in golden)
+        assert int((got["actions"] == 43).sum()) == n_hora, (p, n_hora)
+        logged = [e for e in golden if e.get("actor") == p and e["type"] in AGENT_EVENTS]
+        assert len(moves) == len(logged) and len(moves) > 20, (p, len(moves), len(logged))
+        for (label, mask), e in zip(moves, logged):
+            if e["type"] == "dahai":
+                assert label == tile_id[e["pai"]], (p, e, label)
+            elif e["type"] == "reach":
+                assert label == 37
+            elif e["type"] == "pon":
+                assert label == 41
+            elif e["type"] == "chi":
+                assert label in (38, 39, 40)
+            if "meta" in e and "mask_bits" in e["meta"]:
+                assert sum(1 << i for i in range(46) if mask[i]) == e["meta"]["mask_bits"], (p, e)
+                checked_masks += 1
+        # bookkeeping columns: kyoku index non-decreasing from 0 to 2, apply_gamma exactly on discards / riichi / kans
+        assert got["at_kyoku"][0] == 0 and got["at_kyoku"][-1] == 2 and (np.diff(got["at_kyoku"].astype(int)) >= 0).all()
+        assert (got["apply_gamma"] == (got["actions"] <= 37)).all()
+    assert checked_masks >= 100
