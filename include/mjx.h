@@ -88,6 +88,8 @@ int mjx_env_total_steps(mjx_env* env, void* stream, int64_t* steps);    /* game.
  * mjx_env_read_log copies [n_tables, words_per_table] words and the per-table counts to host (count > capacity = overflow). */
 int mjx_env_enable_log(mjx_env* env, int words_per_table);
 int mjx_env_read_log(mjx_env* env, void* stream, uint64_t* words_host, int32_t* len_host);
+int32_t* mjx_env_log_len_dev(mjx_env* env); /* int32 [n_tables] device view of the per-table word counts (null before enable_log):
+                                              read after every step it tells which events that step wrote (per-decision meta) */
 
 /* ---- log replay: dataset/gameplay.rs:247-449 GameplayLoader ------------------------------------------
  * A job = one (game log, player). `hdr`: the games' events as 64-bit words (csrc/mjx_step.cuh `log_word`; start_game = 15,

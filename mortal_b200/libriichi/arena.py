@@ -8,6 +8,8 @@ engines are called once per cycle per agent like MortalBatchAgent::evaluate (mor
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from ..engine import HostProtocolEngine
@@ -18,6 +20,72 @@ def _adapt(engine):
     if hasattr(engine, "react_device"):
         return engine
     return HostProtocolEngine(engine)
+
+
+class _MetaRecorder:
+    """Collects what agent/mortal.rs:161-186 gen_meta puts into a logged reaction: per step the rows' (table, seat, kan-select,
+    action, legal mask, Q-values, shanten / furiten read back from the v4 observation) and the per-table log length right after
+    every environment step; `finish()` groups them per game for mortal_b200.mjai_log.attach_meta."""
+
+    def __init__(self, n_games: int, version: int):
+        self.n, self.version = n_games, version
+        self.bounds, self.rows, self.q = [], [], {}
+        self.error = None  # the metadata is optional: a failure while recording must never take the game loop down
+
+    def _guard(fn):
+        def wrapped(self, *a, **k):
+            if self.error is not None:
+                return None
+            try:
+                return fn(self, *a, **k)
+            except Exception as exc:
+                self.error = exc
+                return None
+        return wrapped
+
+    @_guard
+    def add_bounds(self, log_len_dev):
+        self.bounds.append(log_len_dev.cpu().numpy().copy())
+
+    @_guard
+    def add_agent(self, cycle, idx, q, eval_ns):
+        self.q.setdefault(cycle, []).append((idx.cpu().numpy(), q.float().cpu().numpy(), int(eval_ns)))
+
+    @_guard
+    def add_rows(self, cycle, tbl, row_seat, actions, masks, obs):
+        sh = fu = None
+        if self.version == 4:  # v4 rows 861 (furiten) and 862-868 (shanten one-hot), obs_repr.rs
+            sh = obs[:, 862:869, 0].argmax(1).cpu().numpy()
+            fu = (obs[:, 861, 0] > 0).cpu().numpy()
+        self.rows.append((cycle, tbl.cpu().numpy(), row_seat.cpu().numpy(), actions.cpu().numpy(), masks.cpu().numpy().astype(bool), sh, fu))
+
+    def finish(self):
+        from ..mjai_log import make_meta
+
+        if self.error is not None:
+            raise self.error
+        decisions = [dict() for _ in range(self.n)]
+        for cycle, tbl, rs, act, masks, sh, fu in self.rows:
+            nr = len(tbl)
+            q_rows = np.zeros((nr, 46), dtype=np.float32)
+            batch, ns = np.zeros(nr, dtype=np.int64), np.zeros(nr, dtype=np.int64)
+            for idx, q, eval_ns in self.q.get(cycle, []):
+                q_rows[idx] = q
+                batch[idx] = len(idx)
+                ns[idx] = eval_ns
+            pos = {(int(tbl[r]), int(rs[r] & 3), bool(rs[r] & 4)): r for r in range(nr)}
+            for (t, seat, kan), r in pos.items():
+                if kan:
+                    continue
+                common = dict(batch_size=int(batch[r]), eval_time_ns=int(ns[r]), shanten=None if sh is None else int(sh[r]),
+                              at_furiten=None if fu is None else bool(fu[r]))
+                kan_meta = None
+                kr = pos.get((t, seat, True))
+                if kr is not None and int(act[r]) == 42:
+                    km = make_meta(int(act[kr]), masks[kr], q_rows[kr], **common)
+                    kan_meta = {k: v for k, v in km.items() if not k.startswith("_") and v is not None}
+                decisions[t].setdefault(cycle, {})[seat] = make_meta(int(act[r]), masks[r], q_rows[r], kan_select=kan_meta, **common)
+        return np.array(self.bounds), decisions
 
 
 class _Arena:
@@ -32,6 +100,8 @@ class _Arena:
         self.record_decisions = False  # test hook: keep (table, step, seat, kan_select, action) of every row
         self.last_decisions = None
         self.log_dir = log_dir  # arena/one_vs_three.rs:26-34: gz mjai logs are written here when set
+        self.log_meta = True    # attach the per-decision meta (q-values, mask bits, ...) to the agent events (mortal.rs:161-186)
+        self.last_meta_error = None
 
     def _challenger_seats(self, game_in_seed: int):
         raise NotImplementedError
@@ -63,8 +133,10 @@ class _Arena:
         for g in range(per):
             for s in self._challenger_seats(g):
                 is_challenger[g, s] = True
+        meta_rec = None
         if self.log_dir is not None:
             env.enable_log()
+            meta_rec = _MetaRecorder(n, versions[0]) if self.log_meta else None
         actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
         guards = [bool(getattr(a, "enable_rule_based_agari_guard", False)) for a in agents]
         q_all = None
@@ -92,6 +164,8 @@ class _Arena:
         while True:
             env.step(None if first else actions, None if first else q_all)
             first = False
+            if meta_rec is not None:
+                meta_rec.add_bounds(env.log_len)
             if host_mode:
                 nr = env.encode_obs_host(h_obs, h_masks)
                 if nr == 0 and env.num_live() == 0:
@@ -103,10 +177,15 @@ class _Arena:
                     for idx, agent in ((np.nonzero(chal_h)[0], agents[0]), (np.nonzero(~chal_h)[0], agents[1])):
                         if idx.size == 0:
                             continue
+                        t_eval = time.perf_counter_ns()
                         a, q = agent.react_host(obs_np, masks_np, idx)
+                        if meta_rec is not None:
+                            meta_rec.add_agent(cycles, torch.from_numpy(idx), torch.from_numpy(q).reshape(-1, 46), time.perf_counter_ns() - t_eval)
                         h_actions[torch.from_numpy(idx)] = torch.from_numpy(a)
                         if h_q is not None:
                             h_q[torch.from_numpy(idx)] = torch.from_numpy(q).reshape(-1, 46)
+                    if meta_rec is not None:
+                        meta_rec.add_rows(cycles, torch.from_numpy(tbl_h).long(), torch.from_numpy(rs_h), h_actions[:nr], h_masks[:nr], h_obs[:nr])
                     actions[:nr].copy_(h_actions[:nr], non_blocking=True)
                     if h_q is not None:
                         q_all[:nr].copy_(h_q[:nr], non_blocking=True)
@@ -128,10 +207,15 @@ class _Arena:
                 for idx, agent in ((chal.nonzero().squeeze(1), agents[0]), ((~chal).nonzero().squeeze(1), agents[1])):
                     if idx.numel() == 0:
                         continue
+                    t_eval = time.perf_counter_ns()
                     a, q = agent.react_device(obs[idx], masks[idx])
                     actions[idx] = a.to(torch.int64)
                     if q_all is not None:
                         q_all[idx] = q.float()
+                    if meta_rec is not None:
+                        meta_rec.add_agent(cycles, idx, q, time.perf_counter_ns() - t_eval)
+                if meta_rec is not None:
+                    meta_rec.add_rows(cycles, tbl, env.row_seat[:nr], actions[:nr], masks, obs)
                 if self.record_decisions:
                     recorded.append(torch.stack([tbl, env.row_step[:nr].long(), seat, (env.row_seat[:nr] >> 2).long() & 1,
                                                  actions[:nr]], dim=1).cpu())
@@ -145,7 +229,14 @@ class _Arena:
             agent_names = [str(getattr(a, "name", "NoName")) for a in agents]
             names = [[agent_names[0] if ic[g % per, seat] else agent_names[1] for seat in range(4)] for g in range(n)]
             seeds = [(int(nonces[g]), int(keys[g])) for g in range(n)]
-            self.last_log_paths = mjai_log.write_logs(self.log_dir, words, lens, seeds, names, "abcd"[:per])
+            bounds = decisions = None
+            if meta_rec is not None:
+                try:
+                    bounds, decisions = meta_rec.finish()
+                except Exception as exc:  # the logs themselves must not depend on the optional metadata
+                    self.last_meta_error = exc
+                    bounds = decisions = None
+            self.last_log_paths = mjai_log.write_logs(self.log_dir, words, lens, seeds, names, "abcd"[:per], bounds, decisions)
         self.last_stats = dict(cycles=cycles, table_steps=int(res["steps"].sum()))
         self.last_results = res
         if self.record_decisions:

@@ -49,6 +49,7 @@ def lib():
         L.emul_env_errs.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_env_enable_log.argtypes = [C.c_void_p, C.c_int]
         L.emul_env_read_log.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emul_env_log_lens.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_env_results.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         if L.emul_init(DATA_DIR.encode()) != 0:
             raise RuntimeError(L.emul_last_error().decode())
@@ -119,6 +120,11 @@ class EmulEnv:
     def enable_log(self, cap=8192):
         self._log_cap = cap
         self.L.emul_env_enable_log(self._h, cap)
+
+    def log_lens(self):
+        lens = np.zeros(self.n_tables, dtype=np.int32)
+        self.L.emul_env_log_lens(self._h, lens.ctypes.data)
+        return lens
 
     def read_log(self):
         words = np.zeros((self.n_tables, self._log_cap), dtype=np.uint64)

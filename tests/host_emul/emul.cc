@@ -214,6 +214,14 @@ void emul_env_enable_log(void* p, int cap) {
     EmulEnv* E = static_cast<EmulEnv*>(p);
     E->log_cap = cap; E->log.assign((size_t)E->n * cap, 0); E->log_len.assign(E->n, 0);
 }
+void emul_env_log_lens(void* p, int32_t* lens) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    memcpy(lens, E->log_len.data(), E->log_len.size() * sizeof(i32));
+}
+void emul_env_row_steps(void* p, uint32_t* steps) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    for (int r = 0; r < E->n_rows[0]; r++) steps[r] = E->row_step[r];
+}
 void emul_env_read_log(void* p, uint64_t* words, int32_t* lens) {
     EmulEnv* E = static_cast<EmulEnv*>(p);
     memcpy(words, E->log.data(), E->log.size() * sizeof(u64));

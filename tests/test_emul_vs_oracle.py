@@ -5,6 +5,8 @@ built with -DMJX_HOST_EMUL and driven by the shared counter-based test policies;
 (table, step, seat, legal-mask bits, action) and every final score / rank / step count must be equal.
 The `-m gpu` tests repeat this through the real kernels and the C ABI.
 """
+import json
+
 import numpy as np
 import pytest
 
@@ -298,3 +300,70 @@ def test_log_replay_observations_match_gameplay_loader_emulated():
             d = np.abs(got - ref["obs"])
             assert not ((d != 0) & ((ref["obs"] == 0) | (ref["obs"] == 1))).any() and d.max() <= 1e-6
         rep.close()
+
+
+@pytest.mark.parametrize("quick_eval,policy_kind", [(False, 0), (True, 1)])
+def test_log_meta_attachment_emulated(quick_eval, policy_kind):
+    """mortal_b200.mjai_log.attach_meta: with the per-step log bounds every agent event gets exactly the decision that caused it
+    (its action decodes to that event), pass decisions and overridden calls attach to nothing, and with quick-eval the events
+    that had no decision row stay without meta, as in the reference (mortal.rs:161-186, 210-242)."""
+    from mortal_b200 import mjai_log
+
+    n = 10
+    nonces = np.arange(2600, 2600 + n, dtype=np.uint64)
+    keys = np.full(n, 8, dtype=np.uint64)
+    env = E.EmulEnv(nonces, keys, enable_quick_eval=quick_eval)
+    env.enable_log()
+    bounds, decisions = [], [dict() for _ in range(n)]
+    acts = None
+    for cyc in range(4000):
+        env.step(acts)
+        bounds.append(env.log_lens().copy())
+        rt, rs, masks = env.rows()
+        acts = env.policy_test(policy_kind)
+        rows = {}
+        for r in range(len(rt)):
+            rows[(int(rt[r]), int(rs[r] & 3), bool(rs[r] & 4))] = r
+        for (t, seat, kan), r in rows.items():
+            if kan:
+                continue
+            q = np.where(masks[r], np.float32(0.25) * np.arange(46, dtype=np.float32), -np.inf)
+            kr = rows.get((t, seat, True))
+            kan_meta = None
+            if kr is not None and int(acts[r]) == 42:
+                kan_meta = {k: v for k, v in mjai_log.make_meta(int(acts[kr]), masks[kr], q).items() if not k.startswith("_") and v is not None}
+            decisions[t].setdefault(cyc, {})[seat] = mjai_log.make_meta(int(acts[r]), masks[r], q, kan_select=kan_meta)
+        if env.num_live() == 0:
+            break
+    words, lens = env.read_log()
+    env.close()
+    bounds = np.array(bounds)
+    tile_id = {name: i for i, name in enumerate(mjai_log.TILE_NAMES)}
+    total_events = total_meta = 0
+    for t in range(n):
+        events, offsets = mjai_log.decode_events(words[t, : int(lens[t])], with_offsets=True)
+        got = mjai_log.attach_meta(events, offsets, [int(b) for b in bounds[:, t]], decisions[t])
+        agent = [e for e in events if e["type"] in mjai_log.AGENT_EVENT_ACTIONS and (e["type"] != "ryukyoku" or "meta" in e)]
+        with_meta = [e for e in agent if "meta" in e]
+        assert got == len(with_meta)
+        n_applied = sum(1 for c in decisions[t].values() for m in c.values() if m["_action"] != 45)
+        # every decision row that was not a pass produced at most one event; calls overridden by a higher-priority reaction none
+        assert len(with_meta) <= n_applied
+        if not quick_eval:
+            unmatched = [e for e in agent if "meta" not in e]
+            assert not unmatched, unmatched[:3]  # no quick-eval: every agent event has a decision behind it
+        for e in with_meta:
+            m = e["meta"]
+            assert bin(m["mask_bits"]).count("1") == len(m["q_values"]) and m["is_greedy"] is True and "_action" not in m
+            if e["type"] == "dahai":  # the legal mask of the decision allows exactly this discard
+                assert (m["mask_bits"] >> tile_id[e["pai"]]) & 1
+            if e["type"] in ("ankan", "kakan") and not quick_eval:  # with quick-eval a single kan candidate needs no second row
+                assert "kan_select" in m and bin(m["kan_select"]["mask_bits"]).count("1") >= 1
+        # the serialised line keeps serde's field order: event fields, then meta
+        line = json.dumps(with_meta[0], separators=(",", ":"))
+        assert line.startswith('{"type":"') and ',"meta":{"q_values":[' in line
+        total_events += len(agent)
+        total_meta += len(with_meta)
+    assert total_meta > 3000 and (quick_eval or total_meta == total_events)
+    if quick_eval:
+        assert total_meta < total_events  # some discards were forced and never reached the engine

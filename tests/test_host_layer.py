@@ -205,3 +205,64 @@ def test_event_codec_round_trip_on_golden_and_selfplay_logs():
                 assert a["type"] == b["type"] and a.get("actor") == b.get("actor") and a.get("target") == b.get("target")
             else:
                 assert a == b, (a, b)
+
+
+def test_arena_meta_recorder_writes_meta_into_logs(tmp_path):
+    """The arena's _MetaRecorder + mjai_log.write_logs on CPU tensors (driven by the emulated env with the call pattern of
+    _Arena._run): the written .json.gz files carry a `meta` with the reference's fields on the agent events, the events
+    themselves are unchanged, and a recorder failure degrades to logs without meta instead of an exception."""
+    import gzip
+    import json
+
+    import torch
+
+    import emul_lib as E
+    from mortal_b200 import mjai_log
+    from mortal_b200.libriichi.arena import _MetaRecorder
+
+    n = 4
+    nonces = np.arange(3300, 3300 + n, dtype=np.uint64)
+    keys = np.full(n, 2, dtype=np.uint64)
+    env = E.EmulEnv(nonces, keys, enable_quick_eval=True)
+    env.enable_log()
+    rec = _MetaRecorder(n, 4)
+    acts, cycles = None, 0
+    while True:
+        env.step(acts)
+        rec.add_bounds(torch.from_numpy(env.log_lens()))
+        rt, rs, masks = env.rows()
+        nr = len(rt)
+        if nr == 0 and env.num_live() == 0:
+            break
+        acts = env.policy_test(1)
+        if nr:
+            obs = torch.from_numpy(env.encode_obs(sp=False, version=4))
+            idx = torch.arange(nr)
+            q = torch.where(torch.from_numpy(masks), torch.rand(nr, 46), torch.full((nr, 46), -float("inf")))
+            rec.add_agent(cycles, idx, q, 12345)
+            rec.add_rows(cycles, torch.from_numpy(rt).long(), torch.from_numpy(rs), torch.from_numpy(acts[:nr]), torch.from_numpy(masks), obs)
+        cycles += 1
+    words, lens = env.read_log()
+    env.close()
+    bounds, decisions = rec.finish()
+    seeds = [(int(nonces[g]), 2) for g in range(n)]
+    names = [["a", "b", "c", "d"]] * n
+    paths = mjai_log.write_logs(str(tmp_path / "m"), words, lens, seeds, names, "abcd", bounds, decisions)
+    plain = mjai_log.write_logs(str(tmp_path / "p"), words, lens, seeds, names, "abcd")
+    n_meta = 0
+    for pm, pp in zip(paths, plain):
+        with_meta = [json.loads(ln) for ln in gzip.open(pm, "rt")]
+        without = [json.loads(ln) for ln in gzip.open(pp, "rt")]
+        assert [{k: v for k, v in e.items() if k != "meta"} for e in with_meta] == without
+        for e in with_meta:
+            if "meta" in e:
+                m = e["meta"]
+                assert list(m)[:5] == ["q_values", "mask_bits", "is_greedy", "batch_size", "eval_time_ns"] and "shanten" in m and "at_furiten" in m
+                assert 0 <= m["shanten"] <= 6 and m["eval_time_ns"] == 12345 and all(np.isfinite(m["q_values"]))
+                n_meta += 1
+    assert n_meta > 800
+    broken = _MetaRecorder(n, 4)
+    broken.add_rows(0, None, None, None, None, None)  # bad input: recorded as an error, not raised
+    assert broken.error is not None
+    with pytest.raises(Exception):
+        broken.finish()
