@@ -6,8 +6,7 @@ always_include_kan_select, augmented)`, `.load_gz_log_files(filenames) -> list[l
 take_shantens / take_player_id`. The logs are replayed on device (csrc/mjx_replay.cuh) and the observations come from the
 same encoder kernels self-play uses. Differences, stated rather than hidden: `take_obs()` / `take_masks()` return ONE tensor
 per Gameplay ([n_moves, C, 34] float32 / [n_moves, 46] bool, CUDA by default, `host=True` for numpy) instead of a list of
-per-move arrays; the oracle (invisible) observation and tile augmentation are not built (`oracle=True` / `augmented=True`
-raise NotImplementedError); logs must carry full information (no "?" tiles). `Grp` (dataset/grp.rs:19-164) is plain host-side
+per-move arrays; the oracle (invisible) observation is not built (`oracle=True` raises NotImplementedError); logs must carry full information (no "?" tiles). `Grp` (dataset/grp.rs:19-164) is plain host-side
 log arithmetic and is provided in Python.
 """
 from __future__ import annotations
@@ -130,8 +129,6 @@ class GameplayLoader:
                  always_include_kan_select: bool = True, augmented: bool = False, device: int = 0):
         if oracle:
             raise NotImplementedError("oracle (invisible) observations are not built (SURVEY.md §8f N4); pass oracle=False")
-        if augmented:
-            raise NotImplementedError("tile augmentation is not built")
         self.version, self.oracle, self.trust_seed = version, oracle, trust_seed
         self.player_names, self.excludes = list(player_names or []), list(excludes or [])
         self.always_include_kan_select, self.augmented = always_include_kan_select, augmented
@@ -159,6 +156,8 @@ class GameplayLoader:
         import torch
 
         games = [dataset_codec.parse_log(t) for t in texts]
+        if self.augmented:  # gameplay.rs:126-128: manzu <-> pinzu on every event before anything else
+            games = [dataset_codec.augment_events(ev) for ev in games]
         for ev in games:
             if not ev or ev[0].get("type") != "start_game" or len(ev) < 4:
                 raise ValueError("empty or invalid game log")

@@ -56,6 +56,31 @@ def encode_events(events):
     return np.array(hdr, dtype=np.uint64), np.array(pay, dtype=np.uint64).reshape(-1, 9)
 
 
+def _swap_tile(name: str) -> str:
+    """tile.rs:154-167 Tile::augment: manzu <-> pinzu, red fives stay red, souzu / honours / unknown unchanged"""
+    if len(name) >= 2 and name[0].isdigit() and name[1] in "mp":
+        return name[0] + ("p" if name[1] == "m" else "m") + name[2:]
+    return name
+
+
+def augment_events(events):
+    """mjai/event.rs:187-217 Event::augment applied to a whole game: returns new event dicts, the input is not modified"""
+    out = []
+    for ev in events:
+        e = dict(ev)
+        for key in ("pai", "dora_marker", "bakaze"):
+            if key in e:
+                e[key] = _swap_tile(e[key])
+        if "consumed" in e:
+            e["consumed"] = [_swap_tile(x) for x in e["consumed"]]
+        if "tehais" in e:
+            e["tehais"] = [[_swap_tile(x) for x in hand] for hand in e["tehais"]]
+        if e.get("ura_markers") is not None:
+            e["ura_markers"] = [_swap_tile(x) for x in e["ura_markers"]]
+        out.append(e)
+    return out
+
+
 def parse_log(text: str):
     return [json.loads(ln) for ln in text.splitlines() if ln.strip()]
 

@@ -367,3 +367,39 @@ def test_log_meta_attachment_emulated(quick_eval, policy_kind):
     assert total_meta > 3000 and (quick_eval or total_meta == total_events)
     if quick_eval:
         assert total_meta < total_events  # some discards were forced and never reached the engine
+
+
+def test_log_replay_with_augmentation_emulated():
+    """gameplay.rs:126-128 + mjai/event.rs:187-217: the manzu <-> pinzu augmentation is an involution on the events, and the
+    replay of the augmented game matches the oracle loader on the same augmented events (labels move with the tiles)."""
+    from mortal_b200 import dataset_codec as DC
+
+    games = _selfplay_logs(3, 1, 5100)
+    aug = [DC.augment_events(ev) for ev in games]
+    assert [DC.augment_events(ev) for ev in aug] == games and aug != games
+    sk = next(e for e in games[0] if e["type"] == "start_kyoku")
+    ak = next(e for e in aug[0] if e["type"] == "start_kyoku")
+    assert ak["bakaze"] == sk["bakaze"] and ak["scores"] == sk["scores"]
+    assert [[t[0] + {"m": "p", "p": "m"}.get(t[1], t[1]) + t[2:] if t[0].isdigit() else t for t in hand] for hand in sk["tehais"]] == ak["tehais"]
+    jobs = DC.build_jobs(aug, [[0, 1, 2, 3]] * len(aug))
+    rep = E.EmulReplay(jobs)
+    per_job = [[] for _ in range(rep.n_tables)]
+    for _ in range(3000):
+        rep.replay_step()
+        if rep.num_rows():
+            rt, _, _ = rep.rows()
+            lab, _ = rep.row_labels()
+            for r in range(len(rt)):
+                per_job[rt[r]].append(int(lab[r]))
+        if rep.live == 0:
+            break
+    assert (rep.errs() == 0).all()
+    swap = lambda a: a + 9 if a < 9 else a - 9 if a < 18 else {34: 35, 35: 34}.get(a, a)
+    for job in range(rep.n_tables):
+        g, pid = int(jobs["job_game"][job]), int(jobs["players"][job])
+        ref_aug = O.gameplay_load(aug[g], pid, with_obs=False, sp_mode=0)["actions"].tolist()
+        ref_raw = O.gameplay_load(games[g], pid, with_obs=False, sp_mode=0)["actions"].tolist()
+        assert per_job[job] == ref_aug
+        # discards (and kan-select tiles) move with the suits, everything else keeps its label
+        assert len(ref_aug) == len(ref_raw) and all(b == a or b == swap(a) for a, b in zip(ref_raw, ref_aug))
+    rep.close()
