@@ -266,3 +266,38 @@ def test_arena_meta_recorder_writes_meta_into_logs(tmp_path):
     assert broken.error is not None
     with pytest.raises(Exception):
         broken.finish()
+
+
+def test_policy_net_fast_path_equals_stock_forward_on_cpu():
+    """mortal_b200/model.py: the BN-folded, channels-last (1x3 conv2d) inference path is the same function as the stock module
+    (mortal/model.py architecture) in fp32; the DQN head's masked dueling combination (mortal/model.py DQN) and the nucleus
+    sampler behave as specified."""
+    import torch
+
+    from mortal_b200.engine import sample_top_p
+    from mortal_b200.model import DQN, Brain
+
+    torch.manual_seed(0)
+    brain = Brain(conv_channels=32, num_blocks=3).eval()
+    for m in brain.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.normal_(); m.running_var.uniform_(0.5, 2); m.weight.data.normal_(1, 0.2); m.bias.data.normal_()
+    obs = (torch.rand(7, 1012, 34) < 0.05).float()
+    with torch.no_grad():
+        ref = brain(obs)
+        brain.prepare_fast(None)
+        fast = brain.forward_fast(obs)
+    assert ref.shape == (7, 1024) and (ref - fast).abs().max() < 1e-5
+    dqn = DQN().eval()
+    mask = torch.rand(7, 46) > 0.5
+    mask[:, 45] = True
+    with torch.no_grad():
+        q = dqn(ref, mask)
+        v, a = dqn.net(ref).split((1, 46), dim=-1)
+    assert torch.isneginf(q[~mask]).all()
+    want = v + a - (a * mask).sum(-1, keepdim=True) / mask.sum(-1, keepdim=True)
+    assert torch.allclose(q[mask], want[mask], atol=1e-6)
+    logits = torch.tensor([[2.0, 1.0, 0.5, -1.0, -float("inf")]]).repeat(4000, 1)
+    s = sample_top_p(logits, 0.7)
+    assert set(s.tolist()) <= {0, 1} and 0.68 < (s == 0).float().mean() < 0.78  # nucleus {0, 1}: 0.61 / (0.61 + 0.224)
+    assert sample_top_p(logits[:3], 0.0).tolist() == [0, 0, 0]
