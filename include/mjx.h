@@ -82,6 +82,11 @@ int mjx_env_num_rows(mjx_env* env, void* stream, int* n_rows);          /* rows 
 int mjx_env_num_live(mjx_env* env, void* stream, int* n_live);          /* tables still playing */
 int mjx_env_total_steps(mjx_env* env, void* stream, int64_t* steps);    /* game.rs:304 `actions` counter */
 
+/* One blocking read-back per BatchGame::run cycle: out4 = { rows emitted by the last step, tables still playing,
+ * tables that have failed so far (err != 0; game.rs:288,292 aborts the batch at that cycle, so should the caller),
+ * single-player arena overflows so far (see mjx_env_sp_overflows) }. */
+int mjx_env_poll(mjx_env* env, void* stream, int* out4);
+
 /* arena/result.rs:19-51 GameResult.game_log: record every table's mjai events on device (compact 64-bit words, layout in
  * csrc/mjx_step.cuh `log_word`; mortal_b200/mjai_log.py turns them into the reference's JSON lines). Call
  * mjx_env_enable_log before the first step; `words_per_table` bounds one hanchan (a kyoku is ~170 words; 8192 is ample).
@@ -159,7 +164,9 @@ typedef struct mjx_agari_out { /* algo/agari.rs:66-74 Agari + algo/point.rs Poin
     uint8_t fu, han, yakuman;
     int32_t ron, tsumo_ko, tsumo_oya; /* -1 where point.rs would panic */
 } mjx_agari_out;
-/* mode 0 = search_yakus (agari.rs:212), 1 = agari (agari.rs:225), 2 = has_yaku (agari.rs:206) */
+/* mode 0 = search_yakus (agari.rs:212), 1 = agari (agari.rs:225), 2 = has_yaku (agari.rs:206),
+ * 3 = check_ankan_after_riichi(tehai, len_div3 = additional_hans, tile = winning_tile, strict = false) (agari.rs:854-912;
+ *     the call state/update.rs:278 makes): out.kind = 1 when the kan is allowed */
 int mjx_agari(const mjx_agari_in* in_dev, mjx_agari_out* out_dev, int n, int mode, void* stream);
 
 /* Host-buffer conveniences (H2D + kernel + D2H), the shape a foreign-language binding would call. */

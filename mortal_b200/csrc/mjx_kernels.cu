@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(EnvView V, Tables T) {
     c.lane = lane;
     c.df = s_scratch[warp].dora_factor;
     if (V.log) { c.log = V.log + (size_t)table * V.log_cap; c.log_n = V.log_len + table; c.log_cap = V.log_cap; }
+    const i32 err_before = c.S->err;
     const bool live = step_table(c, V, table);
     __syncwarp();
     uint4* gdst = reinterpret_cast<uint4*>(g);
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(EnvView V, Tables T) {
         atomicAdd(&V.counters[0], 1ull);
         atomicAdd(&V.counters[1], 1ull);
     }
+    if (lane == 0 && err_before == 0 && c.S->err != 0) atomicAdd(&V.counters[2], 1ull);  // tables that failed so far (mjx_env_poll)
 }
 
 // Log replay (csrc/mjx_replay.cuh): one warp = one (game log, player) job, advanced to its next logged decision.
@@ -403,6 +405,8 @@ __global__ void __launch_bounds__(128) k_agari(Tables T, const mjx_agari_in* __r
     o.kind = 0; o.fu = o.han = o.yakuman = 0; o.ron = o.tsumo_ko = o.tsumo_oya = 0;
     if (mode == 2) {
         o.kind = has_yaku(T, a) ? 1 : 0;
+    } else if (mode == 3) {  // agari.rs:854-912 check_ankan_after_riichi, strict = false (what update.rs:278 asks)
+        o.kind = ankan_after_riichi_ok(T, q.tehai, q.additional_hans, q.winning_tile) ? 1 : 0;
     } else {
         Agari r = mode == 0 ? search_yakus(T, a, false) : agari_with(T, a, q.additional_hans, q.doras);
         if (r.kind != 0) {
@@ -561,7 +565,7 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
     CU(cudaMalloc(&V.done, sizeof(i32) * (size_t)n_tables));
     CU(cudaMalloc(&V.steps, sizeof(i32) * (size_t)n_tables));
     CU(cudaMalloc(&V.err, sizeof(i32) * (size_t)n_tables));
-    CU(cudaMalloc(&V.counters, sizeof(unsigned long long) * 2));
+    CU(cudaMalloc(&V.counters, sizeof(unsigned long long) * 4));
     CU(cudaMalloc(&env->d_nonces, sizeof(u64) * (size_t)n_tables));
     CU(cudaMalloc(&env->d_keys, sizeof(u64) * (size_t)n_tables));
     CU(cudaMalloc(&env->d_dummy_actions, sizeof(i64) * cap));
@@ -612,7 +616,7 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
     CU(cudaMemset(V.scores, 0, sizeof(i32) * 4 * (size_t)n_tables));
     CU(cudaMemset(V.ranks, 0, 4 * (size_t)n_tables));
     CU(cudaMemset(V.n_rows, 0, sizeof(i32)));
-    CU(cudaMemset(V.counters, 0, sizeof(unsigned long long) * 2));
+    CU(cudaMemset(V.counters, 0, sizeof(unsigned long long) * 4));
     CU(cudaMemcpy(env->d_nonces, nonces, sizeof(u64) * (size_t)n_tables, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(env->d_keys, keys, sizeof(u64) * (size_t)n_tables, cudaMemcpyHostToDevice));
     k_init_tables<<<(n_tables + 127) / 128, 128>>>(V.tables, n_tables, env->d_nonces, env->d_keys, shuffle_kind, V.done,
@@ -883,6 +887,21 @@ int mjx_env_num_rows(mjx_env* env, void* stream, int* n_rows) {
     return MJX_OK;
 }
 
+int mjx_env_poll(mjx_env* env, void* stream, int* out4) {
+    if (!env || !out4) return fail(MJX_ERR_ARG, "mjx_env_poll: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long c[4] = {0, 0, 0, 0};
+    int sp[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(&out4[0], env->V.n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c, env->V.counters, sizeof c, cudaMemcpyDeviceToHost, st));
+    if (env->sp.counters) CU(cudaMemcpyAsync(sp, env->sp.counters, sizeof sp, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out4[1] = (int)c[0];
+    out4[2] = (int)c[2];
+    out4[3] = sp[3] + (sp[2] ? 1 : 0);
+    return MJX_OK;
+}
+
 int mjx_env_num_live(mjx_env* env, void* stream, int* n_live) {
     if (!env || !n_live) return fail(MJX_ERR_ARG, "mjx_env_num_live: bad arguments");
     unsigned long long v = 0;
@@ -980,7 +999,7 @@ int mjx_shanten(const uint8_t* tiles_dev, const uint8_t* len_dev, int8_t* out_de
 
 int mjx_agari(const mjx_agari_in* in_dev, mjx_agari_out* out_dev, int n, int mode, void* stream) {
     if (!g_ready) return fail(MJX_ERR_STATE, "mjx_agari: call mjx_init first");
-    if (mode < 0 || mode > 2) return fail(MJX_ERR_ARG, "mjx_agari: mode must be 0, 1 or 2");
+    if (mode < 0 || mode > 3) return fail(MJX_ERR_ARG, "mjx_agari: mode must be 0..3");
     if (n <= 0) return MJX_OK;
     k_agari<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g_T, in_dev, out_dev, n, mode);
     CU(cudaGetLastError());

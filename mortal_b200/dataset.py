@@ -180,8 +180,12 @@ class GameplayLoader:
                 if env.num_live() == 0:
                     break
             res = env.results()
+            sp_overflows = env.sp_overflows() if self.version == 4 else 0
         finally:
             env.close()
+        if sp_overflows:
+            raise RuntimeError(f"single-player state arena overflowed in {sp_overflows} replay step(s): observation rows 889-1011 "
+                               "would be zero; load fewer logs per call")
         if (res["err"] != 0).any():
             bad = int(np.nonzero(res["err"])[0][0])
             raise RuntimeError(f"replay job {bad} (log {int(jobs['job_game'][bad])}, player {int(jobs['players'][bad])}) failed "

@@ -8,6 +8,8 @@ still works through `HostProtocolEngine`, which pays the device->host->device ro
 """
 from __future__ import annotations
 
+import copy
+
 import numpy as np
 import torch
 
@@ -23,11 +25,12 @@ class DeviceEngine:
         self.dqn = dqn.to(self.device).eval()
         # BN-folded bf16 inference path when the brain offers one (mortal_b200.model.Brain); plain autocast otherwise
         self.fast = bool(fast_inference and enable_amp and hasattr(self.brain, "prepare_fast") and self.device.type == "cuda")
+        self._fast_brain = None
         if self.fast:
             from . import _lib
 
             _lib.init(self.device.index or 0)  # the fused elementwise kernels live in libmjx
-            self.brain.prepare_fast(torch.bfloat16)
+            self.refresh()
         self.version = version
         self.is_oracle = is_oracle
         self.enable_amp = enable_amp
@@ -39,11 +42,21 @@ class DeviceEngine:
         self.top_p = top_p
         self._graphs = {}
 
-    @torch.inference_mode()
-    def react_device(self, obs: torch.Tensor, masks: torch.Tensor):
-        """obs [B, C, 34] f32 cuda, masks [B, 46] bool cuda -> (actions int64 [B], q [B, 46])"""
+    @torch.no_grad()
+    def refresh(self):
+        """(Re)build the bf16 BN-folded inference copy from the caller's module. The caller's `brain` is never touched:
+        mortal/train.py:317 and player.py:120 hand the live training model to the engine and keep training it afterwards, so its
+        fp32 parameters and BatchNorm statistics must survive. Call again after the weights changed."""
         if self.fast:
-            q = self.dqn(self.brain.forward_fast(obs).float(), masks)
+            self._fast_brain = copy.deepcopy(self.brain).eval()
+            self._fast_brain.prepare_fast(torch.bfloat16)
+            self._graphs = {}
+
+    @torch.inference_mode()
+    def react_device(self, obs: torch.Tensor, masks: torch.Tensor, return_greedy: bool = False):
+        """obs [B, C, 34] f32 cuda, masks [B, 46] bool cuda -> (actions int64 [B], q [B, 46][, is_greedy bool [B]])"""
+        if self.fast:
+            q = self.dqn(self._fast_brain.forward_fast(obs).float(), masks)
         else:
             with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.enable_amp):
                 q = self.dqn(self.brain(obs), masks)
@@ -55,6 +68,11 @@ class DeviceEngine:
             actions = torch.where(greedy, q.argmax(-1), sampled)
         else:
             actions = q.argmax(-1)
+            greedy = None
+        if return_greedy:
+            if greedy is None:
+                greedy = torch.ones(obs.shape[0], dtype=torch.bool, device=self.device)
+            return actions, q, greedy
         return actions, q
 
     @torch.inference_mode()
@@ -87,8 +105,8 @@ class DeviceEngine:
     def react_batch(self, obs, masks, invisible_obs):
         o = torch.as_tensor(np.stack(obs, axis=0), device=self.device)
         m = torch.as_tensor(np.stack(masks, axis=0), device=self.device)
-        actions, q = self.react_device(o, m)
-        return actions.tolist(), q.float().tolist(), m.tolist(), [True] * o.shape[0]
+        actions, q, greedy = self.react_device(o, m, return_greedy=True)
+        return actions.tolist(), q.float().tolist(), m.tolist(), greedy.tolist()
 
 
 def sample_top_p(logits, p):

@@ -167,6 +167,12 @@ class BatchEnv:
         _lib.check(self.L.mjx_env_num_rows(self._h, self._stream(), C.byref(n)), "mjx_env_num_rows")
         return n.value
 
+    def poll(self):
+        """(rows of the last step, live tables, failed tables so far, SP arena overflows so far) in one read-back"""
+        out = (C.c_int * 4)()
+        _lib.check(self.L.mjx_env_poll(self._h, self._stream(), out), "mjx_env_poll")
+        return out[0], out[1], out[2], out[3]
+
     def num_live(self) -> int:
         n = C.c_int(0)
         _lib.check(self.L.mjx_env_num_live(self._h, self._stream(), C.byref(n)), "mjx_env_num_live")

@@ -102,6 +102,8 @@ class _Arena:
         self.log_dir = log_dir  # arena/one_vs_three.rs:26-34: gz mjai logs are written here when set
         self.log_meta = True    # attach the per-decision meta (q-values, mask bits, ...) to the agent events (mortal.rs:161-186)
         self.last_meta_error = None
+        self.max_cycles = 0     # test hook: stop after this many BatchGame::run cycles (0 = play every table to the end)
+        self.last_decision_masks = None  # with record_decisions: the legal mask (46 bits) each recorded row was decided under
 
     def _challenger_seats(self, game_in_seed: int):
         raise NotImplementedError
@@ -160,16 +162,38 @@ class _Arena:
             ic_host = is_challenger.cpu().numpy()
         first = True
         cycles = 0
-        recorded = []
+        recorded, recorded_masks = [], []
+        mask_weights = (1 << torch.arange(46, dtype=torch.int64))
+
+        def check_health():
+            # game.rs:288,292: an error from any table aborts the whole batch at that cycle (`?`); so does a single-player arena
+            # overflow, which would otherwise hand zeroed rows 889-1011 to the engines
+            nr_, live_, n_err, sp_ovf = env.poll()
+            if n_err:
+                res_ = env.results()
+                bad = int(np.nonzero(res_["err"])[0][0])
+                env.close()
+                raise RuntimeError(f"table {bad} (seed {int(nonces[bad])},{int(keys[bad])}) failed at cycle {cycles} with mjx error code "
+                                   f"{int(res_['err'][bad])} (invalid action or inconsistent state; board.rs:527-532)")
+            if sp_ovf:
+                env.close()
+                raise RuntimeError(f"single-player state arena overflowed at cycle {cycles}: observation rows 889-1011 would be zero; "
+                                   "run fewer tables per environment")
+            return nr_, live_
+
         while True:
+            if self.max_cycles and cycles >= self.max_cycles:
+                break
             env.step(None if first else actions, None if first else q_all)
             first = False
             if meta_rec is not None:
                 meta_rec.add_bounds(env.log_len)
+            nr, n_live = check_health()
             if host_mode:
-                nr = env.encode_obs_host(h_obs, h_masks)
-                if nr == 0 and env.num_live() == 0:
+                if nr == 0 and n_live == 0:
                     break
+                if nr > 0:
+                    assert env.encode_obs_host(h_obs, h_masks) == nr
                 if nr > 0:
                     tbl_h = env.row_table[:nr].cpu().numpy()
                     rs_h = env.row_seat[:nr].cpu().numpy()
@@ -193,10 +217,10 @@ class _Arena:
                         recorded.append(torch.stack([torch.from_numpy(tbl_h).long(), env.row_step[:nr].cpu().long(),
                                                      torch.from_numpy(rs_h & 3).long(), torch.from_numpy((rs_h >> 2) & 1).long(),
                                                      h_actions[:nr].clone()], dim=1))
+                        recorded_masks.append((h_masks[:nr].long() * mask_weights).sum(1))
                 cycles += 1
                 continue
-            nr = env.num_rows()
-            if nr == 0 and env.num_live() == 0:
+            if nr == 0 and n_live == 0:
                 break
             if nr > 0:
                 obs = env.encode_obs()[:nr]
@@ -219,6 +243,7 @@ class _Arena:
                 if self.record_decisions:
                     recorded.append(torch.stack([tbl, env.row_step[:nr].long(), seat, (env.row_seat[:nr] >> 2).long() & 1,
                                                  actions[:nr]], dim=1).cpu())
+                    recorded_masks.append((masks.long() * mask_weights.to(dev)).sum(1).cpu())
             cycles += 1
         res = env.results()
         if self.log_dir is not None:  # one_vs_three.rs:195-225: one {seed}_{key}_{split}.json.gz per game
@@ -237,11 +262,15 @@ class _Arena:
                     self.last_meta_error = exc
                     bounds = decisions = None
             self.last_log_paths = mjai_log.write_logs(self.log_dir, words, lens, seeds, names, "abcd"[:per], bounds, decisions)
-        self.last_stats = dict(cycles=cycles, table_steps=int(res["steps"].sum()))
+        self.last_stats = dict(cycles=cycles, table_steps=int(res["steps"].sum()), sp_overflows=env.sp_overflows())
         self.last_results = res
         if self.record_decisions:
             self.last_decisions = torch.cat(recorded).numpy() if recorded else np.zeros((0, 5), dtype=np.int64)
+            self.last_decision_masks = torch.cat(recorded_masks).numpy() if recorded_masks else np.zeros(0, dtype=np.int64)
         env.close()
+        if self.last_stats["sp_overflows"]:
+            raise RuntimeError("single-player state arena overflowed during the run: observation rows 889-1011 were zero in "
+                               f"{self.last_stats['sp_overflows']} step(s)")
         if (res["err"] != 0).any():
             bad = int(np.nonzero(res["err"])[0][0])
             raise RuntimeError(f"table {bad} failed with mjx error code {int(res['err'][bad])}")

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <memory>
 #include <thread>
 
 namespace orc { extern long g_sp_stats[8]; }
@@ -429,134 +430,238 @@ struct orc_run_out {
     double seconds;
 };
 
-static void run_range(const orc_run_cfg& cfg, const uint64_t* nonces, const uint64_t* keys, const int32_t* table_ids,
-                      int lo, int hi, int32_t* scores, uint8_t* ranks, int32_t* steps, int64_t* trace, int64_t trace_cap,
-                      std::atomic<int64_t>* trace_len, std::atomic<int64_t>* total_steps, std::atomic<int64_t>* total_rows,
-                      std::string* err) {
-    try {
-        std::vector<float> obs;
-        if (cfg.encode_obs) obs.resize((size_t)obs_rows(cfg.encode_obs) * 34);
-        for (int t = lo; t < hi; t++) {
-            Game g;
-            g.seed_nonce = nonces[t]; g.seed_key = keys[t]; g.shuffle_kind = cfg.shuffle_kind;
-            g.table = table_ids ? table_ids[t] : t;
-            AgentConfig ac;
-            ac.enable_quick_eval = cfg.enable_quick_eval != 0;
-            ac.enable_rule_based_agari_guard = cfg.enable_agari_guard != 0;
-            AgentConfig cfgs[4] = {ac, ac, ac, ac};
-            int64_t rows = 0;
-            PolicyFn pol = [&](const Scene& sc, const u8* mask, float*) {
-                rows++;
-                if (cfg.encode_obs && (int64_t)sc.step_idx >= cfg.encode_from_step) {
-                    u8 m2[46];
-                    sc.state->encode_obs(cfg.encode_obs, sc.is_kan_select, obs.data(), m2, cfg.sp_mode);
-                }
-                int a = test_policy(cfg.policy_kind, sc, g.seed_nonce, g.seed_key, mask);
-                if (trace) {
-                    int64_t at = trace_len->fetch_add(1);
-                    if (at < trace_cap) {
-                        u64 bits = 0;
-                        for (int i = 0; i < 46; i++) if (mask[i]) bits |= 1ull << i;
-                        int64_t* r = trace + at * 6;
-                        r[0] = sc.table; r[1] = (int64_t)sc.step_idx; r[2] = sc.seat; r[3] = a;
-                        r[4] = sc.is_kan_select; r[5] = (int64_t)bits;
-                    }
-                }
-                return a;
-            };
-            PolicyFn pols[4] = {pol, pol, pol, pol};
-            int64_t n_steps = 0;
-            for (;;) {
-                g.poll();
-                if (g.commit(cfgs, pols, nullptr)) break;
-                n_steps++;
-                if (cfg.max_steps_per_table > 0 && n_steps >= cfg.max_steps_per_table) break;
-            }
-            for (int i = 0; i < 4; i++) scores[t * 4 + i] = g.scores[i];
-            rankings(g.scores, nullptr, ranks + t * 4);
-            steps[t] = (int32_t)n_steps;
-            total_steps->fetch_add(std::max<int64_t>(0, n_steps - cfg.encode_from_step));
-            total_rows->fetch_add(rows);
+// One table's run, kept alive across the two phases of a batch (fast-forward, then the timed / sampled part).
+struct TableRun {
+    Game g;
+    int64_t n_steps = 0, rows = 0;
+    bool done = false;
+};
+
+// Optional observation sampling (parity at benchmark scale): `samples` = int64 [m, 4] rows (table, step_idx, seat, kan_select)
+// sorted lexicographically; the observation / mask of every decision found there is written to obs_out[idx] / masks_out[idx].
+struct SampleSink {
+    const int64_t* samples = nullptr;
+    int64_t m = 0;
+    int version = 4;
+    float* obs_out = nullptr;
+    uint8_t* masks_out = nullptr;
+    uint8_t* found = nullptr;
+    int64_t find(const Scene& sc) const {
+        const int64_t key[4] = {sc.table, (int64_t)sc.step_idx, sc.seat, sc.is_kan_select ? 1 : 0};
+        int64_t lo = 0, hi = m;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) / 2;
+            const int64_t* r = samples + mid * 4;
+            bool less = false;
+            for (int q = 0; q < 4; q++) { if (r[q] != key[q]) { less = r[q] < key[q]; break; } }
+            if (less) lo = mid + 1; else hi = mid;
         }
-    } catch (const std::exception& e) { *err = e.what(); }
+        if (lo >= m) return -1;
+        const int64_t* r = samples + lo * 4;
+        return (r[0] == key[0] && r[1] == key[1] && r[2] == key[2] && r[3] == key[3]) ? lo : -1;
+    }
+};
+
+// Advance table t until it ends or has played `until` table-steps (0 = to the end). Rows at step_idx >= encode_from are
+// encoded when cfg.encode_obs is set (the timed work of the CPU arm).
+static void run_table(const orc_run_cfg& cfg, TableRun& tr, int t, int64_t until, int64_t encode_from, std::vector<float>& obs,
+                      int64_t* trace, int64_t trace_cap, std::atomic<int64_t>* trace_len, const SampleSink* sink) {
+    Game& g = tr.g;
+    AgentConfig ac;
+    ac.enable_quick_eval = cfg.enable_quick_eval != 0;
+    ac.enable_rule_based_agari_guard = cfg.enable_agari_guard != 0;
+    AgentConfig cfgs[4] = {ac, ac, ac, ac};
+    PolicyFn pol = [&](const Scene& sc, const u8* mask, float*) {
+        tr.rows++;
+        if (cfg.encode_obs && (int64_t)sc.step_idx >= encode_from) {
+            u8 m2[46];
+            sc.state->encode_obs(cfg.encode_obs, sc.is_kan_select, obs.data(), m2, cfg.sp_mode);
+        }
+        if (sink && sink->m) {
+            const int64_t at = sink->find(sc);
+            if (at >= 0) {
+                const size_t stride = (size_t)obs_rows(sink->version) * 34;
+                sc.state->encode_obs(sink->version, sc.is_kan_select, sink->obs_out + (size_t)at * stride,
+                                     sink->masks_out + (size_t)at * 46, cfg.sp_mode);
+                sink->found[at] = 1;
+            }
+        }
+        int a = test_policy(cfg.policy_kind, sc, g.seed_nonce, g.seed_key, mask);
+        if (trace) {
+            int64_t at = trace_len->fetch_add(1);
+            if (at < trace_cap) {
+                u64 bits = 0;
+                for (int i = 0; i < 46; i++) if (mask[i]) bits |= 1ull << i;
+                int64_t* r = trace + at * 6;
+                r[0] = sc.table; r[1] = (int64_t)sc.step_idx; r[2] = sc.seat; r[3] = a;
+                r[4] = sc.is_kan_select; r[5] = (int64_t)bits;
+            }
+        }
+        return a;
+    };
+    PolicyFn pols[4] = {pol, pol, pol, pol};
+    while (!tr.done && (until <= 0 || tr.n_steps < until)) {
+        g.poll();
+        if (g.commit(cfgs, pols, nullptr)) { tr.done = true; break; }
+        tr.n_steps++;
+    }
+    (void)t;
 }
 
-int orc_run_batch(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t* keys, const int32_t* table_ids,
-                  int32_t* scores, uint8_t* ranks, int32_t* steps, int64_t* trace, int64_t trace_cap,
-                  int64_t* trace_len_out, orc_run_out* out) {
+// Two phases, each with dynamic table hand-out over n_threads workers: (1) untimed fast-forward of every table to
+// `encode_from_step` table-steps (skipped when 0), (2) the timed part up to `max_steps_per_table` (0 = to the end).
+// `seconds` clocks phase 2 only; `table_steps` counts phase-2 steps only.
+static int run_batch_impl(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t* keys, const int32_t* table_ids,
+                          int32_t* scores, uint8_t* ranks, int32_t* steps, int64_t* trace, int64_t trace_cap,
+                          int64_t* trace_len_out, orc_run_out* out, const SampleSink* sink) {
     try {
-        int n = cfg->n_tables;
-        int nt = std::max(1, cfg->n_threads);
-        std::atomic<int64_t> tlen(0), tsteps(0), trows(0);
-        std::vector<std::string> errs(nt);
-        auto t0 = std::chrono::steady_clock::now();
-        std::vector<std::thread> th;
-        for (int k = 0; k < nt; k++) {
-            int lo = (int)((int64_t)n * k / nt), hi = (int)((int64_t)n * (k + 1) / nt);
-            th.emplace_back(run_range, std::cref(*cfg), nonces, keys, table_ids, lo, hi, scores, ranks, steps, trace,
-                            trace_cap, &tlen, &tsteps, &trows, &errs[k]);
+        const int n = cfg->n_tables;
+        const int nt = std::max(1, cfg->n_threads);
+        std::atomic<int64_t> tlen(0);
+        std::vector<std::unique_ptr<TableRun>> runs(n);
+        for (int t = 0; t < n; t++) {
+            runs[t].reset(new TableRun());
+            Game& g = runs[t]->g;
+            g.seed_nonce = nonces[t]; g.seed_key = keys[t]; g.shuffle_kind = cfg->shuffle_kind;
+            g.table = table_ids ? table_ids[t] : t;
         }
-        for (auto& t : th) t.join();
+        std::vector<std::string> errs(nt);
+        auto phase = [&](int64_t until, int64_t encode_from) {
+            std::atomic<int> next(0);
+            std::vector<std::thread> th;
+            for (int k = 0; k < nt; k++)
+                th.emplace_back([&, k]() {
+                    try {
+                        std::vector<float> obs;
+                        if (cfg->encode_obs) obs.resize((size_t)obs_rows(cfg->encode_obs) * 34);
+                        for (;;) {
+                            const int t = next.fetch_add(1);
+                            if (t >= n) break;
+                            run_table(*cfg, *runs[t], t, until, encode_from, obs, trace, trace_cap, &tlen, sink);
+                        }
+                    } catch (const std::exception& e) { errs[k] = e.what(); }
+                });
+            for (auto& t : th) t.join();
+            for (auto& e : errs) if (!e.empty()) throw OrcError(e);
+        };
+        const int64_t ff = cfg->encode_from_step;
+        if (ff > 0) phase(ff, ff);
+        int64_t before = 0;
+        for (int t = 0; t < n; t++) before += runs[t]->n_steps;
+        auto t0 = std::chrono::steady_clock::now();
+        phase(cfg->max_steps_per_table, ff);
         auto t1 = std::chrono::steady_clock::now();
-        for (auto& e : errs) if (!e.empty()) throw OrcError(e);
+        int64_t total = 0, rows = 0;
+        for (int t = 0; t < n; t++) {
+            const Game& g = runs[t]->g;
+            for (int i = 0; i < 4; i++) scores[t * 4 + i] = g.scores[i];
+            rankings(g.scores, nullptr, ranks + t * 4);
+            steps[t] = (int32_t)runs[t]->n_steps;
+            total += runs[t]->n_steps;
+            rows += runs[t]->rows;
+        }
         if (trace_len_out) *trace_len_out = tlen.load();
         if (out) {
-            out->table_steps = tsteps.load();
-            out->obs_rows = trows.load();
+            out->table_steps = total - before;
+            out->obs_rows = rows;
             out->seconds = std::chrono::duration<double>(t1 - t0).count();
         }
         return 0;
     } catch (const std::exception& e) { return fail(e); }
 }
 
+int orc_run_batch(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t* keys, const int32_t* table_ids,
+                  int32_t* scores, uint8_t* ranks, int32_t* steps, int64_t* trace, int64_t trace_cap,
+                  int64_t* trace_len_out, orc_run_out* out) {
+    return run_batch_impl(cfg, nonces, keys, table_ids, scores, ranks, steps, trace, trace_cap, trace_len_out, out, nullptr);
+}
+
+// The same run, additionally encoding the decisions listed in `samples` (see SampleSink) with obs `version`.
+int orc_run_sample_obs(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t* keys, int32_t* scores, uint8_t* ranks,
+                       int32_t* steps, const int64_t* samples, int64_t m, int version, float* obs_out, uint8_t* masks_out,
+                       uint8_t* found) {
+    SampleSink sink;
+    sink.samples = samples; sink.m = m; sink.version = version; sink.obs_out = obs_out; sink.masks_out = masks_out; sink.found = found;
+    return run_batch_impl(cfg, nonces, keys, nullptr, scores, ranks, steps, nullptr, 0, nullptr, nullptr, &sink);
+}
+
 void orc_sp_stats(long* out) { for (int i = 0; i < 8; i++) { out[i] = orc::g_sp_stats[i]; orc::g_sp_stats[i] = 0; } }
 
 // Action-replay parity (SURVEY.md §8d protocol ii): drive the oracle with decisions recorded elsewhere.
 // replay rows: [table, step_idx, seat, kan_select, action], sorted lexicographically by the first four.
-// Every replayed action must be legal in the oracle's own mask, otherwise the call fails.
-int orc_run_replay(int n_tables, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int enable_quick_eval,
-                   const int64_t* replay, int64_t n_replay, int32_t* scores, uint8_t* ranks, int32_t* steps) {
+// Every replayed action must be legal in the oracle's own mask, otherwise the call fails. `mask_bits` (optional, aligned
+// with the replay rows) = the legal mask the recorder saw, compared with the oracle's bit for bit. `max_steps` > 0 stops
+// every table after that many table-steps (the recording was cut at the same point); scores are then the running scores.
+int orc_run_replay2(int n_tables, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int enable_quick_eval,
+                    const int64_t* replay, int64_t n_replay, const int64_t* mask_bits, int64_t max_steps, int n_threads,
+                    int32_t* scores, uint8_t* ranks, int32_t* steps) {
     try {
-        int64_t used = 0;
-        for (int t = 0; t < n_tables; t++) {
-            Game g;
-            g.seed_nonce = nonces[t]; g.seed_key = keys[t]; g.shuffle_kind = shuffle_kind; g.table = t;
-            AgentConfig ac;
-            ac.enable_quick_eval = enable_quick_eval != 0;
-            AgentConfig cfgs[4] = {ac, ac, ac, ac};
-            PolicyFn pol = [&](const Scene& sc, const u8* mask, float*) {
-                int64_t key[4] = {sc.table, (int64_t)sc.step_idx, sc.seat, sc.is_kan_select ? 1 : 0};
-                int64_t lo = 0, hi = n_replay;
-                while (lo < hi) {
-                    int64_t mid = (lo + hi) / 2;
-                    const int64_t* r = replay + mid * 5;
-                    bool less = false;
-                    for (int q = 0; q < 4; q++) { if (r[q] != key[q]) { less = r[q] < key[q]; break; } }
-                    if (less) lo = mid + 1; else hi = mid;
+        std::atomic<int64_t> used(0);
+        std::atomic<int> next(0);
+        const int nt = std::max(1, n_threads);
+        std::vector<std::string> errs(nt);
+        auto work = [&](int k) {
+            try {
+                for (;;) {
+                    const int t = next.fetch_add(1);
+                    if (t >= n_tables) break;
+                    Game g;
+                    g.seed_nonce = nonces[t]; g.seed_key = keys[t]; g.shuffle_kind = shuffle_kind; g.table = t;
+                    AgentConfig ac;
+                    ac.enable_quick_eval = enable_quick_eval != 0;
+                    AgentConfig cfgs[4] = {ac, ac, ac, ac};
+                    PolicyFn pol = [&](const Scene& sc, const u8* mask, float*) {
+                        int64_t key[4] = {sc.table, (int64_t)sc.step_idx, sc.seat, sc.is_kan_select ? 1 : 0};
+                        int64_t lo = 0, hi = n_replay;
+                        while (lo < hi) {
+                            int64_t mid = (lo + hi) / 2;
+                            const int64_t* r = replay + mid * 5;
+                            bool less = false;
+                            for (int q = 0; q < 4; q++) { if (r[q] != key[q]) { less = r[q] < key[q]; break; } }
+                            if (less) lo = mid + 1; else hi = mid;
+                        }
+                        const int64_t* r = replay + lo * 5;
+                        if (lo >= n_replay || r[0] != key[0] || r[1] != key[1] || r[2] != key[2] || r[3] != key[3])
+                            throw OrcError("replay: no recorded decision for table " + std::to_string(sc.table) + " step " +
+                                           std::to_string(sc.step_idx) + " seat " + std::to_string(sc.seat));
+                        int a = (int)r[4];
+                        if (a < 0 || a >= 46 || !mask[a]) throw OrcError("replay: recorded action is illegal in the oracle");
+                        if (mask_bits) {
+                            u64 bits = 0;
+                            for (int i = 0; i < 46; i++) if (mask[i]) bits |= 1ull << i;
+                            if ((int64_t)bits != mask_bits[lo])
+                                throw OrcError("replay: recorded legal mask differs from the oracle's at table " + std::to_string(sc.table) +
+                                               " step " + std::to_string(sc.step_idx) + " seat " + std::to_string(sc.seat));
+                        }
+                        used.fetch_add(1);
+                        return a;
+                    };
+                    PolicyFn pols[4] = {pol, pol, pol, pol};
+                    int64_t n_steps = 0;
+                    for (;;) {
+                        g.poll();
+                        if (g.commit(cfgs, pols, nullptr)) break;
+                        n_steps++;
+                        if (max_steps > 0 && n_steps >= max_steps) break;
+                    }
+                    for (int i = 0; i < 4; i++) scores[t * 4 + i] = g.scores[i];
+                    rankings(g.scores, nullptr, ranks + t * 4);
+                    steps[t] = (int32_t)n_steps;
                 }
-                const int64_t* r = replay + lo * 5;
-                if (lo >= n_replay || r[0] != key[0] || r[1] != key[1] || r[2] != key[2] || r[3] != key[3])
-                    throw OrcError("replay: no recorded decision for table " + std::to_string(sc.table) + " step " +
-                                   std::to_string(sc.step_idx) + " seat " + std::to_string(sc.seat));
-                int a = (int)r[4];
-                if (a < 0 || a >= 46 || !mask[a]) throw OrcError("replay: recorded action is illegal in the oracle");
-                used++;
-                return a;
-            };
-            PolicyFn pols[4] = {pol, pol, pol, pol};
-            int64_t n_steps = 0;
-            for (;;) {
-                g.poll();
-                if (g.commit(cfgs, pols, nullptr)) break;
-                n_steps++;
-            }
-            for (int i = 0; i < 4; i++) scores[t * 4 + i] = g.scores[i];
-            rankings(g.scores, nullptr, ranks + t * 4);
-            steps[t] = (int32_t)n_steps;
-        }
-        if (used != n_replay) throw OrcError("replay: " + std::to_string(n_replay - used) + " recorded decisions were never requested");
+            } catch (const std::exception& e) { errs[k] = e.what(); }
+        };
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; k++) th.emplace_back(work, k);
+        for (auto& t : th) t.join();
+        for (auto& e : errs) if (!e.empty()) throw OrcError(e);
+        if (used.load() != n_replay)
+            throw OrcError("replay: " + std::to_string(n_replay - used.load()) + " recorded decisions were never requested");
         return 0;
     } catch (const std::exception& e) { return fail(e); }
+}
+int orc_run_replay(int n_tables, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int enable_quick_eval,
+                   const int64_t* replay, int64_t n_replay, int32_t* scores, uint8_t* ranks, int32_t* steps) {
+    return orc_run_replay2(n_tables, nonces, keys, shuffle_kind, enable_quick_eval, replay, n_replay, nullptr, 0, 1, scores, ranks, steps);
 }
 
 uint64_t orc_policy_hash(uint64_t nonce, uint64_t key, uint64_t table, uint64_t step_idx, uint32_t seat, uint32_t kan) {

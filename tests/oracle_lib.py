@@ -198,6 +198,10 @@ def lib():
                                 C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(RunOut)]
     L.orc_run_replay.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                  C.c_void_p, C.c_void_p]
+    L.orc_run_replay2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_run_sample_obs.argtypes = [C.POINTER(RunCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_policy_hash.restype = C.c_uint64
     L.orc_policy_hash.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
     if L.orc_init(DATA_DIR.encode()) != 0:
@@ -466,22 +470,56 @@ def run_batch(nonces, keys, *, shuffle_kind=0, policy_kind=1, quick_eval=True, a
     return res
 
 
-def run_replay(nonces, keys, replay, *, shuffle_kind=0, quick_eval=True):
-    """replay: int64 [m, 5] rows (table, step, seat, kan_select, action) recorded from another implementation."""
+def run_replay(nonces, keys, replay, *, shuffle_kind=0, quick_eval=True, mask_bits=None, max_steps=0, n_threads=1):
+    """replay: int64 [m, 5] rows (table, step, seat, kan_select, action) recorded from another implementation;
+    mask_bits: optional int64 [m] legal masks the recorder saw (compared bit for bit); max_steps: the recording was cut
+    after that many table-steps per table (0 = whole hanchans)."""
     n = len(nonces)
     nonces = np.ascontiguousarray(nonces, dtype=np.uint64)
     keys = np.ascontiguousarray(keys, dtype=np.uint64)
     rp = np.ascontiguousarray(replay, dtype=np.int64).reshape(-1, 5)
     order = np.lexsort((rp[:, 3], rp[:, 2], rp[:, 1], rp[:, 0]))
     rp = np.ascontiguousarray(rp[order])
+    mb = None if mask_bits is None else np.ascontiguousarray(np.asarray(mask_bits, dtype=np.int64)[order])
     scores = np.zeros((n, 4), dtype=np.int32)
     ranks = np.zeros((n, 4), dtype=np.uint8)
     steps = np.zeros(n, dtype=np.int32)
-    rc = lib().orc_run_replay(n, nonces.ctypes.data, keys.ctypes.data, shuffle_kind, int(quick_eval), rp.ctypes.data,
-                              len(rp), scores.ctypes.data, ranks.ctypes.data, steps.ctypes.data)
+    rc = lib().orc_run_replay2(n, nonces.ctypes.data, keys.ctypes.data, shuffle_kind, int(quick_eval), rp.ctypes.data,
+                               len(rp), None if mb is None else mb.ctypes.data, max_steps, n_threads,
+                               scores.ctypes.data, ranks.ctypes.data, steps.ctypes.data)
     if rc != 0:
         raise RuntimeError(err())
     return dict(scores=scores, ranks=ranks, steps=steps)
+
+
+def run_sample_obs(nonces, keys, samples, *, version=4, shuffle_kind=0, policy_kind=1, quick_eval=True, sp_mode=1,
+                   n_threads=1, max_steps=0):
+    """Replay the tables with the built-in counter-based policy and encode the decisions listed in `samples`
+    (int64 [m, 4] rows (table, step_idx, seat, kan_select)) -> (obs f32 [m, rows, 34], masks bool [m, 46], found bool [m]),
+    in the order of `samples`."""
+    n = len(nonces)
+    nonces = np.ascontiguousarray(nonces, dtype=np.uint64)
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    sm = np.ascontiguousarray(samples, dtype=np.int64).reshape(-1, 4)
+    order = np.lexsort((sm[:, 3], sm[:, 2], sm[:, 1], sm[:, 0]))
+    srt = np.ascontiguousarray(sm[order])
+    m = len(srt)
+    rows = {1: 938, 2: 942, 3: 934, 4: 1012}[version]
+    obs = np.zeros((m, rows, 34), dtype=np.float32)
+    masks = np.zeros((m, 46), dtype=np.uint8)
+    found = np.zeros(m, dtype=np.uint8)
+    scores = np.zeros((n, 4), dtype=np.int32)
+    ranks = np.zeros((n, 4), dtype=np.uint8)
+    steps = np.zeros(n, dtype=np.int32)
+    cfg = RunCfg(n, shuffle_kind, policy_kind, int(quick_eval), 0, 0, sp_mode, n_threads, max_steps, 0)
+    rc = lib().orc_run_sample_obs(C.byref(cfg), nonces.ctypes.data, keys.ctypes.data, scores.ctypes.data, ranks.ctypes.data,
+                                  steps.ctypes.data, srt.ctypes.data, m, version, obs.ctypes.data, masks.ctypes.data,
+                                  found.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(err())
+    inv = np.empty(m, dtype=np.int64)
+    inv[order] = np.arange(m)
+    return obs[inv], masks[inv].astype(bool), found[inv].astype(bool)
 
 
 def gameplay_load(events, player_id, *, version=4, always_include_kan_select=True, sp_mode=1, max_moves=2048, with_obs=True):
