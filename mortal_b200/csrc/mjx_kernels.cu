@@ -264,87 +264,60 @@ constexpr int SP_WARPS = 4;
 constexpr int MJX_HOST_COPY_GROUPS = 4;  // mjx_env_encode_obs_host: row groups of the SP block / D2H pipeline
 
 __global__ void k_sp_begin(SpGlobal G) {
-    if (threadIdx.x < SP_SLOTS) G.slot_count[threadIdx.x] = 0;
+    if (threadIdx.x < SP_SLOTS) G.wl_count[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
-        if (G.counters[2]) G.counters[3] += 1;  // an overflow happened in the previous step
-        G.counters[0] = 0; G.counters[1] = 0; G.counters[2] = 0; G.counters[6] = 0; G.counters[7] = 0;
+        if (G.counters[2]) G.counters[3] += 1;  // an overflow happened in the previous block
+        G.counters[0] = 0; G.counters[1] = 0; G.counters[2] = 0; G.counters[4] = 0; G.counters[5] = 0;
     }
 }
 
-#define SP_KERNEL_PROLOGUE                                                                      \
-    __shared__ SpWarpScratch s_ws[SP_WARPS];                                                    \
+// one warp per observation row (init / finalize)
+#define SP_ROW_PROLOGUE                                                                         \
+    __shared__ u8 s_df[SP_WARPS][40];                                                           \
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                 \
     const int gwarp = blockIdx.x * SP_WARPS + warp, nwarps = gridDim.x * SP_WARPS;              \
-    SpCtx s; s.G = G; s.T = T; s.ws = &s_ws[warp]; s.lane = lane;                               \
-    Ctx c; c.S = nullptr; c.W = nullptr; c.T = T; c.lane = lane; c.df = nullptr;
+    SpCtx s; s.G = G; s.T = T; s.df = s_df[warp]; s.lane = lane;
 
 __global__ void __launch_bounds__(SP_WARPS * 32) k_sp_init(SpGlobal G, Tables T, EnvView V, int row_lo, int row_hi) {
-    SP_KERNEL_PROLOGUE
-    (void)c;
+    SP_ROW_PROLOGUE
     const int n_rows = min(*V.n_rows, row_hi);
     for (int row = row_lo + gwarp; row < n_rows; row += nwarps)
         sp_stage_init(s, V.tables + V.row_table[row], row, V.row_table[row], V.row_seat[row] & 3);
 }
 
-__global__ void __launch_bounds__(SP_WARPS * 32, 4) k_sp_expand(SpGlobal G, Tables T, int slot) {
-    SP_KERNEL_PROLOGUE
-    const int n = min(G.slot_count[slot], G.slot_cap);
-    const i32* list = G.slot_list + (size_t)slot * G.slot_cap;
-    if (lane == 0) {
-        SpWarpScratch& ws = s_ws[warp];
-        ws.a_node = ws.a_node_end = ws.a_pos = ws.a_pos_end = ws.a_edge = ws.a_edge_end = 0;
-        ws.created = ws.created_edges = 0;
-    }
-    __syncwarp();
-    for (int i = gwarp; i < n; i += nwarps) {
-        const int node = list[i];
-        if (node >= 0) sp_expand(s, c, node, slot);  // negative = hole (unused tail of a reserved chunk)
-    }
-    __syncwarp();
-    if (lane == 0) {  // statistics: states / edges actually created (the allocation counters include chunk tails)
-        if (s_ws[warp].created) atomicAdd(&G.counters[6], s_ws[warp].created);
-        if (s_ws[warp].created_edges) atomicAdd(&G.counters[7], s_ws[warp].created_edges);
-    }
+// KIND 0: D level, 1: W level, 2: the tenpai W level (csrc/mjx_sp.cuh sp_expand_batch): one CTA = batches of 32 states
+template <int KIND>
+__global__ void __launch_bounds__(SP_THREADS) k_sp_expand(SpGlobal G, Tables T, int level) {
+    __shared__ SpExpandBatch sb;
+    SpBlk B; B.tid = threadIdx.x; B.nthr = blockDim.x; B.bid = blockIdx.x; B.nblk = gridDim.x;
+    sp_expand_level<KIND>(G, T, sb, B, level);
 }
 
-// KIND 0: D-state (per-turn best discard), 1: W-state above tenpai, 2: tenpai W-state (scores the winning draws)
 template <int KIND>
-__global__ void __launch_bounds__(SP_WARPS * 32, KIND == 2 ? 3 : (KIND == 1 ? 4 : 8)) k_sp_eval(SpGlobal G, Tables T, int slot) {
-    SP_KERNEL_PROLOGUE
-    const int n = min(G.slot_count[slot], G.slot_cap);
-    const i32* list = G.slot_list + (size_t)slot * G.slot_cap;
-    const int k = sp_slot_shanten(slot);
-    if (KIND == 0) {
-        // two D-states per warp, one per half-warp (sp_eval_d2); no warp-level sync inside, the halves just diverge
-        const int hw = lane >> 4;
-        for (int i = gwarp * 2; i < n; i += nwarps * 2) sp_eval_d2(s, i + hw < n ? list[i + hw] : -1);
-    } else {
-        // two W-states per warp, one per half-warp (csrc/mjx_sp.cuh sp_eval_w2)
-        __shared__ SpEvalScratch s_es[SP_WARPS];
-        const int hw = lane >> 4;
-        for (int i = gwarp * 2; i < n; i += nwarps * 2) {
-            const int node = i + hw < n ? list[i + hw] : -1;
-            if (KIND == 1) sp_eval_w2<false>(s, s_es[warp], node, k);
-            else sp_eval_w2<true>(s, s_es[warp], node, 0);
-        }
-    }
+__global__ void __launch_bounds__(SP_THREADS) k_sp_eval(SpGlobal G, int level) {
+    __shared__ SpEvalBatch sb;
+    SpBlk B; B.tid = threadIdx.x; B.nthr = blockDim.x; B.bid = blockIdx.x; B.nblk = gridDim.x;
+    sp_eval_level<KIND>(G, sb, B, level);
 }
 
 __global__ void k_sp_mark(SpGlobal G, int which) { G.counters[4 + which] = min(G.counters[1], G.edge_cap); }
 
 __global__ void __launch_bounds__(128) k_sp_score(SpGlobal G, Tables T) {
-    SpCtx s; s.G = G; s.T = T; s.ws = nullptr; s.lane = threadIdx.x & 31;
     const int b = G.counters[4], e_end = G.counters[5];
-    for (int e = b + blockIdx.x * blockDim.x + threadIdx.x; e < e_end; e += gridDim.x * blockDim.x) sp_score_edge(s, e);
+    for (int e = b + blockIdx.x * blockDim.x + threadIdx.x; e < e_end; e += gridDim.x * blockDim.x) sp_score_edge(G, T, e);
 }
 
 __global__ void __launch_bounds__(SP_WARPS * 32) k_sp_finalize(SpGlobal G, Tables T, EnvView V, float* __restrict__ obs, int row_lo,
                                                                int row_hi) {
-    SP_KERNEL_PROLOGUE
-    (void)c;
+    SP_ROW_PROLOGUE
     const int n_rows = min(*V.n_rows, row_hi);
     for (int row = row_lo + gwarp; row < n_rows; row += nwarps)
         sp_stage_finalize(s, row, obs + (size_t)row * OBS_ROWS_V4 * OBS_COLS);
+}
+
+__global__ void __launch_bounds__(256) k_sp_release(SpGlobal G) {
+    SpBlk B; B.tid = threadIdx.x; B.nthr = blockDim.x; B.bid = blockIdx.x; B.nblk = gridDim.x;
+    sp_release(G, B);
 }
 
 __global__ void k_policy_test(EnvView V, int kind, i64* actions, i64* trace, float* q_out) {
@@ -583,33 +556,30 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
     }
     {
         SpGlobal& G = env->sp;
-        G.node_cap = n_tables * 2048 > (1 << 20) ? n_tables * 2048 : (1 << 20);  // ~0.4 KB per state
-        if (G.node_cap > (1 << 24) - 2) G.node_cap = (1 << 24) - 2;  // 24-bit index field of the hash entries
-        G.slot_cap = G.node_cap;
-        G.edge_cap = G.node_cap * 6;
-        G.score_cap = G.edge_cap / 2;
-        // ~1.3x the arena capacity: a typical step fills a third of the arena, so the table stays under ~25%
-        // load and (32 MB at 4096 tables) inside the 126 MB L2; the 24-bit index field bounds node_cap at 16M
-        int hc = 1;
-        while (hc < G.node_cap + G.node_cap / 4) hc <<= 1;
+        // state table: the slot index is the state id; ~3K slots per table keeps the load under ~20 % in the heaviest steps seen
+        long long want = (long long)n_tables * 3072;
+        if (const char* e = getenv("MJX_SP_SLOTS_PER_TABLE")) want = (long long)n_tables * atoll(e);
+        int hc = 1 << 20;
+        while (hc < want && hc < (1 << 26)) hc <<= 1;
         G.hash_cap = hc;
+        G.wl_cap = hc / 4;       // per level
+        G.edge_cap = hc * 2;
+        G.score_cap = hc;
         CU(cudaMalloc(&G.rows, cap * sizeof(SpRow)));
-        CU(cudaMalloc(&G.keys, (size_t)G.node_cap * sizeof(SpKey)));
-        CU(cudaMalloc(&G.sigs, (size_t)G.node_cap * sizeof(SpSig)));
-        CU(cudaMalloc(&G.node_row, (size_t)G.node_cap * sizeof(i32)));
-        CU(cudaMalloc(&G.vals, (size_t)G.node_cap * 3 * SP_T_MAX * sizeof(float)));
-        CU(cudaMalloc(&G.edge_begin, (size_t)G.node_cap * sizeof(u32)));
-        CU(cudaMalloc(&G.n_edges, (size_t)G.node_cap));
-        CU(cudaMalloc(&G.edge_child, (size_t)G.edge_cap * sizeof(u32)));
-        CU(cudaMalloc(&G.edge_meta, (size_t)G.edge_cap * sizeof(u16)));
-        CU(cudaMalloc(&G.edge_owner, (size_t)G.edge_cap * sizeof(u32)));
+        CU(cudaMalloc(&G.hkey, (size_t)G.hash_cap * sizeof(u64)));
+        CU(cudaMalloc(&G.nsig, (size_t)G.hash_cap * sizeof(SpSigP)));
+        CU(cudaMalloc(&G.einfo, (size_t)G.hash_cap * sizeof(u64)));
+        CU(cudaMalloc(&G.vals, (size_t)G.hash_cap * SP_VALS * sizeof(float)));
+        CU(cudaMalloc(&G.echild, (size_t)G.edge_cap * sizeof(u32)));
+        CU(cudaMalloc(&G.emeta, (size_t)G.edge_cap * sizeof(u16)));
+        CU(cudaMalloc(&G.eowner, (size_t)G.edge_cap * sizeof(u32)));
         CU(cudaMalloc(&G.leaf_scores, (size_t)G.score_cap * 4 * sizeof(float)));
-        CU(cudaMalloc(&G.hash, (size_t)G.hash_cap * sizeof(u32)));
-        CU(cudaMalloc(&G.slot_list, (size_t)SP_SLOTS * G.slot_cap * sizeof(i32)));
-        CU(cudaMalloc(&G.slot_count, SP_SLOTS * sizeof(i32)));
+        CU(cudaMalloc(&G.wl, (size_t)SP_SLOTS * G.wl_cap * sizeof(u32)));
+        CU(cudaMalloc(&G.wl_count, SP_SLOTS * sizeof(i32)));
         CU(cudaMalloc(&G.counters, 8 * sizeof(i32)));
         CU(cudaMemset(G.counters, 0, 8 * sizeof(i32)));
-        CU(cudaMemset(G.slot_count, 0, SP_SLOTS * sizeof(i32)));
+        CU(cudaMemset(G.wl_count, 0, SP_SLOTS * sizeof(i32)));
+        CU(cudaMemset(G.hkey, 0xFF, (size_t)G.hash_cap * sizeof(u64)));  // SP_EMPTY; afterwards k_sp_release frees what a block used
     }
     CU(cudaMemset(env->d_dummy_actions, 0, sizeof(i64) * cap));
     CU(cudaMemset(V.masks, 0, cap * ACTION_SPACE));
@@ -640,9 +610,8 @@ void mjx_env_destroy(mjx_env* env) {
     for (int i = 0; i < 3; i++) if (env->ev_enc[i]) cudaEventDestroy(env->ev_enc[i]);
     cudaFree(env->d_guard); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len);
     SpGlobal& G = env->sp;
-    cudaFree(G.rows); cudaFree(G.keys); cudaFree(G.sigs); cudaFree(G.node_row); cudaFree(G.vals); cudaFree(G.edge_begin); cudaFree(G.n_edges);
-    cudaFree(G.edge_child); cudaFree(G.edge_meta); cudaFree(G.edge_owner); cudaFree(G.leaf_scores); cudaFree(G.hash); cudaFree(G.slot_list); cudaFree(G.slot_count);
-    cudaFree(G.counters);
+    cudaFree(G.rows); cudaFree(G.hkey); cudaFree(G.nsig); cudaFree(G.einfo); cudaFree(G.vals); cudaFree(G.echild); cudaFree(G.emeta);
+    cudaFree(G.eowner); cudaFree(G.leaf_scores); cudaFree(G.wl); cudaFree(G.wl_count); cudaFree(G.counters);
     if (env->copy_stream) { cudaStreamDestroy(env->copy_stream); cudaEventDestroy(env->ev_rows); cudaEventDestroy(env->ev_sp); for (int g = 0; g < MJX_HOST_COPY_GROUPS; g++) cudaEventDestroy(env->ev_grp[g]); }
     delete env;
 }
@@ -687,29 +656,32 @@ static int launch_encode_rows(mjx_env* env, float* obs_dev, cudaStream_t st) {
     return MJX_OK;
 }
 
-// single-player block (rows 889..1011): init -> expand slots 0..7 -> score -> evaluate slots 7..0 -> finalize
+// single-player block (rows 889..1011): init -> expand levels 0..7 -> score -> evaluate levels 7..0 -> finalize -> release
 // rows [row_lo, row_hi) of the step form one DP (the whole step by default; mjx_env_encode_obs_host runs it in row groups)
 static int launch_sp_block(mjx_env* env, float* obs_dev, cudaStream_t st, int row_lo = 0, int row_hi = 0x7fffffff) {
     if (!env->sp_enabled) return MJX_OK;
     const SpGlobal& G = env->sp;
-    const int grid = g_sm_count * 8;
-    CU(cudaMemsetAsync(G.hash, 0, (size_t)G.hash_cap * sizeof(u32), st));
+    const int grid_rows = g_sm_count * 8, grid = g_sm_count * 8;
     k_sp_begin<<<1, 32, 0, st>>>(G);
-    k_sp_init<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, row_lo, row_hi);
-    for (int slot = 0; slot < SP_SLOTS; slot++) {
-        if (slot == SP_SLOTS - 1) k_sp_mark<<<1, 1, 0, st>>>(G, 0);
-        k_sp_expand<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+    k_sp_init<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, row_lo, row_hi);
+    for (int level = 0; level < SP_SLOTS; level++) {
+        if (level == SP_SLOTS - 1) {
+            k_sp_mark<<<1, 1, 0, st>>>(G, 0);
+            k_sp_expand<2><<<grid, SP_THREADS, 0, st>>>(G, g_T, level);
+        } else if (sp_slot_is_w(level)) k_sp_expand<1><<<grid, SP_THREADS, 0, st>>>(G, g_T, level);
+        else k_sp_expand<0><<<grid, SP_THREADS, 0, st>>>(G, g_T, level);
     }
     k_sp_mark<<<1, 1, 0, st>>>(G, 1);
     k_sp_score<<<g_sm_count * 16, 128, 0, st>>>(G, g_T);
-    for (int slot = SP_SLOTS - 1; slot >= 0; slot--) {
-        if (!sp_slot_is_w(slot)) k_sp_eval<0><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
-        else if (slot == SP_SLOTS - 1) k_sp_eval<2><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
-        else k_sp_eval<1><<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, slot);
+    for (int level = SP_SLOTS - 1; level >= 0; level--) {
+        if (!sp_slot_is_w(level)) k_sp_eval<0><<<grid, SP_THREADS, 0, st>>>(G, level);
+        else if (level == SP_SLOTS - 1) k_sp_eval<2><<<grid, SP_THREADS, 0, st>>>(G, level);
+        else k_sp_eval<1><<<grid, SP_THREADS, 0, st>>>(G, level);
     }
-    k_sp_finalize<<<grid, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev, row_lo, row_hi);
+    k_sp_finalize<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev, row_lo, row_hi);
+    k_sp_release<<<g_sm_count * 4, 256, 0, st>>>(G);
     CU(cudaGetLastError());
-    env->launches += 5 + 2 * SP_SLOTS + 1;
+    env->launches += 6 + 2 * SP_SLOTS + 1;
     return MJX_OK;
 }
 
@@ -874,9 +846,11 @@ int mjx_env_sp_stats(mjx_env* env, void* stream, int* out10) {
     if (!env || !out10) return fail(MJX_ERR_ARG, "mjx_env_sp_stats: bad arguments");
     int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(cnt, env->sp.counters, sizeof cnt, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CU(cudaMemcpyAsync(out10 + 2, env->sp.slot_count, SP_SLOTS * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(out10 + 2, env->sp.wl_count, SP_SLOTS * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    out10[0] = cnt[6]; out10[1] = cnt[7];  // states / edges actually created; out[2..9] are work-list lengths incl. holes
+    out10[0] = 0;
+    for (int i = 0; i < SP_SLOTS; i++) out10[0] += out10[2 + i];  // states = sum of the level work lists
+    out10[1] = cnt[1];                                            // edges
     return MJX_OK;
 }
 

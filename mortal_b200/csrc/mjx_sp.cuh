@@ -7,43 +7,54 @@
 // The reference is a memoised recursion per observation (AHashMap<State, Rc<Values>> per shanten level).
 // Here ALL observations of a step are solved together as one level-synchronous dynamic programme over the
 // union of their (hand, wall) state DAGs:
-//   slots      D3 W3 D2 W2 D1 W1 D0 W0   (D = 3n+2 hand choosing a shanten-keeping discard,
+//   levels     D3 W3 D2 W2 D1 W1 D0 W0   (D = 3n+2 hand choosing a shanten-keeping discard,
 //                                          W = 3n+1 hand waiting for a shanten-lowering draw)
-//   init       one warp per observation row: availability, parameters, root state -> its slot
-//   expand     one launch per slot, one warp per state: lanes = the 34 tile ids (shanten of hand+-tile per
-//              lane); children are interned in a global open-addressing hash table keyed by (row, state)
-//   evaluate   slots in reverse, one warp per state: lane i owns turn i and accumulates over the state's
-//              edges in the reference's iteration order with explicitly rounded f32 ops, so every
-//              tenpai / win / EV value follows the same sequence of roundings as the Rust code
+//   state      a state of row r is the root hand plus the multiset of tiles drawn and the multiset discarded since
+//              (sp/state.rs:10-21: tehai / wall / akas follow from those) — at most 3 draws and 4 discards, so the
+//              memo key is ONE 64-bit word: row << 42 | discards (4 x 6 bit, sorted) << 18 | draws (3 x 6 bit, sorted).
+//              States are interned by a single 64-bit CAS into an open-addressing table; the table slot is the state's
+//              id and indexes its signature, edge range and value vectors — no key arrays, no second phase, no fences.
+//   expand     one launch per level; a CTA takes a batch of 32 states: (state, tile) candidate pairs are compacted in shared
+//              memory and evaluated one per THREAD (shanten of hand +- tile from the carried base-5 signatures), effective
+//              tiles become edges at the offset their rank gives (the reference's iteration order), children are interned
+//              one per thread; edge slots and next-level work-list positions are reserved once per batch.
+//   evaluate   levels in reverse; one thread per (state, turn) accumulates over the state's edges in the reference's order
+//              with explicitly rounded f32 ops, so every tenpai / win / EV value follows the same sequence of roundings
+//              as the Rust code (bit-exact); the probability vectors of a state are staged once per batch in shared memory.
 //   finalize   one warp per row: candidates, comparators, rows 889..1011 written into the obs tensor
-// Work is balanced across the whole GPU at state granularity (a 15k-state hand costs as much as 30 small
-// ones and is shared by all SMs), and there is no per-observation synchronisation.
 #pragma once
 #include "mjx_obs.cuh"
 
 namespace mjx {
 
-constexpr int SP_NODE_CHUNK = 16;   // state indices / work-list positions reserved per global atomic
-constexpr int SP_EDGE_CHUNK = 128;  // edge slots reserved per global atomic
-constexpr u32 SP_NO_OWNER = 0xFFFFFFFFu;  // edge_owner of a reserved-but-unused edge slot
 constexpr int SP_T_MAX = 17;             // sp/mod.rs:42 MAX_TSUMOS_LEFT
 constexpr int SP_SHANTEN_THRES = 3;      // calc.rs:13
 constexpr int SP_MAX_TILES_LEFT = 34 * 4 - 1 - 13;  // calc.rs:14
 constexpr int SP_SLOTS = 8;
+constexpr int SP_B = 32;                 // states per CTA batch
+constexpr int SP_THREADS = 128;
+constexpr int SP_MAX_EDGES = 37;         // 34 tile kinds + 3 aka splits
+constexpr u64 SP_EMPTY = ~0ull;
 constexpr u32 SP_NO_CHILD = 0xFFFFFFFFu;
+constexpr u32 SP_DR_NONE = 0x3FFFFu, SP_DI_NONE = 0xFFFFFFu;
+constexpr int SP_VALS = 3 * SP_T_MAX;    // floats per state: tenpai[17] | win[17] | ev[17]
 
 #ifdef MJX_HOST_EMUL
 #define SP_FMUL(a, b) ((a) * (b))
 #define SP_FADD(a, b) ((a) + (b))
 #define SP_FDIV(a, b) ((a) / (b))
+#define SP_SYNC() ((void)0)
 #else
 // never contracted into FMA: the reference rounds after every multiply and add
 #define SP_FMUL(a, b) __fmul_rn((a), (b))
 #define SP_FADD(a, b) __fadd_rn((a), (b))
 #define SP_FDIV(a, b) __fdiv_rn((a), (b))
+#define SP_SYNC() __syncthreads()
 #endif
+// block-parallel loop: every phase of a batch is `SP_PFOR` + `SP_SYNC()` (the host emulation runs one thread)
+#define SP_PFOR(i, n) for (int i = B.tid; i < (n); i += B.nthr)
 
-// sp/state.rs:10-21 (n_extra_tsumo is always 0 without tegawari)
+// sp/state.rs:10-21 of the ROOT of a row (n_extra_tsumo is always 0 without tegawari)
 struct alignas(8) SpKey {
     u8 tehai[34];
     u8 wall[34];
@@ -52,40 +63,59 @@ struct alignas(8) SpKey {
 };
 static_assert(sizeof(SpKey) == 72, "SpKey layout");
 
-// 9 x 8-byte moves instead of 72 byte moves (the u8 arrays alone would only guarantee 1-byte alignment)
-MJX_D void sp_key_copy(SpKey* dst, const SpKey* src) {
-    const u64* a = reinterpret_cast<const u64*>(src);
-    u64* b = reinterpret_cast<u64*>(dst);
-#pragma unroll
-    for (int i = 0; i < 9; i++) b[i] = a[i];
+// ---- the 64-bit state key
+MJX_HD u64 sp_key_make(u32 row, u32 dr, u32 di) { return ((u64)row << 42) | ((u64)di << 18) | (u64)dr; }
+MJX_HD u32 sp_key_row(u64 k) { return (u32)(k >> 42); }
+MJX_HD u32 sp_key_dr(u64 k) { return (u32)k & SP_DR_NONE; }
+MJX_HD u32 sp_key_di(u64 k) { return (u32)(k >> 18) & SP_DI_NONE; }
+// insert tile id `t` (0..36) into a tuple of `n` ascending 6-bit fields (63 = empty, always at the top)
+MJX_HD u32 sp_tuple_insert(u32 packed, int n, u32 t) {
+    int p = 0;
+    for (int i = 0; i < n; i++) p += ((packed >> (6 * i)) & 63u) < t;
+    const u32 low = packed & ((1u << (6 * p)) - 1u);
+    const u32 high = (packed >> (6 * p)) << (6 * (p + 1));
+    return (low | (t << (6 * p)) | high) & ((n == 3) ? SP_DR_NONE : SP_DI_NONE);
+}
+// how many fields of the tuple are tile kind `t` (aka ids count as their 5)
+MJX_HD int sp_tuple_count(u32 packed, int n, int t) {
+    int c = 0;
+    for (int i = 0; i < n; i++) {
+        const int f = (int)((packed >> (6 * i)) & 63u);
+        c += f != 63 && deaka(f) == t;
+    }
+    return c;
+}
+// akas byte of the state: the root's, with drawn akas moved wall -> hand and discarded akas removed
+MJX_HD int sp_key_akas(int root_akas, u32 dr, u32 di) {
+    int a = root_akas;
+    for (int i = 0; i < 3; i++) {
+        const int f = (int)((dr >> (6 * i)) & 63u);
+        if (f >= T_5MR && f <= T_5SR) a = (a | (1 << (f - T_5MR))) & ~(1 << (3 + f - T_5MR));
+    }
+    for (int i = 0; i < 4; i++) {
+        const int f = (int)((di >> (6 * i)) & 63u);
+        if (f >= T_5MR && f <= T_5SR) a &= ~(1 << (f - T_5MR));
+    }
+    return a;
+}
+MJX_HD u32 sp_hash64(u64 x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (u32)x;
 }
 
-// What a state's expansion needs besides the key, carried from parent to child incrementally instead of being
-// recomputed from the 34 counts: the shanten signatures of the hand (mjx_algo.cuh HandSig) and a Zobrist hash of the key.
-struct alignas(8) SpSig {
-    u32 idx[4];
-    i8 kinds, pairs, kkinds, kpairs;
-    u32 hash;
-};
-static_assert(sizeof(SpSig) == 24, "SpSig layout");
-MJX_D HandSig sp_sig_hand(const SpSig& g) {
+// shanten signatures of a state's hand (mjx_algo.cuh HandSig), 16 bytes: w[s] = base-5 suit index (21 bits) | counter << 21
+struct alignas(16) SpSigP { u32 w[4]; };
+MJX_D SpSigP sp_sig_pack(const HandSig& h) {
+    SpSigP p;
+    p.w[0] = h.idx[0] | ((u32)h.kinds << 21); p.w[1] = h.idx[1] | ((u32)h.pairs << 21);
+    p.w[2] = h.idx[2] | ((u32)h.kkinds << 21); p.w[3] = h.idx[3] | ((u32)h.kpairs << 21);
+    return p;
+}
+MJX_D HandSig sp_sig_unpack(const SpSigP& p) {
     HandSig h;
-    for (int i = 0; i < 4; i++) h.idx[i] = g.idx[i];
-    h.kinds = g.kinds; h.pairs = g.pairs; h.kkinds = g.kkinds; h.kpairs = g.kpairs;
+    for (int i = 0; i < 4; i++) h.idx[i] = p.w[i] & 0x1FFFFFu;
+    h.kinds = (int)(p.w[0] >> 21); h.pairs = (int)(p.w[1] >> 21); h.kkinds = (int)(p.w[2] >> 21); h.kpairs = (int)(p.w[3] >> 21);
     return h;
-}
-MJX_D SpSig sp_sig_make(const HandSig& h, u32 hash) {
-    SpSig g;
-    for (int i = 0; i < 4; i++) g.idx[i] = h.idx[i];
-    g.kinds = (i8)h.kinds; g.pairs = (i8)h.pairs; g.kkinds = (i8)h.kkinds; g.kpairs = (i8)h.kpairs;
-    g.hash = hash;
-    return g;
-}
-// Zobrist terms: kind 0 = tehai[t] == c, 1 = wall[t] == c, 2 = the akas byte; the key hash is their XOR
-MJX_D u32 sp_zob(int kind, int t, int c) {
-    u32 x = ((u32)kind << 9) | ((u32)t << 3) | (u32)c;
-    x = (x + 0x9E3779B9u) * 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
-    return x;
 }
 
 // per observation row: sp/calc.rs:36-62 parameters + what obs_repr.rs needs afterwards
@@ -105,29 +135,26 @@ struct SpRow {
     i8 cur_shanten;
     u8 seat;
     i32 table;
-    i32 root;         // root node index, -1 if none
+    u32 root;         // table slot of the root state, SP_NO_CHILD if none
     float fallback_ev;  // obs_repr.rs:604-616
     SpKey root_key;
 };
 
 struct SpGlobal {
-    SpRow* rows;       // [row_cap]
-    SpKey* keys;       // [node_cap]
-    SpSig* sigs;       // [node_cap]
-    i32* node_row;     // [node_cap]
-    float* vals;       // [node_cap][3][SP_T_MAX]
-    u32* edge_begin;   // [node_cap]
-    u8* n_edges;       // [node_cap]
-    u32* edge_child;   // [edge_cap]
-    u16* edge_meta;    // [edge_cap] tile (6 bits) | count << 6 | (no-yaku flag << 15, tenpai states only)
-    u32* edge_owner;   // [edge_cap] node the edge belongs to
-    float* leaf_scores;  // [score_cap][4] get_score of every winning draw of the tenpai (W0) states
-    u32* hash;         // [hash_cap] node index + 1, 0 = empty
-    i32* slot_list;    // [SP_SLOTS][slot_cap] node indices
-    i32* slot_count;   // [SP_SLOTS]
-    i32* counters;     // [0] nodes, [1] edges, [2] overflow flag, [3] overflow events (cumulative),
-                       // [4],[5] edge range of the tenpai (W0) states
-    i32 node_cap, edge_cap, hash_cap, slot_cap, score_cap;
+    SpRow* rows;        // [row_cap]
+    u64* hkey;          // [hash_cap] state key (SP_EMPTY = free); the slot index is the state's id
+    SpSigP* nsig;       // [hash_cap] shanten signatures of the state's hand
+    u64* einfo;         // [hash_cap] edge_begin | n_edges << 32 | sum of required-tile counts << 40
+    float* vals;        // [hash_cap][3][SP_T_MAX]
+    u32* echild;        // [edge_cap] child state (table slot)
+    u16* emeta;         // [edge_cap] tile (6 bits) | count << 6 | (no-yaku flag << 15, tenpai states only)
+    u32* eowner;        // [edge_cap] owning state; written for the tenpai (W0) level only (k_sp_score walks that edge range)
+    float* leaf_scores; // [score_cap][4] get_score of every winning draw of the tenpai (W0) states
+    u32* wl;            // [SP_SLOTS][wl_cap] work list of each level: table slots
+    i32* wl_count;      // [SP_SLOTS]
+    i32* counters;      // [1] edges, [2] overflow flag, [3] overflow events (cumulative), [4],[5] edge range of the tenpai level
+    i32 row_base;       // rows [row_base, ...) of the step form this DP (row groups of mjx_env_encode_obs_host)
+    i32 hash_cap, wl_cap, edge_cap, score_cap;
 };
 
 MJX_CONST float c_uradora_prob[5][13] = {  // algo/data/uradora_prob_table.txt
@@ -148,412 +175,232 @@ MJX_D int cmp_discard_priority(int l, int r) {
     return 0;
 }
 
-// per-warp scratch (shared memory on device)
-struct SpWarpScratch {
-    float nts[SP_T_MAX];       // not_tsumo_prob row of the state (calc.rs:148-167)
-    float tpn[SP_T_MAX];       // tsumo_prob[cnt-1][j] * not_tsumo[j] of the current edge
-    float cv[3][SP_T_MAX];     // child values of the current edge
-    float scores[40][4];       // get_score of each winning draw of a W0 state
-    u8 score_ok[40];
-    SpKey key;                   // the state being expanded, staged once per warp
-    u8 ed_tile[40], ed_cnt[40];  // edge descriptors of the state being expanded
-    u8 cand[40];                 // candidate tiles of the state being expanded, compacted
-    u8 df[34];
-    u8 pad_[2];
-    i32 ed_n, ed_begin;
-    // warp-private allocation chunks (device): indices are taken from the global counters SP_*_CHUNK at a time, so the
-    // three hot counters see ~1/16 .. 1/128 of the atomics (same-address L2 atomics serialise, B300 guide 'Atomics')
-    i32 a_node, a_node_end, a_pos, a_pos_end, a_edge, a_edge_end;
-    i32 fill_from, fill_n, efill_from, efill_n, created, created_edges, bc_node, bc_pos;
-};
-
-struct SpCtx {
-    SpGlobal G;
-    Tables T;
-    SpWarpScratch* ws;
-    int lane;
-};
-
-#ifdef MJX_HOST_EMUL
-#define SP_FOR_LANES(i, n) for (int i = 0; i < (n); i++)
-#else
-#define SP_FOR_LANES(i, n) for (int i = s.lane; i < (n); i += 32)
-#endif
-
-MJX_D u32 sp_key_hash_full(const SpKey& k) {
-    u32 h = sp_zob(2, 0, k.akas);
-    for (int t = 0; t < 34; t++) h ^= sp_zob(0, t, k.tehai[t]) ^ sp_zob(1, t, k.wall[t]);
-    return h;
-}
-// table slot hash of (row, key): the key's Zobrist hash mixed with the row
-MJX_D u32 sp_hash_key(int row, u32 key_hash) {
-    u32 x = key_hash ^ ((u32)row * 0x9E3779B9u);
-    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-    return x;
-}
-
-// `a` lives in the global arena and may have been written by another SM during this launch: read it through
-// L2 (ld.global.cg) — an L1 line shared with a neighbouring, older node could otherwise serve stale bytes.
-MJX_D bool sp_key_eq(const SpKey& a, const SpKey& b) {
-    const u32* x = reinterpret_cast<const u32*>(&a);
-    const u32* y = reinterpret_cast<const u32*>(&b);
-    bool eq = true;
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(SpKey) / 4); i++) {
-#ifdef MJX_HOST_EMUL
-        eq &= x[i] == y[i];
-#else
-        eq &= __ldcg(x + i) == y[i];
-#endif
-    }
-    return eq;
-}
-MJX_D int sp_ld_row(const i32* p) {
-#ifdef MJX_HOST_EMUL
-    return *p;
-#else
-    return __ldcg(p);
-#endif
-}
-
-MJX_D void sp_set_overflow(SpCtx& s) { s.G.counters[2] = 1; }
-
-// allocate a node in `slot`; executed by one lane. Returns -1 on overflow.
-MJX_DN int sp_new_node(SpCtx& s, int row, const SpKey& key, const SpSig& sig, int slot) {
-#ifdef MJX_HOST_EMUL
-    int idx = s.G.counters[0]++;
-    int pos = s.G.slot_count[slot]++;
-#else
-    int idx = atomicAdd(&s.G.counters[0], 1);
-    int pos = atomicAdd(&s.G.slot_count[slot], 1);
-    atomicAdd(&s.G.counters[6], 1);  // states actually created (counters[0] also counts abandoned chunk tails)
-#endif
-    if (idx >= s.G.node_cap || pos >= s.G.slot_cap) { sp_set_overflow(s); return -1; }
-    sp_key_copy(&s.G.keys[idx], &key);
-    {
-        const u64* a = reinterpret_cast<const u64*>(&sig);
-        u64* b = reinterpret_cast<u64*>(&s.G.sigs[idx]);
-        b[0] = a[0]; b[1] = a[1]; b[2] = a[2];
-    }
-    s.G.node_row[idx] = row;
-    s.G.n_edges[idx] = 0;
-    s.G.edge_begin[idx] = 0;
-    s.G.slot_list[(size_t)slot * s.G.slot_cap + pos] = idx;
-    return idx;
-}
-
-// find-or-insert (row, key) in `slot`. May be called by several lanes of a warp at once (different keys).
-// Lock-free without spinning: the node is allocated and written first, then published with one CAS; if another
-// thread published the same state in the meantime its node wins and ours is simply never referenced.
-MJX_DN int sp_intern(SpCtx& s, int row, const SpKey& key, const SpSig& sig, int slot) {
-    const u32 mask = (u32)s.G.hash_cap - 1;
-    const u32 hv = sp_hash_key(row, sig.hash);
-    const u32 tag = (hv >> 24) << 24;  // 8-bit tag kept beside the 24-bit index: mismatches never touch the key array
-    u32 h = hv & mask;
-    int mine = -1;
-    for (int probe = 0; probe < s.G.hash_cap; probe++, h = (h + 1) & mask) {
-#ifdef MJX_HOST_EMUL
-        u32 cur = s.G.hash[h];
-        if (cur == 0) {
-            int idx = sp_new_node(s, row, key, sig, slot);
-            if (idx < 0) return -1;
-            s.G.hash[h] = ((u32)idx + 1) | tag;
-            return idx;
-        }
-#else
-        u32 cur = __ldcg(&s.G.hash[h]);
-        if (cur == 0) {
-            if (mine < 0) {
-                mine = sp_new_node(s, row, key, sig, slot);
-                if (mine < 0) return -1;
-                __threadfence();
-            }
-            const u32 prev = atomicCAS(&s.G.hash[h], 0u, ((u32)mine + 1) | tag);
-            if (prev == 0) return mine;
-            cur = prev;
-        }
-#endif
-        if ((cur & 0xFF000000u) != tag) continue;
-        const int ci = (int)(cur & 0x00FFFFFFu) - 1;
-        if (sp_ld_row(s.G.node_row + ci) == row && sp_key_eq(s.G.keys[ci], key)) return ci;
-    }
-    sp_set_overflow(s);
-    return -1;
-}
-
-#ifndef MJX_HOST_EMUL
-// Device interning in two phases so that new states are allocated per warp, not per lane.
-// Phase 1: read-only probe. Returns the state's index, or -1 with `h` left at the first empty hash slot seen.
-MJX_DN int sp_lookup(const SpCtx& s, int row, const SpKey& key, u32 hv, u32& h) {
-    const u32 mask = (u32)s.G.hash_cap - 1;
-    const u32 tag = (hv >> 24) << 24;
-    h = hv & mask;
-    for (int probe = 0; probe < s.G.hash_cap; probe++, h = (h + 1) & mask) {
-        const u32 cur = __ldcg(&s.G.hash[h]);
-        if (cur == 0) return -1;
-        if ((cur & 0xFF000000u) != tag) continue;
-        const int ci = (int)(cur & 0x00FFFFFFu) - 1;
-        if (sp_ld_row(s.G.node_row + ci) == row && sp_key_eq(s.G.keys[ci], key)) return ci;
-    }
-    return -1;
-}
-// Phase 2: publish the already written state `mine` starting at hash slot `h`. If another warp published the same
-// state in the meantime its index is returned and `lost` is set (ours becomes a hole in the work list).
-MJX_DN int sp_publish(SpCtx& s, int row, const SpKey& key, u32 hv, u32 h, int mine, bool& lost) {
-    const u32 mask = (u32)s.G.hash_cap - 1;
-    const u32 tag = (hv >> 24) << 24;
-    lost = false;
-    for (int probe = 0; probe < s.G.hash_cap; probe++, h = (h + 1) & mask) {
-        u32 cur = __ldcg(&s.G.hash[h]);
-        if (cur == 0) {
-            const u32 prev = atomicCAS(&s.G.hash[h], 0u, ((u32)mine + 1) | tag);
-            if (prev == 0) return mine;
-            cur = prev;
-        }
-        if ((cur & 0xFF000000u) != tag) continue;
-        const int ci = (int)(cur & 0x00FFFFFFu) - 1;
-        if (sp_ld_row(s.G.node_row + ci) == row && sp_key_eq(s.G.keys[ci], key)) { lost = true; return ci; }
-    }
-    sp_set_overflow(s);
-    lost = true;
-    return -1;
-}
-// Warp-collective: reserve `count` consecutive state indices and work-list positions of `slot` from the warp's chunks,
-// refilling a chunk from its global counter when it runs short (the abandoned remainder stays a run of holes: the
-// positions were pre-filled with -1 when the chunk was taken). Returns false on arena overflow.
-MJX_DN bool sp_reserve(SpCtx& s, int slot, int count, int& node_base, int& pos_base) {
-    SpWarpScratch& ws = *s.ws;
-    __syncwarp();
-    if (s.lane == 0) {
-        if (ws.a_node_end - ws.a_node < count) {
-            const int n = max(SP_NODE_CHUNK, count);
-            ws.a_node = atomicAdd(&s.G.counters[0], n);
-            ws.a_node_end = ws.a_node + n;
-        }
-        ws.fill_n = 0;
-        if (ws.a_pos_end - ws.a_pos < count) {
-            const int n = max(SP_NODE_CHUNK, count);
-            ws.a_pos = atomicAdd(&s.G.slot_count[slot], n);
-            ws.a_pos_end = ws.a_pos + n;
-            ws.fill_from = ws.a_pos; ws.fill_n = n;
-        }
-        ws.bc_node = ws.a_node; ws.bc_pos = ws.a_pos;
-        ws.a_node += count; ws.a_pos += count;
-    }
-    __syncwarp();
-    node_base = ws.bc_node; pos_base = ws.bc_pos;
-    const int ff = ws.fill_from, fn = ws.fill_n;
-    i32* list = s.G.slot_list + (size_t)slot * s.G.slot_cap;
-    for (int i = s.lane; i < fn; i += 32) if (ff + i < s.G.slot_cap) list[ff + i] = -1;
-    __syncwarp();
-    if (node_base + count > s.G.node_cap || pos_base + count > s.G.slot_cap) { sp_set_overflow(s); return false; }
-    return true;
-}
-#endif
+struct SpBlk { int tid, nthr, bid, nblk; };  // thread / block coordinates of a launch (host emulation: 0, 1, 0, 1)
 
 MJX_HD bool sp_slot_is_w(int slot) { return (slot & 1) != 0; }
 MJX_HD int sp_slot_shanten(int slot) { return 3 - (slot >> 1); }
-MJX_D float* sp_vals(const SpCtx& s, int node, int which) { return s.G.vals + ((size_t)node * 3 + which) * SP_T_MAX; }
+MJX_D float* sp_vals(const SpGlobal& G, u32 node, int which) { return G.vals + ((size_t)node * 3 + which) * SP_T_MAX; }
+MJX_D u32 sp_einfo_begin(u64 e) { return (u32)e; }
+MJX_D int sp_einfo_n(u64 e) { return (int)((e >> 32) & 0xFF); }
+MJX_D int sp_einfo_sum(u64 e) { return (int)((e >> 40) & 0xFF); }
 
-// Expand one state (one warp): edges = shanten-lowering draws (W) or shanten-keeping discards (D).
-MJX_DN void sp_expand(SpCtx& s, const Ctx& c, int node, int slot) {
-    const bool is_w = sp_slot_is_w(slot);
-    const int k = sp_slot_shanten(slot);
-    const bool leaf = is_w && k == 0;
-    const int row = s.G.node_row[node];
-    SpWarpScratch& ws = *s.ws;
-    MJX_SYNCWARP();
+MJX_D void sp_set_overflow(const SpGlobal& G) { G.counters[2] = 1; }
+
+MJX_D i32 sp_atomic_add(i32* p, i32 v) {
 #ifdef MJX_HOST_EMUL
-    sp_key_copy(&ws.key, &s.G.keys[node]);
+    const i32 o = *p; *p += v; return o;
 #else
-    if (s.lane < 9) reinterpret_cast<u64*>(&ws.key)[s.lane] = reinterpret_cast<const u64*>(&s.G.keys[node])[s.lane];
+    return atomicAdd(p, v);
 #endif
-    const SpSig sg = s.G.sigs[node];
-    MJX_SYNCWARP();
-    const SpKey& key = ws.key;
-    const int len = s.G.rows[row].tehai_len_div3;
-    const HandSig base = sp_sig_hand(sg);
-    // candidate tiles: still in the wall (W) / held (D); only those need a shanten evaluation
-    const u8* cnts = is_w ? key.wall : key.tehai;
-    const u64 cand = tile_mask(c, [&](int t) { return cnts[t] != 0; });
-    auto effective = [&](int t) {
-        if (is_w) return shanten_all_sig(s.T, sig_variant(base, t, +1, key.tehai[t]), len) - k == -1;
-        return shanten_all_sig(s.T, sig_variant(base, t, -1, key.tehai[t]), len) == k;
-    };
-    u64 eff = 0;
+}
+MJX_D void sp_atomic_or(u32* p, u32 v) {
 #ifdef MJX_HOST_EMUL
-    for (int t = 0; t < 34; t++) if (((cand >> t) & 1) && effective(t)) eff |= 1ull << t;
+    *p |= v;
 #else
-    {   // lane i evaluates the i-th candidate: one pass unless more than 32 kinds qualify
-        for (int t = s.lane; t < 34; t += 32)
-            if ((cand >> t) & 1) ws.cand[mjx_popcll(cand & ((1ull << t) - 1))] = (u8)t;
-        __syncwarp();
-        const int n_c = mjx_popcll(cand);
-        for (int i0 = 0; i0 < n_c; i0 += 32) {
-            const int i = i0 + s.lane;
-            const int t = i < n_c ? (int)ws.cand[i] : -1;
-            const bool ok = t >= 0 && effective(t);
-            const unsigned lo = (ok && t < 32) ? 1u << t : 0u, hi = (ok && t >= 32) ? 1u << (t - 32) : 0u;
-            eff |= (u64)__reduce_or_sync(0xffffffffu, lo) | ((u64)__reduce_or_sync(0xffffffffu, hi) << 32);
-        }
-    }
+    atomicOr(p, v);
 #endif
-    // edge descriptors in tile order; an effective 5 whose aka is still in the wall splits in two
-    // (sp/state.rs:160-176); a discarded 5 is the aka only when it is the last 5 in hand (state.rs:127-132).
-    // Every effective tile writes its own descriptors at the offset its rank gives.
-    u64 split = 0;
-    if (is_w)
-        for (int s5 = 0; s5 < 3; s5++) {
-            const int t5 = 4 + 9 * s5;
-            if (((eff >> t5) & 1) && ((key.akas >> (3 + s5)) & 1) && key.wall[t5] >= 2) split |= 1ull << t5;
-        }
-    const int ne_all = mjx_popcll(eff) + mjx_popcll(split);
-    MJX_FOR_TILES(c, t) {
-        if (!((eff >> t) & 1)) continue;
-        const u64 below = (1ull << t) - 1;
-        const int off = mjx_popcll(eff & below) + mjx_popcll(split & below);
-        const int suit5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
-        if (is_w) {
-            const int count = key.wall[t];
-            if (suit5 >= 0 && ((key.akas >> (3 + suit5)) & 1)) {
-                int o = off;
-                if (count >= 2) { ws.ed_tile[o] = (u8)t; ws.ed_cnt[o] = (u8)(count - 1); o++; }
-                ws.ed_tile[o] = (u8)(T_5MR + suit5); ws.ed_cnt[o] = 1;
-            } else {
-                ws.ed_tile[off] = (u8)t; ws.ed_cnt[off] = (u8)count;
-            }
-        } else {
-            int tile = t;
-            if (suit5 >= 0 && ((key.akas >> suit5) & 1) && key.tehai[t] == 1) tile = T_5MR + suit5;
-            ws.ed_tile[off] = (u8)tile; ws.ed_cnt[off] = 0;
-        }
-    }
-    if (MJX_IS_L0(c)) {
-        int ne = ne_all;
-#ifdef MJX_HOST_EMUL
-        int eb = s.G.counters[1]; s.G.counters[1] += ne;
-#else
-        ws.efill_n = 0;
-        if (ws.a_edge_end - ws.a_edge < ne) {  // take a new chunk of edge slots; the remainder of the old one stays unused
-            // the tenpai level's edge range is walked edge by edge by k_sp_score: keep its unused tails short
-            const int n = max(leaf ? 32 : SP_EDGE_CHUNK, ne);
-            ws.a_edge = atomicAdd(&s.G.counters[1], n);
-            ws.a_edge_end = ws.a_edge + n;
-            ws.efill_from = ws.a_edge; ws.efill_n = n;
-        }
-        int eb = ws.a_edge;
-        ws.a_edge += ne;
-        ws.created_edges += ne;
-#endif
-        if (eb + ne > s.G.edge_cap) { sp_set_overflow(s); ne = 0; eb = 0; }
-        ws.ed_n = ne; ws.ed_begin = eb;
-        s.G.edge_begin[node] = (u32)eb;
-        s.G.n_edges[node] = (u8)ne;
-    }
-    MJX_SYNCWARP();
-#ifndef MJX_HOST_EMUL
-    {   // unused edge slots of a fresh chunk must read as "no edge" for k_sp_score, which walks the edge range
-        const int ff = ws.efill_from, fn = ws.efill_n;
-        for (int i = s.lane; i < fn; i += 32) if (ff + i < s.G.edge_cap) s.G.edge_owner[ff + i] = SP_NO_OWNER;
-        __syncwarp();
-    }
-#endif
-    // one edge per lane: build the child state (key, signatures, hash: all incremental) and intern it
-    const int ne = ws.ed_n, eb = ws.ed_begin;
-    auto child_of = [&](int e, SpKey& ck, SpSig& cs) {
-        const int tile = ws.ed_tile[e], t = deaka(tile);
-        const int suit5 = is_aka(tile) ? tile - T_5MR : -1;
-        sp_key_copy(&ck, &key);
-        const int c0 = key.tehai[t];
-        u32 h = sg.hash ^ sp_zob(0, t, c0);
-        if (is_w) {
-            ck.tehai[t] += 1;
-            ck.wall[t] -= 1;
-            if (suit5 >= 0) ck.akas = (u8)((ck.akas | (1 << suit5)) & ~(1 << (3 + suit5)));
-            h ^= sp_zob(0, t, c0 + 1) ^ sp_zob(1, t, key.wall[t]) ^ sp_zob(1, t, key.wall[t] - 1);
-        } else {
-            ck.tehai[t] -= 1;
-            if (suit5 >= 0) ck.akas = (u8)(ck.akas & ~(1 << suit5));
-            h ^= sp_zob(0, t, c0 - 1);
-        }
-        if (ck.akas != key.akas) h ^= sp_zob(2, 0, key.akas) ^ sp_zob(2, 0, ck.akas);
-        cs = sp_sig_make(sig_variant(base, t, is_w ? +1 : -1, c0), h);
-    };
-#ifdef MJX_HOST_EMUL
-    for (int e = 0; e < ne; e++) {
-        u32 child = SP_NO_CHILD;
-        if (!leaf) {
-            SpKey ck; SpSig cs;
-            child_of(e, ck, cs);
-            int ci = sp_intern(s, row, ck, cs, slot + 1);
-            child = ci < 0 ? SP_NO_CHILD : (u32)ci;
-        }
-        s.G.edge_child[eb + e] = child;
-        s.G.edge_meta[eb + e] = (u16)(ws.ed_tile[e] | (ws.ed_cnt[e] << 6));
-        s.G.edge_owner[eb + e] = (u32)node;
-    }
-#else
-    for (int e0 = 0; e0 < ne; e0 += 32) {
-        const int e = e0 + s.lane;
-        const bool active = e < ne;
-        const int my_tile = active ? ws.ed_tile[e] : 0, my_cnt = active ? ws.ed_cnt[e] : 0;
-        u32 child = SP_NO_CHILD;
-        if (!leaf) {
-            SpKey ck; SpSig cs;
-            u32 hv = 0, h = 0;
-            int found = -1;
-            if (active) {
-                child_of(e, ck, cs);
-                hv = sp_hash_key(row, cs.hash);
-                found = sp_lookup(s, row, ck, hv, h);
-            }
-            const bool need = active && found < 0;
-            const unsigned m = __ballot_sync(0xffffffffu, need);
-            if (m) {
-                int node_base = 0, pos_base = 0;
-                const bool ok = sp_reserve(s, slot + 1, __popc(m), node_base, pos_base);
-                if (need && ok) {
-                    const int rank = __popc(m & ((1u << s.lane) - 1));
-                    const int idx = node_base + rank, pos = pos_base + rank;
-                    sp_key_copy(&s.G.keys[idx], &ck);
-                    {
-                        const u64* a = reinterpret_cast<const u64*>(&cs);
-                        u64* b = reinterpret_cast<u64*>(&s.G.sigs[idx]);
-                        b[0] = a[0]; b[1] = a[1]; b[2] = a[2];
-                    }
-                    s.G.node_row[idx] = row;
-                    s.G.n_edges[idx] = 0;
-                    s.G.edge_begin[idx] = 0;
-                    i32* list = s.G.slot_list + (size_t)(slot + 1) * s.G.slot_cap;
-                    list[pos] = idx;
-                    __threadfence();
-                    bool lost;
-                    found = sp_publish(s, row, ck, hv, h, idx, lost);
-                    if (lost) list[pos] = -1;
-                }
-                if (s.lane == 0) ws.created += __popc(m);
-            }
-            child = found < 0 ? SP_NO_CHILD : (u32)found;
-        }
-        if (active) {
-            s.G.edge_child[eb + e] = child;
-            s.G.edge_meta[eb + e] = (u16)(my_tile | (my_cnt << 6));
-            s.G.edge_owner[eb + e] = (u32)node;
-        }
-    }
-#endif
-    MJX_SYNCWARP();
 }
 
-// calc.rs:640-758 for one winning draw; executed by one lane. Returns false when there is no yaku.
-MJX_DN bool sp_get_score(const SpCtx& s, const SpRow& P, const SpKey& key, int win_tile, float* scores) {
+// find-or-insert a state key; the returned slot is the state's id. `won` = this thread created it (and must append it to
+// the next level's work list and write its signature). Lock-free: one 64-bit CAS publishes the state, the key IS the entry.
+MJX_DN u32 sp_intern(const SpGlobal& G, u64 key, bool& won) {
+    const u32 mask = (u32)G.hash_cap - 1;
+    u32 h = sp_hash64(key) & mask;
+    won = false;
+    for (int probe = 0; probe < 8192; probe++, h = (h + 1) & mask) {
+#ifdef MJX_HOST_EMUL
+        const u64 cur = G.hkey[h];
+        if (cur == key) return h;
+        if (cur == SP_EMPTY) { G.hkey[h] = key; won = true; return h; }
+#else
+        const u64 cur = __ldcg(reinterpret_cast<const unsigned long long*>(G.hkey + h));
+        if (cur == key) return h;
+        if (cur == SP_EMPTY) {
+            const u64 prev = atomicCAS(reinterpret_cast<unsigned long long*>(G.hkey + h), (unsigned long long)SP_EMPTY,
+                                       (unsigned long long)key);
+            if (prev == SP_EMPTY) { won = true; return h; }
+            if (prev == key) return h;
+        }
+#endif
+    }
+    sp_set_overflow(G);  // table (nearly) full
+    return SP_NO_CHILD;
+}
+
+// ---------------------------------------------------------------------------------------------- expansion
+// shared-memory working set of one batch
+struct SpExpandBatch {
+    u64 key[SP_B];
+    u32 slot[SP_B];
+    SpSigP sig[SP_B];
+    u8 akas[SP_B], len[SP_B];
+    u8 teh[SP_B][34], wall[SP_B][34];
+    u32 cand[SP_B][2], eff[SP_B][2];
+    u8 split[SP_B], ne[SP_B], sumreq[SP_B];
+    u16 cand_off[SP_B + 1], e_off[SP_B + 1];
+    u16 cand_list[SP_B * 34];
+    u32 edge[SP_B * SP_MAX_EDGES];  // state | tile << 8 | count << 16
+    u32 win[SP_B * SP_MAX_EDGES];
+    i32 n_cand, n_edge, e_base, n_win, w_base;
+};
+
+MJX_D u64 sp_mask64(const u32* m) { return (u64)m[0] | ((u64)m[1] << 32); }
+
+// KIND 0: D level (shanten-keeping discards, sp/state.rs:98-137), 1: W level (shanten-lowering draws, state.rs:139-179),
+// 2: the tenpai W level (winning draws: edges only, no children)
+template <int KIND>
+MJX_DN void sp_expand_batch(const SpGlobal& G, const Tables& T, SpExpandBatch& S, const SpBlk& B, int level, int first, int nb) {
+    constexpr bool IS_W = KIND != 0, LEAF = KIND == 2;
+    const int k = sp_slot_shanten(level);
+    const u32* list = G.wl + (size_t)level * G.wl_cap;
+    SP_PFOR(st, nb) {
+        const u32 slot = list[first + st];
+        const u64 key = G.hkey[slot];
+        const SpRow& R = G.rows[sp_key_row(key)];
+        S.slot[st] = slot; S.key[st] = key;
+        S.sig[st] = G.nsig[slot];
+        S.akas[st] = (u8)sp_key_akas(R.root_key.akas, sp_key_dr(key), sp_key_di(key));
+        S.len[st] = R.tehai_len_div3;
+        S.cand[st][0] = S.cand[st][1] = S.eff[st][0] = S.eff[st][1] = 0;
+    }
+    if (B.tid == 0) S.n_win = 0;
+    SP_SYNC();
+    // counts of every tile kind in the state's hand and wall; candidate tiles: still in the wall (W) / held (D)
+    SP_PFOR(it, nb * 34) {
+        const int st = it / 34, t = it - st * 34;
+        const u64 key = S.key[st];
+        const SpRow& R = G.rows[sp_key_row(key)];
+        const int nd = sp_tuple_count(sp_key_dr(key), 3, t), nx = sp_tuple_count(sp_key_di(key), 4, t);
+        const int th = (int)R.root_key.tehai[t] + nd - nx, wl = (int)R.root_key.wall[t] - nd;
+        S.teh[st][t] = (u8)th; S.wall[st][t] = (u8)wl;
+        if ((IS_W ? wl : th) > 0) sp_atomic_or(&S.cand[st][t >> 5], 1u << (t & 31));
+    }
+    SP_SYNC();
+    if (B.tid == 0) {
+        int acc = 0;
+        for (int st = 0; st < nb; st++) { S.cand_off[st] = (u16)acc; acc += mjx_popcll(sp_mask64(S.cand[st])); }
+        S.cand_off[nb] = (u16)acc; S.n_cand = acc;
+    }
+    SP_SYNC();
+    SP_PFOR(it, nb * 34) {
+        const int st = it / 34, t = it - st * 34;
+        const u64 m = sp_mask64(S.cand[st]);
+        if ((m >> t) & 1) S.cand_list[S.cand_off[st] + mjx_popcll(m & ((1ull << t) - 1))] = (u16)((st << 6) | t);
+    }
+    SP_SYNC();
+    // one candidate per thread: shanten of hand +- tile
+    SP_PFOR(i, S.n_cand) {
+        const int st = S.cand_list[i] >> 6, t = S.cand_list[i] & 63;
+        const HandSig base = sp_sig_unpack(S.sig[st]);
+        const int len = S.len[st], c0 = S.teh[st][t];
+        bool ok;
+        if (IS_W) ok = shanten_all_sig(T, sig_variant(base, t, +1, c0), len) - k == -1;
+        else ok = shanten_all_sig(T, sig_variant(base, t, -1, c0), len) == k;
+        if (ok) sp_atomic_or(&S.eff[st][t >> 5], 1u << (t & 31));
+    }
+    SP_SYNC();
+    // an effective 5 whose aka is still in the wall splits in two edges (sp/state.rs:160-176)
+    SP_PFOR(st, nb) {
+        const u64 eff = sp_mask64(S.eff[st]);
+        int split = 0, sum = 0;
+        if (IS_W) {
+            for (int s5 = 0; s5 < 3; s5++) {
+                const int t5 = 4 + 9 * s5;
+                if (((eff >> t5) & 1) && ((S.akas[st] >> (3 + s5)) & 1) && S.wall[st][t5] >= 2) split |= 1 << s5;
+            }
+            for (u64 rest = eff; rest; rest &= rest - 1) sum += S.wall[st][mjx_ffsll(rest) - 1];
+        }
+        S.split[st] = (u8)split;
+        S.ne[st] = (u8)(mjx_popcll(eff) + mjx_popc((u32)split));
+        S.sumreq[st] = (u8)sum;  // u8 arithmetic, as the reference's `.sum::<u8>()`
+    }
+    SP_SYNC();
+    if (B.tid == 0) {
+        int acc = 0;
+        for (int st = 0; st < nb; st++) { S.e_off[st] = (u16)acc; acc += S.ne[st]; }
+        S.e_off[nb] = (u16)acc;
+        int eb = sp_atomic_add(&G.counters[1], acc);
+        if (eb + acc > G.edge_cap) { sp_set_overflow(G); acc = 0; eb = 0; }
+        S.n_edge = acc; S.e_base = eb;
+    }
+    SP_SYNC();
+    SP_PFOR(st, nb) {
+        const int ne = S.n_edge ? S.ne[st] : 0;
+        G.einfo[S.slot[st]] = (u64)(u32)(S.e_base + S.e_off[st]) | ((u64)ne << 32) | ((u64)S.sumreq[st] << 40);
+    }
+    // edge descriptors in tile order: every effective tile writes its own at the offset its rank gives
+    if (S.n_edge) SP_PFOR(it, nb * 34) {
+        const int st = it / 34, t = it - st * 34;
+        const u64 eff = sp_mask64(S.eff[st]);
+        if (!((eff >> t) & 1)) continue;
+        int off = S.e_off[st] + mjx_popcll(eff & ((1ull << t) - 1));
+        for (int s5 = 0; s5 < 3; s5++) off += ((S.split[st] >> s5) & 1) && 4 + 9 * s5 < t;
+        const int suit5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
+        if (IS_W) {
+            const int count = S.wall[st][t];
+            if (suit5 >= 0 && ((S.akas[st] >> (3 + suit5)) & 1)) {
+                if (count >= 2) { S.edge[off] = (u32)st | ((u32)t << 8) | ((u32)(count - 1) << 16); off++; }
+                S.edge[off] = (u32)st | ((u32)(T_5MR + suit5) << 8) | (1u << 16);
+            } else {
+                S.edge[off] = (u32)st | ((u32)t << 8) | ((u32)count << 16);
+            }
+        } else {
+            // a discarded 5 is the aka only when it is the last 5 in hand (state.rs:127-132)
+            int tile = t;
+            if (suit5 >= 0 && ((S.akas[st] >> suit5) & 1) && S.teh[st][t] == 1) tile = T_5MR + suit5;
+            S.edge[off] = (u32)st | ((u32)tile << 8);
+        }
+    }
+    SP_SYNC();
+    // one edge per thread: child key and signatures (both incremental), interning
+    SP_PFOR(e, S.n_edge) {
+        const u32 d = S.edge[e];
+        const int st = (int)(d & 0xFF), tile = (int)((d >> 8) & 0xFF), cnt = (int)(d >> 16);
+        const int ge = S.e_base + e;
+        G.emeta[ge] = (u16)(tile | (cnt << 6));
+        if (LEAF) { G.eowner[ge] = S.slot[st]; continue; }
+        const u64 key = S.key[st];
+        const int t = deaka(tile);
+        const u64 ckey = IS_W ? sp_key_make(sp_key_row(key), sp_tuple_insert(sp_key_dr(key), 3, (u32)tile), sp_key_di(key))
+                              : sp_key_make(sp_key_row(key), sp_key_dr(key), sp_tuple_insert(sp_key_di(key), 4, (u32)tile));
+        bool won;
+        const u32 child = sp_intern(G, ckey, won);
+        G.echild[ge] = child;
+        if (won) {
+            G.nsig[child] = sp_sig_pack(sig_variant(sp_sig_unpack(S.sig[st]), t, IS_W ? +1 : -1, S.teh[st][t]));
+            S.win[sp_atomic_add(&S.n_win, 1)] = child;
+        }
+    }
+    SP_SYNC();
+    if (!LEAF) {
+        if (B.tid == 0) {
+            int wb = sp_atomic_add(&G.wl_count[level + 1], S.n_win);
+            if (wb + S.n_win > G.wl_cap) { sp_set_overflow(G); S.n_win = 0; wb = 0; }
+            S.w_base = wb;
+        }
+        SP_SYNC();
+        u32* next = G.wl + (size_t)(level + 1) * G.wl_cap;
+        SP_PFOR(i, S.n_win) next[S.w_base + i] = S.win[i];
+        SP_SYNC();
+    }
+}
+
+template <int KIND>
+MJX_DN void sp_expand_level(const SpGlobal& G, const Tables& T, SpExpandBatch& S, const SpBlk& B, int level) {
+    const int n = min(G.wl_count[level], G.wl_cap);
+    for (int first = B.bid * SP_B; first < n; first += B.nblk * SP_B) sp_expand_batch<KIND>(G, T, S, B, level, first, min(SP_B, n - first));
+}
+
+// ---------------------------------------------------------------------------------------------- scoring of winning draws
+// calc.rs:640-758 for one winning draw; executed by one thread. Returns false when there is no yaku.
+MJX_DN bool sp_get_score(const Tables& T, const SpRow& P, const u8* tehai13, const u8* wall_in, int akas, int win_tile, float* scores) {
     u8 th[34];
-    for (int i = 0; i < 34; i++) th[i] = key.tehai[i];
+    for (int i = 0; i < 34; i++) th[i] = tehai13[i];
     const int wid = deaka(win_tile);
     th[wid] += 1;
-    const int akas_in_hand = (key.akas & 7) | (is_aka(win_tile) ? (1 << (win_tile - T_5MR)) : 0);
+    const int akas_in_hand = (akas & 7) | (is_aka(win_tile) ? (1 << (win_tile - T_5MR)) : 0);
     u8 wall[34];
-    for (int i = 0; i < 34; i++) wall[i] = key.wall[i];
+    for (int i = 0; i < 34; i++) wall[i] = wall_in[i];
     wall[wid] -= 1;
     AgariQuery q;
     q.tehai = th;
@@ -564,7 +411,7 @@ MJX_DN bool sp_get_score(const SpCtx& s, const SpRow& P, const SpKey& key, int w
     const int additional = P.is_menzen ? (P.prefer_riichi ? 2 : 1) : 0;
     int doras = mjx_popc((u32)akas_in_hand) + P.num_doras_in_fuuro;
     for (int i = 0; i < P.n_dora; i++) doras += th[tile_next(P.dora_ind[i])];
-    Agari a = agari_with(s.T, q, additional, doras & 0xFF);
+    Agari a = agari_with(T, q, additional, doras & 0xFF);
     if (a.kind == 0) return false;
     if (a.kind == 2) {
         float v = (float)tsumo_total(point_yakuman(is_oya, a.yakuman), is_oya);
@@ -610,295 +457,214 @@ MJX_DN bool sp_get_score(const SpCtx& s, const SpRow& P, const SpKey& key, int w
     return true;
 }
 
-// calc.rs:447-561 draw_without_tegawari_slow for one W-state at shanten k (one warp, lane i = turn i)
-// stage: score every winning draw of every tenpai state, ONE THREAD PER DRAW (calc.rs:478-479 get_score).
-// Full lane utilisation for the branchy agari evaluation; the per-turn accumulation happens in sp_eval_w<true>.
-MJX_DN void sp_score_edge(const SpCtx& s, int e) {
-    if (s.G.edge_owner[e] == SP_NO_OWNER) return;  // reserved but unused edge slot
-    const int node = (int)s.G.edge_owner[e];
-    const SpRow& P = s.G.rows[s.G.node_row[node]];
+// score one winning draw of a tenpai state (calc.rs:478-479 get_score), ONE THREAD PER DRAW; the per-turn accumulation
+// happens in the evaluation of the tenpai level.
+MJX_DN void sp_score_edge(const SpGlobal& G, const Tables& T, int e) {
+    const u32 node = G.eowner[e];
+    const u64 key = G.hkey[node];
+    const SpRow& P = G.rows[sp_key_row(key)];
+    const u32 dr = sp_key_dr(key), di = sp_key_di(key);
+    u8 th[34], wall[34];
+    for (int t = 0; t < 34; t++) { th[t] = P.root_key.tehai[t]; wall[t] = P.root_key.wall[t]; }
+    for (int i = 0; i < 3; i++) { const int f = (int)((dr >> (6 * i)) & 63u); if (f != 63) { th[deaka(f)] += 1; wall[deaka(f)] -= 1; } }
+    for (int i = 0; i < 4; i++) { const int f = (int)((di >> (6 * i)) & 63u); if (f != 63) th[deaka(f)] -= 1; }
     float sc[4];
-    const u16 m = s.G.edge_meta[e];
-    SpKey key;
-    sp_key_copy(&key, &s.G.keys[node]);
-    const bool ok = sp_get_score(s, P, key, m & 63, sc);
-    const int le = e - s.G.counters[4];
-    if (le >= s.G.score_cap) s.G.counters[2] = 1;  // score arena too small for this step: reported as an overflow
-    if (!ok) s.G.edge_meta[e] = (u16)(m | 0x8000);
-    else if (le >= 0 && le < s.G.score_cap) {
-        float* o = s.G.leaf_scores + (size_t)le * 4;
+    const u16 m = G.emeta[e];
+    const bool ok = sp_get_score(T, P, th, wall, sp_key_akas(P.root_key.akas, dr, di), m & 63, sc);
+    const int le = e - G.counters[4];
+    if (le >= G.score_cap) G.counters[2] = 1;  // score arena too small for this step: reported as an overflow
+    if (!ok) G.emeta[e] = (u16)(m | 0x8000);
+    else if (le >= 0 && le < G.score_cap) {
+        float* o = G.leaf_scores + (size_t)le * 4;
         o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2]; o[3] = sc[3];
     }
 }
 
-template <bool LEAF>
-MJX_DN void sp_eval_w(SpCtx& s, const Ctx& c, int node, int k_rt) {
-    const int k = LEAF ? 0 : k_rt;
-    const int row = s.G.node_row[node];
-    const SpRow& P = s.G.rows[row];
-    const int T = P.T, n_left = P.n_left;
-    const int ne = s.G.n_edges[node];
-    const u32 eb = s.G.edge_begin[node];
-    SpWarpScratch& ws = *s.ws;
-    int sum_required = 0;
-    for (int e = 0; e < ne; e++) sum_required += (s.G.edge_meta[eb + e] >> 6) & 7;
-    sum_required &= 0xFF;
-    // not_tsumo_prob_table[sum_required][j], recomputed with the table's own recurrence (calc.rs:158-165)
-    SP_FOR_LANES(j, T) {
-        float v = 0.f;
-        const int i0 = sum_required;
-        if (i0 <= n_left && i0 <= SP_MAX_TILES_LEFT) {
-            const int lim = min(T - 1, n_left - i0);
-            if (j <= lim) {
-                v = 1.f;
-                for (int q = 0; q < j; q++) v = SP_FDIV(SP_FMUL(v, (float)(n_left - i0 - q)), (float)(n_left - q));
-            }
-        }
-        ws.nts[j] = v;
-    }
-    if (k == 0) {
-        // scores were produced by sp_score_edge; stage them for the turn lanes
-        const int le0 = (int)eb - s.G.counters[4];
-        SP_FOR_LANES(e, ne) {
-            const bool ok = !(s.G.edge_meta[eb + e] & 0x8000) && le0 + e >= 0 && le0 + e < s.G.score_cap;
-            ws.score_ok[e] = ok ? 1 : 0;
-            if (ok) for (int q = 0; q < 4; q++) ws.scores[e][q] = s.G.leaf_scores[(size_t)(le0 + e) * 4 + q];
-        }
-    }
-    MJX_SYNCWARP();
-    float tenpai = 0.f, win = 0.f, ev = 0.f;  // lane-private accumulators (emulation: see below)
-#ifdef MJX_HOST_EMUL
-    float a_t[SP_T_MAX] = {0}, a_w[SP_T_MAX] = {0}, a_v[SP_T_MAX] = {0};
-#endif
-    const bool assume_riichi = P.is_menzen && P.prefer_riichi;
-    for (int e = 0; e < ne; e++) {
-        const int cnt = (s.G.edge_meta[eb + e] >> 6) & 7;
-        if (k == 0 && !ws.score_ok[e]) continue;  // uniform
-        const u32 child = s.G.edge_child[eb + e];
-        if (k > 0 && child == SP_NO_CHILD) continue;  // only after an overflow
-        MJX_SYNCWARP();
-        SP_FOR_LANES(j, T) {
-            ws.tpn[j] = SP_FMUL(SP_FDIV((float)cnt, (float)(n_left - j)), ws.nts[j]);
-            if (k > 0) {
-                ws.cv[0][j] = sp_vals(s, (int)child, 0)[j];
-                ws.cv[1][j] = sp_vals(s, (int)child, 1)[j];
-                ws.cv[2][j] = sp_vals(s, (int)child, 2)[j];
-            }
-        }
-        MJX_SYNCWARP();
-        SP_FOR_LANES(i, T) {
-#ifdef MJX_HOST_EMUL
-            tenpai = a_t[i]; win = a_w[i]; ev = a_v[i];
-#endif
-            const float m = ws.nts[i];
-            if (m != 0.f) {
-                for (int j = i; j < T; j++) {
-                    if (ws.nts[j] == 0.f) break;
-                    const float prob = SP_FDIV(ws.tpn[j], m);
-                    if (k == 0) {
-                        const int han_plus = (assume_riichi && P.calc_double_riichi && i == 0) + (assume_riichi && j == i) +
-                                             (P.calc_haitei && j == T - 1);
-                        win = SP_FADD(win, prob);
-                        ev = SP_FADD(ev, SP_FMUL(prob, ws.scores[e][han_plus]));
-                    } else {
-                        if (k == 1) tenpai = SP_FADD(tenpai, prob);
-                        if (j < T - 1) {
-                            if (k > 1) tenpai = SP_FADD(tenpai, SP_FMUL(prob, ws.cv[0][j + 1]));
-                            win = SP_FADD(win, SP_FMUL(prob, ws.cv[1][j + 1]));
-                            ev = SP_FADD(ev, SP_FMUL(prob, ws.cv[2][j + 1]));
-                        }
-                    }
-                }
-            }
-#ifdef MJX_HOST_EMUL
-            a_t[i] = tenpai; a_w[i] = win; a_v[i] = ev;
-#endif
-        }
-    }
-    MJX_SYNCWARP();
-    SP_FOR_LANES(i, T) {
-#ifdef MJX_HOST_EMUL
-        tenpai = a_t[i]; win = a_w[i]; ev = a_v[i];
-#endif
-        sp_vals(s, node, 0)[i] = tenpai;
-        sp_vals(s, node, 1)[i] = win;
-        sp_vals(s, node, 2)[i] = ev;
-    }
-    MJX_SYNCWARP();
-}
-
-#ifndef MJX_HOST_EMUL
-// Device form of sp_eval_w: TWO states per warp, one per half-warp (turn i = sub-lane; a state has at most 17
-// turns, sub-lane 15 also carries turn 16). Every lane performs exactly the float operations sp_eval_w performs for
-// its turn, in the same order, so the values are bit-identical; the halves only share the instruction stream.
-struct SpEvalScratch {
-    float nts[2][SP_T_MAX], tpn[2][SP_T_MAX], cv[2][3][SP_T_MAX];
-    float scores[2][40][4];
-    u8 score_ok[2][40];
+// ---------------------------------------------------------------------------------------------- evaluation
+struct SpEvalBatch {
+    u32 slot[SP_B], ebeg[SP_B];
+    u8 ne[SP_B], T[SP_B], nleft[SP_B], sumreq[SP_B], flags[SP_B];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei
+    u16 off[SP_B + 1];
+    float nts[SP_B][SP_T_MAX];      // not_tsumo_prob row of the state (calc.rs:148-167)
+    float tp[SP_B][4][SP_T_MAX];    // tsumo_prob[c-1][j] * not_tsumo[j] for c = 1..4
+    i32 n_items;
 };
 
-template <bool LEAF>
-MJX_DN void sp_eval_w2(SpCtx& s, SpEvalScratch& es, int node, int k_rt) {
-    const int k = LEAF ? 0 : k_rt;
-    const int hw = s.lane >> 4, l = s.lane & 15;
-    const bool live = node >= 0;
-    const SpRow* P = live ? &s.G.rows[s.G.node_row[node]] : nullptr;
-    const int T = live ? P->T : 0, n_left = live ? P->n_left : 0;
-    const int ne = live ? s.G.n_edges[node] : 0;
-    const u32 eb = live ? s.G.edge_begin[node] : 0;
-    float* nts = es.nts[hw];
-    float* tpn = es.tpn[hw];
-    int sum_required = 0;
-    for (int e = 0; e < ne; e++) sum_required += (s.G.edge_meta[eb + e] >> 6) & 7;
-    sum_required &= 0xFF;
-    for (int j = l; j < T; j += 16) {  // not_tsumo_prob_table[sum_required][j] (calc.rs:158-165)
-        float v = 0.f;
-        const int i0 = sum_required;
-        if (i0 <= n_left && i0 <= SP_MAX_TILES_LEFT) {
-            const int lim = min(T - 1, n_left - i0);
-            if (j <= lim) {
-                v = 1.f;
-                for (int q = 0; q < j; q++) v = SP_FDIV(SP_FMUL(v, (float)(n_left - i0 - q)), (float)(n_left - q));
-            }
-        }
-        nts[j] = v;
+// common prologue: stage the batch, lay the (state, turn) items out densely
+MJX_DN void sp_eval_stage(const SpGlobal& G, SpEvalBatch& S, const SpBlk& B, int level, int first, int nb, bool want_probs) {
+    const u32* list = G.wl + (size_t)level * G.wl_cap;
+    SP_PFOR(st, nb) {
+        const u32 slot = list[first + st];
+        const SpRow& R = G.rows[sp_key_row(G.hkey[slot])];
+        const u64 ei = G.einfo[slot];
+        S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei); S.sumreq[st] = (u8)sp_einfo_sum(ei);
+        S.T[st] = R.T; S.nleft[st] = R.n_left;
+        const bool ar = R.is_menzen && R.prefer_riichi;
+        S.flags[st] = (u8)((ar ? 1 : 0) | (R.calc_double_riichi ? 2 : 0) | (R.calc_haitei ? 4 : 0));
     }
-    if (k == 0) {
-        const int le0 = (int)eb - s.G.counters[4];
-        for (int e = l; e < ne; e += 16) {
-            const bool ok = !(s.G.edge_meta[eb + e] & 0x8000) && le0 + e >= 0 && le0 + e < s.G.score_cap;
-            es.score_ok[hw][e] = ok ? 1 : 0;
-            if (ok) for (int q = 0; q < 4; q++) es.scores[hw][e][q] = s.G.leaf_scores[(size_t)(le0 + e) * 4 + q];
-        }
+    SP_SYNC();
+    if (B.tid == 0) {
+        int acc = 0;
+        for (int st = 0; st < nb; st++) { S.off[st] = (u16)acc; acc += S.T[st]; }
+        S.off[nb] = (u16)acc; S.n_items = acc;
     }
-    __syncwarp();
-    float a0[3] = {0.f, 0.f, 0.f}, a1[3] = {0.f, 0.f, 0.f};  // (tenpai, win, ev) of turn l and of turn 16
-    const bool assume_riichi = live && P->is_menzen && P->prefer_riichi;
-    const bool dbl = live && P->calc_double_riichi, haitei = live && P->calc_haitei;
-    const int ne_max = max(ne, __shfl_xor_sync(0xffffffffu, ne, 16));
-    for (int e = 0; e < ne_max; e++) {
-        bool skip = e >= ne;
-        int cnt = 0;
-        u32 child = SP_NO_CHILD;
-        if (!skip) {
-            cnt = (s.G.edge_meta[eb + e] >> 6) & 7;
-            if (k == 0 && !es.score_ok[hw][e]) skip = true;
-            child = s.G.edge_child[eb + e];
-            if (k > 0 && child == SP_NO_CHILD) skip = true;  // only after an overflow
-        }
-        __syncwarp();
-        if (!skip)
-            for (int j = l; j < T; j += 16) {
-                tpn[j] = SP_FMUL(SP_FDIV((float)cnt, (float)(n_left - j)), nts[j]);
-                if (k > 0) {
-                    es.cv[hw][0][j] = sp_vals(s, (int)child, 0)[j];
-                    es.cv[hw][1][j] = sp_vals(s, (int)child, 1)[j];
-                    es.cv[hw][2][j] = sp_vals(s, (int)child, 2)[j];
+    if (want_probs) {
+        // not_tsumo_prob_table[sum_required][j], recomputed with the table's own recurrence (calc.rs:158-165)
+        SP_PFOR(it, nb * SP_T_MAX) {
+            const int st = it / SP_T_MAX, j = it - st * SP_T_MAX;
+            const int Tn = S.T[st], n_left = S.nleft[st], i0 = S.sumreq[st];
+            float v = 0.f;
+            if (j < Tn && i0 <= n_left && i0 <= SP_MAX_TILES_LEFT) {
+                const int lim = min(Tn - 1, n_left - i0);
+                if (j <= lim) {
+                    v = 1.f;
+                    for (int q = 0; q < j; q++) v = SP_FDIV(SP_FMUL(v, (float)(n_left - i0 - q)), (float)(n_left - q));
                 }
             }
-        __syncwarp();
-        if (!skip) {
-            auto turn = [&](int i, float* a) {
-                float tenpai = a[0], win = a[1], ev = a[2];
-                const float m = nts[i];
-                if (m != 0.f) {
-                    for (int j = i; j < T; j++) {
+            S.nts[st][j] = v;
+        }
+        SP_SYNC();
+        SP_PFOR(it, nb * 4 * SP_T_MAX) {
+            const int st = it / (4 * SP_T_MAX), r = it - st * 4 * SP_T_MAX, c = r / SP_T_MAX, j = r - c * SP_T_MAX;
+            float v = 0.f;
+            if (j < S.T[st]) v = SP_FMUL(SP_FDIV((float)(c + 1), (float)((int)S.nleft[st] - j)), S.nts[st][j]);
+            S.tp[st][c][j] = v;
+        }
+    }
+    SP_SYNC();
+}
+MJX_D int sp_eval_find(const SpEvalBatch& S, int nb, int item) {
+    int lo = 0, hi = nb - 1;  // last state whose offset is <= item
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)S.off[mid] <= item) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// calc.rs:447-561 draw_without_tegawari_slow. LEAF: the tenpai level (scores of the winning draws); otherwise shanten k >= 1.
+template <bool LEAF>
+MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalBatch& S, const SpBlk& B, int level, int first, int nb) {
+    const int k = LEAF ? 0 : sp_slot_shanten(level);
+    sp_eval_stage(G, S, B, level, first, nb, true);
+    SP_PFOR(item, S.n_items) {
+        const int st = sp_eval_find(S, nb, item), i = item - S.off[st];
+        const int Tn = S.T[st], ne = S.ne[st];
+        const u32 eb = S.ebeg[st];
+        const float* nts = S.nts[st];
+        float tenpai = 0.f, win = 0.f, ev = 0.f;
+        const float m = nts[i];
+        if (m != 0.f) {
+            const bool assume_riichi = (S.flags[st] & 1) != 0, dbl = (S.flags[st] & 2) != 0, haitei = (S.flags[st] & 4) != 0;
+            for (int e = 0; e < ne; e++) {
+                const u16 meta = G.emeta[eb + e];
+                const int cnt = (meta >> 6) & 7;
+                const float* tp = S.tp[st][cnt - 1];
+                if (LEAF) {
+                    if (meta & 0x8000) continue;  // no yaku
+                    const int le = (int)(eb + e) - G.counters[4];
+                    if (le < 0 || le >= G.score_cap) continue;
+                    const float* sc = G.leaf_scores + (size_t)le * 4;
+                    const float s0 = sc[0], s1 = sc[1], s2 = sc[2], s3 = sc[3];
+                    for (int j = i; j < Tn; j++) {
                         if (nts[j] == 0.f) break;
-                        const float prob = SP_FDIV(tpn[j], m);
-                        if (k == 0) {
-                            const int han_plus = (assume_riichi && dbl && i == 0) + (assume_riichi && j == i) + (haitei && j == T - 1);
-                            win = SP_FADD(win, prob);
-                            ev = SP_FADD(ev, SP_FMUL(prob, es.scores[hw][e][han_plus]));
-                        } else {
-                            if (k == 1) tenpai = SP_FADD(tenpai, prob);
-                            if (j < T - 1) {
-                                if (k > 1) tenpai = SP_FADD(tenpai, SP_FMUL(prob, es.cv[hw][0][j + 1]));
-                                win = SP_FADD(win, SP_FMUL(prob, es.cv[hw][1][j + 1]));
-                                ev = SP_FADD(ev, SP_FMUL(prob, es.cv[hw][2][j + 1]));
-                            }
+                        const float prob = SP_FDIV(tp[j], m);
+                        const int han_plus = (assume_riichi && dbl && i == 0) + (assume_riichi && j == i) + (haitei && j == Tn - 1);
+                        const float s = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : (han_plus == 2 ? s2 : s3));
+                        win = SP_FADD(win, prob);
+                        ev = SP_FADD(ev, SP_FMUL(prob, s));
+                    }
+                } else {
+                    const u32 child = G.echild[eb + e];
+                    if (child == SP_NO_CHILD) continue;  // only after an overflow
+                    const float* cv = G.vals + (size_t)child * SP_VALS;
+                    for (int j = i; j < Tn; j++) {
+                        if (nts[j] == 0.f) break;
+                        const float prob = SP_FDIV(tp[j], m);
+                        if (k == 1) tenpai = SP_FADD(tenpai, prob);
+                        if (j < Tn - 1) {
+                            if (k > 1) tenpai = SP_FADD(tenpai, SP_FMUL(prob, cv[j + 1]));
+                            win = SP_FADD(win, SP_FMUL(prob, cv[SP_T_MAX + j + 1]));
+                            ev = SP_FADD(ev, SP_FMUL(prob, cv[2 * SP_T_MAX + j + 1]));
                         }
                     }
                 }
-                a[0] = tenpai; a[1] = win; a[2] = ev;
-            };
-            if (l < T) turn(l, a0);
-            if (T > 16 && l == 15) turn(16, a1);
+            }
         }
+        float* o = G.vals + (size_t)S.slot[st] * SP_VALS;
+        o[i] = tenpai; o[SP_T_MAX + i] = win; o[2 * SP_T_MAX + i] = ev;
     }
-    __syncwarp();
-    if (live) {
-        if (l < T) for (int q = 0; q < 3; q++) sp_vals(s, node, q)[l] = a0[q];
-        if (T > 16 && l == 15) for (int q = 0; q < 3; q++) sp_vals(s, node, q)[16] = a1[q];
-    }
-    __syncwarp();
+    SP_SYNC();
 }
-#endif
 
-// calc.rs:563-637 discard_slow for one D-state (one warp, lane i = turn i)
-MJX_DN void sp_eval_d(SpCtx& s, const Ctx& c, int node) {
-    const int T = s.G.rows[s.G.node_row[node]].T;
-    const int ne = s.G.n_edges[node];
-    const u32 eb = s.G.edge_begin[node];
-    SP_FOR_LANES(i, T) {
+// calc.rs:563-637 discard_slow: per turn the child with the largest (truncated) EV, ties by discard priority
+MJX_DN void sp_eval_d_batch(const SpGlobal& G, SpEvalBatch& S, const SpBlk& B, int level, int first, int nb) {
+    sp_eval_stage(G, S, B, level, first, nb, false);
+    SP_PFOR(item, S.n_items) {
+        const int st = sp_eval_find(S, nb, item), i = item - S.off[st];
+        const int ne = S.ne[st];
+        const u32 eb = S.ebeg[st];
         const float FMIN = -3.40282347e+38f;
         float bt = FMIN, bw = FMIN, bv = FMIN;
         int best_tile = T_UNK;
         i32 best_value = (i32)0x80000000;
         for (int e = 0; e < ne; e++) {
-            const u32 child = s.G.edge_child[eb + e];
+            const u32 child = G.echild[eb + e];
             if (child == SP_NO_CHILD) continue;
-            const int tile = s.G.edge_meta[eb + e] & 63;
-            const float v = sp_vals(s, (int)child, 2)[i];
+            const int tile = G.emeta[eb + e] & 63;
+            const float* cv = G.vals + (size_t)child * SP_VALS;
+            const float v = cv[2 * SP_T_MAX + i];
             const i32 value = (i32)v;  // finite and < 2^31 here; Rust `as i32` truncates the same way
             if (value > best_value || (value == best_value && cmp_discard_priority(tile, best_tile) > 0)) {
-                bt = sp_vals(s, (int)child, 0)[i]; bw = sp_vals(s, (int)child, 1)[i]; bv = v;
+                bt = cv[i]; bw = cv[SP_T_MAX + i]; bv = v;
                 best_value = value; best_tile = tile;
             }
         }
-        sp_vals(s, node, 0)[i] = bt;
-        sp_vals(s, node, 1)[i] = bw;
-        sp_vals(s, node, 2)[i] = bv;
+        float* o = G.vals + (size_t)S.slot[st] * SP_VALS;
+        o[i] = bt; o[SP_T_MAX + i] = bw; o[2 * SP_T_MAX + i] = bv;
     }
-    MJX_SYNCWARP();
+    SP_SYNC();
 }
 
-#ifndef MJX_HOST_EMUL
-// Device form of sp_eval_d: two D-states per warp, one per half-warp (turn i = sub-lane, sub-lane 15 also carries turn 16).
-MJX_DN void sp_eval_d2(SpCtx& s, int node) {
-    if (node < 0) return;
-    const int l = s.lane & 15;
-    const int T = s.G.rows[s.G.node_row[node]].T;
-    const int ne = s.G.n_edges[node];
-    const u32 eb = s.G.edge_begin[node];
-    for (int pass = 0; pass < 2; pass++) {
-        const int i = pass == 0 ? l : 16;
-        if (pass == 0 ? i >= T : !(T > 16 && l == 15)) continue;
-        const float FMIN = -3.40282347e+38f;
-        float bt = FMIN, bw = FMIN, bv = FMIN;
-        int best_tile = T_UNK;
-        i32 best_value = (i32)0x80000000;
-        for (int e = 0; e < ne; e++) {
-            const u32 child = s.G.edge_child[eb + e];
-            if (child == SP_NO_CHILD) continue;
-            const int tile = s.G.edge_meta[eb + e] & 63;
-            const float v = sp_vals(s, (int)child, 2)[i];
-            const i32 value = (i32)v;  // finite and < 2^31 here; Rust `as i32` truncates the same way
-            if (value > best_value || (value == best_value && cmp_discard_priority(tile, best_tile) > 0)) {
-                bt = sp_vals(s, (int)child, 0)[i]; bw = sp_vals(s, (int)child, 1)[i]; bv = v;
-                best_value = value; best_tile = tile;
-            }
-        }
-        sp_vals(s, node, 0)[i] = bt;
-        sp_vals(s, node, 1)[i] = bw;
-        sp_vals(s, node, 2)[i] = bv;
+// KIND 0: D level, 1: W level above tenpai, 2: the tenpai W level
+template <int KIND>
+MJX_DN void sp_eval_level(const SpGlobal& G, SpEvalBatch& S, const SpBlk& B, int level) {
+    const int n = min(G.wl_count[level], G.wl_cap);
+    for (int first = B.bid * SP_B; first < n; first += B.nblk * SP_B) {
+        const int nb = min(SP_B, n - first);
+        if (KIND == 0) sp_eval_d_batch(G, S, B, level, first, nb);
+        else if (KIND == 1) sp_eval_w_batch<false>(G, S, B, level, first, nb);
+        else sp_eval_w_batch<true>(G, S, B, level, first, nb);
     }
 }
-#endif
+
+// release the table slots this DP used (instead of a full-table memset per step); after an overflow states may exist that
+// are in no work list, so the whole table is cleared.
+MJX_DN void sp_release(const SpGlobal& G, const SpBlk& B) {
+    const int gtid = B.bid * B.nthr + B.tid, gn = B.nblk * B.nthr;
+    if (G.counters[2]) {
+        for (int i = gtid; i < G.hash_cap; i += gn) G.hkey[i] = SP_EMPTY;
+        return;
+    }
+    for (int level = 0; level < SP_SLOTS; level++) {
+        const int n = min(G.wl_count[level], G.wl_cap);
+        const u32* list = G.wl + (size_t)level * G.wl_cap;
+        for (int i = gtid; i < n; i += gn) G.hkey[list[i]] = SP_EMPTY;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- rows: init / finalize
+struct SpCtx {  // warp-per-row stages
+    SpGlobal G;
+    Tables T;
+    u8* df;     // 34 bytes of per-warp scratch (dora factors)
+    int lane;
+};
 
 // per-candidate summary used by the obs rows
 struct SpCand {
     int tile;           // as sp/candidate.rs (may be an aka id)
-    int node;           // W-state whose values are the candidate's, or -1 (simple mode)
+    int node;           // W-state (table slot) whose values are the candidate's, or -1 (simple mode)
     u64 required;       // 34-bit set of required tile ids
     int num_required;   // sum of counts (u8 arithmetic in the reference)
     bool shanten_down;
@@ -956,10 +722,10 @@ MJX_DN void sp_stage_init(SpCtx& s, const TableState* S, int row, int table, int
     MJX_FOR_TILES(s, t) {
         int f = 0;
         for (int q = 0; q < S->n_dora; q++) f += tile_next(S->wall[60 - q]) == t;
-        s.ws->df[t] = (u8)f;
+        s.df[t] = (u8)f;
     }
     MJX_END_TILES(s);
-    const u8* df = s.ws->df;
+    const u8* df = s.df;
     Ctx c;
     c.S = const_cast<TableState*>(S); c.W = nullptr; c.T = s.T; c.lane = s.lane; c.df = df;
 
@@ -989,7 +755,7 @@ MJX_DN void sp_stage_init(SpCtx& s, const TableState* S, int row, int table, int
         R.avail = avail ? 1 : 0;
         R.fallback_ev = fallback;
         R.table = table; R.seat = (u8)seat;
-        R.root = -1;
+        R.root = SP_NO_CHILD;
         R.cd_flag = (cans & CAN_DISCARD) ? 1 : 0;
         R.cur_shanten = (i8)cur_shanten;
         R.has_values = cur_shanten <= SP_SHANTEN_THRES ? 1 : 0;
@@ -1037,10 +803,18 @@ MJX_DN void sp_stage_init(SpCtx& s, const TableState* S, int row, int table, int
             const int akas_seen = S->akas_public | PV.akas_in_hand;
             root.akas = (u8)((akas_hand & 7) | (((~akas_seen) & 7) << 3));
             root.pad_[0] = root.pad_[1] = root.pad_[2] = 0;
-            sp_key_copy(&R.root_key, &root);
+            R.root_key = root;
             if (R.has_values) {
-                const int slot = 2 * (3 - cur_shanten) + (R.can_discard ? 0 : 1);
-                R.root = sp_new_node(s, row, root, sp_sig_make(hand_sig(root.tehai), sp_key_hash_full(root)), slot);
+                // the root state: no draws, no discards; unique per row, so the insertion always creates it
+                const int level = 2 * (3 - cur_shanten) + (R.can_discard ? 0 : 1);
+                bool won;
+                const u32 slot = sp_intern(s.G, sp_key_make((u32)row, SP_DR_NONE, SP_DI_NONE), won);
+                if (slot != SP_NO_CHILD) {
+                    s.G.nsig[slot] = sp_sig_pack(hand_sig(root.tehai));
+                    const int pos = sp_atomic_add(&s.G.wl_count[level], 1);
+                    if (pos < s.G.wl_cap) { s.G.wl[(size_t)level * s.G.wl_cap + pos] = slot; R.root = slot; }
+                    else sp_set_overflow(s.G);
+                }
             }
         }
     }
@@ -1096,38 +870,40 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
             sp_required(s, c, len, R.root_key.tehai, R.root_key.wall, &cd.required, &cd.num_required);
         }
     } else {
-        if (R.root < 0) return;
+        if (R.root == SP_NO_CHILD) return;
         if (can_discard) {  // calc.rs:203-253: one candidate per shanten-keeping discard of the root
-            const int ne = s.G.n_edges[R.root];
-            const u32 eb = s.G.edge_begin[R.root];
+            const u64 ri = s.G.einfo[R.root];
+            const int ne = sp_einfo_n(ri);
+            const u32 eb = sp_einfo_begin(ri);
             for (int i = 0; i < ne && n_cands < 14; i++) {
-                const u32 child = s.G.edge_child[eb + i];
+                const u32 child = s.G.echild[eb + i];
                 if (child == SP_NO_CHILD) continue;
                 SpCand& cd = cands[n_cands++];
-                cd.tile = s.G.edge_meta[eb + i] & 63;
+                cd.tile = s.G.emeta[eb + i] & 63;
                 cd.node = (int)child;
                 cd.shanten_down = false;
             }
         } else {
             SpCand& cd = cands[n_cands++];
-            cd.tile = T_UNK; cd.node = R.root; cd.shanten_down = false;
+            cd.tile = T_UNK; cd.node = (int)R.root; cd.shanten_down = false;
         }
         for (int i = 0; i < n_cands; i++) {
             SpCand& cd = cands[i];
             const int node = cd.node;
-            const int ne = s.G.n_edges[node];
-            const u32 eb = s.G.edge_begin[node];
+            const u64 ni = s.G.einfo[node];
+            const int ne = sp_einfo_n(ni);
+            const u32 eb = sp_einfo_begin(ni);
             u64 req = 0; int num = 0;
             for (int q = 0; q < ne; q++) {
-                const u16 m = s.G.edge_meta[eb + q];
+                const u16 m = s.G.emeta[eb + q];
                 req |= 1ull << deaka(m & 63);
                 num += (m >> 6) & 7;
             }
             cd.required = req;
             cd.num_required = num & 0xFF;
-            cd.t0 = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s, node, 0)[0]);
-            cd.w0 = clamp01(sp_vals(s, node, 1)[0]);
-            cd.e0 = fmaxf(sp_vals(s, node, 2)[0], 0.f);
+            cd.t0 = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s.G, (u32)node, 0)[0]);
+            cd.w0 = clamp01(sp_vals(s.G, (u32)node, 1)[0]);
+            cd.e0 = fmaxf(sp_vals(s.G, (u32)node, 2)[0], 0.f);
         }
     }
     if (n_cands == 0) return;
@@ -1159,10 +935,10 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
         const SpCand& cd = cd_flag ? cands[q] : cands[first];
         const int node = cd.node;
         for (int turn = 0; turn < T; turn++) {
-            const float tp = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s, node, 0)[turn]);
+            const float tp = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s.G, (u32)node, 0)[turn]);
             if (!(tp > 0.f)) break;
-            const float wp = clamp01(sp_vals(s, node, 1)[turn]);
-            const float ev = fminf(SP_FMUL(fmaxf(sp_vals(s, node, 2)[turn], 0.f), ev_scale), 1.f);
+            const float wp = clamp01(sp_vals(s.G, (u32)node, 1)[turn]);
+            const float ev = fminf(SP_FMUL(fmaxf(sp_vals(s.G, (u32)node, 2)[turn], 0.f), ev_scale), 1.f);
             if (cd_flag) {
                 const int tid = deaka(cd.tile);
                 SPO_ASSIGN(961 + turn, tid, tp);

@@ -280,47 +280,44 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
             enc_materialize(L, e, tile + (size_t)lo * OBS_COLS, lo, lo + OBS_SLICE_ROWS < L.rows ? lo + OBS_SLICE_ROWS : L.rows);
     }
     if (!sp || version != 4) return;
-    // the same stage sequence mjx_env_encode_obs launches, executed by one lane
+    // the same stage sequence mjx_env_encode_obs launches (csrc/mjx_kernels.cu launch_sp_block), executed by one thread
     static SpGlobal G;
-    static std::vector<SpRow> rows; static std::vector<SpKey> keys; static std::vector<i32> node_row, slot_list;
-    static std::vector<float> vals; static std::vector<u32> edge_begin, edge_child, hash; static std::vector<u8> n_edges;
-    static std::vector<u16> edge_meta; static i32 slot_count[SP_SLOTS], counters[8];
-    static std::vector<u32> edge_owner; static std::vector<float> leaf_scores; static std::vector<SpSig> sigs;
-    if (keys.empty()) {
-        G.node_cap = 1 << 20; G.slot_cap = G.node_cap; G.edge_cap = G.node_cap * 6; G.hash_cap = 1 << 21; G.score_cap = G.edge_cap / 2;
-        edge_owner.resize(G.edge_cap); leaf_scores.resize((size_t)G.score_cap * 4); G.edge_owner = edge_owner.data(); G.leaf_scores = leaf_scores.data();
-        rows.resize(1 << 16); keys.resize(G.node_cap); node_row.resize(G.node_cap);
-        vals.resize((size_t)G.node_cap * 3 * SP_T_MAX); edge_begin.resize(G.node_cap); n_edges.resize(G.node_cap);
-        edge_child.resize(G.edge_cap); edge_meta.resize(G.edge_cap); hash.resize(G.hash_cap);
-        slot_list.resize((size_t)SP_SLOTS * G.slot_cap);
-        sigs.resize(G.node_cap); G.sigs = sigs.data();
-        G.rows = rows.data(); G.keys = keys.data(); G.node_row = node_row.data(); G.vals = vals.data();
-        G.edge_begin = edge_begin.data(); G.n_edges = n_edges.data(); G.edge_child = edge_child.data();
-        G.edge_meta = edge_meta.data(); G.hash = hash.data(); G.slot_list = slot_list.data(); G.slot_count = slot_count;
-        G.counters = counters;
+    static std::vector<SpRow> rows; static std::vector<u64> hkey, einfo; static std::vector<SpSigP> nsig;
+    static std::vector<float> vals, leaf_scores; static std::vector<u32> echild, eowner, wl; static std::vector<u16> emeta;
+    static i32 wl_count[SP_SLOTS], counters[8];
+    if (hkey.empty()) {
+        G.hash_cap = 1 << 21; G.wl_cap = G.hash_cap / 4; G.edge_cap = G.hash_cap * 2; G.score_cap = G.hash_cap;
+        rows.resize(1 << 16); hkey.assign(G.hash_cap, SP_EMPTY); einfo.resize(G.hash_cap); nsig.resize(G.hash_cap);
+        vals.resize((size_t)G.hash_cap * SP_VALS); leaf_scores.resize((size_t)G.score_cap * 4);
+        echild.resize(G.edge_cap); eowner.resize(G.edge_cap); emeta.resize(G.edge_cap); wl.resize((size_t)SP_SLOTS * G.wl_cap);
+        G.rows = rows.data(); G.hkey = hkey.data(); G.einfo = einfo.data(); G.nsig = nsig.data(); G.vals = vals.data();
+        G.leaf_scores = leaf_scores.data(); G.echild = echild.data(); G.eowner = eowner.data(); G.emeta = emeta.data();
+        G.wl = wl.data(); G.wl_count = wl_count; G.counters = counters;
+        for (int i = 0; i < 8; i++) counters[i] = 0;
     }
-    std::fill(hash.begin(), hash.end(), 0u);
-    for (int i = 0; i < SP_SLOTS; i++) slot_count[i] = 0;
-    counters[0] = counters[1] = counters[2] = 0;
-    SpWarpScratch ws;
-    SpCtx s; s.G = G; s.T = g_T; s.ws = &ws; s.lane = 0;
-    Ctx c; c.S = nullptr; c.W = nullptr; c.T = g_T; c.lane = 0; c.df = nullptr;
+    for (int i = 0; i < SP_SLOTS; i++) wl_count[i] = 0;
+    counters[1] = counters[2] = counters[4] = counters[5] = 0;
+    u8 df[40];
+    SpCtx s; s.G = G; s.T = g_T; s.df = df; s.lane = 0;
+    SpBlk B; B.tid = 0; B.nthr = 1; B.bid = 0; B.nblk = 1;
+    static SpExpandBatch xb; static SpEvalBatch eb;
     for (int r = 0; r < n_rows; r++) sp_stage_init(s, &E->tabs[E->row_table[r]], r, E->row_table[r], E->row_seat[r] & 3);
-    for (int slot = 0; slot < SP_SLOTS; slot++) {
-        if (slot == SP_SLOTS - 1) counters[4] = counters[1];
-        for (int i = 0; i < std::min(slot_count[slot], G.slot_cap); i++) sp_expand(s, c, slot_list[(size_t)slot * G.slot_cap + i], slot);
+    for (int level = 0; level < SP_SLOTS; level++) {
+        if (level == SP_SLOTS - 1) { counters[4] = counters[1]; sp_expand_level<2>(G, g_T, xb, B, level); }
+        else if (sp_slot_is_w(level)) sp_expand_level<1>(G, g_T, xb, B, level);
+        else sp_expand_level<0>(G, g_T, xb, B, level);
     }
     counters[5] = counters[1];
-    for (int e = counters[4]; e < counters[5]; e++) sp_score_edge(s, e);
-    for (int slot = SP_SLOTS - 1; slot >= 0; slot--)
-        for (int i = 0; i < std::min(slot_count[slot], G.slot_cap); i++) {
-            int node = slot_list[(size_t)slot * G.slot_cap + i];
-            if (!sp_slot_is_w(slot)) sp_eval_d(s, c, node);
-            else if (sp_slot_shanten(slot) == 0) sp_eval_w<true>(s, c, node, 0);
-            else sp_eval_w<false>(s, c, node, sp_slot_shanten(slot));
-        }
+    for (int e = counters[4]; e < counters[5]; e++) sp_score_edge(G, g_T, e);
+    for (int level = SP_SLOTS - 1; level >= 0; level--) {
+        if (!sp_slot_is_w(level)) sp_eval_level<0>(G, eb, B, level);
+        else if (level == SP_SLOTS - 1) sp_eval_level<2>(G, eb, B, level);
+        else sp_eval_level<1>(G, eb, B, level);
+    }
     for (int r = 0; r < n_rows; r++) sp_stage_finalize(s, r, obs + (size_t)r * OBS_ROWS_V4 * OBS_COLS);
     if (counters[2]) g_emul_sp_overflows++;
+    sp_release(G, B);
+    counters[2] = 0;
 }
 void emul_env_results(void* p, int32_t* scores, uint8_t* ranks, int32_t* steps, int32_t* errs, int32_t* done) {
     EmulEnv* E = static_cast<EmulEnv*>(p);

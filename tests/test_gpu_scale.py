@@ -64,7 +64,7 @@ def test_obs_parity_4096_tables_steady_state(mjx):
         got_obs.append(obs[pick].cpu().numpy())
         got_masks.append(env.masks[pick].cpu().numpy())
         rs = env.row_seat[pick].long()
-        samples.append(torch.stack([env.row_table[pick].long(), env.row_step[pick].long(), rs & 3, (rs >> 2) & 1], dim=1).cpu().numpy())
+        samples.append(torch.stack([env.row_table[pick].long(), env.row_step[:nr].long()[pick], rs & 3, (rs >> 2) & 1], dim=1).cpu().numpy())
         env.policy_test(1, actions)
         env.step(actions)
     assert env.sp_overflows() == 0
