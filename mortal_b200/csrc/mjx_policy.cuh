@@ -30,7 +30,9 @@ MJX_D int kth_set_bit(u64 m, int k) {
 
 // kind 0: uniform over the legal mask. kind 1: agari first, riichi with p = 3/4, calls vs discards
 // by coin flip, discards prefer next-shanten then keep-shanten tiles (see oracle/board.cc).
+// kind 2: kind 1 with the hash taken from the legal mask alone (a function of what an engine sees; bench.py's e2e engine).
 MJX_D int test_policy(int kind, u64 h, bool kan_select, u64 mask, u64 keep34, u64 next34) {
+    if (kind == 2) { h = splitmix64(mask); kind = 1; }
     if (kind == 0 || kan_select) return kth_set_bit(mask, (int)(h % (u64)mjx_popcll(mask)));
     if ((mask >> 43) & 1) return 43;
     u64 h2 = splitmix64(h);

@@ -103,6 +103,8 @@ class _Arena:
         self.log_meta = True    # attach the per-decision meta (q-values, mask bits, ...) to the agent events (mortal.rs:161-186)
         self.last_meta_error = None
         self.max_cycles = 0     # test hook: stop after this many BatchGame::run cycles (0 = play every table to the end)
+        self.fast_forward_steps = 0  # bench hook: play this many batch steps with the counter-free test policy (kind 2) first
+        self.cycle_hook = None       # bench hook: callable(cycle_index, env) at the top of every cycle
         self.last_decision_masks = None  # with record_decisions: the legal mask (46 bits) each recorded row was decided under
 
     def _challenger_seats(self, game_in_seed: int):
@@ -181,11 +183,21 @@ class _Arena:
                                    "run fewer tables per environment")
             return nr_, live_
 
+        skip_step = False
+        if self.fast_forward_steps:
+            env.step(None)
+            for _ in range(int(self.fast_forward_steps)):
+                env.policy_test(2, actions)
+                env.step(actions)
+            first, skip_step = False, True
         while True:
             if self.max_cycles and cycles >= self.max_cycles:
                 break
-            env.step(None if first else actions, None if first else q_all)
-            first = False
+            if self.cycle_hook is not None:
+                self.cycle_hook(cycles, env)
+            if not skip_step:
+                env.step(None if first else actions, None if first else q_all)
+            first = skip_step = False
             if meta_rec is not None:
                 meta_rec.add_bounds(env.log_len)
             nr, n_live = check_health()

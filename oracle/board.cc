@@ -860,6 +860,15 @@ static int count_set(const u8* mask, int lo, int hi) {
 //   CUDA test policy (mortal_b200/csrc/policy_test.cu) computes the identical choice.
 int test_policy(int kind, const Scene& sc, u64 nonce, u64 key, const u8* mask) {
     u64 h = policy_hash(nonce, key, (u64)sc.table, sc.step_idx, sc.seat, sc.is_kan_select ? 1 : 0);
+    if (kind == 2) {
+        // kind 2 = kind 1 with the hash taken from the legal mask alone: a function of what an engine is handed
+        // (mask + the keep / next-shanten planes of the observation), so the CPU arm, the device test policy and a
+        // react_batch engine behind the plugin API all play the very same games (bench.py)
+        u64 bits = 0;
+        for (int i = 0; i < 46; i++) if (mask[i]) bits |= 1ull << i;
+        h = splitmix64(bits);
+        kind = 1;
+    }
     if (kind == 0 || sc.is_kan_select) {
         int n = count_set(mask, 0, 46);
         return kth_set(mask, 0, 46, (int)(h % (u64)n));

@@ -570,6 +570,63 @@ static int run_batch_impl(const orc_run_cfg* cfg, const uint64_t* nonces, const 
     } catch (const std::exception& e) { return fail(e); }
 }
 
+// ---- persistent batch (bench.py --impl reference): the tables live across calls, so one timed "step" is one pass
+// of the whole batch, exactly like BatchGame::run's loop body (game.rs:286-304).
+struct OrcBatch {
+    orc_run_cfg cfg;
+    std::vector<std::unique_ptr<TableRun>> runs;
+};
+void* orc_batch_new(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t* keys) {
+    OrcBatch* b = new OrcBatch();
+    b->cfg = *cfg;
+    b->runs.resize(cfg->n_tables);
+    for (int t = 0; t < cfg->n_tables; t++) {
+        b->runs[t].reset(new TableRun());
+        Game& g = b->runs[t]->g;
+        g.seed_nonce = nonces[t]; g.seed_key = keys[t]; g.shuffle_kind = cfg->shuffle_kind; g.table = t;
+    }
+    return b;
+}
+void orc_batch_free(void* p) { delete static_cast<OrcBatch*>(p); }
+// advance every live table to `until` table-steps (dynamic hand-out over cfg.n_threads workers); rows at step_idx >=
+// encode_from are encoded when cfg.encode_obs is set. out: table-steps advanced by this call, rows, seconds of this call.
+int orc_batch_run(void* p, int64_t until, int64_t encode_from, orc_run_out* out) {
+    try {
+        OrcBatch& b = *static_cast<OrcBatch*>(p);
+        const int n = b.cfg.n_tables, nt = std::max(1, b.cfg.n_threads);
+        int64_t before = 0, rows_before = 0;
+        for (int t = 0; t < n; t++) { before += b.runs[t]->n_steps; rows_before += b.runs[t]->rows; }
+        std::vector<std::string> errs(nt);
+        std::atomic<int> next(0);
+        std::atomic<int64_t> tlen(0);
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; k++)
+            th.emplace_back([&, k]() {
+                try {
+                    std::vector<float> obs;
+                    if (b.cfg.encode_obs) obs.resize((size_t)obs_rows(b.cfg.encode_obs) * 34);
+                    for (;;) {
+                        const int t = next.fetch_add(1);
+                        if (t >= n) break;
+                        run_table(b.cfg, *b.runs[t], t, until, encode_from, obs, nullptr, 0, &tlen, nullptr);
+                    }
+                } catch (const std::exception& e) { errs[k] = e.what(); }
+            });
+        for (auto& t : th) t.join();
+        auto t1 = std::chrono::steady_clock::now();
+        for (auto& e : errs) if (!e.empty()) throw OrcError(e);
+        int64_t after = 0, rows_after = 0;
+        for (int t = 0; t < n; t++) { after += b.runs[t]->n_steps; rows_after += b.runs[t]->rows; }
+        if (out) {
+            out->table_steps = after - before;
+            out->obs_rows = rows_after - rows_before;
+            out->seconds = std::chrono::duration<double>(t1 - t0).count();
+        }
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
 int orc_run_batch(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t* keys, const int32_t* table_ids,
                   int32_t* scores, uint8_t* ranks, int32_t* steps, int64_t* trace, int64_t trace_cap,
                   int64_t* trace_len_out, orc_run_out* out) {

@@ -202,6 +202,10 @@ def lib():
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_run_sample_obs.argtypes = [C.POINTER(RunCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_batch_new.restype = C.c_void_p
+    L.orc_batch_new.argtypes = [C.POINTER(RunCfg), C.c_void_p, C.c_void_p]
+    L.orc_batch_free.argtypes = [C.c_void_p]
+    L.orc_batch_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(RunOut)]
     L.orc_policy_hash.restype = C.c_uint64
     L.orc_policy_hash.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
     if L.orc_init(DATA_DIR.encode()) != 0:
@@ -537,3 +541,28 @@ def gameplay_load(events, player_id, *, version=4, always_include_kan_select=Tru
     assert n >= 0, err()
     return dict(obs=obs[:n] if with_obs else None, masks=masks[:n].astype(bool), actions=actions[:n], at_kyoku=at_kyoku[:n],
                 apply_gamma=gamma[:n].astype(bool), at_turns=at_turns[:n], shantens=shantens[:n])
+
+
+class Batch:
+    """Persistent CPU arena (bench.py --impl reference): tables live across calls; run(until) advances every live table to
+    `until` table-steps and returns (table_steps advanced, rows decided, seconds)."""
+
+    def __init__(self, nonces, keys, *, shuffle_kind=0, policy_kind=2, quick_eval=True, encode_obs=4, sp_mode=1, n_threads=1):
+        nonces = np.ascontiguousarray(nonces, dtype=np.uint64)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        cfg = RunCfg(len(nonces), shuffle_kind, policy_kind, int(quick_eval), 0, encode_obs, sp_mode, n_threads, 0, 0)
+        self._h = lib().orc_batch_new(C.byref(cfg), nonces.ctypes.data, keys.ctypes.data)
+
+    def run(self, until, encode_from=0):
+        out = RunOut()
+        if lib().orc_batch_run(self._h, until, encode_from, C.byref(out)) != 0:
+            raise RuntimeError(err())
+        return out.table_steps, out.obs_rows, out.seconds
+
+    def close(self):
+        if self._h:
+            lib().orc_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()

@@ -28,7 +28,7 @@ def first_diff(a, b):
     return n, None, None
 
 
-@pytest.mark.parametrize("policy_kind", [1, 0])
+@pytest.mark.parametrize("policy_kind", [1, 0, 2])
 @pytest.mark.parametrize("quick_eval", [True, False])
 @pytest.mark.parametrize("shuffle_kind", [0, 1])
 def test_selfplay_trace_parity(policy_kind, quick_eval, shuffle_kind):
@@ -403,3 +403,36 @@ def test_log_replay_with_augmentation_emulated():
         # discards (and kan-select tiles) move with the suits, everything else keeps its label
         assert len(ref_aug) == len(ref_raw) and all(b == a or b == swap(a) for a, b in zip(ref_raw, ref_aug))
     rep.close()
+
+
+def test_bench_engine_plays_policy_kind_2():
+    """bench.py's MaskHashEngine (a reference-protocol react_batch engine in numpy) chooses, from the legal mask and the v4
+    observation planes alone, exactly what the test policy kind 2 chooses on the device / in the oracle: the CPU arm, env_only
+    and e2e of the benchmark therefore play the same games."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    eng = bench.MaskHashEngine()
+    n = 24
+    nonces = np.arange(3000, 3000 + n, dtype=np.uint64)
+    keys = np.full(n, 11, dtype=np.uint64)
+    env = E.EmulEnv(nonces, keys, enable_quick_eval=True)
+    env.step(None)
+    checked = 0
+    for cycle in range(220):
+        rt, rs, masks = env.rows()
+        want = env.policy_test(2)
+        if len(rt):
+            obs = env.encode_obs(sp=False)
+            got, q, m, greedy = eng.react_batch([obs[i] for i in range(len(rt))], [masks[i] for i in range(len(rt))], None)
+            assert got == want[: len(rt)].tolist(), (cycle, np.nonzero(np.array(got) != want[: len(rt)])[0][:5])
+            assert len(q) == len(rt) and len(q[0]) == 46 and m[0] == masks[0].tolist() and all(greedy)
+            checked += len(rt)
+        env.step(want)
+        if env.num_live() == 0:
+            break
+    env.close()
+    assert checked > 3000

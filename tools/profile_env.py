@@ -24,16 +24,16 @@ env.set_sp(not args.no_sp)
 actions = torch.zeros(env.row_cap, dtype=torch.int64, device=env.device)
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 env.step(None)
-env.policy_test(1, actions)
+env.policy_test(2, actions)
 for _ in range(args.skip):
     env.step(actions)
-    env.policy_test(1, actions)
+    env.policy_test(2, actions)
 for i in range(args.cycles):
     if i == 3:
         t0.record()
     env.step(actions)
     env.encode_obs()
-    env.policy_test(1, actions)
+    env.policy_test(2, actions)
 t1.record()
 torch.cuda.synchronize()
 print(f"{args.cycles - 3} cycles, {t0.elapsed_time(t1) / max(args.cycles - 3, 1):.3f} ms/cycle, rows last {env.num_rows()}, "
