@@ -105,6 +105,7 @@ class _Arena:
         self.max_cycles = 0     # test hook: stop after this many BatchGame::run cycles (0 = play every table to the end)
         self.fast_forward_steps = 0  # bench hook: play this many batch steps with the counter-free test policy (kind 2) first
         self.cycle_hook = None       # bench hook: callable(cycle_index, env) at the top of every cycle
+        self.env_factory = BatchEnv  # test hook: tests/emul_batch_env.py injects the host-emulated environment; the product has no CPU path
         self.last_decision_masks = None  # with record_decisions: the legal mask (46 bits) each recorded row was decided under
 
     def _challenger_seats(self, game_in_seed: int):
@@ -129,8 +130,8 @@ class _Arena:
         n = int(seed_count) * per
         nonces = np.repeat(np.arange(seed_start[0], seed_start[0] + int(seed_count), dtype=np.uint64), per)
         keys = np.full(n, seed_start[1], dtype=np.uint64)
-        env = BatchEnv(nonces, keys, obs_version=versions[0], shuffle_kind=self.shuffle_kind, enable_quick_eval=qe[0],
-                       device=self.device)
+        env = self.env_factory(nonces, keys, obs_version=versions[0], shuffle_kind=self.shuffle_kind, enable_quick_eval=qe[0],
+                               device=self.device)
         dev = env.device
         # seat -> agent index table per game-in-seed
         is_challenger = torch.zeros((per, 4), dtype=torch.bool, device=dev)
@@ -156,10 +157,11 @@ class _Arena:
         # mjx_env_encode_obs_host: pinned host buffers, D2H overlapped with the single-player kernels
         host_mode = all(isinstance(a, HostProtocolEngine) for a in agents)
         if host_mode:
-            h_obs = torch.empty((env.row_cap, env.obs_rows, 34), dtype=torch.float32).pin_memory()
-            h_masks = torch.empty((env.row_cap, 46), dtype=torch.bool).pin_memory()
-            h_actions = torch.zeros(env.row_cap, dtype=torch.int64).pin_memory()
-            h_q = torch.zeros((env.row_cap, 46), dtype=torch.float32).pin_memory() if q_all is not None else None
+            pin = (lambda t: t.pin_memory()) if dev.type == "cuda" else (lambda t: t)
+            h_obs = pin(torch.empty((env.row_cap, env.obs_rows, 34), dtype=torch.float32))
+            h_masks = pin(torch.empty((env.row_cap, 46), dtype=torch.bool))
+            h_actions = pin(torch.zeros(env.row_cap, dtype=torch.int64))
+            h_q = pin(torch.zeros((env.row_cap, 46), dtype=torch.float32)) if q_all is not None else None
             obs_np, masks_np = h_obs.numpy(), h_masks.numpy()
             ic_host = is_challenger.cpu().numpy()
         first = True

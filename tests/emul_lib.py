@@ -47,6 +47,7 @@ def lib():
         L.emul_replay_step.argtypes = [C.c_void_p]
         L.emul_replay_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_env_errs.argtypes = [C.c_void_p, C.c_void_p]
+        L.emul_env_row_steps.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_env_enable_log.argtypes = [C.c_void_p, C.c_int]
         L.emul_env_read_log.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_env_log_lens.argtypes = [C.c_void_p, C.c_void_p]

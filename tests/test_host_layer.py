@@ -301,3 +301,104 @@ def test_policy_net_fast_path_equals_stock_forward_on_cpu():
     s = sample_top_p(logits, 0.7)
     assert set(s.tolist()) <= {0, 1} and 0.68 < (s == 0).float().mean() < 0.78  # nucleus {0, 1}: 0.61 / (0.61 + 0.224)
     assert sample_top_p(logits[:3], 0.0).tolist() == [0, 0, 0]
+
+
+import oracle_lib as O  # noqa: E402 (test infrastructure)
+
+
+def _emul_arena(cls):
+    from emul_batch_env import EmulBatchEnv
+
+    arena = cls(disable_progress_bar=True)
+    arena.env_factory = EmulBatchEnv
+    return arena
+
+
+def test_arena_host_protocol_loop_on_emulated_env_fail_fast():
+    """The arena's host-protocol loop on the host-emulated environment: (1) an engine that answers an illegal action makes
+    py_vs_py raise at that very cycle (game.rs:288,292 aborts the batch), not after the games were played out; (2) a legal
+    engine's recorded decisions replay in the oracle to the same scores."""
+    import pytest
+
+    from mortal_b200.libriichi.arena import OneVsThree
+
+    class Eng:
+        engine_type = "mortal"; name = "e"; version = 4; is_oracle = False
+        enable_quick_eval = True; enable_rule_based_agari_guard = False
+
+        def __init__(self, bad_at=None):
+            self.calls, self.bad_at = 0, bad_at
+
+        def react_batch(self, obs, masks, invisible_obs):
+            self.calls += 1
+            m = np.stack(masks)
+            a = [int(np.nonzero(r)[0][-1]) for r in m]            # the highest legal action id
+            if self.bad_at is not None and self.calls >= self.bad_at:
+                a[0] = int(np.nonzero(~m[0])[0][0])               # an illegal one
+            return a, np.where(m, 0.0, -np.inf).tolist(), m.tolist(), [True] * len(a)
+
+    bad = Eng(bad_at=7)
+    arena = _emul_arena(OneVsThree)
+    with pytest.raises(RuntimeError, match="failed at cycle"):
+        arena.py_vs_py(bad, bad, (5000, 3), 1)
+    assert bad.calls <= 9, "the batch must abort at the offending cycle"
+
+    good = Eng()
+    arena = _emul_arena(OneVsThree)
+    arena.record_decisions = True
+    rankings = arena.py_vs_py(good, good, (5000, 3), 1)
+    assert sum(rankings) == 4
+    nonces = np.repeat(np.arange(5000, 5001, dtype=np.uint64), 4)
+    keys = np.full(4, 3, dtype=np.uint64)
+    ref = O.run_replay(nonces, keys, arena.last_decisions, quick_eval=True, mask_bits=arena.last_decision_masks)
+    assert (ref["scores"] == arena.last_results["scores"]).all() and (ref["ranks"] == arena.last_results["ranks"]).all()
+
+
+def test_reference_mortal_engine_and_model_drop_in_unchanged():
+    """north_star: "mortal/train.py and mortal/engine.py drop in unchanged". The reference's OWN, unmodified mortal/engine.py
+    (MortalEngine) and mortal/model.py (Brain, DQN) are imported from /root/reference against the `libriichi` module this repo
+    installs, and drive libriichi.arena.OneVsThree.py_vs_py exactly like mortal/player.py:60-69 does (host-emulated environment:
+    this container has no GPU). The recorded decisions replay in the oracle to the same scores / rankings. Skipped where the
+    reference tree is absent (the GPU box)."""
+    import importlib
+    import sys
+
+    import pytest
+
+    ref_dir = "/root/reference/mortal"
+    if not os.path.isdir(ref_dir):
+        pytest.skip("reference tree not present")
+    import torch
+
+    import mortal_b200.libriichi as lr
+
+    lr.install()
+    sys.path.insert(0, ref_dir)
+    try:
+        for name in ("model", "engine"):
+            sys.modules.pop(name, None)
+        ref_model = importlib.import_module("model")
+        ref_engine = importlib.import_module("engine")
+    finally:
+        sys.path.remove(ref_dir)
+    assert ref_model.__file__.startswith(ref_dir) and ref_engine.__file__.startswith(ref_dir)
+    from libriichi.arena import OneVsThree
+
+    torch.manual_seed(0)
+    mk = lambda name: ref_engine.MortalEngine(ref_model.Brain(version=4, conv_channels=16, num_blocks=1).eval(),
+                                              ref_model.DQN(version=4).eval(), is_oracle=False, version=4,
+                                              device=torch.device("cpu"), enable_amp=False, enable_quick_eval=True,
+                                              enable_rule_based_agari_guard=False, name=name)
+    arena = _emul_arena(OneVsThree)
+    arena.record_decisions = True
+    rankings = arena.py_vs_py(challenger=mk("challenger"), champion=mk("champion"), seed_start=(10000, 0x2000), seed_count=1)
+    assert sum(rankings) == 4
+    nonces = np.repeat(np.arange(10000, 10001, dtype=np.uint64), 4)
+    keys = np.full(4, 0x2000, dtype=np.uint64)
+    ref = O.run_replay(nonces, keys, arena.last_decisions, quick_eval=True, mask_bits=arena.last_decision_masks)
+    got = arena.last_results
+    assert (ref["scores"] == got["scores"]).all() and (ref["ranks"] == got["ranks"]).all() and (ref["steps"] == got["steps"]).all()
+    hist = [0, 0, 0, 0]
+    for i in range(4):
+        hist[int(ref["ranks"][i, i % 4])] += 1
+    assert hist == rankings
