@@ -134,6 +134,31 @@ MJX_D int shanten_all_sig(const Tables& T, const HandSig& s, int len_div3) {
     return sh;
 }
 
+// The same for a hand of which only suit `sx` differs from a base hand: `others` = the min-plus merge of the other three
+// suits' rows (10 entries; shanten.rs:51-80 is an exact min-plus convolution, so association order does not matter).
+// One gather + the single entry 5 + len_div3 of the last merge: min over a + b = len of others[5+a] + row[b], others[a] + row[5+b].
+MJX_D int shanten_all_others(const Tables& T, const HandSig& s, int sx, const u8* others, int len_div3) {
+    const u64 r = sx < 3 ? ld_row(T.suhai, s.idx[sx], SUHAI_ROWS) : ld_row(T.jihai, s.idx[sx], JIHAI_ROWS);
+    int v = 1 << 20;
+#pragma unroll
+    for (int a = 0; a <= 4; a++) {
+        if (a <= len_div3) {
+            const int b = len_div3 - a;
+            v = min(v, (int)others[5 + a] + (int)((r >> (4 * b)) & 0xF));
+            v = min(v, (int)others[a] + (int)((r >> (4 * (5 + b))) & 0xF));
+        }
+    }
+    int sh = v - 1;
+    if (sh <= 0 || len_div3 < 4) return sh;
+    int chitoi = 7 - s.pairs + max(7 - s.kinds, 0) - 1;
+    sh = min(sh, chitoi);
+    if (sh > 0) {
+        int kokushi = 14 - s.kkinds - (s.kpairs > 0 ? 1 : 0) - 1;
+        sh = min(sh, kokushi);
+    }
+    return sh;
+}
+
 MJX_D int shanten_all(const Tables& T, const u8* tehai, int len_div3) {
     return shanten_all_sig(T, hand_sig(tehai), len_div3);
 }

@@ -293,11 +293,17 @@ __global__ void __launch_bounds__(SP_THREADS) k_sp_expand(SpGlobal G, Tables T, 
     sp_expand_level<KIND>(G, T, sb, B, level);
 }
 
+// KIND 0: D level (per-turn best discard), 1: W level above tenpai, 2: the tenpai W level (scores of the winning draws)
 template <int KIND>
 __global__ void __launch_bounds__(SP_THREADS) k_sp_eval(SpGlobal G, int level) {
-    __shared__ SpEvalBatch sb;
     SpBlk B; B.tid = threadIdx.x; B.nthr = blockDim.x; B.bid = blockIdx.x; B.nblk = gridDim.x;
-    sp_eval_level<KIND>(G, sb, B, level);
+    if (KIND == 0) {
+        __shared__ SpEvalDBatch sd;
+        sp_eval_d_level(G, sd, B, level);
+    } else {
+        __shared__ SpEvalWBatch sw;
+        sp_eval_w_level<KIND == 2>(G, sw, B, level);
+    }
 }
 
 __global__ void k_sp_mark(SpGlobal G, int which) { G.counters[4 + which] = min(G.counters[1], G.edge_cap); }

@@ -144,7 +144,7 @@ struct SpGlobal {
     SpRow* rows;        // [row_cap]
     u64* hkey;          // [hash_cap] state key (SP_EMPTY = free); the slot index is the state's id
     SpSigP* nsig;       // [hash_cap] shanten signatures of the state's hand
-    u64* einfo;         // [hash_cap] edge_begin | n_edges << 32 | sum of required-tile counts << 40
+    u64* einfo;         // [hash_cap] edge_begin | n_edges << 32 | sum of required-tile counts << 40 | counts present (4 bits) << 48
     float* vals;        // [hash_cap][3][SP_T_MAX]
     u32* echild;        // [edge_cap] child state (table slot)
     u16* emeta;         // [edge_cap] tile (6 bits) | count << 6 | (no-yaku flag << 15, tenpai states only)
@@ -183,6 +183,7 @@ MJX_D float* sp_vals(const SpGlobal& G, u32 node, int which) { return G.vals + (
 MJX_D u32 sp_einfo_begin(u64 e) { return (u32)e; }
 MJX_D int sp_einfo_n(u64 e) { return (int)((e >> 32) & 0xFF); }
 MJX_D int sp_einfo_sum(u64 e) { return (int)((e >> 40) & 0xFF); }
+MJX_D int sp_einfo_cmask(u64 e) { return (int)((e >> 48) & 0xF); }
 
 MJX_D void sp_set_overflow(const SpGlobal& G) { G.counters[2] = 1; }
 
@@ -235,8 +236,9 @@ struct SpExpandBatch {
     SpSigP sig[SP_B];
     u8 akas[SP_B], len[SP_B];
     u8 teh[SP_B][34], wall[SP_B][34];
+    u8 oth[SP_B][4][12];   // per suit s: min-plus merge of the OTHER three suits' table rows (10 entries)
     u32 cand[SP_B][2], eff[SP_B][2];
-    u8 split[SP_B], ne[SP_B], sumreq[SP_B];
+    u8 split[SP_B], ne[SP_B], sumreq[SP_B], cmask[SP_B];
     u16 cand_off[SP_B + 1], e_off[SP_B + 1];
     u16 cand_list[SP_B * 34];
     u32 edge[SP_B * SP_MAX_EDGES];  // state | tile << 8 | count << 16
@@ -265,15 +267,36 @@ MJX_DN void sp_expand_batch(const SpGlobal& G, const Tables& T, SpExpandBatch& S
     }
     if (B.tid == 0) S.n_win = 0;
     SP_SYNC();
-    // counts of every tile kind in the state's hand and wall; candidate tiles: still in the wall (W) / held (D)
+    // counts of every tile kind in the state's hand and wall: the root's, then the state's <= 7 draws / discards applied
     SP_PFOR(it, nb * 34) {
         const int st = it / 34, t = it - st * 34;
+        const SpRow& R = G.rows[sp_key_row(S.key[st])];
+        S.teh[st][t] = R.root_key.tehai[t]; S.wall[st][t] = R.root_key.wall[t];
+    }
+    // for every suit the min-plus merge of the other three suits' rows (shanten.rs:51-80 is an exact min-plus convolution,
+    // so it may be associated freely): a candidate then costs ONE table gather and one partial merge instead of four and three
+    SP_PFOR(it, nb * 4) {
+        const int st = it >> 2, sx = it & 3;
+        const HandSig h = sp_sig_unpack(S.sig[st]);
+        Row10 acc;
+        bool first = true;
+        for (int q = 0; q < 4; q++) {
+            if (q == sx) continue;
+            const Row10 r = unpack_row(q < 3 ? ld_row(T.suhai, h.idx[q], SUHAI_ROWS) : ld_row(T.jihai, h.idx[q], JIHAI_ROWS));
+            if (first) { acc = r; first = false; } else add_suhai_full(acc, r);
+        }
+        for (int q = 0; q < 10; q++) S.oth[st][sx][q] = (u8)acc.v[q];
+    }
+    SP_SYNC();
+    // candidate tiles: still in the wall (W) / held (D)
+    SP_PFOR(st, nb) {
         const u64 key = S.key[st];
-        const SpRow& R = G.rows[sp_key_row(key)];
-        const int nd = sp_tuple_count(sp_key_dr(key), 3, t), nx = sp_tuple_count(sp_key_di(key), 4, t);
-        const int th = (int)R.root_key.tehai[t] + nd - nx, wl = (int)R.root_key.wall[t] - nd;
-        S.teh[st][t] = (u8)th; S.wall[st][t] = (u8)wl;
-        if ((IS_W ? wl : th) > 0) sp_atomic_or(&S.cand[st][t >> 5], 1u << (t & 31));
+        const u32 dr = sp_key_dr(key), di = sp_key_di(key);
+        for (int i = 0; i < 3; i++) { const int f = (int)((dr >> (6 * i)) & 63u); if (f != 63) { S.teh[st][deaka(f)] += 1; S.wall[st][deaka(f)] -= 1; } }
+        for (int i = 0; i < 4; i++) { const int f = (int)((di >> (6 * i)) & 63u); if (f != 63) S.teh[st][deaka(f)] -= 1; }
+        u64 m = 0;
+        for (int t = 0; t < 34; t++) if ((IS_W ? S.wall[st][t] : S.teh[st][t]) > 0) m |= 1ull << t;
+        S.cand[st][0] = (u32)m; S.cand[st][1] = (u32)(m >> 32);
     }
     SP_SYNC();
     if (B.tid == 0) {
@@ -293,24 +316,30 @@ MJX_DN void sp_expand_batch(const SpGlobal& G, const Tables& T, SpExpandBatch& S
         const int st = S.cand_list[i] >> 6, t = S.cand_list[i] & 63;
         const HandSig base = sp_sig_unpack(S.sig[st]);
         const int len = S.len[st], c0 = S.teh[st][t];
-        bool ok;
-        if (IS_W) ok = shanten_all_sig(T, sig_variant(base, t, +1, c0), len) - k == -1;
-        else ok = shanten_all_sig(T, sig_variant(base, t, -1, c0), len) == k;
+        const int sh = shanten_all_others(T, sig_variant(base, t, IS_W ? +1 : -1, c0), t / 9, S.oth[st][t / 9], len);
+        const bool ok = IS_W ? sh - k == -1 : sh == k;
         if (ok) sp_atomic_or(&S.eff[st][t >> 5], 1u << (t & 31));
     }
     SP_SYNC();
     // an effective 5 whose aka is still in the wall splits in two edges (sp/state.rs:160-176)
     SP_PFOR(st, nb) {
         const u64 eff = sp_mask64(S.eff[st]);
-        int split = 0, sum = 0;
+        int split = 0, sum = 0, cmask = 0;  // cmask: which edge counts 1..4 occur (the evaluation caches one probability row each)
         if (IS_W) {
             for (int s5 = 0; s5 < 3; s5++) {
                 const int t5 = 4 + 9 * s5;
                 if (((eff >> t5) & 1) && ((S.akas[st] >> (3 + s5)) & 1) && S.wall[st][t5] >= 2) split |= 1 << s5;
             }
-            for (u64 rest = eff; rest; rest &= rest - 1) sum += S.wall[st][mjx_ffsll(rest) - 1];
+            for (u64 rest = eff; rest; rest &= rest - 1) {
+                const int t = mjx_ffsll(rest) - 1, cnt = S.wall[st][t];
+                sum += cnt;
+                const int s5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
+                if (s5 >= 0 && ((S.akas[st] >> (3 + s5)) & 1)) { cmask |= 1; if (cnt >= 2) cmask |= 1 << (cnt - 2); }
+                else cmask |= 1 << (cnt - 1);
+            }
         }
         S.split[st] = (u8)split;
+        S.cmask[st] = (u8)cmask;
         S.ne[st] = (u8)(mjx_popcll(eff) + mjx_popc((u32)split));
         S.sumreq[st] = (u8)sum;  // u8 arithmetic, as the reference's `.sum::<u8>()`
     }
@@ -326,7 +355,7 @@ MJX_DN void sp_expand_batch(const SpGlobal& G, const Tables& T, SpExpandBatch& S
     SP_SYNC();
     SP_PFOR(st, nb) {
         const int ne = S.n_edge ? S.ne[st] : 0;
-        G.einfo[S.slot[st]] = (u64)(u32)(S.e_base + S.e_off[st]) | ((u64)ne << 32) | ((u64)S.sumreq[st] << 40);
+        G.einfo[S.slot[st]] = (u64)(u32)(S.e_base + S.e_off[st]) | ((u64)ne << 32) | ((u64)S.sumreq[st] << 40) | ((u64)S.cmask[st] << 48);
     }
     // edge descriptors in tile order: every effective tile writes its own at the offset its rank gives
     if (S.n_edge) SP_PFOR(it, nb * 34) {
@@ -481,26 +510,157 @@ MJX_DN void sp_score_edge(const SpGlobal& G, const Tables& T, int e) {
 }
 
 // ---------------------------------------------------------------------------------------------- evaluation
-struct SpEvalBatch {
+// pair index of (turn i, draw turn j), i <= j < 17, ordered by j then i: the pairs with j < T are a prefix for every T
+MJX_HD int sp_tri(int i, int j) { return j * (j + 1) / 2 + i; }
+constexpr int SP_TRI = SP_T_MAX * (SP_T_MAX + 1) / 2;  // 153
+constexpr int SP_EB = 14;                              // W states per evaluation batch (shared-memory bound)
+
+struct SpEvalDBatch {
     u32 slot[SP_B], ebeg[SP_B];
-    u8 ne[SP_B], T[SP_B], nleft[SP_B], sumreq[SP_B], flags[SP_B];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei
+    u8 ne[SP_B], T[SP_B];
     u16 off[SP_B + 1];
-    float nts[SP_B][SP_T_MAX];      // not_tsumo_prob row of the state (calc.rs:148-167)
-    float tp[SP_B][4][SP_T_MAX];    // tsumo_prob[c-1][j] * not_tsumo[j] for c = 1..4
     i32 n_items;
 };
+// W levels: the probability of drawing an effective tile of count c at turn j given turn i (calc.rs:486-497
+// `tsumo_probs[j] * n / m`) depends on (c, i, j) only, not on the edge: it is computed ONCE per state and count that occurs
+// (one IEEE division per (c, i, j), dense over the batch) and the per-edge accumulation reads it from shared memory.
+struct SpEvalWBatch {
+    u32 slot[SP_EB], ebeg[SP_EB];
+    u8 ne[SP_EB], T[SP_EB], nleft[SP_EB], sumreq[SP_EB], flags[SP_EB], cmask[SP_EB];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei
+    u16 poff[SP_EB + 1], aoff[SP_EB + 1];
+    float nts[SP_EB][SP_T_MAX];        // not_tsumo_prob row of the state (calc.rs:148-167)
+    float tp[SP_EB][4][SP_T_MAX];      // tsumo_prob[c-1][j] * not_tsumo[j]
+    float P[SP_EB][4][SP_TRI];         // tp[c][j] / nts[i] at sp_tri(i, j)
+    i32 n_p, n_a;
+};
+template <typename Tb>
+MJX_D int sp_find_state(const u16* off, int nb, int item) {
+    int lo = 0, hi = nb - 1;  // last state whose offset is <= item
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)off[mid] <= item) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
 
-// common prologue: stage the batch, lay the (state, turn) items out densely
-MJX_DN void sp_eval_stage(const SpGlobal& G, SpEvalBatch& S, const SpBlk& B, int level, int first, int nb, bool want_probs) {
+// calc.rs:447-561 draw_without_tegawari_slow. LEAF: the tenpai level (scores of the winning draws); otherwise shanten k >= 1.
+template <bool LEAF>
+MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, int level, int first, int nb) {
+    const int k = LEAF ? 0 : sp_slot_shanten(level);
     const u32* list = G.wl + (size_t)level * G.wl_cap;
     SP_PFOR(st, nb) {
         const u32 slot = list[first + st];
         const SpRow& R = G.rows[sp_key_row(G.hkey[slot])];
         const u64 ei = G.einfo[slot];
         S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei); S.sumreq[st] = (u8)sp_einfo_sum(ei);
-        S.T[st] = R.T; S.nleft[st] = R.n_left;
+        S.cmask[st] = (u8)sp_einfo_cmask(ei);
+        const int Tn = R.T, n_left = R.n_left, i0 = sp_einfo_sum(ei);
+        S.T[st] = (u8)Tn; S.nleft[st] = (u8)n_left;
         const bool ar = R.is_menzen && R.prefer_riichi;
         S.flags[st] = (u8)((ar ? 1 : 0) | (R.calc_double_riichi ? 2 : 0) | (R.calc_haitei ? 4 : 0));
+        // not_tsumo_prob_table[sum_required][j] by the table's own recurrence (calc.rs:158-165), zero past its end
+        float v = 1.f;
+        const bool row_ok = i0 <= n_left && i0 <= SP_MAX_TILES_LEFT;
+        const int lim = row_ok ? min(Tn - 1, n_left - i0) : -1;
+        for (int j = 0; j < SP_T_MAX; j++) {
+            S.nts[st][j] = j <= lim ? v : 0.f;
+            if (j < lim) v = SP_FDIV(SP_FMUL(v, (float)(n_left - i0 - j)), (float)(n_left - j));
+        }
+    }
+    SP_SYNC();
+    if (B.tid == 0) {
+        int pa = 0, aa = 0;
+        for (int st = 0; st < nb; st++) {
+            const int Tn = S.T[st];
+            S.poff[st] = (u16)pa; S.aoff[st] = (u16)aa;
+            pa += mjx_popc((u32)S.cmask[st]) * (Tn * (Tn + 1) / 2);
+            aa += (Tn + 1) / 2;
+        }
+        S.poff[nb] = (u16)pa; S.aoff[nb] = (u16)aa; S.n_p = pa; S.n_a = aa;
+    }
+    SP_PFOR(it, nb * 4 * SP_T_MAX) {
+        const int st = it / (4 * SP_T_MAX), r = it - st * 4 * SP_T_MAX, c = r / SP_T_MAX, j = r - c * SP_T_MAX;
+        float v = 0.f;
+        if (j < S.T[st] && ((S.cmask[st] >> c) & 1)) v = SP_FMUL(SP_FDIV((float)(c + 1), (float)((int)S.nleft[st] - j)), S.nts[st][j]);
+        S.tp[st][c][j] = v;
+    }
+    SP_SYNC();
+    // one division per (state, count that occurs, i <= j < T), dense over the batch
+    SP_PFOR(item, S.n_p) {
+        const int st = sp_find_state<int>(S.poff, nb, item);
+        const int Tn = S.T[st], tri = Tn * (Tn + 1) / 2;
+        const int local = item - S.poff[st], ci = local / tri, kk = local - ci * tri;
+        int c = 0;
+        for (int seen = 0, q = 0; q < 4; q++) if ((S.cmask[st] >> q) & 1) { if (seen == ci) c = q; seen++; }
+        int j = 0;
+        while ((j + 1) * (j + 2) / 2 <= kk) j++;
+        const int i = kk - j * (j + 1) / 2;
+        const float m = S.nts[st][i];
+        S.P[st][c][kk] = m != 0.f ? SP_FDIV(S.tp[st][c][j], m) : 0.f;
+    }
+    SP_SYNC();
+    // accumulation: a thread takes turns p and T-1-p of a state (T+1 draw turns together: balanced), edges in the reference's
+    // order, j ascending, every add and multiply rounded as the reference rounds it
+    SP_PFOR(item, S.n_a) {
+        const int st = sp_find_state<int>(S.aoff, nb, item), p = item - S.aoff[st];
+        const int Tn = S.T[st], ne = S.ne[st];
+        const u32 eb = S.ebeg[st];
+        const float* nts = S.nts[st];
+        const bool assume_riichi = (S.flags[st] & 1) != 0, dbl = (S.flags[st] & 2) != 0, haitei = (S.flags[st] & 4) != 0;
+        float* o = G.vals + (size_t)S.slot[st] * SP_VALS;
+        for (int half = 0; half < 2; half++) {
+            const int i = half == 0 ? p : Tn - 1 - p;
+            if (half == 1 && i <= p) break;
+            float tenpai = 0.f, win = 0.f, ev = 0.f;
+            if (nts[i] != 0.f) {
+                int jend = i;  // the reference stops at the first j with not_tsumo_probs[j] == 0 (monotone)
+                while (jend < Tn && nts[jend] != 0.f) jend++;
+                for (int e = 0; e < ne; e++) {
+                    const u16 meta = G.emeta[eb + e];
+                    const float* Pc = S.P[st][((meta >> 6) & 7) - 1];
+                    if (LEAF) {
+                        if (meta & 0x8000) continue;  // no yaku
+                        const int le = (int)(eb + e) - G.counters[4];
+                        if (le < 0 || le >= G.score_cap) continue;
+                        const float* sc = G.leaf_scores + (size_t)le * 4;
+                        const float s0 = sc[0], s1 = sc[1], s2 = sc[2], s3 = sc[3];
+                        for (int j = i; j < jend; j++) {
+                            const float prob = Pc[sp_tri(i, j)];
+                            const int han_plus = (assume_riichi && dbl && i == 0) + (assume_riichi && j == i) + (haitei && j == Tn - 1);
+                            const float sv = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : (han_plus == 2 ? s2 : s3));
+                            win = SP_FADD(win, prob);
+                            ev = SP_FADD(ev, SP_FMUL(prob, sv));
+                        }
+                    } else {
+                        const u32 child = G.echild[eb + e];
+                        if (child == SP_NO_CHILD) continue;  // only after an overflow
+                        const float* cv = G.vals + (size_t)child * SP_VALS;
+                        for (int j = i; j < jend; j++) {
+                            const float prob = Pc[sp_tri(i, j)];
+                            if (k == 1) tenpai = SP_FADD(tenpai, prob);
+                            if (j < Tn - 1) {
+                                if (k > 1) tenpai = SP_FADD(tenpai, SP_FMUL(prob, cv[j + 1]));
+                                win = SP_FADD(win, SP_FMUL(prob, cv[SP_T_MAX + j + 1]));
+                                ev = SP_FADD(ev, SP_FMUL(prob, cv[2 * SP_T_MAX + j + 1]));
+                            }
+                        }
+                    }
+                }
+            }
+            o[i] = tenpai; o[SP_T_MAX + i] = win; o[2 * SP_T_MAX + i] = ev;
+        }
+    }
+    SP_SYNC();
+}
+
+// calc.rs:563-637 discard_slow: per turn the child with the largest (truncated) EV, ties by discard priority
+MJX_DN void sp_eval_d_batch(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, int level, int first, int nb) {
+    const u32* list = G.wl + (size_t)level * G.wl_cap;
+    SP_PFOR(st, nb) {
+        const u32 slot = list[first + st];
+        const u64 ei = G.einfo[slot];
+        S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei);
+        S.T[st] = G.rows[sp_key_row(G.hkey[slot])].T;
     }
     SP_SYNC();
     if (B.tid == 0) {
@@ -508,100 +668,9 @@ MJX_DN void sp_eval_stage(const SpGlobal& G, SpEvalBatch& S, const SpBlk& B, int
         for (int st = 0; st < nb; st++) { S.off[st] = (u16)acc; acc += S.T[st]; }
         S.off[nb] = (u16)acc; S.n_items = acc;
     }
-    if (want_probs) {
-        // not_tsumo_prob_table[sum_required][j], recomputed with the table's own recurrence (calc.rs:158-165)
-        SP_PFOR(it, nb * SP_T_MAX) {
-            const int st = it / SP_T_MAX, j = it - st * SP_T_MAX;
-            const int Tn = S.T[st], n_left = S.nleft[st], i0 = S.sumreq[st];
-            float v = 0.f;
-            if (j < Tn && i0 <= n_left && i0 <= SP_MAX_TILES_LEFT) {
-                const int lim = min(Tn - 1, n_left - i0);
-                if (j <= lim) {
-                    v = 1.f;
-                    for (int q = 0; q < j; q++) v = SP_FDIV(SP_FMUL(v, (float)(n_left - i0 - q)), (float)(n_left - q));
-                }
-            }
-            S.nts[st][j] = v;
-        }
-        SP_SYNC();
-        SP_PFOR(it, nb * 4 * SP_T_MAX) {
-            const int st = it / (4 * SP_T_MAX), r = it - st * 4 * SP_T_MAX, c = r / SP_T_MAX, j = r - c * SP_T_MAX;
-            float v = 0.f;
-            if (j < S.T[st]) v = SP_FMUL(SP_FDIV((float)(c + 1), (float)((int)S.nleft[st] - j)), S.nts[st][j]);
-            S.tp[st][c][j] = v;
-        }
-    }
     SP_SYNC();
-}
-MJX_D int sp_eval_find(const SpEvalBatch& S, int nb, int item) {
-    int lo = 0, hi = nb - 1;  // last state whose offset is <= item
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if ((int)S.off[mid] <= item) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
-// calc.rs:447-561 draw_without_tegawari_slow. LEAF: the tenpai level (scores of the winning draws); otherwise shanten k >= 1.
-template <bool LEAF>
-MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalBatch& S, const SpBlk& B, int level, int first, int nb) {
-    const int k = LEAF ? 0 : sp_slot_shanten(level);
-    sp_eval_stage(G, S, B, level, first, nb, true);
     SP_PFOR(item, S.n_items) {
-        const int st = sp_eval_find(S, nb, item), i = item - S.off[st];
-        const int Tn = S.T[st], ne = S.ne[st];
-        const u32 eb = S.ebeg[st];
-        const float* nts = S.nts[st];
-        float tenpai = 0.f, win = 0.f, ev = 0.f;
-        const float m = nts[i];
-        if (m != 0.f) {
-            const bool assume_riichi = (S.flags[st] & 1) != 0, dbl = (S.flags[st] & 2) != 0, haitei = (S.flags[st] & 4) != 0;
-            for (int e = 0; e < ne; e++) {
-                const u16 meta = G.emeta[eb + e];
-                const int cnt = (meta >> 6) & 7;
-                const float* tp = S.tp[st][cnt - 1];
-                if (LEAF) {
-                    if (meta & 0x8000) continue;  // no yaku
-                    const int le = (int)(eb + e) - G.counters[4];
-                    if (le < 0 || le >= G.score_cap) continue;
-                    const float* sc = G.leaf_scores + (size_t)le * 4;
-                    const float s0 = sc[0], s1 = sc[1], s2 = sc[2], s3 = sc[3];
-                    for (int j = i; j < Tn; j++) {
-                        if (nts[j] == 0.f) break;
-                        const float prob = SP_FDIV(tp[j], m);
-                        const int han_plus = (assume_riichi && dbl && i == 0) + (assume_riichi && j == i) + (haitei && j == Tn - 1);
-                        const float s = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : (han_plus == 2 ? s2 : s3));
-                        win = SP_FADD(win, prob);
-                        ev = SP_FADD(ev, SP_FMUL(prob, s));
-                    }
-                } else {
-                    const u32 child = G.echild[eb + e];
-                    if (child == SP_NO_CHILD) continue;  // only after an overflow
-                    const float* cv = G.vals + (size_t)child * SP_VALS;
-                    for (int j = i; j < Tn; j++) {
-                        if (nts[j] == 0.f) break;
-                        const float prob = SP_FDIV(tp[j], m);
-                        if (k == 1) tenpai = SP_FADD(tenpai, prob);
-                        if (j < Tn - 1) {
-                            if (k > 1) tenpai = SP_FADD(tenpai, SP_FMUL(prob, cv[j + 1]));
-                            win = SP_FADD(win, SP_FMUL(prob, cv[SP_T_MAX + j + 1]));
-                            ev = SP_FADD(ev, SP_FMUL(prob, cv[2 * SP_T_MAX + j + 1]));
-                        }
-                    }
-                }
-            }
-        }
-        float* o = G.vals + (size_t)S.slot[st] * SP_VALS;
-        o[i] = tenpai; o[SP_T_MAX + i] = win; o[2 * SP_T_MAX + i] = ev;
-    }
-    SP_SYNC();
-}
-
-// calc.rs:563-637 discard_slow: per turn the child with the largest (truncated) EV, ties by discard priority
-MJX_DN void sp_eval_d_batch(const SpGlobal& G, SpEvalBatch& S, const SpBlk& B, int level, int first, int nb) {
-    sp_eval_stage(G, S, B, level, first, nb, false);
-    SP_PFOR(item, S.n_items) {
-        const int st = sp_eval_find(S, nb, item), i = item - S.off[st];
+        const int st = sp_find_state<int>(S.off, nb, item), i = item - S.off[st];
         const int ne = S.ne[st];
         const u32 eb = S.ebeg[st];
         const float FMIN = -3.40282347e+38f;
@@ -626,16 +695,14 @@ MJX_DN void sp_eval_d_batch(const SpGlobal& G, SpEvalBatch& S, const SpBlk& B, i
     SP_SYNC();
 }
 
-// KIND 0: D level, 1: W level above tenpai, 2: the tenpai W level
-template <int KIND>
-MJX_DN void sp_eval_level(const SpGlobal& G, SpEvalBatch& S, const SpBlk& B, int level) {
+MJX_DN void sp_eval_d_level(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, int level) {
     const int n = min(G.wl_count[level], G.wl_cap);
-    for (int first = B.bid * SP_B; first < n; first += B.nblk * SP_B) {
-        const int nb = min(SP_B, n - first);
-        if (KIND == 0) sp_eval_d_batch(G, S, B, level, first, nb);
-        else if (KIND == 1) sp_eval_w_batch<false>(G, S, B, level, first, nb);
-        else sp_eval_w_batch<true>(G, S, B, level, first, nb);
-    }
+    for (int first = B.bid * SP_B; first < n; first += B.nblk * SP_B) sp_eval_d_batch(G, S, B, level, first, min(SP_B, n - first));
+}
+template <bool LEAF>
+MJX_DN void sp_eval_w_level(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, int level) {
+    const int n = min(G.wl_count[level], G.wl_cap);
+    for (int first = B.bid * SP_EB; first < n; first += B.nblk * SP_EB) sp_eval_w_batch<LEAF>(G, S, B, level, first, min(SP_EB, n - first));
 }
 
 // release the table slots this DP used (instead of a full-table memset per step); after an overflow states may exist that

@@ -193,10 +193,10 @@ class _Arena:
                 env.step(actions)
             first, skip_step = False, True
         while True:
-            if self.max_cycles and cycles >= self.max_cycles:
-                break
             if self.cycle_hook is not None:
                 self.cycle_hook(cycles, env)
+            if self.max_cycles and cycles >= self.max_cycles:
+                break
             if not skip_step:
                 env.step(None if first else actions, None if first else q_all)
             first = skip_step = False

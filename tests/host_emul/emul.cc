@@ -300,7 +300,7 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
     u8 df[40];
     SpCtx s; s.G = G; s.T = g_T; s.df = df; s.lane = 0;
     SpBlk B; B.tid = 0; B.nthr = 1; B.bid = 0; B.nblk = 1;
-    static SpExpandBatch xb; static SpEvalBatch eb;
+    static SpExpandBatch xb; static SpEvalDBatch ed; static SpEvalWBatch ew;
     for (int r = 0; r < n_rows; r++) sp_stage_init(s, &E->tabs[E->row_table[r]], r, E->row_table[r], E->row_seat[r] & 3);
     for (int level = 0; level < SP_SLOTS; level++) {
         if (level == SP_SLOTS - 1) { counters[4] = counters[1]; sp_expand_level<2>(G, g_T, xb, B, level); }
@@ -310,9 +310,9 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
     counters[5] = counters[1];
     for (int e = counters[4]; e < counters[5]; e++) sp_score_edge(G, g_T, e);
     for (int level = SP_SLOTS - 1; level >= 0; level--) {
-        if (!sp_slot_is_w(level)) sp_eval_level<0>(G, eb, B, level);
-        else if (level == SP_SLOTS - 1) sp_eval_level<2>(G, eb, B, level);
-        else sp_eval_level<1>(G, eb, B, level);
+        if (!sp_slot_is_w(level)) sp_eval_d_level(G, ed, B, level);
+        else if (level == SP_SLOTS - 1) sp_eval_w_level<true>(G, ew, B, level);
+        else sp_eval_w_level<false>(G, ew, B, level);
     }
     for (int r = 0; r < n_rows; r++) sp_stage_finalize(s, r, obs + (size_t)r * OBS_ROWS_V4 * OBS_COLS);
     if (counters[2]) g_emul_sp_overflows++;
