@@ -306,6 +306,14 @@ __global__ void __launch_bounds__(SP_THREADS) k_sp_eval(SpGlobal G, int level) {
     }
 }
 
+// the two probability tables of the W evaluation (csrc/mjx_sp.cuh), built once per process with the reference's recurrences
+__global__ void k_sp_tables(float* nts_tab, float* div_tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < SP_NTS_DIM * SP_NTS_DIM) sp_fill_nts_row(nts_tab + (size_t)i * SP_T_MAX, i / SP_NTS_DIM, i % SP_NTS_DIM);
+    if (i < 4) sp_fill_div_row(div_tab + (size_t)i * SP_DIV_DIM, i);
+}
+
+
 __global__ void k_sp_mark(SpGlobal G, int which) { G.counters[4 + which] = min(G.counters[1], G.edge_cap); }
 
 __global__ void __launch_bounds__(128) k_sp_score(SpGlobal G, Tables T) {
@@ -415,6 +423,7 @@ bool g_ready = false;
 int g_device = -1;
 int g_sm_count = 148;
 Tables g_T;
+const float *g_sp_nts_tab = nullptr, *g_sp_div_tab = nullptr;  // csrc/mjx_sp.cuh probability tables (device)
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CU(call)                                                                          \
@@ -500,6 +509,15 @@ int mjx_init(const char* data_dir, int device) {
         CU(cudaMemcpyToSymbol(c_sv_row, tab, sizeof tab));
     }
     CU(cudaFuncSetAttribute(k_encode_store, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENCS_SMEM_BYTES));
+    {
+        float *nts = nullptr, *dv = nullptr;
+        CU(cudaMalloc(&nts, sizeof(float) * SP_NTS_DIM * SP_NTS_DIM * SP_T_MAX));
+        CU(cudaMalloc(&dv, sizeof(float) * 4 * SP_DIV_DIM));
+        k_sp_tables<<<(SP_NTS_DIM * SP_NTS_DIM + 127) / 128, 128>>>(nts, dv);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+        g_sp_nts_tab = nts; g_sp_div_tab = dv;
+    }
     g_device = device;
     g_ready = true;
     return MJX_OK;
@@ -568,7 +586,8 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
         int hc = 1 << 20;
         while (hc < want && hc < (1 << 26)) hc <<= 1;
         G.hash_cap = hc;
-        G.wl_cap = hc / 4;       // per level
+        G.nts_tab = g_sp_nts_tab; G.div_tab = g_sp_div_tab;
+        G.wl_cap = hc / 2;       // per level
         G.edge_cap = hc * 2;
         G.score_cap = hc;
         CU(cudaMalloc(&G.rows, cap * sizeof(SpRow)));

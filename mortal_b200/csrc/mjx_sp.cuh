@@ -152,6 +152,8 @@ struct SpGlobal {
     float* leaf_scores; // [score_cap][4] get_score of every winning draw of the tenpai (W0) states
     u32* wl;            // [SP_SLOTS][wl_cap] work list of each level: table slots
     i32* wl_count;      // [SP_SLOTS]
+    const float* nts_tab;  // [SP_NTS_DIM][SP_NTS_DIM][SP_T_MAX] not_tsumo_prob rows by (tiles left, sum of required counts)
+    const float* div_tab;  // [4][SP_DIV_DIM] (c + 1) / d
     i32* counters;      // [1] edges, [2] overflow flag, [3] overflow events (cumulative), [4],[5] edge range of the tenpai level
     i32 row_base;       // rows [row_base, ...) of the step form this DP (row groups of mjx_env_encode_obs_host)
     i32 hash_cap, wl_cap, edge_cap, score_cap;
@@ -513,7 +515,6 @@ MJX_DN void sp_score_edge(const SpGlobal& G, const Tables& T, int e) {
 // pair index of (turn i, draw turn j), i <= j < 17, ordered by j then i: the pairs with j < T are a prefix for every T
 MJX_HD int sp_tri(int i, int j) { return j * (j + 1) / 2 + i; }
 constexpr int SP_TRI = SP_T_MAX * (SP_T_MAX + 1) / 2;  // 153
-constexpr int SP_EB = 14;                              // W states per evaluation batch (shared-memory bound)
 
 struct SpEvalDBatch {
     u32 slot[SP_B], ebeg[SP_B];
@@ -521,17 +522,32 @@ struct SpEvalDBatch {
     u16 off[SP_B + 1];
     i32 n_items;
 };
-// W levels: the probability of drawing an effective tile of count c at turn j given turn i (calc.rs:486-497
-// `tsumo_probs[j] * n / m`) depends on (c, i, j) only, not on the edge: it is computed ONCE per state and count that occurs
-// (one IEEE division per (c, i, j), dense over the batch) and the per-edge accumulation reads it from shared memory.
+// W levels. not_tsumo_prob_table rows (calc.rs:148-167) depend on (tiles left at the root, sum of required counts) only and
+// tsumo_prob_table entries (calc.rs:136-146) on (count, tiles left - turn): both come from two small global tables built once
+// per process with the reference's own recurrences (k_sp_tables), so a state's probability vectors cost loads, not divisions.
+constexpr int SP_NTS_DIM = SP_MAX_TILES_LEFT + 2;  // n_left, sum_required in 0..123
+constexpr int SP_DIV_DIM = 140;
+MJX_D size_t sp_nts_index(int n_left, int i0) { return ((size_t)n_left * SP_NTS_DIM + (size_t)i0) * SP_T_MAX; }
+// one (n_left, i0) row of the table: row[0] = 1, row[j+1] = row[j] * (n_left - i0 - j) / (n_left - j)   (calc.rs:158-165)
+MJX_D void sp_fill_nts_row(float* row, int n_left, int i0) {
+    float v = 1.f;
+    for (int j = 0; j < SP_T_MAX; j++) {
+        const bool ok = i0 <= n_left && j <= n_left - i0;
+        row[j] = ok ? v : 0.f;
+        if (ok && j < n_left - i0) v = SP_FDIV(SP_FMUL(v, (float)(n_left - i0 - j)), (float)(n_left - j));
+    }
+}
+MJX_D void sp_fill_div_row(float* row, int c) {  // (c + 1) / d
+    for (int d = 0; d < SP_DIV_DIM; d++) row[d] = d > 0 ? SP_FDIV((float)(c + 1), (float)d) : 0.f;
+}
+
 struct SpEvalWBatch {
-    u32 slot[SP_EB], ebeg[SP_EB];
-    u8 ne[SP_EB], T[SP_EB], nleft[SP_EB], sumreq[SP_EB], flags[SP_EB], cmask[SP_EB];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei
-    u16 poff[SP_EB + 1], aoff[SP_EB + 1];
-    float nts[SP_EB][SP_T_MAX];        // not_tsumo_prob row of the state (calc.rs:148-167)
-    float tp[SP_EB][4][SP_T_MAX];      // tsumo_prob[c-1][j] * not_tsumo[j]
-    float P[SP_EB][4][SP_TRI];         // tp[c][j] / nts[i] at sp_tri(i, j)
-    i32 n_p, n_a;
+    u32 slot[SP_B], ebeg[SP_B];
+    u8 ne[SP_B], T[SP_B], flags[SP_B], jend[SP_B];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei; jend: first j with nts[j] == 0
+    u16 aoff[SP_B + 1];
+    float nts[SP_B][SP_T_MAX];        // not_tsumo_prob row of the state, truncated at T
+    float tp[SP_B][4][SP_T_MAX];      // tsumo_prob[c-1][j] * not_tsumo[j]
+    i32 n_a;
 };
 template <typename Tb>
 MJX_D int sp_find_state(const u16* off, int nb, int item) {
@@ -548,107 +564,100 @@ template <bool LEAF>
 MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, int level, int first, int nb) {
     const int k = LEAF ? 0 : sp_slot_shanten(level);
     const u32* list = G.wl + (size_t)level * G.wl_cap;
-    SP_PFOR(st, nb) {
+    // (state, j): stage the probability vectors; lane j == 0 also stages the state's scalars
+    SP_PFOR(it, nb * SP_T_MAX) {
+        const int st = it / SP_T_MAX, j = it - st * SP_T_MAX;
         const u32 slot = list[first + st];
         const SpRow& R = G.rows[sp_key_row(G.hkey[slot])];
         const u64 ei = G.einfo[slot];
-        S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei); S.sumreq[st] = (u8)sp_einfo_sum(ei);
-        S.cmask[st] = (u8)sp_einfo_cmask(ei);
         const int Tn = R.T, n_left = R.n_left, i0 = sp_einfo_sum(ei);
-        S.T[st] = (u8)Tn; S.nleft[st] = (u8)n_left;
-        const bool ar = R.is_menzen && R.prefer_riichi;
-        S.flags[st] = (u8)((ar ? 1 : 0) | (R.calc_double_riichi ? 2 : 0) | (R.calc_haitei ? 4 : 0));
-        // not_tsumo_prob_table[sum_required][j] by the table's own recurrence (calc.rs:158-165), zero past its end
-        float v = 1.f;
         const bool row_ok = i0 <= n_left && i0 <= SP_MAX_TILES_LEFT;
         const int lim = row_ok ? min(Tn - 1, n_left - i0) : -1;
-        for (int j = 0; j < SP_T_MAX; j++) {
-            S.nts[st][j] = j <= lim ? v : 0.f;
-            if (j < lim) v = SP_FDIV(SP_FMUL(v, (float)(n_left - i0 - j)), (float)(n_left - j));
+        const float v = j <= lim ? G.nts_tab[sp_nts_index(n_left, i0) + j] : 0.f;
+        S.nts[st][j] = v;
+        const int d = n_left - j;
+        for (int c = 0; c < 4; c++) S.tp[st][c][j] = (j < Tn && d > 0) ? SP_FMUL(G.div_tab[c * SP_DIV_DIM + d], v) : 0.f;
+        if (j == 0) {
+            S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei);
+            S.T[st] = (u8)Tn;
+            const bool ar = R.is_menzen && R.prefer_riichi;
+            S.flags[st] = (u8)((ar ? 1 : 0) | (R.calc_double_riichi ? 2 : 0) | (R.calc_haitei ? 4 : 0));
+            S.jend[st] = (u8)max(0, min(Tn, lim + 1));
         }
     }
     SP_SYNC();
     if (B.tid == 0) {
-        int pa = 0, aa = 0;
-        for (int st = 0; st < nb; st++) {
-            const int Tn = S.T[st];
-            S.poff[st] = (u16)pa; S.aoff[st] = (u16)aa;
-            pa += mjx_popc((u32)S.cmask[st]) * (Tn * (Tn + 1) / 2);
-            aa += (Tn + 1) / 2;
-        }
-        S.poff[nb] = (u16)pa; S.aoff[nb] = (u16)aa; S.n_p = pa; S.n_a = aa;
-    }
-    SP_PFOR(it, nb * 4 * SP_T_MAX) {
-        const int st = it / (4 * SP_T_MAX), r = it - st * 4 * SP_T_MAX, c = r / SP_T_MAX, j = r - c * SP_T_MAX;
-        float v = 0.f;
-        if (j < S.T[st] && ((S.cmask[st] >> c) & 1)) v = SP_FMUL(SP_FDIV((float)(c + 1), (float)((int)S.nleft[st] - j)), S.nts[st][j]);
-        S.tp[st][c][j] = v;
-    }
-    SP_SYNC();
-    // one division per (state, count that occurs, i <= j < T), dense over the batch
-    SP_PFOR(item, S.n_p) {
-        const int st = sp_find_state<int>(S.poff, nb, item);
-        const int Tn = S.T[st], tri = Tn * (Tn + 1) / 2;
-        const int local = item - S.poff[st], ci = local / tri, kk = local - ci * tri;
-        int c = 0;
-        for (int seen = 0, q = 0; q < 4; q++) if ((S.cmask[st] >> q) & 1) { if (seen == ci) c = q; seen++; }
-        int j = 0;
-        while ((j + 1) * (j + 2) / 2 <= kk) j++;
-        const int i = kk - j * (j + 1) / 2;
-        const float m = S.nts[st][i];
-        S.P[st][c][kk] = m != 0.f ? SP_FDIV(S.tp[st][c][j], m) : 0.f;
+        int aa = 0;
+        for (int st = 0; st < nb; st++) { S.aoff[st] = (u16)aa; aa += (S.T[st] + 1) / 2; }
+        S.aoff[nb] = (u16)aa; S.n_a = aa;
     }
     SP_SYNC();
     // accumulation: a thread takes turns p and T-1-p of a state (T+1 draw turns together: balanced), edges in the reference's
-    // order, j ascending, every add and multiply rounded as the reference rounds it
+    // order, j ascending, every divide, multiply and add rounded as the reference rounds it
     SP_PFOR(item, S.n_a) {
         const int st = sp_find_state<int>(S.aoff, nb, item), p = item - S.aoff[st];
-        const int Tn = S.T[st], ne = S.ne[st];
+        const int Tn = S.T[st], ne = S.ne[st], jend = S.jend[st];
         const u32 eb = S.ebeg[st];
         const float* nts = S.nts[st];
         const bool assume_riichi = (S.flags[st] & 1) != 0, dbl = (S.flags[st] & 2) != 0, haitei = (S.flags[st] & 4) != 0;
-        float* o = G.vals + (size_t)S.slot[st] * SP_VALS;
-        for (int half = 0; half < 2; half++) {
-            const int i = half == 0 ? p : Tn - 1 - p;
-            if (half == 1 && i <= p) break;
-            float tenpai = 0.f, win = 0.f, ev = 0.f;
-            if (nts[i] != 0.f) {
-                int jend = i;  // the reference stops at the first j with not_tsumo_probs[j] == 0 (monotone)
-                while (jend < Tn && nts[jend] != 0.f) jend++;
-                for (int e = 0; e < ne; e++) {
-                    const u16 meta = G.emeta[eb + e];
-                    const float* Pc = S.P[st][((meta >> 6) & 7) - 1];
-                    if (LEAF) {
-                        if (meta & 0x8000) continue;  // no yaku
-                        const int le = (int)(eb + e) - G.counters[4];
-                        if (le < 0 || le >= G.score_cap) continue;
-                        const float* sc = G.leaf_scores + (size_t)le * 4;
-                        const float s0 = sc[0], s1 = sc[1], s2 = sc[2], s3 = sc[3];
-                        for (int j = i; j < jend; j++) {
-                            const float prob = Pc[sp_tri(i, j)];
-                            const int han_plus = (assume_riichi && dbl && i == 0) + (assume_riichi && j == i) + (haitei && j == Tn - 1);
-                            const float sv = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : (han_plus == 2 ? s2 : s3));
-                            win = SP_FADD(win, prob);
-                            ev = SP_FADD(ev, SP_FMUL(prob, sv));
-                        }
-                    } else {
-                        const u32 child = G.echild[eb + e];
-                        if (child == SP_NO_CHILD) continue;  // only after an overflow
-                        const float* cv = G.vals + (size_t)child * SP_VALS;
-                        for (int j = i; j < jend; j++) {
-                            const float prob = Pc[sp_tri(i, j)];
-                            if (k == 1) tenpai = SP_FADD(tenpai, prob);
-                            if (j < Tn - 1) {
-                                if (k > 1) tenpai = SP_FADD(tenpai, SP_FMUL(prob, cv[j + 1]));
-                                win = SP_FADD(win, SP_FMUL(prob, cv[SP_T_MAX + j + 1]));
-                                ev = SP_FADD(ev, SP_FMUL(prob, cv[2 * SP_T_MAX + j + 1]));
-                            }
+        const int i0 = p, i1 = Tn - 1 - p;
+        const bool two = i1 > i0;
+        const float m0 = nts[i0], m1 = two ? nts[i1] : 0.f;  // the reference stops at the first zero of the (monotone) row
+        float t0 = 0.f, w0 = 0.f, v0 = 0.f, t1 = 0.f, w1 = 0.f, v1 = 0.f;
+        for (int e = 0; e < ne; e++) {
+            const u16 meta = G.emeta[eb + e];
+            const float* tp = S.tp[st][((meta >> 6) & 7) - 1];
+            if (LEAF) {
+                if (meta & 0x8000) continue;  // no yaku
+                const int le = (int)(eb + e) - G.counters[4];
+                if (le < 0 || le >= G.score_cap) continue;
+                const float* sc = G.leaf_scores + (size_t)le * 4;
+                const float s0 = sc[0], s1 = sc[1], s2 = sc[2], s3 = sc[3];
+                if (m0 != 0.f)
+                    for (int j = i0; j < jend; j++) {
+                        const float prob = SP_FDIV(tp[j], m0);
+                        const int han_plus = (assume_riichi && dbl && i0 == 0) + (assume_riichi && j == i0) + (haitei && j == Tn - 1);
+                        const float sv = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : (han_plus == 2 ? s2 : s3));
+                        w0 = SP_FADD(w0, prob);
+                        v0 = SP_FADD(v0, SP_FMUL(prob, sv));
+                    }
+                if (m1 != 0.f)
+                    for (int j = i1; j < jend; j++) {
+                        const float prob = SP_FDIV(tp[j], m1);
+                        const int han_plus = (assume_riichi && j == i1) + (haitei && j == Tn - 1);  // i1 > 0
+                        const float sv = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : s2);
+                        w1 = SP_FADD(w1, prob);
+                        v1 = SP_FADD(v1, SP_FMUL(prob, sv));
+                    }
+            } else {
+                const u32 child = G.echild[eb + e];
+                if (child == SP_NO_CHILD) continue;  // only after an overflow
+                const float* cv = G.vals + (size_t)child * SP_VALS;
+                if (m0 != 0.f)
+                    for (int j = i0; j < jend; j++) {
+                        const float prob = SP_FDIV(tp[j], m0);
+                        if (k == 1) t0 = SP_FADD(t0, prob);
+                        if (j < Tn - 1) {
+                            if (k > 1) t0 = SP_FADD(t0, SP_FMUL(prob, cv[j + 1]));
+                            w0 = SP_FADD(w0, SP_FMUL(prob, cv[SP_T_MAX + j + 1]));
+                            v0 = SP_FADD(v0, SP_FMUL(prob, cv[2 * SP_T_MAX + j + 1]));
                         }
                     }
-                }
+                if (m1 != 0.f)
+                    for (int j = i1; j < jend; j++) {
+                        const float prob = SP_FDIV(tp[j], m1);
+                        if (k == 1) t1 = SP_FADD(t1, prob);
+                        if (j < Tn - 1) {
+                            if (k > 1) t1 = SP_FADD(t1, SP_FMUL(prob, cv[j + 1]));
+                            w1 = SP_FADD(w1, SP_FMUL(prob, cv[SP_T_MAX + j + 1]));
+                            v1 = SP_FADD(v1, SP_FMUL(prob, cv[2 * SP_T_MAX + j + 1]));
+                        }
+                    }
             }
-            o[i] = tenpai; o[SP_T_MAX + i] = win; o[2 * SP_T_MAX + i] = ev;
         }
+        float* o = G.vals + (size_t)S.slot[st] * SP_VALS;
+        o[i0] = t0; o[SP_T_MAX + i0] = w0; o[2 * SP_T_MAX + i0] = v0;
+        if (two) { o[i1] = t1; o[SP_T_MAX + i1] = w1; o[2 * SP_T_MAX + i1] = v1; }
     }
     SP_SYNC();
 }
@@ -702,7 +711,7 @@ MJX_DN void sp_eval_d_level(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, 
 template <bool LEAF>
 MJX_DN void sp_eval_w_level(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, int level) {
     const int n = min(G.wl_count[level], G.wl_cap);
-    for (int first = B.bid * SP_EB; first < n; first += B.nblk * SP_EB) sp_eval_w_batch<LEAF>(G, S, B, level, first, min(SP_EB, n - first));
+    for (int first = B.bid * SP_B; first < n; first += B.nblk * SP_B) sp_eval_w_batch<LEAF>(G, S, B, level, first, min(SP_B, n - first));
 }
 
 // release the table slots this DP used (instead of a full-table memset per step); after an overflow states may exist that
