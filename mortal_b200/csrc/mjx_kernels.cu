@@ -306,13 +306,11 @@ __global__ void __launch_bounds__(SP_THREADS) k_sp_eval(SpGlobal G, int level) {
     }
 }
 
-// the two probability tables of the W evaluation (csrc/mjx_sp.cuh), built once per process with the reference's recurrences
-__global__ void k_sp_tables(float* nts_tab, float* div_tab) {
+// the probability table of the W evaluation (csrc/mjx_sp.cuh), built once per process with the reference's operation sequence
+__global__ void k_sp_tables(float* p_tab) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < SP_NTS_DIM * SP_NTS_DIM) sp_fill_nts_row(nts_tab + (size_t)i * SP_T_MAX, i / SP_NTS_DIM, i % SP_NTS_DIM);
-    if (i < 4) sp_fill_div_row(div_tab + (size_t)i * SP_DIV_DIM, i);
+    if (i < SP_NTS_DIM * SP_NTS_DIM) sp_fill_ptab_block(p_tab + (size_t)i * 4 * SP_TRI, i / SP_NTS_DIM, i % SP_NTS_DIM);
 }
-
 
 __global__ void k_sp_mark(SpGlobal G, int which) { G.counters[4 + which] = min(G.counters[1], G.edge_cap); }
 
@@ -423,7 +421,7 @@ bool g_ready = false;
 int g_device = -1;
 int g_sm_count = 148;
 Tables g_T;
-const float *g_sp_nts_tab = nullptr, *g_sp_div_tab = nullptr;  // csrc/mjx_sp.cuh probability tables (device)
+const float* g_sp_p_tab = nullptr;  // csrc/mjx_sp.cuh draw-probability table (device)
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CU(call)                                                                          \
@@ -510,13 +508,12 @@ int mjx_init(const char* data_dir, int device) {
     }
     CU(cudaFuncSetAttribute(k_encode_store, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENCS_SMEM_BYTES));
     {
-        float *nts = nullptr, *dv = nullptr;
-        CU(cudaMalloc(&nts, sizeof(float) * SP_NTS_DIM * SP_NTS_DIM * SP_T_MAX));
-        CU(cudaMalloc(&dv, sizeof(float) * 4 * SP_DIV_DIM));
-        k_sp_tables<<<(SP_NTS_DIM * SP_NTS_DIM + 127) / 128, 128>>>(nts, dv);
+        float* pt = nullptr;
+        CU(cudaMalloc(&pt, sizeof(float) * SP_NTS_DIM * SP_NTS_DIM * 4 * SP_TRI));
+        k_sp_tables<<<(SP_NTS_DIM * SP_NTS_DIM + 63) / 64, 64>>>(pt);
         CU(cudaGetLastError());
         CU(cudaDeviceSynchronize());
-        g_sp_nts_tab = nts; g_sp_div_tab = dv;
+        g_sp_p_tab = pt;
     }
     g_device = device;
     g_ready = true;
@@ -586,7 +583,7 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
         int hc = 1 << 20;
         while (hc < want && hc < (1 << 26)) hc <<= 1;
         G.hash_cap = hc;
-        G.nts_tab = g_sp_nts_tab; G.div_tab = g_sp_div_tab;
+        G.p_tab = g_sp_p_tab;
         G.wl_cap = hc / 2;       // per level
         G.edge_cap = hc * 2;
         G.score_cap = hc;
@@ -686,7 +683,7 @@ static int launch_encode_rows(mjx_env* env, float* obs_dev, cudaStream_t st) {
 static int launch_sp_block(mjx_env* env, float* obs_dev, cudaStream_t st, int row_lo = 0, int row_hi = 0x7fffffff) {
     if (!env->sp_enabled) return MJX_OK;
     const SpGlobal& G = env->sp;
-    const int grid_rows = g_sm_count * 8, grid = g_sm_count * 8;
+    const int grid_rows = g_sm_count * 8, grid = g_sm_count * 8, grid_eval = g_sm_count * 16;
     k_sp_begin<<<1, 32, 0, st>>>(G);
     k_sp_init<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, row_lo, row_hi);
     for (int level = 0; level < SP_SLOTS; level++) {
@@ -699,9 +696,9 @@ static int launch_sp_block(mjx_env* env, float* obs_dev, cudaStream_t st, int ro
     k_sp_mark<<<1, 1, 0, st>>>(G, 1);
     k_sp_score<<<g_sm_count * 16, 128, 0, st>>>(G, g_T);
     for (int level = SP_SLOTS - 1; level >= 0; level--) {
-        if (!sp_slot_is_w(level)) k_sp_eval<0><<<grid, SP_THREADS, 0, st>>>(G, level);
-        else if (level == SP_SLOTS - 1) k_sp_eval<2><<<grid, SP_THREADS, 0, st>>>(G, level);
-        else k_sp_eval<1><<<grid, SP_THREADS, 0, st>>>(G, level);
+        if (!sp_slot_is_w(level)) k_sp_eval<0><<<grid_eval, SP_THREADS, 0, st>>>(G, level);
+        else if (level == SP_SLOTS - 1) k_sp_eval<2><<<grid_eval, SP_THREADS, 0, st>>>(G, level);
+        else k_sp_eval<1><<<grid_eval, SP_THREADS, 0, st>>>(G, level);
     }
     k_sp_finalize<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev, row_lo, row_hi);
     k_sp_release<<<g_sm_count * 4, 256, 0, st>>>(G);

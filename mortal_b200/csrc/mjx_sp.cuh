@@ -118,6 +118,35 @@ MJX_D HandSig sp_sig_unpack(const SpSigP& p) {
     return h;
 }
 
+// shanten (shanten.rs:138-150 calc_all) of the hand behind `sg` with tile t added (ADD) or removed; c0 = count of t before.
+// Only suit t / 9 changes: one table gather + entry 5 + len of the merge with `others` (the other three suits pre-merged);
+// the chiitoi / kokushi counters are touched only when they can matter.
+template <bool ADD>
+MJX_D int sp_candidate_shanten(const Tables& T, const SpSigP& sg, const u8* others, int t, int c0, int len_div3) {
+    const int sx = t / 9, pos = t - 9 * sx;
+    const u32 w5 = sx < 3 ? c_pow5[pos] : c_pow5[pos + 2];
+    const u32 idx = (sg.w[sx] & 0x1FFFFFu) + (ADD ? w5 : 0u - w5);
+    const u64 r = sx < 3 ? ld_row(T.suhai, idx, SUHAI_ROWS) : ld_row(T.jihai, idx, JIHAI_ROWS);
+    int v = 1 << 20;
+#pragma unroll
+    for (int a = 0; a <= 4; a++) {
+        if (a <= len_div3) {
+            const int b = len_div3 - a;
+            v = min(v, (int)others[5 + a] + (int)((r >> (4 * b)) & 0xF));
+            v = min(v, (int)others[a] + (int)((r >> (4 * (5 + b))) & 0xF));
+        }
+    }
+    int sh = v - 1;
+    if (sh <= 0 || len_div3 < 4) return sh;
+    int kinds = (int)(sg.w[0] >> 21), pairs = (int)(sg.w[1] >> 21), kkinds = (int)(sg.w[2] >> 21), kpairs = (int)(sg.w[3] >> 21);
+    const bool yao = is_yaokyuu(t);
+    if (ADD) { kinds += c0 == 0; pairs += c0 == 1; if (yao) { kkinds += c0 == 0; kpairs += c0 == 1; } }
+    else { kinds -= c0 == 1; pairs -= c0 == 2; if (yao) { kkinds -= c0 == 1; kpairs -= c0 == 2; } }
+    sh = min(sh, 7 - pairs + max(7 - kinds, 0) - 1);
+    if (sh > 0) sh = min(sh, 14 - kkinds - (kpairs > 0 ? 1 : 0) - 1);
+    return sh;
+}
+
 // per observation row: sp/calc.rs:36-62 parameters + what obs_repr.rs needs afterwards
 struct SpRow {
     u8 tehai_len_div3, is_menzen, prefer_riichi, calc_double_riichi, calc_haitei;
@@ -152,8 +181,7 @@ struct SpGlobal {
     float* leaf_scores; // [score_cap][4] get_score of every winning draw of the tenpai (W0) states
     u32* wl;            // [SP_SLOTS][wl_cap] work list of each level: table slots
     i32* wl_count;      // [SP_SLOTS]
-    const float* nts_tab;  // [SP_NTS_DIM][SP_NTS_DIM][SP_T_MAX] not_tsumo_prob rows by (tiles left, sum of required counts)
-    const float* div_tab;  // [4][SP_DIV_DIM] (c + 1) / d
+    const float* p_tab;    // [SP_NTS_DIM][SP_NTS_DIM][4][SP_TRI] draw probabilities by (tiles left, sum of required counts, count, i, j)
     i32* counters;      // [1] edges, [2] overflow flag, [3] overflow events (cumulative), [4],[5] edge range of the tenpai level
     i32 row_base;       // rows [row_base, ...) of the step form this DP (row groups of mjx_env_encode_obs_host)
     i32 hash_cap, wl_cap, edge_cap, score_cap;
@@ -189,6 +217,15 @@ MJX_D int sp_einfo_cmask(u64 e) { return (int)((e >> 48) & 0xF); }
 
 MJX_D void sp_set_overflow(const SpGlobal& G) { G.counters[2] = 1; }
 
+// pull a state's value vectors (204 B: two 128-byte lines) towards the SM ahead of their use
+MJX_D void sp_prefetch(const float* p) {
+#ifndef MJX_HOST_EMUL
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32));
+#else
+    (void)p;
+#endif
+}
 MJX_D i32 sp_atomic_add(i32* p, i32 v) {
 #ifdef MJX_HOST_EMUL
     const i32 o = *p; *p += v; return o;
@@ -316,9 +353,7 @@ MJX_DN void sp_expand_batch(const SpGlobal& G, const Tables& T, SpExpandBatch& S
     // one candidate per thread: shanten of hand +- tile
     SP_PFOR(i, S.n_cand) {
         const int st = S.cand_list[i] >> 6, t = S.cand_list[i] & 63;
-        const HandSig base = sp_sig_unpack(S.sig[st]);
-        const int len = S.len[st], c0 = S.teh[st][t];
-        const int sh = shanten_all_others(T, sig_variant(base, t, IS_W ? +1 : -1, c0), t / 9, S.oth[st][t / 9], len);
+        const int sh = sp_candidate_shanten<IS_W>(T, S.sig[st], S.oth[st][t / 9], t, S.teh[st][t], S.len[st]);
         const bool ok = IS_W ? sh - k == -1 : sh == k;
         if (ok) sp_atomic_or(&S.eff[st][t >> 5], 1u << (t & 31));
     }
@@ -512,41 +547,41 @@ MJX_DN void sp_score_edge(const SpGlobal& G, const Tables& T, int e) {
 }
 
 // ---------------------------------------------------------------------------------------------- evaluation
-// pair index of (turn i, draw turn j), i <= j < 17, ordered by j then i: the pairs with j < T are a prefix for every T
-MJX_HD int sp_tri(int i, int j) { return j * (j + 1) / 2 + i; }
-constexpr int SP_TRI = SP_T_MAX * (SP_T_MAX + 1) / 2;  // 153
-
 struct SpEvalDBatch {
     u32 slot[SP_B], ebeg[SP_B];
     u8 ne[SP_B], T[SP_B];
     u16 off[SP_B + 1];
     i32 n_items;
 };
-// W levels. not_tsumo_prob_table rows (calc.rs:148-167) depend on (tiles left at the root, sum of required counts) only and
-// tsumo_prob_table entries (calc.rs:136-146) on (count, tiles left - turn): both come from two small global tables built once
-// per process with the reference's own recurrences (k_sp_tables), so a state's probability vectors cost loads, not divisions.
+// W levels. The probability that the draw of turn j brings an effective tile of count c when turn i is the current one
+// (calc.rs:486-497 `tsumo_probs[j] * not_tsumo_probs[j] / not_tsumo_probs[i]`, with the tables of calc.rs:136-167) depends on
+// (tiles left at the root, sum of required counts, c, i, j) only — 124 x 124 x 4 x 153 values. They are tabulated ONCE per
+// process with the reference's own operation sequence (k_sp_tables; 37.6 MB, L2-resident in its hot part), so the inner loop of
+// the evaluation performs the reference's rounded multiply-adds with a table load in place of two divisions and a multiply.
 constexpr int SP_NTS_DIM = SP_MAX_TILES_LEFT + 2;  // n_left, sum_required in 0..123
-constexpr int SP_DIV_DIM = 140;
-MJX_D size_t sp_nts_index(int n_left, int i0) { return ((size_t)n_left * SP_NTS_DIM + (size_t)i0) * SP_T_MAX; }
-// one (n_left, i0) row of the table: row[0] = 1, row[j+1] = row[j] * (n_left - i0 - j) / (n_left - j)   (calc.rs:158-165)
-MJX_D void sp_fill_nts_row(float* row, int n_left, int i0) {
+constexpr int SP_TRI = SP_T_MAX * (SP_T_MAX + 1) / 2;  // (i, j) pairs, i <= j < 17, at j * (j + 1) / 2 + i
+MJX_D size_t sp_ptab_index(int n_left, int i0) { return ((size_t)n_left * SP_NTS_DIM + (size_t)i0) * 4 * SP_TRI; }
+// one (n_left, i0) block of the table: [c][pair]
+MJX_D void sp_fill_ptab_block(float* blk, int n_left, int i0) {
+    float nts[SP_T_MAX];  // not_tsumo_prob_table[i0]: row[0] = 1, row[j+1] = row[j] * (n_left - i0 - j) / (n_left - j)  (calc.rs:158-165)
     float v = 1.f;
     for (int j = 0; j < SP_T_MAX; j++) {
         const bool ok = i0 <= n_left && j <= n_left - i0;
-        row[j] = ok ? v : 0.f;
+        nts[j] = ok ? v : 0.f;
         if (ok && j < n_left - i0) v = SP_FDIV(SP_FMUL(v, (float)(n_left - i0 - j)), (float)(n_left - j));
     }
-}
-MJX_D void sp_fill_div_row(float* row, int c) {  // (c + 1) / d
-    for (int d = 0; d < SP_DIV_DIM; d++) row[d] = d > 0 ? SP_FDIV((float)(c + 1), (float)d) : 0.f;
+    for (int c = 0; c < 4; c++)
+        for (int j = 0; j < SP_T_MAX; j++) {
+            // tsumo_prob_table[c][j] = (c + 1) / (n_left - j)  (calc.rs:136-146)
+            const float tpj = (n_left - j > 0 && nts[j] != 0.f) ? SP_FMUL(SP_FDIV((float)(c + 1), (float)(n_left - j)), nts[j]) : 0.f;
+            for (int i = 0; i <= j; i++) blk[c * SP_TRI + j * (j + 1) / 2 + i] = nts[i] != 0.f ? SP_FDIV(tpj, nts[i]) : 0.f;
+        }
 }
 
 struct SpEvalWBatch {
-    u32 slot[SP_B], ebeg[SP_B];
-    u8 ne[SP_B], T[SP_B], flags[SP_B], jend[SP_B];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei; jend: first j with nts[j] == 0
+    u32 slot[SP_B], ebeg[SP_B], pbase[SP_B];
+    u8 ne[SP_B], T[SP_B], flags[SP_B], jend[SP_B];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei; jend: first j with not_tsumo[j] == 0
     u16 aoff[SP_B + 1];
-    float nts[SP_B][SP_T_MAX];        // not_tsumo_prob row of the state, truncated at T
-    float tp[SP_B][4][SP_T_MAX];      // tsumo_prob[c-1][j] * not_tsumo[j]
     i32 n_a;
 };
 template <typename Tb>
@@ -564,26 +599,19 @@ template <bool LEAF>
 MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, int level, int first, int nb) {
     const int k = LEAF ? 0 : sp_slot_shanten(level);
     const u32* list = G.wl + (size_t)level * G.wl_cap;
-    // (state, j): stage the probability vectors; lane j == 0 also stages the state's scalars
-    SP_PFOR(it, nb * SP_T_MAX) {
-        const int st = it / SP_T_MAX, j = it - st * SP_T_MAX;
+    SP_PFOR(st, nb) {
         const u32 slot = list[first + st];
         const SpRow& R = G.rows[sp_key_row(G.hkey[slot])];
         const u64 ei = G.einfo[slot];
         const int Tn = R.T, n_left = R.n_left, i0 = sp_einfo_sum(ei);
         const bool row_ok = i0 <= n_left && i0 <= SP_MAX_TILES_LEFT;
         const int lim = row_ok ? min(Tn - 1, n_left - i0) : -1;
-        const float v = j <= lim ? G.nts_tab[sp_nts_index(n_left, i0) + j] : 0.f;
-        S.nts[st][j] = v;
-        const int d = n_left - j;
-        for (int c = 0; c < 4; c++) S.tp[st][c][j] = (j < Tn && d > 0) ? SP_FMUL(G.div_tab[c * SP_DIV_DIM + d], v) : 0.f;
-        if (j == 0) {
-            S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei);
-            S.T[st] = (u8)Tn;
-            const bool ar = R.is_menzen && R.prefer_riichi;
-            S.flags[st] = (u8)((ar ? 1 : 0) | (R.calc_double_riichi ? 2 : 0) | (R.calc_haitei ? 4 : 0));
-            S.jend[st] = (u8)max(0, min(Tn, lim + 1));
-        }
+        S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei);
+        S.T[st] = (u8)Tn;
+        const bool ar = R.is_menzen && R.prefer_riichi;
+        S.flags[st] = (u8)((ar ? 1 : 0) | (R.calc_double_riichi ? 2 : 0) | (R.calc_haitei ? 4 : 0));
+        S.jend[st] = (u8)max(0, min(Tn, lim + 1));
+        S.pbase[st] = row_ok ? (u32)sp_ptab_index(n_left, i0) : 0u;
     }
     SP_SYNC();
     if (B.tid == 0) {
@@ -593,49 +621,48 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
     }
     SP_SYNC();
     // accumulation: a thread takes turns p and T-1-p of a state (T+1 draw turns together: balanced), edges in the reference's
-    // order, j ascending, every divide, multiply and add rounded as the reference rounds it
+    // order, j ascending, every multiply and add rounded as the reference rounds it
     SP_PFOR(item, S.n_a) {
         const int st = sp_find_state<int>(S.aoff, nb, item), p = item - S.aoff[st];
         const int Tn = S.T[st], ne = S.ne[st], jend = S.jend[st];
         const u32 eb = S.ebeg[st];
-        const float* nts = S.nts[st];
+        const float* Pb = G.p_tab + S.pbase[st];
         const bool assume_riichi = (S.flags[st] & 1) != 0, dbl = (S.flags[st] & 2) != 0, haitei = (S.flags[st] & 4) != 0;
         const int i0 = p, i1 = Tn - 1 - p;
         const bool two = i1 > i0;
-        const float m0 = nts[i0], m1 = two ? nts[i1] : 0.f;  // the reference stops at the first zero of the (monotone) row
         float t0 = 0.f, w0 = 0.f, v0 = 0.f, t1 = 0.f, w1 = 0.f, v1 = 0.f;
+        // the next edge's descriptor is fetched while the current one is accumulated (dependent chain meta/child -> values)
+        u16 meta_n = ne ? G.emeta[eb] : (u16)0;
+        u32 child_n = (!LEAF && ne) ? G.echild[eb] : 0u;
         for (int e = 0; e < ne; e++) {
-            const u16 meta = G.emeta[eb + e];
-            const float* tp = S.tp[st][((meta >> 6) & 7) - 1];
+            const u16 meta = meta_n;
+            const u32 child = child_n;
+            if (e + 1 < ne) { meta_n = G.emeta[eb + e + 1]; if (!LEAF) child_n = G.echild[eb + e + 1]; }
+            if (!LEAF && e + 1 < ne && child_n != SP_NO_CHILD) sp_prefetch(G.vals + (size_t)child_n * SP_VALS);
+            const float* Pc = Pb + (((meta >> 6) & 7) - 1) * SP_TRI;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            const float* cv = nullptr;
             if (LEAF) {
                 if (meta & 0x8000) continue;  // no yaku
                 const int le = (int)(eb + e) - G.counters[4];
                 if (le < 0 || le >= G.score_cap) continue;
                 const float* sc = G.leaf_scores + (size_t)le * 4;
-                const float s0 = sc[0], s1 = sc[1], s2 = sc[2], s3 = sc[3];
-                if (m0 != 0.f)
-                    for (int j = i0; j < jend; j++) {
-                        const float prob = SP_FDIV(tp[j], m0);
+                s0 = sc[0]; s1 = sc[1]; s2 = sc[2]; s3 = sc[3];
+            } else {
+                if (child == SP_NO_CHILD) continue;  // only after an overflow
+                cv = G.vals + (size_t)child * SP_VALS;
+            }
+            // turn i0: the reference stops a turn whose not_tsumo_probs[i] is zero and a draw turn whose not_tsumo_probs[j] is zero
+            // (the row is monotone: both are `>= jend`)
+            if (i0 < jend)
+                for (int j = i0; j < jend; j++) {
+                    const float prob = Pc[j * (j + 1) / 2 + i0];
+                    if (LEAF) {
                         const int han_plus = (assume_riichi && dbl && i0 == 0) + (assume_riichi && j == i0) + (haitei && j == Tn - 1);
                         const float sv = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : (han_plus == 2 ? s2 : s3));
                         w0 = SP_FADD(w0, prob);
                         v0 = SP_FADD(v0, SP_FMUL(prob, sv));
-                    }
-                if (m1 != 0.f)
-                    for (int j = i1; j < jend; j++) {
-                        const float prob = SP_FDIV(tp[j], m1);
-                        const int han_plus = (assume_riichi && j == i1) + (haitei && j == Tn - 1);  // i1 > 0
-                        const float sv = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : s2);
-                        w1 = SP_FADD(w1, prob);
-                        v1 = SP_FADD(v1, SP_FMUL(prob, sv));
-                    }
-            } else {
-                const u32 child = G.echild[eb + e];
-                if (child == SP_NO_CHILD) continue;  // only after an overflow
-                const float* cv = G.vals + (size_t)child * SP_VALS;
-                if (m0 != 0.f)
-                    for (int j = i0; j < jend; j++) {
-                        const float prob = SP_FDIV(tp[j], m0);
+                    } else {
                         if (k == 1) t0 = SP_FADD(t0, prob);
                         if (j < Tn - 1) {
                             if (k > 1) t0 = SP_FADD(t0, SP_FMUL(prob, cv[j + 1]));
@@ -643,9 +670,16 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
                             v0 = SP_FADD(v0, SP_FMUL(prob, cv[2 * SP_T_MAX + j + 1]));
                         }
                     }
-                if (m1 != 0.f)
-                    for (int j = i1; j < jend; j++) {
-                        const float prob = SP_FDIV(tp[j], m1);
+                }
+            if (two && i1 < jend)
+                for (int j = i1; j < jend; j++) {
+                    const float prob = Pc[j * (j + 1) / 2 + i1];
+                    if (LEAF) {
+                        const int han_plus = (assume_riichi && j == i1) + (haitei && j == Tn - 1);  // i1 > 0
+                        const float sv = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : s2);
+                        w1 = SP_FADD(w1, prob);
+                        v1 = SP_FADD(v1, SP_FMUL(prob, sv));
+                    } else {
                         if (k == 1) t1 = SP_FADD(t1, prob);
                         if (j < Tn - 1) {
                             if (k > 1) t1 = SP_FADD(t1, SP_FMUL(prob, cv[j + 1]));
@@ -653,7 +687,7 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
                             v1 = SP_FADD(v1, SP_FMUL(prob, cv[2 * SP_T_MAX + j + 1]));
                         }
                     }
-            }
+                }
         }
         float* o = G.vals + (size_t)S.slot[st] * SP_VALS;
         o[i0] = t0; o[SP_T_MAX + i0] = w0; o[2 * SP_T_MAX + i0] = v0;
@@ -686,8 +720,10 @@ MJX_DN void sp_eval_d_batch(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, 
         float bt = FMIN, bw = FMIN, bv = FMIN;
         int best_tile = T_UNK;
         i32 best_value = (i32)0x80000000;
+        u32 child_n = ne ? G.echild[eb] : SP_NO_CHILD;
         for (int e = 0; e < ne; e++) {
-            const u32 child = G.echild[eb + e];
+            const u32 child = child_n;
+            if (e + 1 < ne) { child_n = G.echild[eb + e + 1]; if (child_n != SP_NO_CHILD && i == 0) sp_prefetch(G.vals + (size_t)child_n * SP_VALS); }
             if (child == SP_NO_CHILD) continue;
             const int tile = G.emeta[eb + e] & 63;
             const float* cv = G.vals + (size_t)child * SP_VALS;

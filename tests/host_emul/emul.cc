@@ -293,10 +293,9 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
         G.rows = rows.data(); G.hkey = hkey.data(); G.einfo = einfo.data(); G.nsig = nsig.data(); G.vals = vals.data();
         G.leaf_scores = leaf_scores.data(); G.echild = echild.data(); G.eowner = eowner.data(); G.emeta = emeta.data();
         G.wl = wl.data(); G.wl_count = wl_count; G.counters = counters;
-        static std::vector<float> nts_tab((size_t)SP_NTS_DIM * SP_NTS_DIM * SP_T_MAX), div_tab((size_t)4 * SP_DIV_DIM);
-        for (int i = 0; i < SP_NTS_DIM * SP_NTS_DIM; i++) sp_fill_nts_row(nts_tab.data() + (size_t)i * SP_T_MAX, i / SP_NTS_DIM, i % SP_NTS_DIM);
-        for (int c = 0; c < 4; c++) sp_fill_div_row(div_tab.data() + (size_t)c * SP_DIV_DIM, c);
-        G.nts_tab = nts_tab.data(); G.div_tab = div_tab.data();
+        static std::vector<float> p_tab((size_t)SP_NTS_DIM * SP_NTS_DIM * 4 * SP_TRI);
+        for (int i = 0; i < SP_NTS_DIM * SP_NTS_DIM; i++) sp_fill_ptab_block(p_tab.data() + (size_t)i * 4 * SP_TRI, i / SP_NTS_DIM, i % SP_NTS_DIM);
+        G.p_tab = p_tab.data();
         for (int i = 0; i < 8; i++) counters[i] = 0;
     }
     for (int i = 0; i < SP_SLOTS; i++) wl_count[i] = 0;
