@@ -64,6 +64,11 @@ int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream);
  * through the copy engine while the SMs work on the next. Blocking; host buffers should be pinned (cudaHostAlloc / torch
  * pin_memory) for the overlap to happen. */
 int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8_t* masks_host, int* n_rows, void* stream);
+/* The same in two halves, so that a caller can overlap the device work and the D2H copies of one batch with host work on
+ * another (the libriichi.arena mirror steps two half-batches alternately): _begin enqueues everything and returns as soon as
+ * *n_rows is known (it waits for the step kernel only); _finish blocks until the host buffers are complete. */
+int mjx_env_encode_obs_host_begin(mjx_env* env, float* obs_dev, float* obs_host, uint8_t* masks_host, int* n_rows, void* stream);
+int mjx_env_encode_obs_host_finish(mjx_env* env);
 
 /* state/agent_helper.rs:509-593 single_player_tables (obs v4 rows 889-1011): on by default; `enable = 0`
  * leaves the block zero (the reference has no such switch; it exists for profiling the rest of the encoder).

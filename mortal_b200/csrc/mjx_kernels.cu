@@ -716,6 +716,18 @@ int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
 }
 
 int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8_t* masks_host, int* n_rows_out, void* stream) {
+    int rc = mjx_env_encode_obs_host_begin(env, obs_dev, obs_host, masks_host, n_rows_out, stream);
+    if (rc) return rc;
+    return mjx_env_encode_obs_host_finish(env);
+}
+
+int mjx_env_encode_obs_host_finish(mjx_env* env) {
+    if (!env) return fail(MJX_ERR_ARG, "mjx_env_encode_obs_host_finish: null env");
+    if (env->copy_stream) CU(cudaStreamSynchronize(env->copy_stream));
+    return MJX_OK;
+}
+
+int mjx_env_encode_obs_host_begin(mjx_env* env, float* obs_dev, float* obs_host, uint8_t* masks_host, int* n_rows_out, void* stream) {
     if (!env || !obs_dev || !obs_host || !masks_host || !n_rows_out)
         return fail(MJX_ERR_ARG, "mjx_env_encode_obs_host: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -753,7 +765,6 @@ int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8
         }
     }
     CU(cudaMemcpyAsync(masks_host, env->V.masks, (size_t)n * MJX_ACTION_SPACE, cudaMemcpyDeviceToHost, env->copy_stream));
-    CU(cudaStreamSynchronize(env->copy_stream));
     return MJX_OK;
 }
 

@@ -134,10 +134,10 @@ class HostProtocolEngine:
             setattr(self, attr, getattr(engine, attr))
 
     def react_host(self, obs_np: np.ndarray, masks_np: np.ndarray, idx: np.ndarray):
-        """rows `idx` of host arrays (views over pinned buffers filled by mjx_env_encode_obs_host) -> (actions, q) numpy,
+        """rows `idx` of host arrays (views over pinned buffers filled by mjx_env_encode_obs_host) -> (actions, q, is_greedy) numpy,
         through the reference protocol: lists of per-row arrays in, lists out (agent/mortal.rs:126-152)."""
-        actions, q, _, _ = self.engine.react_batch([obs_np[i] for i in idx], [masks_np[i] for i in idx], None)
-        return np.asarray(actions, dtype=np.int64), np.asarray(q, dtype=np.float32)
+        actions, q, _, greedy = self.engine.react_batch([obs_np[i] for i in idx], [masks_np[i] for i in idx], None)
+        return np.asarray(actions, dtype=np.int64), np.asarray(q, dtype=np.float32), np.asarray(greedy, dtype=bool)
 
     def react_device(self, obs: torch.Tensor, masks: torch.Tensor):
         obs_h = obs.cpu().numpy()

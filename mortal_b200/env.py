@@ -120,6 +120,20 @@ class BatchEnv:
                    "mjx_env_encode_obs_host")
         return n.value
 
+    def encode_obs_host_begin(self, obs_host, masks_host) -> int:
+        """Asynchronous half of encode_obs_host: enqueue encode + D2H and return num_rows as soon as it is known."""
+        assert obs_host.dtype == self.torch.float32 and obs_host.is_contiguous() and not obs_host.is_cuda
+        assert obs_host.shape[0] >= self.row_cap and tuple(obs_host.shape[1:]) == (self.obs_rows, 34)
+        assert masks_host.element_size() == 1 and masks_host.is_contiguous() and not masks_host.is_cuda
+        n = C.c_int(0)
+        _lib.check(self.L.mjx_env_encode_obs_host_begin(self._h, C.c_void_p(self.obs_buffer().data_ptr()), C.c_void_p(obs_host.data_ptr()),
+                                                        C.c_void_p(masks_host.data_ptr()), C.byref(n), self._stream()),
+                   "mjx_env_encode_obs_host_begin")
+        return n.value
+
+    def encode_obs_host_finish(self) -> None:
+        _lib.check(self.L.mjx_env_encode_obs_host_finish(self._h), "mjx_env_encode_obs_host_finish")
+
     def set_sp(self, enable: bool) -> None:
         _lib.check(self.L.mjx_env_set_sp(self._h, int(enable)), "mjx_env_set_sp")
 

@@ -5,6 +5,10 @@ Call-compatible with arena/one_vs_three.rs:17-113 and arena/two_vs_two.rs:17-110
 one_vs_three.rs:140-191 (game g = 4*s + r uses seed (seed_start[0] + s, seed_start[1]); the challenger
 sits at absolute seat r). The step loop is BatchGame::run (game.rs:286-304) executed by mjx kernels;
 engines are called once per cycle per agent like MortalBatchAgent::evaluate (mortal.rs:114-159).
+
+Tables are independent, so the batch is played as TWO half-batches stepped alternately (`pipeline`): while the engines
+work on the rows of one half (on the host for reference-protocol engines, on the tensor cores for device engines) the
+environment kernels and the D2H copies of the other half run. Results are those of one batch.
 """
 from __future__ import annotations
 
@@ -48,8 +52,9 @@ class _MetaRecorder:
         self.bounds.append(log_len_dev.cpu().numpy().copy())
 
     @_guard
-    def add_agent(self, cycle, idx, q, eval_ns):
-        self.q.setdefault(cycle, []).append((idx.cpu().numpy(), q.float().cpu().numpy(), int(eval_ns)))
+    def add_agent(self, cycle, idx, q, eval_ns, greedy=None):
+        g = None if greedy is None else np.asarray(greedy.cpu() if hasattr(greedy, "cpu") else greedy, dtype=bool)
+        self.q.setdefault(cycle, []).append((idx.cpu().numpy(), q.float().cpu().numpy(), int(eval_ns), g))
 
     @_guard
     def add_rows(self, cycle, tbl, row_seat, actions, masks, obs):
@@ -69,10 +74,13 @@ class _MetaRecorder:
             nr = len(tbl)
             q_rows = np.zeros((nr, 46), dtype=np.float32)
             batch, ns = np.zeros(nr, dtype=np.int64), np.zeros(nr, dtype=np.int64)
-            for idx, q, eval_ns in self.q.get(cycle, []):
+            greedy = np.ones(nr, dtype=bool)
+            for idx, q, eval_ns, g in self.q.get(cycle, []):
                 q_rows[idx] = q
                 batch[idx] = len(idx)
                 ns[idx] = eval_ns
+                if g is not None:
+                    greedy[idx] = g
             pos = {(int(tbl[r]), int(rs[r] & 3), bool(rs[r] & 4)): r for r in range(nr)}
             for (t, seat, kan), r in pos.items():
                 if kan:
@@ -82,10 +90,198 @@ class _MetaRecorder:
                 kan_meta = None
                 kr = pos.get((t, seat, True))
                 if kr is not None and int(act[r]) == 42:
-                    km = make_meta(int(act[kr]), masks[kr], q_rows[kr], **common)
+                    km = make_meta(int(act[kr]), masks[kr], q_rows[kr], is_greedy=bool(greedy[kr]), **common)
                     kan_meta = {k: v for k, v in km.items() if not k.startswith("_") and v is not None}
-                decisions[t].setdefault(cycle, {})[seat] = make_meta(int(act[r]), masks[r], q_rows[r], kan_select=kan_meta, **common)
+                decisions[t].setdefault(cycle, {})[seat] = make_meta(int(act[r]), masks[r], q_rows[r], is_greedy=bool(greedy[r]),
+                                                                     kan_select=kan_meta, **common)
         return np.array(self.bounds), decisions
+
+
+class _Part:
+    """One independently stepped slice of the batch: a BatchGame (game.rs:222-316) over tables [offset, offset + n)."""
+
+    def __init__(self, arena, agents, nonces, keys, offset, per, challenger_seats, version, quick_eval, use_stream):
+        import torch
+
+        self.arena, self.agents, self.offset, self.per = arena, agents, offset, per
+        self.nonces, self.keys, self.n = nonces, keys, len(nonces)
+        self.env = env = arena.env_factory(nonces, keys, obs_version=version, shuffle_kind=arena.shuffle_kind,
+                                           enable_quick_eval=quick_eval, device=arena.device)
+        self.dev = dev = env.device
+        self.stream = torch.cuda.Stream(dev) if (use_stream and dev.type == "cuda") else None
+        self.is_challenger = torch.zeros((per, 4), dtype=torch.bool, device=dev)
+        for g in range(per):
+            for s in challenger_seats(g):
+                self.is_challenger[g, s] = True
+        self.ic_host = self.is_challenger.cpu().numpy()
+        self.meta_rec = None
+        if arena.log_dir is not None:
+            env.enable_log()
+            self.meta_rec = _MetaRecorder(self.n, version) if arena.log_meta else None
+        self.actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
+        guards = [bool(getattr(a, "enable_rule_based_agari_guard", False)) for a in agents]
+        self.q_all = None
+        if any(guards):  # mortal.rs:319-336 needs the Q-values of the previous decision
+            flags = np.zeros((self.n, 4), dtype=np.uint8)
+            for g in range(self.n):
+                for seat in range(4):
+                    flags[g, seat] = guards[0] if self.ic_host[g % per, seat] else guards[1]
+            env.set_agari_guard(flags)
+            self.q_all = torch.zeros((env.row_cap, 46), dtype=torch.float32, device=dev)
+        # engines that only speak the reference protocol (react_batch over host arrays) get the observations through
+        # mjx_env_encode_obs_host: pinned host buffers, D2H overlapped with the single-player kernels
+        self.host_mode = all(isinstance(a, HostProtocolEngine) for a in agents)
+        if self.host_mode:
+            pin = (lambda t: t.pin_memory()) if dev.type == "cuda" else (lambda t: t)
+            self.h_obs = pin(torch.empty((env.row_cap, env.obs_rows, 34), dtype=torch.float32))
+            self.h_masks = pin(torch.empty((env.row_cap, 46), dtype=torch.bool))
+            self.h_actions = pin(torch.zeros(env.row_cap, dtype=torch.int64))
+            self.h_q = pin(torch.zeros((env.row_cap, 46), dtype=torch.float32)) if self.q_all is not None else None
+            self.obs_np, self.masks_np = self.h_obs.numpy(), self.h_masks.numpy()
+        self.first, self.cycles, self.nr = True, 0, 0
+        self.recorded, self.recorded_masks = [], []
+        self.mask_weights = (1 << torch.arange(46, dtype=torch.int64))
+
+    # every device call of the part goes to its own stream, so the two parts overlap on the GPU
+    def _ctx(self):
+        import contextlib
+
+        import torch
+
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
+    def start(self, fast_forward):
+        with self._ctx():
+            if fast_forward:
+                self.env.step(None)
+                for _ in range(int(fast_forward)):
+                    self.env.policy_test(2, self.actions)
+                    self.env.step(self.actions)
+                self.first = False
+                self._after_step()
+            else:
+                self.begin()
+
+    def begin(self):
+        """One BatchGame::run iteration for this part: commit the decisions, poll to the next decision point (game.rs:286-296);
+        in host mode the encode and the D2H copies are enqueued right away."""
+        with self._ctx():
+            self.env.step(None if self.first else self.actions, None if self.first else self.q_all)
+            self.first = False
+            self._after_step()
+
+    def _after_step(self):
+        if self.meta_rec is not None:
+            self.meta_rec.add_bounds(self.env.log_len)
+        if self.host_mode:
+            self.nr = self.env.encode_obs_host_begin(self.h_obs, self.h_masks)
+
+    def finish(self):
+        """Wait for the part's step; game.rs:288,292: an error from any table aborts the whole batch at that cycle (`?`);
+        so does a single-player arena overflow, which would otherwise hand zeroed rows 889-1011 to the engines."""
+        with self._ctx():
+            if self.host_mode:
+                self.env.encode_obs_host_finish()
+            nr, n_live, n_err, sp_ovf = self.env.poll()
+        if n_err:
+            res = self.env.results()
+            bad = int(np.nonzero(res["err"])[0][0])
+            raise RuntimeError(f"table {self.offset + bad} (seed {int(self.nonces[bad])},{int(self.keys[bad])}) failed at cycle "
+                               f"{self.cycles} with mjx error code {int(res['err'][bad])} (invalid action or inconsistent state; "
+                               "board.rs:527-532)")
+        if sp_ovf:
+            raise RuntimeError(f"single-player state arena overflowed at cycle {self.cycles}: observation rows 889-1011 would be "
+                               "zero; run fewer tables per environment")
+        self.nr = nr
+        return nr, n_live
+
+    def decide(self):
+        import torch
+
+        env, nr, agents, cycles, meta_rec = self.env, self.nr, self.agents, self.cycles, self.meta_rec
+        if nr == 0:
+            return
+        with self._ctx():
+            if self.host_mode:
+                h_actions, h_q = self.h_actions, self.h_q
+                tbl_h = env.row_table[:nr].cpu().numpy()
+                rs_h = env.row_seat[:nr].cpu().numpy()
+                chal_h = self.ic_host[tbl_h % self.per, rs_h & 3]
+                same = agents[0] is agents[1]
+                groups = ((np.arange(nr), agents[0]),) if same else ((np.nonzero(chal_h)[0], agents[0]), (np.nonzero(~chal_h)[0], agents[1]))
+                for idx, agent in groups:
+                    if idx.size == 0:
+                        continue
+                    t_eval = time.perf_counter_ns()
+                    a, q, greedy = agent.react_host(self.obs_np, self.masks_np, idx)
+                    if meta_rec is not None:
+                        meta_rec.add_agent(cycles, torch.from_numpy(idx), torch.from_numpy(q).reshape(-1, 46), time.perf_counter_ns() - t_eval, greedy)
+                    h_actions[torch.from_numpy(idx)] = torch.from_numpy(a)
+                    if h_q is not None:
+                        h_q[torch.from_numpy(idx)] = torch.from_numpy(q).reshape(-1, 46)
+                if meta_rec is not None:
+                    meta_rec.add_rows(cycles, torch.from_numpy(tbl_h).long(), torch.from_numpy(rs_h), h_actions[:nr], self.h_masks[:nr], self.h_obs[:nr])
+                self.actions[:nr].copy_(h_actions[:nr], non_blocking=True)
+                if h_q is not None:
+                    self.q_all[:nr].copy_(h_q[:nr], non_blocking=True)
+                if self.arena.record_decisions:
+                    self.recorded.append(torch.stack([torch.from_numpy(tbl_h).long() + self.offset, env.row_step[:nr].cpu().long(),
+                                                      torch.from_numpy(rs_h & 3).long(), torch.from_numpy((rs_h >> 2) & 1).long(),
+                                                      h_actions[:nr].clone()], dim=1))
+                    self.recorded_masks.append((self.h_masks[:nr].long() * self.mask_weights).sum(1))
+                return
+            obs_buf = env.encode_obs()
+            obs, masks = obs_buf[:nr], env.masks[:nr]
+            tbl = env.row_table[:nr].long()
+            seat = (env.row_seat[:nr] & 3).long()
+            if agents[0] is agents[1]:  # one engine for every seat: no gather of the rows, CUDA-graph replay when the engine has one
+                agent = agents[0]
+                t_eval = time.perf_counter_ns()
+                greedy = None
+                if hasattr(agent, "react_static") and not meta_rec:
+                    a, q = agent.react_static(obs_buf, env.masks, nr)
+                else:
+                    out = agent.react_device(obs, masks)
+                    a, q = out[0], out[1]
+                self.actions[:nr] = a.to(torch.int64)
+                if self.q_all is not None:
+                    self.q_all[:nr] = q.float()
+                if meta_rec is not None:
+                    meta_rec.add_agent(cycles, torch.arange(nr), q, time.perf_counter_ns() - t_eval, greedy)
+            else:
+                chal = self.is_challenger[tbl % self.per, seat]
+                for idx, agent in ((chal.nonzero().squeeze(1), agents[0]), ((~chal).nonzero().squeeze(1), agents[1])):
+                    if idx.numel() == 0:
+                        continue
+                    t_eval = time.perf_counter_ns()
+                    out = agent.react_device(obs[idx], masks[idx])
+                    a, q = out[0], out[1]
+                    self.actions[idx] = a.to(torch.int64)
+                    if self.q_all is not None:
+                        self.q_all[idx] = q.float()
+                    if meta_rec is not None:
+                        meta_rec.add_agent(cycles, idx, q, time.perf_counter_ns() - t_eval)
+            if meta_rec is not None:
+                meta_rec.add_rows(cycles, tbl, env.row_seat[:nr], self.actions[:nr], masks, obs)
+            if self.arena.record_decisions:
+                self.recorded.append(torch.stack([tbl + self.offset, env.row_step[:nr].long(), seat, (env.row_seat[:nr] >> 2).long() & 1,
+                                                  self.actions[:nr]], dim=1).cpu())
+                self.recorded_masks.append((masks.long() * self.mask_weights.to(self.dev)).sum(1).cpu())
+
+
+class _RunState:
+    """What a cycle_hook sees."""
+
+    def __init__(self, parts):
+        self.parts = parts
+
+    def total_steps(self):
+        return sum(p.env.total_steps() for p in self.parts)
+
+    def synchronize(self):
+        for p in self.parts:
+            if p.stream is not None:
+                p.stream.synchronize()
 
 
 class _Arena:
@@ -93,7 +289,6 @@ class _Arena:
 
     def __init__(self, *, disable_progress_bar: bool = False, log_dir=None, shuffle_kind: int = 0, device: int = 0):
         self.disable_progress_bar = disable_progress_bar
-        self.log_dir = log_dir
         self.shuffle_kind = shuffle_kind
         self.device = device
         self.last_stats = None
@@ -102,9 +297,10 @@ class _Arena:
         self.log_dir = log_dir  # arena/one_vs_three.rs:26-34: gz mjai logs are written here when set
         self.log_meta = True    # attach the per-decision meta (q-values, mask bits, ...) to the agent events (mortal.rs:161-186)
         self.last_meta_error = None
+        self.pipeline = True    # play the batch as two half-batches stepped alternately (see the module docstring)
         self.max_cycles = 0     # test hook: stop after this many BatchGame::run cycles (0 = play every table to the end)
         self.fast_forward_steps = 0  # bench hook: play this many batch steps with the counter-free test policy (kind 2) first
-        self.cycle_hook = None       # bench hook: callable(cycle_index, env) at the top of every cycle
+        self.cycle_hook = None       # bench hook: callable(cycle_index, run_state) when the first part starts a cycle
         self.env_factory = BatchEnv  # test hook: tests/emul_batch_env.py injects the host-emulated environment; the product has no CPU path
         self.last_decision_masks = None  # with record_decisions: the legal mask (46 bits) each recorded row was decided under
 
@@ -114,7 +310,10 @@ class _Arena:
     def _run(self, challenger, champion, seed_start, seed_count):
         import torch
 
-        agents = [_adapt(challenger), _adapt(champion)]
+        if challenger is champion:
+            agents = [_adapt(challenger)] * 2
+        else:
+            agents = [_adapt(challenger), _adapt(champion)]
         for a in agents:
             if getattr(a, "is_oracle", False):
                 raise NotImplementedError("oracle (invisible) observations are out of this round's scope")
@@ -127,164 +326,74 @@ class _Arena:
         if qe[0] != qe[1]:
             raise NotImplementedError("challenger and champion must agree on enable_quick_eval")
         per = self.GAMES_PER_SEED
-        n = int(seed_count) * per
-        nonces = np.repeat(np.arange(seed_start[0], seed_start[0] + int(seed_count), dtype=np.uint64), per)
+        seed_count = int(seed_count)
+        n = seed_count * per
+        nonces = np.repeat(np.arange(seed_start[0], seed_start[0] + seed_count, dtype=np.uint64), per)
         keys = np.full(n, seed_start[1], dtype=np.uint64)
-        env = self.env_factory(nonces, keys, obs_version=versions[0], shuffle_kind=self.shuffle_kind, enable_quick_eval=qe[0],
-                               device=self.device)
-        dev = env.device
-        # seat -> agent index table per game-in-seed
-        is_challenger = torch.zeros((per, 4), dtype=torch.bool, device=dev)
-        for g in range(per):
-            for s in self._challenger_seats(g):
-                is_challenger[g, s] = True
-        meta_rec = None
-        if self.log_dir is not None:
-            env.enable_log()
-            meta_rec = _MetaRecorder(n, versions[0]) if self.log_meta else None
-        actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
-        guards = [bool(getattr(a, "enable_rule_based_agari_guard", False)) for a in agents]
-        q_all = None
-        if any(guards):  # mortal.rs:319-336 needs the Q-values of the previous decision
-            flags = np.zeros((n, 4), dtype=np.uint8)
-            ic = is_challenger.cpu().numpy()
-            for g in range(n):
-                for seat in range(4):
-                    flags[g, seat] = guards[0] if ic[g % per, seat] else guards[1]
-            env.set_agari_guard(flags)
-            q_all = torch.zeros((env.row_cap, 46), dtype=torch.float32, device=dev)
-        # engines that only speak the reference protocol (react_batch over host arrays) get the observations through
-        # mjx_env_encode_obs_host: pinned host buffers, D2H overlapped with the single-player kernels
-        host_mode = all(isinstance(a, HostProtocolEngine) for a in agents)
-        if host_mode:
-            pin = (lambda t: t.pin_memory()) if dev.type == "cuda" else (lambda t: t)
-            h_obs = pin(torch.empty((env.row_cap, env.obs_rows, 34), dtype=torch.float32))
-            h_masks = pin(torch.empty((env.row_cap, 46), dtype=torch.bool))
-            h_actions = pin(torch.zeros(env.row_cap, dtype=torch.int64))
-            h_q = pin(torch.zeros((env.row_cap, 46), dtype=torch.float32)) if q_all is not None else None
-            obs_np, masks_np = h_obs.numpy(), h_masks.numpy()
-            ic_host = is_challenger.cpu().numpy()
-        first = True
-        cycles = 0
-        recorded, recorded_masks = [], []
-        mask_weights = (1 << torch.arange(46, dtype=torch.int64))
-
-        def check_health():
-            # game.rs:288,292: an error from any table aborts the whole batch at that cycle (`?`); so does a single-player arena
-            # overflow, which would otherwise hand zeroed rows 889-1011 to the engines
-            nr_, live_, n_err, sp_ovf = env.poll()
-            if n_err:
-                res_ = env.results()
-                bad = int(np.nonzero(res_["err"])[0][0])
-                env.close()
-                raise RuntimeError(f"table {bad} (seed {int(nonces[bad])},{int(keys[bad])}) failed at cycle {cycles} with mjx error code "
-                                   f"{int(res_['err'][bad])} (invalid action or inconsistent state; board.rs:527-532)")
-            if sp_ovf:
-                env.close()
-                raise RuntimeError(f"single-player state arena overflowed at cycle {cycles}: observation rows 889-1011 would be zero; "
-                                   "run fewer tables per environment")
-            return nr_, live_
-
-        skip_step = False
-        if self.fast_forward_steps:
-            env.step(None)
-            for _ in range(int(self.fast_forward_steps)):
-                env.policy_test(2, actions)
-                env.step(actions)
-            first, skip_step = False, True
-        while True:
-            if self.cycle_hook is not None:
-                self.cycle_hook(cycles, env)
-            if self.max_cycles and cycles >= self.max_cycles:
-                break
-            if not skip_step:
-                env.step(None if first else actions, None if first else q_all)
-            first = skip_step = False
-            if meta_rec is not None:
-                meta_rec.add_bounds(env.log_len)
-            nr, n_live = check_health()
-            if host_mode:
-                if nr == 0 and n_live == 0:
-                    break
-                if nr > 0:
-                    assert env.encode_obs_host(h_obs, h_masks) == nr
-                if nr > 0:
-                    tbl_h = env.row_table[:nr].cpu().numpy()
-                    rs_h = env.row_seat[:nr].cpu().numpy()
-                    chal_h = ic_host[tbl_h % per, rs_h & 3]
-                    for idx, agent in ((np.nonzero(chal_h)[0], agents[0]), (np.nonzero(~chal_h)[0], agents[1])):
-                        if idx.size == 0:
-                            continue
-                        t_eval = time.perf_counter_ns()
-                        a, q = agent.react_host(obs_np, masks_np, idx)
-                        if meta_rec is not None:
-                            meta_rec.add_agent(cycles, torch.from_numpy(idx), torch.from_numpy(q).reshape(-1, 46), time.perf_counter_ns() - t_eval)
-                        h_actions[torch.from_numpy(idx)] = torch.from_numpy(a)
-                        if h_q is not None:
-                            h_q[torch.from_numpy(idx)] = torch.from_numpy(q).reshape(-1, 46)
-                    if meta_rec is not None:
-                        meta_rec.add_rows(cycles, torch.from_numpy(tbl_h).long(), torch.from_numpy(rs_h), h_actions[:nr], h_masks[:nr], h_obs[:nr])
-                    actions[:nr].copy_(h_actions[:nr], non_blocking=True)
-                    if h_q is not None:
-                        q_all[:nr].copy_(h_q[:nr], non_blocking=True)
-                    if self.record_decisions:
-                        recorded.append(torch.stack([torch.from_numpy(tbl_h).long(), env.row_step[:nr].cpu().long(),
-                                                     torch.from_numpy(rs_h & 3).long(), torch.from_numpy((rs_h >> 2) & 1).long(),
-                                                     h_actions[:nr].clone()], dim=1))
-                        recorded_masks.append((h_masks[:nr].long() * mask_weights).sum(1))
-                cycles += 1
-                continue
-            if nr == 0 and n_live == 0:
-                break
-            if nr > 0:
-                obs = env.encode_obs()[:nr]
-                masks = env.masks[:nr]
-                tbl = env.row_table[:nr].long()
-                seat = (env.row_seat[:nr] & 3).long()
-                chal = is_challenger[tbl % per, seat]
-                for idx, agent in ((chal.nonzero().squeeze(1), agents[0]), ((~chal).nonzero().squeeze(1), agents[1])):
-                    if idx.numel() == 0:
+        # the seat rotations of a seed stay together; two parts when there is something to overlap
+        cuts = [0, n]
+        if self.pipeline and seed_count >= 2:
+            cuts = [0, (seed_count // 2) * per, n]
+        parts = []
+        try:
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                parts.append(_Part(self, agents, nonces[lo:hi], keys[lo:hi], lo, per, self._challenger_seats, versions[0], qe[0],
+                                   use_stream=len(cuts) > 2))
+            state = _RunState(parts)
+            for p in parts:
+                p.start(self.fast_forward_steps)
+            live = list(parts)
+            while live:
+                for p in list(live):
+                    if p is parts[0] and self.cycle_hook is not None:
+                        self.cycle_hook(p.cycles, state)
+                    if self.max_cycles and p.cycles >= self.max_cycles:
+                        live.remove(p)
                         continue
-                    t_eval = time.perf_counter_ns()
-                    a, q = agent.react_device(obs[idx], masks[idx])
-                    actions[idx] = a.to(torch.int64)
-                    if q_all is not None:
-                        q_all[idx] = q.float()
-                    if meta_rec is not None:
-                        meta_rec.add_agent(cycles, idx, q, time.perf_counter_ns() - t_eval)
-                if meta_rec is not None:
-                    meta_rec.add_rows(cycles, tbl, env.row_seat[:nr], actions[:nr], masks, obs)
-                if self.record_decisions:
-                    recorded.append(torch.stack([tbl, env.row_step[:nr].long(), seat, (env.row_seat[:nr] >> 2).long() & 1,
-                                                 actions[:nr]], dim=1).cpu())
-                    recorded_masks.append((masks.long() * mask_weights.to(dev)).sum(1).cpu())
-            cycles += 1
-        res = env.results()
-        if self.log_dir is not None:  # one_vs_three.rs:195-225: one {seed}_{key}_{split}.json.gz per game
-            from .. import mjai_log
+                    nr, n_live = p.finish()
+                    if nr == 0 and n_live == 0:
+                        live.remove(p)
+                        continue
+                    p.decide()
+                    p.cycles += 1
+                    if self.max_cycles and p.cycles >= self.max_cycles:
+                        continue  # the decisions of the last cycle are computed but not applied (oracle replay cuts there too)
+                    p.begin()
+            state.synchronize()
+            results = [p.env.results() for p in parts]
+            res = {k: np.concatenate([r[k] for r in results]) for k in results[0]}
+            if self.log_dir is not None:  # one_vs_three.rs:195-225: one {seed}_{key}_{split}.json.gz per game
+                from .. import mjai_log
 
-            words, lens = env.read_log()
-            ic = is_challenger.cpu().numpy()
-            agent_names = [str(getattr(a, "name", "NoName")) for a in agents]
-            names = [[agent_names[0] if ic[g % per, seat] else agent_names[1] for seat in range(4)] for g in range(n)]
-            seeds = [(int(nonces[g]), int(keys[g])) for g in range(n)]
-            bounds = decisions = None
-            if meta_rec is not None:
-                try:
-                    bounds, decisions = meta_rec.finish()
-                except Exception as exc:  # the logs themselves must not depend on the optional metadata
-                    self.last_meta_error = exc
+                agent_names = [str(getattr(a, "name", "NoName")) for a in agents]
+                self.last_log_paths = []
+                for p in parts:
+                    words, lens = p.env.read_log()
+                    names = [[agent_names[0] if p.ic_host[g % per, seat] else agent_names[1] for seat in range(4)] for g in range(p.n)]
+                    seeds = [(int(p.nonces[g]), int(p.keys[g])) for g in range(p.n)]
                     bounds = decisions = None
-            self.last_log_paths = mjai_log.write_logs(self.log_dir, words, lens, seeds, names, "abcd"[:per], bounds, decisions)
-        self.last_stats = dict(cycles=cycles, table_steps=int(res["steps"].sum()), sp_overflows=env.sp_overflows())
-        self.last_results = res
-        if self.record_decisions:
-            self.last_decisions = torch.cat(recorded).numpy() if recorded else np.zeros((0, 5), dtype=np.int64)
-            self.last_decision_masks = torch.cat(recorded_masks).numpy() if recorded_masks else np.zeros(0, dtype=np.int64)
-        env.close()
-        if self.last_stats["sp_overflows"]:
+                    if p.meta_rec is not None:
+                        try:
+                            bounds, decisions = p.meta_rec.finish()
+                        except Exception as exc:  # the logs themselves must not depend on the optional metadata
+                            self.last_meta_error = exc
+                            bounds = decisions = None
+                    self.last_log_paths += mjai_log.write_logs(self.log_dir, words, lens, seeds, names, "abcd"[:per], bounds, decisions)
+            sp_overflows = sum(p.env.sp_overflows() for p in parts)
+            self.last_stats = dict(cycles=max(p.cycles for p in parts), table_steps=int(res["steps"].sum()), sp_overflows=sp_overflows,
+                                   parts=len(parts), launches=sum(p.env.launch_count() for p in parts if hasattr(p.env, "launch_count")))
+            self.last_results = res
+            if self.record_decisions:
+                rec = [x for p in parts for x in p.recorded]
+                recm = [x for p in parts for x in p.recorded_masks]
+                self.last_decisions = torch.cat(rec).numpy() if rec else np.zeros((0, 5), dtype=np.int64)
+                self.last_decision_masks = torch.cat(recm).numpy() if recm else np.zeros(0, dtype=np.int64)
+        finally:
+            for p in parts:
+                p.env.close()
+        if sp_overflows:
             raise RuntimeError("single-player state arena overflowed during the run: observation rows 889-1011 were zero in "
-                               f"{self.last_stats['sp_overflows']} step(s)")
+                               f"{sp_overflows} step(s)")
         if (res["err"] != 0).any():
             bad = int(np.nonzero(res["err"])[0][0])
             raise RuntimeError(f"table {bad} failed with mjx error code {int(res['err'][bad])}")

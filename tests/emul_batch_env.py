@@ -70,6 +70,12 @@ class EmulBatchEnv:
             h_masks[:n] = self.masks[:n]
         return n
 
+    def encode_obs_host_begin(self, h_obs, h_masks):
+        return self.encode_obs_host(h_obs, h_masks)
+
+    def encode_obs_host_finish(self):
+        pass
+
     def policy_test(self, kind, actions):
         actions.copy_(torch.from_numpy(self._e.policy_test(kind)))
 

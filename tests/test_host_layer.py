@@ -346,10 +346,10 @@ def test_arena_host_protocol_loop_on_emulated_env_fail_fast():
     good = Eng()
     arena = _emul_arena(OneVsThree)
     arena.record_decisions = True
-    rankings = arena.py_vs_py(good, good, (5000, 3), 1)
-    assert sum(rankings) == 4
-    nonces = np.repeat(np.arange(5000, 5001, dtype=np.uint64), 4)
-    keys = np.full(4, 3, dtype=np.uint64)
+    rankings = arena.py_vs_py(good, good, (5000, 3), 3)  # 12 games: two half-batches (4 + 8 tables) stepped alternately
+    assert sum(rankings) == 12 and arena.last_stats["parts"] == 2
+    nonces = np.repeat(np.arange(5000, 5003, dtype=np.uint64), 4)
+    keys = np.full(12, 3, dtype=np.uint64)
     ref = O.run_replay(nonces, keys, arena.last_decisions, quick_eval=True, mask_bits=arena.last_decision_masks)
     assert (ref["scores"] == arena.last_results["scores"]).all() and (ref["ranks"] == arena.last_results["ranks"]).all()
 
