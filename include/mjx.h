@@ -70,6 +70,12 @@ int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8
 int mjx_env_encode_obs_host_begin(mjx_env* env, float* obs_dev, float* obs_host, uint8_t* masks_host, int* n_rows, void* stream);
 int mjx_env_encode_obs_host_finish(mjx_env* env);
 
+/* arena/board.rs:680-782 encode_oracle_obs for every row of the current step — the invisible observation an `is_oracle`
+ * engine receives as react_batch's third argument (agent/mortal.rs:253-255; dataset/invisible.rs for the loader):
+ * inv_dev = float32 [row_cap, mjx_oracle_obs_rows(version), 34]. consts.rs:30-38: 211 rows for version 1, else 217. */
+int mjx_oracle_obs_rows(int version);
+int mjx_env_encode_invisible(mjx_env* env, float* inv_dev, int version, void* stream);
+
 /* state/agent_helper.rs:509-593 single_player_tables (obs v4 rows 889-1011): on by default; `enable = 0`
  * leaves the block zero (the reference has no such switch; it exists for profiling the rest of the encoder).
  * mjx_env_sp_overflows: number of steps so far in which the state arena (2048 states per table on average)
@@ -103,7 +109,8 @@ int32_t* mjx_env_log_len_dev(mjx_env* env); /* int32 [n_tables] device view of t
 
 /* ---- log replay: dataset/gameplay.rs:247-449 GameplayLoader ------------------------------------------
  * A job = one (game log, player). `hdr`: the games' events as 64-bit words (csrc/mjx_step.cuh `log_word`; start_game = 15,
- * end_game = 16), concatenated, job j owning ev_cnt[j] words from ev_off[j]; `kyoku`: 9 words per start_kyoku (scores, haipai),
+ * end_game = 16), concatenated, job j owning ev_cnt[j] words from ev_off[j]; `kyoku`: 19 words per start_kyoku (2 of scores, 17 = the
+ * 136-byte wall in board.rs:109-122 layout: the 52 dealt tiles, the rest `?` = 37 unless the hidden tiles are known),
  * job j's first payload at index ky_off[j]; `players`: the job's point of view. All host arrays. Full-information logs only.
  * mjx_env_replay_step advances every job to the next decision the log shows its player making and emits the row(s)
  * (decision, then kan-select); observation / mask / row_table / row_seat are read exactly as after mjx_env_step, plus the
@@ -112,6 +119,11 @@ int mjx_env_create_replay(mjx_env** out, int n_jobs, const uint64_t* hdr, const 
                           const uint64_t* kyoku, const int32_t* ky_off, long long n_kyoku_words, const uint8_t* players,
                           int obs_version, int always_include_kan_select);
 int mjx_env_replay_step(mjx_env* env, void* stream);
+/* dataset/invisible.rs:35-66 (`trust_seed`): the logs were produced from known seeds (start_game.seed, what this arena and
+ * libriichi's write) — host arrays (nonce, key) per job. Every kyoku's wall is then regenerated on device (board.rs:99-123), checked
+ * against the logged haipai / dora marker (a mismatch fails the job), and mjx_env_encode_invisible can show the hidden tiles.
+ * Call before the first mjx_env_replay_step. */
+int mjx_env_replay_trust_seeds(mjx_env* env, const uint64_t* nonces_host, const uint64_t* keys_host, int shuffle_kind);
 int64_t* mjx_env_row_label(mjx_env* env); /* int64 [row_cap] device */
 uint8_t* mjx_env_row_meta(mjx_env* env);  /* uint8 [row_cap, 4] device: at_kyoku, at_turn, shanten (int8), apply_gamma */
 

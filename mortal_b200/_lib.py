@@ -43,6 +43,8 @@ SYMBOLS = {
     "mjx_env_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mjx_env_set_agari_guard": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mjx_env_encode_obs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mjx_oracle_obs_rows": (C.c_int, [C.c_int]),
+    "mjx_env_encode_invisible": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "mjx_env_set_sp": (C.c_int, [C.c_void_p, C.c_int]),
     "mjx_env_encode_obs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "mjx_env_encode_obs_host_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
@@ -57,6 +59,7 @@ SYMBOLS = {
     "mjx_nn_gate_residual_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mjx_env_create_replay": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                         C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int]),
+    "mjx_env_replay_trust_seeds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mjx_env_replay_step": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mjx_env_row_label": (C.c_void_p, [C.c_void_p]),
     "mjx_env_row_meta": (C.c_void_p, [C.c_void_p]),

@@ -9,6 +9,7 @@
 #include "mjx_sp.cuh"
 #include "mjx_policy.cuh"
 #include "mjx_replay.cuh"
+#include "mjx_invisible.cuh"
 #include "mjx_nn.cuh"
 #include "mjx_tables_host.h"
 
@@ -257,6 +258,19 @@ __global__ void __launch_bounds__(ENCS_WARPS * 32, 1) k_encode_store(EnvView V, 
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
+}
+
+// invisible (oracle) observation of every row of the step: one warp per row (csrc/mjx_invisible.cuh)
+__global__ void __launch_bounds__(128) k_encode_invisible(EnvView V, int version, float* __restrict__ out, int all_yama) {
+    const int lane = threadIdx.x & 31, gwarp = blockIdx.x * 4 + (threadIdx.x >> 5), nwarps = gridDim.x * 4;
+    const int n_rows = *V.n_rows, rows = oracle_obs_rows(version);
+    for (int row = gwarp; row < n_rows; row += nwarps)
+        encode_invisible(V.tables + V.row_table[row], V.row_seat[row] & 3, version, out + (size_t)row * rows * OBS_COLS, lane, all_yama != 0);
+}
+
+__global__ void k_set_seeds(TableState* tabs, int n, const u64* nonces, const u64* keys, int shuffle_kind) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) { tabs[t].nonce = nonces[t]; tabs[t].key = keys[t]; tabs[t].shuffle_kind = (u8)shuffle_kind; }
 }
 
 // ---- single-player tables: level-synchronous DP over all rows of the step (csrc/mjx_sp.cuh)
@@ -715,6 +729,17 @@ int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
     return launch_sp_block(env, obs_dev, st);
 }
 
+int mjx_oracle_obs_rows(int version) { return (version >= 1 && version <= 4) ? oracle_obs_rows(version) : MJX_ERR_ARG; }
+
+int mjx_env_encode_invisible(mjx_env* env, float* inv_dev, int version, void* stream) {
+    if (!env || !inv_dev || version < 1 || version > 4) return fail(MJX_ERR_ARG, "mjx_env_encode_invisible: bad arguments");
+    // a log replay follows dataset/invisible.rs (every tile left in the live wall), self-play follows board.rs:748-758
+    k_encode_invisible<<<g_sm_count * 8, 128, 0, (cudaStream_t)stream>>>(env->V, version, inv_dev, env->replay ? 1 : 0);
+    CU(cudaGetLastError());
+    env->launches += 1;
+    return MJX_OK;
+}
+
 int mjx_env_encode_obs_host(mjx_env* env, float* obs_dev, float* obs_host, uint8_t* masks_host, int* n_rows_out, void* stream) {
     int rc = mjx_env_encode_obs_host_begin(env, obs_dev, obs_host, masks_host, n_rows_out, stream);
     if (rc) return rc;
@@ -828,6 +853,20 @@ int mjx_env_create_replay(mjx_env** out, int n_jobs, const uint64_t* hdr, const 
     CU(cudaMemset(R.ky_seen, 0, sizeof(i32) * (size_t)n_jobs));
     R.hdr = d_hdr; R.kyoku = d_ky; R.ev_off = d_off; R.ev_cnt = d_cnt; R.ky_off = d_kyoff; R.player = d_pl;
     R.always_include_kan_select = always_include_kan_select ? 1 : 0;
+    return MJX_OK;
+}
+
+int mjx_env_replay_trust_seeds(mjx_env* env, const uint64_t* nonces_host, const uint64_t* keys_host, int shuffle_kind) {
+    if (!env || !env->replay || !nonces_host || !keys_host) return fail(MJX_ERR_ARG, "mjx_env_replay_trust_seeds: bad arguments");
+    if (!env->first) return fail(MJX_ERR_STATE, "mjx_env_replay_trust_seeds: must be called before the first mjx_env_replay_step");
+    if (shuffle_kind != 0 && shuffle_kind != 1) return fail(MJX_ERR_ARG, "mjx_env_replay_trust_seeds: shuffle_kind must be 0 or 1");
+    const size_t n = (size_t)env->n_tables;
+    CU(cudaMemcpy(env->d_nonces, nonces_host, sizeof(u64) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(env->d_keys, keys_host, sizeof(u64) * n, cudaMemcpyHostToDevice));
+    k_set_seeds<<<(env->n_tables + 127) / 128, 128>>>(env->V.tables, env->n_tables, env->d_nonces, env->d_keys, shuffle_kind);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    env->R.trust_seed = 1;
     return MJX_OK;
 }
 

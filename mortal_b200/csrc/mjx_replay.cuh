@@ -12,13 +12,14 @@
 namespace mjx {
 
 enum : u8 { LOG_START_GAME = 15, LOG_END_GAME = 16 };
+constexpr int REPLAY_KYOKU_WORDS = 19;  // start_kyoku payload: 2 score words + the 136-byte wall (unknown tiles = T_UNK)
 
 struct ReplayView {
     const u64* hdr;     // event words of all jobs, concatenated (one word per event)
     const i32* ev_off;  // [n_jobs] first event of the job
     const i32* ev_cnt;  // [n_jobs] number of events
-    const u64* kyoku;   // start_kyoku payloads, 9 words each (2 score words + 7 haipai words), concatenated
-    const i32* ky_off;  // [n_jobs] first payload (in units of 9 words) of the job
+    const u64* kyoku;   // start_kyoku payloads, REPLAY_KYOKU_WORDS each (2 score words + 17 wall words), concatenated
+    const i32* ky_off;  // [n_jobs] first payload (in units of REPLAY_KYOKU_WORDS) of the job
     i32* pos;           // [n_jobs] next event window to process
     i32* ky_idx;        // [n_jobs] end_kyoku events seen (gameplay.rs kyoku_idx)
     i32* ky_seen;       // [n_jobs] start_kyoku events applied (payload cursor)
@@ -26,6 +27,8 @@ struct ReplayView {
     i64* row_label;     // [row_cap] action label of each emitted row
     u8* row_meta;       // [row_cap, 4] at_kyoku, at_turn, shanten (as i8), apply_gamma
     i32 always_include_kan_select;
+    i32 trust_seed;     // the jobs carry their game's seed (TableState.nonce / key): regenerate every kyoku's wall from it
+                        // (dataset/invisible.rs:35-66), which the invisible observation needs; else hidden tiles stay unknown
 };
 
 MJX_D int lw_type(u64 w) { return (int)(w & 0xFF); }
@@ -49,13 +52,20 @@ MJX_DN void replay_apply(Ctx& c, const ReplayView& R, int job, u64 w) {
     switch (lw_type(w)) {
         case LOG_START_KYOKU: {
             if (MJX_IS_L0(c)) {
-                const u64* pay = R.kyoku + ((size_t)R.ky_off[job] + R.ky_seen[job]) * 9;
+                const u64* pay = R.kyoku + ((size_t)R.ky_off[job] + R.ky_seen[job]) * REPLAY_KYOKU_WORDS;
                 R.ky_seen[job] += 1;
                 S->kyoku = (u8)lw_c(w, 0); S->honba = (u8)lw_c(w, 1); S->kyotaku = (u8)lw_c(w, 2); S->oya = (u8)lw_c(w, 3);
                 S->scores[0] = (i32)(u32)pay[0]; S->scores[1] = (i32)(u32)(pay[0] >> 32);
                 S->scores[2] = (i32)(u32)pay[1]; S->scores[3] = (i32)(u32)(pay[1] >> 32);
-                for (int i = 0; i < 136; i++) S->wall[i] = T_UNK;
-                for (int i = 0; i < 52; i++) S->wall[i] = (u8)((pay[2 + i / 8] >> (8 * (i % 8))) & 0xFF);
+                // the wall as far as the caller knows it (haipai always; the hidden tiles when an invisible observation is wanted)
+                for (int i = 0; i < 136; i++) S->wall[i] = (u8)((pay[2 + i / 8] >> (8 * (i % 8))) & 0xFF);
+                if (R.trust_seed) {
+                    u8 hp[52];
+                    for (int i = 0; i < 52; i++) hp[i] = S->wall[i];
+                    make_wall(S->nonce, S->key, S->kyoku, S->honba, S->shuffle_kind, S->wall);
+                    for (int i = 0; i < 52; i++) if (S->wall[i] != hp[i] && S->err == 0) S->err = ERR_SEED_MISMATCH;  // not dealt from this seed
+                }
+                if (R.trust_seed && S->wall[60] != (u8)lw_pai(w) && S->err == 0) S->err = ERR_SEED_MISMATCH;
                 S->wall[60] = (u8)lw_pai(w);  // the first dora indicator; later ones arrive with their dora events
                 S->bflags = 0;
                 S->tiles_left = 70;
@@ -74,13 +84,17 @@ MJX_DN void replay_apply(Ctx& c, const ReplayView& R, int job, u64 w) {
             ev_start_kyoku(c);
             break;
         }
-        case LOG_TSUMO: ev_tsumo(c, lw_actor(w), lw_pai(w)); break;
+        case LOG_TSUMO:
+            // dataset/gameplay.rs:315-322: a draw after a kan comes from the rinshan (the invisible observation counts them)
+            MJX_L0(if (S->bflags & BF_DEAL_FROM_RINSHAN) { S->n_rinshan += 1; S->bflags &= (u16)~BF_DEAL_FROM_RINSHAN; });
+            ev_tsumo(c, lw_actor(w), lw_pai(w));
+            break;
         case LOG_DAHAI: ev_dahai(c, lw_actor(w), lw_pai(w), ((w >> 20) & 1) != 0); break;
         case LOG_CHI: ev_chi(c, lw_reaction(w, R_CHI)); break;
         case LOG_PON: ev_pon(c, lw_reaction(w, R_PON)); break;
-        case LOG_DAIMINKAN: ev_daiminkan(c, lw_reaction(w, R_DAIMINKAN)); MJX_L0(S->kans += 1); break;
-        case LOG_KAKAN: ev_kakan(c, lw_reaction(w, R_KAKAN)); MJX_L0(S->kans += 1); break;
-        case LOG_ANKAN: ev_ankan(c, lw_reaction(w, R_ANKAN)); MJX_L0(S->kans += 1); break;
+        case LOG_DAIMINKAN: ev_daiminkan(c, lw_reaction(w, R_DAIMINKAN)); MJX_L0(S->kans += 1; S->bflags |= BF_DEAL_FROM_RINSHAN); break;
+        case LOG_KAKAN: ev_kakan(c, lw_reaction(w, R_KAKAN)); MJX_L0(S->kans += 1; S->bflags |= BF_DEAL_FROM_RINSHAN); break;
+        case LOG_ANKAN: ev_ankan(c, lw_reaction(w, R_ANKAN)); MJX_L0(S->kans += 1; S->bflags |= BF_DEAL_FROM_RINSHAN); break;
         case LOG_DORA:
             MJX_L0(if (S->n_dora < 5) S->wall[60 - S->n_dora] = (u8)lw_pai(w));
             ev_dora(c);

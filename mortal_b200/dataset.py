@@ -6,8 +6,10 @@ always_include_kan_select, augmented)`, `.load_gz_log_files(filenames) -> list[l
 take_shantens / take_player_id`. The logs are replayed on device (csrc/mjx_replay.cuh) and the observations come from the
 same encoder kernels self-play uses. Differences, stated rather than hidden: `take_obs()` / `take_masks()` return ONE tensor
 per Gameplay ([n_moves, C, 34] float32 / [n_moves, 46] bool, CUDA by default, `host=True` for numpy) instead of a list of
-per-move arrays; the oracle (invisible) observation is not built (`oracle=True` raises NotImplementedError); logs must carry full information (no "?" tiles). `Grp` (dataset/grp.rs:19-164) is plain host-side
-log arithmetic and is provided in Python.
+per-move arrays (`take_invisible_obs()` likewise: [n_moves, 217 | 211, 34]); logs must carry full information (no "?" tiles).
+With `oracle=True` the hidden tiles come from the game seed when `trust_seed=True` (walls regenerated on device and checked
+against the logged deal) and otherwise from the log plus a random fill of the unseen tiles, as dataset/invisible.rs does.
+`Grp` (dataset/grp.rs:19-164) is plain host-side log arithmetic and is provided in Python.
 """
 from __future__ import annotations
 
@@ -81,9 +83,11 @@ class Grp:
 
 
 class Gameplay:
-    def __init__(self, player_id: int, player_name: str, obs, actions, masks, at_kyoku, apply_gamma, at_turns, shantens, grp=None):
+    def __init__(self, player_id: int, player_name: str, obs, actions, masks, at_kyoku, apply_gamma, at_turns, shantens, grp=None,
+                 invisible_obs=None):
         self.player_id, self.player_name = player_id, player_name
         self.grp = grp
+        self._invisible = invisible_obs
         self._obs, self._masks = obs, masks
         self._actions, self._at_kyoku, self._apply_gamma = actions, at_kyoku, apply_gamma
         self._at_turns, self._shantens = at_turns, shantens
@@ -96,8 +100,11 @@ class Gameplay:
     def take_masks(self, host: bool = False):
         return self._masks.cpu().numpy() if host else self._masks
 
-    def take_invisible_obs(self):
-        raise NotImplementedError("oracle (invisible) observations are not built (SURVEY.md §8f N4)")
+    def take_invisible_obs(self, host: bool = False):
+        """gameplay.rs:199-201: the invisible (oracle) observation of every move; only with GameplayLoader(oracle=True)"""
+        if self._invisible is None:
+            raise ValueError("the loader was created with oracle=False")
+        return self._invisible.cpu().numpy() if host else self._invisible
 
     def take_grp(self):
         return self.grp
@@ -125,11 +132,16 @@ class Gameplay:
 
 
 class GameplayLoader:
-    def __init__(self, version: int, *, oracle: bool = False, player_names=None, excludes=None, trust_seed: bool = False,
-                 always_include_kan_select: bool = True, augmented: bool = False, device: int = 0):
-        if oracle:
-            raise NotImplementedError("oracle (invisible) observations are not built (SURVEY.md §8f N4); pass oracle=False")
+    def __init__(self, version: int, *, oracle: bool = True, player_names=None, excludes=None, trust_seed: bool = False,
+                 always_include_kan_select: bool = True, augmented: bool = False, device: int = 0, shuffle_kind: int = 0, rng=None):
+        # gameplay.rs:80-113: same keywords and defaults (oracle = true, always_include_kan_select = true); `shuffle_kind` selects the
+        # wall shuffle of the seeds (see mjx_env_create), `rng` the numpy Generator behind the random fill of unseen tiles
+        if oracle and trust_seed and augmented:
+            raise NotImplementedError("oracle + trust_seed + augmented: the regenerated walls would not match the augmented events "
+                                      "(the reference mismatches them too, dataset/invisible.rs:51-66)")
         self.version, self.oracle, self.trust_seed = version, oracle, trust_seed
+        self.shuffle_kind = shuffle_kind
+        self.rng = rng if rng is not None else np.random.default_rng()
         self.player_names, self.excludes = list(player_names or []), list(excludes or [])
         self.always_include_kan_select, self.augmented = always_include_kan_select, augmented
         self.device = device
@@ -162,21 +174,35 @@ class GameplayLoader:
             if not ev or ev[0].get("type") != "start_game" or len(ev) < 4:
                 raise ValueError("empty or invalid game log")
         players = [self._players(ev[0].get("names", ["", "", "", ""])) for ev in games]
-        jobs = dataset_codec.build_jobs(games, players)
+        walls = None
+        if self.oracle and not self.trust_seed:  # dataset/invisible.rs:24-148: from the log, unseen tiles filled at random
+            walls = [dataset_codec.reconstruct_walls(ev, self.rng) for ev in games]
+        jobs = dataset_codec.build_jobs(games, players, walls)
         n_jobs = len(jobs["players"])
         out = [[] for _ in games]
         if n_jobs == 0:
             return out
         env = ReplayEnv(jobs, obs_version=self.version, always_include_kan_select=self.always_include_kan_select, device=self.device)
-        chunks = []  # per step: (job ids, obs, masks, labels, meta)
+        chunks = []  # per step: (job ids, obs, masks, labels, meta[, invisible obs])
         try:
+            if self.oracle and self.trust_seed:  # invisible.rs:35-66: the walls are those of the game's seed
+                seeds = []
+                for ev in games:
+                    sd = ev[0].get("seed")
+                    if sd is None:
+                        raise ValueError("trust_seed=True needs start_game.seed in every log")
+                    seeds.append((int(sd[0]), int(sd[1])))
+                env.trust_seeds([seeds[g][0] for g in jobs["job_game"]], [seeds[g][1] for g in jobs["job_game"]], self.shuffle_kind)
             while True:
                 env.replay_step()
                 nr = env.num_rows()
                 if nr:
                     obs = env.encode_obs()[:nr]
-                    chunks.append((env.row_table[:nr].long().clone(), obs.clone(), env.masks[:nr].clone(),
-                                   env.row_label[:nr].clone(), env.row_meta[:nr].clone()))
+                    chunk = (env.row_table[:nr].long().clone(), obs.clone(), env.masks[:nr].clone(),
+                             env.row_label[:nr].clone(), env.row_meta[:nr].clone())
+                    if self.oracle:
+                        chunk += (env.encode_invisible(self.version)[:nr].clone(),)
+                    chunks.append(chunk)
                 if env.num_live() == 0:
                     break
             res = env.results()
@@ -194,6 +220,7 @@ class GameplayLoader:
             job = torch.cat([c[0] for c in chunks]); obs = torch.cat([c[1] for c in chunks]); masks = torch.cat([c[2] for c in chunks])
             label = torch.cat([c[3] for c in chunks]); meta = torch.cat([c[4] for c in chunks])
             order = torch.sort(job, stable=True).indices  # moves of a job stay in emission order
+            inv = torch.cat([c[5] for c in chunks])[order] if self.oracle else None
             job, obs, masks, label, meta = job[order], obs[order], masks[order], label[order].cpu().numpy(), meta[order].cpu().numpy()
             counts = torch.bincount(job, minlength=n_jobs).cpu().numpy()
         else:
@@ -206,7 +233,7 @@ class GameplayLoader:
             name = games[g][0].get("names", ["", "", "", ""])[pid]
             if n:
                 gp = Gameplay(pid, name, obs[sl], label[sl], masks[sl], meta[sl, 0].copy(), meta[sl, 3].astype(bool),
-                              meta[sl, 1].copy(), meta[sl, 2].astype(np.int8), grp=grps[g])
+                              meta[sl, 1].copy(), meta[sl, 2].astype(np.int8), grp=grps[g], invisible_obs=None if inv is None else inv[sl])
             else:
                 z = np.zeros(0, dtype=np.uint8)
                 gp = Gameplay(pid, name, torch.zeros((0, env.obs_rows, 34), device=obs.device if chunks else "cpu"), np.zeros(0, dtype=np.int64),

@@ -133,15 +133,17 @@ class HostProtocolEngine:
         for attr in ("name", "version", "is_oracle", "enable_quick_eval", "enable_rule_based_agari_guard"):
             setattr(self, attr, getattr(engine, attr))
 
-    def react_host(self, obs_np: np.ndarray, masks_np: np.ndarray, idx: np.ndarray):
+    def react_host(self, obs_np: np.ndarray, masks_np: np.ndarray, idx: np.ndarray, inv_np=None):
         """rows `idx` of host arrays (views over pinned buffers filled by mjx_env_encode_obs_host) -> (actions, q, is_greedy) numpy,
         through the reference protocol: lists of per-row arrays in, lists out (agent/mortal.rs:126-152)."""
-        actions, q, _, greedy = self.engine.react_batch([obs_np[i] for i in idx], [masks_np[i] for i in idx], None)
+        invisible = None if inv_np is None else [inv_np[i] for i in idx]  # mortal.rs:137-146: Some(list) for oracle engines only
+        actions, q, _, greedy = self.engine.react_batch([obs_np[i] for i in idx], [masks_np[i] for i in idx], invisible)
         return np.asarray(actions, dtype=np.int64), np.asarray(q, dtype=np.float32), np.asarray(greedy, dtype=bool)
 
-    def react_device(self, obs: torch.Tensor, masks: torch.Tensor):
+    def react_device(self, obs: torch.Tensor, masks: torch.Tensor, invisible_obs=None):
         obs_h = obs.cpu().numpy()
         masks_h = masks.cpu().numpy()
-        actions, q, _, _ = self.engine.react_batch(list(obs_h), list(masks_h), None)
+        inv = None if invisible_obs is None else list(invisible_obs.cpu().numpy())
+        actions, q, _, _ = self.engine.react_batch(list(obs_h), list(masks_h), inv)
         dev = obs.device
         return torch.as_tensor(actions, dtype=torch.int64, device=dev), torch.as_tensor(q, dtype=torch.float32, device=dev)

@@ -120,6 +120,16 @@ class BatchEnv:
                    "mjx_env_encode_obs_host")
         return n.value
 
+    def encode_invisible(self, version: int = None):
+        """Invisible (oracle) observation of the current rows (board.rs:680-782): [row_cap, 211 | 217, 34] f32 on the device."""
+        version = self.obs_version if version is None else version
+        rows = self.L.mjx_oracle_obs_rows(version)
+        if getattr(self, "_inv", None) is None or self._inv.shape[1] != rows:
+            self._inv = self.torch.empty((self.row_cap, rows, 34), dtype=self.torch.float32, device=self.device)
+        _lib.check(self.L.mjx_env_encode_invisible(self._h, C.c_void_p(self._inv.data_ptr()), version, self._stream()),
+                   "mjx_env_encode_invisible")
+        return self._inv
+
     def encode_obs_host_begin(self, obs_host, masks_host) -> int:
         """Asynchronous half of encode_obs_host: enqueue encode + D2H and return num_rows as soon as it is known."""
         assert obs_host.dtype == self.torch.float32 and obs_host.is_contiguous() and not obs_host.is_cuda
@@ -277,6 +287,13 @@ class ReplayEnv(BatchEnv):
         self._bind_views()
         self.row_label = self._as_t(self.L.mjx_env_row_label(h), (self.row_cap,), "<i8")
         self.row_meta = self._as_t(self.L.mjx_env_row_meta(h), (self.row_cap, 4), "|u1")
+
+    def trust_seeds(self, nonces, keys, shuffle_kind: int = 0) -> None:
+        """Per-job game seeds (start_game.seed): walls are regenerated on device, which the invisible observation needs."""
+        n_ = np.ascontiguousarray(nonces, dtype=np.uint64)
+        k_ = np.ascontiguousarray(keys, dtype=np.uint64)
+        assert n_.shape == k_.shape == (self.n_tables,)
+        _lib.check(self.L.mjx_env_replay_trust_seeds(self._h, n_.ctypes.data, k_.ctypes.data, shuffle_kind), "mjx_env_replay_trust_seeds")
 
     def replay_step(self) -> None:
         _lib.check(self.L.mjx_env_replay_step(self._h, self._stream()), "mjx_env_replay_step")

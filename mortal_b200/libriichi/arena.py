@@ -138,6 +138,13 @@ class _Part:
             self.h_actions = pin(torch.zeros(env.row_cap, dtype=torch.int64))
             self.h_q = pin(torch.zeros((env.row_cap, 46), dtype=torch.float32)) if self.q_all is not None else None
             self.obs_np, self.masks_np = self.h_obs.numpy(), self.h_masks.numpy()
+        # agent/mortal.rs:253-255: engines with is_oracle also get the invisible observation (board.rs:680-782) of their rows
+        self.oracle = [bool(getattr(a, "is_oracle", False)) for a in agents]
+        self.version = version
+        self.h_inv = None
+        if any(self.oracle) and self.host_mode:
+            inv_rows = 211 if version == 1 else 217
+            self.h_inv = pin(torch.empty((env.row_cap, inv_rows, 34), dtype=torch.float32))
         self.first, self.cycles, self.nr = True, 0, 0
         self.recorded, self.recorded_masks = [], []
         self.mask_weights = (1 << torch.arange(46, dtype=torch.int64))
@@ -208,12 +215,17 @@ class _Part:
                 rs_h = env.row_seat[:nr].cpu().numpy()
                 chal_h = self.ic_host[tbl_h % self.per, rs_h & 3]
                 same = agents[0] is agents[1]
-                groups = ((np.arange(nr), agents[0]),) if same else ((np.nonzero(chal_h)[0], agents[0]), (np.nonzero(~chal_h)[0], agents[1]))
-                for idx, agent in groups:
+                groups = ((np.arange(nr), agents[0], self.oracle[0]),) if same else (
+                    (np.nonzero(chal_h)[0], agents[0], self.oracle[0]), (np.nonzero(~chal_h)[0], agents[1], self.oracle[1]))
+                inv_np = None
+                if self.h_inv is not None:
+                    self.h_inv[:nr].copy_(env.encode_invisible(self.version)[:nr])
+                    inv_np = self.h_inv.numpy()
+                for idx, agent, is_oracle in groups:
                     if idx.size == 0:
                         continue
                     t_eval = time.perf_counter_ns()
-                    a, q, greedy = agent.react_host(self.obs_np, self.masks_np, idx)
+                    a, q, greedy = agent.react_host(self.obs_np, self.masks_np, idx, inv_np if is_oracle else None)
                     if meta_rec is not None:
                         meta_rec.add_agent(cycles, torch.from_numpy(idx), torch.from_numpy(q).reshape(-1, 46), time.perf_counter_ns() - t_eval, greedy)
                     h_actions[torch.from_numpy(idx)] = torch.from_numpy(a)
@@ -234,14 +246,15 @@ class _Part:
             obs, masks = obs_buf[:nr], env.masks[:nr]
             tbl = env.row_table[:nr].long()
             seat = (env.row_seat[:nr] & 3).long()
+            inv = env.encode_invisible(self.version)[:nr] if any(self.oracle) else None
             if agents[0] is agents[1]:  # one engine for every seat: no gather of the rows, CUDA-graph replay when the engine has one
                 agent = agents[0]
                 t_eval = time.perf_counter_ns()
                 greedy = None
-                if hasattr(agent, "react_static") and not meta_rec:
+                if hasattr(agent, "react_static") and not meta_rec and not self.oracle[0]:
                     a, q = agent.react_static(obs_buf, env.masks, nr)
                 else:
-                    out = agent.react_device(obs, masks)
+                    out = agent.react_device(obs, masks, invisible_obs=inv) if self.oracle[0] else agent.react_device(obs, masks)
                     a, q = out[0], out[1]
                 self.actions[:nr] = a.to(torch.int64)
                 if self.q_all is not None:
@@ -250,11 +263,12 @@ class _Part:
                     meta_rec.add_agent(cycles, torch.arange(nr), q, time.perf_counter_ns() - t_eval, greedy)
             else:
                 chal = self.is_challenger[tbl % self.per, seat]
-                for idx, agent in ((chal.nonzero().squeeze(1), agents[0]), ((~chal).nonzero().squeeze(1), agents[1])):
+                for idx, agent, is_oracle in ((chal.nonzero().squeeze(1), agents[0], self.oracle[0]),
+                                              ((~chal).nonzero().squeeze(1), agents[1], self.oracle[1])):
                     if idx.numel() == 0:
                         continue
                     t_eval = time.perf_counter_ns()
-                    out = agent.react_device(obs[idx], masks[idx])
+                    out = agent.react_device(obs[idx], masks[idx], invisible_obs=inv[idx]) if is_oracle else agent.react_device(obs[idx], masks[idx])
                     a, q = out[0], out[1]
                     self.actions[idx] = a.to(torch.int64)
                     if self.q_all is not None:
@@ -315,8 +329,6 @@ class _Arena:
         else:
             agents = [_adapt(challenger), _adapt(champion)]
         for a in agents:
-            if getattr(a, "is_oracle", False):
-                raise NotImplementedError("oracle (invisible) observations are out of this round's scope")
             if getattr(a, "version", 4) not in (1, 2, 3, 4):
                 raise ValueError(f"unsupported obs version {a.version} (consts.rs:18 MAX_VERSION = 4)")
         versions = [int(getattr(a, "version", 4)) for a in agents]

@@ -184,6 +184,58 @@ void Board::init_from_wall(const u8* seq) {
 BoardState::BoardState(const Board& b) : board(b) {
     oya = board.kyoku % 4;
     for (int i = 0; i < 4; i++) player_states[i] = PlayerState((u8)i);
+    dora_indicators_full = board.dora_indicators;  // board.rs:127
+}
+
+int oracle_obs_rows(int version) {  // consts.rs:30-38
+    if (version == 1) return 211;
+    if (version >= 2 && version <= 4) return 217;
+    throw OrcError("unsupported version");
+}
+
+// board.rs:680-782
+void BoardState::encode_oracle_obs(u8 perspective, int version, float* out) const {
+    const int rows = oracle_obs_rows(version);
+    for (int i = 0; i < rows * 34; i++) out[i] = 0.f;
+    auto assign = [&](int r, int c, float v) { out[r * 34 + c] = v; };
+    auto fill = [&](int r, float v) { for (int c = 0; c < 34; c++) out[r * 34 + c] = v; };
+    int idx = 0;
+    for (int k = 1; k <= 3; k++) {  // .iter().cycle().skip(perspective + 1).take(3)
+        const PlayerState& st = player_states[(perspective + k) % 4];
+        for (int t = 0; t < 34; t++)
+            for (int c = 0; c < st.tehai[t]; c++) assign(idx + c, t, 1.f);  // assign_rows
+        idx += 4;
+        for (int i = 0; i < 3; i++) if (st.akas_in_hand[i]) fill(idx + i, 1.f);
+        idx += 3;
+        const int n = st.shanten;
+        if (version == 1) {
+            for (int i = 0; i < n; i++) fill(idx + i, 1.f);  // fill_rows
+            idx += 6;
+        } else {
+            fill(idx + n, 1.f);
+            idx += 7;
+            fill(idx, (float)n / 6.f);
+            idx += 1;
+        }
+        for (int t = 0; t < 34; t++) if (st.waits[t]) assign(idx, t, 1.f);
+        idx += 1;
+        if (st.at_furiten) fill(idx, 1.f);
+        idx += 1;
+    }
+    auto encode_tile = [&](int r, u8 tile) {
+        assign(r, deaka(tile), 1.f);
+        if (is_aka(tile)) fill(r + 1, 1.f);
+    };
+    {   // yama.iter().rev().take(tiles_left)
+        int taken = 0;
+        for (int i = (int)board.yama.size() - 1; i >= 0 && taken < tiles_left; i--, taken++) { encode_tile(idx, board.yama[i]); idx += 2; }
+        idx += (69 - (int)tiles_left) * 2;
+    }
+    for (int i = (int)board.rinshan.size() - 1; i >= 0; i--) { encode_tile(idx, board.rinshan[i]); idx += 2; }
+    idx += (4 - (int)board.rinshan.size()) * 2;
+    for (int i = (int)dora_indicators_full.size() - 1; i >= 0; i--) { encode_tile(idx, dora_indicators_full[i]); idx += 2; }
+    for (size_t i = 0; i < board.ura_indicators.size(); i++) { encode_tile(idx, board.ura_indicators[i]); idx += 2; }
+    ORC_ENSURE(idx == rows, "encode_oracle_obs: row cursor mismatch");
 }
 
 // board.rs:141-161
@@ -793,7 +845,7 @@ bool Game::commit(const AgentConfig cfgs[4], const PolicyFn pols[4], std::vector
         else need_kan_select = st.ankan_candidates.size() + st.kakan_candidates.size() > 1;
 
         Scene sc;
-        sc.table = table; sc.seat = seat; sc.step_idx = step_idx; sc.state = &st;
+        sc.table = table; sc.seat = seat; sc.step_idx = step_idx; sc.state = &st; sc.board = board;
         u8 mask[46];
         int kan_action = -1;
         if (need_kan_select) {

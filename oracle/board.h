@@ -54,8 +54,11 @@ struct BoardState {
     bool check_four_kan = false;
     int paos[4] = {-1, -1, -1, -1};
     std::vector<Event> log;
+    std::vector<u8> dora_indicators_full;  // board.rs:84: all five indicators as dealt, for encode_oracle_obs
 
     explicit BoardState(const Board& b);  // board.rs:125-137 into_state
+    // board.rs:680-782: the invisible (oracle) observation from `perspective`: [oracle_obs_rows(version)][34] f32, zero-filled here
+    void encode_oracle_obs(u8 perspective, int version, float* out) const;
     Poll poll(const Event reactions[4]);  // board.rs:141-161
     KyokuResult end() const;              // board.rs:172-182
 
@@ -86,7 +89,9 @@ struct Scene {
     bool is_kan_select = false;
     u64 step_idx = 0;  // table-step counter of this table (0-based)
     const PlayerState* state = nullptr;
+    const BoardState* board = nullptr;  // the full-information board (what an oracle agent's invisible_obs is encoded from)
 };
+int oracle_obs_rows(int version);  // consts.rs:30-38 oracle_obs_shape(version).0
 // policy: (scene, mask[46]) -> action id. q-values for the agari guard are optional.
 typedef std::function<int(const Scene&, const u8* mask46, float* q46_or_null)> PolicyFn;
 

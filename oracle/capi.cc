@@ -381,6 +381,16 @@ int orc_game_set_action(void* p, int seat, int action, int kan_action) {
         return 0;
     } catch (const std::exception& e) { return fail(e); }
 }
+int orc_oracle_obs_rows(int version) { try { return oracle_obs_rows(version); } catch (const std::exception& e) { return fail(e); } }
+// board.rs:680-782 encode_oracle_obs of the running kyoku from `perspective`
+int orc_game_encode_oracle_obs(void* p, int perspective, int version, float* out) {
+    try {
+        Game& g = static_cast<OrcGame*>(p)->g;
+        if (!g.board) throw OrcError("no running kyoku");
+        g.board->encode_oracle_obs((u8)perspective, version, out);
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
 void orc_game_advance_step(void* p) { static_cast<OrcGame*>(p)->g.step_idx++; }
 // finalises scores once the game has ended (game.rs:180-184)
 int orc_game_finish(void* p, int32_t* scores4) {
@@ -444,6 +454,7 @@ struct SampleSink {
     int64_t m = 0;
     int version = 4;
     float* obs_out = nullptr;
+    float* inv_out = nullptr;  // optional: the invisible (oracle) observation of the same decisions
     uint8_t* masks_out = nullptr;
     uint8_t* found = nullptr;
     int64_t find(const Scene& sc) const {
@@ -483,6 +494,8 @@ static void run_table(const orc_run_cfg& cfg, TableRun& tr, int t, int64_t until
                 const size_t stride = (size_t)obs_rows(sink->version) * 34;
                 sc.state->encode_obs(sink->version, sc.is_kan_select, sink->obs_out + (size_t)at * stride,
                                      sink->masks_out + (size_t)at * 46, cfg.sp_mode);
+                if (sink->inv_out && sc.board)
+                    sc.board->encode_oracle_obs(sc.seat, sink->version, sink->inv_out + (size_t)at * oracle_obs_rows(sink->version) * 34);
                 sink->found[at] = 1;
             }
         }
@@ -636,9 +649,10 @@ int orc_run_batch(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t
 // The same run, additionally encoding the decisions listed in `samples` (see SampleSink) with obs `version`.
 int orc_run_sample_obs(const orc_run_cfg* cfg, const uint64_t* nonces, const uint64_t* keys, int32_t* scores, uint8_t* ranks,
                        int32_t* steps, const int64_t* samples, int64_t m, int version, float* obs_out, uint8_t* masks_out,
-                       uint8_t* found) {
+                       uint8_t* found, float* inv_out) {
     SampleSink sink;
     sink.samples = samples; sink.m = m; sink.version = version; sink.obs_out = obs_out; sink.masks_out = masks_out; sink.found = found;
+    sink.inv_out = inv_out;
     return run_batch_impl(cfg, nonces, keys, nullptr, scores, ranks, steps, nullptr, 0, nullptr, nullptr, &sink);
 }
 
@@ -730,15 +744,92 @@ uint64_t orc_policy_hash(uint64_t nonce, uint64_t key, uint64_t table, uint64_t 
 // making, the observation, legal mask and the label derived from the following events. Not restated: the oracle
 // (invisible) observation, Grp and tile augmentation.
 // Outputs are caller-allocated for `max_moves` entries; returns the number of moves (negative on error).
+// dataset/invisible.rs Invisible (trust_seed branch: 35-66) + Invisible::encode (150-231): the hidden tiles of one kyoku,
+// early -> late, regenerated from the game's seed
+struct OrcInvisible {
+    std::vector<u8> yama, rinshan, dora_indicators, ura_indicators;
+    void encode(const PlayerState opp[3], size_t yama_idx, size_t rinshan_idx, int version, float* out) const {
+        const int rows = oracle_obs_rows(version);
+        for (int i = 0; i < rows * 34; i++) out[i] = 0.f;
+        auto assign = [&](int r, int c, float v) { out[r * 34 + c] = v; };
+        auto fill = [&](int r, float v) { for (int c = 0; c < 34; c++) out[r * 34 + c] = v; };
+        int idx = 0;
+        for (int k = 0; k < 3; k++) {
+            const PlayerState& st = opp[k];
+            for (int t = 0; t < 34; t++) for (int c = 0; c < st.tehai[t]; c++) assign(idx + c, t, 1.f);
+            idx += 4;
+            for (int i = 0; i < 3; i++) if (st.akas_in_hand[i]) fill(idx + i, 1.f);
+            idx += 3;
+            const int n = st.shanten;
+            if (version == 1) { for (int i = 0; i < n; i++) fill(idx + i, 1.f); idx += 6; }
+            else { fill(idx + n, 1.f); idx += 7; fill(idx, (float)n / 6.f); idx += 1; }
+            for (int t = 0; t < 34; t++) if (st.waits[t]) assign(idx, t, 1.f);
+            idx += 1;
+            if (st.at_furiten) fill(idx, 1.f);
+            idx += 1;
+        }
+        auto encode_tile = [&](int r, u8 tile) { assign(r, deaka(tile), 1.f); if (is_aka(tile)) fill(r + 1, 1.f); };
+        for (size_t i = yama_idx; i < yama.size(); i++) { encode_tile(idx, yama[i]); idx += 2; }
+        idx += ((int)yama_idx - 1) * 2;
+        for (size_t i = rinshan_idx; i < rinshan.size(); i++) { encode_tile(idx, rinshan[i]); idx += 2; }
+        idx += (int)rinshan_idx * 2;
+        for (u8 t : dora_indicators) { encode_tile(idx, t); idx += 2; }
+        for (u8 t : ura_indicators) { encode_tile(idx, t); idx += 2; }
+        if (idx != rows) throw OrcError("Invisible::encode: row cursor mismatch");
+    }
+};
+
+static int gameplay_load_impl(const orc_event* evs, int n_events, int player_id, int version, int always_include_kan_select, int sp_mode,
+                              int max_moves, float* obs, uint8_t* masks, int64_t* actions, uint8_t* at_kyoku, uint8_t* apply_gamma,
+                              uint8_t* at_turns, int8_t* shantens, bool oracle, uint64_t seed_nonce, uint64_t seed_key, int shuffle_kind,
+                              float* inv_out, const uint8_t* walls);
+
 int orc_gameplay_load(const orc_event* evs, int n_events, int player_id, int version, int always_include_kan_select, int sp_mode,
                       int max_moves, float* obs /*[max_moves, rows, 34] or null*/, uint8_t* masks /*[max_moves, 46]*/,
                       int64_t* actions, uint8_t* at_kyoku, uint8_t* apply_gamma, uint8_t* at_turns, int8_t* shantens) {
+    return gameplay_load_impl(evs, n_events, player_id, version, always_include_kan_select, sp_mode, max_moves, obs, masks, actions,
+                              at_kyoku, apply_gamma, at_turns, shantens, false, 0, 0, 0, nullptr, nullptr);
+}
+// the same with `oracle = true` (gameplay.rs:164, 308-331, 433-441): inv_out [max_moves, oracle_rows, 34]. The hidden tiles of
+// kyoku q come from walls[q][136] (board.rs:109-122 layout) when given — what Invisible::new reconstructs from the log plus its
+// random filler — else they are regenerated from the seed (`trust_seed`).
+int orc_gameplay_load_oracle(const orc_event* evs, int n_events, int player_id, int version, int always_include_kan_select, int sp_mode,
+                             int max_moves, float* obs, uint8_t* masks, int64_t* actions, uint8_t* at_kyoku, uint8_t* apply_gamma,
+                             uint8_t* at_turns, int8_t* shantens, uint64_t seed_nonce, uint64_t seed_key, int shuffle_kind, float* inv_out,
+                             const uint8_t* walls) {
+    return gameplay_load_impl(evs, n_events, player_id, version, always_include_kan_select, sp_mode, max_moves, obs, masks, actions,
+                              at_kyoku, apply_gamma, at_turns, shantens, true, seed_nonce, seed_key, shuffle_kind, inv_out, walls);
+}
+
+static int gameplay_load_impl(const orc_event* evs, int n_events, int player_id, int version, int always_include_kan_select, int sp_mode,
+                              int max_moves, float* obs, uint8_t* masks, int64_t* actions, uint8_t* at_kyoku, uint8_t* apply_gamma,
+                              uint8_t* at_turns, int8_t* shantens, bool oracle, uint64_t seed_nonce, uint64_t seed_key, int shuffle_kind,
+                              float* inv_out, const uint8_t* walls) {
     try {
         PlayerState state((u8)player_id);
         const int rows = obs_rows(version);
         int kyoku_idx = 0, n = 0;
         std::vector<Event> ev(n_events);
         for (int i = 0; i < n_events; i++) ev[i] = from_c(evs[i]);
+        // oracle: the three other seats' states (gameplay.rs:258-266) and the hidden tiles of every kyoku (invisible.rs:35-66)
+        PlayerState opp[3] = {PlayerState((u8)((player_id + 1) % 4)), PlayerState((u8)((player_id + 2) % 4)), PlayerState((u8)((player_id + 3) % 4))};
+        std::vector<OrcInvisible> invisibles;
+        bool from_rinshan = false;
+        size_t yama_idx = 0, rinshan_idx = 0;
+        const int orows = oracle ? oracle_obs_rows(version) : 0;
+        if (oracle)
+            for (const Event& e : ev)
+                if (e.type == EV_START_KYOKU) {
+                    u8 seq[136];
+                    if (walls) memcpy(seq, walls + invisibles.size() * 136, 136);
+                    else make_wall(seed_nonce, seed_key, (u8)(4 * (e.bakaze - T_E) + e.kyoku - 1), e.honba, shuffle_kind, seq);
+                    OrcInvisible iv;
+                    for (int i = 135; i >= 66; i--) iv.yama.push_back(seq[i]);
+                    for (int i = 55; i >= 52; i--) iv.rinshan.push_back(seq[i]);
+                    for (int i = 60; i >= 56; i--) iv.dora_indicators.push_back(seq[i]);
+                    for (int i = 61; i < 66; i++) iv.ura_indicators.push_back(seq[i]);
+                    invisibles.push_back(std::move(iv));
+                }
         auto add_entry = [&](bool at_kan_select, int label) {  // gameplay.rs:425-447
             if (n >= max_moves) throw OrcError("orc_gameplay_load: max_moves too small");
             std::vector<float> tmp;
@@ -750,6 +841,7 @@ int orc_gameplay_load(const orc_event* evs, int n_events, int player_id, int ver
             apply_gamma[n] = label <= 37;
             at_turns[n] = state.at_turn;
             shantens[n] = state.shanten;
+            if (oracle && inv_out) invisibles.at(kyoku_idx).encode(opp, yama_idx, rinshan_idx, version, inv_out + (size_t)n * orows * 34);
             n++;
         };
         // gameplay.rs:279-283: windows of 4 events
@@ -757,6 +849,12 @@ int orc_gameplay_load(const orc_event* evs, int n_events, int player_id, int ver
             const Event& cur = ev[w];
             const Event& next = (ev[w + 1].type == EV_REACH_ACCEPTED || ev[w + 1].type == EV_DORA) ? ev[w + 2] : ev[w + 1];
             if (cur.type == EV_END_KYOKU) kyoku_idx += 1;
+            if (oracle) {  // gameplay.rs:308-331
+                if (cur.type == EV_END_KYOKU) { from_rinshan = false; yama_idx = 0; rinshan_idx = 0; }
+                else if (cur.type == EV_TSUMO) { if (from_rinshan) { rinshan_idx++; from_rinshan = false; } else yama_idx++; }
+                else if (cur.type == EV_ANKAN || cur.type == EV_KAKAN || cur.type == EV_DAIMINKAN) from_rinshan = true;
+                for (auto& s : opp) s.update(cur);
+            }
             const ActionCandidate cans = state.update(cur);
             if (!cans.can_act()) continue;
             int label = -1, kan_select = -1;

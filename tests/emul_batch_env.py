@@ -70,6 +70,13 @@ class EmulBatchEnv:
             h_masks[:n] = self.masks[:n]
         return n
 
+    def encode_invisible(self, version=4):
+        n = self._e.num_rows()
+        out = torch.zeros((self.row_cap, 211 if version == 1 else 217, 34), dtype=torch.float32)
+        if n:
+            out[:n] = torch.from_numpy(self._e.encode_invisible(version))
+        return out
+
     def encode_obs_host_begin(self, h_obs, h_masks):
         return self.encode_obs_host(h_obs, h_masks)
 

@@ -48,6 +48,9 @@ def lib():
         L.emul_replay_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_env_errs.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_env_row_steps.argtypes = [C.c_void_p, C.c_void_p]
+        L.emul_env_encode_invisible.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.emul_replay_trust_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.emul_replay_encode_invisible.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.emul_env_enable_log.argtypes = [C.c_void_p, C.c_int]
         L.emul_env_read_log.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_env_log_lens.argtypes = [C.c_void_p, C.c_void_p]
@@ -134,6 +137,12 @@ class EmulEnv:
         assert (lens <= self._log_cap).all()
         return words, lens
 
+    def encode_invisible(self, version=4):
+        rows = 211 if version == 1 else 217
+        out = np.zeros((self.num_rows(), rows, 34), dtype=np.float32)
+        self.L.emul_env_encode_invisible(self._h, out.ctypes.data, version)
+        return out
+
     def encode_obs(self, sp=False, version=4):
         rows = {1: 938, 2: 942, 3: 934, 4: 1012}[version]
         obs = np.zeros((self.num_rows(), rows, 34), dtype=np.float32)
@@ -157,6 +166,15 @@ class EmulReplay(EmulEnv):
 
     def replay_step(self):
         self.live = self.L.emul_replay_step(self._h)
+
+    def trust_seeds(self, nonces, keys, shuffle_kind=0):
+        n_ = np.ascontiguousarray(nonces, dtype=np.uint64); k_ = np.ascontiguousarray(keys, dtype=np.uint64)
+        self.L.emul_replay_trust_seeds(self._h, n_.ctypes.data, k_.ctypes.data, shuffle_kind)
+
+    def encode_invisible(self, version=4):
+        out = np.zeros((self.num_rows(), 211 if version == 1 else 217, 34), dtype=np.float32)
+        self.L.emul_replay_encode_invisible(self._h, out.ctypes.data, version)
+        return out
 
     def row_labels(self):
         n = self.num_rows()

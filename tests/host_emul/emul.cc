@@ -8,6 +8,7 @@
 
 #include "mjx_sp.cuh"
 #include "mjx_replay.cuh"
+#include "mjx_invisible.cuh"
 #include "mjx_policy.cuh"
 #include "mjx_tables_host.h"
 
@@ -187,6 +188,17 @@ void* emul_replay_create(int n_jobs, const uint64_t* hdr, const int32_t* ev_off,
     R.always_include_kan_select = always_include_kan_select;
     return E;
 }
+void emul_replay_trust_seeds(void* p, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    for (int t = 0; t < E->n; t++) { E->tabs[t].nonce = nonces[t]; E->tabs[t].key = keys[t]; E->tabs[t].shuffle_kind = (u8)shuffle_kind; }
+    E->R.trust_seed = 1;
+}
+void emul_replay_encode_invisible(void* p, float* out, int version) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    const int rows = oracle_obs_rows(version);
+    for (int r = 0; r < E->n_rows[0]; r++)
+        encode_invisible(&E->tabs[E->row_table[r]], E->row_seat[r] & 3, version, out + (size_t)r * rows * OBS_COLS, 0, true);
+}
 int emul_replay_step(void* p) {
     EmulEnv* E = static_cast<EmulEnv*>(p);
     E->n_rows[0] = 0;
@@ -321,6 +333,13 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
     if (counters[2]) g_emul_sp_overflows++;
     sp_release(G, B);
     counters[2] = 0;
+}
+// invisible (oracle) observation of every current row: [n_rows, oracle_obs_rows(version), 34]
+void emul_env_encode_invisible(void* p, float* out, int version) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    const int rows = oracle_obs_rows(version);
+    for (int r = 0; r < E->n_rows[0]; r++)
+        encode_invisible(&E->tabs[E->row_table[r]], E->row_seat[r] & 3, version, out + (size_t)r * rows * OBS_COLS, 0);
 }
 void emul_env_results(void* p, int32_t* scores, uint8_t* ranks, int32_t* steps, int32_t* errs, int32_t* done) {
     EmulEnv* E = static_cast<EmulEnv*>(p);

@@ -194,6 +194,8 @@ def lib():
     L.orc_game_info.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_game_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.orc_gameplay_load.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
+    L.orc_gameplay_load_oracle.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
+                                           + [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p])
     L.orc_run_batch.argtypes = [C.POINTER(RunCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(RunOut)]
     L.orc_run_replay.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
@@ -201,7 +203,9 @@ def lib():
     L.orc_run_replay2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_run_sample_obs.argtypes = [C.POINTER(RunCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+                                     C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_oracle_obs_rows.argtypes = [C.c_int]
+    L.orc_game_encode_oracle_obs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.orc_batch_new.restype = C.c_void_p
     L.orc_batch_new.argtypes = [C.POINTER(RunCfg), C.c_void_p, C.c_void_p]
     L.orc_batch_free.argtypes = [C.c_void_p]
@@ -497,7 +501,7 @@ def run_replay(nonces, keys, replay, *, shuffle_kind=0, quick_eval=True, mask_bi
 
 
 def run_sample_obs(nonces, keys, samples, *, version=4, shuffle_kind=0, policy_kind=1, quick_eval=True, sp_mode=1,
-                   n_threads=1, max_steps=0):
+                   n_threads=1, max_steps=0, invisible=False):
     """Replay the tables with the built-in counter-based policy and encode the decisions listed in `samples`
     (int64 [m, 4] rows (table, step_idx, seat, kan_select)) -> (obs f32 [m, rows, 34], masks bool [m, 46], found bool [m]),
     in the order of `samples`."""
@@ -516,18 +520,23 @@ def run_sample_obs(nonces, keys, samples, *, version=4, shuffle_kind=0, policy_k
     ranks = np.zeros((n, 4), dtype=np.uint8)
     steps = np.zeros(n, dtype=np.int32)
     cfg = RunCfg(n, shuffle_kind, policy_kind, int(quick_eval), 0, 0, sp_mode, n_threads, max_steps, 0)
+    inv_obs = np.zeros((m, lib().orc_oracle_obs_rows(version), 34), dtype=np.float32) if invisible else None
     rc = lib().orc_run_sample_obs(C.byref(cfg), nonces.ctypes.data, keys.ctypes.data, scores.ctypes.data, ranks.ctypes.data,
                                   steps.ctypes.data, srt.ctypes.data, m, version, obs.ctypes.data, masks.ctypes.data,
-                                  found.ctypes.data)
+                                  found.ctypes.data, None if inv_obs is None else inv_obs.ctypes.data)
     if rc != 0:
         raise RuntimeError(err())
     inv = np.empty(m, dtype=np.int64)
     inv[order] = np.arange(m)
+    if invisible:
+        return obs[inv], masks[inv].astype(bool), found[inv].astype(bool), inv_obs[inv]
     return obs[inv], masks[inv].astype(bool), found[inv].astype(bool)
 
 
-def gameplay_load(events, player_id, *, version=4, always_include_kan_select=True, sp_mode=1, max_moves=2048, with_obs=True):
-    """dataset/gameplay.rs GameplayLoader for one (game, player): events = list of mjai dicts (start_game .. end_game)."""
+def gameplay_load(events, player_id, *, version=4, always_include_kan_select=True, sp_mode=1, max_moves=2048, with_obs=True,
+                  oracle_seed=None, shuffle_kind=0, walls=None):
+    """dataset/gameplay.rs GameplayLoader for one (game, player): events = list of mjai dicts (start_game .. end_game).
+    oracle_seed = (nonce, key): additionally the invisible observations of `oracle=True, trust_seed=True` ("invisible")."""
     evs = (OrcEvent * len(events))(*[event_from_json(e) for e in events])
     rows = {1: 938, 2: 942, 3: 934, 4: 1012}[version]
     obs = np.zeros((max_moves, rows, 34), dtype=np.float32) if with_obs else None
@@ -535,11 +544,23 @@ def gameplay_load(events, player_id, *, version=4, always_include_kan_select=Tru
     actions = np.zeros(max_moves, dtype=np.int64)
     at_kyoku = np.zeros(max_moves, dtype=np.uint8); gamma = np.zeros(max_moves, dtype=np.uint8)
     at_turns = np.zeros(max_moves, dtype=np.uint8); shantens = np.zeros(max_moves, dtype=np.int8)
-    n = lib().orc_gameplay_load(evs, len(events), player_id, version, int(always_include_kan_select), sp_mode, max_moves,
-                                obs.ctypes.data if with_obs else None, masks.ctypes.data, actions.ctypes.data,
-                                at_kyoku.ctypes.data, gamma.ctypes.data, at_turns.ctypes.data, shantens.ctypes.data)
+    inv = None
+    if walls is not None:
+        walls = np.ascontiguousarray(walls, dtype=np.uint8).reshape(-1, 136)
+        oracle_seed = oracle_seed or (0, 0)
+    if oracle_seed is None:
+        n = lib().orc_gameplay_load(evs, len(events), player_id, version, int(always_include_kan_select), sp_mode, max_moves,
+                                    obs.ctypes.data if with_obs else None, masks.ctypes.data, actions.ctypes.data,
+                                    at_kyoku.ctypes.data, gamma.ctypes.data, at_turns.ctypes.data, shantens.ctypes.data)
+    else:
+        inv = np.zeros((max_moves, lib().orc_oracle_obs_rows(version), 34), dtype=np.float32)
+        n = lib().orc_gameplay_load_oracle(evs, len(events), player_id, version, int(always_include_kan_select), sp_mode, max_moves,
+                                           obs.ctypes.data if with_obs else None, masks.ctypes.data, actions.ctypes.data,
+                                           at_kyoku.ctypes.data, gamma.ctypes.data, at_turns.ctypes.data, shantens.ctypes.data,
+                                           int(oracle_seed[0]), int(oracle_seed[1]), shuffle_kind, inv.ctypes.data,
+                                           None if walls is None else walls.ctypes.data)
     assert n >= 0, err()
-    return dict(obs=obs[:n] if with_obs else None, masks=masks[:n].astype(bool), actions=actions[:n], at_kyoku=at_kyoku[:n],
+    return dict(invisible=None if inv is None else inv[:n], obs=obs[:n] if with_obs else None, masks=masks[:n].astype(bool), actions=actions[:n], at_kyoku=at_kyoku[:n],
                 apply_gamma=gamma[:n].astype(bool), at_turns=at_turns[:n], shantens=shantens[:n])
 
 

@@ -428,11 +428,113 @@ def test_bench_engine_plays_policy_kind_2():
         if len(rt):
             obs = env.encode_obs(sp=False)
             got, q, m, greedy = eng.react_batch([obs[i] for i in range(len(rt))], [masks[i] for i in range(len(rt))], None)
-            assert got == want[: len(rt)].tolist(), (cycle, np.nonzero(np.array(got) != want[: len(rt)])[0][:5])
-            assert len(q) == len(rt) and len(q[0]) == 46 and m[0] == masks[0].tolist() and all(greedy)
+            assert list(got) == want[: len(rt)].tolist(), (cycle, np.nonzero(np.array(got) != want[: len(rt)])[0][:5])
+            assert len(q) == len(rt) and len(q[0]) == 46 and list(m[0]) == masks[0].tolist() and all(greedy)
             checked += len(rt)
         env.step(want)
         if env.num_live() == 0:
             break
     env.close()
     assert checked > 3000
+
+
+@pytest.mark.parametrize("version", [4, 1])
+def test_invisible_obs_parity_emulated(version):
+    """arena/board.rs:680-782 encode_oracle_obs: the device encoder (host-emulated) against the oracle's restatement at every
+    decision of seeded games played in lock step (hands / akas / shanten / waits / furiten of the three other seats, the
+    remaining wall in drawing order, rinshan, all dora and ura indicators)."""
+    n = 6
+    nonces = np.arange(880, 880 + n, dtype=np.uint64)
+    keys = np.full(n, 5, dtype=np.uint64)
+    env = E.EmulEnv(nonces, keys, enable_quick_eval=False)
+    L = O.lib()
+    games = [L.orc_game_new(int(nonces[t]), int(keys[t]), 0, t) for t in range(n)]
+    rows = L.orc_oracle_obs_rows(version)
+    checked = nonzero_wall = 0
+    try:
+        env.step(None)
+        for cycle in range(260):
+            rt, rs, masks = env.rows()
+            inv = env.encode_invisible(version)
+            acts = env.policy_test(1)
+            for t in range(n):
+                assert L.orc_game_poll(games[t]) >= 0, O.err()
+            chosen = {}
+            for r in range(len(rt)):
+                t, seat, kan = int(rt[r]), int(rs[r] & 3), bool(rs[r] & 4)
+                ref = np.zeros((rows, 34), dtype=np.float32)
+                assert L.orc_game_encode_oracle_obs(games[t], seat, version, ref.ctypes.data) == 0, O.err()
+                assert inv[r].shape == ref.shape
+                bad = np.argwhere(inv[r] != ref)
+                assert len(bad) == 0, (version, cycle, t, seat, bad[:6], inv[r][tuple(bad[0])], ref[tuple(bad[0])])
+                checked += 1
+                nonzero_wall += int(ref[51 if version != 1 else 45:].sum() > 0)
+                chosen[(t, seat, kan)] = int(acts[r])
+            for (t, seat, kan), a in chosen.items():
+                if kan:
+                    continue
+                ka = chosen.get((t, seat, True), -1)
+                assert L.orc_game_set_action(games[t], seat, a, ka if a == 42 else -1) == 0, O.err()
+            for t in range(n):
+                L.orc_game_advance_step(games[t])
+            env.step(acts)
+            if env.num_live() == 0:
+                break
+        assert checked > 1200 and nonzero_wall == checked
+    finally:
+        for g in games:
+            L.orc_game_free(g)
+        env.close()
+
+
+@pytest.mark.parametrize("trust_seed", [True, False])
+def test_log_replay_invisible_obs_match_gameplay_loader_emulated(trust_seed):
+    """GameplayLoader(oracle=True): the invisible observation of every move (dataset/invisible.rs Invisible::encode: every tile
+    left in the live wall, not just `tiles_left` of them) — with `trust_seed` the walls are regenerated from the game seed on
+    both sides; without it they are reconstructed from the log with a random fill of the unseen tiles (mortal_b200.dataset_codec
+    restates Invisible::new) and handed to both sides."""
+    from mortal_b200 import dataset_codec as DC
+
+    games = _selfplay_logs(4, 0, 1500)  # uniform policy: kans (rinshan draws) occur
+    rng = np.random.default_rng(3)
+    walls = None if trust_seed else [DC.reconstruct_walls(ev, rng) for ev in games]
+    if walls is not None:  # the reconstruction keeps what the log shows and fills the rest with exactly the unseen tiles
+        for ev, w in zip(games, walls):
+            assert len(w) == sum(e["type"] == "start_kyoku" for e in ev)
+            for q in range(len(w)):
+                assert np.bincount(w[q], minlength=37).tolist() == DC.new_unknown_tiles()
+    jobs = DC.build_jobs(games, [[0, 1, 2, 3]] * len(games), walls)
+    rep = E.EmulReplay(jobs)
+    if trust_seed:
+        seeds = [ev[0]["seed"] for ev in games]
+        rep.trust_seeds([seeds[g][0] for g in jobs["job_game"]], [seeds[g][1] for g in jobs["job_game"]])
+    inv_per = [[] for _ in range(rep.n_tables)]
+    for _ in range(3000):
+        rep.replay_step()
+        if rep.num_rows():
+            rt, _, _ = rep.rows()
+            inv = rep.encode_invisible(4)
+            for r in range(len(rt)):
+                inv_per[rt[r]].append(inv[r])
+        if rep.live == 0:
+            break
+    assert rep.live == 0 and (rep.errs() == 0).all()
+    kans = 0
+    for job in range(rep.n_tables):
+        g = jobs["job_game"][job]
+        ref = O.gameplay_load(games[g], int(jobs["players"][job]), with_obs=False, sp_mode=0,
+                              oracle_seed=tuple(games[g][0]["seed"]) if trust_seed else None, walls=None if trust_seed else walls[g])
+        got = np.array(inv_per[job])
+        assert got.shape == ref["invisible"].shape and got.shape[0] > 50
+        bad = np.argwhere(got != ref["invisible"])
+        assert len(bad) == 0, (job, bad[:5])
+        kans += int((ref["actions"] == 42).sum())
+    assert kans > 0
+    rep.close()
+    # a log replayed with the wrong seed fails loudly
+    if trust_seed:
+        rep = E.EmulReplay(DC.build_jobs(games[:1], [[0]]))
+        rep.trust_seeds([12345], [6789])
+        rep.replay_step()
+        assert (rep.errs() != 0).any()
+        rep.close()

@@ -599,3 +599,23 @@ def test_gameplay_loader_on_device_matches_oracle(mjx, tmp_path):
     assert moves > 8 * 4 * 100
     only_x = GameplayLoader(4, oracle=False, player_names=["x"]).load_gz_log_files(files[:2])
     assert [len(g) for g in only_x] == [1, 1] and only_x[0][0].player_name == "x"
+    # oracle=True (the reference's default): the invisible observation of every move. trust_seed: walls regenerated from
+    # start_game.seed on device; otherwise reconstructed from the log with a random fill (the same walls handed to the oracle)
+    orc = GameplayLoader(4, trust_seed=True).load_gz_log_files(files[:3])
+    for fn, per_player in zip(files[:3], orc):
+        events = DC.parse_log(gzip.open(fn, "rt").read())
+        for gp in per_player:
+            ref = O.gameplay_load(events, gp.take_player_id(), version=4, sp_mode=0, with_obs=False, oracle_seed=tuple(events[0]["seed"]))
+            inv = gp.take_invisible_obs(host=True)
+            assert inv.shape == ref["invisible"].shape and (inv == ref["invisible"]).all()
+            assert gp.take_actions() == ref["actions"].tolist()
+    rng = np.random.default_rng(11)
+    loader2 = GameplayLoader(4, trust_seed=False, rng=rng)
+    got2 = loader2.load_gz_log_files(files[:2])
+    rng_ref = np.random.default_rng(11)
+    for fn, per_player in zip(files[:2], got2):
+        events = DC.parse_log(gzip.open(fn, "rt").read())
+        walls = DC.reconstruct_walls(events, rng_ref)
+        for gp in per_player:
+            ref = O.gameplay_load(events, gp.take_player_id(), version=4, sp_mode=0, with_obs=False, walls=walls)
+            assert (gp.take_invisible_obs(host=True) == ref["invisible"]).all()

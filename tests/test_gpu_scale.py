@@ -54,14 +54,16 @@ def test_obs_parity_4096_tables_steady_state(mjx):
     for _ in range(ff):
         env.policy_test(1, actions)
         env.step(actions)
-    samples, got_obs, got_masks = [], [], []
+    samples, got_obs, got_masks, got_inv = [], [], [], []
     states = []
     for _ in range(steps):
         obs = env.encode_obs()
+        inv = env.encode_invisible()
         nr = env.num_rows()
         states.append(env.sp_stats()[0])
         pick = torch.randperm(nr, generator=gen)[:per_step].to(env.device)
         got_obs.append(obs[pick].cpu().numpy())
+        got_inv.append(inv[pick].cpu().numpy())
         got_masks.append(env.masks[pick].cpu().numpy())
         rs = env.row_seat[pick].long()
         samples.append(torch.stack([env.row_table[pick].long(), env.row_step[:nr].long()[pick], rs & 3, (rs >> 2) & 1], dim=1).cpu().numpy())
@@ -71,8 +73,10 @@ def test_obs_parity_4096_tables_steady_state(mjx):
     env.close()
     samples = np.concatenate(samples); got_obs = np.concatenate(got_obs); got_masks = np.concatenate(got_masks)
     assert len(samples) >= 2000 and min(states) > 100_000, (len(samples), states)  # the contended regime of the state arena
-    ref_obs, ref_masks, found = O.run_sample_obs(nonces, keys, samples, n_threads=NCPU, max_steps=ff + steps + 2)
+    ref_obs, ref_masks, found, ref_inv = O.run_sample_obs(nonces, keys, samples, n_threads=NCPU, max_steps=ff + steps + 2, invisible=True)
     assert found.all(), "the oracle never reached some sampled decisions: the trajectories differ"
+    got_inv = np.concatenate(got_inv)
+    assert got_inv.shape == ref_inv.shape == (len(samples), 217, 34) and (got_inv == ref_inv).all()  # board.rs:680-782, exact
     assert (ref_masks == got_masks).all()
     exact = np.ones(1012, dtype=bool)
     exact[EXP_ROWS] = False

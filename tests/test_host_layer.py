@@ -184,7 +184,7 @@ def test_event_codec_round_trip_on_golden_and_selfplay_logs():
         golden = [{k: v for k, v in json.loads(ln).items() if k != "meta"} for ln in f if ln.strip()]
     for events in [golden] + _selfplay_logs(3, 0, 77):
         hdr, pay = DC.encode_events(events)
-        assert len(hdr) == len(events) and pay.shape == (sum(e["type"] == "start_kyoku" for e in events), 9)
+        assert len(hdr) == len(events) and pay.shape == (sum(e["type"] == "start_kyoku" for e in events), DC.KYOKU_WORDS)
         # re-expand into the multi-word stream decode_events reads (payload after each start_kyoku, zero deltas after hora/ryukyoku)
         words, k = [], 0
         for w in hdr:
@@ -193,7 +193,7 @@ def test_event_codec_round_trip_on_golden_and_selfplay_logs():
                 continue
             words.append(int(w))
             if ty == mjai_log.START_KYOKU:
-                words += [int(x) for x in pay[k]]
+                words += [int(x) for x in pay[k][:9]]  # the device log carries scores + the 52 dealt tiles only
                 k += 1
             elif ty in (mjai_log.HORA, mjai_log.RYUKYOKU):
                 words += [0, 0]
@@ -402,3 +402,39 @@ def test_reference_mortal_engine_and_model_drop_in_unchanged():
     for i in range(4):
         hist[int(ref["ranks"][i, i % 4])] += 1
     assert hist == rankings
+
+
+def test_arena_feeds_oracle_engines_the_invisible_observation():
+    """agent/mortal.rs:253-255, 137-146: an engine with is_oracle=True receives invisible_obs (list of (217, 34) arrays, one per row)
+    next to obs and masks; an ordinary engine receives None. Checked on the host-emulated environment: the other seats' hand
+    planes of the invisible observation hold 13/14-tile hands and the wall planes are populated."""
+    from mortal_b200.libriichi.arena import OneVsThree
+
+    seen = dict(oracle_rows=0, plain_calls=0)
+
+    class Eng:
+        engine_type = "mortal"; version = 4; enable_quick_eval = True; enable_rule_based_agari_guard = False
+
+        def __init__(self, name, is_oracle):
+            self.name, self.is_oracle = name, is_oracle
+
+        def react_batch(self, obs, masks, invisible_obs):
+            m = np.stack(masks)
+            if self.is_oracle:
+                assert invisible_obs is not None and len(invisible_obs) == len(obs)
+                for iv in invisible_obs:
+                    assert iv.shape == (217, 34) and iv.dtype == np.float32
+                    for k in range(3):  # 4 count planes per opponent: a 13- or 14-tile hand minus its melds
+                        assert iv[17 * k:17 * k + 4].sum() in (1, 2, 4, 5, 7, 8, 10, 11, 13, 14)
+                    assert iv[51:51 + 138].sum() > 0
+                seen["oracle_rows"] += len(obs)
+            else:
+                assert invisible_obs is None
+                seen["plain_calls"] += 1
+            a = [int(np.nonzero(r)[0][0]) for r in m]
+            return a, np.where(m, 0.0, -np.inf).tolist(), m.tolist(), [True] * len(a)
+
+    arena = _emul_arena(OneVsThree)
+    arena.max_cycles = 40
+    arena.py_vs_py(Eng("o", True), Eng("p", False), (7100, 2), 2)
+    assert seen["oracle_rows"] > 20 and seen["plain_calls"] > 20
