@@ -399,8 +399,8 @@ def run_ours(args):
         env.policy_test(2, actions)
         return 0
 
-    # -------- the product path: libriichi.arena.OneVsThree.py_vs_py (two half-batches stepped alternately, csrc kernels of one half
-    # overlapping the engine of the other), timed between two cycle hooks
+    # -------- the product path: libriichi.arena.OneVsThree.py_vs_py (for host-protocol engines two half-batches stepped alternately:
+    # kernels + D2H of one half overlap the engine's host work on the other), timed between two cycle hooks
     def run_arena(agent, n_warm, n_timed, pipeline=True):
         arena = OneVsThree(disable_progress_bar=True)
         arena.pipeline = pipeline
@@ -568,9 +568,10 @@ def run_ours(args):
             # the timed step split with CUDA events (rank 0): env kernels (k_step + encode + single-player block, whose cost
             # depends on the positions the policy steers the tables into) and the policy network incl. the row-count sync
             "step_breakdown_ms": {"env": a_env_ms, "policy_net": a_nn_ms, "sequential_total": a_ms / K, "pipelined_total": av_ms / K,
-                                  "note": "`value` runs OneVsThree.py_vs_py with the DeviceEngine for all seats: two half-batches on two CUDA streams, "
-                                          "the env kernels of one half overlapping the policy net of the other; env / policy_net are the same "
-                                          "workload run as ONE batch on one stream (CUDA events), whose throughput is value_sequential"},
+                                  "note": "`value` runs OneVsThree.py_vs_py with the DeviceEngine for all seats (one batch, one stream, CUDA-graph "
+                                          "forward); env / policy_net split the same workload driven by bench.py's own loop (CUDA events), whose "
+                                          "throughput is value_sequential. Two half-batches on two streams were measured SLOWER for device engines "
+                                          "(208 K vs 252 K table-steps/s): the arena pipelines half-batches for host-protocol engines only (e2e)"},
             "value_sequential": a_units / (a_ms * 1e-3),
             "env_only": {"value": b_units / (b_ms * 1e-3), "unit": "table-steps/s", "ms_per_step": b_ms / K,
                          "policy": "device test policy kind 2 (mask-hash; the CPU arm's and the e2e engine's policy), no host sync",

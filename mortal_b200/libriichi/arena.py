@@ -6,9 +6,9 @@ one_vs_three.rs:140-191 (game g = 4*s + r uses seed (seed_start[0] + s, seed_sta
 sits at absolute seat r). The step loop is BatchGame::run (game.rs:286-304) executed by mjx kernels;
 engines are called once per cycle per agent like MortalBatchAgent::evaluate (mortal.rs:114-159).
 
-Tables are independent, so the batch is played as TWO half-batches stepped alternately (`pipeline`): while the engines
-work on the rows of one half (on the host for reference-protocol engines, on the tensor cores for device engines) the
-environment kernels and the D2H copies of the other half run. Results are those of one batch.
+Tables are independent, so for reference-protocol engines (react_batch over host arrays) the batch is played as TWO half-batches
+stepped alternately (`pipeline`): while an engine works on the rows of one half on the host, the environment kernels and the
+D2H copies of the other half run. Results are those of one batch. Device engines run the batch as one.
 """
 from __future__ import annotations
 
@@ -342,9 +342,12 @@ class _Arena:
         n = seed_count * per
         nonces = np.repeat(np.arange(seed_start[0], seed_start[0] + seed_count, dtype=np.uint64), per)
         keys = np.full(n, seed_start[1], dtype=np.uint64)
-        # the seat rotations of a seed stay together; two parts when there is something to overlap
+        # the seat rotations of a seed stay together; two parts when there is something to overlap: host-side engines (their
+        # numpy / list work and the D2H copies of the other half). Device engines already keep the GPU busy back to back — two
+        # half-size forward passes on two streams measured slower than one full-size pass (profiles/r02_summary.md).
         cuts = [0, n]
-        if self.pipeline and seed_count >= 2:
+        host_engines = all(isinstance(a, HostProtocolEngine) for a in agents)
+        if self.pipeline and host_engines and seed_count >= 2:
             cuts = [0, (seed_count // 2) * per, n]
         parts = []
         try:
