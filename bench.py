@@ -402,7 +402,7 @@ def run_ours(args):
     # -------- the product path: libriichi.arena.OneVsThree.py_vs_py (for host-protocol engines two half-batches stepped alternately:
     # kernels + D2H of one half overlap the engine's host work on the other), timed between two cycle hooks
     def run_arena(agent, n_warm, n_timed, pipeline=True):
-        arena = OneVsThree(disable_progress_bar=True)
+        arena = OneVsThree(disable_progress_bar=True, device=local_rank)
         arena.pipeline = pipeline
         arena.fast_forward_steps = args.skip
         arena.max_cycles = n_warm + n_timed + 1  # the hook of cycle n_warm + n_timed must fire
