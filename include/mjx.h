@@ -76,6 +76,11 @@ int mjx_env_encode_obs_host_finish(mjx_env* env);
 int mjx_oracle_obs_rows(int version);
 int mjx_env_encode_invisible(mjx_env* env, float* inv_dev, int version, void* stream);
 
+/* Switch the observation version the encoder entry points produce (consts.rs:20-28; obs buffers must then hold
+ * mjx_obs_rows(version) rows per observation). agent/mortal.rs:54-74: every agent has its own `version`; a PlayerState encodes
+ * any version on request (obs_repr.rs:780). */
+int mjx_env_set_obs_version(mjx_env* env, int version);
+
 /* state/agent_helper.rs:509-593 single_player_tables (obs v4 rows 889-1011): on by default; `enable = 0`
  * leaves the block zero (the reference has no such switch; it exists for profiling the rest of the encoder).
  * mjx_env_sp_overflows: number of steps so far in which the state arena (2048 states per table on average)
@@ -126,6 +131,50 @@ int mjx_env_replay_step(mjx_env* env, void* stream);
 int mjx_env_replay_trust_seeds(mjx_env* env, const uint64_t* nonces_host, const uint64_t* keys_host, int shuffle_kind);
 int64_t* mjx_env_row_label(mjx_env* env); /* int64 [row_cap] device */
 uint8_t* mjx_env_row_meta(mjx_env* env);  /* uint8 [row_cap, 4] device: at_kyoku, at_turn, shanten (int8), apply_gamma */
+
+/* ---- libriichi.state.PlayerState (state/player_state.rs:143-264, state/getter.rs:6-156, state/obs_repr.rs:776-791) ---------
+ * A batch of n independent single-seat states: table records in single-seat mode (other seats' hidden tiles are `?` = 37), updated
+ * by the same device event handlers self-play uses. `mjx_state_create` returns an mjx_env whose encoder entry points
+ * (mjx_env_encode_obs, mjx_env_masks, mjx_env_encode_obs_host ...) work on the rows mjx_state_rows prepares.
+ *   mjx_state_update  PlayerState::update (update.rs:24-122): one event per state as a 64-bit word (csrc/mjx_step.cuh log_word;
+ *                     mortal_b200/dataset_codec.py encodes mjai JSON), start_kyoku with its 19-word payload (scores + wall, see
+ *                     mjx_env_create_replay); word 0 = no event for that state. cans_host[i] = the ActionCandidate of state i
+ *                     (action.rs:11-40: bit k = the k-th can_* flag in declaration order, target_actor << 16).
+ *   mjx_state_view    every getter of state/getter.rs plus the fields state/test.rs asserts, for one state.
+ *   mjx_state_rows    one decision row per state (kan-select rows where at_kan_select_host[i] != 0): row i = state i.
+ *   mjx_state_query   what = 0 agent_helper.rs:377-462 agari_points(is_ron = args[0], ura tiles args[2 .. 2 + args[1]))
+ *                              -> out = {ron, tsumo_ko, tsumo_oya, ok};  1 rule_based_agari (agent_helper.rs:262-368) -> out[0];
+ *                     2 discard_candidates_aka (agent_helper.rs:35-79) -> out[0..1] = 37-bit mask (low, high word);
+ *                     3 discard_candidates_with_unconditional_tenpai (agent_helper.rs:88-197) -> 34-bit mask;
+ *                     4 agent/mortal.rs:338-573 action id -> reaction: args = {action, kan_select_action or -1}
+ *                              -> out[0..1] = the event word (low, high), out[2] = 0 or an error code. */
+typedef struct mjx_player_view {
+    uint8_t tehai[34], waits[34], dora_factor[34], tiles_seen[34], keep_shanten_discards[34], next_shanten_discards[34],
+        forbidden_tiles[34], discarded_tiles[34];
+    uint8_t akas_seen[3], akas_in_hand[3];
+    uint8_t bakaze, jikaze, kyoku, honba, kyotaku, rank, oya, is_all_last;
+    int32_t scores[4];                       /* rotated: [0] = self */
+    uint8_t n_dora_indicators, dora_indicators[5];
+    uint8_t riichi_declared[4], riichi_accepted[4];  /* relative seats */
+    uint8_t at_turn, tiles_left;
+    int8_t shanten, real_time_shanten;
+    uint8_t has_last_self_tsumo, last_self_tsumo, has_last_kawa_tile, last_kawa_tile;
+    uint32_t cans;
+    uint8_t n_ankan_candidates, ankan_candidates[3], n_kakan_candidates, kakan_candidates[3];
+    uint8_t chankan_chance, can_w_riichi, is_w_riichi, at_rinshan, at_ippatsu, at_furiten, to_mark_same_cycle_furiten,
+        kans_on_board, is_menzen;
+    uint8_t n_chis, chis[4], n_pons, pons[4], n_minkans, minkans[4], n_ankans, ankans[4];
+    uint8_t doras_owned[4], doras_seen, tehai_len_div3, has_next_shanten_discard;
+    uint8_t kawa_len[4];
+    uint8_t viewer, pad_[3];
+    int32_t err;                             /* 0, or the code of the inconsistency the last events produced */
+} mjx_player_view;
+int mjx_state_create(mjx_env** out, int n, const uint8_t* player_ids_host, int obs_version);
+int mjx_state_update(mjx_env* env, const uint64_t* words_host, const uint64_t* payload_host, uint32_t* cans_host);
+int mjx_state_view(mjx_env* env, int index, mjx_player_view* out_host);
+int mjx_state_rows(mjx_env* env, const uint8_t* at_kan_select_host, void* stream);
+int mjx_state_query(mjx_env* env, int index, int what, const int32_t* args, int32_t* out);
+int mjx_state_copy(mjx_env* dst, int dst_index, mjx_env* src, int src_index); /* PlayerState: Clone */
 
 /* Instrumentation for bench.py's roofline: when enabled, mjx_env_encode_obs brackets its two encoder kernels with CUDA events
  * on the launch stream; mjx_env_last_encode_ms (blocking) returns the durations of k_encode_features and k_encode_store. */

@@ -10,6 +10,7 @@
 #include "mjx_policy.cuh"
 #include "mjx_replay.cuh"
 #include "mjx_invisible.cuh"
+#include "mjx_state.cuh"
 #include "mjx_nn.cuh"
 #include "mjx_tables_host.h"
 
@@ -273,6 +274,98 @@ __global__ void k_set_seeds(TableState* tabs, int n, const u64* nonces, const u6
     if (t < n) { tabs[t].nonce = nonces[t]; tabs[t].key = keys[t]; tabs[t].shuffle_kind = (u8)shuffle_kind; }
 }
 
+// ---- libriichi.state.PlayerState batch (csrc/mjx_state.cuh): one warp = one state, record staged in shared memory
+#define STATE_KERNEL_PROLOGUE                                                                                     \
+    __shared__ __align__(16) unsigned char s_tab[STEP_WARPS][sizeof(TableState)];                                \
+    __shared__ WarpScratch s_scratch[STEP_WARPS];                                                                 \
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                                   \
+    const int i = blockIdx.x * STEP_WARPS + warp;                                                                 \
+    if (i >= V.n_tables) return;                                                                                  \
+    TableState* g = V.tables + i;                                                                                 \
+    constexpr int NV = sizeof(TableState) / 16;                                                                   \
+    uint4* dst = reinterpret_cast<uint4*>(s_tab[warp]);                                                           \
+    for (int q = lane; q < NV; q += 32) dst[q] = reinterpret_cast<const uint4*>(g)[q];                            \
+    __syncwarp();                                                                                                 \
+    Ctx c; c.S = reinterpret_cast<TableState*>(s_tab[warp]); c.W = &s_scratch[warp]; c.T = T; c.lane = lane;     \
+    c.df = s_scratch[warp].dora_factor;                                                                           \
+    recompute_dora_factor(c);
+
+__global__ void k_state_init(TableState* tabs, int n, const u8* player_ids) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) { tabs[t].viewer1 = (u8)(player_ids[t] + 1); tabs[t].gflags = GF_ALIVE; tabs[t].last_kawa_tile = T_NONE;
+                 for (int s = 0; s < 4; s++) tabs[t].priv[s].last_self_tsumo = T_NONE; }
+}
+
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_state_update(EnvView V, Tables T, const u64* __restrict__ words,
+                                                                    const u64* __restrict__ payload, u32* __restrict__ cans) {
+    STATE_KERNEL_PROLOGUE
+    const u64 w = words[i];
+    const int p = c.S->viewer1 - 1;
+    if (w != 0) {
+        apply_event(c, w, payload ? payload + (size_t)i * REPLAY_KYOKU_WORDS : nullptr, false);
+        __syncwarp();
+        for (int q = lane; q < NV; q += 32) reinterpret_cast<uint4*>(g)[q] = dst[q];
+    }
+    if (lane == 0) cans[i] = (u32)c.S->priv[p].cans | ((u32)c.S->priv[p].target_actor << 16);
+}
+
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_state_view(EnvView V, Tables T, int index, mjx_player_view* out) {
+    STATE_KERNEL_PROLOGUE
+    if (i != index) return;
+    if (lane == 0) state_view(c, c.S->viewer1 - 1, out);
+}
+
+// one decision row per state: row i = state i (obs_repr.rs:776-790 encode_obs(version, at_kan_select))
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_state_rows(EnvView V, Tables T, const u8* __restrict__ at_kan_select) {
+    STATE_KERNEL_PROLOGUE
+    const int p = c.S->viewer1 - 1;
+    const bool kan = at_kan_select && at_kan_select[i];
+    const u16 cans_bits = c.S->priv[p].cans;
+    const u64 discards = (cans_bits & CAN_DISCARD) ? discard_candidates(c, p) : 0;
+    write_mask_row(c, V, i, legal_mask(c, p, kan, discards));
+    if (lane == 0) { V.row_table[i] = i; V.row_seat[i] = (u8)(p | (kan ? 4 : 0)); V.row_step[i] = 0; if (i == 0) *V.n_rows = V.n_tables; }
+}
+
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_state_query(EnvView V, Tables T, int index, int what, const i32* __restrict__ args,
+                                                                   i32* __restrict__ out) {
+    STATE_KERNEL_PROLOGUE
+    if (i != index) return;
+    const int p = c.S->viewer1 - 1;
+    if (what == 0) {
+        u8 ura[5];
+        const int n_ura = min(max(args[1], 0), 5);
+        for (int k = 0; k < n_ura; k++) ura[k] = (u8)args[2 + k];
+        bool ok;
+        const Point pt = agari_points_ura(c, p, args[0] != 0, ura, n_ura, &ok);
+        if (lane == 0) { out[0] = pt.ron; out[1] = pt.tsumo_ko; out[2] = pt.tsumo_oya; out[3] = ok ? 1 : 0; }
+    } else if (what == 1) {
+        const bool r = rule_based_agari(c, p);
+        if (lane == 0) out[0] = r ? 1 : 0;
+    } else if (what == 2) {
+        const u64 m = discard_candidates(c, p);
+        if (lane == 0) { out[0] = (i32)(u32)m; out[1] = (i32)(u32)(m >> 32); }
+    } else if (what == 3) {
+        EncCtx e; e.S = c.S; e.T = T; e.bm = nullptr; e.sv = nullptr; e.seat = p; e.kan_select = false; e.lane = lane;
+        e.dora_factor = c.df; e.parts = 0;
+        const u64 m = unconditional_tenpai_discards(e, c);
+        if (lane == 0) { out[0] = (i32)(u32)m; out[1] = (i32)(u32)(m >> 32); }
+    } else if (what == 4) {
+        Reaction r;
+        i32 err = 0;
+        const bool okd = decode_action(c.S, p, args[0], args[1], r, &err);
+        if (lane == 0) {
+            u64 w = 0;
+            if (okd) {
+                const int ty = r.type == R_DAHAI ? LOG_DAHAI : r.type == R_CHI ? LOG_CHI : r.type == R_PON ? LOG_PON :
+                               r.type == R_DAIMINKAN ? LOG_DAIMINKAN : r.type == R_KAKAN ? LOG_KAKAN : r.type == R_ANKAN ? LOG_ANKAN :
+                               r.type == R_REACH ? LOG_REACH : r.type == R_HORA ? LOG_HORA : r.type == R_RYUKYOKU ? LOG_RYUKYOKU : 0;
+                w = log_word(ty, r.actor, r.target, r.pai, r.tsumogiri, 0, r.consumed[0], r.consumed[1], r.consumed[2], r.consumed[3], 0);
+            }
+            out[0] = (i32)(u32)w; out[1] = (i32)(u32)(w >> 32); out[2] = okd ? 0 : (err ? err : ERR_ILLEGAL_ACTION);
+        }
+    }
+}
+
 // ---- single-player tables: level-synchronous DP over all rows of the step (csrc/mjx_sp.cuh)
 constexpr int SP_WARPS = 4;
 constexpr int MJX_HOST_COPY_GROUPS = 4;  // mjx_env_encode_obs_host: row groups of the SP block / D2H pipeline
@@ -464,7 +557,7 @@ struct mjx_env {
     i64* d_dummy_actions = nullptr;
     u8* d_guard = nullptr;
     SpGlobal sp;
-    int sp_enabled = 1;
+    int sp_enabled = 1, sp_wanted = 1;
     unsigned char* d_compact = nullptr;
     cudaEvent_t ev_enc[3] = {nullptr, nullptr, nullptr};  // optional per-kernel timing of the encoder pair (bench.py roofline)
     bool time_encode = false;
@@ -475,7 +568,19 @@ struct mjx_env {
     cudaStream_t copy_stream = nullptr;  // mjx_env_encode_obs_host: D2H overlapped with the SP kernels
     cudaEvent_t ev_rows = nullptr, ev_sp = nullptr, ev_grp[MJX_HOST_COPY_GROUPS] = {};
     long long launches = 0;  // kernels launched on behalf of this env (bench.py's gpu_launches)
+    bool is_state = false;   // mjx_state_create: a batch of single-seat PlayerStates
+    u64 *d_state_words = nullptr, *d_state_pay = nullptr;
+    u32* d_state_cans = nullptr;
+    unsigned char* d_state_misc = nullptr;
 };
+
+static void set_enc_args(mjx_env* env, int version) {
+    const ObsLayout L = make_layout(version);
+    env->enc_args.rows = L.rows; env->enc_args.bm_rows = L.bm_rows; env->enc_args.n_sv = L.n_sv;
+    env->enc_args.compact_bytes = L.bm_rows * 8 + L.n_sv * OBS_COLS * 4;
+    env->enc_args.n_slices = (L.rows + OBS_SLICE_ROWS - 1) / OBS_SLICE_ROWS;
+    env->enc_args.ver = version;
+}
 
 template <int VER>
 static void launch_features(mjx_env* env, cudaStream_t st) {
@@ -579,12 +684,13 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
     CU(cudaMalloc(&env->d_dummy_actions, sizeof(i64) * cap));
     memset(&env->sp, 0, sizeof env->sp);
     {
-        const ObsLayout L = make_layout(obs_version);
-        env->enc_args.rows = L.rows; env->enc_args.bm_rows = L.bm_rows; env->enc_args.n_sv = L.n_sv;
-        env->enc_args.compact_bytes = L.bm_rows * 8 + L.n_sv * OBS_COLS * 4;
-        env->enc_args.n_slices = (L.rows + OBS_SLICE_ROWS - 1) / OBS_SLICE_ROWS;
-        env->enc_args.ver = obs_version;
-        CU(cudaMalloc(&env->d_compact, cap * (size_t)env->enc_args.compact_bytes));  // compact observations (mjx_obs.cuh)
+        set_enc_args(env, obs_version);
+        int max_compact = 0;  // the compact-form scratch fits every obs version (mjx_env_set_obs_version switches freely)
+        for (int v = 1; v <= 4; v++) {
+            const ObsLayout Lv = make_layout(v);
+            max_compact = std::max(max_compact, Lv.bm_rows * 8 + Lv.n_sv * OBS_COLS * 4);
+        }
+        CU(cudaMalloc(&env->d_compact, cap * (size_t)max_compact));  // compact observations (mjx_obs.cuh)
         env->sp_enabled = obs_version == 4 ? 1 : 0;  // the single-player block exists in v4 only
         CU(cudaMalloc(&env->d_enc_work, sizeof(int)));
         CU(cudaMemset(env->d_enc_work, 0, sizeof(int)));
@@ -648,6 +754,7 @@ void mjx_env_destroy(mjx_env* env) {
     SpGlobal& G = env->sp;
     cudaFree(G.rows); cudaFree(G.hkey); cudaFree(G.nsig); cudaFree(G.einfo); cudaFree(G.vals); cudaFree(G.echild); cudaFree(G.emeta);
     cudaFree(G.eowner); cudaFree(G.leaf_scores); cudaFree(G.wl); cudaFree(G.wl_count); cudaFree(G.counters);
+    cudaFree(env->d_state_words); cudaFree(env->d_state_pay); cudaFree(env->d_state_cans); cudaFree(env->d_state_misc);
     if (env->copy_stream) { cudaStreamDestroy(env->copy_stream); cudaEventDestroy(env->ev_rows); cudaEventDestroy(env->ev_sp); for (int g = 0; g < MJX_HOST_COPY_GROUPS; g++) cudaEventDestroy(env->ev_grp[g]); }
     delete env;
 }
@@ -856,6 +963,91 @@ int mjx_env_create_replay(mjx_env** out, int n_jobs, const uint64_t* hdr, const 
     return MJX_OK;
 }
 
+// ---- libriichi.state.PlayerState batch
+int mjx_state_create(mjx_env** out, int n, const uint8_t* player_ids_host, int obs_version) {
+    if (!out || n <= 0 || !player_ids_host) return fail(MJX_ERR_ARG, "mjx_state_create: bad arguments");
+    for (int i = 0; i < n; i++) if (player_ids_host[i] > 3) return fail(MJX_ERR_ARG, "mjx_state_create: player_id must be within 0..3");
+    std::vector<uint64_t> zeros((size_t)n, 0);
+    int rc = mjx_env_create(out, n, zeros.data(), zeros.data(), obs_version, 0, 0);
+    if (rc) return rc;
+    mjx_env* env = *out;
+    env->is_state = true;
+    u8* d_ids = nullptr;
+    CU(cudaMalloc(&d_ids, (size_t)n));
+    CU(cudaMemcpy(d_ids, player_ids_host, (size_t)n, cudaMemcpyHostToDevice));
+    k_state_init<<<(n + 127) / 128, 128>>>(env->V.tables, n, d_ids);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    cudaFree(d_ids);
+    CU(cudaMalloc(&env->d_state_words, sizeof(u64) * (size_t)n));
+    CU(cudaMalloc(&env->d_state_pay, sizeof(u64) * (size_t)n * REPLAY_KYOKU_WORDS));
+    CU(cudaMalloc(&env->d_state_cans, sizeof(u32) * (size_t)n));
+    CU(cudaMalloc(&env->d_state_misc, 256));
+    return MJX_OK;
+}
+
+int mjx_state_update(mjx_env* env, const uint64_t* words_host, const uint64_t* payload_host, uint32_t* cans_host) {
+    if (!env || !env->is_state || !words_host || !cans_host) return fail(MJX_ERR_ARG, "mjx_state_update: bad arguments");
+    const size_t n = (size_t)env->n_tables;
+    CU(cudaMemcpy(env->d_state_words, words_host, sizeof(u64) * n, cudaMemcpyHostToDevice));
+    if (payload_host) CU(cudaMemcpy(env->d_state_pay, payload_host, sizeof(u64) * n * REPLAY_KYOKU_WORDS, cudaMemcpyHostToDevice));
+    k_state_update<<<(env->n_tables + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32>>>(env->V, g_T, env->d_state_words,
+                                                                                       payload_host ? env->d_state_pay : nullptr, env->d_state_cans);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(cans_host, env->d_state_cans, sizeof(u32) * n, cudaMemcpyDeviceToHost));
+    env->launches += 1;
+    return MJX_OK;
+}
+
+int mjx_state_view(mjx_env* env, int index, mjx_player_view* out_host) {
+    if (!env || !env->is_state || !out_host || index < 0 || index >= env->n_tables) return fail(MJX_ERR_ARG, "mjx_state_view: bad arguments");
+    static_assert(sizeof(mjx_player_view) <= 512, "view scratch");
+    mjx_player_view* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(mjx_player_view)));
+    CU(cudaMemset(d, 0, sizeof(mjx_player_view)));
+    k_state_view<<<(env->n_tables + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32>>>(env->V, g_T, index, d);
+    cudaError_t e = cudaMemcpy(out_host, d, sizeof(mjx_player_view), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(MJX_ERR_CUDA, std::string("mjx_state_view: ") + cudaGetErrorString(e));
+    return MJX_OK;
+}
+
+int mjx_state_rows(mjx_env* env, const uint8_t* at_kan_select_host, void* stream) {
+    if (!env || !env->is_state) return fail(MJX_ERR_ARG, "mjx_state_rows: not a state batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    u8* d_kan = nullptr;
+    if (at_kan_select_host) {
+        d_kan = reinterpret_cast<u8*>(env->d_state_words);  // scratch: n bytes fit in the n words
+        CU(cudaMemcpyAsync(d_kan, at_kan_select_host, (size_t)env->n_tables, cudaMemcpyHostToDevice, st));
+    }
+    k_state_rows<<<(env->n_tables + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32, 0, st>>>(env->V, g_T, d_kan);
+    CU(cudaGetLastError());
+    env->launches += 1;
+    return MJX_OK;
+}
+
+int mjx_state_query(mjx_env* env, int index, int what, const int32_t* args, int32_t* out) {
+    if (!env || !env->is_state || !out || index < 0 || index >= env->n_tables || what < 0 || what > 4)
+        return fail(MJX_ERR_ARG, "mjx_state_query: bad arguments");
+    i32* d = reinterpret_cast<i32*>(env->d_state_misc);
+    i32 host_args[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (args) for (int k = 0; k < 8; k++) host_args[k] = args[k];
+    CU(cudaMemcpy(d, host_args, sizeof host_args, cudaMemcpyHostToDevice));
+    CU(cudaMemset(d + 8, 0, 8 * sizeof(i32)));
+    k_state_query<<<(env->n_tables + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32>>>(env->V, g_T, index, what, d, d + 8);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d + 8, 4 * sizeof(i32), cudaMemcpyDeviceToHost));
+    return MJX_OK;
+}
+
+int mjx_state_copy(mjx_env* dst, int dst_index, mjx_env* src, int src_index) {
+    if (!dst || !src || !dst->is_state || !src->is_state || dst_index < 0 || dst_index >= dst->n_tables || src_index < 0 ||
+        src_index >= src->n_tables)
+        return fail(MJX_ERR_ARG, "mjx_state_copy: bad arguments");
+    CU(cudaMemcpy(dst->V.tables + dst_index, src->V.tables + src_index, sizeof(TableState), cudaMemcpyDeviceToDevice));
+    return MJX_OK;
+}
+
 int mjx_env_replay_trust_seeds(mjx_env* env, const uint64_t* nonces_host, const uint64_t* keys_host, int shuffle_kind) {
     if (!env || !env->replay || !nonces_host || !keys_host) return fail(MJX_ERR_ARG, "mjx_env_replay_trust_seeds: bad arguments");
     if (!env->first) return fail(MJX_ERR_STATE, "mjx_env_replay_trust_seeds: must be called before the first mjx_env_replay_step");
@@ -899,8 +1091,17 @@ int mjx_env_last_encode_ms(mjx_env* env, float* ms_features, float* ms_store) {
 
 long long mjx_env_launch_count(mjx_env* env) { return env ? env->launches : -1; }
 
+int mjx_env_set_obs_version(mjx_env* env, int version) {
+    if (!env || version < 1 || version > 4) return fail(MJX_ERR_ARG, "mjx_env_set_obs_version: version must be 1..4 (consts.rs:18)");
+    env->obs_version = version;
+    set_enc_args(env, version);
+    env->sp_enabled = (version == 4 && env->sp_wanted) ? 1 : 0;
+    return MJX_OK;
+}
+
 int mjx_env_set_sp(mjx_env* env, int enable) {
     if (!env) return fail(MJX_ERR_ARG, "mjx_env_set_sp: null env");
+    env->sp_wanted = enable ? 1 : 0;
     env->sp_enabled = (enable && env->obs_version == 4) ? 1 : 0;
     return MJX_OK;
 }

@@ -46,26 +46,25 @@ MJX_D Reaction lw_reaction(u64 w, int type) {
     return r;
 }
 
-// PlayerState::update (state/update.rs:24-122) for all four seats at once, driven by a logged event
-MJX_DN void replay_apply(Ctx& c, const ReplayView& R, int job, u64 w) {
+// PlayerState::update (state/update.rs:24-122) driven by one event word — for all four seats of a full-information record, or
+// for the single known seat of a PlayerState record (TableState.viewer1). `pay` = the start_kyoku payload (only read for that event).
+MJX_DN void apply_event(Ctx& c, u64 w, const u64* pay, bool trust_seed) {
     TableState* S = c.S;
     switch (lw_type(w)) {
         case LOG_START_KYOKU: {
             if (MJX_IS_L0(c)) {
-                const u64* pay = R.kyoku + ((size_t)R.ky_off[job] + R.ky_seen[job]) * REPLAY_KYOKU_WORDS;
-                R.ky_seen[job] += 1;
                 S->kyoku = (u8)lw_c(w, 0); S->honba = (u8)lw_c(w, 1); S->kyotaku = (u8)lw_c(w, 2); S->oya = (u8)lw_c(w, 3);
                 S->scores[0] = (i32)(u32)pay[0]; S->scores[1] = (i32)(u32)(pay[0] >> 32);
                 S->scores[2] = (i32)(u32)pay[1]; S->scores[3] = (i32)(u32)(pay[1] >> 32);
                 // the wall as far as the caller knows it (haipai always; the hidden tiles when an invisible observation is wanted)
                 for (int i = 0; i < 136; i++) S->wall[i] = (u8)((pay[2 + i / 8] >> (8 * (i % 8))) & 0xFF);
-                if (R.trust_seed) {
+                if (trust_seed) {
                     u8 hp[52];
                     for (int i = 0; i < 52; i++) hp[i] = S->wall[i];
                     make_wall(S->nonce, S->key, S->kyoku, S->honba, S->shuffle_kind, S->wall);
                     for (int i = 0; i < 52; i++) if (S->wall[i] != hp[i] && S->err == 0) S->err = ERR_SEED_MISMATCH;  // not dealt from this seed
                 }
-                if (R.trust_seed && S->wall[60] != (u8)lw_pai(w) && S->err == 0) S->err = ERR_SEED_MISMATCH;
+                if (trust_seed && S->wall[60] != (u8)lw_pai(w) && S->err == 0) S->err = ERR_SEED_MISMATCH;
                 S->wall[60] = (u8)lw_pai(w);  // the first dora indicator; later ones arrive with their dora events
                 S->bflags = 0;
                 S->tiles_left = 70;
@@ -108,6 +107,17 @@ MJX_DN void replay_apply(Ctx& c, const ReplayView& R, int job, u64 w) {
             ev_prologue(c, -1);
             break;
     }
+}
+
+MJX_DN void replay_apply(Ctx& c, const ReplayView& R, int job, u64 w) {
+    const u64* pay = nullptr;
+    if (lw_type(w) == LOG_START_KYOKU) {
+        const int seen = R.ky_seen[job];
+        MJX_SYNCWARP();  // every lane has read the cursor before lane 0 advances it
+        pay = R.kyoku + ((size_t)R.ky_off[job] + seen) * REPLAY_KYOKU_WORDS;
+        MJX_L0(R.ky_seen[job] = seen + 1);
+    }
+    apply_event(c, w, pay, R.trust_seed != 0);
 }
 
 // Advance one job to its next logged decision. Returns true while the job still has events to process.

@@ -303,6 +303,7 @@ MJX_DN void ev_start_kyoku(Ctx& c) {
         P.shanten = 0;
         for (int i = 0; i < 13; i++) {
             int t = S->wall[13 * s + i];
+            if (t >= T_UNK) continue;  // `?`: another seat's hand seen from a single PlayerState
             P.tehai[deaka(t)] += 1;
             if (is_aka(t)) P.akas_in_hand |= (u8)(1 << (t - T_5MR));
         }
@@ -331,6 +332,7 @@ MJX_DN void ev_start_kyoku(Ctx& c) {
     }
     recompute_dora_factor(c);
     for (int s = 0; s < 4; s++) {
+        if (!seat_known(S, s)) continue;
         update_shanten(c, s);
         update_waits_and_furiten(c, s);
     }
@@ -341,6 +343,10 @@ MJX_DN void ev_tsumo(Ctx& c, int actor, int pai) {
     TableState* S = c.S;
     ev_prologue(c, actor);
     SeatPrivate& P = S->priv[actor];
+    if (!seat_known(S, actor)) {  // update.rs:220-225: somebody else's draw only shortens the wall
+        MJX_L0(S->tiles_left -= 1);
+        return;
+    }
     const int pid = deaka(pai);
     const bool riichi_acc = (S->riichi_accepted >> actor) & 1;
     MJX_L0(S->tiles_left -= 1;
@@ -401,9 +407,12 @@ MJX_DN void ev_dahai(Ctx& c, int actor, int pai, bool tsumogiri) {
     const int pid = deaka(pai);
     const bool is_riichi = ((S->riichi_declared >> actor) & 1) && !((S->riichi_accepted >> actor) & 1);
     const bool actor_riichi_acc = (S->riichi_accepted >> actor) & 1;
+    const bool known = seat_known(S, actor);
     if (MJX_IS_L0(c)) {
-        A.tehai[pid] -= 1;
-        if (is_aka(pai)) A.akas_in_hand &= (u8)~(1 << (pai - T_5MR));
+        if (known) {
+            A.tehai[pid] -= 1;
+            if (is_aka(pai)) A.akas_in_hand &= (u8)~(1 << (pai - T_5MR));
+        }
         public_witness(S, pai);
         KawaItem it;
         it.tile = (u8)pai;
@@ -427,7 +436,8 @@ MJX_DN void ev_dahai(Ctx& c, int actor, int pai, bool tsumogiri) {
     MJX_SYNCWARP();
 
     // the discarder's own shanten / waits (3n+1 now)
-    if (!actor_riichi_acc) {
+    if (!known) {
+    } else if (!actor_riichi_acc) {
         if ((A.next_shanten >> pid) & 1) { MJX_L0(A.shanten -= 1); }
         else if (!((A.keep_shanten >> pid) & 1)) update_shanten(c, actor);
         update_waits_and_furiten(c, actor);
@@ -470,9 +480,11 @@ MJX_D void others_after_call(Ctx& c, int actor) {
     MJX_END_SEATS(c);
 }
 
-MJX_D void consume_from_hand(SeatPrivate& P, TableState* S, int tile) {
-    P.tehai[deaka(tile)] -= 1;
-    if (is_aka(tile)) P.akas_in_hand &= (u8)~(1 << (tile - T_5MR));
+MJX_D void consume_from_hand(SeatPrivate& P, TableState* S, int tile, bool known = true) {
+    if (known) {
+        P.tehai[deaka(tile)] -= 1;
+        if (is_aka(tile)) P.akas_in_hand &= (u8)~(1 << (tile - T_5MR));
+    }
     public_witness(S, tile);
 }
 
@@ -507,8 +519,8 @@ MJX_DN void ev_chi(Ctx& c, const Reaction& r) {
         P.flags &= (u16)~PF_IS_MENZEN;
         P.tehai_len_div3 -= 1;
         P.last_self_tsumo = T_NONE;
-        consume_from_hand(P, S, r.consumed[0]);
-        consume_from_hand(P, S, r.consumed[1]);
+        consume_from_hand(P, S, r.consumed[0], seat_known(S, actor));
+        consume_from_hand(P, S, r.consumed[1], seat_known(S, actor));
         int a = deaka(r.consumed[0]), b = deaka(r.consumed[1]);
         int mn = min(a, b), mx = max(a, b), tid = deaka(pai);
         P.chis[P.n_chis++] = (u8)min(mn, tid);
@@ -523,6 +535,7 @@ MJX_DN void ev_chi(Ctx& c, const Reaction& r) {
     }
     MJX_SYNCWARP();
     others_after_call(c, actor);
+    if (!seat_known(S, actor)) return;
     update_shanten(c, actor);
     update_shanten_discards(c, actor);
 }
@@ -544,13 +557,14 @@ MJX_DN void ev_pon(Ctx& c, const Reaction& r) {
         P.flags &= (u16)~PF_IS_MENZEN;
         P.tehai_len_div3 -= 1;
         P.last_self_tsumo = T_NONE;
-        consume_from_hand(P, S, r.consumed[0]);
-        consume_from_hand(P, S, r.consumed[1]);
+        consume_from_hand(P, S, r.consumed[0], seat_known(S, actor));
+        consume_from_hand(P, S, r.consumed[1], seat_known(S, actor));
         P.pons[P.n_pons++] = (u8)pid;
         if (P.tehai[pid] > 0) P.forbidden |= 1ull << pid;
     }
     MJX_SYNCWARP();
     others_after_call(c, actor);
+    if (!seat_known(S, actor)) return;
     update_shanten(c, actor);
     update_shanten_discards(c, actor);
 }
@@ -568,11 +582,12 @@ MJX_DN void ev_daiminkan(Ctx& c, const Reaction& r) {
         pad_kawa_for_call(c, actor, r.target);
         P.flags = (u16)((P.flags | PF_AT_RINSHAN) & ~PF_IS_MENZEN);
         P.tehai_len_div3 -= 1;
-        for (int i = 0; i < 3; i++) consume_from_hand(P, S, r.consumed[i]);
+        for (int i = 0; i < 3; i++) consume_from_hand(P, S, r.consumed[i], seat_known(S, actor));
         P.minkans[P.n_minkans++] = (u8)deaka(pai);
     }
     MJX_SYNCWARP();
     others_after_call(c, actor);
+    if (!seat_known(S, actor)) return;
     update_shanten(c, actor);
     update_waits_and_furiten(c, actor);
 }
@@ -592,7 +607,7 @@ MJX_DN void ev_kakan(Ctx& c, const Reaction& r) {
         if (S->n_intermediate_kan < 4) S->intermediate_kan[S->n_intermediate_kan++] = (u8)pid;
         S->last_kawa_tile = (u8)pai;  // read by the chankan ronners only (update.rs:599)
         P.flags |= PF_AT_RINSHAN;
-        consume_from_hand(P, S, pai);
+        consume_from_hand(P, S, pai, seat_known(S, actor));
         int w = 0;
         for (int i = 0; i < P.n_pons; i++) if (P.pons[i] != pid) P.pons[w++] = P.pons[i];
         P.n_pons = (u8)w;
@@ -610,6 +625,7 @@ MJX_DN void ev_kakan(Ctx& c, const Reaction& r) {
         }
     }
     MJX_END_SEATS(c);
+    if (!seat_known(S, actor)) return;
     if (was_next) { MJX_L0(P.shanten -= 1); }
     else if (!was_keep) update_shanten(c, actor);
     update_waits_and_furiten(c, actor);
@@ -629,11 +645,11 @@ MJX_DN void ev_ankan(Ctx& c, const Reaction& r) {
         if (S->n_intermediate_kan < 4) S->intermediate_kan[S->n_intermediate_kan++] = (u8)tile;
         P.flags |= PF_AT_RINSHAN;
         P.tehai_len_div3 -= 1;
-        for (int i = 0; i < 4; i++) consume_from_hand(P, S, r.consumed[i]);
+        for (int i = 0; i < 4; i++) consume_from_hand(P, S, r.consumed[i], seat_known(S, actor));
         P.ankans[P.n_ankans++] = (u8)tile;
     }
     MJX_SYNCWARP();
-    if (!((S->riichi_accepted >> actor) & 1)) {
+    if (seat_known(S, actor) && !((S->riichi_accepted >> actor) & 1)) {
         update_shanten(c, actor);
         update_waits_and_furiten(c, actor);
     }

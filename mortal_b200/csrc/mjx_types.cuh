@@ -130,7 +130,9 @@ struct TableState {
     u8 kyoku, honba, kyotaku, gflags;
     u8 shuffle_kind;
     u8 n_kyoku_played;
-    u8 pad0_[2];
+    u8 viewer1;              // 0: the record holds all four hands (arena, full-information replay); s + 1: a single PlayerState of
+                             // seat s (state/player_state.rs) — the other seats' hands are unknown (`?`) and stay untouched
+    u8 pad0_[1];
     i32 row_of_seat[4];      // decision rows handed to the policy this cycle (-1 none)
     i32 kan_row_of_seat[4];
     i8 auto_action[4];       // quick-eval shortcut (mortal.rs:210-242), -1 none
@@ -158,6 +160,9 @@ struct TableState {
     SeatPrivate priv[4];
     SeatPublic pub[4];
 };
+
+// whether the record knows seat s's hand
+MJX_HD bool seat_known(const TableState* S, int s) { return S->viewer1 == 0 || S->viewer1 == s + 1; }
 
 static_assert(sizeof(KawaItem) == 8, "KawaItem must be 8 bytes");
 static_assert(sizeof(TableState) % 16 == 0, "TableState must be a multiple of 16 bytes");

@@ -9,6 +9,7 @@
 #include "mjx_sp.cuh"
 #include "mjx_replay.cuh"
 #include "mjx_invisible.cuh"
+#include "mjx_state.cuh"
 #include "mjx_policy.cuh"
 #include "mjx_tables_host.h"
 
@@ -340,6 +341,84 @@ void emul_env_encode_invisible(void* p, float* out, int version) {
     const int rows = oracle_obs_rows(version);
     for (int r = 0; r < E->n_rows[0]; r++)
         encode_invisible(&E->tabs[E->row_table[r]], E->row_seat[r] & 3, version, out + (size_t)r * rows * OBS_COLS, 0);
+}
+// ---- libriichi.state.PlayerState batch: the surface of mjx_state_* (include/mjx.h), one lane
+void* emul_state_create(int n, const uint8_t* player_ids) {
+    std::vector<uint64_t> zeros(n, 0);
+    EmulEnv* E = static_cast<EmulEnv*>(emul_env_create(n, zeros.data(), zeros.data(), 0, 0));
+    for (int t = 0; t < n; t++) {
+        TableState& S = E->tabs[t];
+        S.viewer1 = (u8)(player_ids[t] + 1); S.last_kawa_tile = T_NONE;
+        for (int s = 0; s < 4; s++) S.priv[s].last_self_tsumo = T_NONE;
+    }
+    return E;
+}
+static Ctx emul_state_ctx(EmulEnv* E, int i, WarpScratch& W) {
+    Ctx c; c.S = &E->tabs[i]; c.W = &W; c.T = g_T; c.lane = 0; c.df = W.dora_factor;
+    recompute_dora_factor(c);
+    return c;
+}
+void emul_state_update(void* p, const uint64_t* words, const uint64_t* payload, uint32_t* cans) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    WarpScratch W;
+    for (int i = 0; i < E->n; i++) {
+        Ctx c = emul_state_ctx(E, i, W);
+        if (words[i] != 0) apply_event(c, words[i], payload ? payload + (size_t)i * REPLAY_KYOKU_WORDS : nullptr, false);
+        const SeatPrivate& P = E->tabs[i].priv[E->tabs[i].viewer1 - 1];
+        cans[i] = (u32)P.cans | ((u32)P.target_actor << 16);
+    }
+}
+void emul_state_view(void* p, int index, mjx_player_view* out) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    WarpScratch W;
+    Ctx c = emul_state_ctx(E, index, W);
+    memset(out, 0, sizeof *out);
+    state_view(c, E->tabs[index].viewer1 - 1, out);
+}
+void emul_state_rows(void* p, const uint8_t* at_kan_select) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    WarpScratch W;
+    for (int i = 0; i < E->n; i++) {
+        Ctx c = emul_state_ctx(E, i, W);
+        const int pl = E->tabs[i].viewer1 - 1;
+        const bool kan = at_kan_select && at_kan_select[i];
+        const u64 discards = (E->tabs[i].priv[pl].cans & CAN_DISCARD) ? discard_candidates(c, pl) : 0;
+        write_mask_row(c, E->V, i, legal_mask(c, pl, kan, discards));
+        E->row_table[i] = i; E->row_seat[i] = (u8)(pl | (kan ? 4 : 0)); E->row_step[i] = 0;
+    }
+    E->n_rows[0] = E->n;
+}
+void emul_state_query(void* p, int index, int what, const int32_t* args, int32_t* out) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    WarpScratch W;
+    Ctx c = emul_state_ctx(E, index, W);
+    const int pl = E->tabs[index].viewer1 - 1;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (what == 0) {
+        u8 ura[5]; const int n_ura = std::min(std::max(args[1], 0), 5);
+        for (int k = 0; k < n_ura; k++) ura[k] = (u8)args[2 + k];
+        bool ok; const Point pt = agari_points_ura(c, pl, args[0] != 0, ura, n_ura, &ok);
+        out[0] = pt.ron; out[1] = pt.tsumo_ko; out[2] = pt.tsumo_oya; out[3] = ok ? 1 : 0;
+    } else if (what == 1) out[0] = rule_based_agari(c, pl) ? 1 : 0;
+    else if (what == 2) { const u64 m = discard_candidates(c, pl); out[0] = (i32)(u32)m; out[1] = (i32)(u32)(m >> 32); }
+    else if (what == 3) {
+        EncCtx e; e.S = c.S; e.T = g_T; e.bm = nullptr; e.sv = nullptr; e.seat = pl; e.kan_select = false; e.lane = 0; e.dora_factor = c.df; e.parts = 0;
+        const u64 m = unconditional_tenpai_discards(e, c); out[0] = (i32)(u32)m; out[1] = (i32)(u32)(m >> 32);
+    } else if (what == 4) {
+        Reaction r; i32 err = 0;
+        const bool okd = decode_action(c.S, pl, args[0], args[1], r, &err);
+        u64 w = 0;
+        if (okd) {
+            const int ty = r.type == R_DAHAI ? LOG_DAHAI : r.type == R_CHI ? LOG_CHI : r.type == R_PON ? LOG_PON :
+                           r.type == R_DAIMINKAN ? LOG_DAIMINKAN : r.type == R_KAKAN ? LOG_KAKAN : r.type == R_ANKAN ? LOG_ANKAN :
+                           r.type == R_REACH ? LOG_REACH : r.type == R_HORA ? LOG_HORA : r.type == R_RYUKYOKU ? LOG_RYUKYOKU : 0;
+            w = log_word(ty, r.actor, r.target, r.pai, r.tsumogiri, 0, r.consumed[0], r.consumed[1], r.consumed[2], r.consumed[3], 0);
+        }
+        out[0] = (i32)(u32)w; out[1] = (i32)(u32)(w >> 32); out[2] = okd ? 0 : (err ? err : ERR_ILLEGAL_ACTION);
+    }
+}
+void emul_state_copy(void* dst, int di, void* src, int si) {
+    static_cast<EmulEnv*>(dst)->tabs[di] = static_cast<EmulEnv*>(src)->tabs[si];
 }
 void emul_env_results(void* p, int32_t* scores, uint8_t* ranks, int32_t* steps, int32_t* errs, int32_t* done) {
     EmulEnv* E = static_cast<EmulEnv*>(p);

@@ -350,9 +350,39 @@ def test_arena_writes_mjai_logs(mjx, tmp_path):
             return q.argmax(-1), q
 
     arena = OneVsThree(disable_progress_bar=True, log_dir=str(tmp_path))
+    arena.record_decisions = True
     torch.manual_seed(0)
     rankings = arena.py_vs_py(Greedy("chal"), Greedy("champ"), (4000, 77), 3)
     assert sum(rankings) == 12
+    # agent/mortal.rs:161-186 gen_meta on the GPU path: the recorder must not have failed, and every logged agent event's meta is
+    # the decision that caused it: legal-only q-values, the legal mask, shanten / furiten, is_greedy
+    assert arena.last_meta_error is None, repr(arena.last_meta_error)
+    dec, bits = arena.last_decisions, arena.last_decision_masks
+    nonces_m = np.repeat(np.arange(4000, 4003, dtype=np.uint64), 4)
+    O.run_replay(nonces_m, np.full(12, 77, dtype=np.uint64), dec, quick_eval=True, mask_bits=bits)  # the recorded masks ARE the oracle's
+    mask_of = {}
+    for (t, _, seat, kan, a), b in zip(dec.tolist(), bits.tolist()):
+        if not kan:
+            mask_of.setdefault((t, seat), []).append((a, b))
+    n_meta = 0
+    for g, path in enumerate(arena.last_log_paths):
+        pos = {s: 0 for s in range(4)}
+        for ev in (json.loads(ln) for ln in gzip.open(path, "rt")):
+            m = ev.get("meta")
+            if m is None:
+                continue
+            n_meta += 1
+            assert len(m["q_values"]) == bin(m["mask_bits"]).count("1") and m["is_greedy"] is True
+            assert 0 <= m["shanten"] <= 6 and isinstance(m["at_furiten"], bool) and m["batch_size"] > 0 and m["eval_time_ns"] > 0
+            seat = ev.get("actor")
+            if seat is None:
+                continue
+            # the seat's recorded decisions are in order; this event's meta must be one of them, further down the list
+            lst = mask_of[(g, seat)]
+            while pos[seat] < len(lst) and lst[pos[seat]][1] != m["mask_bits"]:
+                pos[seat] += 1
+            assert pos[seat] < len(lst), (g, seat, ev)
+    assert n_meta > 12 * 100
     names = sorted(p.name for p in tmp_path.iterdir())
     assert names == sorted(f"{4000 + s}_77_{c}.json.gz" for s in range(3) for c in "abcd")
     res = arena.last_results
