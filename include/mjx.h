@@ -50,6 +50,10 @@ void mjx_env_destroy(mjx_env* env);
  * set enable_rule_based_agari_guard (agent/mortal.rs:319-336: "wants agari but the guard objects -> best other Q"). */
 int mjx_env_step(mjx_env* env, const int64_t* actions_dev, const float* q_values_dev, void* stream);
 
+/* agent/mortal.rs:54-74, 210-250: enable_quick_eval is a property of the agent, so of the seat: host uint8 [n_tables, 4]
+ * (NULL = the single flag given to mjx_env_create for every seat). */
+int mjx_env_set_quick_eval(mjx_env* env, const uint8_t* flags_host);
+
 /* agent/mortal.rs:61-66 enable_rule_based_agari_guard per table and seat: host uint8 [n_tables, 4] (NULL = off).
  * The guard itself is state/agent_helper.rs:262-368 rule_based_agari, evaluated on device. */
 int mjx_env_set_agari_guard(mjx_env* env, const uint8_t* flags_host);

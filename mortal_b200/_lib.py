@@ -41,6 +41,7 @@ SYMBOLS = {
     "mjx_env_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "mjx_env_destroy": (None, [C.c_void_p]),
     "mjx_env_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mjx_env_set_quick_eval": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mjx_env_set_agari_guard": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mjx_env_encode_obs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mjx_oracle_obs_rows": (C.c_int, [C.c_int]),

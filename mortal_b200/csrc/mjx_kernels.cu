@@ -556,6 +556,7 @@ struct mjx_env {
     u64 *d_nonces = nullptr, *d_keys = nullptr;
     i64* d_dummy_actions = nullptr;
     u8* d_guard = nullptr;
+    u8* d_quick_eval = nullptr;
     SpGlobal sp;
     int sp_enabled = 1, sp_wanted = 1;
     unsigned char* d_compact = nullptr;
@@ -750,13 +751,21 @@ void mjx_env_destroy(mjx_env* env) {
         cudaFree((void*)R.player); cudaFree(R.pos); cudaFree(R.ky_idx); cudaFree(R.ky_seen); cudaFree(R.row_label); cudaFree(R.row_meta);
     }
     for (int i = 0; i < 3; i++) if (env->ev_enc[i]) cudaEventDestroy(env->ev_enc[i]);
-    cudaFree(env->d_guard); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len);
+    cudaFree(env->d_guard); cudaFree(env->d_quick_eval); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len);
     SpGlobal& G = env->sp;
     cudaFree(G.rows); cudaFree(G.hkey); cudaFree(G.nsig); cudaFree(G.einfo); cudaFree(G.vals); cudaFree(G.echild); cudaFree(G.emeta);
     cudaFree(G.eowner); cudaFree(G.leaf_scores); cudaFree(G.wl); cudaFree(G.wl_count); cudaFree(G.counters);
     cudaFree(env->d_state_words); cudaFree(env->d_state_pay); cudaFree(env->d_state_cans); cudaFree(env->d_state_misc);
     if (env->copy_stream) { cudaStreamDestroy(env->copy_stream); cudaEventDestroy(env->ev_rows); cudaEventDestroy(env->ev_sp); for (int g = 0; g < MJX_HOST_COPY_GROUPS; g++) cudaEventDestroy(env->ev_grp[g]); }
     delete env;
+}
+
+int mjx_env_set_quick_eval(mjx_env* env, const uint8_t* flags_host) {
+    if (!env) return fail(MJX_ERR_ARG, "mjx_env_set_quick_eval: null env");
+    if (!flags_host) { cudaFree(env->d_quick_eval); env->d_quick_eval = nullptr; return MJX_OK; }
+    if (!env->d_quick_eval) CU(cudaMalloc(&env->d_quick_eval, (size_t)env->n_tables * 4));
+    CU(cudaMemcpy(env->d_quick_eval, flags_host, (size_t)env->n_tables * 4, cudaMemcpyHostToDevice));
+    return MJX_OK;
 }
 
 int mjx_env_set_agari_guard(mjx_env* env, const uint8_t* flags_host) {
@@ -775,6 +784,7 @@ int mjx_env_step(mjx_env* env, const int64_t* actions_dev, const float* q_values
     V.actions = actions_dev ? (const i64*)actions_dev : env->d_dummy_actions;
     V.q_values = q_values_dev;
     V.agari_guard = env->d_guard;
+    V.quick_eval_seat = env->d_quick_eval;
     k_begin_step<<<1, 1, 0, st>>>(V);
     k_step<<<(env->n_tables + STEP_WARPS - 1) / STEP_WARPS, STEP_WARPS * 32, 0, st>>>(V, g_T);
     CU(cudaGetLastError());

@@ -1295,6 +1295,7 @@ struct EnvView {
     i32* err;           // [n_tables]
     unsigned long long* counters;  // [0] live tables after this step, [1] total table-steps so far
     i32 enable_quick_eval;
+    const u8* quick_eval_seat;  // [n_tables, 4] or null: per-seat enable_quick_eval (agent/mortal.rs:54-74: every agent has its own)
     u64* log;           // [n_tables, log_cap] mjai event words (see log_word) or null
     i32* log_len;       // [n_tables] words written (may exceed log_cap: overflow)
     i32 log_cap;
@@ -1384,14 +1385,15 @@ MJX_DN void emit_decisions(Ctx& c, EnvView& V, int table) {
         const u16 cans = P.cans;
         if (!(cans & CAN_ACT)) continue;
         const u64 discards = (cans & CAN_DISCARD) ? discard_candidates(c, s) : 0;
-        if (V.enable_quick_eval && (cans & CAN_DISCARD) &&
+        const bool quick_eval = V.quick_eval_seat ? V.quick_eval_seat[table * 4 + s] != 0 : V.enable_quick_eval != 0;
+        if (quick_eval && (cans & CAN_DISCARD) &&
             !(cans & (CAN_RIICHI | CAN_TSUMO_AGARI | CAN_ANKAN | CAN_KAKAN | CAN_RYUKYOKU)) && mjx_popcll(discards) == 1) {
             MJX_L0(S->auto_action[s] = (i8)(mjx_ffsll(discards) - 1));
             continue;
         }
         bool need_kan = false;
         if (cans & (CAN_ANKAN | CAN_KAKAN))
-            need_kan = !V.enable_quick_eval || (mjx_popcll(P.ankan_cand) + mjx_popcll(P.kakan_cand)) > 1;
+            need_kan = !quick_eval || (mjx_popcll(P.ankan_cand) + mjx_popcll(P.kakan_cand)) > 1;
         const int n = need_kan ? 2 : 1;
         const int base = alloc_rows(c, V, n);
         if (base + n > V.row_cap) { set_err(c, ERR_ROW_OVERFLOW); return; }

@@ -94,6 +94,23 @@ class BatchEnv:
         assert f.shape == (self.n_tables, 4)
         _lib.check(self.L.mjx_env_set_agari_guard(self._h, f.ctypes.data), "mjx_env_set_agari_guard")
 
+    def set_quick_eval(self, flags) -> None:
+        """flags: None or uint8 array [n_tables, 4] (1 = that seat's engine has enable_quick_eval)."""
+        if flags is None:
+            _lib.check(self.L.mjx_env_set_quick_eval(self._h, None), "mjx_env_set_quick_eval")
+            return
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        assert f.shape == (self.n_tables, 4)
+        _lib.check(self.L.mjx_env_set_quick_eval(self._h, f.ctypes.data), "mjx_env_set_quick_eval")
+
+    def set_obs_version(self, version: int) -> None:
+        """switch the version encode_obs / encode_obs_host produce (agent/mortal.rs:54-74: every agent has its own)"""
+        _lib.check(self.L.mjx_env_set_obs_version(self._h, int(version)), "mjx_env_set_obs_version")
+        if version != self.obs_version:
+            self.obs_version = int(version)
+            self.obs_rows = self.L.mjx_obs_rows(version)
+            self._obs = None
+
     def obs_buffer(self):
         if self._obs is None:
             self._obs = self.torch.empty((self.row_cap, self.obs_rows, 34), dtype=self.torch.float32, device=self.device)

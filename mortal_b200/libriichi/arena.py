@@ -100,11 +100,14 @@ class _MetaRecorder:
 class _Part:
     """One independently stepped slice of the batch: a BatchGame (game.rs:222-316) over tables [offset, offset + n)."""
 
-    def __init__(self, arena, agents, nonces, keys, offset, per, challenger_seats, version, quick_eval, use_stream):
+    def __init__(self, arena, agents, nonces, keys, offset, per, challenger_seats, versions, quick_evals, use_stream):
         import torch
 
         self.arena, self.agents, self.offset, self.per = arena, agents, offset, per
         self.nonces, self.keys, self.n = nonces, keys, len(nonces)
+        version, quick_eval = versions[0], quick_evals[0]
+        self.versions = list(versions)
+        self.mixed = versions[0] != versions[1]  # agent/mortal.rs:54-74: every agent encodes with its own obs version
         self.env = env = arena.env_factory(nonces, keys, obs_version=version, shuffle_kind=arena.shuffle_kind,
                                            enable_quick_eval=quick_eval, device=arena.device)
         self.dev = dev = env.device
@@ -114,10 +117,16 @@ class _Part:
             for s in challenger_seats(g):
                 self.is_challenger[g, s] = True
         self.ic_host = self.is_challenger.cpu().numpy()
+        if quick_evals[0] != quick_evals[1]:  # enable_quick_eval is the agent's, so the seat's (mortal.rs:210-250)
+            qf = np.zeros((self.n, 4), dtype=np.uint8)
+            for g in range(self.n):
+                for seat in range(4):
+                    qf[g, seat] = quick_evals[0] if self.ic_host[g % per, seat] else quick_evals[1]
+            env.set_quick_eval(qf)
         self.meta_rec = None
         if arena.log_dir is not None:
             env.enable_log()
-            self.meta_rec = _MetaRecorder(self.n, version) if arena.log_meta else None
+            self.meta_rec = _MetaRecorder(self.n, 0 if self.mixed else version) if arena.log_meta else None
         self.actions = torch.zeros(env.row_cap, dtype=torch.int64, device=dev)
         guards = [bool(getattr(a, "enable_rule_based_agari_guard", False)) for a in agents]
         self.q_all = None
@@ -131,9 +140,12 @@ class _Part:
         # engines that only speak the reference protocol (react_batch over host arrays) get the observations through
         # mjx_env_encode_obs_host: pinned host buffers, D2H overlapped with the single-player kernels
         self.host_mode = all(isinstance(a, HostProtocolEngine) for a in agents)
+        rows_of = {1: 938, 2: 942, 3: 934, 4: 1012}
         if self.host_mode:
             pin = (lambda t: t.pin_memory()) if dev.type == "cuda" else (lambda t: t)
             self.h_obs = pin(torch.empty((env.row_cap, env.obs_rows, 34), dtype=torch.float32))
+            # a second host buffer when the champion encodes another obs version
+            self.h_obs2 = pin(torch.empty((env.row_cap, rows_of[versions[1]], 34), dtype=torch.float32)) if self.mixed else None
             self.h_masks = pin(torch.empty((env.row_cap, 46), dtype=torch.bool))
             self.h_actions = pin(torch.zeros(env.row_cap, dtype=torch.int64))
             self.h_q = pin(torch.zeros((env.row_cap, 46), dtype=torch.float32)) if self.q_all is not None else None
@@ -180,14 +192,14 @@ class _Part:
     def _after_step(self):
         if self.meta_rec is not None:
             self.meta_rec.add_bounds(self.env.log_len)
-        if self.host_mode:
+        if self.host_mode and not self.mixed:
             self.nr = self.env.encode_obs_host_begin(self.h_obs, self.h_masks)
 
     def finish(self):
         """Wait for the part's step; game.rs:288,292: an error from any table aborts the whole batch at that cycle (`?`);
         so does a single-player arena overflow, which would otherwise hand zeroed rows 889-1011 to the engines."""
         with self._ctx():
-            if self.host_mode:
+            if self.host_mode and not self.mixed:
                 self.env.encode_obs_host_finish()
             nr, n_live, n_err, sp_ovf = self.env.poll()
         if n_err:
@@ -221,11 +233,17 @@ class _Part:
                 if self.h_inv is not None:
                     self.h_inv[:nr].copy_(env.encode_invisible(self.version)[:nr])
                     inv_np = self.h_inv.numpy()
-                for idx, agent, is_oracle in groups:
+                for k, (idx, agent, is_oracle) in enumerate(groups):
                     if idx.size == 0:
                         continue
+                    obs_np = self.obs_np
+                    if self.mixed:  # each agent's rows in its own layout (mortal.rs:256-287): one encode per version
+                        env.set_obs_version(self.versions[k])
+                        buf = self.h_obs if k == 0 else self.h_obs2
+                        assert env.encode_obs_host(buf, self.h_masks) == nr
+                        obs_np = buf.numpy()
                     t_eval = time.perf_counter_ns()
-                    a, q, greedy = agent.react_host(self.obs_np, self.masks_np, idx, inv_np if is_oracle else None)
+                    a, q, greedy = agent.react_host(obs_np, self.masks_np, idx, inv_np if is_oracle else None)
                     if meta_rec is not None:
                         meta_rec.add_agent(cycles, torch.from_numpy(idx), torch.from_numpy(q).reshape(-1, 46), time.perf_counter_ns() - t_eval, greedy)
                     h_actions[torch.from_numpy(idx)] = torch.from_numpy(a)
@@ -263,10 +281,14 @@ class _Part:
                     meta_rec.add_agent(cycles, torch.arange(nr), q, time.perf_counter_ns() - t_eval, greedy)
             else:
                 chal = self.is_challenger[tbl % self.per, seat]
-                for idx, agent, is_oracle in ((chal.nonzero().squeeze(1), agents[0], self.oracle[0]),
-                                              ((~chal).nonzero().squeeze(1), agents[1], self.oracle[1])):
+                for k, (idx, agent, is_oracle) in enumerate(((chal.nonzero().squeeze(1), agents[0], self.oracle[0]),
+                                                             ((~chal).nonzero().squeeze(1), agents[1], self.oracle[1]))):
                     if idx.numel() == 0:
                         continue
+                    if self.mixed and k == 1:  # the champion's rows in its own layout (mortal.rs:256-287)
+                        env.set_obs_version(self.versions[1])
+                        obs = env.encode_obs()[:nr]
+                        env.set_obs_version(self.versions[0])
                     t_eval = time.perf_counter_ns()
                     out = agent.react_device(obs[idx], masks[idx], invisible_obs=inv[idx]) if is_oracle else agent.react_device(obs[idx], masks[idx])
                     a, q = out[0], out[1]
@@ -332,11 +354,7 @@ class _Arena:
             if getattr(a, "version", 4) not in (1, 2, 3, 4):
                 raise ValueError(f"unsupported obs version {a.version} (consts.rs:18 MAX_VERSION = 4)")
         versions = [int(getattr(a, "version", 4)) for a in agents]
-        if versions[0] != versions[1]:
-            raise NotImplementedError("challenger and champion must use the same obs version (one encoder pass per step)")
         qe = [bool(getattr(a, "enable_quick_eval", True)) for a in agents]
-        if qe[0] != qe[1]:
-            raise NotImplementedError("challenger and champion must agree on enable_quick_eval")
         per = self.GAMES_PER_SEED
         seed_count = int(seed_count)
         n = seed_count * per
@@ -352,7 +370,7 @@ class _Arena:
         parts = []
         try:
             for lo, hi in zip(cuts[:-1], cuts[1:]):
-                parts.append(_Part(self, agents, nonces[lo:hi], keys[lo:hi], lo, per, self._challenger_seats, versions[0], qe[0],
+                parts.append(_Part(self, agents, nonces[lo:hi], keys[lo:hi], lo, per, self._challenger_seats, versions, qe,
                                    use_stream=len(cuts) > 2))
             state = _RunState(parts)
             for p in parts:

@@ -663,9 +663,11 @@ void orc_sp_stats(long* out) { for (int i = 0; i < 8; i++) { out[i] = orc::g_sp_
 // Every replayed action must be legal in the oracle's own mask, otherwise the call fails. `mask_bits` (optional, aligned
 // with the replay rows) = the legal mask the recorder saw, compared with the oracle's bit for bit. `max_steps` > 0 stops
 // every table after that many table-steps (the recording was cut at the same point); scores are then the running scores.
+static const uint8_t* g_replay_qe_flags = nullptr;  // optional [n_tables, 4] per-seat enable_quick_eval (set by orc_run_replay3)
 int orc_run_replay2(int n_tables, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int enable_quick_eval,
                     const int64_t* replay, int64_t n_replay, const int64_t* mask_bits, int64_t max_steps, int n_threads,
                     int32_t* scores, uint8_t* ranks, int32_t* steps) {
+    const uint8_t* qe_flags = g_replay_qe_flags;
     try {
         std::atomic<int64_t> used(0);
         std::atomic<int> next(0);
@@ -681,6 +683,7 @@ int orc_run_replay2(int n_tables, const uint64_t* nonces, const uint64_t* keys, 
                     AgentConfig ac;
                     ac.enable_quick_eval = enable_quick_eval != 0;
                     AgentConfig cfgs[4] = {ac, ac, ac, ac};
+                    if (qe_flags) for (int sx = 0; sx < 4; sx++) cfgs[sx].enable_quick_eval = qe_flags[t * 4 + sx] != 0;  // mortal.rs:54-74
                     PolicyFn pol = [&](const Scene& sc, const u8* mask, float*) {
                         int64_t key[4] = {sc.table, (int64_t)sc.step_idx, sc.seat, sc.is_kan_select ? 1 : 0};
                         int64_t lo = 0, hi = n_replay;
@@ -729,6 +732,15 @@ int orc_run_replay2(int n_tables, const uint64_t* nonces, const uint64_t* keys, 
             throw OrcError("replay: " + std::to_string(n_replay - used.load()) + " recorded decisions were never requested");
         return 0;
     } catch (const std::exception& e) { return fail(e); }
+}
+// the same with a per-seat enable_quick_eval (uint8 [n_tables, 4]): challenger and champion may differ (agent/mortal.rs:54-74)
+int orc_run_replay3(int n_tables, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, const uint8_t* qe_flags,
+                    const int64_t* replay, int64_t n_replay, const int64_t* mask_bits, int64_t max_steps, int n_threads,
+                    int32_t* scores, uint8_t* ranks, int32_t* steps) {
+    g_replay_qe_flags = qe_flags;
+    const int rc = orc_run_replay2(n_tables, nonces, keys, shuffle_kind, 1, replay, n_replay, mask_bits, max_steps, n_threads, scores, ranks, steps);
+    g_replay_qe_flags = nullptr;
+    return rc;
 }
 int orc_run_replay(int n_tables, const uint64_t* nonces, const uint64_t* keys, int shuffle_kind, int enable_quick_eval,
                    const int64_t* replay, int64_t n_replay, int32_t* scores, uint8_t* ranks, int32_t* steps) {

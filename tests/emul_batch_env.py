@@ -10,13 +10,12 @@ import emul_lib as E
 
 class EmulBatchEnv:
     def __init__(self, nonces, keys, *, obs_version=4, shuffle_kind=0, enable_quick_eval=True, device=0):
-        assert obs_version == 4
         self._e = E.EmulEnv(nonces, keys, shuffle_kind=shuffle_kind, enable_quick_eval=enable_quick_eval)
         self.L = self._e.L
         self.device = torch.device("cpu")
         self.n_tables = self._e.n_tables
         self.row_cap = self._e.row_cap
-        self.obs_version, self.obs_rows = 4, 1012
+        self.obs_version, self.obs_rows = obs_version, {1: 938, 2: 942, 3: 934, 4: 1012}[obs_version]
         self.masks = torch.zeros((self.row_cap, 46), dtype=torch.bool)
         self.row_table = torch.zeros(self.row_cap, dtype=torch.int32)
         self.row_seat = torch.zeros(self.row_cap, dtype=torch.uint8)
@@ -60,13 +59,20 @@ class EmulBatchEnv:
     def sp_overflows(self):
         return int(self.L.emul_sp_overflows()) - self._ovf0
 
+    def set_obs_version(self, version):
+        self.obs_version, self.obs_rows = version, {1: 938, 2: 942, 3: 934, 4: 1012}[version]
+
+    def set_quick_eval(self, flags):
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        self.L.emul_env_set_quick_eval(self._e._h, f.ctypes.data)
+
     def set_agari_guard(self, flags):
         assert flags is None or not np.asarray(flags).any()
 
     def encode_obs_host(self, h_obs, h_masks):
         n = self._e.num_rows()
         if n:
-            h_obs[:n] = torch.from_numpy(self._e.encode_obs(sp=True))
+            h_obs[:n] = torch.from_numpy(self._e.encode_obs(sp=self.obs_version == 4, version=self.obs_version))
             h_masks[:n] = self.masks[:n]
         return n
 

@@ -48,6 +48,7 @@ def lib():
         L.emul_replay_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_env_errs.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_env_row_steps.argtypes = [C.c_void_p, C.c_void_p]
+        L.emul_env_set_quick_eval.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_env_encode_invisible.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.emul_replay_trust_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.emul_replay_encode_invisible.argtypes = [C.c_void_p, C.c_void_p, C.c_int]

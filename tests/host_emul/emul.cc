@@ -70,7 +70,7 @@ int emul_run(int n, const uint64_t* nonces, const uint64_t* keys, int shuffle_ki
     V.tables = tabs.data(); V.n_tables = n; V.row_cap = cap; V.n_rows = n_rows.data();
     V.row_table = row_table.data(); V.row_seat = row_seat.data(); V.row_step = row_step.data();
     V.masks = masks.data(); V.actions = actions.data(); V.scores = scores; V.ranks = ranks; V.done = done.data();
-    V.steps = steps; V.err = errs; V.counters = counters; V.enable_quick_eval = quick_eval;
+    V.steps = steps; V.err = errs; V.counters = counters; V.enable_quick_eval = quick_eval; V.quick_eval_seat = nullptr;
     std::vector<float> qv((size_t)cap * ACTION_SPACE, 0.f);
     std::vector<u8> guard((size_t)n * 4, 1);
     V.log = nullptr; V.log_len = nullptr; V.log_cap = 0;
@@ -115,7 +115,7 @@ struct EmulEnv {
     int n = 0, cap = 0;
     std::vector<TableState> tabs;
     std::vector<i32> row_table, done, steps, errs, scores, n_rows;
-    std::vector<u8> row_seat, masks, ranks;
+    std::vector<u8> row_seat, masks, ranks, qe_seat;
     std::vector<u32> row_step;
     std::vector<i64> actions;
     unsigned long long counters[2] = {0, 0};
@@ -150,11 +150,17 @@ void* emul_env_create(int n, const uint64_t* nonces, const uint64_t* keys, int s
     V.masks = E->masks.data(); V.actions = E->actions.data(); V.scores = E->scores.data(); V.ranks = E->ranks.data();
     V.done = E->done.data(); V.steps = E->steps.data(); V.err = E->errs.data(); V.counters = E->counters;
     V.q_values = nullptr; V.agari_guard = nullptr;
-    V.enable_quick_eval = quick_eval;
+    V.enable_quick_eval = quick_eval; V.quick_eval_seat = nullptr;
     V.log = nullptr; V.log_len = nullptr; V.log_cap = 0;
     return E;
 }
 void emul_env_destroy(void* p) { delete static_cast<EmulEnv*>(p); }
+void emul_env_set_quick_eval(void* p, const uint8_t* flags) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    static_assert(sizeof(u8) == 1, "");
+    E->qe_seat.assign(flags, flags + (size_t)E->n * 4);
+    E->V.quick_eval_seat = E->qe_seat.data();
+}
 
 // returns number of live tables after the step
 int emul_env_step(void* p, const int64_t* actions) {

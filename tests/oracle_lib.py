@@ -202,6 +202,8 @@ def lib():
                                  C.c_void_p, C.c_void_p]
     L.orc_run_replay2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_run_replay3.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_run_sample_obs.argtypes = [C.POINTER(RunCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_oracle_obs_rows.argtypes = [C.c_int]
@@ -478,7 +480,7 @@ def run_batch(nonces, keys, *, shuffle_kind=0, policy_kind=1, quick_eval=True, a
     return res
 
 
-def run_replay(nonces, keys, replay, *, shuffle_kind=0, quick_eval=True, mask_bits=None, max_steps=0, n_threads=1):
+def run_replay(nonces, keys, replay, *, shuffle_kind=0, quick_eval=True, mask_bits=None, max_steps=0, n_threads=1, quick_eval_seats=None):
     """replay: int64 [m, 5] rows (table, step, seat, kan_select, action) recorded from another implementation;
     mask_bits: optional int64 [m] legal masks the recorder saw (compared bit for bit); max_steps: the recording was cut
     after that many table-steps per table (0 = whole hanchans)."""
@@ -492,9 +494,15 @@ def run_replay(nonces, keys, replay, *, shuffle_kind=0, quick_eval=True, mask_bi
     scores = np.zeros((n, 4), dtype=np.int32)
     ranks = np.zeros((n, 4), dtype=np.uint8)
     steps = np.zeros(n, dtype=np.int32)
-    rc = lib().orc_run_replay2(n, nonces.ctypes.data, keys.ctypes.data, shuffle_kind, int(quick_eval), rp.ctypes.data,
-                               len(rp), None if mb is None else mb.ctypes.data, max_steps, n_threads,
-                               scores.ctypes.data, ranks.ctypes.data, steps.ctypes.data)
+    if quick_eval_seats is not None:  # uint8 [n, 4]: per-seat enable_quick_eval
+        qf = np.ascontiguousarray(quick_eval_seats, dtype=np.uint8).reshape(n, 4)
+        rc = lib().orc_run_replay3(n, nonces.ctypes.data, keys.ctypes.data, shuffle_kind, qf.ctypes.data, rp.ctypes.data,
+                                   len(rp), None if mb is None else mb.ctypes.data, max_steps, n_threads,
+                                   scores.ctypes.data, ranks.ctypes.data, steps.ctypes.data)
+    else:
+        rc = lib().orc_run_replay2(n, nonces.ctypes.data, keys.ctypes.data, shuffle_kind, int(quick_eval), rp.ctypes.data,
+                                   len(rp), None if mb is None else mb.ctypes.data, max_steps, n_threads,
+                                   scores.ctypes.data, ranks.ctypes.data, steps.ctypes.data)
     if rc != 0:
         raise RuntimeError(err())
     return dict(scores=scores, ranks=ranks, steps=steps)

@@ -649,3 +649,37 @@ def test_gameplay_loader_on_device_matches_oracle(mjx, tmp_path):
         for gp in per_player:
             ref = O.gameplay_load(events, gp.take_player_id(), version=4, sp_mode=0, with_obs=False, walls=walls)
             assert (gp.take_invisible_obs(host=True) == ref["invisible"]).all()
+
+
+def test_arena_agents_with_different_obs_version_and_quick_eval_on_device(mjx):
+    """agent/mortal.rs:54-74, 256-287 on the CUDA path: a version-4 quick-eval challenger against a version-3 champion without
+    quick-eval (device engines). Each engine is handed observations of its own layout; the recorded decisions and legal masks
+    replay in the oracle under the same per-seat settings, to the same scores."""
+    import torch
+
+    from mortal_b200.libriichi.arena import OneVsThree
+
+    class Eng:
+        engine_type = "mortal"; is_oracle = False; enable_rule_based_agari_guard = False
+
+        def __init__(self, name, version, qe):
+            self.name, self.version, self.enable_quick_eval, self.rows = name, version, qe, 0
+
+        def react_device(self, obs, masks):
+            assert obs.shape[1:] == ({3: 934, 4: 1012}[self.version], 34) and float(obs.min()) >= 0.0 and float(obs.max()) <= 1.0
+            self.rows += obs.shape[0]
+            q = torch.rand(masks.shape, device=masks.device).masked_fill(~masks, -1.0)
+            return q.argmax(-1), q
+
+    torch.manual_seed(7)
+    chal, champ = Eng("v4", 4, True), Eng("v3", 3, False)
+    arena = OneVsThree(disable_progress_bar=True)
+    arena.record_decisions = True
+    rankings = arena.py_vs_py(chal, champ, (6600, 12), 4)
+    assert sum(rankings) == 16 and chal.rows > 500 and champ.rows > 3 * chal.rows * 0.8
+    n = 16
+    nonces = np.repeat(np.arange(6600, 6604, dtype=np.uint64), 4)
+    keys = np.full(n, 12, dtype=np.uint64)
+    qf = np.array([[1 if seat == g % 4 else 0 for seat in range(4)] for g in range(n)], dtype=np.uint8)
+    ref = O.run_replay(nonces, keys, arena.last_decisions, mask_bits=arena.last_decision_masks, quick_eval_seats=qf)
+    assert (ref["scores"] == arena.last_results["scores"]).all() and (ref["ranks"] == arena.last_results["ranks"]).all()

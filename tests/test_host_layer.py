@@ -438,3 +438,36 @@ def test_arena_feeds_oracle_engines_the_invisible_observation():
     arena.max_cycles = 40
     arena.py_vs_py(Eng("o", True), Eng("p", False), (7100, 2), 2)
     assert seen["oracle_rows"] > 20 and seen["plain_calls"] > 20
+
+
+def test_arena_agents_with_different_obs_version_and_quick_eval():
+    """agent/mortal.rs:54-74, 256-287: `version` and `enable_quick_eval` belong to the agent. A version-4 quick-eval challenger
+    against a version-2 champion without quick-eval: each engine sees observations of its own layout, the champion's seats emit
+    rows for forced discards too, and the recorded decisions replay in the oracle with the same per-seat settings."""
+    from mortal_b200.libriichi.arena import OneVsThree
+
+    class Eng:
+        engine_type = "mortal"; is_oracle = False; enable_rule_based_agari_guard = False
+
+        def __init__(self, name, version, qe):
+            self.name, self.version, self.enable_quick_eval, self.rows = name, version, qe, 0
+
+        def react_batch(self, obs, masks, invisible_obs):
+            assert all(o.shape == ({2: 942, 4: 1012}[self.version], 34) for o in obs)
+            m = np.stack(masks)
+            self.rows += len(obs)
+            a = [int(np.nonzero(r)[0][0]) for r in m]  # the lowest legal action id
+            return a, np.where(m, 0.0, -np.inf).tolist(), m.tolist(), [True] * len(a)
+
+    chal, champ = Eng("c4", 4, True), Eng("c2", 2, False)
+    arena = _emul_arena(OneVsThree)
+    arena.record_decisions = True
+    arena.max_cycles = 70
+    arena.py_vs_py(chal, champ, (8100, 4), 2)
+    assert chal.rows > 50 and champ.rows > 3 * chal.rows * 0.8
+    n = 8
+    nonces = np.repeat(np.arange(8100, 8102, dtype=np.uint64), 4)
+    keys = np.full(n, 4, dtype=np.uint64)
+    qf = np.array([[1 if seat == g % 4 else 0 for seat in range(4)] for g in range(n)], dtype=np.uint8)
+    ref = O.run_replay(nonces, keys, arena.last_decisions, mask_bits=arena.last_decision_masks, max_steps=70, quick_eval_seats=qf)
+    assert (ref["steps"] == arena.last_results["steps"]).all()
