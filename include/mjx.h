@@ -116,6 +116,14 @@ int mjx_env_read_log(mjx_env* env, void* stream, uint64_t* words_host, int32_t* 
 int32_t* mjx_env_log_len_dev(mjx_env* env); /* int32 [n_tables] device view of the per-table word counts (null before enable_log):
                                               read after every step it tells which events that step wrote (per-decision meta) */
 
+/* dataset/grp.rs:90-164 without the logs: the GRP feature row of every kyoku — {grand_kyoku (E1 = 0 .. S4 = 7, W = 8+), honba,
+ * kyotaku, scores[4]} as int32 (the reference's f64 row is these with the scores divided by 10000) — is written by the step
+ * kernel when the kyoku starts. mjx_env_read_grp copies [n_tables, max_kyoku, 7] rows and the per-table kyoku counts (a count
+ * above max_kyoku = overflow); with mjx_env_results (final scores, rank_by_player) that is everything
+ * mortal/reward_calculator.py:13-38 consumes. Call mjx_env_enable_grp before the first step. */
+int mjx_env_enable_grp(mjx_env* env, int max_kyoku);
+int mjx_env_read_grp(mjx_env* env, void* stream, int32_t* feat_host, int32_t* n_kyoku_host);
+
 /* ---- log replay: dataset/gameplay.rs:247-449 GameplayLoader ------------------------------------------
  * A job = one (game log, player). `hdr`: the games' events as 64-bit words (csrc/mjx_step.cuh `log_word`; start_game = 15,
  * end_game = 16), concatenated, job j owning ev_cnt[j] words from ev_off[j]; `kyoku`: 19 words per start_kyoku (2 of scores, 17 = the

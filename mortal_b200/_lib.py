@@ -59,6 +59,8 @@ SYMBOLS = {
     "mjx_env_encode_obs_host_finish": (C.c_int, [C.c_void_p]),
     "mjx_env_sp_overflows": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "mjx_env_sp_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "mjx_env_enable_grp": (C.c_int, [C.c_void_p, C.c_int]),
+    "mjx_env_read_grp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mjx_env_enable_log": (C.c_int, [C.c_void_p, C.c_int]),
     "mjx_env_log_len_dev": (C.c_void_p, [C.c_void_p]),
     "mjx_env_read_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_step(EnvView V, Tables T) {
     c.lane = lane;
     c.df = s_scratch[warp].dora_factor;
     if (V.log) { c.log = V.log + (size_t)table * V.log_cap; c.log_n = V.log_len + table; c.log_cap = V.log_cap; }
+    if (V.grp) { c.grp = V.grp + (size_t)table * V.grp_cap * 7; c.grp_n = V.grp_len + table; c.grp_cap = V.grp_cap; }
     const i32 err_before = c.S->err;
     const bool live = step_table(c, V, table);
     __syncwarp();
@@ -751,7 +752,7 @@ void mjx_env_destroy(mjx_env* env) {
         cudaFree((void*)R.player); cudaFree(R.pos); cudaFree(R.ky_idx); cudaFree(R.ky_seen); cudaFree(R.row_label); cudaFree(R.row_meta);
     }
     for (int i = 0; i < 3; i++) if (env->ev_enc[i]) cudaEventDestroy(env->ev_enc[i]);
-    cudaFree(env->d_guard); cudaFree(env->d_quick_eval); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len);
+    cudaFree(env->d_guard); cudaFree(env->d_quick_eval); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len); cudaFree(env->V.grp); cudaFree(env->V.grp_len);
     SpGlobal& G = env->sp;
     cudaFree(G.rows); cudaFree(G.hkey); cudaFree(G.nsig); cudaFree(G.einfo); cudaFree(G.vals); cudaFree(G.echild); cudaFree(G.emeta);
     cudaFree(G.eowner); cudaFree(G.leaf_scores); cudaFree(G.wl); cudaFree(G.wl_count); cudaFree(G.counters);
@@ -918,6 +919,26 @@ int mjx_env_enable_log(mjx_env* env, int words_per_table) {
     CU(cudaMalloc(&env->V.log_len, (size_t)env->n_tables * sizeof(i32)));
     CU(cudaMemset(env->V.log_len, 0, (size_t)env->n_tables * sizeof(i32)));
     env->V.log_cap = words_per_table;
+    return MJX_OK;
+}
+
+int mjx_env_enable_grp(mjx_env* env, int max_kyoku) {
+    if (!env || max_kyoku <= 0) return fail(MJX_ERR_ARG, "mjx_env_enable_grp: bad arguments");
+    if (!env->first) return fail(MJX_ERR_STATE, "mjx_env_enable_grp: must be called before the first mjx_env_step");
+    if (env->V.grp) return MJX_OK;
+    CU(cudaMalloc(&env->V.grp, (size_t)env->n_tables * (size_t)max_kyoku * 7 * sizeof(i32)));
+    CU(cudaMalloc(&env->V.grp_len, (size_t)env->n_tables * sizeof(i32)));
+    CU(cudaMemset(env->V.grp_len, 0, (size_t)env->n_tables * sizeof(i32)));
+    env->V.grp_cap = max_kyoku;
+    return MJX_OK;
+}
+
+int mjx_env_read_grp(mjx_env* env, void* stream, int32_t* feat_host, int32_t* n_kyoku_host) {
+    if (!env || !feat_host || !n_kyoku_host) return fail(MJX_ERR_ARG, "mjx_env_read_grp: bad arguments");
+    if (!env->V.grp) return fail(MJX_ERR_STATE, "mjx_env_read_grp: mjx_env_enable_grp was not called");
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    CU(cudaMemcpy(n_kyoku_host, env->V.grp_len, (size_t)env->n_tables * sizeof(i32), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(feat_host, env->V.grp, (size_t)env->n_tables * (size_t)env->V.grp_cap * 7 * sizeof(i32), cudaMemcpyDeviceToHost));
     return MJX_OK;
 }
 

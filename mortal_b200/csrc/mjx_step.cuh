@@ -47,6 +47,10 @@ struct Ctx {
     u64* log = nullptr;
     i32* log_n = nullptr;
     int log_cap = 0;
+    // optional GRP feature rows of this table (dataset/grp.rs:134-147): 7 x i32 per kyoku, written when a kyoku starts
+    i32* grp = nullptr;
+    i32* grp_n = nullptr;
+    int grp_cap = 0;
 };
 
 // ---------------------------------------------------------------- event log (mjai/event.rs:20-120, compact form)
@@ -1069,6 +1073,15 @@ MJX_D void clear_reactions(Ctx& c) {
 MJX_DN void start_kyoku_board(Ctx& c) {
     TableState* S = c.S;
     if (MJX_IS_L0(c)) {
+        if (c.grp) {  // dataset/grp.rs:134-147: [grand_kyoku, honba, kyotaku, scores x 4] at the start of every kyoku
+            const int k = *c.grp_n;
+            if (k < c.grp_cap) {
+                i32* row = c.grp + (size_t)k * 7;
+                row[0] = S->kyoku; row[1] = S->honba; row[2] = S->kyotaku;
+                for (int i = 0; i < 4; i++) row[3 + i] = S->scores[i];
+            }
+            *c.grp_n = k + 1;
+        }
         make_wall(S->nonce, S->key, S->kyoku, S->honba, S->shuffle_kind, S->wall);
         S->oya = S->kyoku & 3;
         S->bflags = BF_CAN_FOUR_WIND;
@@ -1299,6 +1312,9 @@ struct EnvView {
     u64* log;           // [n_tables, log_cap] mjai event words (see log_word) or null
     i32* log_len;       // [n_tables] words written (may exceed log_cap: overflow)
     i32 log_cap;
+    i32* grp;           // [n_tables, grp_cap, 7] GRP feature rows (dataset/grp.rs:134-147) or null
+    i32* grp_len;       // [n_tables] kyoku started so far
+    i32 grp_cap;
 };
 
 MJX_D int alloc_rows(Ctx& c, EnvView& V, int n) {

@@ -190,6 +190,25 @@ class BatchEnv:
             raise RuntimeError(f"event log overflow: {int(lens.max())} words > capacity {self._log_cap}")
         return words, lens
 
+    def enable_grp(self, max_kyoku: int = 32) -> None:
+        """Record the GRP feature row of every kyoku on device (dataset/grp.rs:134-147); call before the first step."""
+        _lib.check(self.L.mjx_env_enable_grp(self._h, int(max_kyoku)), "mjx_env_enable_grp")
+        self._grp_cap = int(max_kyoku)
+
+    def read_grp(self):
+        """-> list (per table) of float64 [n_kyoku, 7] feature arrays, exactly dataset.Grp.take_feature() of the game's log"""
+        feat = np.zeros((self.n_tables, self._grp_cap, 7), dtype=np.int32)
+        cnt = np.zeros(self.n_tables, dtype=np.int32)
+        _lib.check(self.L.mjx_env_read_grp(self._h, self._stream(), feat.ctypes.data, cnt.ctypes.data), "mjx_env_read_grp")
+        if (cnt > self._grp_cap).any():
+            raise RuntimeError(f"GRP feature overflow: {int(cnt.max())} kyoku > capacity {self._grp_cap}")
+        out = []
+        for t in range(self.n_tables):
+            f = feat[t, : cnt[t]].astype(np.float64)
+            f[:, 3:] /= 10000.0
+            out.append(f)
+        return out
+
     def set_encode_timing(self, enable: bool) -> None:
         _lib.check(self.L.mjx_env_set_encode_timing(self._h, int(enable)), "mjx_env_set_encode_timing")
 

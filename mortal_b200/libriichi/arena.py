@@ -123,6 +123,8 @@ class _Part:
                 for seat in range(4):
                     qf[g, seat] = quick_evals[0] if self.ic_host[g % per, seat] else quick_evals[1]
             env.set_quick_eval(qf)
+        if arena.record_grp and hasattr(env, "enable_grp"):
+            env.enable_grp()
         self.meta_rec = None
         if arena.log_dir is not None:
             env.enable_log()
@@ -333,6 +335,8 @@ class _Arena:
         self.log_dir = log_dir  # arena/one_vs_three.rs:26-34: gz mjai logs are written here when set
         self.log_meta = True    # attach the per-decision meta (q-values, mask bits, ...) to the agent events (mortal.rs:161-186)
         self.last_meta_error = None
+        self.record_grp = False  # keep the per-kyoku GRP features of every game (read on device, no logs): last_grp
+        self.last_grp = None
         self.pipeline = True    # play the batch as two half-batches stepped alternately (see the module docstring)
         self.max_cycles = 0     # test hook: stop after this many BatchGame::run cycles (0 = play every table to the end)
         self.fast_forward_steps = 0  # bench hook: play this many batch steps with the counter-free test policy (kind 2) first
@@ -412,6 +416,11 @@ class _Arena:
                             self.last_meta_error = exc
                             bounds = decisions = None
                     self.last_log_paths += mjai_log.write_logs(self.log_dir, words, lens, seeds, names, "abcd"[:per], bounds, decisions)
+            if self.record_grp:  # dataset/grp.rs:90-164 straight from the table records: what reward_calculator.py:13-38 consumes
+                from ..dataset import Grp
+
+                feats = [f for p in parts for f in p.env.read_grp()]
+                self.last_grp = [Grp(feats[g], [int(x) for x in res["ranks"][g]], [int(x) for x in res["scores"][g]]) for g in range(n)]
             sp_overflows = sum(p.env.sp_overflows() for p in parts)
             self.last_stats = dict(cycles=max(p.cycles for p in parts), table_steps=int(res["steps"].sum()), sp_overflows=sp_overflows,
                                    parts=len(parts), launches=sum(p.env.launch_count() for p in parts if hasattr(p.env, "launch_count")))

@@ -49,6 +49,8 @@ def lib():
         L.emul_env_errs.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_env_row_steps.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_env_set_quick_eval.argtypes = [C.c_void_p, C.c_void_p]
+        L.emul_env_enable_grp.argtypes = [C.c_void_p, C.c_int]
+        L.emul_env_read_grp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emul_env_encode_invisible.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.emul_replay_trust_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.emul_replay_encode_invisible.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -121,6 +123,20 @@ class EmulEnv:
         a = np.full(self.row_cap, 45, dtype=np.int64)
         self.L.emul_env_policy_test(self._h, kind, a.ctypes.data)
         return a
+
+    def enable_grp(self, cap=32):
+        self._grp_cap = cap
+        self.L.emul_env_enable_grp(self._h, cap)
+
+    def read_grp(self):
+        feat = np.zeros((self.n_tables, self._grp_cap, 7), dtype=np.int32); cnt = np.zeros(self.n_tables, dtype=np.int32)
+        self.L.emul_env_read_grp(self._h, feat.ctypes.data, cnt.ctypes.data)
+        out = []
+        for t in range(self.n_tables):
+            f = feat[t, : cnt[t]].astype(np.float64)
+            f[:, 3:] /= 10000.0
+            out.append(f)
+        return out
 
     def enable_log(self, cap=8192):
         self._log_cap = cap

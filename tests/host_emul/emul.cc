@@ -122,6 +122,7 @@ struct EmulEnv {
     EnvView V;
     bool first = true;
     std::vector<u64> log; std::vector<i32> log_len; int log_cap = 0;
+    std::vector<i32> grp, grp_len; int grp_cap = 0;
     // log replay (mjx_replay.cuh)
     std::vector<u64> r_hdr, r_kyoku; std::vector<i32> r_ev_off, r_ev_cnt, r_ky_off, r_pos, r_ky_idx, r_ky_seen;
     std::vector<u8> r_player, r_meta; std::vector<i64> r_label;
@@ -155,6 +156,14 @@ void* emul_env_create(int n, const uint64_t* nonces, const uint64_t* keys, int s
     return E;
 }
 void emul_env_destroy(void* p) { delete static_cast<EmulEnv*>(p); }
+void emul_env_enable_grp(void* p, int cap) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    E->grp_cap = cap; E->grp.assign((size_t)E->n * cap * 7, 0); E->grp_len.assign(E->n, 0);
+}
+void emul_env_read_grp(void* p, int32_t* feat, int32_t* cnt) {
+    EmulEnv* E = static_cast<EmulEnv*>(p);
+    memcpy(feat, E->grp.data(), E->grp.size() * sizeof(i32)); memcpy(cnt, E->grp_len.data(), E->grp_len.size() * sizeof(i32));
+}
 void emul_env_set_quick_eval(void* p, const uint8_t* flags) {
     EmulEnv* E = static_cast<EmulEnv*>(p);
     static_assert(sizeof(u8) == 1, "");
@@ -172,6 +181,7 @@ int emul_env_step(void* p, const int64_t* actions) {
     for (int t = 0; t < E->n; t++) {
         Ctx c; c.S = &E->tabs[t]; c.W = &W; c.T = g_T; c.lane = 0; c.df = W.dora_factor;
         if (E->log_cap) { c.log = E->log.data() + (size_t)t * E->log_cap; c.log_n = &E->log_len[t]; c.log_cap = E->log_cap; }
+        if (E->grp_cap) { c.grp = E->grp.data() + (size_t)t * E->grp_cap * 7; c.grp_n = &E->grp_len[t]; c.grp_cap = E->grp_cap; }
         if (step_table(c, E->V, t)) live++;
     }
     return live;

