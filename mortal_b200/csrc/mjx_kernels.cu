@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_sp_eval(SpGlobal G, int level) {
         __shared__ SpEvalDBatch sd;
         sp_eval_d_level(G, sd, B, level);
     } else {
-        __shared__ SpEvalWBatch sw;
+        __shared__ SpEvalWBatch sw[SP_THREADS / 32];
         sp_eval_w_level<KIND == 2>(G, sw, B, level);
     }
 }

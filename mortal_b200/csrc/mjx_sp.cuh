@@ -559,7 +559,8 @@ struct SpEvalDBatch {
 // process with the reference's own operation sequence (k_sp_tables; 37.6 MB, L2-resident in its hot part), so the inner loop of
 // the evaluation performs the reference's rounded multiply-adds with a table load in place of two divisions and a multiply.
 constexpr int SP_NTS_DIM = SP_MAX_TILES_LEFT + 2;  // n_left, sum_required in 0..123
-constexpr int SP_TRI = SP_T_MAX * (SP_T_MAX + 1) / 2;  // (i, j) pairs, i <= j < 17, at j * (j + 1) / 2 + i
+constexpr int SP_TRI = SP_T_MAX * (SP_T_MAX + 1) / 2;  // (i, j) pairs, i <= j < 17: row i (j contiguous) starts at sp_tri_row(i)
+MJX_HD int sp_tri_row(int i) { return SP_T_MAX * i - i * (i - 1) / 2; }
 MJX_D size_t sp_ptab_index(int n_left, int i0) { return ((size_t)n_left * SP_NTS_DIM + (size_t)i0) * 4 * SP_TRI; }
 // one (n_left, i0) block of the table: [c][pair]
 MJX_D void sp_fill_ptab_block(float* blk, int n_left, int i0) {
@@ -574,16 +575,22 @@ MJX_D void sp_fill_ptab_block(float* blk, int n_left, int i0) {
         for (int j = 0; j < SP_T_MAX; j++) {
             // tsumo_prob_table[c][j] = (c + 1) / (n_left - j)  (calc.rs:136-146)
             const float tpj = (n_left - j > 0 && nts[j] != 0.f) ? SP_FMUL(SP_FDIV((float)(c + 1), (float)(n_left - j)), nts[j]) : 0.f;
-            for (int i = 0; i <= j; i++) blk[c * SP_TRI + j * (j + 1) / 2 + i] = nts[i] != 0.f ? SP_FDIV(tpj, nts[i]) : 0.f;
+            for (int i = 0; i <= j; i++) blk[c * SP_TRI + sp_tri_row(i) + (j - i)] = nts[i] != 0.f ? SP_FDIV(tpj, nts[i]) : 0.f;
         }
 }
 
-struct SpEvalWBatch {
-    u32 slot[SP_B], ebeg[SP_B], pbase[SP_B];
-    u8 ne[SP_B], T[SP_B], flags[SP_B], jend[SP_B];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei; jend: first j with not_tsumo[j] == 0
-    u16 aoff[SP_B + 1];
+constexpr int SP_WB = 7;  // W states per WARP mini-batch: 7 x ceil(17 / 2) = 63 (state, turn-pair) items = two full rounds of 32 lanes
+struct SpEvalWBatch {      // one per warp: the W evaluation needs no CTA-wide barrier
+    u32 slot[SP_WB], ebeg[SP_WB], pbase[SP_WB];
+    u8 ne[SP_WB], T[SP_WB], flags[SP_WB], jend[SP_WB];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei; jend: first j with not_tsumo[j] == 0
+    u16 aoff[SP_WB + 1];
     i32 n_a;
 };
+#ifdef MJX_HOST_EMUL
+#define SP_WSYNC() ((void)0)
+#else
+#define SP_WSYNC() __syncwarp()
+#endif
 template <typename Tb>
 MJX_D int sp_find_state(const u16* off, int nb, int item) {
     int lo = 0, hi = nb - 1;  // last state whose offset is <= item
@@ -613,13 +620,13 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
         S.jend[st] = (u8)max(0, min(Tn, lim + 1));
         S.pbase[st] = row_ok ? (u32)sp_ptab_index(n_left, i0) : 0u;
     }
-    SP_SYNC();
+    SP_WSYNC();
     if (B.tid == 0) {
         int aa = 0;
         for (int st = 0; st < nb; st++) { S.aoff[st] = (u16)aa; aa += (S.T[st] + 1) / 2; }
         S.aoff[nb] = (u16)aa; S.n_a = aa;
     }
-    SP_SYNC();
+    SP_WSYNC();
     // accumulation: a thread takes turns p and T-1-p of a state (T+1 draw turns together: balanced), edges in the reference's
     // order, j ascending, every multiply and add rounded as the reference rounds it
     SP_PFOR(item, S.n_a) {
@@ -627,6 +634,7 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
         const int Tn = S.T[st], ne = S.ne[st], jend = S.jend[st];
         const u32 eb = S.ebeg[st];
         const float* Pb = G.p_tab + S.pbase[st];
+        // row i of the probability triangle is contiguous in j: Pc[row(i) - i + j]
         const bool assume_riichi = (S.flags[st] & 1) != 0, dbl = (S.flags[st] & 2) != 0, haitei = (S.flags[st] & 4) != 0;
         const int i0 = p, i1 = Tn - 1 - p;
         const bool two = i1 > i0;
@@ -640,6 +648,8 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
             if (e + 1 < ne) { meta_n = G.emeta[eb + e + 1]; if (!LEAF) child_n = G.echild[eb + e + 1]; }
             if (!LEAF && e + 1 < ne && child_n != SP_NO_CHILD) sp_prefetch(G.vals + (size_t)child_n * SP_VALS);
             const float* Pc = Pb + (((meta >> 6) & 7) - 1) * SP_TRI;
+            const float* P0 = Pc + sp_tri_row(i0) - i0;
+            const float* P1 = Pc + sp_tri_row(i1 > 0 ? i1 : 0) - i1;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             const float* cv = nullptr;
             if (LEAF) {
@@ -656,7 +666,7 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
             // (the row is monotone: both are `>= jend`)
             if (i0 < jend)
                 for (int j = i0; j < jend; j++) {
-                    const float prob = Pc[j * (j + 1) / 2 + i0];
+                    const float prob = P0[j];
                     if (LEAF) {
                         const int han_plus = (assume_riichi && dbl && i0 == 0) + (assume_riichi && j == i0) + (haitei && j == Tn - 1);
                         const float sv = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : (han_plus == 2 ? s2 : s3));
@@ -673,7 +683,7 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
                 }
             if (two && i1 < jend)
                 for (int j = i1; j < jend; j++) {
-                    const float prob = Pc[j * (j + 1) / 2 + i1];
+                    const float prob = P1[j];
                     if (LEAF) {
                         const int han_plus = (assume_riichi && j == i1) + (haitei && j == Tn - 1);  // i1 > 0
                         const float sv = han_plus == 0 ? s0 : (han_plus == 1 ? s1 : s2);
@@ -693,7 +703,7 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
         o[i0] = t0; o[SP_T_MAX + i0] = w0; o[2 * SP_T_MAX + i0] = v0;
         if (two) { o[i1] = t1; o[SP_T_MAX + i1] = w1; o[2 * SP_T_MAX + i1] = v1; }
     }
-    SP_SYNC();
+    SP_WSYNC();
 }
 
 // calc.rs:563-637 discard_slow: per turn the child with the largest (truncated) EV, ties by discard priority
@@ -744,10 +754,14 @@ MJX_DN void sp_eval_d_level(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, 
     const int n = min(G.wl_count[level], G.wl_cap);
     for (int first = B.bid * SP_B; first < n; first += B.nblk * SP_B) sp_eval_d_batch(G, S, B, level, first, min(SP_B, n - first));
 }
+// every WARP works through its own mini-batches (S = the warp's staging area): no CTA-wide barrier, a slow state only holds its warp
 template <bool LEAF>
-MJX_DN void sp_eval_w_level(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, int level) {
+MJX_DN void sp_eval_w_level(const SpGlobal& G, SpEvalWBatch* S, const SpBlk& B, int level) {
     const int n = min(G.wl_count[level], G.wl_cap);
-    for (int first = B.bid * SP_B; first < n; first += B.nblk * SP_B) sp_eval_w_batch<LEAF>(G, S, B, level, first, min(SP_B, n - first));
+    const int lanes = B.nthr >= 32 ? 32 : B.nthr, wpc = B.nthr / lanes, warp = B.tid / lanes;
+    SpBlk W; W.tid = B.tid - warp * lanes; W.nthr = lanes; W.bid = B.bid * wpc + warp; W.nblk = B.nblk * wpc;
+    for (int first = W.bid * SP_WB; first < n; first += W.nblk * SP_WB)
+        sp_eval_w_batch<LEAF>(G, S[warp], W, level, first, min(SP_WB, n - first));
 }
 
 // release the table slots this DP used (instead of a full-table memset per step); after an overflow states may exist that

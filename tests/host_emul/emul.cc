@@ -343,8 +343,8 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
     for (int e = counters[4]; e < counters[5]; e++) sp_score_edge(G, g_T, e);
     for (int level = SP_SLOTS - 1; level >= 0; level--) {
         if (!sp_slot_is_w(level)) sp_eval_d_level(G, ed, B, level);
-        else if (level == SP_SLOTS - 1) sp_eval_w_level<true>(G, ew, B, level);
-        else sp_eval_w_level<false>(G, ew, B, level);
+        else if (level == SP_SLOTS - 1) sp_eval_w_level<true>(G, &ew, B, level);
+        else sp_eval_w_level<false>(G, &ew, B, level);
     }
     for (int r = 0; r < n_rows; r++) sp_stage_finalize(s, r, obs + (size_t)r * OBS_ROWS_V4 * OBS_COLS);
     if (counters[2]) g_emul_sp_overflows++;
