@@ -579,7 +579,7 @@ MJX_D void sp_fill_ptab_block(float* blk, int n_left, int i0) {
         }
 }
 
-constexpr int SP_WB = 7;  // W states per WARP mini-batch: 7 x ceil(17 / 2) = 63 (state, turn-pair) items = two full rounds of 32 lanes
+constexpr int SP_WB = 7;  // W states per WARP mini-batch: 7 x ceil(17 / 2) = 63 (state, turn-pair) items = two rounds of 32 lanes (16 per warp measured slower)
 struct SpEvalWBatch {      // one per warp: the W evaluation needs no CTA-wide barrier
     u32 slot[SP_WB], ebeg[SP_WB], pbase[SP_WB];
     u8 ne[SP_WB], T[SP_WB], flags[SP_WB], jend[SP_WB];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei; jend: first j with not_tsumo[j] == 0
