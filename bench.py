@@ -483,7 +483,7 @@ def run_ours(args):
     cn = None
     if not args.no_e2e_net:
         kn = max(3, min(K, args.e2e_net_steps))
-        cn = run_e2e(HostNetEngine(engine), 3, kn)
+        cn = run_e2e(HostNetEngine(engine), max(W, 4), kn)
         barrier()
     # what the link gives for the same bytes: one plain pinned D2H copy (context for e2e, not a claim)
     nprobe = max(1, c["rows"] // K)
@@ -710,10 +710,14 @@ def bench_algo_1m(torch, np, dev, args):
     ref = O.shanten(tiles, lens)
     cpu_s = time.perf_counter() - t0
     assert (d_o.cpu().numpy() == ref).all()
-    t0 = time.perf_counter()
     tmp = np.zeros(n, dtype=np.int8)
-    _lib.check(L.mjx_shanten_host(tiles.ctypes.data, lens.ctypes.data, tmp.ctypes.data, n), "mjx_shanten_host")
-    host_s = time.perf_counter() - t0
+    host_s = float("inf")
+    for _ in range(4):  # first call sizes the library's device scratch; best of the rest
+        t0 = time.perf_counter()
+        _lib.check(L.mjx_shanten_host(tiles.ctypes.data, lens.ctypes.data, tmp.ctypes.data, n), "mjx_shanten_host")
+        if _:
+            host_s = min(host_s, time.perf_counter() - t0)
+    assert (tmp == ref).all()
     out = {"shanten_1m": {"hands": n, "ms_per_launch": ms, "hands_per_s": n / (ms * 1e-3), "table_lookups_per_s": 4 * n / (ms * 1e-3),
                           "achieved": n * 36 / (ms * 1e-3) / 1e9, "unit": "GB/s", "bytes_per_hand": 36,
                           "note": "L2-latency bound (4 gathers into the 16 MB table per hand), not HBM bound; inputs resident in HBM, "
@@ -749,7 +753,7 @@ def main():
     ap.add_argument("--skip", type=int, default=300, help="untimed fast-forward batch steps before warm-up (both arms)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-baseline-steps", type=int, default=12, help="timed batch steps of the cpu_baseline leg of the default arm")
-    ap.add_argument("--e2e-net-steps", type=int, default=6)
+    ap.add_argument("--e2e-net-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-net", action="store_true")
     ap.add_argument("--no-algo-1m", action="store_true", help="skip BASELINE configs[2] (shanten / agari at 1M hands)")

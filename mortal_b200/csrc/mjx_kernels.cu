@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_state_query(EnvView V, Tabl
 
 // ---- single-player tables: level-synchronous DP over all rows of the step (csrc/mjx_sp.cuh)
 constexpr int SP_WARPS = 4;
-constexpr int MJX_HOST_COPY_GROUPS = 4;  // mjx_env_encode_obs_host: row groups of the SP block / D2H pipeline
+constexpr int MJX_HOST_COPY_GROUPS = 4;
+constexpr int MJX_SP_MAX_LANES = 4;  // mjx_env_encode_obs_host: row groups of the SP block / D2H pipeline
 
 __global__ void k_sp_begin(SpGlobal G) {
     if (threadIdx.x < SP_SLOTS) G.wl_count[threadIdx.x] = 0;
@@ -386,10 +387,16 @@ __global__ void k_sp_begin(SpGlobal G) {
     const int gwarp = blockIdx.x * SP_WARPS + warp, nwarps = gridDim.x * SP_WARPS;              \
     SpCtx s; s.G = G; s.T = T; s.df = s_df[warp]; s.lane = lane;
 
-__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_init(SpGlobal G, Tables T, EnvView V, int row_lo, int row_hi) {
+// rows [row_lo, min(n_rows, row_hi)) of the step, of which this launch takes the `part`-th of `parts` equal shares (the step's row
+// count only exists on the device, so concurrent DP lanes name their share as a fraction)
+#define SP_ROW_RANGE                                                                            \
+    const int span_ = max(min(*V.n_rows, row_hi) - row_lo, 0);                                  \
+    const int r0 = row_lo + (int)((long long)span_ * part / parts), r1 = row_lo + (int)((long long)span_ * (part + 1) / parts);
+
+__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_init(SpGlobal G, Tables T, EnvView V, int row_lo, int row_hi, int part, int parts) {
     SP_ROW_PROLOGUE
-    const int n_rows = min(*V.n_rows, row_hi);
-    for (int row = row_lo + gwarp; row < n_rows; row += nwarps)
+    SP_ROW_RANGE
+    for (int row = r0 + gwarp; row < r1; row += nwarps)
         sp_stage_init(s, V.tables + V.row_table[row], row, V.row_table[row], V.row_seat[row] & 3);
 }
 
@@ -428,10 +435,10 @@ __global__ void __launch_bounds__(128) k_sp_score(SpGlobal G, Tables T) {
 }
 
 __global__ void __launch_bounds__(SP_WARPS * 32) k_sp_finalize(SpGlobal G, Tables T, EnvView V, float* __restrict__ obs, int row_lo,
-                                                               int row_hi) {
+                                                               int row_hi, int part, int parts) {
     SP_ROW_PROLOGUE
-    const int n_rows = min(*V.n_rows, row_hi);
-    for (int row = row_lo + gwarp; row < n_rows; row += nwarps)
+    SP_ROW_RANGE
+    for (int row = r0 + gwarp; row < r1; row += nwarps)
         sp_stage_finalize(s, row, obs + (size_t)row * OBS_ROWS_V4 * OBS_COLS);
 }
 
@@ -560,6 +567,13 @@ struct mjx_env {
     u8* d_quick_eval = nullptr;
     SpGlobal sp;
     int sp_enabled = 1, sp_wanted = 1;
+    // concurrent DP lanes of the single-player block (mjx_env_encode_obs): lane 0 = `sp` on the caller's stream, lanes 1.. own a
+    // smaller state table and a side stream each; allocated on first use
+    SpGlobal sp_lane[MJX_SP_MAX_LANES - 1];
+    int sp_lanes = 1, sp_lanes_alloc = 1;
+    long long sp_want_slots = 0;
+    cudaStream_t sp_stream[MJX_SP_MAX_LANES - 1] = {};
+    cudaEvent_t ev_sp_fork = nullptr, ev_sp_join[MJX_SP_MAX_LANES - 1] = {};
     unsigned char* d_compact = nullptr;
     cudaEvent_t ev_enc[3] = {nullptr, nullptr, nullptr};  // optional per-kernel timing of the encoder pair (bench.py roofline)
     bool time_encode = false;
@@ -587,6 +601,53 @@ static void set_enc_args(mjx_env* env, int version) {
 template <int VER>
 static void launch_features(mjx_env* env, cudaStream_t st) {
     k_encode_features<VER><<<g_sm_count, EncF<VER>::WARPS * 32, EncF<VER>::SMEM, st>>>(env->V, g_T, env->d_compact, env->d_enc_work);
+}
+
+// device buffers of one DP instance (csrc/mjx_sp.cuh SpGlobal) for about `want` live states; `G.rows` is shared by all instances
+static int sp_alloc(SpGlobal& G, long long want) {
+    int hc = 1 << 20;
+    while (hc < want && hc < (1 << 26)) hc <<= 1;
+    G.hash_cap = hc;
+    G.p_tab = g_sp_p_tab;
+    G.wl_cap = hc / 2;       // per level
+    G.edge_cap = hc * 2;
+    G.score_cap = hc;
+    CU(cudaMalloc(&G.hkey, (size_t)G.hash_cap * sizeof(u64)));
+    CU(cudaMalloc(&G.nsig, (size_t)G.hash_cap * sizeof(SpSigP)));
+    CU(cudaMalloc(&G.einfo, (size_t)G.hash_cap * sizeof(u64)));
+    CU(cudaMalloc(&G.vals, (size_t)G.hash_cap * SP_VALS * sizeof(float)));
+    CU(cudaMalloc(&G.echild, (size_t)G.edge_cap * sizeof(u32)));
+    CU(cudaMalloc(&G.emeta, (size_t)G.edge_cap * sizeof(u16)));
+    CU(cudaMalloc(&G.eowner, (size_t)G.edge_cap * sizeof(u32)));
+    CU(cudaMalloc(&G.leaf_scores, (size_t)G.score_cap * 4 * sizeof(float)));
+    CU(cudaMalloc(&G.wl, (size_t)SP_SLOTS * G.wl_cap * sizeof(u32)));
+    CU(cudaMalloc(&G.wl_count, SP_SLOTS * sizeof(i32)));
+    CU(cudaMalloc(&G.counters, 8 * sizeof(i32)));
+    CU(cudaMemset(G.counters, 0, 8 * sizeof(i32)));
+    CU(cudaMemset(G.wl_count, 0, SP_SLOTS * sizeof(i32)));
+    CU(cudaMemset(G.hkey, 0xFF, (size_t)G.hash_cap * sizeof(u64)));  // SP_EMPTY; afterwards k_sp_release frees what a block used
+    return MJX_OK;
+}
+static SpGlobal& sp_of(mjx_env* env, int lane) { return lane == 0 ? env->sp : env->sp_lane[lane - 1]; }
+static void sp_free(SpGlobal& G) {
+    cudaFree(G.hkey); cudaFree(G.nsig); cudaFree(G.einfo); cudaFree(G.vals); cudaFree(G.echild); cudaFree(G.emeta);
+    cudaFree(G.eowner); cudaFree(G.leaf_scores); cudaFree(G.wl); cudaFree(G.wl_count); cudaFree(G.counters);
+}
+// lanes 1..n-1 (lane 0 is env->sp): each expects 1/n of the step's states and gets twice that
+static int sp_ensure_lanes(mjx_env* env, int lanes) {
+    if (env->sp_lanes_alloc >= lanes) return MJX_OK;
+    if (!env->ev_sp_fork) CU(cudaEventCreateWithFlags(&env->ev_sp_fork, cudaEventDisableTiming));
+    for (int g = env->sp_lanes_alloc; g < lanes; g++) {
+        SpGlobal& G = env->sp_lane[g - 1];
+        memset(&G, 0, sizeof G);
+        G.rows = env->sp.rows;
+        int rc = sp_alloc(G, env->sp_want_slots * 2 / lanes);
+        if (rc) return rc;
+        CU(cudaStreamCreateWithFlags(&env->sp_stream[g - 1], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&env->ev_sp_join[g - 1], cudaEventDisableTiming));
+        env->sp_lanes_alloc = g + 1;
+    }
+    return MJX_OK;
 }
 
 extern "C" {
@@ -698,32 +759,16 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
         CU(cudaMemset(env->d_enc_work, 0, sizeof(int)));
     }
     {
-        SpGlobal& G = env->sp;
         // state table: the slot index is the state id; ~3K slots per table keeps the load under ~20 % in the heaviest steps seen
         long long want = (long long)n_tables * 3072;
         if (const char* e = getenv("MJX_SP_SLOTS_PER_TABLE")) want = (long long)n_tables * atoll(e);
-        int hc = 1 << 20;
-        while (hc < want && hc < (1 << 26)) hc <<= 1;
-        G.hash_cap = hc;
-        G.p_tab = g_sp_p_tab;
-        G.wl_cap = hc / 2;       // per level
-        G.edge_cap = hc * 2;
-        G.score_cap = hc;
-        CU(cudaMalloc(&G.rows, cap * sizeof(SpRow)));
-        CU(cudaMalloc(&G.hkey, (size_t)G.hash_cap * sizeof(u64)));
-        CU(cudaMalloc(&G.nsig, (size_t)G.hash_cap * sizeof(SpSigP)));
-        CU(cudaMalloc(&G.einfo, (size_t)G.hash_cap * sizeof(u64)));
-        CU(cudaMalloc(&G.vals, (size_t)G.hash_cap * SP_VALS * sizeof(float)));
-        CU(cudaMalloc(&G.echild, (size_t)G.edge_cap * sizeof(u32)));
-        CU(cudaMalloc(&G.emeta, (size_t)G.edge_cap * sizeof(u16)));
-        CU(cudaMalloc(&G.eowner, (size_t)G.edge_cap * sizeof(u32)));
-        CU(cudaMalloc(&G.leaf_scores, (size_t)G.score_cap * 4 * sizeof(float)));
-        CU(cudaMalloc(&G.wl, (size_t)SP_SLOTS * G.wl_cap * sizeof(u32)));
-        CU(cudaMalloc(&G.wl_count, SP_SLOTS * sizeof(i32)));
-        CU(cudaMalloc(&G.counters, 8 * sizeof(i32)));
-        CU(cudaMemset(G.counters, 0, 8 * sizeof(i32)));
-        CU(cudaMemset(G.wl_count, 0, SP_SLOTS * sizeof(i32)));
-        CU(cudaMemset(G.hkey, 0xFF, (size_t)G.hash_cap * sizeof(u64)));  // SP_EMPTY; afterwards k_sp_release frees what a block used
+        env->sp_want_slots = want;
+        CU(cudaMalloc(&env->sp.rows, cap * sizeof(SpRow)));
+        int rc = sp_alloc(env->sp, want);
+        if (rc) return rc;
+        int lanes = n_tables >= 1024 ? MJX_SP_MAX_LANES : 1;  // small batches do not fill the SMs with one DP either, but launch-bound
+        if (const char* e = getenv("MJX_SP_LANES")) lanes = std::max(1, std::min(MJX_SP_MAX_LANES, atoi(e)));
+        env->sp_lanes = lanes;
     }
     CU(cudaMemset(env->d_dummy_actions, 0, sizeof(i64) * cap));
     CU(cudaMemset(V.masks, 0, cap * ACTION_SPACE));
@@ -753,9 +798,13 @@ void mjx_env_destroy(mjx_env* env) {
     }
     for (int i = 0; i < 3; i++) if (env->ev_enc[i]) cudaEventDestroy(env->ev_enc[i]);
     cudaFree(env->d_guard); cudaFree(env->d_quick_eval); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len); cudaFree(env->V.grp); cudaFree(env->V.grp_len);
-    SpGlobal& G = env->sp;
-    cudaFree(G.rows); cudaFree(G.hkey); cudaFree(G.nsig); cudaFree(G.einfo); cudaFree(G.vals); cudaFree(G.echild); cudaFree(G.emeta);
-    cudaFree(G.eowner); cudaFree(G.leaf_scores); cudaFree(G.wl); cudaFree(G.wl_count); cudaFree(G.counters);
+    cudaFree(env->sp.rows);
+    sp_free(env->sp);
+    for (int g = 1; g < env->sp_lanes_alloc; g++) {
+        sp_free(env->sp_lane[g - 1]);
+        cudaStreamDestroy(env->sp_stream[g - 1]); cudaEventDestroy(env->ev_sp_join[g - 1]);
+    }
+    if (env->ev_sp_fork) cudaEventDestroy(env->ev_sp_fork);
     cudaFree(env->d_state_words); cudaFree(env->d_state_pay); cudaFree(env->d_state_cans); cudaFree(env->d_state_misc);
     if (env->copy_stream) { cudaStreamDestroy(env->copy_stream); cudaEventDestroy(env->ev_rows); cudaEventDestroy(env->ev_sp); for (int g = 0; g < MJX_HOST_COPY_GROUPS; g++) cudaEventDestroy(env->ev_grp[g]); }
     delete env;
@@ -812,12 +861,12 @@ static int launch_encode_rows(mjx_env* env, float* obs_dev, cudaStream_t st) {
 
 // single-player block (rows 889..1011): init -> expand levels 0..7 -> score -> evaluate levels 7..0 -> finalize -> release
 // rows [row_lo, row_hi) of the step form one DP (the whole step by default; mjx_env_encode_obs_host runs it in row groups)
-static int launch_sp_block(mjx_env* env, float* obs_dev, cudaStream_t st, int row_lo = 0, int row_hi = 0x7fffffff) {
+static int launch_sp_block(mjx_env* env, const SpGlobal& G, float* obs_dev, cudaStream_t st, int row_lo = 0, int row_hi = 0x7fffffff,
+                           int part = 0, int parts = 1) {
     if (!env->sp_enabled) return MJX_OK;
-    const SpGlobal& G = env->sp;
     const int grid_rows = g_sm_count * 8, grid = g_sm_count * 8, grid_eval = g_sm_count * 16;
     k_sp_begin<<<1, 32, 0, st>>>(G);
-    k_sp_init<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, row_lo, row_hi);
+    k_sp_init<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, row_lo, row_hi, part, parts);
     for (int level = 0; level < SP_SLOTS; level++) {
         if (level == SP_SLOTS - 1) {
             k_sp_mark<<<1, 1, 0, st>>>(G, 0);
@@ -832,7 +881,7 @@ static int launch_sp_block(mjx_env* env, float* obs_dev, cudaStream_t st, int ro
         else if (level == SP_SLOTS - 1) k_sp_eval<2><<<grid_eval, SP_THREADS, 0, st>>>(G, level);
         else k_sp_eval<1><<<grid_eval, SP_THREADS, 0, st>>>(G, level);
     }
-    k_sp_finalize<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev, row_lo, row_hi);
+    k_sp_finalize<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev, row_lo, row_hi, part, parts);
     k_sp_release<<<g_sm_count * 4, 256, 0, st>>>(G);
     CU(cudaGetLastError());
     env->launches += 6 + 2 * SP_SLOTS + 1;
@@ -843,8 +892,21 @@ int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
     if (!env || !obs_dev) return fail(MJX_ERR_ARG, "mjx_env_encode_obs: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_encode_rows(env, obs_dev, st);
-    if (rc) return rc;
-    return launch_sp_block(env, obs_dev, st);
+    if (rc || !env->sp_enabled) return rc;
+    const int lanes = env->sp_lanes;
+    if (lanes <= 1) return launch_sp_block(env, env->sp, obs_dev, st);
+    // The step's rows are solved as `lanes` independent DPs on concurrent streams: the latency-bound launches of one lane (small
+    // levels, init / finalize / release, the tails of every level) run under the other lanes' work.
+    if ((rc = sp_ensure_lanes(env, lanes))) return rc;
+    CU(cudaEventRecord(env->ev_sp_fork, st));
+    for (int g = 1; g < lanes; g++) {
+        CU(cudaStreamWaitEvent(env->sp_stream[g - 1], env->ev_sp_fork, 0));
+        if ((rc = launch_sp_block(env, env->sp_lane[g - 1], obs_dev, env->sp_stream[g - 1], 0, 0x7fffffff, g, lanes))) return rc;
+        CU(cudaEventRecord(env->ev_sp_join[g - 1], env->sp_stream[g - 1]));
+    }
+    if ((rc = launch_sp_block(env, env->sp, obs_dev, st, 0, 0x7fffffff, 0, lanes))) return rc;
+    for (int g = 1; g < lanes; g++) CU(cudaStreamWaitEvent(st, env->ev_sp_join[g - 1], 0));
+    return MJX_OK;
 }
 
 int mjx_oracle_obs_rows(int version) { return (version >= 1 && version <= 4) ? oracle_obs_rows(version) : MJX_ERR_ARG; }
@@ -899,7 +961,7 @@ int mjx_env_encode_obs_host_begin(mjx_env* env, float* obs_dev, float* obs_host,
         for (int g = 0; g < GROUPS; g++) {
             const int r0 = (int)((long long)n * g / GROUPS), r1 = (int)((long long)n * (g + 1) / GROUPS);
             if (r1 <= r0) continue;
-            rc = launch_sp_block(env, obs_dev, st, r0, r1);
+            rc = launch_sp_block(env, env->sp, obs_dev, st, r0, r1);
             if (rc) return rc;
             CU(cudaEventRecord(env->ev_grp[g], st));
             CU(cudaStreamWaitEvent(env->copy_stream, env->ev_grp[g], 0));
@@ -1139,22 +1201,28 @@ int mjx_env_set_sp(mjx_env* env, int enable) {
 
 int mjx_env_sp_overflows(mjx_env* env, void* stream, int* n) {
     if (!env || !n) return fail(MJX_ERR_ARG, "mjx_env_sp_overflows: bad arguments");
-    int cnt[4] = {0, 0, 0, 0};
-    CU(cudaMemcpyAsync(cnt, env->sp.counters, sizeof cnt, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    int cnt[MJX_SP_MAX_LANES][4] = {};
+    for (int g = 0; g < env->sp_lanes_alloc; g++)
+        CU(cudaMemcpyAsync(cnt[g], sp_of(env, g).counters, sizeof cnt[g], cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    *n = cnt[3] + (cnt[2] ? 1 : 0);
+    *n = 0;
+    for (int g = 0; g < env->sp_lanes_alloc; g++) *n += cnt[g][3] + (cnt[g][2] ? 1 : 0);
     return MJX_OK;
 }
 
 int mjx_env_sp_stats(mjx_env* env, void* stream, int* out10) {
     if (!env || !out10) return fail(MJX_ERR_ARG, "mjx_env_sp_stats: bad arguments");
-    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    CU(cudaMemcpyAsync(cnt, env->sp.counters, sizeof cnt, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CU(cudaMemcpyAsync(out10 + 2, env->sp.wl_count, SP_SLOTS * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    int cnt[MJX_SP_MAX_LANES][8] = {}, wl[MJX_SP_MAX_LANES][SP_SLOTS] = {};
+    for (int g = 0; g < env->sp_lanes_alloc; g++) {
+        CU(cudaMemcpyAsync(cnt[g], sp_of(env, g).counters, sizeof cnt[g], cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CU(cudaMemcpyAsync(wl[g], sp_of(env, g).wl_count, sizeof wl[g], cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    }
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    out10[0] = 0;
-    for (int i = 0; i < SP_SLOTS; i++) out10[0] += out10[2 + i];  // states = sum of the level work lists
-    out10[1] = cnt[1];                                            // edges
+    for (int i = 0; i < 10; i++) out10[i] = 0;
+    for (int g = 0; g < env->sp_lanes_alloc; g++) {
+        for (int i = 0; i < SP_SLOTS; i++) { out10[2 + i] += wl[g][i]; out10[0] += wl[g][i]; }  // states = sum of the level work lists
+        out10[1] += cnt[g][1];                                                                    // edges
+    }
     return MJX_OK;
 }
 
@@ -1169,14 +1237,16 @@ int mjx_env_poll(mjx_env* env, void* stream, int* out4) {
     if (!env || !out4) return fail(MJX_ERR_ARG, "mjx_env_poll: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long c[4] = {0, 0, 0, 0};
-    int sp[4] = {0, 0, 0, 0};
+    int sp[MJX_SP_MAX_LANES][4] = {};
     CU(cudaMemcpyAsync(&out4[0], env->V.n_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c, env->V.counters, sizeof c, cudaMemcpyDeviceToHost, st));
-    if (env->sp.counters) CU(cudaMemcpyAsync(sp, env->sp.counters, sizeof sp, cudaMemcpyDeviceToHost, st));
+    if (env->sp.counters)
+        for (int g = 0; g < env->sp_lanes_alloc; g++) CU(cudaMemcpyAsync(sp[g], sp_of(env, g).counters, sizeof sp[g], cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     out4[1] = (int)c[0];
     out4[2] = (int)c[2];
-    out4[3] = sp[3] + (sp[2] ? 1 : 0);
+    out4[3] = 0;
+    for (int g = 0; g < env->sp_lanes_alloc; g++) out4[3] += sp[g][3] + (sp[g][2] ? 1 : 0);
     return MJX_OK;
 }
 
@@ -1284,39 +1354,61 @@ int mjx_agari(const mjx_agari_in* in_dev, mjx_agari_out* out_dev, int n, int mod
     return MJX_OK;
 }
 
+// grow-only device scratch of the *_host entry points (they are called repeatedly with similar sizes: no cudaMalloc per call)
+namespace {
+struct HostScratch {
+    std::mutex mu;
+    void* p[3] = {nullptr, nullptr, nullptr};
+    size_t cap[3] = {0, 0, 0};
+    int reserve(int i, size_t bytes, void** out) {
+        if (cap[i] < bytes) {
+            cudaFree(p[i]); p[i] = nullptr; cap[i] = 0;
+            size_t want = 1 << 16;
+            while (want < bytes) want <<= 1;
+            cudaError_t e = cudaMalloc(&p[i], want);
+            if (e != cudaSuccess) return fail(MJX_ERR_CUDA, cudaGetErrorString(e));
+            cap[i] = want;
+        }
+        *out = p[i];
+        return MJX_OK;
+    }
+};
+HostScratch g_host_scratch;
+}  // namespace
+
 int mjx_shanten_host(const uint8_t* tiles, const uint8_t* len_div3, int8_t* out, int n) {
     if (!g_ready) return fail(MJX_ERR_STATE, "mjx_shanten_host: call mjx_init first");
     if (n <= 0) return MJX_OK;
-    u8 *d_t = nullptr, *d_l = nullptr;
-    i8* d_o = nullptr;
-    CU(cudaMalloc(&d_t, (size_t)n * 34));
-    CU(cudaMalloc(&d_l, (size_t)n));
-    CU(cudaMalloc(&d_o, (size_t)n));
+    std::lock_guard<std::mutex> lk(g_host_scratch.mu);
+    void *d_t = nullptr, *d_l = nullptr, *d_o = nullptr;
+    int rc;
+    if ((rc = g_host_scratch.reserve(0, (size_t)n * 34, &d_t)) || (rc = g_host_scratch.reserve(1, (size_t)n, &d_l)) ||
+        (rc = g_host_scratch.reserve(2, (size_t)n, &d_o)))
+        return rc;
     CU(cudaMemcpy(d_t, tiles, (size_t)n * 34, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d_l, len_div3, (size_t)n, cudaMemcpyHostToDevice));
-    int rc = mjx_shanten(d_t, d_l, (int8_t*)d_o, n, nullptr);
+    rc = mjx_shanten((const uint8_t*)d_t, (const uint8_t*)d_l, (int8_t*)d_o, n, nullptr);
     if (rc == MJX_OK) {
         cudaError_t e = cudaMemcpy(out, d_o, (size_t)n, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(MJX_ERR_CUDA, cudaGetErrorString(e));
     }
-    cudaFree(d_t); cudaFree(d_l); cudaFree(d_o);
     return rc;
 }
 
 int mjx_agari_host(const mjx_agari_in* in, mjx_agari_out* out, int n, int mode) {
     if (!g_ready) return fail(MJX_ERR_STATE, "mjx_agari_host: call mjx_init first");
     if (n <= 0) return MJX_OK;
-    mjx_agari_in* d_i = nullptr;
-    mjx_agari_out* d_o = nullptr;
-    CU(cudaMalloc(&d_i, sizeof(mjx_agari_in) * (size_t)n));
-    CU(cudaMalloc(&d_o, sizeof(mjx_agari_out) * (size_t)n));
+    std::lock_guard<std::mutex> lk(g_host_scratch.mu);
+    void *d_i = nullptr, *d_o = nullptr;
+    int rc;
+    if ((rc = g_host_scratch.reserve(0, sizeof(mjx_agari_in) * (size_t)n, &d_i)) || (rc = g_host_scratch.reserve(1, sizeof(mjx_agari_out) * (size_t)n, &d_o)))
+        return rc;
     CU(cudaMemcpy(d_i, in, sizeof(mjx_agari_in) * (size_t)n, cudaMemcpyHostToDevice));
-    int rc = mjx_agari(d_i, d_o, n, mode, nullptr);
+    rc = mjx_agari((const mjx_agari_in*)d_i, (mjx_agari_out*)d_o, n, mode, nullptr);
     if (rc == MJX_OK) {
         cudaError_t e = cudaMemcpy(out, d_o, sizeof(mjx_agari_out) * (size_t)n, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(MJX_ERR_CUDA, cudaGetErrorString(e));
     }
-    cudaFree(d_i); cudaFree(d_o);
     return rc;
 }
 

@@ -103,10 +103,23 @@ class DeviceEngine:
 
     # the reference protocol, for callers that only know libriichi's calling convention
     def react_batch(self, obs, masks, invisible_obs):
-        o = torch.as_tensor(np.stack(obs, axis=0), device=self.device)
-        m = torch.as_tensor(np.stack(masks, axis=0), device=self.device)
+        o = torch.as_tensor(_stack_rows(obs), device=self.device)
+        m = torch.as_tensor(_stack_rows(masks), device=self.device)
         actions, q, greedy = self.react_device(o, m, return_greedy=True)
         return actions.tolist(), q.float().tolist(), m.tolist(), greedy.tolist()
+
+
+def _stack_rows(rows):
+    """np.stack(rows) without the copy when the rows already are consecutive slices of one buffer — which is how the arena hands
+    them out (views over the pinned buffer mjx_env_encode_obs_host filled), so the H2D copy then reads pinned memory directly."""
+    first = rows[0]
+    n, step = len(rows), first.nbytes
+    if n > 1 and first.flags.c_contiguous and step:
+        p0 = first.__array_interface__["data"][0]
+        if all(r.__array_interface__["data"][0] == p0 + i * step and r.shape == first.shape and r.dtype == first.dtype
+               for i, r in enumerate(rows)):
+            return np.lib.stride_tricks.as_strided(first, shape=(n, *first.shape), strides=(step, *first.strides), writeable=bool(first.flags.writeable))
+    return np.stack(rows, axis=0)
 
 
 def sample_top_p(logits, p):

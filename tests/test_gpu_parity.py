@@ -265,6 +265,44 @@ def test_encode_obs_host_equals_device_encode(mjx):
     env.close()
 
 
+def test_sp_lanes_give_the_single_dp_result(mjx, monkeypatch):
+    """mjx_env_encode_obs solves the single-player block as several concurrent DPs (row shares on side streams) for large batches;
+    forced on here for a small batch (MJX_SP_LANES): every observation equals the one-DP result bit for bit, no overflow."""
+    import torch
+
+    n = 96
+    nonces = np.arange(900, 900 + n, dtype=np.uint64)
+    keys = np.full(n, 11, dtype=np.uint64)
+    envs = []
+    for lanes in ("1", "3", "4"):
+        monkeypatch.setenv("MJX_SP_LANES", lanes)
+        envs.append(mjx.BatchEnv(nonces, keys))
+    actions = [torch.zeros(env.row_cap, dtype=torch.int64, device=env.device) for env in envs]
+    for env in envs:
+        env.step(None)
+
+    def ordered(env, obs):  # rows are appended by atomics: compare in (table, seat | kan-select) order
+        nr = env.num_rows()
+        key = env.row_table[:nr].long() * 8 + env.row_seat[:nr].long()
+        return obs[:nr][torch.argsort(key)]
+
+    checked = 0
+    for cycle in range(80):
+        ref = ordered(envs[0], envs[0].encode_obs())
+        for env in envs[1:]:
+            got = ordered(env, env.encode_obs())
+            assert got.shape == ref.shape and torch.equal(got, ref)
+        checked += ref.shape[0]
+        for env, a in zip(envs, actions):
+            env.policy_test(2, a)
+            env.step(a)
+    assert checked > 80 * n * 0.9
+    assert all(env.sp_overflows() == 0 for env in envs)
+    assert envs[2].sp_stats() == envs[0].sp_stats()  # states / edges / per-level counts summed over the lanes
+    for env in envs:
+        env.close()
+
+
 def test_one_vs_three_network_policy_action_replay(mjx):
     """BASELINE config 2 protocol (SURVEY.md §8d ii): a float policy (random-init Mortal brain, greedy) drives the CUDA
     arena through the libriichi-compatible OneVsThree.py_vs_py; the recorded decisions are replayed in the oracle,
