@@ -567,13 +567,15 @@ struct mjx_env {
     u8* d_quick_eval = nullptr;
     SpGlobal sp;
     int sp_enabled = 1, sp_wanted = 1;
-    // concurrent DP lanes of the single-player block (mjx_env_encode_obs): lane 0 = `sp` on the caller's stream, lanes 1.. own a
-    // smaller state table and a side stream each; allocated on first use
+    // concurrent DP lanes of the single-player block (mjx_env_encode_obs): every lane runs on a side stream of its own while the
+    // caller's stream runs the two encoder kernels; lane 0 = `sp`, lanes 1.. own a smaller state table each, allocated on first use
     SpGlobal sp_lane[MJX_SP_MAX_LANES - 1];
     int sp_lanes = 1, sp_lanes_alloc = 1;
+    int sp_grid_x = 10, sp_grid_e = 16;  // CTAs per SM of the expansion / evaluation launches
+    int sp_thr_x = SP_THREADS, sp_thr_e = SP_THREADS;
     long long sp_want_slots = 0;
-    cudaStream_t sp_stream[MJX_SP_MAX_LANES - 1] = {};
-    cudaEvent_t ev_sp_fork = nullptr, ev_sp_join[MJX_SP_MAX_LANES - 1] = {};
+    cudaStream_t sp_stream[MJX_SP_MAX_LANES] = {};
+    cudaEvent_t ev_sp_fork = nullptr, ev_sp_store = nullptr, ev_sp_join[MJX_SP_MAX_LANES] = {};
     unsigned char* d_compact = nullptr;
     cudaEvent_t ev_enc[3] = {nullptr, nullptr, nullptr};  // optional per-kernel timing of the encoder pair (bench.py roofline)
     bool time_encode = false;
@@ -635,16 +637,21 @@ static void sp_free(SpGlobal& G) {
 }
 // lanes 1..n-1 (lane 0 is env->sp): each expects 1/n of the step's states and gets twice that
 static int sp_ensure_lanes(mjx_env* env, int lanes) {
-    if (env->sp_lanes_alloc >= lanes) return MJX_OK;
-    if (!env->ev_sp_fork) CU(cudaEventCreateWithFlags(&env->ev_sp_fork, cudaEventDisableTiming));
+    if (!env->ev_sp_fork) {
+        CU(cudaEventCreateWithFlags(&env->ev_sp_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&env->ev_sp_store, cudaEventDisableTiming));
+    }
+    for (int g = 0; g < lanes; g++)
+        if (!env->sp_stream[g]) {
+            CU(cudaStreamCreateWithFlags(&env->sp_stream[g], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&env->ev_sp_join[g], cudaEventDisableTiming));
+        }
     for (int g = env->sp_lanes_alloc; g < lanes; g++) {
         SpGlobal& G = env->sp_lane[g - 1];
         memset(&G, 0, sizeof G);
         G.rows = env->sp.rows;
         int rc = sp_alloc(G, env->sp_want_slots * 2 / lanes);
         if (rc) return rc;
-        CU(cudaStreamCreateWithFlags(&env->sp_stream[g - 1], cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&env->ev_sp_join[g - 1], cudaEventDisableTiming));
         env->sp_lanes_alloc = g + 1;
     }
     return MJX_OK;
@@ -766,9 +773,13 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
         CU(cudaMalloc(&env->sp.rows, cap * sizeof(SpRow)));
         int rc = sp_alloc(env->sp, want);
         if (rc) return rc;
-        int lanes = n_tables >= 1024 ? MJX_SP_MAX_LANES : 1;  // small batches do not fill the SMs with one DP either, but launch-bound
+        int lanes = n_tables >= 1024 ? 2 : 1;  // small batches do not fill the SMs with one DP either, but launch-bound
         if (const char* e = getenv("MJX_SP_LANES")) lanes = std::max(1, std::min(MJX_SP_MAX_LANES, atoi(e)));
         env->sp_lanes = lanes;
+        if (const char* e = getenv("MJX_SP_GRID_X")) env->sp_grid_x = std::max(1, atoi(e));
+        if (const char* e = getenv("MJX_SP_GRID_E")) env->sp_grid_e = std::max(1, atoi(e));
+        if (const char* e = getenv("MJX_SP_THR_X")) env->sp_thr_x = std::max(32, std::min(SP_THREADS, atoi(e) / 32 * 32));
+        if (const char* e = getenv("MJX_SP_THR_E")) env->sp_thr_e = std::max(32, std::min(SP_THREADS, atoi(e) / 32 * 32));
     }
     CU(cudaMemset(env->d_dummy_actions, 0, sizeof(i64) * cap));
     CU(cudaMemset(V.masks, 0, cap * ACTION_SPACE));
@@ -800,11 +811,10 @@ void mjx_env_destroy(mjx_env* env) {
     cudaFree(env->d_guard); cudaFree(env->d_quick_eval); cudaFree(env->d_compact); cudaFree(env->d_enc_work); cudaFree(env->V.log); cudaFree(env->V.log_len); cudaFree(env->V.grp); cudaFree(env->V.grp_len);
     cudaFree(env->sp.rows);
     sp_free(env->sp);
-    for (int g = 1; g < env->sp_lanes_alloc; g++) {
-        sp_free(env->sp_lane[g - 1]);
-        cudaStreamDestroy(env->sp_stream[g - 1]); cudaEventDestroy(env->ev_sp_join[g - 1]);
-    }
-    if (env->ev_sp_fork) cudaEventDestroy(env->ev_sp_fork);
+    for (int g = 1; g < env->sp_lanes_alloc; g++) sp_free(env->sp_lane[g - 1]);
+    for (int g = 0; g < MJX_SP_MAX_LANES; g++)
+        if (env->sp_stream[g]) { cudaStreamDestroy(env->sp_stream[g]); cudaEventDestroy(env->ev_sp_join[g]); }
+    if (env->ev_sp_fork) { cudaEventDestroy(env->ev_sp_fork); cudaEventDestroy(env->ev_sp_store); }
     cudaFree(env->d_state_words); cudaFree(env->d_state_pay); cudaFree(env->d_state_cans); cudaFree(env->d_state_misc);
     if (env->copy_stream) { cudaStreamDestroy(env->copy_stream); cudaEventDestroy(env->ev_rows); cudaEventDestroy(env->ev_sp); for (int g = 0; g < MJX_HOST_COPY_GROUPS; g++) cudaEventDestroy(env->ev_grp[g]); }
     delete env;
@@ -861,26 +871,28 @@ static int launch_encode_rows(mjx_env* env, float* obs_dev, cudaStream_t st) {
 
 // single-player block (rows 889..1011): init -> expand levels 0..7 -> score -> evaluate levels 7..0 -> finalize -> release
 // rows [row_lo, row_hi) of the step form one DP (the whole step by default; mjx_env_encode_obs_host runs it in row groups)
+// `before_finalize`: an event the stream waits for before the block writes into the observations (the rows must have been stored)
 static int launch_sp_block(mjx_env* env, const SpGlobal& G, float* obs_dev, cudaStream_t st, int row_lo = 0, int row_hi = 0x7fffffff,
-                           int part = 0, int parts = 1) {
+                           int part = 0, int parts = 1, cudaEvent_t before_finalize = nullptr) {
     if (!env->sp_enabled) return MJX_OK;
-    const int grid_rows = g_sm_count * 8, grid = g_sm_count * 8, grid_eval = g_sm_count * 16;
+    const int grid_rows = g_sm_count * 8, grid = g_sm_count * env->sp_grid_x, grid_eval = g_sm_count * env->sp_grid_e;
     k_sp_begin<<<1, 32, 0, st>>>(G);
     k_sp_init<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, row_lo, row_hi, part, parts);
     for (int level = 0; level < SP_SLOTS; level++) {
         if (level == SP_SLOTS - 1) {
             k_sp_mark<<<1, 1, 0, st>>>(G, 0);
-            k_sp_expand<2><<<grid, SP_THREADS, 0, st>>>(G, g_T, level);
-        } else if (sp_slot_is_w(level)) k_sp_expand<1><<<grid, SP_THREADS, 0, st>>>(G, g_T, level);
-        else k_sp_expand<0><<<grid, SP_THREADS, 0, st>>>(G, g_T, level);
+            k_sp_expand<2><<<grid, env->sp_thr_x, 0, st>>>(G, g_T, level);
+        } else if (sp_slot_is_w(level)) k_sp_expand<1><<<grid, env->sp_thr_x, 0, st>>>(G, g_T, level);
+        else k_sp_expand<0><<<grid, env->sp_thr_x, 0, st>>>(G, g_T, level);
     }
     k_sp_mark<<<1, 1, 0, st>>>(G, 1);
     k_sp_score<<<g_sm_count * 16, 128, 0, st>>>(G, g_T);
     for (int level = SP_SLOTS - 1; level >= 0; level--) {
-        if (!sp_slot_is_w(level)) k_sp_eval<0><<<grid_eval, SP_THREADS, 0, st>>>(G, level);
-        else if (level == SP_SLOTS - 1) k_sp_eval<2><<<grid_eval, SP_THREADS, 0, st>>>(G, level);
-        else k_sp_eval<1><<<grid_eval, SP_THREADS, 0, st>>>(G, level);
+        if (!sp_slot_is_w(level)) k_sp_eval<0><<<grid_eval, env->sp_thr_e, 0, st>>>(G, level);
+        else if (level == SP_SLOTS - 1) k_sp_eval<2><<<grid_eval, env->sp_thr_e, 0, st>>>(G, level);
+        else k_sp_eval<1><<<grid_eval, env->sp_thr_e, 0, st>>>(G, level);
     }
+    if (before_finalize) CU(cudaStreamWaitEvent(st, before_finalize, 0));
     k_sp_finalize<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev, row_lo, row_hi, part, parts);
     k_sp_release<<<g_sm_count * 4, 256, 0, st>>>(G);
     CU(cudaGetLastError());
@@ -891,21 +903,27 @@ static int launch_sp_block(mjx_env* env, const SpGlobal& G, float* obs_dev, cuda
 int mjx_env_encode_obs(mjx_env* env, float* obs_dev, void* stream) {
     if (!env || !obs_dev) return fail(MJX_ERR_ARG, "mjx_env_encode_obs: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_encode_rows(env, obs_dev, st);
-    if (rc || !env->sp_enabled) return rc;
-    const int lanes = env->sp_lanes;
-    if (lanes <= 1) return launch_sp_block(env, env->sp, obs_dev, st);
-    // The step's rows are solved as `lanes` independent DPs on concurrent streams: the latency-bound launches of one lane (small
-    // levels, init / finalize / release, the tails of every level) run under the other lanes' work.
-    if ((rc = sp_ensure_lanes(env, lanes))) return rc;
-    CU(cudaEventRecord(env->ev_sp_fork, st));
-    for (int g = 1; g < lanes; g++) {
-        CU(cudaStreamWaitEvent(env->sp_stream[g - 1], env->ev_sp_fork, 0));
-        if ((rc = launch_sp_block(env, env->sp_lane[g - 1], obs_dev, env->sp_stream[g - 1], 0, 0x7fffffff, g, lanes))) return rc;
-        CU(cudaEventRecord(env->ev_sp_join[g - 1], env->sp_stream[g - 1]));
+    const int lanes = env->sp_enabled ? env->sp_lanes : 0;
+    int rc;
+    if (lanes <= 1) {
+        if ((rc = launch_encode_rows(env, obs_dev, st))) return rc;
+        return lanes ? launch_sp_block(env, env->sp, obs_dev, st) : MJX_OK;
     }
-    if ((rc = launch_sp_block(env, env->sp, obs_dev, st, 0, 0x7fffffff, 0, lanes))) return rc;
-    for (int g = 1; g < lanes; g++) CU(cudaStreamWaitEvent(st, env->ev_sp_join[g - 1], 0));
+    // The step's rows are solved as `lanes` independent DPs on concurrent side streams while this stream runs the two encoder
+    // kernels: the latency-bound launches of one lane (small levels, init / finalize / release, the tail of every level) and the
+    // bandwidth-bound store run under the other lanes' work. A lane only touches the observations in its last kernel, after the store.
+    if ((rc = sp_ensure_lanes(env, lanes))) return rc;
+    // (with mjx_env_set_encode_timing the lanes start after the store, so that the two encoder kernels are timed alone)
+    if (!env->time_encode) CU(cudaEventRecord(env->ev_sp_fork, st));
+    if ((rc = launch_encode_rows(env, obs_dev, st))) return rc;
+    CU(cudaEventRecord(env->ev_sp_store, st));
+    if (env->time_encode) CU(cudaEventRecord(env->ev_sp_fork, st));
+    for (int g = 0; g < lanes; g++) {
+        CU(cudaStreamWaitEvent(env->sp_stream[g], env->ev_sp_fork, 0));
+        if ((rc = launch_sp_block(env, sp_of(env, g), obs_dev, env->sp_stream[g], 0, 0x7fffffff, g, lanes, env->ev_sp_store))) return rc;
+        CU(cudaEventRecord(env->ev_sp_join[g], env->sp_stream[g]));
+    }
+    for (int g = 0; g < lanes; g++) CU(cudaStreamWaitEvent(st, env->ev_sp_join[g], 0));
     return MJX_OK;
 }
 
