@@ -224,6 +224,14 @@ int mjx_nn_affine_mish_bf16(const void* x, const float* scale, const float* bias
 int mjx_nn_pool_bf16(const void* x, void* avg, void* mx, int batch, int length, int channels, void* stream);  /* [batch, channels] each */
 int mjx_nn_gate_residual_bf16(const void* y, const void* gate, const void* x, void* out, int batch, int length, int channels,
                               void* stream);                                 /* out = y * gate[b, c] + x */
+/* The tail of a residual block and the next pre-activation in one pass (model.py ChannelAttention + residual; next BN + Mish):
+ * gate = sigmoid(mlp(mean_l y) + mlp(max_l y)), mlp = w2 . mish(w1 [hidden, channels] . v + b1) + b2, w2 passed TRANSPOSED as w2t
+ * [hidden, channels] (fp32 device
+ * arrays); x_out = y * gate + x; a_out = mish(x_out * scale[c] + bias[c]). Two launches: one warp per batch row computes the gate,
+ * one streaming pass applies it. channels % 8 == 0, <= 256. */
+int mjx_nn_block_tail_bf16(const void* y, const void* x, const float* w1, const float* b1, const float* w2t, const float* b2,
+                           const float* scale, const float* bias, void* gate_scratch /* bf16 [batch, channels] */, void* x_out,
+                           void* a_out, int batch, int length, int channels, int hidden, void* stream);
 
 /* ---- standalone kernels (BASELINE configs 3/4) ------------------------------------------------ */
 /* algo/shanten.rs:138-150 calc_all: tiles_dev uint8 [n,34], len_div3_dev uint8 [n] -> int8 [n]. */

@@ -1321,13 +1321,22 @@ static int nn_grid(size_t n_items) {
     const size_t cap = (size_t)g_sm_count * 16;
     return (int)(g < cap ? (g ? g : 1) : cap);
 }
+// a grid of 256-thread CTAs whose total thread count is a multiple of c8 (every thread then keeps one channel group for the whole
+// grid-stride loop): gridDim is rounded up to a multiple of c8 / gcd(c8, 256)
+static int nn_grid_for(size_t n_items, int c8) {
+    int q = c8, p = 256;
+    while (p) { const int t = q % p; q = p; p = t; }  // q = gcd(c8, 256)
+    const int unit = c8 / q;
+    const int g = nn_grid(n_items);
+    return (g + unit - 1) / unit * unit;
+}
 int mjx_nn_affine_mish_bf16(const void* x, const float* scale, const float* bias, void* out, long long n_elems, int channels,
                             void* stream) {
     if (!x || !scale || !bias || !out || channels <= 0 || channels % 8 || n_elems % channels)
         return fail(MJX_ERR_ARG, "mjx_nn_affine_mish_bf16: bad arguments");
     if (!g_ready) return fail(MJX_ERR_STATE, "mjx_nn_*: call mjx_init first");
     const size_t n_vec = (size_t)n_elems / 8;
-    mjx_nn::k_affine_mish<<<nn_grid(n_vec), 256, 0, (cudaStream_t)stream>>>((const mjx_nn::Vec8*)x, scale, bias, (mjx_nn::Vec8*)out,
+    mjx_nn::k_affine_mish<<<nn_grid_for(n_vec, channels / 8), 256, 0, (cudaStream_t)stream>>>((const mjx_nn::Vec8*)x, scale, bias, (mjx_nn::Vec8*)out,
                                                                             n_vec, channels / 8);
     CU(cudaGetLastError());
     return MJX_OK;
@@ -1338,6 +1347,27 @@ int mjx_nn_pool_bf16(const void* x, void* avg, void* mx, int batch, int length, 
     if (!g_ready) return fail(MJX_ERR_STATE, "mjx_nn_*: call mjx_init first");
     mjx_nn::k_pool<<<nn_grid((size_t)batch * (channels / 8)), 256, 0, (cudaStream_t)stream>>>(
         (const mjx_nn::Vec8*)x, (mjx_nn::Vec8*)avg, (mjx_nn::Vec8*)mx, batch, length, channels / 8);
+    CU(cudaGetLastError());
+    return MJX_OK;
+}
+int mjx_nn_block_tail_bf16(const void* y, const void* x, const float* w1, const float* b1, const float* w2t, const float* b2,
+                           const float* scale, const float* bias, void* gate_scratch, void* x_out, void* a_out, int batch, int length,
+                           int channels, int hidden, void* stream) {
+    if (!y || !x || !w1 || !b1 || !w2t || !b2 || !scale || !bias || !gate_scratch || !x_out || !a_out || batch <= 0 || length <= 0 ||
+        channels <= 0 || channels % 8 || channels > 256 || hidden <= 0 || hidden > 64)
+        return fail(MJX_ERR_ARG, "mjx_nn_block_tail_bf16: bad arguments (channels % 8 == 0, <= 256; hidden <= 64)");
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_nn_*: call mjx_init first");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int c8 = channels / 8;
+    const int warps_per_cta = 8;
+    const int grid = std::max(1, std::min((batch + warps_per_cta - 1) / warps_per_cta, g_sm_count * 8));
+    mjx_nn::k_pool_gate<<<grid, warps_per_cta * 32, 0, st>>>((const mjx_nn::Vec8*)y, w1, b1, w2t, b2, (mjx_nn::Vec8*)gate_scratch, batch, length,
+                                                               c8, hidden);
+    CU(cudaGetLastError());
+    const size_t n_vec = (size_t)batch * length * c8;
+    mjx_nn::k_gate_residual_mish<<<nn_grid_for(n_vec, c8), 256, 0, st>>>(
+        (const mjx_nn::Vec8*)y, (const mjx_nn::Vec8*)gate_scratch, (const mjx_nn::Vec8*)x, scale, bias, (mjx_nn::Vec8*)x_out,
+        (mjx_nn::Vec8*)a_out, n_vec, length, c8);
     CU(cudaGetLastError());
     return MJX_OK;
 }

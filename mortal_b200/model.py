@@ -110,6 +110,9 @@ class Brain(nn.Module):
             self.to(dtype)
         self._aff = [(PreActBlock._affine(b.bn1), PreActBlock._affine(b.bn2)) for b in self.blocks]
         self._aff_out = PreActBlock._affine(self.bn)
+        # the channel-gate MLPs as fp32 copies of the (possibly down-cast) parameters, for the fused block tail
+        f32 = lambda t: t.detach().float().contiguous()
+        self._gate32 = [(f32(b.gate.fc1.weight), f32(b.gate.fc1.bias), f32(b.gate.fc2.weight.t()), f32(b.gate.fc2.bias)) for b in self.blocks]
         # the Conv1d kernels as (1 x 3) Conv2d kernels in channels_last, so cuDNN runs NHWC without layout round trips
         cl = lambda conv: conv.weight.unsqueeze(2).contiguous(memory_format=torch.channels_last)
         self._w = [(cl(b.conv1), cl(b.conv2)) for b in self.blocks]
@@ -124,14 +127,24 @@ class Brain(nn.Module):
         x = obs.unsqueeze(2).contiguous(memory_format=torch.channels_last)  # [B, C, 1, 34]
         x = F.conv2d(x, self._w_stem, padding=(0, 1))
         fused = x.is_cuda and x.dtype == torch.bfloat16
-        for blk, aff, (w1, w2), a32 in zip(self.blocks, self._aff, self._w, self._aff32):
-            x = blk.forward_fast(x, aff, w1, w2, a32 if fused else None)
-        s, b = self._aff_out
         if fused:
+            # libmjx kernels (csrc/mjx_nn.cuh) around the cuDNN convolutions: per block one BN-affine+Mish pass and one pass for
+            # everything between conv2 and the next block's conv1 (pooling, gate MLP, sigmoid, gate * y + x, next BN-affine+Mish)
             from . import nn_ops
 
-            x = nn_ops.affine_mish(x, *self._aff32_out)
+            n = len(self.blocks)
+            a = nn_ops.affine_mish(x, *self._aff32[0][0]) if n else nn_ops.affine_mish(x, *self._aff32_out)
+            for i in range(n):
+                (w1, w2), (_, (f2, g2)) = self._w[i], self._aff32[i]
+                y = F.conv2d(a, w1, padding=(0, 1))
+                y = F.conv2d(nn_ops.affine_mish(y, f2, g2), w2, padding=(0, 1))
+                nxt = self._aff32[i + 1][0] if i + 1 < n else self._aff32_out
+                x, a = nn_ops.block_tail(y, x, *self._gate32[i], *nxt)
+            x = a
         else:
+            for blk, aff, (w1, w2) in zip(self.blocks, self._aff, self._w):
+                x = blk.forward_fast(x, aff, w1, w2, None)
+            s, b = self._aff_out
             x = F.mish(torch.addcmul(b, x, s))
         x = F.mish(F.conv2d(x, self._w_neck, self.neck.bias, padding=(0, 1)))
         return F.mish(self.fc(x.flatten(1)))

@@ -48,3 +48,21 @@ def gate_residual(y: torch.Tensor, gate: torch.Tensor, x: torch.Tensor) -> torch
     _lib.check(_lib.load().mjx_nn_gate_residual_bf16(C.c_void_p(y.data_ptr()), C.c_void_p(gate.data_ptr()), C.c_void_p(x.data_ptr()),
                                                      C.c_void_p(out.data_ptr()), b, l, c, _stream(y)), "mjx_nn_gate_residual_bf16")
     return out
+
+
+def block_tail(y: torch.Tensor, x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2t: torch.Tensor, b2: torch.Tensor,
+               scale: torch.Tensor, bias: torch.Tensor):
+    """Channel gate + residual + the next pre-activation: gate = sigmoid(mlp(mean_L y) + mlp(max_L y)) with
+    mlp(v) = w2 @ mish(w1 @ v + b1) + b2 (float32: w1 [H, C], w2t = w2.T [H, C]); returns (y * gate + x, mish((y * gate + x) * scale + bias))."""
+    b, c, l = _check_nhwc(y)
+    assert _check_nhwc(x) == (b, c, l)
+    h = w1.shape[0]
+    for t, shape in ((w1, (h, c)), (b1, (h,)), (w2t, (h, c)), (b2, (c,)), (scale, (c,)), (bias, (c,))):
+        assert t.dtype == torch.float32 and tuple(t.shape) == shape and t.is_contiguous() and t.is_cuda
+    assert c <= 256, "block_tail: at most 256 channels"
+    x_out, a_out = torch.empty_like(y), torch.empty_like(y)
+    gate = torch.empty((b, c), dtype=torch.bfloat16, device=y.device)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(_lib.load().mjx_nn_block_tail_bf16(p(y), p(x), p(w1), p(b1), p(w2t), p(b2), p(scale), p(bias), p(gate), p(x_out), p(a_out),
+                                                  b, l, c, h, _stream(y)), "mjx_nn_block_tail_bf16")
+    return x_out, a_out
