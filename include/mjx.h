@@ -224,6 +224,9 @@ int mjx_nn_affine_mish_bf16(const void* x, const float* scale, const float* bias
 int mjx_nn_pool_bf16(const void* x, void* avg, void* mx, int batch, int length, int channels, void* stream);  /* [batch, channels] each */
 int mjx_nn_gate_residual_bf16(const void* y, const void* gate, const void* x, void* out, int batch, int length, int channels,
                               void* stream);                                 /* out = y * gate[b, c] + x */
+/* observations f32 [batch, channels, length] -> bf16 channels-last [batch, length, channels_padded], padded channels zero
+ * (channels_padded % 64 == 0): the input of the stem convolution. */
+int mjx_nn_obs_to_nhwc_bf16(const float* obs, void* out, int batch, int channels, int length, int channels_padded, void* stream);
 /* The tail of a residual block and the next pre-activation in one pass (model.py ChannelAttention + residual; next BN + Mish):
  * gate = sigmoid(mlp(mean_l y) + mlp(max_l y)), mlp = w2 . mish(w1 [hidden, channels] . v + b1) + b2, w2 passed TRANSPOSED as w2t
  * [hidden, channels] (fp32 device

@@ -1350,6 +1350,18 @@ int mjx_nn_pool_bf16(const void* x, void* avg, void* mx, int batch, int length, 
     CU(cudaGetLastError());
     return MJX_OK;
 }
+int mjx_nn_obs_to_nhwc_bf16(const float* obs, void* out, int batch, int channels, int length, int channels_padded, void* stream) {
+    if (!obs || !out || batch <= 0 || channels <= 0 || length <= 0 || length > 128 || channels_padded < channels ||
+        channels_padded % mjx_nn::NHWC_TC)
+        return fail(MJX_ERR_ARG, "mjx_nn_obs_to_nhwc_bf16: bad arguments (channels_padded a multiple of 64, length <= 128)");
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_nn_*: call mjx_init first");
+    const size_t smem = (size_t)mjx_nn::NHWC_TC * (length + 1) * sizeof(float);
+    const long long grid = (long long)batch * (channels_padded / mjx_nn::NHWC_TC);
+    if (grid > 0x7fffffffLL) return fail(MJX_ERR_ARG, "mjx_nn_obs_to_nhwc_bf16: batch too large");
+    mjx_nn::k_obs_to_nhwc<<<(int)grid, 256, smem, (cudaStream_t)stream>>>(obs, (__nv_bfloat16*)out, channels, length, channels_padded);
+    CU(cudaGetLastError());
+    return MJX_OK;
+}
 int mjx_nn_block_tail_bf16(const void* y, const void* x, const float* w1, const float* b1, const float* w2t, const float* b2,
                            const float* scale, const float* bias, void* gate_scratch, void* x_out, void* a_out, int batch, int length,
                            int channels, int hidden, void* stream) {

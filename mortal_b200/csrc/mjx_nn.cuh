@@ -195,4 +195,30 @@ __global__ void __launch_bounds__(256) k_gate_residual_mish(const Vec8* __restri
     }
 }
 
+// The network's first step as one pass: observations f32 [batch, channels, length] (libriichi's layout: one row of `length` floats
+// per channel) -> bf16 channels-last [batch, length, cpad] with the channel count padded with zeros to a multiple of 64, which is
+// what the stem convolution's implicit GEMM wants (PyTorch + cuDNN otherwise run a cast, a layout copy and two padding kernels).
+// One CTA = 64 channels of one observation through a shared-memory tile.
+constexpr int NHWC_TC = 64;
+__global__ void __launch_bounds__(256) k_obs_to_nhwc(const float* __restrict__ obs, __nv_bfloat16* __restrict__ out, int channels, int length,
+                                                     int cpad) {
+    extern __shared__ float tile[];  // [NHWC_TC][length + 1]
+    const int chunks = cpad / NHWC_TC;
+    const int b = blockIdx.x / chunks, c0 = (blockIdx.x - b * chunks) * NHWC_TC;
+    const int nc = max(0, min(NHWC_TC, channels - c0));  // real channels in this chunk
+    const float* src = obs + ((size_t)b * channels + c0) * length;
+    const int pitch = length + 1;
+    for (int i = threadIdx.x; i < nc * length; i += blockDim.x) {
+        const int c = i / length, l = i - c * length;
+        tile[c * pitch + l] = src[i];
+    }
+    __syncthreads();
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * length) * cpad + c0);
+    for (int i = threadIdx.x; i < length * (NHWC_TC / 2); i += blockDim.x) {
+        const int l = i / (NHWC_TC / 2), c = (i - l * (NHWC_TC / 2)) * 2;
+        const float a = c < nc ? tile[c * pitch + l] : 0.f, bb = c + 1 < nc ? tile[(c + 1) * pitch + l] : 0.f;
+        dst[(size_t)l * (cpad / 2) + c / 2] = __floats2bfloat162_rn(a, bb);
+    }
+}
+
 }  // namespace mjx_nn

@@ -117,16 +117,27 @@ class Brain(nn.Module):
         cl = lambda conv: conv.weight.unsqueeze(2).contiguous(memory_format=torch.channels_last)
         self._w = [(cl(b.conv1), cl(b.conv2)) for b in self.blocks]
         self._w_stem, self._w_neck = cl(self.stem), cl(self.neck)
+        # the stem with its input channels zero-padded to a multiple of 64 (1012 -> 1024): nn_ops.obs_to_nhwc emits that layout
+        cin = self.stem.weight.shape[1]
+        self._cpad = (cin + 63) // 64 * 64
+        wp = torch.zeros((self.stem.weight.shape[0], self._cpad, 3), dtype=self.stem.weight.dtype, device=self.stem.weight.device)
+        wp[:, :cin] = self.stem.weight.detach()
+        self._w_stem_pad = wp.unsqueeze(2).contiguous(memory_format=torch.channels_last)
         self._fast_dtype = dtype
         return self
 
     def forward_fast(self, obs):
         F = torch.nn.functional
-        if self._fast_dtype is not None:
-            obs = obs.to(self._fast_dtype)
-        x = obs.unsqueeze(2).contiguous(memory_format=torch.channels_last)  # [B, C, 1, 34]
-        x = F.conv2d(x, self._w_stem, padding=(0, 1))
-        fused = x.is_cuda and x.dtype == torch.bfloat16
+        fused = obs.is_cuda and self._fast_dtype == torch.bfloat16
+        if fused and obs.dtype == torch.float32 and obs.is_contiguous():
+            from . import nn_ops
+
+            x = F.conv2d(nn_ops.obs_to_nhwc(obs, self._cpad), self._w_stem_pad, padding=(0, 1))
+        else:
+            if self._fast_dtype is not None:
+                obs = obs.to(self._fast_dtype)
+            x = obs.unsqueeze(2).contiguous(memory_format=torch.channels_last)  # [B, C, 1, 34]
+            x = F.conv2d(x, self._w_stem, padding=(0, 1))
         if fused:
             # libmjx kernels (csrc/mjx_nn.cuh) around the cuDNN convolutions: per block one BN-affine+Mish pass and one pass for
             # everything between conv2 and the next block's conv1 (pooling, gate MLP, sigmoid, gate * y + x, next BN-affine+Mish)

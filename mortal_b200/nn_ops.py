@@ -66,3 +66,14 @@ def block_tail(y: torch.Tensor, x: torch.Tensor, w1: torch.Tensor, b1: torch.Ten
     _lib.check(_lib.load().mjx_nn_block_tail_bf16(p(y), p(x), p(w1), p(b1), p(w2t), p(b2), p(scale), p(bias), p(gate), p(x_out), p(a_out),
                                                   b, l, c, h, _stream(y)), "mjx_nn_block_tail_bf16")
     return x_out, a_out
+
+
+def obs_to_nhwc(obs: torch.Tensor, channels_padded: int) -> torch.Tensor:
+    """f32 [B, C, L] (contiguous) -> bf16 [B, channels_padded, 1, L] in channels_last memory format, extra channels zero."""
+    assert obs.is_cuda and obs.dtype == torch.float32 and obs.dim() == 3 and obs.is_contiguous()
+    b, c, l = obs.shape
+    assert channels_padded >= c and channels_padded % 64 == 0
+    out = torch.empty((b, channels_padded, 1, l), dtype=torch.bfloat16, device=obs.device, memory_format=torch.channels_last)
+    _lib.check(_lib.load().mjx_nn_obs_to_nhwc_bf16(C.c_void_p(obs.data_ptr()), C.c_void_p(out.data_ptr()), b, c, l, channels_padded,
+                                                   _stream(obs)), "mjx_nn_obs_to_nhwc_bf16")
+    return out

@@ -607,6 +607,12 @@ def test_fused_policy_net_kernels_match_torch(mjx):
     assert dev_old.max().item() <= 0.2, dev_old.max().item()  # that pipeline rounds pooled vectors, hidden layer and logits to bf16
     assert dev_old.median().item() <= 0.0
 
+    # the stem's input transform: f32 [B, C, L] -> bf16 channels-last, channels zero-padded to a multiple of 64 (exact)
+    o3 = torch.randn(37, 1012, 34, device=dev)
+    t = nn_ops.obs_to_nhwc(o3, 1024)
+    assert t.shape == (37, 1024, 1, 34) and t.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(t[:, :1012, 0, :], o3.to(torch.bfloat16)) and (t[:, 1012:] == 0).all()
+
     brain = Brain(conv_channels=192, num_blocks=6).to(dev).eval()
     for m in brain.modules():
         if isinstance(m, torch.nn.BatchNorm1d):
