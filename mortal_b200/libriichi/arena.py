@@ -338,6 +338,7 @@ class _Arena:
         self.record_grp = False  # keep the per-kyoku GRP features of every game (read on device, no logs): last_grp
         self.last_grp = None
         self.pipeline = True    # play the batch as two half-batches stepped alternately (see the module docstring)
+        self.pipeline_device_engines = False  # the same for device engines (env kernels of one half under the other half's forward)
         self.max_cycles = 0     # test hook: stop after this many BatchGame::run cycles (0 = play every table to the end)
         self.fast_forward_steps = 0  # bench hook: play this many batch steps with the counter-free test policy (kind 2) first
         self.cycle_hook = None       # bench hook: callable(cycle_index, run_state) when the first part starts a cycle
@@ -369,7 +370,7 @@ class _Arena:
         # half-size forward passes on two streams measured slower than one full-size pass (profiles/r02_summary.md).
         cuts = [0, n]
         host_engines = all(isinstance(a, HostProtocolEngine) for a in agents)
-        if self.pipeline and host_engines and seed_count >= 2:
+        if self.pipeline and (host_engines or self.pipeline_device_engines) and seed_count >= 2:
             cuts = [0, (seed_count // 2) * per, n]
         parts = []
         try:
