@@ -1,4 +1,5 @@
-"""The shanten lookup tables are generated from first principles (tools/gen_shanten_tables.cc); this pins the generator."""
+"""The shanten and agari lookup tables are generated from first principles (tools/gen_shanten_tables.cc,
+tools/gen_agari_table.py); this pins the generators."""
 import gzip
 import os
 import sys
@@ -52,3 +53,53 @@ def test_installed_tables_are_the_generated_ones(generated):
     for name in ("shanten_suhai.bin", "shanten_jihai.bin"):
         with open(os.path.join(ROOT, "mortal_b200", "data", name), "rb") as f:
             assert f.read() == generated[name], name
+
+
+@pytest.fixture(scope="module")
+def agari_table():
+    import gen_agari_table
+
+    return gen_agari_table.generate()
+
+
+def test_agari_table_known_answers(agari_table):
+    import gen_agari_table as g
+
+    assert len(agari_table) == 9_362
+    # 123 456 789 + 123 + 11-pair in another suit: one split, four runs, straight flag, pair is the last kind
+    key = g.shape_key([[1] * 9, [1, 1, 1], [2]])
+    (div,) = agari_table[key]
+    assert div & 7 == 0 and (div >> 3) & 7 == 4 and (div >> 6) & 15 == 12 and div & g.F_ITTSUU
+    # seven separate pairs: the seven-pairs flag alone; 11223344556677: three splits with two double runs each, no seven-pairs flag
+    assert agari_table[g.shape_key([[2]] * 7)] == [g.F_CHITOI]
+    divs = agari_table[g.shape_key([[2] * 7])]
+    assert len(divs) == 3 and all(d & g.F_RYANPEIKOU and not d & g.F_CHITOI for d in divs)
+    # nine gates on its 9th tile: 1112345678999 + 5
+    assert all(d & g.F_CHUUREN for d in agari_table[g.shape_key([[3, 1, 1, 1, 2, 1, 1, 1, 3]])])
+    # 45556 (five concealed tiles beside three called melds): the one split is the pair 55 + the run 456
+    assert agari_table[g.shape_key([[1, 3, 1]])] == [0 | 1 << 3 | 1 << 6 | 0 << 10]
+    # 111222333444 + pair: {four triplets} and {123 123 123 + 444}; the table never lists {111 + 234 234 234}
+    divs = agari_table[g.shape_key([[3, 3, 3, 3], [2]])]
+    assert [(d & 7, (d >> 3) & 7) for d in divs] == [(4, 0), (1, 3)] and (divs[1] >> 10) & 15 == 3
+    # every div decodes to as many melds as the hand holds
+    for key, divs in agari_table.items():
+        for d in divs:
+            if d & g.F_CHITOI:
+                continue
+            assert (d & 7) + ((d >> 3) & 7) <= 4
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box): generator is pinned in the dev container")
+def test_agari_table_equals_reference_data(agari_table):
+    import gen_agari_table as g
+
+    with gzip.open(os.path.join(REF, "agari.bin.gz"), "rb") as f:
+        ref = g.parse(f.read())
+    assert ref == agari_table  # key -> ordered list of divs; the record order of the file is not content (agari.rs:22-51)
+
+
+def test_installed_agari_table_is_the_generated_one(agari_table):
+    import gen_agari_table as g
+
+    with open(os.path.join(ROOT, "mortal_b200", "data", "agari.bin"), "rb") as f:
+        assert f.read() == g.serialize(agari_table)

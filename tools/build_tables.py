@@ -6,8 +6,11 @@ to the GPU box like a built .so).
   the rank counts; no input files) and truncated to the row counts of libriichi's tables (1,940,777 / 78,032 rows:
   indices past the end read as an all-zero row in the reference, algo/shanten.rs:52, and that quirk is part of the
   contract). When the reference tree is present the result is checked byte for byte against its data files.
-* agari.bin (9,362 keys) is data libriichi ships gzipped under libriichi/src/algo/data/; it is only gunzipped here.
-  On a box without /root/reference the prebuilt file is used. Formats: SURVEY.md Appendix A.
+* agari.bin (9,362 keys) is GENERATED from first principles by tools/gen_agari_table.py (enumeration of all hand shapes
+  that split into melds + pair or seven pairs; no input files). Records are written in ascending key order; when the
+  reference tree is present the result is checked against libriichi's data file as key -> ordered div list (the
+  reference loads its file into a hash map, agari.rs:22-51, so the order of records is not content).
+Nothing is copied from the reference any more. Formats: SURVEY.md Appendix A.
 """
 import gzip
 import os
@@ -40,6 +43,20 @@ def generate_shanten_tables() -> dict:
     return out
 
 
+def generate_agari_table() -> bytes:
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import gen_agari_table
+
+    table = gen_agari_table.generate()
+    raw = gen_agari_table.serialize(table)
+    assert len(table) == 9_362 and len(raw) == FILES["agari.bin"][1]
+    ref_path = os.path.join(REF, FILES["agari.bin"][0])
+    if os.path.exists(ref_path):
+        with gzip.open(ref_path, "rb") as f:
+            assert gen_agari_table.parse(f.read()) == table, "agari.bin: generated table differs from the reference's data file"
+    return raw
+
+
 def main() -> int:
     os.makedirs(OUT, exist_ok=True)
     todo = [n for n in ("shanten_suhai.bin", "shanten_jihai.bin")
@@ -54,20 +71,16 @@ def main() -> int:
             with open(os.path.join(OUT, name), "wb") as f:
                 f.write(gen[name])
             print(f"build_tables: generated {name} ({len(gen[name])} bytes)")
-    for out_name, (src, size) in FILES.items():
-        dst = os.path.join(OUT, out_name)
-        if os.path.exists(dst) and os.path.getsize(dst) == size:
-            continue
-        src_path = os.path.join(REF, src)
-        if not os.path.exists(src_path):
-            print(f"build_tables: {src_path} missing and {dst} not prebuilt", file=sys.stderr)
-            return 1
-        with gzip.open(src_path, "rb") as f:
-            raw = f.read()
-        assert len(raw) == size, (out_name, len(raw), size)
+    raw = generate_agari_table()
+    dst = os.path.join(OUT, "agari.bin")
+    old = None
+    if os.path.exists(dst):
+        with open(dst, "rb") as f:
+            old = f.read()
+    if old != raw:  # also replaces a table gunzipped from the reference by an earlier build
         with open(dst, "wb") as f:
             f.write(raw)
-        print(f"build_tables: wrote {dst} ({len(raw)} bytes)")
+        print(f"build_tables: generated agari.bin ({len(raw)} bytes)")
     return 0
 
 
