@@ -719,13 +719,11 @@ int mjx_obs_rows(int version) {
     }
 }
 
-int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const uint64_t* keys, int obs_version,
-                   int shuffle_kind, int enable_quick_eval) {
-    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_env_create: call mjx_init first");
-    if (!out || n_tables <= 0 || !nonces || !keys) return fail(MJX_ERR_ARG, "mjx_env_create: bad arguments");
-    if (obs_version < 1 || obs_version > 4) return fail(MJX_ERR_ARG, "mjx_env_create: obs_version must be 1..4 (consts.rs:18)");
-    if (shuffle_kind != 0 && shuffle_kind != 1) return fail(MJX_ERR_ARG, "mjx_env_create: shuffle_kind must be 0 or 1");
-    mjx_env* env = new mjx_env();
+}  // extern "C"
+
+// allocate and initialise into a zeroed `env`; on failure the caller destroys the half-built env (nothing leaks)
+static int env_create_impl(mjx_env* env, int n_tables, const uint64_t* nonces, const uint64_t* keys, int obs_version,
+                           int shuffle_kind, int enable_quick_eval) {
     env->n_tables = n_tables;
     env->row_cap = n_tables * MJX_MAX_ROWS_PER_TABLE;
     env->obs_version = obs_version;
@@ -793,6 +791,32 @@ int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const ui
                                                    V.steps, V.err);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
+    return MJX_OK;
+}
+
+// a creator failed half way: free what the env owns, keep the error text of the failure
+static int destroy_failed(mjx_env** out, mjx_env* env, int rc) {
+    const std::string msg = g_err;
+    mjx_env_destroy(env);
+    cudaGetLastError();
+    if (out) *out = nullptr;
+    g_err = msg;
+    return rc;
+}
+
+extern "C" {
+
+int mjx_env_create(mjx_env** out, int n_tables, const uint64_t* nonces, const uint64_t* keys, int obs_version,
+                   int shuffle_kind, int enable_quick_eval) {
+    if (out) *out = nullptr;
+    if (!g_ready) return fail(MJX_ERR_STATE, "mjx_env_create: call mjx_init first");
+    if (!out || n_tables <= 0 || !nonces || !keys) return fail(MJX_ERR_ARG, "mjx_env_create: bad arguments");
+    if (obs_version < 1 || obs_version > 4) return fail(MJX_ERR_ARG, "mjx_env_create: obs_version must be 1..4 (consts.rs:18)");
+    if (shuffle_kind != 0 && shuffle_kind != 1) return fail(MJX_ERR_ARG, "mjx_env_create: shuffle_kind must be 0 or 1");
+    CU(cudaSetDevice(g_device));  // the calling thread may not be the one that ran mjx_init
+    mjx_env* env = new mjx_env();
+    const int rc = env_create_impl(env, n_tables, nonces, keys, obs_version, shuffle_kind, enable_quick_eval);
+    if (rc) return destroy_failed(out, env, rc);  // e.g. out of memory on the single-player state table
     *out = env;
     return MJX_OK;
 }
@@ -1044,33 +1068,33 @@ int mjx_env_create_replay(mjx_env** out, int n_jobs, const uint64_t* hdr, const 
     if (rc) return rc;
     mjx_env* env = *out;
     env->replay = true;
-    ReplayView& R = env->R;
-    const size_t cap = (size_t)env->row_cap;
-    u64 *d_hdr = nullptr, *d_ky = nullptr;
-    i32 *d_off = nullptr, *d_cnt = nullptr, *d_kyoff = nullptr;
-    u8* d_pl = nullptr;
-    CU(cudaMalloc(&d_hdr, sizeof(u64) * (size_t)n_hdr));
-    CU(cudaMalloc(&d_ky, sizeof(u64) * (size_t)(n_kyoku_words > 0 ? n_kyoku_words : 1)));
-    CU(cudaMalloc(&d_off, sizeof(i32) * (size_t)n_jobs));
-    CU(cudaMalloc(&d_cnt, sizeof(i32) * (size_t)n_jobs));
-    CU(cudaMalloc(&d_kyoff, sizeof(i32) * (size_t)n_jobs));
-    CU(cudaMalloc(&d_pl, (size_t)n_jobs));
-    CU(cudaMalloc(&R.pos, sizeof(i32) * (size_t)n_jobs));
-    CU(cudaMalloc(&R.ky_idx, sizeof(i32) * (size_t)n_jobs));
-    CU(cudaMalloc(&R.ky_seen, sizeof(i32) * (size_t)n_jobs));
-    CU(cudaMalloc(&R.row_label, sizeof(i64) * cap));
-    CU(cudaMalloc(&R.row_meta, cap * 4));
-    CU(cudaMemcpy(d_hdr, hdr, sizeof(u64) * (size_t)n_hdr, cudaMemcpyHostToDevice));
-    if (n_kyoku_words > 0) CU(cudaMemcpy(d_ky, kyoku, sizeof(u64) * (size_t)n_kyoku_words, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_off, ev_off, sizeof(i32) * (size_t)n_jobs, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_cnt, ev_cnt, sizeof(i32) * (size_t)n_jobs, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_kyoff, ky_off, sizeof(i32) * (size_t)n_jobs, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_pl, players, (size_t)n_jobs, cudaMemcpyHostToDevice));
-    CU(cudaMemset(R.pos, 0, sizeof(i32) * (size_t)n_jobs));
-    CU(cudaMemset(R.ky_idx, 0, sizeof(i32) * (size_t)n_jobs));
-    CU(cudaMemset(R.ky_seen, 0, sizeof(i32) * (size_t)n_jobs));
-    R.hdr = d_hdr; R.kyoku = d_ky; R.ev_off = d_off; R.ev_cnt = d_cnt; R.ky_off = d_kyoff; R.player = d_pl;
-    R.always_include_kan_select = always_include_kan_select ? 1 : 0;
+    rc = [&]() -> int {  // every buffer belongs to the env as soon as it exists, so a failure below frees it with the env
+        ReplayView& R = env->R;
+        const size_t cap = (size_t)env->row_cap;
+        CU(cudaMalloc((void**)&R.hdr, sizeof(u64) * (size_t)n_hdr));
+        CU(cudaMalloc((void**)&R.kyoku, sizeof(u64) * (size_t)(n_kyoku_words > 0 ? n_kyoku_words : 1)));
+        CU(cudaMalloc((void**)&R.ev_off, sizeof(i32) * (size_t)n_jobs));
+        CU(cudaMalloc((void**)&R.ev_cnt, sizeof(i32) * (size_t)n_jobs));
+        CU(cudaMalloc((void**)&R.ky_off, sizeof(i32) * (size_t)n_jobs));
+        CU(cudaMalloc((void**)&R.player, (size_t)n_jobs));
+        CU(cudaMalloc(&R.pos, sizeof(i32) * (size_t)n_jobs));
+        CU(cudaMalloc(&R.ky_idx, sizeof(i32) * (size_t)n_jobs));
+        CU(cudaMalloc(&R.ky_seen, sizeof(i32) * (size_t)n_jobs));
+        CU(cudaMalloc(&R.row_label, sizeof(i64) * cap));
+        CU(cudaMalloc(&R.row_meta, cap * 4));
+        CU(cudaMemcpy((void*)R.hdr, hdr, sizeof(u64) * (size_t)n_hdr, cudaMemcpyHostToDevice));
+        if (n_kyoku_words > 0) CU(cudaMemcpy((void*)R.kyoku, kyoku, sizeof(u64) * (size_t)n_kyoku_words, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy((void*)R.ev_off, ev_off, sizeof(i32) * (size_t)n_jobs, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy((void*)R.ev_cnt, ev_cnt, sizeof(i32) * (size_t)n_jobs, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy((void*)R.ky_off, ky_off, sizeof(i32) * (size_t)n_jobs, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy((void*)R.player, players, (size_t)n_jobs, cudaMemcpyHostToDevice));
+        CU(cudaMemset(R.pos, 0, sizeof(i32) * (size_t)n_jobs));
+        CU(cudaMemset(R.ky_idx, 0, sizeof(i32) * (size_t)n_jobs));
+        CU(cudaMemset(R.ky_seen, 0, sizeof(i32) * (size_t)n_jobs));
+        R.always_include_kan_select = always_include_kan_select ? 1 : 0;
+        return MJX_OK;
+    }();
+    if (rc) return destroy_failed(out, env, rc);
     return MJX_OK;
 }
 
@@ -1083,17 +1107,19 @@ int mjx_state_create(mjx_env** out, int n, const uint8_t* player_ids_host, int o
     if (rc) return rc;
     mjx_env* env = *out;
     env->is_state = true;
-    u8* d_ids = nullptr;
-    CU(cudaMalloc(&d_ids, (size_t)n));
-    CU(cudaMemcpy(d_ids, player_ids_host, (size_t)n, cudaMemcpyHostToDevice));
-    k_state_init<<<(n + 127) / 128, 128>>>(env->V.tables, n, d_ids);
-    CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());
-    cudaFree(d_ids);
-    CU(cudaMalloc(&env->d_state_words, sizeof(u64) * (size_t)n));
-    CU(cudaMalloc(&env->d_state_pay, sizeof(u64) * (size_t)n * REPLAY_KYOKU_WORDS));
-    CU(cudaMalloc(&env->d_state_cans, sizeof(u32) * (size_t)n));
-    CU(cudaMalloc(&env->d_state_misc, 256));
+    rc = [&]() -> int {
+        CU(cudaMalloc(&env->d_state_words, sizeof(u64) * (size_t)n));
+        u8* d_ids = reinterpret_cast<u8*>(env->d_state_words);  // n bytes of scratch until the first update
+        CU(cudaMemcpy(d_ids, player_ids_host, (size_t)n, cudaMemcpyHostToDevice));
+        k_state_init<<<(n + 127) / 128, 128>>>(env->V.tables, n, d_ids);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+        CU(cudaMalloc(&env->d_state_pay, sizeof(u64) * (size_t)n * REPLAY_KYOKU_WORDS));
+        CU(cudaMalloc(&env->d_state_cans, sizeof(u32) * (size_t)n));
+        CU(cudaMalloc(&env->d_state_misc, 256));
+        return MJX_OK;
+    }();
+    if (rc) return destroy_failed(out, env, rc);
     return MJX_OK;
 }
 

@@ -68,6 +68,14 @@ MJX_HD u64 sp_key_make(u32 row, u32 dr, u32 di) { return ((u64)row << 42) | ((u6
 MJX_HD u32 sp_key_row(u64 k) { return (u32)(k >> 42); }
 MJX_HD u32 sp_key_dr(u64 k) { return (u32)k & SP_DR_NONE; }
 MJX_HD u32 sp_key_di(u64 k) { return (u32)(k >> 18) & SP_DI_NONE; }
+// number of draws a state is away from the root of its row. Only turns >= that depth of a state's value vectors are ever read:
+// the root is evaluated at turns 0..T-1, a discard level reads its children at the same turn (calc.rs:563-637), a draw level at
+// turn i reads its children at turns j+1 > i (calc.rs:486-530) -- so a state n draws down is only asked about turns >= n and
+// the evaluation skips the others (their slots keep stale values nobody reads).
+MJX_HD int sp_key_depth(u64 k) {
+    const u32 dr = (u32)k & SP_DR_NONE;
+    return (int)((dr & 63u) != 63u) + (int)(((dr >> 6) & 63u) != 63u) + (int)(((dr >> 12) & 63u) != 63u);
+}
 // insert tile id `t` (0..36) into a tuple of `n` ascending 6-bit fields (63 = empty, always at the top)
 MJX_HD u32 sp_tuple_insert(u32 packed, int n, u32 t) {
     int p = 0;
@@ -549,7 +557,7 @@ MJX_DN void sp_score_edge(const SpGlobal& G, const Tables& T, int e) {
 // ---------------------------------------------------------------------------------------------- evaluation
 struct SpEvalDBatch {
     u32 slot[SP_B], ebeg[SP_B];
-    u8 ne[SP_B], T[SP_B];
+    u8 ne[SP_B], T[SP_B], d[SP_B];  // d: first turn anybody reads (sp_key_depth)
     u16 off[SP_B + 1];
     i32 n_items;
 };
@@ -582,7 +590,7 @@ MJX_D void sp_fill_ptab_block(float* blk, int n_left, int i0) {
 constexpr int SP_WB = 7;  // W states per WARP mini-batch: 7 x ceil(17 / 2) = 63 (state, turn-pair) items = two rounds of 32 lanes (16 per warp measured slower)
 struct SpEvalWBatch {      // one per warp: the W evaluation needs no CTA-wide barrier
     u32 slot[SP_WB], ebeg[SP_WB], pbase[SP_WB];
-    u8 ne[SP_WB], T[SP_WB], flags[SP_WB], jend[SP_WB];  // flags: 1 assume_riichi, 2 double riichi, 4 haitei; jend: first j with not_tsumo[j] == 0
+    u8 ne[SP_WB], T[SP_WB], d[SP_WB], flags[SP_WB], jend[SP_WB];  // d: first turn anybody reads (sp_key_depth); flags: 1 assume_riichi, 2 double riichi, 4 haitei; jend: first j with not_tsumo[j] == 0
     u16 aoff[SP_WB + 1];
     i32 n_a;
 };
@@ -608,13 +616,17 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
     const u32* list = G.wl + (size_t)level * G.wl_cap;
     SP_PFOR(st, nb) {
         const u32 slot = list[first + st];
-        const SpRow& R = G.rows[sp_key_row(G.hkey[slot])];
+        const u64 key = G.hkey[slot];
+        const SpRow& R = G.rows[sp_key_row(key)];
         const u64 ei = G.einfo[slot];
         const int Tn = R.T, n_left = R.n_left, i0 = sp_einfo_sum(ei);
         const bool row_ok = i0 <= n_left && i0 <= SP_MAX_TILES_LEFT;
         const int lim = row_ok ? min(Tn - 1, n_left - i0) : -1;
         S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei);
-        S.T[st] = (u8)Tn;
+        S.T[st] = (u8)Tn; S.d[st] = (u8)min(sp_key_depth(key), Tn);
+#ifdef MJX_HOST_EMUL  // the emulated parity tests poison the turns nobody may read
+        for (int i = 0; i < S.d[st]; i++) { float* o = G.vals + (size_t)slot * SP_VALS; o[i] = o[SP_T_MAX + i] = o[2 * SP_T_MAX + i] = __builtin_nanf(""); }
+#endif
         const bool ar = R.is_menzen && R.prefer_riichi;
         S.flags[st] = (u8)((ar ? 1 : 0) | (R.calc_double_riichi ? 2 : 0) | (R.calc_haitei ? 4 : 0));
         S.jend[st] = (u8)max(0, min(Tn, lim + 1));
@@ -623,11 +635,11 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
     SP_WSYNC();
     if (B.tid == 0) {
         int aa = 0;
-        for (int st = 0; st < nb; st++) { S.aoff[st] = (u16)aa; aa += (S.T[st] + 1) / 2; }
+        for (int st = 0; st < nb; st++) { S.aoff[st] = (u16)aa; aa += (S.T[st] - S.d[st] + 1) / 2; }
         S.aoff[nb] = (u16)aa; S.n_a = aa;
     }
     SP_WSYNC();
-    // accumulation: a thread takes turns p and T-1-p of a state (T+1 draw turns together: balanced), edges in the reference's
+    // accumulation: a thread takes turns d+p and T-1-p of a state (T-d+1 draw turns together: balanced), edges in the reference's
     // order, j ascending, every multiply and add rounded as the reference rounds it
     SP_PFOR(item, S.n_a) {
         const int st = sp_find_state<int>(S.aoff, nb, item), p = item - S.aoff[st];
@@ -636,7 +648,7 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
         const float* Pb = G.p_tab + S.pbase[st];
         // row i of the probability triangle is contiguous in j: Pc[row(i) - i + j]
         const bool assume_riichi = (S.flags[st] & 1) != 0, dbl = (S.flags[st] & 2) != 0, haitei = (S.flags[st] & 4) != 0;
-        const int i0 = p, i1 = Tn - 1 - p;
+        const int i0 = S.d[st] + p, i1 = Tn - 1 - p;
         const bool two = i1 > i0;
         float t0 = 0.f, w0 = 0.f, v0 = 0.f, t1 = 0.f, w1 = 0.f, v1 = 0.f;
         // the next edge's descriptor is fetched while the current one is accumulated (dependent chain meta/child -> values)
@@ -713,17 +725,21 @@ MJX_DN void sp_eval_d_batch(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, 
         const u32 slot = list[first + st];
         const u64 ei = G.einfo[slot];
         S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei);
-        S.T[st] = G.rows[sp_key_row(G.hkey[slot])].T;
+        const u64 key = G.hkey[slot];
+        S.T[st] = G.rows[sp_key_row(key)].T; S.d[st] = (u8)min(sp_key_depth(key), (int)S.T[st]);
+#ifdef MJX_HOST_EMUL
+        for (int i = 0; i < S.d[st]; i++) { float* o = G.vals + (size_t)slot * SP_VALS; o[i] = o[SP_T_MAX + i] = o[2 * SP_T_MAX + i] = __builtin_nanf(""); }
+#endif
     }
     SP_SYNC();
     if (B.tid == 0) {
         int acc = 0;
-        for (int st = 0; st < nb; st++) { S.off[st] = (u16)acc; acc += S.T[st]; }
+        for (int st = 0; st < nb; st++) { S.off[st] = (u16)acc; acc += S.T[st] - S.d[st]; }
         S.off[nb] = (u16)acc; S.n_items = acc;
     }
     SP_SYNC();
     SP_PFOR(item, S.n_items) {
-        const int st = sp_find_state<int>(S.off, nb, item), i = item - S.off[st];
+        const int st = sp_find_state<int>(S.off, nb, item), i = S.d[st] + item - S.off[st];
         const int ne = S.ne[st];
         const u32 eb = S.ebeg[st];
         const float FMIN = -3.40282347e+38f;
@@ -733,7 +749,7 @@ MJX_DN void sp_eval_d_batch(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, 
         u32 child_n = ne ? G.echild[eb] : SP_NO_CHILD;
         for (int e = 0; e < ne; e++) {
             const u32 child = child_n;
-            if (e + 1 < ne) { child_n = G.echild[eb + e + 1]; if (child_n != SP_NO_CHILD && i == 0) sp_prefetch(G.vals + (size_t)child_n * SP_VALS); }
+            if (e + 1 < ne) { child_n = G.echild[eb + e + 1]; if (child_n != SP_NO_CHILD && i == S.d[st]) sp_prefetch(G.vals + (size_t)child_n * SP_VALS); }
             if (child == SP_NO_CHILD) continue;
             const int tile = G.emeta[eb + e] & 63;
             const float* cv = G.vals + (size_t)child * SP_VALS;
