@@ -429,6 +429,11 @@ __global__ void k_sp_tables(float* p_tab) {
 
 __global__ void k_sp_mark(SpGlobal G, int which) { G.counters[4 + which] = min(G.counters[1], G.edge_cap); }
 
+__global__ void __launch_bounds__(256) k_sp_densify(SpGlobal G) {
+    SpBlk B; B.tid = threadIdx.x; B.nthr = blockDim.x; B.bid = blockIdx.x; B.nblk = gridDim.x;
+    sp_densify(G, B);
+}
+
 __global__ void __launch_bounds__(128) k_sp_score(SpGlobal G, Tables T) {
     const int b = G.counters[4], e_end = G.counters[5];
     for (int e = b + blockIdx.x * blockDim.x + threadIdx.x; e < e_end; e += gridDim.x * blockDim.x) sp_score_edge(G, T, e);
@@ -618,7 +623,11 @@ static int sp_alloc(SpGlobal& G, long long want) {
     CU(cudaMalloc(&G.nsig, (size_t)G.hash_cap * sizeof(SpSigP)));
     CU(cudaMalloc(&G.einfo, (size_t)G.hash_cap * sizeof(u64)));
     CU(cudaMalloc(&G.vals, (size_t)G.hash_cap * SP_VALS * sizeof(float)));
+    CU(cudaMalloc(&G.sid, (size_t)G.hash_cap * sizeof(u32)));
+    CU(cudaMalloc(&G.dkey, (size_t)G.hash_cap * sizeof(u64)));
     CU(cudaMalloc(&G.echild, (size_t)G.edge_cap * sizeof(u32)));
+    CU(cudaMalloc(&G.evid, (size_t)G.edge_cap * sizeof(u32)));
+    CU(cudaMemset(G.evid, 0, (size_t)G.edge_cap * sizeof(u32)));
     CU(cudaMalloc(&G.emeta, (size_t)G.edge_cap * sizeof(u16)));
     CU(cudaMalloc(&G.eowner, (size_t)G.edge_cap * sizeof(u32)));
     CU(cudaMalloc(&G.leaf_scores, (size_t)G.score_cap * 4 * sizeof(float)));
@@ -632,7 +641,7 @@ static int sp_alloc(SpGlobal& G, long long want) {
 }
 static SpGlobal& sp_of(mjx_env* env, int lane) { return lane == 0 ? env->sp : env->sp_lane[lane - 1]; }
 static void sp_free(SpGlobal& G) {
-    cudaFree(G.hkey); cudaFree(G.nsig); cudaFree(G.einfo); cudaFree(G.vals); cudaFree(G.echild); cudaFree(G.emeta);
+    cudaFree(G.hkey); cudaFree(G.nsig); cudaFree(G.einfo); cudaFree(G.vals); cudaFree(G.sid); cudaFree(G.dkey); cudaFree(G.echild); cudaFree(G.evid); cudaFree(G.emeta);
     cudaFree(G.eowner); cudaFree(G.leaf_scores); cudaFree(G.wl); cudaFree(G.wl_count); cudaFree(G.counters);
 }
 // lanes 1..n-1 (lane 0 is env->sp): each expects 1/n of the step's states and gets twice that
@@ -910,6 +919,7 @@ static int launch_sp_block(mjx_env* env, const SpGlobal& G, float* obs_dev, cuda
         else k_sp_expand<0><<<grid, env->sp_thr_x, 0, st>>>(G, g_T, level);
     }
     k_sp_mark<<<1, 1, 0, st>>>(G, 1);
+    k_sp_densify<<<g_sm_count * 8, 256, 0, st>>>(G);
     k_sp_score<<<g_sm_count * 16, 128, 0, st>>>(G, g_T);
     for (int level = SP_SLOTS - 1; level >= 0; level--) {
         if (!sp_slot_is_w(level)) k_sp_eval<0><<<grid_eval, env->sp_thr_e, 0, st>>>(G, level);
@@ -920,7 +930,7 @@ static int launch_sp_block(mjx_env* env, const SpGlobal& G, float* obs_dev, cuda
     k_sp_finalize<<<grid_rows, SP_WARPS * 32, 0, st>>>(G, g_T, env->V, obs_dev, row_lo, row_hi, part, parts);
     k_sp_release<<<g_sm_count * 4, 256, 0, st>>>(G);
     CU(cudaGetLastError());
-    env->launches += 6 + 2 * SP_SLOTS + 1;
+    env->launches += 7 + 2 * SP_SLOTS + 1;
     return MJX_OK;
 }
 

@@ -181,11 +181,14 @@ struct SpGlobal {
     SpRow* rows;        // [row_cap]
     u64* hkey;          // [hash_cap] state key (SP_EMPTY = free); the slot index is the state's id
     SpSigP* nsig;       // [hash_cap] shanten signatures of the state's hand
-    u64* einfo;         // [hash_cap] edge_begin | n_edges << 32 | sum of required-tile counts << 40 | counts present (4 bits) << 48
-    float* vals;        // [hash_cap][3][SP_T_MAX]
+    u64* einfo;         // [hash_cap] BY DENSE ID: edge_begin | n_edges << 32 | sum of required-tile counts << 40 | counts present (4 bits) << 48
+    u64* dkey;          // [hash_cap] BY DENSE ID: the state's key (what the evaluation needs of hkey without the scattered read)
+    float* vals;        // [hash_cap][3][SP_T_MAX] value vectors, indexed by the DENSE state id (sp_vid): level base + work-list position
+    u32* sid;           // [hash_cap] level << 28 | work-list position of the state in that slot (written by whoever appends it)
     u32* echild;        // [edge_cap] child state (table slot)
+    u32* evid;          // [edge_cap] dense id of the child (k_sp_densify, after the expansion): what the evaluation follows
     u16* emeta;         // [edge_cap] tile (6 bits) | count << 6 | (no-yaku flag << 15, tenpai states only)
-    u32* eowner;        // [edge_cap] owning state; written for the tenpai (W0) level only (k_sp_score walks that edge range)
+    u32* eowner;        // [edge_cap] owning state (dense id); written for the tenpai (W0) level only (k_sp_score walks that edge range)
     float* leaf_scores; // [score_cap][4] get_score of every winning draw of the tenpai (W0) states
     u32* wl;            // [SP_SLOTS][wl_cap] work list of each level: table slots
     i32* wl_count;      // [SP_SLOTS]
@@ -217,13 +220,42 @@ struct SpBlk { int tid, nthr, bid, nblk; };  // thread / block coordinates of a 
 
 MJX_HD bool sp_slot_is_w(int slot) { return (slot & 1) != 0; }
 MJX_HD int sp_slot_shanten(int slot) { return 3 - (slot >> 1); }
-MJX_D float* sp_vals(const SpGlobal& G, u32 node, int which) { return G.vals + ((size_t)node * 3 + which) * SP_T_MAX; }
+MJX_D float* sp_vals(const SpGlobal& G, u32 vid, int which) { return G.vals + ((size_t)vid * 3 + which) * SP_T_MAX; }  // vid: dense id
 MJX_D u32 sp_einfo_begin(u64 e) { return (u32)e; }
 MJX_D int sp_einfo_n(u64 e) { return (int)((e >> 32) & 0xFF); }
 MJX_D int sp_einfo_sum(u64 e) { return (int)((e >> 40) & 0xFF); }
 MJX_D int sp_einfo_cmask(u64 e) { return (int)((e >> 48) & 0xF); }
 
 MJX_D void sp_set_overflow(const SpGlobal& G) { G.counters[2] = 1; }
+
+// Dense state ids. The table slot of a state is a hash of its key, so value vectors indexed by slot would be scattered over the
+// whole table (gigabytes) and every child read of the evaluation would miss L2. The work lists already enumerate the states
+// level by level, so the value vectors live at `level base + position in the level's work list`: the children of a level are
+// one contiguous, just-written region (tens of MB: L2-resident) instead.
+constexpr u32 SP_SID_POS = (1u << 28) - 1u;
+MJX_D u32 sp_level_base(const SpGlobal& G, int level) {
+    u32 b = 0;
+    for (int l = 0; l < level; l++) b += (u32)min(G.wl_count[l], G.wl_cap);
+    return b;
+}
+MJX_D u32 sp_vid(const SpGlobal& G, u32 slot) {
+    const u32 s = G.sid[slot];
+    return sp_level_base(G, (int)(s >> 28)) + (s & SP_SID_POS);
+}
+// after the expansion (all work lists final): the dense id of every edge's child
+MJX_DN void sp_densify(const SpGlobal& G, const SpBlk& B) {
+    if (G.counters[2]) return;  // overflow: the step's block is dropped anyway and the evaluation does not run
+    u32 base[SP_SLOTS];
+    for (int l = 0; l < SP_SLOTS; l++) base[l] = sp_level_base(G, l);
+    const int n = min(G.counters[1], G.edge_cap), leaf_b = G.counters[4], leaf_e = G.counters[5];
+    for (int e = B.bid * B.nthr + B.tid; e < n; e += B.nblk * B.nthr) {
+        if (e >= leaf_b && e < leaf_e) continue;  // winning draws have no child
+        const u32 c = G.echild[e];
+        u32 v = SP_NO_CHILD;
+        if (c != SP_NO_CHILD) { const u32 sd = G.sid[c]; v = base[sd >> 28] + (sd & SP_SID_POS); }
+        G.evid[e] = v;
+    }
+}
 
 // pull a state's value vectors (204 B: two 128-byte lines) towards the SM ahead of their use
 MJX_D void sp_prefetch(const float* p) {
@@ -400,7 +432,9 @@ MJX_DN void sp_expand_batch(const SpGlobal& G, const Tables& T, SpExpandBatch& S
     SP_SYNC();
     SP_PFOR(st, nb) {
         const int ne = S.n_edge ? S.ne[st] : 0;
-        G.einfo[S.slot[st]] = (u64)(u32)(S.e_base + S.e_off[st]) | ((u64)ne << 32) | ((u64)S.sumreq[st] << 40) | ((u64)S.cmask[st] << 48);
+        const u32 vid = sp_level_base(G, level) + (u32)(first + st);  // this level's work list is final: so is the state's dense id
+        G.einfo[vid] = (u64)(u32)(S.e_base + S.e_off[st]) | ((u64)ne << 32) | ((u64)S.sumreq[st] << 40) | ((u64)S.cmask[st] << 48);
+        G.dkey[vid] = S.key[st];
     }
     // edge descriptors in tile order: every effective tile writes its own at the offset its rank gives
     if (S.n_edge) SP_PFOR(it, nb * 34) {
@@ -432,7 +466,7 @@ MJX_DN void sp_expand_batch(const SpGlobal& G, const Tables& T, SpExpandBatch& S
         const int st = (int)(d & 0xFF), tile = (int)((d >> 8) & 0xFF), cnt = (int)(d >> 16);
         const int ge = S.e_base + e;
         G.emeta[ge] = (u16)(tile | (cnt << 6));
-        if (LEAF) { G.eowner[ge] = S.slot[st]; continue; }
+        if (LEAF) { G.eowner[ge] = sp_level_base(G, level) + (u32)(first + st); continue; }
         const u64 key = S.key[st];
         const int t = deaka(tile);
         const u64 ckey = IS_W ? sp_key_make(sp_key_row(key), sp_tuple_insert(sp_key_dr(key), 3, (u32)tile), sp_key_di(key))
@@ -454,7 +488,10 @@ MJX_DN void sp_expand_batch(const SpGlobal& G, const Tables& T, SpExpandBatch& S
         }
         SP_SYNC();
         u32* next = G.wl + (size_t)(level + 1) * G.wl_cap;
-        SP_PFOR(i, S.n_win) next[S.w_base + i] = S.win[i];
+        SP_PFOR(i, S.n_win) {
+            next[S.w_base + i] = S.win[i];
+            G.sid[S.win[i]] = ((u32)(level + 1) << 28) | (u32)(S.w_base + i);
+        }
         SP_SYNC();
     }
 }
@@ -535,7 +572,7 @@ MJX_DN bool sp_get_score(const Tables& T, const SpRow& P, const u8* tehai13, con
 // happens in the evaluation of the tenpai level.
 MJX_DN void sp_score_edge(const SpGlobal& G, const Tables& T, int e) {
     const u32 node = G.eowner[e];
-    const u64 key = G.hkey[node];
+    const u64 key = G.dkey[node];
     const SpRow& P = G.rows[sp_key_row(key)];
     const u32 dr = sp_key_dr(key), di = sp_key_di(key);
     u8 th[34], wall[34];
@@ -556,7 +593,7 @@ MJX_DN void sp_score_edge(const SpGlobal& G, const Tables& T, int e) {
 
 // ---------------------------------------------------------------------------------------------- evaluation
 struct SpEvalDBatch {
-    u32 slot[SP_B], ebeg[SP_B];
+    u32 vid[SP_B], ebeg[SP_B];  // vid: dense id (where the state's values go)
     u8 ne[SP_B], T[SP_B], d[SP_B];  // d: first turn anybody reads (sp_key_depth)
     u16 off[SP_B + 1];
     i32 n_items;
@@ -589,7 +626,7 @@ MJX_D void sp_fill_ptab_block(float* blk, int n_left, int i0) {
 
 constexpr int SP_WB = 7;  // W states per WARP mini-batch: 7 x ceil(17 / 2) = 63 (state, turn-pair) items = two rounds of 32 lanes (16 per warp measured slower)
 struct SpEvalWBatch {      // one per warp: the W evaluation needs no CTA-wide barrier
-    u32 slot[SP_WB], ebeg[SP_WB], pbase[SP_WB];
+    u32 vid[SP_WB], ebeg[SP_WB], pbase[SP_WB];  // vid: dense id (where the state's values go)
     u8 ne[SP_WB], T[SP_WB], d[SP_WB], flags[SP_WB], jend[SP_WB];  // d: first turn anybody reads (sp_key_depth); flags: 1 assume_riichi, 2 double riichi, 4 haitei; jend: first j with not_tsumo[j] == 0
     u16 aoff[SP_WB + 1];
     i32 n_a;
@@ -613,19 +650,18 @@ MJX_D int sp_find_state(const u16* off, int nb, int item) {
 template <bool LEAF>
 MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, int level, int first, int nb) {
     const int k = LEAF ? 0 : sp_slot_shanten(level);
-    const u32* list = G.wl + (size_t)level * G.wl_cap;
+    const u32 vbase = sp_level_base(G, level) + (u32)first;  // the states of the batch are consecutive dense ids
     SP_PFOR(st, nb) {
-        const u32 slot = list[first + st];
-        const u64 key = G.hkey[slot];
+        const u64 key = G.dkey[vbase + st];
         const SpRow& R = G.rows[sp_key_row(key)];
-        const u64 ei = G.einfo[slot];
+        const u64 ei = G.einfo[vbase + st];
         const int Tn = R.T, n_left = R.n_left, i0 = sp_einfo_sum(ei);
         const bool row_ok = i0 <= n_left && i0 <= SP_MAX_TILES_LEFT;
         const int lim = row_ok ? min(Tn - 1, n_left - i0) : -1;
-        S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei);
+        S.vid[st] = vbase + (u32)st; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei);
         S.T[st] = (u8)Tn; S.d[st] = (u8)min(sp_key_depth(key), Tn);
 #ifdef MJX_HOST_EMUL  // the emulated parity tests poison the turns nobody may read
-        for (int i = 0; i < S.d[st]; i++) { float* o = G.vals + (size_t)slot * SP_VALS; o[i] = o[SP_T_MAX + i] = o[2 * SP_T_MAX + i] = __builtin_nanf(""); }
+        for (int i = 0; i < S.d[st]; i++) { float* o = G.vals + (size_t)S.vid[st] * SP_VALS; o[i] = o[SP_T_MAX + i] = o[2 * SP_T_MAX + i] = __builtin_nanf(""); }
 #endif
         const bool ar = R.is_menzen && R.prefer_riichi;
         S.flags[st] = (u8)((ar ? 1 : 0) | (R.calc_double_riichi ? 2 : 0) | (R.calc_haitei ? 4 : 0));
@@ -653,11 +689,11 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
         float t0 = 0.f, w0 = 0.f, v0 = 0.f, t1 = 0.f, w1 = 0.f, v1 = 0.f;
         // the next edge's descriptor is fetched while the current one is accumulated (dependent chain meta/child -> values)
         u16 meta_n = ne ? G.emeta[eb] : (u16)0;
-        u32 child_n = (!LEAF && ne) ? G.echild[eb] : 0u;
+        u32 child_n = (!LEAF && ne) ? G.evid[eb] : 0u;
         for (int e = 0; e < ne; e++) {
             const u16 meta = meta_n;
             const u32 child = child_n;
-            if (e + 1 < ne) { meta_n = G.emeta[eb + e + 1]; if (!LEAF) child_n = G.echild[eb + e + 1]; }
+            if (e + 1 < ne) { meta_n = G.emeta[eb + e + 1]; if (!LEAF) child_n = G.evid[eb + e + 1]; }
             if (!LEAF && e + 1 < ne && child_n != SP_NO_CHILD) sp_prefetch(G.vals + (size_t)child_n * SP_VALS);
             const float* Pc = Pb + (((meta >> 6) & 7) - 1) * SP_TRI;
             const float* P0 = Pc + sp_tri_row(i0) - i0;
@@ -711,7 +747,7 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
                     }
                 }
         }
-        float* o = G.vals + (size_t)S.slot[st] * SP_VALS;
+        float* o = G.vals + (size_t)S.vid[st] * SP_VALS;
         o[i0] = t0; o[SP_T_MAX + i0] = w0; o[2 * SP_T_MAX + i0] = v0;
         if (two) { o[i1] = t1; o[SP_T_MAX + i1] = w1; o[2 * SP_T_MAX + i1] = v1; }
     }
@@ -720,15 +756,14 @@ MJX_DN void sp_eval_w_batch(const SpGlobal& G, SpEvalWBatch& S, const SpBlk& B, 
 
 // calc.rs:563-637 discard_slow: per turn the child with the largest (truncated) EV, ties by discard priority
 MJX_DN void sp_eval_d_batch(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, int level, int first, int nb) {
-    const u32* list = G.wl + (size_t)level * G.wl_cap;
+    const u32 vbase = sp_level_base(G, level) + (u32)first;
     SP_PFOR(st, nb) {
-        const u32 slot = list[first + st];
-        const u64 ei = G.einfo[slot];
-        S.slot[st] = slot; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei);
-        const u64 key = G.hkey[slot];
+        const u64 ei = G.einfo[vbase + st];
+        S.vid[st] = vbase + (u32)st; S.ebeg[st] = sp_einfo_begin(ei); S.ne[st] = (u8)sp_einfo_n(ei);
+        const u64 key = G.dkey[vbase + st];
         S.T[st] = G.rows[sp_key_row(key)].T; S.d[st] = (u8)min(sp_key_depth(key), (int)S.T[st]);
 #ifdef MJX_HOST_EMUL
-        for (int i = 0; i < S.d[st]; i++) { float* o = G.vals + (size_t)slot * SP_VALS; o[i] = o[SP_T_MAX + i] = o[2 * SP_T_MAX + i] = __builtin_nanf(""); }
+        for (int i = 0; i < S.d[st]; i++) { float* o = G.vals + (size_t)S.vid[st] * SP_VALS; o[i] = o[SP_T_MAX + i] = o[2 * SP_T_MAX + i] = __builtin_nanf(""); }
 #endif
     }
     SP_SYNC();
@@ -746,10 +781,10 @@ MJX_DN void sp_eval_d_batch(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, 
         float bt = FMIN, bw = FMIN, bv = FMIN;
         int best_tile = T_UNK;
         i32 best_value = (i32)0x80000000;
-        u32 child_n = ne ? G.echild[eb] : SP_NO_CHILD;
+        u32 child_n = ne ? G.evid[eb] : SP_NO_CHILD;
         for (int e = 0; e < ne; e++) {
             const u32 child = child_n;
-            if (e + 1 < ne) { child_n = G.echild[eb + e + 1]; if (child_n != SP_NO_CHILD && i == S.d[st]) sp_prefetch(G.vals + (size_t)child_n * SP_VALS); }
+            if (e + 1 < ne) { child_n = G.evid[eb + e + 1]; if (child_n != SP_NO_CHILD && i == S.d[st]) sp_prefetch(G.vals + (size_t)child_n * SP_VALS); }
             if (child == SP_NO_CHILD) continue;
             const int tile = G.emeta[eb + e] & 63;
             const float* cv = G.vals + (size_t)child * SP_VALS;
@@ -760,19 +795,21 @@ MJX_DN void sp_eval_d_batch(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, 
                 best_value = value; best_tile = tile;
             }
         }
-        float* o = G.vals + (size_t)S.slot[st] * SP_VALS;
+        float* o = G.vals + (size_t)S.vid[st] * SP_VALS;
         o[i] = bt; o[SP_T_MAX + i] = bw; o[2 * SP_T_MAX + i] = bv;
     }
     SP_SYNC();
 }
 
 MJX_DN void sp_eval_d_level(const SpGlobal& G, SpEvalDBatch& S, const SpBlk& B, int level) {
+    if (G.counters[2]) return;  // overflow: the dense ids were not assigned, the step's block is dropped
     const int n = min(G.wl_count[level], G.wl_cap);
     for (int first = B.bid * SP_B; first < n; first += B.nblk * SP_B) sp_eval_d_batch(G, S, B, level, first, min(SP_B, n - first));
 }
 // every WARP works through its own mini-batches (S = the warp's staging area): no CTA-wide barrier, a slow state only holds its warp
 template <bool LEAF>
 MJX_DN void sp_eval_w_level(const SpGlobal& G, SpEvalWBatch* S, const SpBlk& B, int level) {
+    if (G.counters[2]) return;
     const int n = min(G.wl_count[level], G.wl_cap);
     const int lanes = B.nthr >= 32 ? 32 : B.nthr, wpc = B.nthr / lanes, warp = B.tid / lanes;
     SpBlk W; W.tid = B.tid - warp * lanes; W.nthr = lanes; W.bid = B.bid * wpc + warp; W.nblk = B.nblk * wpc;
@@ -807,6 +844,7 @@ struct SpCtx {  // warp-per-row stages
 struct SpCand {
     int tile;           // as sp/candidate.rs (may be an aka id)
     int node;           // W-state (table slot) whose values are the candidate's, or -1 (simple mode)
+    u32 vid;            // its dense id (where its values are)
     u64 required;       // 34-bit set of required tile ids
     int num_required;   // sum of counts (u8 arithmetic in the reference)
     bool shanten_down;
@@ -954,7 +992,7 @@ MJX_DN void sp_stage_init(SpCtx& s, const TableState* S, int row, int table, int
                 if (slot != SP_NO_CHILD) {
                     s.G.nsig[slot] = sp_sig_pack(hand_sig(root.tehai));
                     const int pos = sp_atomic_add(&s.G.wl_count[level], 1);
-                    if (pos < s.G.wl_cap) { s.G.wl[(size_t)level * s.G.wl_cap + pos] = slot; R.root = slot; }
+                    if (pos < s.G.wl_cap) { s.G.wl[(size_t)level * s.G.wl_cap + pos] = slot; s.G.sid[slot] = ((u32)level << 28) | (u32)pos; R.root = slot; }
                     else sp_set_overflow(s.G);
                 }
             }
@@ -1014,7 +1052,7 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
     } else {
         if (R.root == SP_NO_CHILD) return;
         if (can_discard) {  // calc.rs:203-253: one candidate per shanten-keeping discard of the root
-            const u64 ri = s.G.einfo[R.root];
+            const u64 ri = s.G.einfo[sp_vid(s.G, R.root)];
             const int ne = sp_einfo_n(ri);
             const u32 eb = sp_einfo_begin(ri);
             for (int i = 0; i < ne && n_cands < 14; i++) {
@@ -1032,7 +1070,8 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
         for (int i = 0; i < n_cands; i++) {
             SpCand& cd = cands[i];
             const int node = cd.node;
-            const u64 ni = s.G.einfo[node];
+            cd.vid = sp_vid(s.G, (u32)node);
+            const u64 ni = s.G.einfo[cd.vid];
             const int ne = sp_einfo_n(ni);
             const u32 eb = sp_einfo_begin(ni);
             u64 req = 0; int num = 0;
@@ -1043,9 +1082,9 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
             }
             cd.required = req;
             cd.num_required = num & 0xFF;
-            cd.t0 = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s.G, (u32)node, 0)[0]);
-            cd.w0 = clamp01(sp_vals(s.G, (u32)node, 1)[0]);
-            cd.e0 = fmaxf(sp_vals(s.G, (u32)node, 2)[0], 0.f);
+            cd.t0 = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s.G, cd.vid, 0)[0]);
+            cd.w0 = clamp01(sp_vals(s.G, cd.vid, 1)[0]);
+            cd.e0 = fmaxf(sp_vals(s.G, cd.vid, 2)[0], 0.f);
         }
     }
     if (n_cands == 0) return;
@@ -1075,12 +1114,12 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
     const int n_emit = cd_flag ? n_cands : 1;
     for (int q = 0; q < n_emit; q++) {
         const SpCand& cd = cd_flag ? cands[q] : cands[first];
-        const int node = cd.node;
+        const u32 vid = cd.vid;
         for (int turn = 0; turn < T; turn++) {
-            const float tp = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s.G, (u32)node, 0)[turn]);
+            const float tp = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s.G, vid, 0)[turn]);
             if (!(tp > 0.f)) break;
-            const float wp = clamp01(sp_vals(s.G, (u32)node, 1)[turn]);
-            const float ev = fminf(SP_FMUL(fmaxf(sp_vals(s.G, (u32)node, 2)[turn], 0.f), ev_scale), 1.f);
+            const float wp = clamp01(sp_vals(s.G, vid, 1)[turn]);
+            const float ev = fminf(SP_FMUL(fmaxf(sp_vals(s.G, vid, 2)[turn], 0.f), ev_scale), 1.f);
             if (cd_flag) {
                 const int tid = deaka(cd.tile);
                 SPO_ASSIGN(961 + turn, tid, tp);

@@ -311,8 +311,8 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
     if (!sp || version != 4) return;
     // the same stage sequence mjx_env_encode_obs launches (csrc/mjx_kernels.cu launch_sp_block), executed by one thread
     static SpGlobal G;
-    static std::vector<SpRow> rows; static std::vector<u64> hkey, einfo; static std::vector<SpSigP> nsig;
-    static std::vector<float> vals, leaf_scores; static std::vector<u32> echild, eowner, wl; static std::vector<u16> emeta;
+    static std::vector<SpRow> rows; static std::vector<u64> hkey, einfo, dkey; static std::vector<SpSigP> nsig;
+    static std::vector<float> vals, leaf_scores; static std::vector<u32> echild, eowner, wl, sid, evid; static std::vector<u16> emeta;
     static i32 wl_count[SP_SLOTS], counters[8];
     if (hkey.empty()) {
         G.hash_cap = 1 << 21; G.wl_cap = G.hash_cap / 4; G.edge_cap = G.hash_cap * 2; G.score_cap = G.hash_cap;
@@ -321,6 +321,8 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
         echild.resize(G.edge_cap); eowner.resize(G.edge_cap); emeta.resize(G.edge_cap); wl.resize((size_t)SP_SLOTS * G.wl_cap);
         G.rows = rows.data(); G.hkey = hkey.data(); G.einfo = einfo.data(); G.nsig = nsig.data(); G.vals = vals.data();
         G.leaf_scores = leaf_scores.data(); G.echild = echild.data(); G.eowner = eowner.data(); G.emeta = emeta.data();
+        dkey.resize(G.hash_cap); G.dkey = dkey.data();
+        sid.resize(G.hash_cap); evid.assign(G.edge_cap, 0); G.sid = sid.data(); G.evid = evid.data();
         G.wl = wl.data(); G.wl_count = wl_count; G.counters = counters;
         static std::vector<float> p_tab((size_t)SP_NTS_DIM * SP_NTS_DIM * 4 * SP_TRI);
         for (int i = 0; i < SP_NTS_DIM * SP_NTS_DIM; i++) sp_fill_ptab_block(p_tab.data() + (size_t)i * 4 * SP_TRI, i / SP_NTS_DIM, i % SP_NTS_DIM);
@@ -340,6 +342,7 @@ void emul_env_encode_obs_v(void* p, float* obs, int sp, int version) {
         else sp_expand_level<0>(G, g_T, xb, B, level);
     }
     counters[5] = counters[1];
+    sp_densify(G, B);
     for (int e = counters[4]; e < counters[5]; e++) sp_score_edge(G, g_T, e);
     for (int level = SP_SLOTS - 1; level >= 0; level--) {
         if (!sp_slot_is_w(level)) sp_eval_d_level(G, ed, B, level);
