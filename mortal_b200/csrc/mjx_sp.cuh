@@ -1067,6 +1067,7 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
             SpCand& cd = cands[n_cands++];
             cd.tile = T_UNK; cd.node = (int)R.root; cd.shanten_down = false;
         }
+#ifdef MJX_HOST_EMUL
         for (int i = 0; i < n_cands; i++) {
             SpCand& cd = cands[i];
             const int node = cd.node;
@@ -1086,6 +1087,43 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
             cd.w0 = clamp01(sp_vals(s.G, cd.vid, 1)[0]);
             cd.e0 = fmaxf(sp_vals(s.G, cd.vid, 2)[0], 0.f);
         }
+#else
+        // the same, with the dependent loads of the candidates side by side: lane i fetches candidate i (dense id, edge
+        // descriptor, first-turn values), the warp then walks each candidate's edges 32 at a time
+        {
+            u32 my_vid = 0, my_eb = 0;
+            int my_ne = 0;
+            float my_t0 = 0.f, my_w0 = 0.f, my_e0 = 0.f;
+            if (s.lane < n_cands) {
+                my_vid = sp_vid(s.G, (u32)cands[s.lane].node);
+                const u64 ni = s.G.einfo[my_vid];
+                my_ne = sp_einfo_n(ni); my_eb = sp_einfo_begin(ni);
+                my_t0 = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s.G, my_vid, 0)[0]);
+                my_w0 = clamp01(sp_vals(s.G, my_vid, 1)[0]);
+                my_e0 = fmaxf(sp_vals(s.G, my_vid, 2)[0], 0.f);
+            }
+            for (int i = 0; i < n_cands; i++) {
+                SpCand& cd = cands[i];
+                cd.vid = __shfl_sync(0xffffffffu, my_vid, i);
+                const int ne = __shfl_sync(0xffffffffu, my_ne, i);
+                const u32 eb = __shfl_sync(0xffffffffu, my_eb, i);
+                cd.t0 = __shfl_sync(0xffffffffu, my_t0, i);
+                cd.w0 = __shfl_sync(0xffffffffu, my_w0, i);
+                cd.e0 = __shfl_sync(0xffffffffu, my_e0, i);
+                u32 lo = 0, hi = 0, num = 0;
+                for (int q = s.lane; q < ne; q += 32) {
+                    const u16 m = s.G.emeta[eb + q];
+                    const int t = deaka(m & 63);
+                    if (t < 32) lo |= 1u << t; else hi |= 1u << (t - 32);
+                    num += (m >> 6) & 7;
+                }
+                lo = __reduce_or_sync(0xffffffffu, lo); hi = __reduce_or_sync(0xffffffffu, hi);
+                num = __reduce_add_sync(0xffffffffu, num);
+                cd.required = (u64)lo | ((u64)hi << 32);
+                cd.num_required = (int)(num & 0xFF);
+            }
+        }
+#endif
     }
     if (n_cands == 0) return;
     // `max_ev_table` is sorted descending (stable); index 0 = the maximum under the comparator
@@ -1115,6 +1153,35 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
     for (int q = 0; q < n_emit; q++) {
         const SpCand& cd = cd_flag ? cands[q] : cands[first];
         const u32 vid = cd.vid;
+#ifndef MJX_HOST_EMUL
+        {   // lane = turn: the T <= 17 turns of a candidate are fetched side by side; take_while(p > 0) is a ballot
+            const int turn = s.lane;
+            float tp = 0.f, wp = 0.f, ev = 0.f;
+            if (turn < T) {
+                tp = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s.G, vid, 0)[turn]);
+                wp = clamp01(sp_vals(s.G, vid, 1)[turn]);
+                ev = fminf(SP_FMUL(fmaxf(sp_vals(s.G, vid, 2)[turn], 0.f), ev_scale), 1.f);
+            }
+            const unsigned stop = __ballot_sync(0xffffffffu, !(turn < T && tp > 0.f));  // never 0: T < 32
+            const int n_turns = __ffs(stop) - 1;
+            if (cd_flag) {
+                if (turn < n_turns) {
+                    const int tid = deaka(cd.tile);
+                    obs_row[(961 + turn) * 34 + tid] = tp;
+                    obs_row[(961 + SP_T_MAX + turn) * 34 + tid] = wp;
+                    obs_row[(961 + 2 * SP_T_MAX + turn) * 34 + tid] = ev;
+                }
+            } else {
+                for (int t = 0; t < n_turns; t++) {
+                    const float a = __shfl_sync(0xffffffffu, tp, t), b = __shfl_sync(0xffffffffu, wp, t), c2 = __shfl_sync(0xffffffffu, ev, t);
+                    SPO_FILL(961 + t, a);
+                    SPO_FILL(961 + SP_T_MAX + t, b);
+                    SPO_FILL(961 + 2 * SP_T_MAX + t, c2);
+                }
+            }
+            continue;
+        }
+#endif
         for (int turn = 0; turn < T; turn++) {
             const float tp = cur_shanten == 0 ? 1.f : clamp01(sp_vals(s.G, vid, 0)[turn]);
             if (!(tp > 0.f)) break;
