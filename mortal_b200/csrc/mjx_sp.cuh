@@ -1030,6 +1030,66 @@ MJX_DN void sp_stage_finalize(SpCtx& s, int row, float* obs_row) {
         // calc.rs:281-314 analyze_*_simple
         if (can_discard) {
             const HandSig base = hand_sig(R.root_key.tehai);
+#ifndef MJX_HOST_EMUL
+            // Device form of the loop below (same results): the <= 14 discards are independent, so lane i first takes discard i
+            // (hand signature and shanten after it), then the (discard, drawn tile) pairs are spread over the lanes 32 at a time --
+            // 15 rounds of table gathers instead of 14 x (1 + 1 + 2) dependent ones, which were the kernel's long pole.
+            {
+                u64 held = 0;
+                for (int t = 0; t < 34; t++) if (R.root_key.tehai[t]) held |= 1ull << t;
+                const int nk = min(mjx_popcll(held), 14);
+                // lane i: its discard
+                int my_t = 0, my_after = 0;
+                HandSig my_sig = base;
+                if (s.lane < nk) {
+                    u64 m = held;
+                    for (int q = 0; q < s.lane; q++) m &= m - 1;
+                    my_t = mjx_ffsll(m) - 1;
+                    my_sig = sig_variant(base, my_t, -1, R.root_key.tehai[my_t]);
+                    my_after = shanten_all_sig(s.T, my_sig, len);
+                }
+                u64 my_req = 0;
+                const int n_items = nk * 34;
+                for (int b0 = 0; b0 < n_items; b0 += 32) {
+                    const int item = b0 + s.lane;
+                    const int ci = min(item / 34, nk - 1), u = item - (item / 34) * 34;
+                    HandSig g;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) g.idx[q] = __shfl_sync(0xffffffffu, my_sig.idx[q], ci);
+                    g.kinds = __shfl_sync(0xffffffffu, my_sig.kinds, ci); g.pairs = __shfl_sync(0xffffffffu, my_sig.pairs, ci);
+                    g.kkinds = __shfl_sync(0xffffffffu, my_sig.kkinds, ci); g.kpairs = __shfl_sync(0xffffffffu, my_sig.kpairs, ci);
+                    const int ct = __shfl_sync(0xffffffffu, my_t, ci), cafter = __shfl_sync(0xffffffffu, my_after, ci);
+                    bool ok = false;
+                    if (item < n_items && R.root_key.wall[u] > 0) {
+                        const int cnt = (int)R.root_key.tehai[u] - (u == ct ? 1 : 0);  // copies of u held after the discard
+                        ok = shanten_all_sig(s.T, sig_variant(g, u, +1, cnt), len) < cafter;
+                    }
+                    const unsigned bits = __ballot_sync(0xffffffffu, ok);  // bit l <-> item b0 + l
+                    // lane i keeps the part of this round that belongs to its discard: items [34 i, 34 i + 34)
+                    const int lo = max(34 * s.lane, b0), hi = min(34 * s.lane + 34, b0 + 32);
+                    if (s.lane < nk && lo < hi) {
+                        const unsigned part = (bits >> (lo - b0)) & (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u));
+                        my_req |= (u64)part << (lo - 34 * s.lane);
+                    }
+                }
+                int my_num = 0;
+                for (u64 rest = my_req; rest; rest &= rest - 1) my_num += R.root_key.wall[mjx_ffsll(rest) - 1];
+                for (int i = 0; i < nk; i++) {
+                    SpCand& cd = cands[n_cands++];
+                    const int t = __shfl_sync(0xffffffffu, my_t, i);
+                    const int after = __shfl_sync(0xffffffffu, my_after, i);
+                    const int k5 = (t == T_5M || t == T_5P || t == T_5S) ? t / 9 : -1;
+                    cd.tile = (k5 >= 0 && ((R.root_key.akas >> k5) & 1) && R.root_key.tehai[t] == 1) ? T_5MR + k5 : t;
+                    cd.node = -1;
+                    cd.shanten_down = after - cur_shanten == 1;
+                    cd.t0 = cd.w0 = cd.e0 = 0.f;
+                    const u32 rlo = __shfl_sync(0xffffffffu, (u32)my_req, i), rhi = __shfl_sync(0xffffffffu, (u32)(my_req >> 32), i);
+                    cd.required = (u64)rlo | ((u64)rhi << 32);
+                    cd.num_required = __shfl_sync(0xffffffffu, my_num, i) & 0xFF;
+                }
+            }
+            if (false)
+#endif
             for (int t = 0; t < 34; t++) {
                 if (R.root_key.tehai[t] == 0) continue;
                 u8 th[34];

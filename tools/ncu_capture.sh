@@ -5,7 +5,7 @@
 set -e
 k=$1; sk=$2; nm=$3
 rep=/tmp/$nm.ncu-rep
-ncu --set full --clock-control none --import-source on -k regex:$k -s $sk -c 1 -o /tmp/$nm python tools/profile_env.py --cycles 4 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:$k" -s $sk -c 1 -o /tmp/$nm python tools/profile_env.py --cycles 4 > /dev/null 2>&1
 ncu -i $rep --page raw --csv > gpurun_out/$nm.raw.csv 2>/dev/null
 ncu -i $rep --page source --csv --print-source cuda,sass 2>/dev/null | python tools/ncu_lines.py 25 > gpurun_out/$nm.lines.txt
 rm -f $rep

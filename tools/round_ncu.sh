@@ -10,10 +10,11 @@ rm -f gpurun_out/*.ncu-rep
 timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${tag}_traffic.csv python tools/profile_env.py --cycles 5 > /dev/null 2>&1
 echo "traffic rc=$?"
-# k_sp_eval<1>: 6 launches per cycle (levels W1, W2, W3 of lane 0, then of lane 1); the 3rd cycle's W1 of lane 0 = skip 12
-timeout 200 bash tools/ncu_capture.sh "k_sp_eval<1>" 12 ${tag}_k_sp_eval_W1; echo "eval rc=$?"
-# k_sp_expand<1>: 6 per cycle (W3, W2, W1 of lane 0, then lane 1); the 3rd cycle's W1 of lane 0 = skip 14
-timeout 200 bash tools/ncu_capture.sh "k_sp_expand<1>" 14 ${tag}_k_sp_expand_W1; echo "expand rc=$?"
+# ncu matches the function name without template arguments. k_sp_eval: 8 launches per lane and cycle (levels 7..0: W0, D0, W1, ...),
+# 16 per cycle; the W1 level of lane 0 in the 3rd cycle = skip 2 * 16 + 2
+timeout 200 bash tools/ncu_capture.sh k_sp_eval 34 ${tag}_k_sp_eval_W1; echo "eval rc=$?"
+# k_sp_expand: 8 per lane and cycle (levels 0..7: D3, W3, D2, W2, D1, W1, D0, W0); W1 of lane 0 in the 3rd cycle = skip 2 * 16 + 5
+timeout 200 bash tools/ncu_capture.sh k_sp_expand 37 ${tag}_k_sp_expand_W1; echo "expand rc=$?"
 timeout 200 bash tools/ncu_capture.sh "k_encode_store" 2 ${tag}_k_encode_store; echo "store rc=$?"
 timeout 200 bash tools/ncu_capture.sh "k_sp_finalize" 4 ${tag}_k_sp_finalize; echo "finalize rc=$?"
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_net_launches.csv \
