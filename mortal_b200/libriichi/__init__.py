@@ -7,7 +7,12 @@ this package as `libriichi` (and `libriichi.<sub>`) in sys.modules the way the r
 """
 import sys
 
-from . import arena, consts, dataset, mjai, stat, state  # noqa: F401
+from .. import dataset, stat  # GameplayLoader / Grp (dataset/gameplay.rs, dataset/grp.rs) and Stat (stat.rs): the modules themselves
+from . import arena, consts, mjai, state  # noqa: F401
+
+# `mortal_b200.libriichi.dataset` / `.stat` are the implementation modules under their libriichi names (no re-export shims)
+sys.modules.setdefault(__name__ + ".dataset", dataset)
+sys.modules.setdefault(__name__ + ".stat", stat)
 
 __profile__ = "release"
 __version__ = "0.1.0-mortal_b200"
