@@ -103,3 +103,129 @@ def test_installed_agari_table_is_the_generated_one(agari_table):
 
     with open(os.path.join(ROOT, "mortal_b200", "data", "agari.bin"), "rb") as f:
         assert f.read() == g.serialize(agari_table)
+
+
+def _decode_shape(key: int):
+    """inverse of gen_agari_table.shape_key: a kind is a run of r one-bits from its position (count = r // 2 + 1, r odd = the
+    block ends here), the next kind starts r + 1 bits further"""
+    blocks, cur, b, top = [], [], 0, key.bit_length()
+    while b < top:
+        r = 0
+        while (key >> (b + r)) & 1:
+            r += 1
+        cur.append(r // 2 + 1)
+        if r & 1:
+            blocks.append(cur)
+            cur = []
+        b += r + 1
+    assert not cur
+    return blocks
+
+
+def test_agari_table_every_split_rebuilds_its_shape(agari_table):
+    """Reference-independent: the key decodes to a shape of 3n+2 tiles, and pair + triplets + runs of every listed split
+    add up to exactly that shape (runs stay inside one block)."""
+    import gen_agari_table as g
+
+    for key, divs in agari_table.items():
+        blocks = _decode_shape(key)
+        assert g.shape_key(blocks) == key
+        counts = [c for b in blocks for c in b]
+        block_of = [i for i, b in enumerate(blocks) for _ in b]
+        assert sum(counts) in (2, 5, 8, 11, 14) and max(counts) <= 4 and len(counts) <= 14
+        assert len(set(divs)) == len(divs)
+        for d in divs:
+            if d & g.F_CHITOI:
+                assert counts == [2] * 7 and d == g.F_CHITOI
+                continue
+            nk, ns, pair = d & 7, (d >> 3) & 7, (d >> 6) & 15
+            idx = [(d >> (10 + 4 * j)) & 15 for j in range(nk + ns)]
+            rebuilt = [0] * len(counts)
+            rebuilt[pair] += 2
+            for i in idx[:nk]:
+                rebuilt[i] += 3
+            for i in idx[nk:]:
+                assert block_of[i] == block_of[i + 2]
+                for j in range(3):
+                    rebuilt[i + j] += 1
+            assert rebuilt == counts, (hex(key), hex(d))
+            assert 3 * (nk + ns) + 2 == sum(counts)
+
+
+def _hand_blocks(counts34):
+    """the shape of a concrete hand: runs of adjacent kinds inside a suit, every honour its own block (agari.rs:767-838)"""
+    blocks = []
+    for lo, hi in ((0, 9), (9, 18), (18, 27)):
+        run = []
+        for c in list(counts34[lo:hi]) + [0]:
+            if c:
+                run.append(c)
+            elif run:
+                blocks.append(run)
+                run = []
+    blocks += [[c] for c in counts34[27:] if c]
+    return blocks
+
+
+def _splits_into_melds(counts34, need_pair):
+    c = list(counts34)
+
+    def rec(i, pair_left):
+        while i < 34 and c[i] == 0:
+            i += 1
+        if i == 34:
+            return not pair_left
+        ok = False
+        if c[i] >= 3:
+            c[i] -= 3
+            ok = rec(i, pair_left)
+            c[i] += 3
+        if not ok and pair_left and c[i] >= 2:
+            c[i] -= 2
+            ok = rec(i, False)
+            c[i] += 2
+        if not ok and i < 27 and i % 9 <= 6 and c[i + 1] and c[i + 2]:
+            for j in range(3):
+                c[i + j] -= 1
+            ok = rec(i, pair_left)
+            for j in range(3):
+                c[i + j] += 1
+        return ok
+
+    return rec(0, need_pair)
+
+
+def test_agari_table_membership_equals_brute_force_on_random_hands(agari_table):
+    """Completeness, reference-independent: a concrete hand's key is in the table iff the hand splits into melds + pair or is
+    seven distinct pairs (10,000 hands built from random melds and then perturbed, sizes 2..14)."""
+    import gen_agari_table as g
+
+    rng = np.random.default_rng(7)
+    n_win = n_lose = 0
+    for _ in range(10_000):
+        n_melds = int(rng.integers(0, 5))
+        c = [0] * 34
+        for _m in range(n_melds):
+            if rng.random() < 0.4:
+                c[int(rng.integers(0, 34))] += 3
+            else:
+                s0 = int(rng.integers(0, 3)) * 9 + int(rng.integers(0, 7))
+                for j in range(3):
+                    c[s0 + j] += 1
+        c[int(rng.integers(0, 34))] += 2
+        if rng.random() < 0.15 and n_melds == 4:  # some seven-pairs shapes
+            c = [0] * 34
+            for t in rng.choice(34, 7, replace=False):
+                c[int(t)] = 2
+        if rng.random() < 0.5:  # move one tile: usually breaks the hand, sometimes not
+            held = [t for t in range(34) if c[t]]
+            c[held[int(rng.integers(0, len(held)))]] -= 1
+            c[int(rng.integers(0, 34))] += 1
+        if max(c) > 4:
+            continue
+        wins = _splits_into_melds(c, True) or (sum(c) == 14 and sorted(x for x in c if x) == [2] * 7)
+        in_table = g.shape_key(_hand_blocks(c)) in agari_table
+        assert wins == in_table, c
+        n_win += wins
+        n_lose += not wins
+    assert n_win > 2000 and n_lose > 2000
